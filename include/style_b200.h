@@ -1,0 +1,185 @@
+/*
+ * style_b200.h -- C ABI of libstyle_b200.so, the B200 (sm_100a) engine for the per-tile hot path
+ * of crowsonkb/style_transfer.
+ *
+ * The reference has no FFI of its own: its hot path is Python calling pycaffe (C++/CUDA, external)
+ * and SciPy BLAS.  The entry points below are what a binding for that path binds instead; each
+ * cites the reference interface it replaces (file:line in the reference tree).  INTEGRATION.md
+ * shows the ctypes stubs a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every function returns 0 on success and a negative st_status on failure; the message of the
+ *     last failure on the calling thread is returned by st_last_error();
+ *   - "dev" pointers are CUDA device pointers on the context's device, "host" pointers are
+ *     ordinary host memory; all tensors are float32, C-contiguous, single image;
+ *   - images / gradients are [3][h][w] (BGR, mean-subtracted: style_transfer.py:388-393), feature
+ *     maps are [C][hf][wf], Gram matrices are [C][C] with only the LOWER triangle meaningful
+ *     (num_utils.py:53-56, 143-147);
+ *   - the caller owns every buffer it passes; the library owns its context (packed weights,
+ *     activation workspace, copies of the targets).  No pointer is retained after a call returns,
+ *     but work is asynchronous on `stream` (a cudaStream_t; 0 = legacy default stream): buffers
+ *     must stay alive until the stream has been synchronised;
+ *   - calls on one context must be serialised by the caller; contexts are independent.
+ *   - scalars produced on the device (losses) are ACCUMULATED into a caller-provided device
+ *     double so that a whole evaluation needs no host synchronisation.
+ */
+#ifndef STYLE_B200_H
+#define STYLE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define ST_API __attribute__((visibility("default")))
+#else
+#define ST_API
+#endif
+
+typedef struct st_ctx st_ctx;
+typedef void* st_stream;            /* cudaStream_t */
+
+enum st_status {
+  ST_OK = 0,
+  ST_ERR_INVALID = -1,              /* bad argument / unsupported shape */
+  ST_ERR_CUDA = -2,                 /* a CUDA runtime or driver call failed */
+  ST_ERR_STATE = -3,                /* call out of order (e.g. targets not set) */
+  ST_ERR_NOMEM = -4
+};
+
+/* Arithmetic of the convolution / Gram contractions.  Reductions, losses, regularisers and the
+ * optimizers are float32 (double accumulators) in both modes. */
+enum st_precision {
+  ST_PREC_FP32 = 0,                 /* float32 SIMT everywhere: the parity mode                */
+  ST_PREC_BF16 = 1                  /* bf16 operands, fp32 accumulate on tcgen05 tensor cores  */
+};
+
+enum st_layer_kind { ST_CONV3X3 = 0, ST_POOL_MAX = 1, ST_POOL_AVE = 2 };
+
+/* One layer of the deploy graph (vgg19.prototxt:16-60).  Blob 0 is "data"; the top of layers[i]
+ * is blob i+1.  Convolutions are 3x3 / pad 1 / stride 1 followed by an in-place ReLU layer
+ * (vgg19.prototxt:27-32); pools are 2x2 / stride 2, ceil mode. */
+typedef struct {
+  int32_t kind;                     /* st_layer_kind */
+  int32_t bottom;                   /* blob index this layer reads */
+  int32_t cin, cout;                /* channels (pools: cin == cout) */
+} st_layer_desc;
+
+/* Loss terms attached to one blob in eval_sc_grad_tile (style_transfer.py:569-604).  The weights
+ * are the fully-multiplied factors the reference uses:
+ *   content_weight = lw * content_weight[layer]        (:579-580)
+ *   style_weight   = lw * style_weight[layer]          (:591-592; the library divides by n_styles)
+ *   dd_weight      = lw * dd_weight[layer]             (:603-604)
+ * A zero weight together with the matching flag cleared disables the term. */
+typedef struct {
+  int32_t blob;
+  int32_t use_content, use_style, use_dd;
+  float content_weight, style_weight, dd_weight;
+} st_loss_spec;
+
+ST_API const char* st_last_error(void);
+ST_API int st_version(void);
+
+/* ---- context ----------------------------------------------------------------------------
+ * Replaces CaffeModel.__init__ -> caffe.Net(deploy, 1, weights=...) (style_transfer.py:359-376). */
+ST_API int st_create(int device, int precision, int n_layers, const st_layer_desc* layers, st_ctx** out);
+ST_API int st_destroy(st_ctx* ctx);
+/* Weights of conv layer `layer` (index into layers[]): host float32 OIHW [cout][cin][3][3] and
+ * bias [cout] -- the .caffemodel blobs. */
+ST_API int st_set_conv_params(st_ctx* ctx, int layer, const float* w_host, const float* b_host);
+/* Reserve the activation / gradient workspace for tiles up to max_h x max_w (grows if needed;
+ * later calls with smaller tiles reuse it).  Replaces blobs['data'].reshape (:423, :559). */
+ST_API int st_reserve(st_ctx* ctx, int max_h, int max_w);
+ST_API int st_device_info(st_ctx* ctx, int* sm_count, size_t* workspace_bytes);
+
+/* ---- targets: TileWorker SetContentsAndStyles (style_transfer.py:243-254, 309-332) ---------- */
+ST_API int st_clear_targets(st_ctx* ctx);
+/* Appends one StyleData entry / sets its Gram for `blob`: dev f32 [C][C], lower triangle used. */
+ST_API int st_set_style_gram(st_ctx* ctx, int style_index, int blob, const float* gram_dev,
+                      st_stream stream);
+/* ContentData.features[layer] of the WHOLE image: dev f32 [C][hf][wf]. */
+ST_API int st_set_content_features(st_ctx* ctx, int content_index, int blob, const float* feat_dev,
+                            int hf, int wf, st_stream stream);
+
+/* ---- the per-tile operator ------------------------------------------------------------------
+ * CaffeModel.eval_features_tile (style_transfer.py:421-427): forward of one tile; blob_ids[i]'s
+ * (post-ReLU) feature map is written to out_dev[i] as f32 [C][hf][wf].  `out_dev` is a HOST array
+ * of device pointers.  The forward runs to the deepest requested blob (the reference always runs
+ * to pool5; the returned maps are identical). */
+ST_API int st_eval_features_tile(st_ctx* ctx, const float* img_dev, int h, int w, int n_blobs,
+                          const int32_t* blob_ids, float* const* out_dev, st_stream stream);
+
+/* CaffeModel.eval_sc_grad_tile (style_transfer.py:556-612): loss and d(loss)/d(pixels) of one
+ * tile.  `img_dev` is the contiguous tile [3][h][w]; (start_y, start_x) is the tile origin in the
+ * rolled image (`start`, :572); (feat_roll_y, feat_roll_x) is the pixel roll the worker applied to
+ * its content features before the call (req.roll, :234) -- the library indexes the un-rolled
+ * feature maps circularly instead of moving them.  grad_dev receives [3][h][w] with row stride
+ * grad_row_stride and plane stride grad_plane_stride (floats); loss_accum_dev (device double) is
+ * incremented by the tile's loss. */
+ST_API int st_eval_sc_grad_tile(st_ctx* ctx, const float* img_dev, int h, int w, int start_y, int start_x,
+                         int feat_roll_y, int feat_roll_x, int n_specs, const st_loss_spec* specs,
+                         double* loss_accum_dev, float* grad_dev, long grad_plane_stride,
+                         long grad_row_stride, st_stream stream);
+
+/* CaffeModel.eval_sc_grad (style_transfer.py:614-645) for the tiles of ONE rank: the image
+ * [3][H][W] is given un-rolled; the per-iteration roll (roll_y, roll_x pixels, i.e. xy*jitter_scale
+ * of :784-786 with xy[0] -> x, xy[1] -> y) is applied virtually while cutting tiles.  Tiles
+ * rank, rank+world, ... of the row-major tile grid (round-robin of TileWorkerPool.request,
+ * :284-298) are evaluated; the gradient of local tile j is written to
+ * packed_grad_dev[j][3][tile_h_max][tile_w_max].  Pass world=1, rank=0 for all tiles. */
+ST_API int st_eval_sc_grad_tiles(st_ctx* ctx, const float* img_dev, int H, int W, int roll_y, int roll_x,
+                          int tile_size, int rank, int world, int n_specs,
+                          const st_loss_spec* specs, double* loss_accum_dev,
+                          float* packed_grad_dev, st_stream stream);
+/* Geometry of the tile grid used above (style_transfer.py:619-631). */
+ST_API int st_tile_grid(int H, int W, int tile_size, int* ntiles_y, int* ntiles_x, int* tile_h_max,
+                 int* tile_w_max);
+/* Pastes the packed gradient tiles of all ranks ([world][tiles_per_rank][3][thmax][twmax], the
+ * all-gather result) into grad_dev [3][H][W] in the UN-rolled frame (:642 + the roll-back :805). */
+ST_API int st_unpack_grad(const float* packed_all_dev, int H, int W, int roll_y, int roll_x, int tile_size,
+                   int world, float* grad_dev, st_stream stream);
+
+/* ---- Gram of a full feature map (preprocess_images, style_transfer.py:534; num_utils.py:143) -- */
+ST_API int st_gram(st_ctx* ctx, const float* feat_dev, int c, int hw, float* gram_dev, st_stream stream);
+
+/* ---- full-image regularisers: StyleTransfer.eval_loss_and_grad (style_transfer.py:700-736) ----
+ * grad += tv_w * d tv_norm(img/127.5, tv_beta) + p_w * d p_norm((img+mean-127.5)/127.5, p_pow)
+ *         + aux_w * (img - aux)/127.5 ;   loss_accum += the matching loss terms.
+ * Weights already include layer_weights['data'].  TV uses periodic differences, so it is
+ * invariant to the roll; `aux_dev` (may be NULL) is compared at the rolled position, as the
+ * reference compares its rolled image with the un-rolled aux image (:731). */
+ST_API int st_regularizers(const float* img_dev, int H, int W, const float mean[3], float tv_w,
+                    float tv_beta, float p_w, float p_pow, const float* aux_dev, float aux_w,
+                    int roll_y, int roll_x, double* loss_accum_dev, float* grad_dev,
+                    st_stream stream);
+
+/* ---- optimizers (optimizers.py) -------------------------------------------------------------
+ * AdamOptimizer.update :26-42 after opfunc returned `grad`: EWMA moments (state g1,g2,p1 hold the
+ * EWMA .value arrays), in-place parameter step, iterate averaging; avg_out = p1 / p1_corr.
+ * g1_corr/g2_corr/p1_corr = 1 - beta^t (or 1 when bias correction is off). */
+ST_API int st_adam_step(float* params, const float* grad, float* g1, float* g2, float* p1, float* avg_out,
+                 size_t n, float step_size, float b1, float b2, float bp1, float g1_corr,
+                 float g2_corr, float p1_corr, st_stream stream);
+/* LBFGSOptimizer.inv_hv :105-121: two-loop recursion over m (<= 16) curvature pairs.  s_dev/y_dev
+ * are HOST arrays of m device pointers (oldest first), sy_host the stored s.y products; p_dev
+ * receives H*grad.  scratch_dev: >= 64 doubles. */
+ST_API int st_lbfgs_inv_hv(const float* grad_dev, size_t n, int m, const float* const* s_dev,
+                    const float* const* y_dev, const double* sy_host, float* p_dev,
+                    double* scratch_dev, st_stream stream);
+/* BLAS-1 helpers used by LBFGSOptimizer.update/store_curvature_pair :74-103. */
+ST_API int st_dot(const float* x, const float* y, size_t n, double* out_dev, st_stream stream);
+ST_API int st_asum(const float* x, size_t n, double* out_dev, st_stream stream);
+/* y = a*x + b*y elementwise (a, b host scalars). */
+ST_API int st_axpby(float a, const float* x, float b, float* y, size_t n, st_stream stream);
+
+/* Number of kernels this library has launched on the calling process since load (bench.py's
+ * "gpu_launches"). */
+ST_API uint64_t st_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STYLE_B200_H */

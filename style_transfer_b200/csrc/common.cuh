@@ -1,0 +1,147 @@
+// Shared device/host helpers for libstyle_b200 (sm_100a only).
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <string>
+
+namespace st {
+
+constexpr float kEps = 1.1920928955078125e-07f;  // float32 machine epsilon (num_utils.py:14)
+
+// ---- error plumbing -----------------------------------------------------------------------------
+void set_error(const std::string& msg);
+extern std::atomic<uint64_t> g_launches;
+
+#define ST_CUDA(call)                                                                      \
+  do {                                                                                     \
+    cudaError_t e_ = (call);                                                               \
+    if (e_ != cudaSuccess) {                                                               \
+      st::set_error(std::string(#call) + ": " + cudaGetErrorString(e_) + " (" + __FILE__ + \
+                    ":" + std::to_string(__LINE__) + ")");                                 \
+      return ST_ERR_CUDA;                                                                  \
+    }                                                                                      \
+  } while (0)
+
+#define ST_REQUIRE(cond, msg)                      \
+  do {                                             \
+    if (!(cond)) {                                 \
+      st::set_error(std::string("invalid: ") + msg); \
+      return ST_ERR_INVALID;                       \
+    }                                              \
+  } while (0)
+
+// Every kernel launch of the library goes through this so bench.py can report "gpu_launches".
+#define ST_LAUNCH(kernel, grid, block, smem, stream, ...)              \
+  do {                                                                 \
+    kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);        \
+    st::g_launches.fetch_add(1, std::memory_order_relaxed);            \
+    ST_CUDA(cudaGetLastError());                                       \
+  } while (0)
+
+inline int cdiv(long a, long b) { return (int)((a + b - 1) / b); }
+
+// ---- storage-type traits: activations are NHWC in float or bf16 ------------------------------------
+template <typename T> struct Store;
+template <> struct Store<float> {
+  static __device__ __forceinline__ float ld(const float* p) { return *p; }
+  static __device__ __forceinline__ void st(float* p, float v) { *p = v; }
+  static __device__ __forceinline__ float4 ld4(const float* p) {
+    return *reinterpret_cast<const float4*>(p);
+  }
+  static __device__ __forceinline__ void st4(float* p, float4 v) {
+    *reinterpret_cast<float4*>(p) = v;
+  }
+};
+template <> struct Store<__nv_bfloat16> {
+  static __device__ __forceinline__ float ld(const __nv_bfloat16* p) {
+    return __bfloat162float(*p);
+  }
+  static __device__ __forceinline__ void st(__nv_bfloat16* p, float v) {
+    *p = __float2bfloat16_rn(v);
+  }
+  static __device__ __forceinline__ float4 ld4(const __nv_bfloat16* p) {
+    uint2 raw = *reinterpret_cast<const uint2*>(p);
+    __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162*>(&raw.x);
+    __nv_bfloat162 b = *reinterpret_cast<__nv_bfloat162*>(&raw.y);
+    float2 fa = __bfloat1622float2(a), fb = __bfloat1622float2(b);
+    return make_float4(fa.x, fa.y, fb.x, fb.y);
+  }
+  static __device__ __forceinline__ void st4(__nv_bfloat16* p, float4 v) {
+    __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y);
+    __nv_bfloat162 b = __floats2bfloat162_rn(v.z, v.w);
+    uint2 raw;
+    raw.x = *reinterpret_cast<uint32_t*>(&a);
+    raw.y = *reinterpret_cast<uint32_t*>(&b);
+    *reinterpret_cast<uint2*>(p) = raw;
+  }
+};
+
+// ---- deterministic grid reductions ----------------------------------------------------------------
+// Each block reduces K doubles, publishes them, takes a ticket; the last block to arrive sums the
+// per-block partials in index order (fixed grid => bit-reproducible) and returns true on its
+// thread 0 with the totals in `v`.  `partials` must hold gridDim.x*K doubles; `*counter` must be 0
+// on entry and is reset to 0 on exit.  All threads of the block must call it.
+template <int K>
+__device__ __forceinline__ bool grid_reduce(double (&v)[K], double* partials, unsigned* counter) {
+  __shared__ double sh[K][32];
+  __shared__ bool is_last;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = (blockDim.x + 31) >> 5;
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    double x = v[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    if (lane == 0) sh[k][warp] = x;
+  }
+  __syncthreads();
+  if (warp == 0) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      double x = lane < nwarps ? sh[k][lane] : 0.0;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+      if (lane == 0) partials[(size_t)blockIdx.x * K + k] = x;
+    }
+  }
+  if (threadIdx.x == 0) {
+    __threadfence();
+    unsigned ticket = atomicAdd(counter, 1u);
+    is_last = (ticket == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!is_last) return false;
+  __threadfence();
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    double x = 0.0;
+    for (unsigned b = threadIdx.x; b < gridDim.x; b += blockDim.x)
+      x += partials[(size_t)b * K + k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    __syncthreads();
+    if (lane == 0) sh[k][warp] = x;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      double x = 0.0;
+      for (int w = 0; w < nwarps; ++w) x += sh[k][w];
+      v[k] = x;
+    }
+    *counter = 0u;
+    return true;
+  }
+  return false;
+}
+
+__device__ __forceinline__ int wrap(int i, int n) {
+  i %= n;
+  return i < 0 ? i + n : i;
+}
+
+}  // namespace st

@@ -1,0 +1,52 @@
+// tcgen05 / TMA implicit-GEMM 3x3 convolution for bf16 NHWC activations (sm_100a).
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <type_traits>
+
+namespace st {
+
+// bf16 weight matrices of one conv layer, K-major, for both directions:
+//   fwd [cout][9*cin]  : B operand of  out[p][co] = sum_k A[p][k] * Wf[co][k],  k = tap*cin + ci
+//   bwd [cin][9*cout]  : same GEMM with flipped taps and in/out channels exchanged
+struct TcWeights {
+  __nv_bfloat16* fwd = nullptr;
+  __nv_bfloat16* bwd = nullptr;
+  void* map_fwd = nullptr;     // host copies of the CUtensorMap descriptors (128 B each)
+  void* map_bwd = nullptr;
+};
+
+struct TcContext {
+  bool enabled = false;
+  int sm_count = 0;
+  void* encode_fn = nullptr;   // cuTensorMapEncodeTiled, fetched through cudaGetDriverEntryPoint
+};
+
+int tc_init(TcContext& tc, int sm_count);
+void tc_destroy(TcContext& tc);
+int tc_pack_weights(TcContext& tc, TcWeights& w, const float* w_oihw_host, int cin, int cout);
+void tc_free_weights(TcWeights& w);
+
+bool tc_shape_ok(const TcContext& tc, const TcWeights& w, int cin, int cout);
+
+template <typename T>
+inline bool tc_usable(const TcContext& tc, const TcWeights& w, int cin, int cout) {
+  if constexpr (std::is_same<T, __nv_bfloat16>::value) return tc_shape_ok(tc, w, cin, cout);
+  return false;
+}
+
+// out = epilogue(conv3x3(in)) with in [h][w][cin], out [h][w][cout] (bf16 NHWC).
+//   forward : out = max(acc + bias, 0)
+//   backward: out = (mask_act > 0 ? acc : 0) + inj   (either may be null)
+int conv3x3_tc(TcContext& tc, const TcWeights& w, const __nv_bfloat16* in, __nv_bfloat16* out,
+               int h, int wd, int cin, int cout, bool forward, const float* bias,
+               const __nv_bfloat16* mask_act, const __nv_bfloat16* inj, cudaStream_t s);
+inline int conv3x3_tc(TcContext&, const TcWeights&, const float*, float*, int, int, int, int, bool,
+                      const float*, const float*, const float*, cudaStream_t) {
+  return -1;   // never reached: tc_usable<float> is false
+}
+
+}  // namespace st

@@ -1,0 +1,705 @@
+// libstyle_b200 engine: context, per-tile forward/backward plan and the extern "C" entry points
+// declared in include/style_b200.h.  See DESIGN.md for the data layout and the kernel list.
+#include <algorithm>
+#include <cstring>
+#include <map>
+#include <vector>
+
+#include "style_b200.h"
+#include "common.cuh"
+#include "conv_tc.h"
+#include "kernels.h"
+
+namespace st {
+
+static thread_local std::string g_error;
+std::atomic<uint64_t> g_launches{0};
+void set_error(const std::string& msg) { g_error = msg; }
+
+struct LayerRt {
+  int kind, bottom, top, cin, cout;
+  float* w_fwd = nullptr;    // [9][cin][cout]
+  float* w_bwd = nullptr;    // [9][cout][cin] (taps flipped); first layer: [9][cout][4]
+  float* bias = nullptr;
+  TcWeights tc;              // bf16 packs for the tcgen05 path
+  bool has_params = false;
+};
+
+struct BlobRt {
+  int c = 0;
+  int producer = -1;         // layer index, -1 for data
+  int scale = 1;             // 224 // shape[1] of style_transfer.py:415-419
+  bool relu = false;         // conv output (carries an in-place ReLU)
+  void* act = nullptr;
+  size_t act_cap = 0;        // elements
+  void* inj = nullptr;
+  size_t inj_cap = 0;
+};
+
+struct ContentTarget {
+  float* nhwc = nullptr;
+  int hf = 0, wf = 0;
+};
+
+}  // namespace st
+
+using namespace st;
+
+struct st_ctx {
+  int device = 0, precision = 0, sm_count = 0;
+  size_t esize = 4;
+  std::vector<LayerRt> layers;
+  std::vector<BlobRt> blobs;
+  void* gbuf[2] = {nullptr, nullptr};
+  void* sbuf = nullptr;
+  size_t gcap = 0;           // elements of gbuf[i] / sbuf
+  float *gram = nullptr, *delta = nullptr, *part = nullptr;
+  size_t part_floats = 0;
+  double* scalars = nullptr; // 64 device doubles
+  ReduceScratch rs{nullptr, nullptr};
+  std::map<std::pair<int, int>, ContentTarget> contents;   // (content index, blob)
+  std::map<std::pair<int, int>, float*> styles;            // (style index, blob) -> full [C][C]
+  int n_contents = 0, n_styles = 0;
+  size_t workspace_bytes = 0;
+  TcContext tc;
+};
+
+namespace {
+
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = true;
+  explicit DeviceGuard(int dev) {
+    ok = cudaGetDevice(&prev) == cudaSuccess && cudaSetDevice(dev) == cudaSuccess;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+#define ST_GUARD(ctx)                                  \
+  ST_REQUIRE((ctx) != nullptr, "null context");        \
+  DeviceGuard guard_((ctx)->device);                   \
+  if (!guard_.ok) {                                    \
+    set_error("cudaSetDevice failed");                 \
+    return ST_ERR_CUDA;                                \
+  }
+
+int dev_alloc(st_ctx* ctx, void** p, size_t bytes) {
+  ST_CUDA(cudaMalloc(p, bytes));
+  ctx->workspace_bytes += bytes;
+  return ST_OK;
+}
+
+int ensure(st_ctx* ctx, void** p, size_t* cap, size_t elems, size_t esize) {
+  if (*cap >= elems) return ST_OK;
+  if (*p) {
+    ST_CUDA(cudaDeviceSynchronize());
+    ST_CUDA(cudaFree(*p));
+    ctx->workspace_bytes -= *cap * esize;
+    *p = nullptr;
+    *cap = 0;
+  }
+  int rc = dev_alloc(ctx, p, elems * esize);
+  if (rc != ST_OK) return rc;
+  *cap = elems;
+  return ST_OK;
+}
+
+inline int pooled(int n) { return (n + 1) / 2; }
+inline int floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
+
+struct Dims {
+  std::vector<int> h, w;
+};
+
+Dims blob_dims(const st_ctx* ctx, int h, int w) {
+  Dims d;
+  d.h.assign(ctx->blobs.size(), 0);
+  d.w.assign(ctx->blobs.size(), 0);
+  d.h[0] = h, d.w[0] = w;
+  for (const LayerRt& l : ctx->layers) {
+    if (l.kind == ST_CONV3X3)
+      d.h[l.top] = d.h[l.bottom], d.w[l.top] = d.w[l.bottom];
+    else
+      d.h[l.top] = pooled(d.h[l.bottom]), d.w[l.top] = pooled(d.w[l.bottom]);
+  }
+  return d;
+}
+
+int reserve_for(st_ctx* ctx, const Dims& d, int last_layer) {
+  size_t gmax = 0;
+  for (int i = 0; i <= last_layer; ++i) {
+    const int b = ctx->layers[i].top;
+    const size_t n = (size_t)d.h[b] * d.w[b] * ctx->blobs[b].c;
+    int rc = ensure(ctx, &ctx->blobs[b].act, &ctx->blobs[b].act_cap, n, ctx->esize);
+    if (rc != ST_OK) return rc;
+    gmax = std::max(gmax, n);
+  }
+  if (ctx->gcap < gmax) {
+    size_t c0 = ctx->gcap, c1 = ctx->gcap, c2 = ctx->gcap;
+    int rc = ensure(ctx, &ctx->gbuf[0], &c0, gmax, ctx->esize);
+    if (rc == ST_OK) rc = ensure(ctx, &ctx->gbuf[1], &c1, gmax, ctx->esize);
+    if (rc == ST_OK) rc = ensure(ctx, &ctx->sbuf, &c2, gmax, ctx->esize);
+    if (rc != ST_OK) return rc;
+    ctx->gcap = gmax;
+  }
+  return ST_OK;
+}
+
+// ---- forward -------------------------------------------------------------------------------------
+template <typename T>
+int forward(st_ctx* ctx, const ImageView& view, const Dims& d, int last_layer, cudaStream_t s) {
+  for (int i = 0; i <= last_layer; ++i) {
+    const LayerRt& l = ctx->layers[i];
+    const int hb = d.h[l.bottom], wb = d.w[l.bottom];
+    T* out = static_cast<T*>(ctx->blobs[l.top].act);
+    int rc;
+    if (l.kind == ST_CONV3X3) {
+      ST_REQUIRE(l.has_params, "conv layer has no weights (st_set_conv_params)");
+      if (l.bottom == 0) {
+        rc = conv_first_fwd<T>(view, hb, wb, l.w_fwd, l.bias, out, l.cout, s);
+      } else {
+        const T* in = static_cast<const T*>(ctx->blobs[l.bottom].act);
+        if (tc_usable<T>(ctx->tc, l.tc, l.cin, l.cout))
+          rc = conv3x3_tc(ctx->tc, l.tc, in, out, hb, wb, l.cin, l.cout, true, l.bias, nullptr,
+                          nullptr, s);
+        else
+          rc = conv3x3_simt<T>(in, l.w_fwd, l.bias, out, hb, wb, l.cin, l.cout, true, nullptr,
+                               nullptr, s);
+      }
+    } else {
+      rc = pool_fwd<T>(static_cast<const T*>(ctx->blobs[l.bottom].act), out, hb, wb, l.cin,
+                       l.kind == ST_POOL_MAX, s);
+    }
+    if (rc != ST_OK) return rc;
+  }
+  return ST_OK;
+}
+
+// ---- loss terms -> injected gradients ----------------------------------------------------------------
+template <typename T>
+int build_injection(st_ctx* ctx, const st_loss_spec& sp, const Dims& d, int start_y, int start_x,
+                    int froll_y, int froll_x, double* loss_accum, cudaStream_t s) {
+  BlobRt& b = ctx->blobs[sp.blob];
+  const int hf = d.h[sp.blob], wf = d.w[sp.blob], c = b.c;
+  const size_t n = (size_t)hf * wf * c;
+  int rc = ensure(ctx, &b.inj, &b.inj_cap, n, ctx->esize);
+  if (rc != ST_OK) return rc;
+  T* inj = static_cast<T*>(b.inj);
+  const T* f = static_cast<const T*>(b.act);
+  bool accumulate = false;
+  double* stats = ctx->scalars;          // [0..1] content/dd stats, [2] sum|S|
+
+  if (sp.use_content) {
+    ST_REQUIRE(ctx->n_contents > 0, "content layer requested but no content features set");
+    for (int ci = 0; ci < ctx->n_contents; ++ci) {
+      auto it = ctx->contents.find({ci, sp.blob});
+      ST_REQUIRE(it != ctx->contents.end(), "content features missing for a content layer");
+      const ContentTarget& t = it->second;
+      const int s0y = start_y / b.scale, s0x = start_x / b.scale;
+      // the reference slices [s0 : s0 + hf] out of the full map; a short slice is a shape error
+      ST_REQUIRE(s0y + hf <= t.hf && s0x + wf <= t.wf,
+                 "tile feature map does not fit into the content feature map at this offset");
+      const int ty0 = s0y - floordiv(froll_y, b.scale), tx0 = s0x - floordiv(froll_x, b.scale);
+      rc = diff_stats<T>(f, hf, wf, c, t.nhwc, t.hf, t.wf, ty0, tx0, stats, ctx->rs, s);
+      if (rc == ST_OK)
+        rc = diff_inject<T>(f, hf, wf, c, t.nhwc, t.hf, t.wf, ty0, tx0, stats, sp.content_weight,
+                            (double)sp.content_weight, loss_accum, inj, accumulate, s);
+      if (rc != ST_OK) return rc;
+      accumulate = true;
+    }
+  }
+  if (sp.use_style) {
+    ST_REQUIRE(ctx->n_styles > 0, "style layer requested but no style Gram set");
+    ST_REQUIRE((size_t)c * c <= 512 * 512, "style layer wider than 512 channels");
+    for (int si = 0; si < ctx->n_styles; ++si) {
+      auto it = ctx->styles.find({si, sp.blob});
+      ST_REQUIRE(it != ctx->styles.end(), "style Gram missing for a style layer");
+      const double w = (double)sp.style_weight / ctx->n_styles;
+      rc = gram_full<T>(f, hf * wf, c, false, ctx->gram, ctx->part, ctx->part_floats,
+                        ctx->sm_count, s);
+      if (rc == ST_OK) rc = gram_delta(ctx->gram, it->second, ctx->delta, c, w, loss_accum, ctx->rs, s);
+      if (rc == ST_OK)
+        rc = style_grad<T>(f, ctx->delta, static_cast<T*>(ctx->sbuf), hf * wf, c, stats + 2,
+                           ctx->rs, s);
+      if (rc == ST_OK)
+        rc = inject_scaled<T>(inj, static_cast<const T*>(ctx->sbuf), n, (float)w, stats + 2,
+                              accumulate, s);
+      if (rc != ST_OK) return rc;
+      accumulate = true;
+    }
+  }
+  if (sp.use_dd) {
+    rc = diff_stats<T>(f, hf, wf, c, nullptr, 1, 1, 0, 0, stats, ctx->rs, s);
+    if (rc == ST_OK)
+      rc = diff_inject<T>(f, hf, wf, c, nullptr, 1, 1, 0, 0, stats, -sp.dd_weight,
+                          -(double)sp.dd_weight, loss_accum, inj, accumulate, s);
+    if (rc != ST_OK) return rc;
+    accumulate = true;
+  }
+  if (!accumulate) ST_CUDA(cudaMemsetAsync(inj, 0, n * ctx->esize, s));
+  return ST_OK;
+}
+
+// ---- backward chain to the pixels ----------------------------------------------------------------------
+template <typename T>
+int backward(st_ctx* ctx, const Dims& d, int deepest_blob, const std::vector<char>& has_inj,
+             float* grad, long plane, long rstride, cudaStream_t s) {
+  int cur = deepest_blob, pp = 0;
+  const T* g = static_cast<const T*>(ctx->blobs[cur].inj);
+  while (true) {
+    const LayerRt& l = ctx->layers[ctx->blobs[cur].producer];
+    const int b = l.bottom;
+    const int hb = d.h[b], wb = d.w[b];
+    if (l.kind == ST_CONV3X3 && b == 0)
+      return conv_last_bwd<T>(g, hb, wb, l.cout, l.w_bwd, grad, plane, rstride, s);
+    ST_REQUIRE(b != 0, "a pooling layer directly on the image is not supported");
+    const BlobRt& bb = ctx->blobs[b];
+    const T* mask = bb.relu ? static_cast<const T*>(bb.act) : nullptr;
+    const T* inj = has_inj[b] ? static_cast<const T*>(bb.inj) : nullptr;
+    T* out = static_cast<T*>(ctx->gbuf[pp]);
+    int rc;
+    if (l.kind == ST_CONV3X3) {
+      if (tc_usable<T>(ctx->tc, l.tc, l.cout, l.cin))
+        rc = conv3x3_tc(ctx->tc, l.tc, g, out, hb, wb, l.cout, l.cin, false, nullptr, mask, inj, s);
+      else
+        rc = conv3x3_simt<T>(g, l.w_bwd, nullptr, out, hb, wb, l.cout, l.cin, false, mask, inj, s);
+    } else {
+      rc = pool_bwd<T>(g, static_cast<const T*>(bb.act), out, hb, wb, l.cin,
+                       l.kind == ST_POOL_MAX, bb.relu, inj, s);
+    }
+    if (rc != ST_OK) return rc;
+    g = out, pp ^= 1, cur = b;
+  }
+}
+
+template <typename T>
+int eval_tile(st_ctx* ctx, const ImageView& view, int h, int w, int start_y, int start_x,
+              int froll_y, int froll_x, int n_specs, const st_loss_spec* specs, double* loss_accum,
+              float* grad, long plane, long rstride, cudaStream_t s) {
+  ST_REQUIRE(n_specs > 0 && specs != nullptr, "no loss layers");
+  ST_REQUIRE(h > 0 && w > 0, "empty tile");
+  const int nb = (int)ctx->blobs.size();
+  int deepest = -1;
+  std::vector<char> has_inj(nb, 0);
+  for (int i = 0; i < n_specs; ++i) {
+    ST_REQUIRE(specs[i].blob > 0 && specs[i].blob < nb, "loss blob index out of range");
+    ST_REQUIRE(!has_inj[specs[i].blob], "duplicate loss blob");
+    has_inj[specs[i].blob] = 1;
+    deepest = std::max(deepest, specs[i].blob);
+  }
+  // every loss blob must lie on the backward chain of the deepest one
+  {
+    std::vector<char> on_chain(nb, 0);
+    for (int cur = deepest; cur != 0; cur = ctx->layers[ctx->blobs[cur].producer].bottom)
+      on_chain[cur] = 1;
+    for (int i = 0; i < n_specs; ++i)
+      ST_REQUIRE(on_chain[specs[i].blob], "loss blob is not an ancestor of the deepest loss blob");
+  }
+  const int last_layer = ctx->blobs[deepest].producer;
+  const Dims d = blob_dims(ctx, h, w);
+  int rc = reserve_for(ctx, d, last_layer);
+  if (rc == ST_OK) rc = forward<T>(ctx, view, d, last_layer, s);
+  for (int i = 0; i < n_specs && rc == ST_OK; ++i)
+    rc = build_injection<T>(ctx, specs[i], d, start_y, start_x, froll_y, froll_x, loss_accum, s);
+  if (rc == ST_OK) rc = backward<T>(ctx, d, deepest, has_inj, grad, plane, rstride, s);
+  return rc;
+}
+
+int eval_tile_any(st_ctx* ctx, const ImageView& view, int h, int w, int start_y, int start_x,
+                  int froll_y, int froll_x, int n_specs, const st_loss_spec* specs,
+                  double* loss_accum, float* grad, long plane, long rstride, cudaStream_t s) {
+  if (ctx->precision == ST_PREC_FP32)
+    return eval_tile<float>(ctx, view, h, w, start_y, start_x, froll_y, froll_x, n_specs, specs,
+                            loss_accum, grad, plane, rstride, s);
+  return eval_tile<__nv_bfloat16>(ctx, view, h, w, start_y, start_x, froll_y, froll_x, n_specs,
+                                  specs, loss_accum, grad, plane, rstride, s);
+}
+
+struct Grid {
+  int nty, ntx, th, tw, thmax, twmax;
+};
+
+Grid tile_grid(int H, int W, int tile_size) {
+  Grid g;
+  g.nty = (H - 1) / tile_size + 1, g.ntx = (W - 1) / tile_size + 1;
+  g.th = H / g.nty, g.tw = W / g.ntx;
+  g.thmax = H - (g.nty - 1) * g.th, g.twmax = W - (g.ntx - 1) * g.tw;
+  return g;
+}
+
+}  // namespace
+
+// =====================================================================================================
+// extern "C"
+// =====================================================================================================
+extern "C" {
+
+const char* st_last_error(void) { return g_error.c_str(); }
+int st_version(void) { return 100; }
+uint64_t st_launch_count(void) { return g_launches.load(); }
+
+int st_create(int device, int precision, int n_layers, const st_layer_desc* layers, st_ctx** out) {
+  ST_REQUIRE(out != nullptr && layers != nullptr && n_layers > 0, "st_create: bad arguments");
+  ST_REQUIRE(precision == ST_PREC_FP32 || precision == ST_PREC_BF16, "unknown precision");
+  int ndev = 0;
+  ST_CUDA(cudaGetDeviceCount(&ndev));
+  ST_REQUIRE(device >= 0 && device < ndev, "no such CUDA device");
+  cudaDeviceProp prop;
+  ST_CUDA(cudaGetDeviceProperties(&prop, device));
+  ST_REQUIRE(prop.major == 10, "libstyle_b200 is built for sm_100a (B200) only");
+  st_ctx* ctx = new st_ctx();
+  ctx->device = device, ctx->precision = precision, ctx->sm_count = prop.multiProcessorCount;
+  ctx->esize = precision == ST_PREC_FP32 ? 4 : 2;
+  DeviceGuard guard(device);
+  ctx->blobs.resize(n_layers + 1);
+  ctx->blobs[0].c = 3;
+  ctx->layers.resize(n_layers);
+  for (int i = 0; i < n_layers; ++i) {
+    const st_layer_desc& ld = layers[i];
+    LayerRt& l = ctx->layers[i];
+    l.kind = ld.kind, l.bottom = ld.bottom, l.top = i + 1, l.cin = ld.cin, l.cout = ld.cout;
+    bool ok = ld.bottom >= 0 && ld.bottom <= i && ld.cin == ctx->blobs[ld.bottom].c &&
+              (ld.kind == ST_CONV3X3 || ((ld.kind == ST_POOL_MAX || ld.kind == ST_POOL_AVE) &&
+                                         ld.cin == ld.cout));
+    if (ok && ld.kind == ST_CONV3X3)
+      ok = ld.cout % 64 == 0 && (ld.bottom == 0 ? ld.cin == 3 : ld.cin % 64 == 0);
+    if (!ok) {
+      delete ctx;
+      set_error("invalid: layer " + std::to_string(i) + " is malformed or unsupported");
+      return ST_ERR_INVALID;
+    }
+    BlobRt& t = ctx->blobs[l.top];
+    t.c = ld.cout, t.producer = i, t.relu = ld.kind == ST_CONV3X3;
+    t.scale = ctx->blobs[ld.bottom].scale * (ld.kind == ST_CONV3X3 ? 1 : 2);
+  }
+  int rc = dev_alloc(ctx, (void**)&ctx->gram, 512 * 512 * sizeof(float));
+  if (rc == ST_OK) rc = dev_alloc(ctx, (void**)&ctx->delta, 512 * 512 * sizeof(float));
+  ctx->part_floats = (size_t)16 << 20;
+  if (rc == ST_OK) rc = dev_alloc(ctx, (void**)&ctx->part, ctx->part_floats * sizeof(float));
+  if (rc == ST_OK) rc = dev_alloc(ctx, (void**)&ctx->scalars, 64 * sizeof(double));
+  if (rc == ST_OK)
+    rc = dev_alloc(ctx, (void**)&ctx->rs.partials, (size_t)kMaxReduceBlocks * 4 * sizeof(double));
+  if (rc == ST_OK) rc = dev_alloc(ctx, (void**)&ctx->rs.counter, sizeof(unsigned));
+  if (rc == ST_OK && cudaMemset(ctx->rs.counter, 0, sizeof(unsigned)) != cudaSuccess) rc = ST_ERR_CUDA;
+  if (rc == ST_OK && cudaMemset(ctx->scalars, 0, 64 * sizeof(double)) != cudaSuccess) rc = ST_ERR_CUDA;
+  if (rc == ST_OK && precision == ST_PREC_BF16) rc = tc_init(ctx->tc, ctx->sm_count);
+  if (rc != ST_OK) {
+    st_destroy(ctx);
+    return rc;
+  }
+  *out = ctx;
+  return ST_OK;
+}
+
+int st_destroy(st_ctx* ctx) {
+  if (!ctx) return ST_OK;
+  DeviceGuard guard(ctx->device);
+  cudaDeviceSynchronize();
+  for (LayerRt& l : ctx->layers) {
+    cudaFree(l.w_fwd), cudaFree(l.w_bwd), cudaFree(l.bias);
+    tc_free_weights(l.tc);
+  }
+  for (BlobRt& b : ctx->blobs) cudaFree(b.act), cudaFree(b.inj);
+  cudaFree(ctx->gbuf[0]), cudaFree(ctx->gbuf[1]), cudaFree(ctx->sbuf);
+  cudaFree(ctx->gram), cudaFree(ctx->delta), cudaFree(ctx->part), cudaFree(ctx->scalars);
+  cudaFree(ctx->rs.partials), cudaFree(ctx->rs.counter);
+  for (auto& kv : ctx->contents) cudaFree(kv.second.nhwc);
+  for (auto& kv : ctx->styles) cudaFree(kv.second);
+  tc_destroy(ctx->tc);
+  delete ctx;
+  return ST_OK;
+}
+
+int st_set_conv_params(st_ctx* ctx, int layer, const float* w, const float* b) {
+  ST_GUARD(ctx);
+  ST_REQUIRE(layer >= 0 && layer < (int)ctx->layers.size() && w && b, "bad layer / null weights");
+  LayerRt& l = ctx->layers[layer];
+  ST_REQUIRE(l.kind == ST_CONV3X3, "st_set_conv_params on a pooling layer");
+  const int ci_n = l.cin, co_n = l.cout;
+  std::vector<float> fwd((size_t)9 * ci_n * co_n), bwd;
+  const bool first = l.bottom == 0;
+  bwd.assign(first ? (size_t)9 * co_n * 4 : (size_t)9 * co_n * ci_n, 0.f);
+  for (int co = 0; co < co_n; ++co)
+    for (int ci = 0; ci < ci_n; ++ci)
+      for (int ky = 0; ky < 3; ++ky)
+        for (int kx = 0; kx < 3; ++kx) {
+          const float v = w[(((size_t)co * ci_n + ci) * 3 + ky) * 3 + kx];
+          fwd[((size_t)(ky * 3 + kx) * ci_n + ci) * co_n + co] = v;
+          const int tapf = (2 - ky) * 3 + (2 - kx);      // flipped tap for the transposed conv
+          if (first)
+            bwd[((size_t)tapf * co_n + co) * 4 + ci] = v;
+          else
+            bwd[((size_t)tapf * co_n + co) * ci_n + ci] = v;
+        }
+  ST_CUDA(cudaDeviceSynchronize());
+  if (!l.w_fwd) {
+    int rc = dev_alloc(ctx, (void**)&l.w_fwd, fwd.size() * sizeof(float));
+    if (rc == ST_OK) rc = dev_alloc(ctx, (void**)&l.w_bwd, bwd.size() * sizeof(float));
+    if (rc == ST_OK) rc = dev_alloc(ctx, (void**)&l.bias, co_n * sizeof(float));
+    if (rc != ST_OK) return rc;
+  }
+  ST_CUDA(cudaMemcpy(l.w_fwd, fwd.data(), fwd.size() * sizeof(float), cudaMemcpyHostToDevice));
+  ST_CUDA(cudaMemcpy(l.w_bwd, bwd.data(), bwd.size() * sizeof(float), cudaMemcpyHostToDevice));
+  ST_CUDA(cudaMemcpy(l.bias, b, co_n * sizeof(float), cudaMemcpyHostToDevice));
+  if (ctx->precision == ST_PREC_BF16 && !first) {
+    int rc = tc_pack_weights(ctx->tc, l.tc, w, ci_n, co_n);
+    if (rc != ST_OK) return rc;
+  }
+  l.has_params = true;
+  return ST_OK;
+}
+
+int st_reserve(st_ctx* ctx, int max_h, int max_w) {
+  ST_GUARD(ctx);
+  ST_REQUIRE(max_h > 0 && max_w > 0, "st_reserve: empty tile");
+  return reserve_for(ctx, blob_dims(ctx, max_h, max_w), (int)ctx->layers.size() - 1);
+}
+
+int st_device_info(st_ctx* ctx, int* sm_count, size_t* workspace_bytes) {
+  ST_REQUIRE(ctx != nullptr, "null context");
+  if (sm_count) *sm_count = ctx->sm_count;
+  if (workspace_bytes) *workspace_bytes = ctx->workspace_bytes;
+  return ST_OK;
+}
+
+int st_clear_targets(st_ctx* ctx) {
+  ST_GUARD(ctx);
+  ST_CUDA(cudaDeviceSynchronize());
+  for (auto& kv : ctx->contents) {
+    ctx->workspace_bytes -= (size_t)kv.second.hf * kv.second.wf * ctx->blobs[kv.first.second].c * 4;
+    cudaFree(kv.second.nhwc);
+  }
+  for (auto& kv : ctx->styles) {
+    const size_t c = ctx->blobs[kv.first.second].c;
+    ctx->workspace_bytes -= c * c * 4;
+    cudaFree(kv.second);
+  }
+  ctx->contents.clear(), ctx->styles.clear();
+  ctx->n_contents = ctx->n_styles = 0;
+  return ST_OK;
+}
+
+int st_set_style_gram(st_ctx* ctx, int style_index, int blob, const float* gram_dev, st_stream stream) {
+  ST_GUARD(ctx);
+  ST_REQUIRE(style_index >= 0 && blob > 0 && blob < (int)ctx->blobs.size() && gram_dev,
+             "st_set_style_gram: bad arguments");
+  const int c = ctx->blobs[blob].c;
+  float*& full = ctx->styles[{style_index, blob}];
+  if (!full) {
+    int rc = dev_alloc(ctx, (void**)&full, (size_t)c * c * sizeof(float));
+    if (rc != ST_OK) return rc;
+  }
+  ctx->n_styles = std::max(ctx->n_styles, style_index + 1);
+  return symmetrize_lower(gram_dev, full, c, (cudaStream_t)stream);
+}
+
+int st_set_content_features(st_ctx* ctx, int content_index, int blob, const float* feat_dev, int hf,
+                            int wf, st_stream stream) {
+  ST_GUARD(ctx);
+  ST_REQUIRE(content_index >= 0 && blob > 0 && blob < (int)ctx->blobs.size() && feat_dev &&
+                 hf > 0 && wf > 0,
+             "st_set_content_features: bad arguments");
+  const int c = ctx->blobs[blob].c;
+  ContentTarget& t = ctx->contents[{content_index, blob}];
+  if (t.nhwc && (t.hf != hf || t.wf != wf)) {
+    ST_CUDA(cudaDeviceSynchronize());
+    ctx->workspace_bytes -= (size_t)t.hf * t.wf * c * 4;
+    cudaFree(t.nhwc);
+    t.nhwc = nullptr;
+  }
+  if (!t.nhwc) {
+    int rc = dev_alloc(ctx, (void**)&t.nhwc, (size_t)hf * wf * c * sizeof(float));
+    if (rc != ST_OK) return rc;
+  }
+  t.hf = hf, t.wf = wf;
+  ctx->n_contents = std::max(ctx->n_contents, content_index + 1);
+  return nchw_to_nhwc_f32(feat_dev, t.nhwc, hf * wf, c, (cudaStream_t)stream);
+}
+
+int st_eval_features_tile(st_ctx* ctx, const float* img_dev, int h, int w, int n_blobs,
+                          const int32_t* blob_ids, float* const* out_dev, st_stream stream) {
+  ST_GUARD(ctx);
+  ST_REQUIRE(img_dev && h > 0 && w > 0 && n_blobs > 0 && blob_ids && out_dev,
+             "st_eval_features_tile: bad arguments");
+  int deepest = 0;
+  for (int i = 0; i < n_blobs; ++i) {
+    ST_REQUIRE(blob_ids[i] > 0 && blob_ids[i] < (int)ctx->blobs.size(), "blob index out of range");
+    deepest = std::max(deepest, blob_ids[i]);
+  }
+  const int last_layer = ctx->blobs[deepest].producer;
+  const Dims d = blob_dims(ctx, h, w);
+  int rc = reserve_for(ctx, d, last_layer);
+  if (rc != ST_OK) return rc;
+  const ImageView view{img_dev, h, w, 0, 0};
+  cudaStream_t s = (cudaStream_t)stream;
+  rc = ctx->precision == ST_PREC_FP32 ? forward<float>(ctx, view, d, last_layer, s)
+                                      : forward<__nv_bfloat16>(ctx, view, d, last_layer, s);
+  for (int i = 0; i < n_blobs && rc == ST_OK; ++i) {
+    const int b = blob_ids[i];
+    const int hw = d.h[b] * d.w[b];
+    rc = ctx->precision == ST_PREC_FP32
+             ? nhwc_to_nchw_f32<float>((const float*)ctx->blobs[b].act, out_dev[i], hw,
+                                       ctx->blobs[b].c, s)
+             : nhwc_to_nchw_f32<__nv_bfloat16>((const __nv_bfloat16*)ctx->blobs[b].act, out_dev[i],
+                                               hw, ctx->blobs[b].c, s);
+  }
+  return rc;
+}
+
+int st_eval_sc_grad_tile(st_ctx* ctx, const float* img_dev, int h, int w, int start_y, int start_x,
+                         int feat_roll_y, int feat_roll_x, int n_specs, const st_loss_spec* specs,
+                         double* loss_accum_dev, float* grad_dev, long grad_plane_stride,
+                         long grad_row_stride, st_stream stream) {
+  ST_GUARD(ctx);
+  ST_REQUIRE(img_dev && loss_accum_dev && grad_dev, "st_eval_sc_grad_tile: null pointer");
+  ST_REQUIRE(start_y >= 0 && start_x >= 0, "negative tile origin");
+  const ImageView view{img_dev, h, w, 0, 0};
+  return eval_tile_any(ctx, view, h, w, start_y, start_x, feat_roll_y, feat_roll_x, n_specs, specs,
+                       loss_accum_dev, grad_dev, grad_plane_stride, grad_row_stride,
+                       (cudaStream_t)stream);
+}
+
+int st_tile_grid(int H, int W, int tile_size, int* ntiles_y, int* ntiles_x, int* tile_h_max,
+                 int* tile_w_max) {
+  ST_REQUIRE(H > 0 && W > 0 && tile_size > 0, "st_tile_grid: bad arguments");
+  const Grid g = tile_grid(H, W, tile_size);
+  if (ntiles_y) *ntiles_y = g.nty;
+  if (ntiles_x) *ntiles_x = g.ntx;
+  if (tile_h_max) *tile_h_max = g.thmax;
+  if (tile_w_max) *tile_w_max = g.twmax;
+  return ST_OK;
+}
+
+int st_eval_sc_grad_tiles(st_ctx* ctx, const float* img_dev, int H, int W, int roll_y, int roll_x,
+                          int tile_size, int rank, int world, int n_specs,
+                          const st_loss_spec* specs, double* loss_accum_dev,
+                          float* packed_grad_dev, st_stream stream) {
+  ST_GUARD(ctx);
+  ST_REQUIRE(img_dev && loss_accum_dev && packed_grad_dev, "st_eval_sc_grad_tiles: null pointer");
+  ST_REQUIRE(H > 0 && W > 0 && tile_size > 0 && world > 0 && rank >= 0 && rank < world,
+             "st_eval_sc_grad_tiles: bad geometry");
+  const Grid g = tile_grid(H, W, tile_size);
+  const long plane = (long)g.thmax * g.twmax;
+  int slot = 0;
+  for (int t = rank; t < g.nty * g.ntx; t += world, ++slot) {
+    const int ty = t / g.ntx, tx = t % g.ntx;
+    const int sy = ty * g.th, sx = tx * g.tw;
+    const int h = ty == g.nty - 1 ? H - sy : g.th, w = tx == g.ntx - 1 ? W - sx : g.tw;
+    // rolled[y][x] = img[(y - roll_y) mod H][(x - roll_x) mod W]  (np.roll, num_utils.py:136-140)
+    const ImageView view{img_dev, H, W, sy - roll_y, sx - roll_x};
+    int rc = eval_tile_any(ctx, view, h, w, sy, sx, roll_y, roll_x, n_specs, specs, loss_accum_dev,
+                           packed_grad_dev + (size_t)slot * 3 * plane, plane, g.twmax,
+                           (cudaStream_t)stream);
+    if (rc != ST_OK) return rc;
+  }
+  return ST_OK;
+}
+
+int st_unpack_grad(const float* packed_all_dev, int H, int W, int roll_y, int roll_x, int tile_size,
+                   int world, float* grad_dev, st_stream stream) {
+  ST_REQUIRE(packed_all_dev && grad_dev && H > 0 && W > 0 && tile_size > 0 && world > 0,
+             "st_unpack_grad: bad arguments");
+  const Grid g = tile_grid(H, W, tile_size);
+  const int tpr = (g.nty * g.ntx + world - 1) / world;
+  return unpack_grad(packed_all_dev, H, W, roll_y, roll_x, g.nty, g.ntx, g.th, g.tw, g.thmax,
+                     g.twmax, world, tpr, grad_dev, (cudaStream_t)stream);
+}
+
+int st_gram(st_ctx* ctx, const float* feat_dev, int c, int hw, float* gram_dev, st_stream stream) {
+  ST_GUARD(ctx);
+  ST_REQUIRE(feat_dev && gram_dev && c > 0 && c <= 512 && hw > 0, "st_gram: bad arguments");
+  cudaStream_t s = (cudaStream_t)stream;
+  int rc = gram_full<float>(feat_dev, hw, c, true, ctx->gram, ctx->part, ctx->part_floats,
+                            ctx->sm_count, s);
+  if (rc == ST_OK) rc = extract_lower(ctx->gram, gram_dev, c, s);
+  return rc;
+}
+
+// The image-level entry points need reduction scratch but no network context; they keep one small
+// scratch per device, created on first use.
+static ReduceScratch g_scratch[16];
+static int global_scratch(ReduceScratch* out) {
+  int dev = 0;
+  ST_CUDA(cudaGetDevice(&dev));
+  ST_REQUIRE(dev < 16, "device index too large");
+  if (!g_scratch[dev].partials) {
+    ST_CUDA(cudaMalloc((void**)&g_scratch[dev].partials, (size_t)4096 * 4 * sizeof(double)));
+    ST_CUDA(cudaMalloc((void**)&g_scratch[dev].counter, sizeof(unsigned)));
+    ST_CUDA(cudaMemset(g_scratch[dev].counter, 0, sizeof(unsigned)));
+  }
+  *out = g_scratch[dev];
+  return ST_OK;
+}
+
+int st_regularizers(const float* img_dev, int H, int W, const float mean[3], float tv_w,
+                    float tv_beta, float p_w, float p_pow, const float* aux_dev, float aux_w,
+                    int roll_y, int roll_x, double* loss_accum_dev, float* grad_dev,
+                    st_stream stream) {
+  ST_REQUIRE(img_dev && mean && loss_accum_dev && grad_dev && H > 0 && W > 0,
+             "st_regularizers: bad arguments");
+  ReduceScratch rs;
+  int rc = global_scratch(&rs);
+  if (rc != ST_OK) return rc;
+  return regularizers(img_dev, H, W, mean[0], mean[1], mean[2], tv_w, tv_beta, p_w, p_pow, aux_dev,
+                      aux_w, roll_y, roll_x, loss_accum_dev, grad_dev, rs, (cudaStream_t)stream);
+}
+
+int st_adam_step(float* params, const float* grad, float* g1, float* g2, float* p1, float* avg_out,
+                 size_t n, float step_size, float b1, float b2, float bp1, float g1_corr,
+                 float g2_corr, float p1_corr, st_stream stream) {
+  ST_REQUIRE(params && grad && g1 && g2 && p1 && avg_out && n > 0, "st_adam_step: bad arguments");
+  return adam_step(params, grad, g1, g2, p1, avg_out, n, step_size, b1, b2, bp1, g1_corr, g2_corr,
+                   p1_corr, (cudaStream_t)stream);
+}
+
+int st_dot(const float* x, const float* y, size_t n, double* out_dev, st_stream stream) {
+  ST_REQUIRE(x && y && out_dev && n > 0, "st_dot: bad arguments");
+  ReduceScratch rs;
+  int rc = global_scratch(&rs);
+  return rc != ST_OK ? rc : dot_to(x, y, n, out_dev, rs, (cudaStream_t)stream);
+}
+
+int st_asum(const float* x, size_t n, double* out_dev, st_stream stream) {
+  ST_REQUIRE(x && out_dev && n > 0, "st_asum: bad arguments");
+  ReduceScratch rs;
+  int rc = global_scratch(&rs);
+  return rc != ST_OK ? rc : asum_to(x, n, out_dev, rs, (cudaStream_t)stream);
+}
+
+int st_axpby(float a, const float* x, float b, float* y, size_t n, st_stream stream) {
+  ST_REQUIRE(x && y && n > 0, "st_axpby: bad arguments");
+  return axpby(a, x, b, y, n, (cudaStream_t)stream);
+}
+
+int st_lbfgs_inv_hv(const float* grad_dev, size_t n, int m, const float* const* s_dev,
+                    const float* const* y_dev, const double* sy_host, float* p_dev,
+                    double* scratch_dev, st_stream stream) {
+  ST_REQUIRE(grad_dev && p_dev && scratch_dev && n > 0 && m >= 0 && m <= 16,
+             "st_lbfgs_inv_hv: bad arguments");
+  ST_REQUIRE(m == 0 || (s_dev && y_dev && sy_host), "st_lbfgs_inv_hv: missing curvature pairs");
+  cudaStream_t s = (cudaStream_t)stream;
+  ReduceScratch rs;
+  int rc = global_scratch(&rs);
+  if (rc != ST_OK) return rc;
+  ST_CUDA(cudaMemcpyAsync(p_dev, grad_dev, n * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  double* alpha = scratch_dev;            // [0..15]
+  double* tmp = scratch_dev + 16;         // [16], [17]
+  for (int k = m - 1; k >= 0 && rc == ST_OK; --k) {       // optimizers.py:109-111
+    rc = dot_to(s_dev[k], p_dev, n, tmp, rs, s);
+    if (rc == ST_OK) rc = axpy_dev(y_dev[k], p_dev, n, tmp, sy_host[k], nullptr, -1.0, alpha + k, s);
+  }
+  if (m > 0 && rc == ST_OK) {                               // :113-115
+    rc = dot_to(y_dev[m - 1], y_dev[m - 1], n, tmp, rs, s);
+    if (rc == ST_OK) rc = scale_dev(p_dev, n, sy_host[m - 1], tmp, s);
+  }
+  for (int k = 0; k < m && rc == ST_OK; ++k) {              // :117-119
+    rc = dot_to(y_dev[k], p_dev, n, tmp, rs, s);
+    // p += (alpha_k - beta) * s_k,  beta = tmp / sy_k
+    if (rc == ST_OK) rc = axpy_dev(s_dev[k], p_dev, n, tmp, sy_host[k], alpha + k, -1.0, nullptr, s);
+  }
+  return rc;
+}
+
+}  // extern "C"

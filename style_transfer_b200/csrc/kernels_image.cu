@@ -1,0 +1,253 @@
+// Whole-image HBM-bound kernels of libstyle_b200: gradient un-packing (virtual un-roll), the fused
+// TV / p-norm / aux regularisers (style_transfer.py:700-736, num_utils.py:74-82,150-162), the Adam
+// step with iterate averaging (optimizers.py:26-42) and the BLAS-1 pieces of L-BFGS
+// (optimizers.py:74-121).  All float32, coalesced along the image width, reductions in double.
+#include "style_b200.h"
+#include "common.cuh"
+#include "kernels.h"
+
+namespace st {
+
+static inline int ew_grid(size_t work_items, int block) {
+  size_t b = (work_items + block - 1) / block;
+  const size_t cap = 148 * 16;
+  return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+// -----------------------------------------------------------------------------------------------------
+// grad[c][y][x] (un-rolled frame) = packed tile gradient at rolled position ((y+ry) mod H, (x+rx) mod W)
+// -----------------------------------------------------------------------------------------------------
+__global__ void unpack_grad_kernel(const float* __restrict__ packed, int H, int W, int roll_y,
+                                   int roll_x, int nty, int ntx, int th, int tw, int thmax,
+                                   int twmax, int world, int tiles_per_rank,
+                                   float* __restrict__ grad) {
+  const size_t n = (size_t)3 * H * W;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const int x = (int)(i % W);
+    const int y = (int)((i / W) % H);
+    const int c = (int)(i / ((size_t)W * H));
+    const int yr = wrap(y + roll_y, H), xr = wrap(x + roll_x, W);
+    const int ty = min(yr / th, nty - 1), tx = min(xr / tw, ntx - 1);
+    const int t = ty * ntx + tx;
+    const int rank = t % world, slot = t / world;
+    const size_t base = ((size_t)(rank * tiles_per_rank + slot) * 3 + c) * thmax * twmax;
+    grad[i] = packed[base + (size_t)(yr - ty * th) * twmax + (xr - tx * tw)];
+  }
+}
+
+int unpack_grad(const float* packed, int H, int W, int roll_y, int roll_x, int nty, int ntx,
+                int th, int tw, int thmax, int twmax, int world, int tiles_per_rank, float* grad,
+                cudaStream_t s) {
+  ST_LAUNCH(unpack_grad_kernel, ew_grid((size_t)3 * H * W, 256), 256, 0, s, packed, H, W, roll_y,
+            roll_x, nty, ntx, th, tw, thmax, twmax, world, tiles_per_rank, grad);
+  return ST_OK;
+}
+
+// -----------------------------------------------------------------------------------------------------
+// Fused regularisers on the un-rolled image.
+// -----------------------------------------------------------------------------------------------------
+struct TvTerm {
+  float ddx, ddy, pw;   // d/d(dx), d/d(dy) contributions and g2^(beta/2)
+};
+
+__device__ __forceinline__ TvTerm tv_term(float xc, float xr, float xd, float beta) {
+  // xc = X[y][x], xr = X[y][x+1], xd = X[y+1][x]  (already divided by 127.5)
+  const float dx = xc - xr, dy = xc - xd;
+  const float g2 = dx * dx + dy * dy + kEps;
+  TvTerm t;
+  float dg;
+  if (beta == 2.f) {
+    t.pw = g2;
+    dg = 1.f;
+  } else if (beta == 1.f) {
+    t.pw = sqrtf(g2);
+    dg = 0.5f / t.pw;
+  } else {
+    t.pw = powf(g2, 0.5f * beta);
+    dg = 0.5f * beta * powf(g2, 0.5f * beta - 1.f);
+  }
+  t.ddx = 2.f * dx * dg;
+  t.ddy = 2.f * dy * dg;
+  return t;
+}
+
+__global__ void regularizers_kernel(const float* __restrict__ img, int H, int W, float m0, float m1,
+                                    float m2, float tv_w, float tv_beta, float p_w, float p_pow,
+                                    const float* __restrict__ aux, float aux_w, int roll_y,
+                                    int roll_x, double* loss_accum, float* __restrict__ grad,
+                                    ReduceScratch rs) {
+  const size_t n = (size_t)3 * H * W;
+  const float inv = 1.f / 127.5f;
+  double v[1] = {0.0};
+  float part = 0.f;
+  int cnt = 0;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const int x = (int)(i % W);
+    const int y = (int)((i / W) % H);
+    const int c = (int)(i / ((size_t)W * H));
+    const float* pl = img + (size_t)c * H * W;
+    const float raw = pl[(size_t)y * W + x];
+    float g = 0.f, l = 0.f;
+    if (tv_w != 0.f) {
+      const int xp = x + 1 == W ? 0 : x + 1, xm = x == 0 ? W - 1 : x - 1;
+      const int yp = y + 1 == H ? 0 : y + 1, ym = y == 0 ? H - 1 : y - 1;
+      // divisions, not multiplications by 1/127.5: the reference computes img / 127.5
+      const float xc = raw / 127.5f;
+      const TvTerm t0 = tv_term(xc, pl[(size_t)y * W + xp] / 127.5f,
+                                pl[(size_t)yp * W + x] / 127.5f, tv_beta);
+      const float xl = pl[(size_t)y * W + xm] / 127.5f;
+      const TvTerm tl = tv_term(xl, xc, pl[(size_t)yp * W + xm] / 127.5f, tv_beta);
+      const float xu = pl[(size_t)ym * W + x] / 127.5f;
+      const TvTerm tu = tv_term(xu, pl[(size_t)ym * W + xp] / 127.5f, xc, tv_beta);
+      g += tv_w * (t0.ddx + t0.ddy - tl.ddx - tu.ddy);
+      l += tv_w * t0.pw;
+    }
+    if (p_w != 0.f) {
+      const float mean = c == 0 ? m0 : (c == 1 ? m1 : m2);
+      const float a = (raw + mean - 127.5f) / 127.5f;
+      const float mag = fabsf(a), sgn = a > 0.f ? 1.f : (a < 0.f ? -1.f : 0.f);
+      if (p_pow == 1.f) {
+        l += p_w * mag, g += p_w * sgn;
+      } else if (p_pow == 2.f) {
+        l += p_w * a * a, g += p_w * 2.f * a;
+      } else {
+        const float mp1 = powf(mag, p_pow - 1.f);
+        l += p_w * mp1 * mag, g += p_w * p_pow * sgn * mp1;
+      }
+    }
+    if (aux != nullptr) {
+      const int ya = wrap(y + roll_y, H), xa = wrap(x + roll_x, W);
+      const float d = (raw - aux[((size_t)c * H + ya) * W + xa]) * inv;
+      l += aux_w * 0.5f * d * d, g += aux_w * d;
+    }
+    grad[i] += g;
+    part += l;
+    if (++cnt == 32) v[0] += part, part = 0.f, cnt = 0;
+  }
+  v[0] += part;
+  if (grid_reduce<1>(v, rs.partials, rs.counter)) atomicAdd(loss_accum, v[0]);
+}
+
+int regularizers(const float* img, int H, int W, float m0, float m1, float m2, float tv_w,
+                 float tv_beta, float p_w, float p_pow, const float* aux, float aux_w, int roll_y,
+                 int roll_x, double* loss_accum, float* grad, ReduceScratch rs, cudaStream_t s) {
+  ST_LAUNCH(regularizers_kernel, ew_grid((size_t)3 * H * W, 256), 256, 0, s, img, H, W, m0, m1, m2,
+            tv_w, tv_beta, p_w, p_pow, aux, aux_w, roll_y, roll_x, loss_accum, grad, rs);
+  return ST_OK;
+}
+
+// -----------------------------------------------------------------------------------------------------
+// Adam + EWMA iterate averaging.  Operation order (and the absence of FMA contraction) follows the
+// numpy expressions of optimizers.py:35-42 / average.EWMA so that results agree to the last bits.
+// -----------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float ewma(float value, float beta, float omb, float x) {
+  return __fadd_rn(__fmul_rn(value, beta), __fmul_rn(omb, x));
+}
+
+__global__ void adam_kernel(float* __restrict__ params, const float* __restrict__ grad,
+                            float* __restrict__ g1, float* __restrict__ g2, float* __restrict__ p1,
+                            float* __restrict__ avg, size_t n, float neg_step, float b1, float omb1,
+                            float b2, float omb2, float bp1, float ombp1, float g1c, float g2c,
+                            float p1c) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const float g = grad[i];
+    const float m1 = ewma(g1[i], b1, omb1, g);
+    const float m2 = ewma(g2[i], b2, omb2, __fmul_rn(g, g));
+    g1[i] = m1, g2[i] = m2;
+    const float step = __fdiv_rn(__fdiv_rn(m1, g1c), __fadd_rn(__fsqrt_rn(__fdiv_rn(m2, g2c)), kEps));
+    const float p = __fadd_rn(params[i], __fmul_rn(neg_step, step));
+    params[i] = p;
+    const float a = ewma(p1[i], bp1, ombp1, p);
+    p1[i] = a;
+    avg[i] = __fdiv_rn(a, p1c);
+  }
+}
+
+int adam_step(float* params, const float* grad, float* g1, float* g2, float* p1, float* avg_out,
+              size_t n, float step_size, float b1, float b2, float bp1, float g1_corr,
+              float g2_corr, float p1_corr, cudaStream_t s) {
+  // (1 - beta) is formed in double and rounded once, as numpy does for a Python-float scalar.
+  const float omb1 = (float)(1.0 - (double)b1), omb2 = (float)(1.0 - (double)b2);
+  const float ombp1 = (float)(1.0 - (double)bp1);
+  ST_LAUNCH(adam_kernel, ew_grid(n, 256), 256, 0, s, params, grad, g1, g2, p1, avg_out, n,
+            -step_size, b1, omb1, b2, omb2, bp1, ombp1, g1_corr, g2_corr, p1_corr);
+  return ST_OK;
+}
+
+// -----------------------------------------------------------------------------------------------------
+// BLAS-1 on the device for L-BFGS.
+// -----------------------------------------------------------------------------------------------------
+template <bool ABS>
+__global__ void dot_kernel(const float* __restrict__ x, const float* __restrict__ y, size_t n,
+                           double* out, ReduceScratch rs) {
+  double v[1] = {0.0};
+  float part = 0.f;
+  int cnt = 0;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
+       i += (size_t)gridDim.x * blockDim.x) {
+    part += ABS ? fabsf(x[i]) : x[i] * y[i];
+    if (++cnt == 32) v[0] += part, part = 0.f, cnt = 0;
+  }
+  v[0] += part;
+  if (grid_reduce<1>(v, rs.partials, rs.counter)) *out = v[0];
+}
+
+int dot_to(const float* x, const float* y, size_t n, double* out, ReduceScratch rs,
+           cudaStream_t s) {
+  auto k = dot_kernel<false>;
+  ST_LAUNCH(k, ew_grid(n, 256), 256, 0, s, x, y, n, out, rs);
+  return ST_OK;
+}
+
+int asum_to(const float* x, size_t n, double* out, ReduceScratch rs, cudaStream_t s) {
+  auto k = dot_kernel<true>;
+  ST_LAUNCH(k, ew_grid(n, 256), 256, 0, s, x, x, n, out, rs);
+  return ST_OK;
+}
+
+__global__ void axpby_kernel(float a, const float* __restrict__ x, float b, float* __restrict__ y,
+                             size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
+       i += (size_t)gridDim.x * blockDim.x)
+    y[i] = b == 0.f ? a * x[i] : a * x[i] + b * y[i];
+}
+
+int axpby(float a, const float* x, float b, float* y, size_t n, cudaStream_t s) {
+  ST_LAUNCH(axpby_kernel, ew_grid(n, 256), 256, 0, s, a, x, b, y, n);
+  return ST_OK;
+}
+
+__global__ void axpy_dev_kernel(const float* __restrict__ x, float* __restrict__ y, size_t n,
+                                const double* __restrict__ num, double den,
+                                const double* __restrict__ sub, double sign, double* store) {
+  const double first = num[0] / den;
+  const float coef = (float)(sign * (sub ? first - sub[0] : first));
+  if (store && blockIdx.x == 0 && threadIdx.x == 0) *store = first;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
+       i += (size_t)gridDim.x * blockDim.x)
+    y[i] += coef * x[i];
+}
+
+int axpy_dev(const float* x, float* y, size_t n, const double* num, double den, const double* sub,
+             double sign, double* store, cudaStream_t s) {
+  ST_LAUNCH(axpy_dev_kernel, ew_grid(n, 256), 256, 0, s, x, y, n, num, den, sub, sign, store);
+  return ST_OK;
+}
+
+__global__ void scale_dev_kernel(float* __restrict__ y, size_t n, double num,
+                                 const double* __restrict__ den) {
+  const float coef = (float)(num / den[0]);
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
+       i += (size_t)gridDim.x * blockDim.x)
+    y[i] *= coef;
+}
+
+int scale_dev(float* y, size_t n, double num, const double* den, cudaStream_t s) {
+  ST_LAUNCH(scale_dev_kernel, ew_grid(n, 256), 256, 0, s, y, n, num, den);
+  return ST_OK;
+}
+
+}  // namespace st

@@ -1,0 +1,344 @@
+"""Host-side mirror of the reference's ``CaffeModel`` operator interface on top of libstyle_b200.
+
+Same method names, argument meaning and error behaviour as style_transfer.py:356-661, with three
+deliberate differences that the B200 design needs:
+
+* tensors live in HBM (torch CUDA tensors are used purely as storage; host numpy arrays are
+  accepted everywhere and copied through pinned memory);
+* the per-iteration roll (:647-661, :784-786) is *virtual*: ``roll()`` only records the offset and
+  the kernels index the un-rolled image / feature maps circularly, so no data moves;
+* tiles are evaluated by this rank's GPU in round-robin order (tile i -> rank i % world, as
+  ``TileWorkerPool.request`` :284-298 does with worker processes) and the gradient tiles are
+  exchanged with one all-gather instead of queues + shared memory.
+
+There is no CPU fallback: constructing a TileEngine without CUDA or without the built library
+raises.
+"""
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from .netdesc import NetDesc
+
+PRECISIONS = {'fp32': _lib.ST_PREC_FP32, 'bf16': _lib.ST_PREC_BF16}
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class ContentData:
+    """``ContentData`` message (style_transfer.py:165): features[layer] = f32[C,Hf,Wf]."""
+
+    def __init__(self, features):
+        self.features = features
+
+
+class StyleData:
+    """``StyleData`` message (style_transfer.py:166): grams[layer] = f32[C,C], lower triangle."""
+
+    def __init__(self, grams):
+        self.grams = grams
+
+
+class TileEngine:
+    def __init__(self, net, weights, mean=(0, 0, 0), device=0, precision='fp32', rank=0, world=1,
+                 group=None):
+        if not torch.cuda.is_available():
+            raise _lib.StError('TileEngine needs a CUDA device (sm_100a); there is no CPU path')
+        if not isinstance(net, NetDesc):
+            raise TypeError('net must be a NetDesc')
+        self.lib = _lib.load()
+        self.net = net
+        self.device = torch.device('cuda', device)
+        self.precision = precision
+        self.rank, self.world, self.group = rank, world, group
+        self.mean = np.float32(mean).reshape((3, 1, 1))
+        self.bgr = True
+        self.shapes = net.shapes
+        self.last_layer = net.last_layer
+        self.contents, self.styles = [], []
+        self.img = None
+        self.roll_px = np.zeros(2, dtype=np.int64)          # accumulated (x, y) pixel roll
+        ctx = C.c_void_p()
+        _lib.call('st_create', device, PRECISIONS[precision], len(net.layers), net.to_ctypes(),
+                  C.byref(ctx))
+        self.ctx = ctx
+        for i, layer in net.conv_layers():
+            w, b = weights[layer.name]
+            w = np.ascontiguousarray(w, dtype=np.float32)
+            b = np.ascontiguousarray(b, dtype=np.float32)
+            if w.shape != (layer.cout, layer.cin, 3, 3) or b.shape != (layer.cout,):
+                raise ValueError('weights of %s have the wrong shape' % layer.name)
+            _lib.call('st_set_conv_params', ctx, i, w.ctypes.data_as(C.c_void_p),
+                      b.ctypes.data_as(C.c_void_p))
+        self._loss = torch.zeros(1, dtype=torch.float64, device=self.device)
+        self._packed = None
+        self._packed_all = None
+
+    def __del__(self):
+        ctx, self.ctx = getattr(self, 'ctx', None), None
+        if ctx:
+            try:
+                self.lib.st_destroy(ctx)
+            except Exception:       # interpreter shutdown
+                pass
+
+    # ---- helpers ------------------------------------------------------------------------------
+    def to_device(self, arr):
+        """numpy / torch (any device) -> contiguous float32 CUDA tensor."""
+        if isinstance(arr, torch.Tensor):
+            return arr.to(self.device, torch.float32).contiguous()
+        host = torch.from_numpy(np.ascontiguousarray(arr, dtype=np.float32))
+        return host.pin_memory().to(self.device, non_blocking=True)
+
+    def layers(self):
+        return self.net.layer_names()
+
+    def layer_info(self, layer):
+        return self.net.layer_info(layer)
+
+    def pil_to_image(self, img):
+        """RGB HxWx3 array / PIL image -> mean-subtracted BGR f32[3,H,W] (:388-393)."""
+        arr = np.float32(img).transpose((2, 0, 1))
+        if self.bgr:
+            arr = arr[::-1]
+        return np.ascontiguousarray(arr - self.mean)
+
+    def set_image(self, img):
+        self.img = self.to_device(self.pil_to_image(img))
+
+    def get_image_array(self, params=None):
+        """uint8 RGB HxWx3 of the current (or given) parameters (:378-386), on the host."""
+        params = self.img if params is None else params
+        arr = params.detach().cpu().numpy() + self.mean
+        if self.bgr:
+            arr = arr[::-1]
+        return np.uint8(np.clip(arr.transpose((1, 2, 0)), 0, 255))
+
+    def _specs(self, layers, content_layers, style_layers, dd_layers, layer_weights,
+               content_weight, style_weight, dd_weight):
+        arr = (_lib.LossSpec * len(layers))()
+        for i, layer in enumerate(layers):
+            lw = layer_weights[layer]
+            c, s, d = layer in content_layers, layer in style_layers, layer in dd_layers
+            arr[i] = _lib.LossSpec(
+                self.net.blob_index(layer), int(c), int(s), int(d),
+                lw * content_weight[layer] if c else 0.0,
+                lw * style_weight[layer] if s else 0.0,
+                lw * dd_weight[layer] if d else 0.0)
+        return arr
+
+    def ordered_layers(self, *layer_sets):
+        """Deepest-first list of the requested layers (TileWorker, :231-233)."""
+        wanted = set().union(*[set(s) for s in layer_sets])
+        return [l for l in reversed(self.layers()) if l in wanted]
+
+    # ---- feature extraction ------------------------------------------------------------------
+    def eval_features_tile(self, img, layers):
+        """Computes a single tile in a set of feature maps (:421-427)."""
+        img = self.to_device(img)
+        h, w = img.shape[-2:]
+        ids = (C.c_int32 * len(layers))(*[self.net.blob_index(l) for l in layers])
+        outs = {}
+        for layer in layers:
+            hf, wf = self.net.feature_hw(layer, h, w)
+            outs[layer] = torch.empty((self.shapes[layer][0], hf, wf), dtype=torch.float32,
+                                      device=self.device)
+        ptrs = (C.c_void_p * len(layers))(*[outs[l].data_ptr() for l in layers])
+        _lib.call('st_eval_features_tile', self.ctx, _ptr(img), h, w, len(layers), ids, ptrs,
+                  _stream())
+        return outs
+
+    def tile_boxes(self, img_size, tile_size):
+        """[(start(y,x), end(y,x))] row-major (:431-450, :619-631)."""
+        img_size = np.array(img_size)
+        ntiles = (img_size - 1) // tile_size + 1
+        tile = img_size // ntiles
+        boxes = []
+        for y in range(ntiles[0]):
+            for x in range(ntiles[1]):
+                start = np.array([y, x]) * tile
+                end = start + tile
+                if y == ntiles[0] - 1:
+                    end[0] = img_size[0]
+                if x == ntiles[1] - 1:
+                    end[1] = img_size[1]
+                boxes.append((start, end))
+        return boxes
+
+    def rolled_image(self):
+        """The image as the reference would hold it after its physical rolls."""
+        if not self.roll_px.any():
+            return self.img
+        return torch.roll(self.img, (int(self.roll_px[0]), int(self.roll_px[1])), dims=(-1, -2))
+
+    def eval_features_once(self, layers, tile_size=512):
+        """Computes the set of feature maps for the (rolled) image, tile by tile (:429-464)."""
+        img = self.rolled_image()
+        img_size = np.array(img.shape[-2:])
+        features = {}
+        for layer in layers:
+            scale, channels = self.layer_info(layer)
+            shape = (channels,) + tuple(int(v) for v in np.ceil(img_size / scale))
+            features[layer] = torch.zeros(shape, dtype=torch.float32, device=self.device)
+        for start, end in self.tile_boxes(img_size, tile_size):
+            tile = img[:, start[0]:end[0], start[1]:end[1]].contiguous()
+            feats = self.eval_features_tile(tile, layers)
+            for layer, feat in feats.items():
+                scale, _ = self.layer_info(layer)
+                s = start // scale
+                e = s + np.array(feat.shape[-2:])
+                features[layer][:, s[0]:e[0], s[1]:e[1]] = feat
+        return features
+
+    def prepare_features(self, layers, tile_size=512, passes=10):
+        """Averages feature maps over randomly rolled passes to obscure tiling (:466-486).
+        Draws from the global numpy RNG exactly like the reference."""
+        img_size = np.array(self.img.shape[-2:])
+        if max(*img_size) <= tile_size:
+            passes = 1
+        features = {}
+        for i in range(passes):
+            xy = np.array((0, 0))
+            if i > 0:
+                xy = np.int32(np.random.uniform(size=2) * img_size) // 32
+            self.roll(xy)
+            self.roll_features(features, xy)
+            feats = self.eval_features_once(layers, tile_size)
+            for layer in layers:
+                if i == 0:
+                    features[layer] = feats[layer] / passes
+                else:
+                    features[layer] += feats[layer] * np.float32(1 / passes)
+            self.roll(-xy)
+            self.roll_features(features, -xy)
+        return features
+
+    def gram_matrix(self, feat):
+        """``num_utils.gram_matrix`` on the device: lower-triangular f32[C,C]."""
+        feat = self.to_device(feat)
+        c = feat.shape[0]
+        hw = feat[0].numel()
+        out = torch.empty((c, c), dtype=torch.float32, device=self.device)
+        _lib.call('st_gram', self.ctx, _ptr(feat), c, hw, _ptr(out), _stream())
+        return out
+
+    def preprocess_images(self, content_images, style_images, content_layers, style_layers,
+                          tile_size=512):
+        """Style Grams and content features (:488-554; arrays in ``pil_to_image`` format; the
+        ``--style-multiscale`` and ``--jitter`` branches are not part of the hot path)."""
+        saved_img, saved_roll = self.img, self.roll_px.copy()
+        self.roll_px[:] = 0
+        if not self.styles:
+            grams, count = {}, 0
+            for image in style_images:
+                self.img = self.to_device(image)
+                feats = self.prepare_features(style_layers, tile_size, passes=1)
+                for layer in feats:
+                    gram = self.gram_matrix(feats[layer])
+                    grams[layer] = gram if layer not in grams else grams[layer] + gram
+                count += 1
+            for gram in grams.values():
+                gram /= count
+            self.styles.append(StyleData(grams))
+        for image in content_images:
+            self.img = self.to_device(image)
+            feats = self.prepare_features(content_layers, tile_size, passes=10)
+            self.contents.append(ContentData(feats))
+        self.img, self.roll_px = saved_img, saved_roll
+
+    def set_contents_and_styles(self, contents=None, styles=None):
+        """``TileWorkerPool.set_contents_and_styles`` (:309-332): hands the targets to the
+        worker -- here, copies them into the library context of this rank's GPU."""
+        contents = self.contents if contents is None else contents
+        styles = self.styles if styles is None else styles
+        _lib.call('st_clear_targets', self.ctx)
+        for i, content in enumerate(contents):
+            for layer, feat in content.features.items():
+                feat = self.to_device(feat)
+                _lib.call('st_set_content_features', self.ctx, i, self.net.blob_index(layer),
+                          _ptr(feat), feat.shape[1], feat.shape[2], _stream())
+        for i, style in enumerate(styles):
+            for layer, gram in style.grams.items():
+                gram = self.to_device(gram)
+                _lib.call('st_set_style_gram', self.ctx, i, self.net.blob_index(layer), _ptr(gram),
+                          _stream())
+        torch.cuda.current_stream().synchronize()
+
+    # ---- loss + gradient ----------------------------------------------------------------------
+    def eval_sc_grad_tile(self, img, start, layers, content_layers, style_layers, dd_layers,
+                          layer_weights, content_weight, style_weight, dd_weight, roll=(0, 0)):
+        """Evaluates an individual style+content gradient tile (:556-612).  ``roll`` = (x, y) is
+        the pixel roll the worker would have applied to its content features (req.roll, :234).
+        Returns (loss, grad) as a Python float and a CUDA tensor."""
+        img = self.to_device(img)
+        h, w = img.shape[-2:]
+        specs = self._specs(layers, content_layers, style_layers, dd_layers, layer_weights,
+                            content_weight, style_weight, dd_weight)
+        grad = torch.empty_like(img)
+        self._loss.zero_()
+        _lib.call('st_eval_sc_grad_tile', self.ctx, _ptr(img), h, w, int(start[0]), int(start[1]),
+                  int(roll[1]), int(roll[0]), len(layers), specs, _ptr(self._loss), _ptr(grad),
+                  h * w, w, _stream())
+        return float(self._loss.item()), grad
+
+    def eval_sc_grad(self, roll, content_layers, style_layers, dd_layers, layer_weights,
+                     content_weight, style_weight, dd_weight, tile_size, img=None):
+        """Evaluates the summed style and content gradients (:614-645) of ``img`` (default
+        ``self.img``) under the virtual roll ``roll`` = (x, y) pixels.  Returns (loss, grad) as
+        CUDA tensors (float64[1], float32[3,H,W]) in the UN-rolled frame; nothing is synchronised."""
+        img = self.img if img is None else img
+        H, W = img.shape[-2:]
+        rx, ry = int(roll[0]), int(roll[1])
+        layers = self.ordered_layers(content_layers, style_layers, dd_layers)
+        specs = self._specs(layers, content_layers, style_layers, dd_layers, layer_weights,
+                            content_weight, style_weight, dd_weight)
+        nty, ntx, thmax, twmax = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        _lib.call('st_tile_grid', H, W, tile_size, C.byref(nty), C.byref(ntx), C.byref(thmax),
+                  C.byref(twmax))
+        ntiles = nty.value * ntx.value
+        per_rank = (ntiles + self.world - 1) // self.world
+        shape = (per_rank, 3, thmax.value, twmax.value)
+        if self._packed is None or self._packed.shape != shape:
+            self._packed = torch.zeros(shape, dtype=torch.float32, device=self.device)
+            self._packed_all = torch.zeros((self.world,) + shape, dtype=torch.float32,
+                                           device=self.device) if self.world > 1 else None
+        loss = torch.zeros(1, dtype=torch.float64, device=self.device)
+        _lib.call('st_eval_sc_grad_tiles', self.ctx, _ptr(img), H, W, ry, rx, tile_size, self.rank,
+                  self.world, len(layers), specs, _ptr(loss), _ptr(self._packed), _stream())
+        packed_all = self._packed
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_gather_into_tensor(self._packed_all, self._packed, group=self.group)
+            dist.all_reduce(loss, group=self.group)
+            packed_all = self._packed_all
+        grad = torch.empty_like(img)
+        _lib.call('st_unpack_grad', _ptr(packed_all), H, W, ry, rx, tile_size, self.world,
+                  _ptr(grad), _stream())
+        return loss, grad
+
+    # ---- roll -----------------------------------------------------------------------------------
+    def roll_features(self, feats, xy, jitter_scale=32):
+        """Rolls an individual set of feature maps in place (:647-655)."""
+        xy = np.asarray(xy) * jitter_scale
+        for layer, feat in feats.items():
+            scale, _ = self.layer_info(layer)
+            sh = xy // scale
+            if sh.any():
+                feat.copy_(torch.roll(feat, (int(sh[0]), int(sh[1])), dims=(-1, -2)))
+        return feats
+
+    def roll(self, xy, jitter_scale=32):
+        """Rolls the image (:657-661) -- virtually: only the offset is recorded.  (The reference
+        also rolls the master's copy of the content features here, which no worker ever sees.)"""
+        # not reduced modulo the image size: feature rolls are floor(roll / scale), which differs
+        # between congruent rolls when the image size is not a multiple of the layer scale
+        self.roll_px += np.asarray(xy, dtype=np.int64) * jitter_scale

@@ -1,0 +1,145 @@
+"""Device-side mirrors of the reference's optimizers (optimizers.py), same method names.
+
+State lives in HBM as float32 CUDA tensors; one fused kernel performs the Adam/EWMA update
+(st_adam_step), the L-BFGS two-loop recursion runs as a chain of dot/axpy kernels whose scalars
+stay on the device (st_lbfgs_inv_hv).  ``roll`` is virtual: all state stays in the un-rolled
+frame, which is equivalent because every operation here is element-wise or a global dot product.
+"""
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class EWMA:
+    """Restates ``average.EWMA`` bookkeeping (third-party, optimizers.py:22-24); the array update
+    itself happens inside st_adam_step."""
+
+    def __init__(self, like, beta, correct_bias=True):
+        self.beta = float(beta)
+        self.beta_accum = 1.0 if correct_bias else 0.0
+        self.value = torch.zeros_like(like)
+
+    def tick(self):
+        self.beta_accum *= self.beta
+        return np.float32(1 - self.beta_accum)
+
+
+class AdamOptimizer:
+    """Adam with iterate averaging (optimizers.py:11-61)."""
+
+    def __init__(self, params, step_size=1, b1=0.9, b2=0.999, bp1=0, decay=0, power=1,
+                 biased_g1=False):
+        self.params = params
+        self.step_size = step_size
+        self.decay, self.power = decay, power
+        self.i = 1
+        self.xy = np.zeros(2, dtype=np.int32)
+        self.g1 = EWMA(params, b1, correct_bias=not biased_g1)
+        self.g2 = EWMA(params, b2)
+        self.p1 = EWMA(params, bp1)
+        self.avg = torch.empty_like(params)
+
+    def update(self, opfunc):
+        """Returns (averaged iterate, loss); ``opfunc(params) -> (loss, grad)`` on the device."""
+        step_size = self.step_size / self.i ** self.power
+        self.i += self.decay
+        loss, grad = opfunc(self.params)
+        _lib.call('st_adam_step', _ptr(self.params), _ptr(grad), _ptr(self.g1.value),
+                  _ptr(self.g2.value), _ptr(self.p1.value), _ptr(self.avg), self.params.numel(),
+                  step_size, self.g1.beta, self.g2.beta, self.p1.beta, self.g1.tick(),
+                  self.g2.tick(), self.p1.tick(), _stream())
+        return self.avg, loss
+
+    def roll(self, xy):
+        """Virtual: the state stays in the un-rolled frame (see module docstring)."""
+        self.xy += np.asarray(xy, dtype=np.int32)
+
+    def set_params(self, last_iterate, resize=None):
+        """Cross-scale restart (optimizers.py:53-61).  ``resize(tensor, hw, method)`` resamples a
+        state array; ``beta_accum`` is deliberately NOT reset, as in the reference."""
+        self.i = 1
+        self.params = last_iterate
+        hw = tuple(self.params.shape[-2:])
+        if tuple(self.g1.value.shape[-2:]) != hw:
+            if resize is None:
+                raise ValueError('set_params with a new shape needs a resize function')
+            self.g1.value = resize(self.g1.value, hw, 'lanczos')
+            self.g2.value = torch.clamp_min(resize(self.g2.value, hw, 'bilinear'), 0)
+            self.p1.value = resize(self.p1.value, hw, 'lanczos')
+        self.avg = torch.empty_like(self.params)
+
+
+class LBFGSOptimizer:
+    """L-BFGS with fixed size steps, no line search (optimizers.py:64-138)."""
+
+    def __init__(self, params, initial_step=0.1, n_corr=10):
+        self.params = params
+        self.initial_step = initial_step
+        self.n_corr = n_corr
+        self.xy = np.zeros(2, dtype=np.int32)
+        self.loss, self.grad = None, None
+        self.sk, self.yk, self.syk = [], [], []
+        self._scratch = torch.zeros(64, dtype=torch.float64, device=params.device)
+
+    def update(self, opfunc):
+        if self.loss is None:
+            self.loss, self.grad = opfunc(self.params)
+            self.grad = self.grad.clone()
+        n = self.params.numel()
+        s = self.inv_hv(self.grad)                       # s = -H g below
+        if not self.sk:
+            _lib.call('st_asum', _ptr(s), n, _ptr(self._scratch[32:]), _stream())
+            mean_abs = float(self._scratch[32].item()) / n
+            scale = -self.initial_step / mean_abs
+        elif len(self.sk) < self.n_corr:
+            scale = -len(self.sk) / self.n_corr
+        else:
+            scale = -1.0
+        _lib.call('st_axpby', scale, _ptr(s), 0.0, _ptr(s), n, _stream())
+        _lib.call('st_axpby', 1.0, _ptr(s), 1.0, _ptr(self.params), n, _stream())
+        loss, grad = opfunc(self.params)
+        y = grad - self.grad
+        self.store_curvature_pair(s, y)
+        self.loss, self.grad = loss, grad.clone()
+        return self.params, loss
+
+    def store_curvature_pair(self, s, y):
+        _lib.call('st_dot', _ptr(s), _ptr(y), s.numel(), _ptr(self._scratch[33:]), _stream())
+        sy = float(self._scratch[33].item())
+        if sy > 1e-10:
+            self.sk.append(s)
+            self.yk.append(y)
+            self.syk.append(sy)
+        if len(self.sk) > self.n_corr:
+            self.sk, self.yk, self.syk = self.sk[1:], self.yk[1:], self.syk[1:]
+
+    def inv_hv(self, p):
+        """Two-loop recursion on the device; returns H p as a new tensor."""
+        m = len(self.sk)
+        out = torch.empty_like(p)
+        s_ptrs = (C.c_void_p * max(m, 1))(*[t.data_ptr() for t in self.sk])
+        y_ptrs = (C.c_void_p * max(m, 1))(*[t.data_ptr() for t in self.yk])
+        sy = (C.c_double * max(m, 1))(*self.syk)
+        _lib.call('st_lbfgs_inv_hv', _ptr(p), p.numel(), m, s_ptrs, y_ptrs, sy, _ptr(out),
+                  _ptr(self._scratch), _stream())
+        return out
+
+    def roll(self, xy):
+        self.xy += np.asarray(xy, dtype=np.int32)
+
+    def set_params(self, last_iterate, resize=None):
+        self.params = last_iterate
+        self.loss, self.grad = None, None
+        self.sk, self.yk, self.syk = [], [], []

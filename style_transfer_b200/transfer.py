@@ -1,0 +1,153 @@
+"""Objective assembly and the optimisation loop: mirror of the reference's ``StyleTransfer``
+(style_transfer.py:664-909) driving the CUDA tile engine.
+
+The loop structure, the order of draws from the global numpy RNG (``np.random.uniform`` at :889,
+:475 and :784) and the ``//jitter_scale`` quantisation of the roll are kept exactly, because the
+result depends on them.  Per-iteration statistics (:808-817) are computed lazily: only when the
+caller's callback asks for them is anything copied off the device.
+"""
+
+import ctypes as C
+from fractions import Fraction
+
+import numpy as np
+import torch
+
+from . import _lib
+from .optimizers import AdamOptimizer, LBFGSOptimizer
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ffloat(s):
+    """Parses fractional or floating point input strings (config_system.py:27-29)."""
+    return float(Fraction(s))
+
+
+def parse_weights(args, master_weight):
+    """Parses name[:number] pairs into a normalized dict of weights (style_transfer.py:685-698)."""
+    names, weights, total = [], {}, 0
+    for arg in args:
+        name, _, w = arg.partition(':')
+        names.append(name)
+        weights[name] = ffloat(w) if w else 1
+        total += abs(weights[name])
+    return names, {name: weight * master_weight / total for name, weight in weights.items()}
+
+
+def scale_ladder(size, min_size):
+    """Sizes from --size down by sqrt(2) while >= --min-size, smallest first (:840-846, :854)."""
+    sizes = [size]
+    while True:
+        size = round(size / np.sqrt(2))
+        if size < min_size:
+            break
+        sizes.append(size)
+    return list(reversed(sizes))
+
+
+class StyleTransfer:
+    """Performs style transfer on the device.  ``args`` carries the reference's flag names
+    (config_system.py:46-119)."""
+
+    def __init__(self, model, args, layer_weights=None):
+        self.model = model
+        self.args = args
+        self.layer_weights = {layer: 1.0 for layer in model.layers() + ['data']}
+        if layer_weights:
+            self.layer_weights.update(layer_weights)
+        self.aux_image = None            # CUDA f32[3,H,W] in pil_to_image format
+        self.current_raw = None
+        self.optimizer = None
+        self._mean = (C.c_float * 3)(*[float(m) for m in np.ravel(model.mean)])
+
+    # ---- objective ------------------------------------------------------------------------------
+    def eval_loss_and_grad(self, img, sc_grad_args):
+        """Returns the summed loss and gradient (:700-736) as CUDA tensors (float64[1], f32[3,H,W]).
+        ``sc_grad_args`` = (roll_xy_pixels, content_layers, style_layers, dd_layers, layer_weights,
+        content_weight, style_weight, dd_weight, tile_size) as in the reference minus the pool."""
+        a = self.args
+        lw = self.layer_weights['data']
+        loss, grad = self.model.eval_sc_grad(*sc_grad_args, img=img)
+        roll = sc_grad_args[0]
+        tv_w = lw * a.tv_weight if a.tv_weight else 0.0
+        p_w = lw * a.p_weight if a.p_weight else 0.0
+        aux_w = lw * a.aux_weight if self.aux_image is not None else 0.0
+        if tv_w or p_w or self.aux_image is not None:
+            H, W = img.shape[-2:]
+            _lib.call('st_regularizers', _ptr(img), H, W, self._mean, tv_w, a.tv_power, p_w,
+                      a.p_power, _ptr(self.aux_image), aux_w, int(roll[1]), int(roll[0]),
+                      _ptr(loss), _ptr(grad), _stream())
+        return loss, grad
+
+    # ---- first-scale initialisation (:882-901) ---------------------------------------------------
+    def init_first_scale(self, h, w, initial_image=None):
+        a = self.args
+        biased_g1 = initial_image is not None
+        if initial_image is None:
+            initial_image = np.random.uniform(0, 255, size=(h, w, 3))       # RNG draw (:889)
+        self.model.set_image(initial_image)
+        if a.optimizer == 'adam':
+            self.optimizer = AdamOptimizer(
+                self.model.img, step_size=a.step_size, bp1=1 - (1 / a.avg_window),
+                decay=a.step_decay[0], power=a.step_decay[1], biased_g1=biased_g1)
+        elif a.optimizer == 'lbfgs':
+            self.optimizer = LBFGSOptimizer(self.model.img)
+        else:
+            raise ValueError('unknown optimizer %r' % a.optimizer)
+
+    # ---- one scale (:738-830) ---------------------------------------------------------------------
+    def prepare(self, content_images, style_images):
+        """Preprocessing part of ``transfer`` (:748-766): weights, targets, hand-off to the GPU."""
+        a, model = self.args, self.model
+        self.c_layers, self.c_weight = parse_weights(a.content_layers, a.content_weight)
+        self.s_layers, self.s_weight = parse_weights(a.style_layers, 1)
+        self.d_layers, self.d_weight = parse_weights(a.dd_layers, a.dd_weight)
+        model.contents, model.styles = [], []
+        model.preprocess_images(content_images, style_images, self.c_layers, self.s_layers,
+                                a.tile_size)
+        model.set_contents_and_styles()
+        deepest_content = [l for l in reversed(model.layers()) if l in self.c_layers]
+        self.jitter_scale = model.layer_info(deepest_content[0])[0] if deepest_content else 1
+
+    def step(self):
+        """One pass of the loop body (:777-806): draw the roll, update, roll back.  Returns
+        (averaged iterate, loss) on the device."""
+        a, model = self.args, self.model
+        js = self.jitter_scale
+        img_size = np.array(model.img.shape[-2:])
+        xy = np.int32(np.random.uniform(-0.5, 0.5, size=2) * img_size) // js       # (:784)
+        model.roll(xy, jitter_scale=js)
+        self.optimizer.roll(xy * js)
+        sc_args = (xy * js, self.c_layers, self.s_layers, self.d_layers, self.layer_weights,
+                   self.c_weight, self.s_weight, self.d_weight, a.tile_size)
+        avg_img, loss = self.optimizer.update(
+            lambda params: self.eval_loss_and_grad(params, sc_args))
+        model.roll(-xy, jitter_scale=js)
+        self.optimizer.roll(-xy * js)
+        return avg_img, loss
+
+    def transfer(self, iterations, content_images, style_images, callback=None):
+        """Performs style transfer at the current scale; returns the averaged raw iterate."""
+        self.prepare(content_images, style_images)
+        old_img = self.model.img.clone()
+        avg_img = None
+        for step in range(1, iterations + 1):
+            avg_img, loss = self.step()
+            if callback is not None:
+                # statistics of :808-817, evaluated on the device, synchronised here
+                update_size = float((avg_img - old_img).abs().mean())
+                old_img.copy_(avg_img)
+                x_diff = avg_img - torch.roll(avg_img, -1, dims=-1)
+                y_diff = avg_img - torch.roll(avg_img, -1, dims=-2)
+                tv_loss = float(torch.sqrt((x_diff ** 2 + y_diff ** 2).mean()))
+                callback(step=step, update_size=update_size, loss=float(loss), tv_loss=tv_loss,
+                         image=avg_img)
+            self.current_raw = avg_img
+        return avg_img

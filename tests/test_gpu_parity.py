@@ -1,0 +1,301 @@
+"""GPU parity tests: the CUDA engine (through the C ABI) against the CPU oracle on identical
+seeded inputs.  Stated tolerances:
+
+  fp32 mode  : max|d| <= 2e-4 * max|ref| for feature maps and gradients, 1e-4 relative for
+               losses (float32 round-off + different summation order);
+  bf16 mode  : relative L2 error <= 4e-2 for gradients, 2e-2 for losses / features
+               (bf16 operands, fp32 accumulation, activations stored in bf16).
+"""
+
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle.caffe_net import he_normal_weights, model_layers
+from oracle import numeric as on
+from oracle import optimizers as oo
+from oracle.tile_operator import OracleModel
+from oracle.transfer import OracleTransfer, default_args, parse_weights, to_params
+
+pytestmark = pytest.mark.gpu
+
+
+def engine_for(model, precision='fp32', seed=1234, **kw):
+    from style_transfer_b200 import netdesc
+    from style_transfer_b200.engine import TileEngine
+    params = he_normal_weights(model_layers(model), seed=seed)
+    net = netdesc.from_model(model)
+    return TileEngine(net, params, precision=precision, **kw), OracleModel(model, params)
+
+
+def maxrel(a, b):
+    a = a.detach().cpu().numpy() if isinstance(a, torch.Tensor) else np.asarray(a)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+def l2rel(a, b):
+    a = a.detach().cpu().numpy() if isinstance(a, torch.Tensor) else np.asarray(a)
+    return float(np.linalg.norm((a - b).ravel()) / max(np.linalg.norm(b.ravel()), 1e-30))
+
+
+def rand_img(rs, h, w):
+    return to_params(rs.randint(0, 256, (h, w, 3)))
+
+
+@pytest.mark.parametrize('model,hw', [('vgg16.prototxt', (37, 52)), ('vgg19_avgpool.prototxt', (33, 31)),
+                                      ('vgg19_big.prototxt', (24, 40)), ('vgg19.prototxt', (64, 64))])
+def test_features_tile(model, hw):
+    eng, ora = engine_for(model)
+    img = rand_img(np.random.RandomState(0), *hw)
+    layers = ['conv1_1', 'pool1', 'conv2_2', 'conv3_1', 'pool3', 'conv4_2', 'conv5_1', 'pool5']
+    got = eng.eval_features_tile(img, layers)
+    want = ora.features_tile(img, layers)
+    for l in layers:
+        assert got[l].shape == want[l].shape, l
+        assert maxrel(got[l], want[l]) < 2e-4, l
+
+
+def setup_targets(eng, ora, rs, H, W, c_layers, s_layers, n_styles=1, n_contents=1, tile=512):
+    contents = [rand_img(rs, H, W) for _ in range(n_contents)]
+    styles = [rand_img(rs, H, W) for _ in range(n_styles)]
+    # oracle targets (one StyleData per style image here, to exercise n_styles > 1)
+    ora.contents, ora.styles = [], []
+    for s in styles:
+        ora.img = s.copy()
+        feats = ora.prepare_features(s_layers, tile, passes=1)
+        ora.styles.append({l: on.gram_lower(feats[l]) for l in feats})
+    for c in contents:
+        ora.img = c.copy()
+        ora.contents.append(ora.prepare_features(c_layers, tile, passes=1))
+    ora.publish()
+    from style_transfer_b200.engine import ContentData, StyleData
+    eng.set_contents_and_styles([ContentData(c) for c in ora.contents],
+                                [StyleData(g) for g in ora.styles])
+
+
+CASES = [
+    # model, (h, w), content layers, style layers, dd layers, start, roll(x, y)
+    ('vgg16.prototxt', (48, 64), ['conv4_2'], ['conv3_1'], [], (0, 0), (0, 0)),
+    ('vgg19.prototxt', (64, 48), ['conv4_2'], ['conv1_1', 'conv2_1', 'conv3_1', 'conv4_1', 'conv5_1'],
+     [], (0, 0), (0, 0)),
+    ('vgg19.prototxt', (35, 50), ['conv4_2', 'conv2_2'], ['conv1_1', 'pool2', 'conv5_1'], ['conv3_3'],
+     (16, 32), (-24, 40)),
+    ('vgg19_avgpool.prototxt', (41, 33), ['conv3_2'], ['conv2_1', 'conv4_1'], ['conv4_1'], (32, 16),
+     (8, -16)),
+    ('vgg16_big.prototxt', (24, 32), ['conv3_2'], ['conv1_2', 'conv2_1'], [], (0, 0), (0, 0)),
+]
+
+
+@pytest.mark.parametrize('case', CASES, ids=[c[0].split('.')[0] + '-%dx%d' % c[1] for c in CASES])
+@pytest.mark.parametrize('precision', ['fp32', 'bf16'])
+def test_sc_grad_tile(case, precision):
+    model, (h, w), c_layers, s_layers, d_layers, start, roll = case
+    eng, ora = engine_for(model, precision)
+    rs = np.random.RandomState(7)
+    H, W = start[0] + h + 16, start[1] + w + 32
+    setup_targets(eng, ora, rs, H, W, c_layers, s_layers, n_styles=2, n_contents=2)
+    img = rand_img(rs, h, w)
+    lw = {l: 1.0 + 0.1 * i for i, l in enumerate(ora.layers())}
+    _, cw = parse_weights(c_layers, 0.05)
+    _, sw = parse_weights([l + ':%d' % (i + 1) for i, l in enumerate(s_layers)], 1)
+    _, dw = parse_weights(d_layers, 0.3)
+    layers = ora.ordered_layers(c_layers, s_layers, d_layers)
+    ora.roll_features_all(ora.w_contents, np.array(roll), 1)           # worker-side roll (:234)
+    loss_o, grad_o = ora.sc_grad_tile(img, np.array(start), layers, c_layers, s_layers, d_layers,
+                                      lw, cw, sw, dw)
+    loss_g, grad_g = eng.eval_sc_grad_tile(img, start, layers, c_layers, s_layers, d_layers, lw,
+                                           cw, sw, dw, roll=roll)
+    if precision == 'fp32':
+        assert abs(loss_g - loss_o) <= 1e-4 * abs(loss_o), (loss_g, loss_o)
+        assert maxrel(grad_g, grad_o) < 2e-4
+    else:
+        assert abs(loss_g - loss_o) <= 2e-2 * abs(loss_o), (loss_g, loss_o)
+        assert l2rel(grad_g, grad_o) < 4e-2
+
+
+def test_sc_grad_tile_rejects_short_content_slice():
+    from style_transfer_b200 import StError
+    eng, ora = engine_for('vgg16.prototxt')
+    rs = np.random.RandomState(3)
+    setup_targets(eng, ora, rs, 32, 32, ['conv4_2'], ['conv1_1'])
+    lw = {l: 1.0 for l in ora.layers()}
+    with pytest.raises(StError):
+        eng.eval_sc_grad_tile(rand_img(rs, 32, 32), (16, 0), ['conv4_2', 'conv1_1'], ['conv4_2'],
+                              ['conv1_1'], [], lw, {'conv4_2': 1.0}, {'conv1_1': 1.0}, {})
+
+
+@pytest.mark.parametrize('tile,HW,roll', [(32, (64, 96), (24, -16)), (40, (75, 52), (-8, 32)),
+                                          (512, (48, 48), (16, 8))])
+def test_sc_grad_tiled_with_virtual_roll(tile, HW, roll):
+    """eval_sc_grad on the un-rolled image + virtual roll == oracle on the physically rolled image,
+    rolled back (style_transfer.py:784-806)."""
+    eng, ora = engine_for('vgg16.prototxt')
+    rs = np.random.RandomState(11)
+    H, W = HW
+    c_layers, s_layers = ['conv4_2'], ['conv1_1', 'conv3_1']
+    setup_targets(eng, ora, rs, H, W, c_layers, s_layers, tile=tile)
+    img = rand_img(rs, H, W)
+    lw = {l: 1.0 for l in ora.layers()}
+    _, cw = parse_weights(c_layers, 0.05)
+    _, sw = parse_weights(s_layers, 1)
+    roll = np.array(roll)
+    ora.img = on.roll2_(img.copy(), roll)
+    loss_o, grad_o = ora.sc_grad(roll, c_layers, s_layers, [], lw, cw, sw, {}, tile)
+    grad_o = on.roll2_(grad_o.copy(), -roll)
+    eng.img = eng.to_device(img)
+    loss_g, grad_g = eng.eval_sc_grad(roll, c_layers, s_layers, [], lw, cw, sw, {}, tile)
+    assert abs(float(loss_g) - loss_o) <= 1e-4 * abs(loss_o)
+    assert maxrel(grad_g, grad_o) < 2e-4
+
+
+def test_tile_sharding_matches_single_rank():
+    """World-size 2 emulated on one GPU: each 'rank' evaluates its round-robin tiles into its
+    packed buffer; the concatenation (= the all-gather result) unpacks to the 1-rank gradient,
+    bit for bit."""
+    import ctypes as C
+    from style_transfer_b200 import _lib
+    eng, ora = engine_for('vgg16.prototxt')
+    rs = np.random.RandomState(5)
+    H, W, tile = 70, 90, 32
+    c_layers, s_layers = ['conv3_2'], ['conv2_1']
+    setup_targets(eng, ora, rs, H, W, c_layers, s_layers, tile=tile)
+    eng.img = eng.to_device(rand_img(rs, H, W))
+    lw = {l: 1.0 for l in ora.layers()}
+    args = ((8, -16), c_layers, s_layers, [], lw, {'conv3_2': 0.05}, {'conv2_1': 1.0}, {}, tile)
+    loss1, grad1 = eng.eval_sc_grad(*args)
+    grad1 = grad1.clone()
+    packs, losses = [], []
+    for rank in range(2):
+        eng.rank, eng.world, eng._packed = rank, 2, None
+        layers = eng.ordered_layers(c_layers, s_layers)
+        specs = eng._specs(layers, c_layers, s_layers, [], lw, args[5], args[6], {})
+        nty, ntx, thm, twm = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        _lib.call('st_tile_grid', H, W, tile, C.byref(nty), C.byref(ntx), C.byref(thm), C.byref(twm))
+        per_rank = (nty.value * ntx.value + 1) // 2
+        packed = torch.zeros((per_rank, 3, thm.value, twm.value), device='cuda')
+        loss = torch.zeros(1, dtype=torch.float64, device='cuda')
+        _lib.call('st_eval_sc_grad_tiles', eng.ctx, C.c_void_p(eng.img.data_ptr()), H, W, -16, 8,
+                  tile, rank, 2, len(layers), specs, C.c_void_p(loss.data_ptr()),
+                  C.c_void_p(packed.data_ptr()), None)
+        packs.append(packed)
+        losses.append(loss)
+    allp = torch.stack(packs).contiguous()
+    grad2 = torch.empty_like(grad1)
+    _lib.call('st_unpack_grad', C.c_void_p(allp.data_ptr()), H, W, -16, 8, tile, 2,
+              C.c_void_p(grad2.data_ptr()), None)
+    torch.cuda.synchronize()
+    assert torch.equal(grad1, grad2)
+    assert abs(float(losses[0] + losses[1]) - float(loss1)) <= 1e-9 * abs(float(loss1))
+
+
+@pytest.mark.parametrize('beta,p', [(2.0, 6.0), (1.5, 2.0), (1.0, 1.0), (2.0, 3.5)])
+def test_regularizers(beta, p):
+    import ctypes as C
+    from style_transfer_b200 import _lib
+    rs = np.random.RandomState(2)
+    H, W = 37, 53
+    img = rand_img(rs, H, W)
+    aux = rand_img(rs, H, W)
+    mean = np.float32((103.939, 116.779, 123.68)).reshape(3, 1, 1)
+    roll = np.array([5, -9])
+    # oracle in the rolled frame (style_transfer.py:710-733), un-rolled afterwards
+    rimg = on.roll2_(img.copy(), roll)
+    tv_l, tv_g = on.tv_norm(rimg / np.float32(127.5), beta)
+    p_l, p_g = on.p_norm((rimg + mean - np.float32(127.5)) / np.float32(127.5), p)
+    a_g = (rimg - aux) / np.float32(127.5)
+    loss_o = 5.0 * tv_l + 2.0 * p_l + 10.0 * on.norm2(a_g)
+    grad_o = on.roll2_(np.float32(5.0 * tv_g + 2.0 * p_g + 10.0 * a_g), -roll)
+    d_img, d_aux = torch.from_numpy(img).cuda(), torch.from_numpy(aux).cuda()
+    grad = torch.zeros_like(d_img)
+    loss = torch.zeros(1, dtype=torch.float64, device='cuda')
+    _lib.call('st_regularizers', C.c_void_p(d_img.data_ptr()), H, W,
+              (C.c_float * 3)(*mean.ravel().tolist()), 5.0, beta, 2.0, p,
+              C.c_void_p(d_aux.data_ptr()), 10.0, int(roll[1]), int(roll[0]),
+              C.c_void_p(loss.data_ptr()), C.c_void_p(grad.data_ptr()), None)
+    assert abs(float(loss) - loss_o) <= 1e-4 * abs(loss_o)
+    assert maxrel(grad, grad_o) < (2e-4 if beta >= 1.5 else 2e-3)
+
+
+def test_gram_matches_reference_golden(golden_dir):
+    nu = np.load(os.path.join(golden_dir, 'num_utils.npz'))
+    eng, _ = engine_for('vgg16.prototxt')
+    feat = np.zeros((64, 9, 7), np.float32)
+    feat[:12] = nu['nu_feat']
+    got = eng.gram_matrix(feat).cpu().numpy()
+    want = nu['nu_gram'] * (12 / 64)           # 1/feat.size scaling with 64 instead of 12 rows
+    assert np.all(np.triu(got, 1) == 0)
+    assert np.abs(got[:12, :12] - want).max() <= 1e-5 * np.abs(want).max()
+    assert np.all(got[12:] == 0)
+
+
+def _opfunc(target, cum, coupling=0.25):
+    def opfunc(x):
+        tgt = torch.roll(target, (int(cum[0]), int(cum[1])), dims=(-1, -2))
+        # evaluate in the rolled frame like the golden script, return in the un-rolled frame
+        xr = torch.roll(x, (int(cum[0]), int(cum[1])), dims=(-1, -2))
+        d = xr - tgt
+        lap = d + coupling * (torch.roll(d, 1, -1) + torch.roll(d, 1, -2))
+        loss = 0.5 * (lap.double() ** 2).sum().reshape(1)
+        grad = lap + coupling * (torch.roll(lap, -1, -1) + torch.roll(lap, -1, -2))
+        return loss, torch.roll(grad, (-int(cum[0]), -int(cum[1])), dims=(-1, -2)).contiguous()
+    return opfunc
+
+
+@pytest.mark.parametrize('name,biased', [('adam', False), ('adam_biased', True)])
+def test_adam_against_reference_golden(golden_dir, name, biased):
+    from style_transfer_b200.optimizers import AdamOptimizer
+    og = np.load(os.path.join(golden_dir, 'optimizers.npz'))
+    params = torch.from_numpy(og['x0'].copy()).cuda()
+    target = torch.from_numpy(og['target']).cuda()
+    opt = AdamOptimizer(params, step_size=15, bp1=1 - 1 / 20, decay=0.05, power=0.5,
+                        biased_g1=biased)
+    for it in range(8):
+        xy = og['rolls'][it]
+        opt.roll(xy)
+        avg, loss = opt.update(_opfunc(target, xy))
+        opt.roll(-xy)
+        assert maxrel(avg, og[name + '_avg'][it]) < 1e-5
+        assert abs(float(loss) - og[name + '_loss'][it]) <= 1e-5 * og[name + '_loss'][it]
+    assert maxrel(params, og[name + '_params']) < 1e-5
+
+
+def test_lbfgs_against_reference_golden(golden_dir):
+    from style_transfer_b200.optimizers import LBFGSOptimizer
+    og = np.load(os.path.join(golden_dir, 'optimizers.npz'))
+    params = torch.from_numpy(og['x0'].copy()).cuda()
+    target = torch.from_numpy(og['target']).cuda()
+    opt = LBFGSOptimizer(params)
+    for it in range(16):
+        xy = og['rolls'][it]
+        opt.roll(xy)
+        opt.update(_opfunc(target, xy))
+        opt.roll(-xy)
+        assert maxrel(params, og['lbfgs_params'][it]) < (1e-4 if it < 8 else 2e-2), it
+    assert len(opt.sk) == int(og['lbfgs_mem'])
+
+
+@pytest.mark.parametrize('optimizer,iters', [('adam', 6), ('lbfgs', 5)])
+def test_n_iterations_match_oracle(optimizer, iters):
+    """cfg1-shaped path parity: VGG-16, 1 content + 1 style layer, after N iterations.
+    Stated per-pixel tolerance (fp32 mode): max|d| <= 0.05 grey levels for Adam after 6
+    iterations, <= 0.5 for fixed-step L-BFGS after 5 (pixel range 0..255)."""
+    from style_transfer_b200.transfer import StyleTransfer
+    model = 'vgg16.prototxt'
+    eng, ora = engine_for(model, mean=(103.939, 116.779, 123.68))
+    rs = np.random.RandomState(21)
+    H, W = 64, 80
+    content, style = rand_img(rs, H, W), rand_img(rs, H, W)
+    args = default_args(tile_size=48, optimizer=optimizer, content_layers=['conv4_2'],
+                        style_layers=['conv3_1'])
+    ot = OracleTransfer(ora, args)
+    np.random.seed(0)
+    ot.init_first_scale(H, W)
+    want = ot.run(iters, [content], [style]).copy()
+    st = StyleTransfer(eng, args)
+    np.random.seed(0)
+    st.init_first_scale(H, W)
+    got = st.transfer(iters, [content], [style])
+    err = np.abs(got.cpu().numpy() - want).max()
+    assert err <= (0.05 if optimizer == 'adam' else 0.5), err
