@@ -1,0 +1,379 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: optimiser iterations per second of one scale of style transfer.
+
+Workload (BASELINE.json metric, SURVEY section 8d "cfg3"): a 2048x2048 image cut into 4x4 tiles of
+512x512, VGG-19 (random-init He-normal weights), 5 style layers + conv4_2 content layer, TV and
+p-norm regularisers at their default weights, Adam with iterate averaging -- i.e. one pass of the
+loop body of the reference's ``StyleTransfer.transfer`` (style_transfer.py:771-828) per step,
+steady state, preprocessing excluded.  With N GPUs the 16 tiles are dealt round-robin to the ranks
+(tile i -> rank i mod N, TileWorkerPool.request :284-298), the gradient tiles are all-gathered and
+every rank runs the regularisers + optimizer redundantly: total work is fixed ("strong" scaling).
+
+  python bench.py [--gpus N --steps K --warmup W]            this repo's CUDA engine
+  python bench.py --impl reference [...]                      the reference's CPU algorithm (the
+        oracle port: Caffe's im2col+SGEMM forward/backward incl. dW, reference Gram/loss code,
+        reference optimizer) on the host cores, one tile-evaluation per step, scaled to 16 tiles
+
+Rank 0 prints ONE JSON line.
+"""
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = 'style-transfer iterations/sec (VGG-19, 2048px/512-tile)'
+STYLE_LAYERS = ['conv1_1', 'conv2_1', 'conv3_1', 'conv4_1', 'conv5_1']
+CONTENT_LAYERS = ['conv4_2']
+
+# Algorithmic work per 512x512 VGG-19 tile evaluation to conv5_1 (SURVEY 8d / DESIGN.md):
+CONV_GFLOP_PER_TILE = 378.70          # forward 189.35 + backward-data 189.35
+GRAM_GFLOP_PER_TILE = 18.25           # F^T F and dG x F on the five style layers
+
+
+def parse_args():
+    p = argparse.ArgumentParser()
+    p.add_argument('--gpus', type=int, default=1)
+    p.add_argument('--steps', type=int, default=10)
+    p.add_argument('--warmup', type=int, default=3)
+    p.add_argument('--impl', default='engine', choices=['engine', 'reference'])
+    p.add_argument('--precision', default='bf16', choices=['bf16', 'fp32'])
+    p.add_argument('--size', type=int, default=2048)
+    p.add_argument('--tile-size', type=int, default=512)
+    p.add_argument('--optimizer', default='adam', choices=['adam', 'lbfgs'])
+    p.add_argument('--no-cpu-baseline', action='store_true')
+    p.add_argument('--no-e2e', action='store_true')
+    return p.parse_args()
+
+
+def workload_config(a, world):
+    ntiles = ((a.size - 1) // a.tile_size + 1) ** 2
+    return {
+        'workload': 'cfg3: %dx%d image, %d tiles of <=%dpx, vgg19.prototxt, 5 style + 1 content '
+                    'layer, tv+p-norm regularisers, %s' % (a.size, a.size, ntiles, a.tile_size,
+                                                           a.optimizer),
+        'size': a.size, 'tile_size': a.tile_size, 'tiles': ntiles, 'optimizer': a.optimizer,
+        'tiles_per_gpu': -(-ntiles // world), 'parallelism': 'tiles round-robin over %d GPU(s)' % world,
+    }
+
+
+def synthetic_rgb(seed, size):
+    return np.random.RandomState(seed).randint(0, 256, (size, size, 3)).astype(np.uint8)
+
+
+# =======================================================================================================
+# CPU leg: the oracle port of the reference's algorithm (test infrastructure, timed as a baseline)
+# =======================================================================================================
+class CpuReference:
+    """One tile-evaluation of the reference's path (forward, losses, backward incl. the dW Caffe
+    computes and discards) + the full-image regularisers/Adam, on the host cores."""
+
+    def __init__(self, a):
+        from oracle import numeric as on
+        from oracle.caffe_net import he_normal_weights, model_layers
+        from oracle.optimizers import Adam
+        from oracle.tile_operator import OracleModel
+        from oracle.transfer import to_params
+        self.a, self.on = a, on
+        model = 'vgg19.prototxt'
+        params = he_normal_weights(model_layers(model))
+        self.ora = ora = OracleModel(model, params, compute_weight_grads=True)
+        t = min(a.tile_size, a.size)
+        content = to_params(synthetic_rgb(1, a.size)[:t, :t])
+        style = to_params(synthetic_rgb(2, a.size)[:t, :t])
+        np.random.seed(0)
+        self.full = to_params(np.random.uniform(0, 255, size=(a.size, a.size, 3)))
+        self.tile = np.ascontiguousarray(self.full[:, :t, :t])
+        # targets of the sampled tile (values do not influence the timing)
+        ora.img = style
+        ora.styles = [{l: on.gram_lower(f) for l, f in ora.features_once(STYLE_LAYERS).items()}]
+        ora.img = content
+        ora.contents = [ora.features_once(CONTENT_LAYERS)]
+        ora.publish()
+        self.layers = ora.ordered_layers(CONTENT_LAYERS, STYLE_LAYERS)
+        self.lw = {l: 1.0 for l in ora.layers()}
+        self.sw = {l: 1.0 / len(STYLE_LAYERS) for l in STYLE_LAYERS}
+        self.adam = Adam(self.full.copy(), step_size=15.0, bp1=1 - 1 / 20.0, decay=0.05, power=0.5)
+        self.ntiles = ((a.size - 1) // a.tile_size + 1) ** 2
+        self.cores = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else os.cpu_count()
+
+    def tile_eval(self):
+        t0 = time.perf_counter()
+        self.ora.sc_grad_tile(self.tile, np.array([0, 0]), self.layers, CONTENT_LAYERS,
+                              STYLE_LAYERS, [], self.lw, {'conv4_2': 0.05}, self.sw, {})
+        return time.perf_counter() - t0
+
+    def full_image_tail(self):
+        """Regularisers (style_transfer.py:710-727) + Adam update (optimizers.py:26-42)."""
+        on = self.on
+        mean = np.float32((103.939, 116.779, 123.68)).reshape(3, 1, 1)
+
+        def opfunc(img):
+            tv_loss, tv_grad = on.tv_norm(img / np.float32(127.5), beta=2.0)
+            p_loss, p_grad = on.p_norm((img + mean - np.float32(127.5)) / np.float32(127.5), p=6.0)
+            return 5 * tv_loss + 2 * p_loss, np.float32(5) * tv_grad + np.float32(2) * np.float32(p_grad)
+        t0 = time.perf_counter()
+        self.adam.update(opfunc)
+        return time.perf_counter() - t0
+
+    def iteration_seconds(self, t_tile, t_tail):
+        return self.ntiles * t_tile + t_tail
+
+    def sample_text(self, n):
+        return ('%d of the %d tile-evaluations of one iteration (512x512 VGG-19 forward + losses + '
+                'backward incl. dW, as Caffe does) timed and scaled x%d, plus one full-image '
+                'regulariser+Adam pass; numpy/OpenBLAS oracle port' % (n, self.ntiles, self.ntiles))
+
+
+def run_reference(a):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    ref = CpuReference(a)
+    t_tail = ref.full_image_tail()
+    for _ in range(a.warmup):
+        ref.tile_eval()
+    times = [ref.tile_eval() for _ in range(a.steps)]
+    t_tile = float(np.mean(times))
+    sec = ref.iteration_seconds(t_tile, t_tail)
+    value = 1.0 / sec
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': 'iterations/s',
+        'n_gpus': a.gpus, 'steps': a.steps, 'warmup': a.warmup, 'ms_per_step': sec * 1e3,
+        'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32',
+        'data': 'synthetic', 'config': workload_config(a, 1),
+        'cpu_baseline': {'value': value, 'unit': 'iterations/s', 'cores': ref.cores, 'kind': 'port',
+                         'sample': 'each step = ' + ref.sample_text(1)},
+        'e2e': {'value': value, 'unit': 'iterations/s', 'h2d_bytes_per_step': 0,
+                'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# =======================================================================================================
+# clocks
+# =======================================================================================================
+class ClockSampler:
+    FIELDS = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+              'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+              'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(
+                ['nvidia-smi', '-i', str(index), '--query-gpu=' + self.FIELDS,
+                 '--format=csv,noheader,nounits', '-lms', '100'],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(',')]))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for t, r in self.rows if t0 <= t <= t1] or [r for _, r in self.rows[-3:]]
+        sm, mx, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for r in rows:
+            try:
+                sm.append(float(r[0])), mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(names, r[3:7]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        return {'sm_mhz': float(np.median(sm)) if sm else None,
+                'sm_max_mhz': max(mx) if mx else None, 'reasons': sorted(reasons),
+                'samples': len(sm)}
+
+
+# =======================================================================================================
+# engine arm
+# =======================================================================================================
+def run_engine(a):
+    import ctypes as C
+    import torch
+    import torch.distributed as dist
+    from style_transfer_b200 import _lib, netdesc, weights
+    from style_transfer_b200.engine import TileEngine
+    from style_transfer_b200.transfer import StyleTransfer, default_args
+
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py needs a CUDA device: the engine has no CPU path')
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=dev)
+    lib = _lib.load()
+
+    args = default_args(size=a.size, min_size=a.size, tile_size=a.tile_size, optimizer=a.optimizer)
+    net = netdesc.from_model(args.model)
+    eng = TileEngine(net, weights.he_normal(net), mean=args.mean, device=local,
+                     precision=a.precision, rank=rank, world=world)
+    st = StyleTransfer(eng, args)
+    content = eng.pil_to_image(synthetic_rgb(1, a.size))
+    style = eng.pil_to_image(synthetic_rgb(2, a.size))
+    np.random.seed(args.seed)
+    st.init_first_scale(a.size, a.size)
+    st.prepare([content], [style])
+    n = eng.img.numel()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    # ---- device-resident throughput --------------------------------------------------------------
+    for _ in range(a.warmup):
+        st.step()
+    sampler = ClockSampler(local) if rank == 0 else None
+    launches0 = lib.st_launch_count()
+    t0 = time.perf_counter()
+    ms = timed(st.step, a.steps)
+    t1 = time.perf_counter()
+    launches = lib.st_launch_count() - launches0
+    clocks = sampler.stop(t0, t1) if sampler else None
+    lt = torch.tensor([launches], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(lt)
+    launches = int(lt.item())
+    value = a.steps / (ms * 1e-3)
+
+    # ---- end to end: host buffers in, host buffers out, every step --------------------------------
+    e2e = None
+    if not a.no_e2e:
+        host_params = torch.empty(eng.img.shape, dtype=torch.float32).pin_memory()
+        host_avg = torch.empty(eng.img.shape, dtype=torch.float32).pin_memory()
+        host_loss = torch.empty(1, dtype=torch.float64).pin_memory()
+        host_params.copy_(eng.img)
+
+        def e2e_step():
+            eng.img.copy_(host_params, non_blocking=True)            # H2D: this step's image
+            avg, loss = st.step()
+            host_avg.copy_(avg, non_blocking=True)                   # D2H: averaged iterate
+            host_params.copy_(eng.img, non_blocking=True)            # D2H: updated parameters
+            host_loss.copy_(loss, non_blocking=True)                 # D2H: loss
+            torch.cuda.current_stream().synchronize()
+        for _ in range(2):
+            e2e_step()
+        ms_e2e = timed(e2e_step, a.steps)
+        e2e = {'value': a.steps / (ms_e2e * 1e-3), 'unit': 'iterations/s',
+               'h2d_bytes_per_step': n * 4, 'd2h_bytes_per_step': 2 * n * 4 + 8,
+               'ms_per_step': ms_e2e / a.steps,
+               'boundary': 'pinned host f32[3,H,W] image in; averaged iterate, updated image and '
+                           'loss out (StyleTransfer.step through the C ABI), every step'}
+
+    # ---- roofline of the dominant kernel (per-launch CUDA events on the launching stream) ---------
+    roofline, breakdown = None, None
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
+            peaks = json.load(f)
+    except OSError:
+        pass
+    lib.st_timing_reset()
+    lib.st_timing_enable(1)
+    tsteps = min(a.steps, 3)
+    ms_timing = timed(st.step, tsteps)
+    lib.st_timing_enable(0)
+    cats = ['conv_tc', 'conv_simt', 'pool', 'gram', 'style_grad', 'loss', 'image']
+    breakdown = {}
+    for i, name in enumerate(cats):
+        t, w, k = C.c_double(), C.c_double(), C.c_uint64()
+        _lib.call('st_timing_read', i, C.byref(t), C.byref(w), C.byref(k))
+        breakdown[name] = {'ms_per_step': t.value / tsteps, 'work_per_step': w.value / tsteps,
+                           'launch_groups_per_step': k.value / tsteps}
+    lib.st_timing_reset()
+    dom = 'conv_tc' if breakdown['conv_tc']['ms_per_step'] > 0 else 'conv_simt'
+    d = breakdown[dom]
+    if d['ms_per_step'] > 0:
+        if a.precision == 'bf16':
+            peak = peaks.get('bf16_tflops_sustained', 1400.0)
+            src = 'MEASURED_PEAKS.json bf16_tflops_sustained' if peaks else 'fallback 1400 (recipe)'
+        else:
+            peak, src = 0.5 * 148 * 128 * 2 * 1.965e-3 * 2, 'nominal fp32 FFMA peak (no tensor cores in fp32 mode)'
+        ach = d['work_per_step'] / (d['ms_per_step'] * 1e-3) / 1e12
+        roofline = {'bound': 'tensor', 'kernel': 'conv3x3_tc_kernel' if dom == 'conv_tc' else 'conv3x3_kernel',
+                    'achieved': ach, 'peak': peak, 'unit': 'TFLOP/s', 'frac': ach / peak,
+                    'traffic': None, 'peak_source': src,
+                    'flops_per_launch': d['work_per_step'] / max(d['launch_groups_per_step'], 1),
+                    'avg_launch_ms': d['ms_per_step'] / max(d['launch_groups_per_step'], 1),
+                    'share_of_step': d['ms_per_step'] / (ms_timing / tsteps)}
+
+    # ---- CPU baseline (rank 0, N = 1) ---------------------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        ref = CpuReference(a)
+        t_tail = ref.full_image_tail()
+        ref.tile_eval()
+        t_tile = float(np.mean([ref.tile_eval() for _ in range(2)]))
+        cpu = {'value': 1.0 / ref.iteration_seconds(t_tile, t_tail), 'unit': 'iterations/s',
+               'cores': ref.cores, 'kind': 'port', 'sample': ref.sample_text(2),
+               'tile_eval_s': t_tile, 'full_image_tail_s': t_tail}
+
+    if rank == 0:
+        cfg = workload_config(a, world)
+        cfg['l2'] = ('no explicit flush: one step streams the %d MB of image + optimizer state and '
+                     '~%d MB of activations per tile, both larger than the 126 MB L2'
+                     % (6 * n * 4 >> 20, 152 if a.precision == 'bf16' else 304))
+        cfg['precision'] = a.precision
+        line = {
+            'metric': METRIC, 'value': value, 'unit': 'iterations/s', 'n_gpus': world,
+            'steps': a.steps, 'warmup': a.warmup, 'ms_per_step': ms / a.steps,
+            'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
+            'dtype': 'bf16' if a.precision == 'bf16' else 'f32', 'data': 'synthetic', 'config': cfg,
+            'clocks': clocks, 'e2e': e2e, 'gpu_launches': launches, 'roofline': roofline,
+            'cpu_baseline': cpu, 'breakdown': breakdown,
+            'tile_eval_ms': breakdown and sum(v['ms_per_step'] for k, v in breakdown.items()
+                                              if k != 'image') / cfg['tiles_per_gpu'],
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse_args()
+    if a.impl == 'reference':
+        run_reference(a)
+    else:
+        run_engine(a)
+
+
+if __name__ == '__main__':
+    main()

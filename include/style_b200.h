@@ -175,6 +175,26 @@ ST_API int st_asum(const float* x, size_t n, double* out_dev, st_stream stream);
 /* y = a*x + b*y elementwise (a, b host scalars). */
 ST_API int st_axpby(float a, const float* x, float b, float* y, size_t n, st_stream stream);
 
+/* ---- opt-in per-kernel timing (bench.py's roofline leg) ------------------------------------------
+ * While enabled, every launcher of the categories below brackets its kernels with CUDA events on
+ * the launching stream.  st_timing_read synchronises the device and returns, for one category, the
+ * summed device time (ms), the summed ALGORITHMIC work (flops for the tensor categories, bytes for
+ * the HBM ones) and the number of bracketed launch groups since the last st_timing_reset.
+ * Process-wide, not thread-safe: enable it from the thread that drives the context. */
+enum st_timing_category {
+  ST_TIME_CONV_TC = 0,      /* tcgen05 implicit-GEMM convolutions, flops */
+  ST_TIME_CONV_SIMT = 1,    /* SIMT convolutions (fp32 mode; 3-channel first/last layer), flops */
+  ST_TIME_POOL = 2,         /* pooling fwd/bwd, bytes */
+  ST_TIME_GRAM = 3,         /* Gram F^T F, flops */
+  ST_TIME_STYLE_GRAD = 4,   /* delta-Gram x F, flops */
+  ST_TIME_LOSS = 5,         /* loss statistics + gradient injection, bytes */
+  ST_TIME_IMAGE = 6,        /* regularisers, optimizers, gradient unpack, bytes */
+  ST_TIME_CATEGORIES = 7
+};
+ST_API int st_timing_enable(int on);
+ST_API int st_timing_read(int category, double* ms_total, double* work_total, uint64_t* n_scopes);
+ST_API int st_timing_reset(void);
+
 /* Number of kernels this library has launched on the calling process since load (bench.py's
  * "gpu_launches"). */
 ST_API uint64_t st_launch_count(void);

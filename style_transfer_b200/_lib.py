@@ -63,6 +63,10 @@ PROTOTYPES = {
     'st_dot': (_i, [_vp, _vp, _sz, _vp, _vp]),
     'st_asum': (_i, [_vp, _sz, _vp, _vp]),
     'st_axpby': (_i, [_f, _vp, _f, _vp, _sz, _vp]),
+    'st_timing_enable': (_i, [_i]),
+    'st_timing_read': (_i, [_i, C.POINTER(C.c_double), C.POINTER(C.c_double),
+                            C.POINTER(C.c_uint64)]),
+    'st_timing_reset': (_i, []),
 }
 
 _lib = None

@@ -44,6 +44,35 @@ extern std::atomic<uint64_t> g_launches;
 
 inline int cdiv(long a, long b) { return (int)((a + b - 1) / b); }
 
+// ---- opt-in per-kernel timing (st_timing_* in style_b200.h) -------------------------------------
+// A launcher declares `TimerScope t(stream, category, work)`; when timing is enabled the scope
+// records a CUDA event on `stream` before and after the launches it covers.  `work` is the
+// ALGORITHMIC work of those launches: flops for the tensor categories, bytes for the HBM ones.
+enum TimingCategory {
+  kTimeConvTc = 0,     // tcgen05 implicit-GEMM convolutions (flops)
+  kTimeConvSimt = 1,   // SIMT convolutions incl. the 3-channel first/last layer (flops)
+  kTimePool = 2,       // pooling forward / backward (bytes)
+  kTimeGram = 3,       // Gram F^T F (flops)
+  kTimeStyleGrad = 4,  // delta-Gram x F (flops)
+  kTimeLoss = 5,       // content / dd / gram-delta statistics and gradient injection (bytes)
+  kTimeImage = 6,      // regularisers, optimizers, gradient unpack (bytes)
+  kTimeCategories = 7
+};
+extern bool g_timing_enabled;
+void timing_mark(cudaStream_t s, int category, double work, bool begin);
+struct TimerScope {
+  cudaStream_t s;
+  int cat;
+  bool on;
+  TimerScope(cudaStream_t stream, int category, double work)
+      : s(stream), cat(category), on(g_timing_enabled) {
+    if (on) timing_mark(s, cat, work, true);
+  }
+  ~TimerScope() {
+    if (on) timing_mark(s, cat, 0.0, false);
+  }
+};
+
 // ---- storage-type traits: activations are NHWC in float or bf16 ------------------------------------
 template <typename T> struct Store;
 template <> struct Store<float> {

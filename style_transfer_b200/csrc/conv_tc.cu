@@ -434,6 +434,7 @@ int launch(TcContext& tc, const CUtensorMap& map_w, const T* in, T* out, const T
   }
   const int tiles = a.tiles_x * a.tiles_y * a.tiles_n;
   const int grid = tiles < tc.sm_count ? tiles : tc.sm_count;
+  TimerScope ts(s, kTimeConvTc, 18.0 * a.cin * a.cout * a.h * a.w);
   ST_LAUNCH(kern, grid, kThreads, Cfg::kSmemBytes, s, map_in, map_w, map_out, a);
   return ST_OK;
 }

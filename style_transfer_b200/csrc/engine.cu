@@ -16,6 +16,42 @@ static thread_local std::string g_error;
 std::atomic<uint64_t> g_launches{0};
 void set_error(const std::string& msg) { g_error = msg; }
 
+// ---- per-kernel timing ---------------------------------------------------------------------------
+bool g_timing_enabled = false;
+namespace {
+struct TimingRec {
+  cudaEvent_t begin, end;
+  int cat;
+  double work;
+};
+std::vector<TimingRec> g_timing_recs;
+std::vector<cudaEvent_t> g_timing_free;
+cudaEvent_t timing_event() {
+  cudaEvent_t e = nullptr;
+  if (!g_timing_free.empty()) {
+    e = g_timing_free.back();
+    g_timing_free.pop_back();
+  } else {
+    cudaEventCreate(&e);
+  }
+  return e;
+}
+}  // namespace
+void timing_mark(cudaStream_t s, int category, double work, bool begin) {
+  if (begin) {
+    TimingRec r{timing_event(), timing_event(), category, work};
+    cudaEventRecord(r.begin, s);
+    g_timing_recs.push_back(r);
+  } else {
+    // scopes nest like a stack; close the innermost open record of this category
+    for (size_t i = g_timing_recs.size(); i-- > 0;)
+      if (g_timing_recs[i].cat == category) {
+        cudaEventRecord(g_timing_recs[i].end, s);
+        break;
+      }
+  }
+}
+
 struct LayerRt {
   int kind, bottom, top, cin, cout;
   float* w_fwd = nullptr;    // [9][cin][cout]
@@ -337,7 +373,36 @@ Grid tile_grid(int H, int W, int tile_size) {
 extern "C" {
 
 const char* st_last_error(void) { return g_error.c_str(); }
-int st_version(void) { return 100; }
+int st_version(void) { return 101; }
+
+int st_timing_enable(int on) {
+  g_timing_enabled = on != 0;
+  return ST_OK;
+}
+
+int st_timing_read(int category, double* ms_total, double* work_total, uint64_t* n_scopes) {
+  ST_REQUIRE(category >= 0 && category < kTimeCategories, "st_timing_read: unknown category");
+  ST_CUDA(cudaDeviceSynchronize());
+  double ms = 0.0, work = 0.0;
+  uint64_t n = 0;
+  for (const TimingRec& r : g_timing_recs) {
+    if (r.cat != category) continue;
+    float t = 0.f;
+    ST_CUDA(cudaEventElapsedTime(&t, r.begin, r.end));
+    ms += t, work += r.work, ++n;
+  }
+  if (ms_total) *ms_total = ms;
+  if (work_total) *work_total = work;
+  if (n_scopes) *n_scopes = n;
+  return ST_OK;
+}
+
+int st_timing_reset(void) {
+  ST_CUDA(cudaDeviceSynchronize());
+  for (const TimingRec& r : g_timing_recs) g_timing_free.push_back(r.begin), g_timing_free.push_back(r.end);
+  g_timing_recs.clear();
+  return ST_OK;
+}
 uint64_t st_launch_count(void) { return g_launches.load(); }
 
 int st_create(int device, int precision, int n_layers, const st_layer_desc* layers, st_ctx** out) {

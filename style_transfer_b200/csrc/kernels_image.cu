@@ -39,6 +39,7 @@ __global__ void unpack_grad_kernel(const float* __restrict__ packed, int H, int 
 int unpack_grad(const float* packed, int H, int W, int roll_y, int roll_x, int nty, int ntx,
                 int th, int tw, int thmax, int twmax, int world, int tiles_per_rank, float* grad,
                 cudaStream_t s) {
+  TimerScope ts(s, kTimeImage, 8.0 * 3 * H * W);
   ST_LAUNCH(unpack_grad_kernel, ew_grid((size_t)3 * H * W, 256), 256, 0, s, packed, H, W, roll_y,
             roll_x, nty, ntx, th, tw, thmax, twmax, world, tiles_per_rank, grad);
   return ST_OK;
@@ -133,6 +134,7 @@ __global__ void regularizers_kernel(const float* __restrict__ img, int H, int W,
 int regularizers(const float* img, int H, int W, float m0, float m1, float m2, float tv_w,
                  float tv_beta, float p_w, float p_pow, const float* aux, float aux_w, int roll_y,
                  int roll_x, double* loss_accum, float* grad, ReduceScratch rs, cudaStream_t s) {
+  TimerScope ts(s, kTimeImage, 4.0 * 3 * H * W * (3 + (aux ? 1 : 0)));
   ST_LAUNCH(regularizers_kernel, ew_grid((size_t)3 * H * W, 256), 256, 0, s, img, H, W, m0, m1, m2,
             tv_w, tv_beta, p_w, p_pow, aux, aux_w, roll_y, roll_x, loss_accum, grad, rs);
   return ST_OK;
@@ -172,6 +174,7 @@ int adam_step(float* params, const float* grad, float* g1, float* g2, float* p1,
   // (1 - beta) is formed in double and rounded once, as numpy does for a Python-float scalar.
   const float omb1 = (float)(1.0 - (double)b1), omb2 = (float)(1.0 - (double)b2);
   const float ombp1 = (float)(1.0 - (double)bp1);
+  TimerScope ts(s, kTimeImage, 40.0 * n);
   ST_LAUNCH(adam_kernel, ew_grid(n, 256), 256, 0, s, params, grad, g1, g2, p1, avg_out, n,
             -step_size, b1, omb1, b2, omb2, bp1, ombp1, g1_corr, g2_corr, p1_corr);
   return ST_OK;

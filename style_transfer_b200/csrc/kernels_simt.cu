@@ -151,6 +151,7 @@ int conv3x3_simt(const T* in, const float* wpack, const float* bias, T* out, int
   a.h = h, a.w = w, a.cin = cin, a.cout = cout, a.forward = forward ? 1 : 0;
   dim3 grid(cdiv(h, kTH) * cdiv(w, kTW), cout / kCoT);
   auto k = conv3x3_kernel<T, 8, false>;
+  TimerScope ts(s, kTimeConvSimt, 18.0 * cin * cout * h * w);
   ST_LAUNCH(k, grid, 256, 0, s, a);
   return ST_OK;
 }
@@ -164,6 +165,7 @@ int conv_first_fwd(const ImageView& img, int h, int w, const float* wpack, const
   a.h = h, a.w = w, a.cin = 3, a.cout = cout, a.forward = 1;
   dim3 grid(cdiv(h, kTH) * cdiv(w, kTW), cout / kCoT);
   auto k = conv3x3_kernel<T, 3, true>;
+  TimerScope ts(s, kTimeConvSimt, 18.0 * 3 * cout * h * w);
   ST_LAUNCH(k, grid, 256, 0, s, a);
   return ST_OK;
 }
@@ -248,6 +250,7 @@ int conv_last_bwd(const T* dz, int h, int w, int cz, const float* wpack, float* 
                   long plane_stride, long row_stride, cudaStream_t s) {
   ST_REQUIRE(cz % kLC == 0, "last conv backward: channel count must be a multiple of 16");
   auto k = conv_last_bwd_kernel<T>;
+  TimerScope ts(s, kTimeConvSimt, 18.0 * 3 * cz * h * w);
   ST_LAUNCH(k, cdiv(h, kLH) * cdiv(w, kLW), 64, 0, s, dz, h, w, cz, wpack, grad, plane_stride,
             row_stride);
   return ST_OK;
@@ -365,6 +368,7 @@ int pool_fwd(const T* in, T* out, int h, int w, int c, bool is_max, cudaStream_t
   ST_REQUIRE(c % 4 == 0, "pool: channels must be a multiple of 4");
   const int ho = (h + 1) / 2, wo = (w + 1) / 2;
   auto k = pool_fwd_kernel<T>;
+  TimerScope ts(s, kTimePool, (double)sizeof(T) * c * ((double)h * w + (double)ho * wo));
   ST_LAUNCH(k, ew_grid((size_t)ho * wo * (c / 4), 256), 256, 0, s, in, out, h, w, c, ho, wo,
             is_max ? 1 : 0);
   return ST_OK;
@@ -376,6 +380,8 @@ int pool_bwd(const T* d_out, const T* in, T* d_in, int h, int w, int c, bool is_
   ST_REQUIRE(c % 4 == 0, "pool: channels must be a multiple of 4");
   const int ho = (h + 1) / 2, wo = (w + 1) / 2;
   auto k = pool_bwd_kernel<T>;
+  TimerScope ts(s, kTimePool, (double)sizeof(T) * c *
+                                  ((double)h * w * (2 + (inj ? 1 : 0)) + (double)ho * wo));
   ST_LAUNCH(k, ew_grid((size_t)ho * wo * (c / 4), 256), 256, 0, s, d_out, in, d_in, h, w, c, ho,
             wo, is_max ? 1 : 0, apply_mask ? 1 : 0, inj);
   return ST_OK;
@@ -468,6 +474,7 @@ int gram_full(const T* f, int hw, int c, bool channel_major, float* gram, float*
   int pps = cdiv(cdiv(hw, nsplit), kGP) * kGP;
   nsplit = cdiv(hw, pps);
   dim3 grid(npairs, nsplit);
+  TimerScope ts(s, kTimeGram, 2.0 * c * c * hw);
   if (channel_major) {
     auto k = gram_partial_kernel<T, true>;
     ST_LAUNCH(k, grid, 256, 0, s, f, hw, c, pps, part);
@@ -586,6 +593,7 @@ int style_grad(const T* f, const float* delta, T* s_out, int hw, int c, double* 
   const long blocks = (long)cdiv(hw, 64) * (c / 64);
   ST_REQUIRE(blocks <= kMaxReduceBlocks, "style_grad: tile too large for the reduction scratch");
   auto k = style_grad_kernel<T>;
+  TimerScope ts(s, kTimeStyleGrad, 2.0 * c * c * hw);
   ST_LAUNCH(k, (int)blocks, 256, 0, s, f, delta, s_out, hw, c, sum_abs, rs);
   return ST_OK;
 }

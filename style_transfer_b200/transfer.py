@@ -41,6 +41,22 @@ def parse_weights(args, master_weight):
     return names, {name: weight * master_weight / total for name, weight in weights.items()}
 
 
+def default_args(**overrides):
+    """The hot-path flags with the defaults of the reference's flag table
+    (config_system.py:46-119); the CLI front end fills the same namespace from argv."""
+    from types import SimpleNamespace
+    args = dict(
+        size=256, min_size=182, tile_size=512, devices=[-1], iterations=[200, 100],
+        optimizer='adam', step_size=15.0, step_decay=[0.05, 0.5], avg_window=20.0,
+        content_weight=0.05, dd_weight=0.0, tv_weight=5.0, tv_power=2.0, p_weight=2.0,
+        p_power=6.0, aux_weight=10.0, content_layers=['conv4_2'],
+        style_layers=['conv1_1', 'conv2_1', 'conv3_1', 'conv4_1', 'conv5_1'], dd_layers=[],
+        model='vgg19.prototxt', weights='vgg19.caffemodel', mean=(103.939, 116.779, 123.68),
+        seed=0, div=1, jitter=False)
+    args.update(overrides)
+    return SimpleNamespace(**args)
+
+
 def scale_ladder(size, min_size):
     """Sizes from --size down by sqrt(2) while >= --min-size, smallest first (:840-846, :854)."""
     sizes = [size]
