@@ -488,6 +488,7 @@ int tc_init(TcContext& tc, int sm_count) {
   }
   tc.encode_fn = fn;
   tc.enabled = true;
+  tc.pair_kernel = getenv("ST_CONV_V1") == nullptr;
   return ST_OK;
 }
 
@@ -514,6 +515,8 @@ bool tc_shape_ok(const TcContext& tc, const TcWeights& w, int cin, int cout) {
 int conv3x3_tc(TcContext& tc, const TcWeights& w, const __nv_bfloat16* in, __nv_bfloat16* out,
                int h, int wd, int cin, int cout, bool forward, const float* bias,
                const __nv_bfloat16* mask_act, const __nv_bfloat16* inj, cudaStream_t s) {
+  if (tc.pair_kernel)
+    return conv3x3_tc_pair(tc, w, in, out, h, wd, cin, cout, forward, bias, mask_act, inj, s);
   TcArgs a{};
   a.h = h, a.w = wd, a.cin = cin, a.cout = cout, a.forward = forward ? 1 : 0;
   a.bias = bias, a.mask_act = mask_act, a.inj = inj;

@@ -21,6 +21,7 @@ struct TcWeights {
 
 struct TcContext {
   bool enabled = false;
+  bool pair_kernel = true;     // conv_tc2.cu (cta_group::2); ST_CONV_V1=1 selects the single-CTA kernel
   int sm_count = 0;
   void* encode_fn = nullptr;   // cuTensorMapEncodeTiled, fetched through cudaGetDriverEntryPoint
 };
@@ -44,6 +45,21 @@ inline bool tc_usable(const TcContext& tc, const TcWeights& w, int cin, int cout
 int conv3x3_tc(TcContext& tc, const TcWeights& w, const __nv_bfloat16* in, __nv_bfloat16* out,
                int h, int wd, int cin, int cout, bool forward, const float* bias,
                const __nv_bfloat16* mask_act, const __nv_bfloat16* inj, cudaStream_t s);
+// CTA-pair (cta_group::2) kernel of conv_tc2.cu: same contract as conv3x3_tc.
+int conv3x3_tc_pair(TcContext& tc, const TcWeights& w, const __nv_bfloat16* in, __nv_bfloat16* out,
+                    int h, int wd, int cin, int cout, bool forward, const float* bias,
+                    const __nv_bfloat16* mask_act, const __nv_bfloat16* inj, cudaStream_t s);
+// S[p][n] = sum_c F[p][c] * D[n][c] for F [h][w][c] (bf16 NHWC) and D [c][c] bf16; the sum of |S|
+// over the tiles of CTA i is written to abs_partials[i], i < *n_partials (<= sm_count).
+int gemm_abs_tc_pair(TcContext& tc, const __nv_bfloat16* f, const __nv_bfloat16* d,
+                     __nv_bfloat16* s_out, int h, int w, int c, double* abs_partials,
+                     int* n_partials, cudaStream_t s);
+
+// gram[C][C] (full, symmetric, fp32) = F^T F / (C*hw) for bf16 NHWC F [hw][c] on tcgen05 (gram_tc.cu).
+bool gram_tc_ok(const TcContext& tc, int c);
+int gram_tc(TcContext& tc, const __nv_bfloat16* f, int hw, int c, float* gram, float* part,
+            size_t part_floats, cudaStream_t s);
+
 inline int conv3x3_tc(TcContext&, const TcWeights&, const float*, float*, int, int, int, int, bool,
                       const float*, const float*, const float*, cudaStream_t) {
   return -1;   // never reached: tc_usable<float> is false

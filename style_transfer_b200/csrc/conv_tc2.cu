@@ -1,0 +1,572 @@
+// tcgen05 / TMA implicit-GEMM convolution for bf16 NHWC activations, CTA-pair version (sm_100a).
+//
+//   out[p][n] = epilogue( sum_{tap, c} in[p + off(tap)][c] * Wk[n][tap*Cin + c] )      TAPS = 9 (3x3)
+//   out[p][n] = epilogue( sum_c in[p][c] * Wk[n][c] )                                  TAPS = 1 (1x1)
+//
+// Why this shape.  A 128x128 single-CTA tile that re-loads its A operand for every tap needs 128
+// bytes of L2->shared traffic per tensor-core cycle and SM; 148 SMs then ask the L2 for three times
+// what it delivers (profiles/r01_conv_v1_l2_bound.md) and the tensor pipe idles.  This kernel cuts
+// that traffic ~3.5x:
+//   * two CTAs of a cluster form one tcgen05 `cta_group::2` MMA: 256 pixels x BN channels per
+//     instruction, each CTA staging only its own 128 pixels of A and HALF of the weight tile B;
+//   * the A operand of one 64-channel block is loaded once per tile as three x-shifted copies of
+//     the (16+2) x 8 pixel halo window; the nine taps are then nine shared-memory descriptors into
+//     those copies (a y shift is a whole number of 1024-byte swizzle atoms because a tile row is
+//     exactly 8 pixels x 128 bytes), so A moves 3 x 18/16 instead of 9 times.
+//
+// Work split: pair tile = 32 rows x 8 columns of pixels (CTA rank r owns rows [16r, 16r+16)) x BN
+// output channels; persistent pairs walk the tile list round-robin.  K loop: 64-channel blocks,
+// inside each the 9 taps, inside each 4 MMAs of K = 16.
+//
+// Warps (224 threads per CTA):
+//   0      A producer   (TMA, one lane)            both CTAs
+//   1      MMA issuer   (one lane, leader CTA only) + TMEM allocation (both CTAs)
+//   2..5   epilogue     TMEM -> registers -> bias/ReLU | mask/inject | abs-sum -> swizzled smem
+//                       -> TMA store; accumulators are double-buffered in TMEM
+//   6      B producer   (TMA, one lane)            both CTAs
+// All "full" barriers live in the leader CTA (TMA of the peer signals them through the cluster
+// address); "empty" barriers are signalled in both CTAs by multicast tcgen05.commit.
+#include <cuda.h>
+
+#include <cstdlib>
+#include <vector>
+
+#include "style_b200.h"
+#include "common.cuh"
+#include "conv_tc.h"
+
+namespace st {
+
+namespace {
+
+constexpr int kBH = 16, kBW = 8;          // pixels per CTA tile: 16 rows x 8 columns = 128 = TMEM lanes
+constexpr int kRowBytes = kBW * 128;      // one tile row of one 64-channel block: one swizzle atom
+constexpr int kThreads2 = 224;
+constexpr uint32_t kSpin = 1u << 26;
+constexpr int kOutStageBytes = 128 * 128; // 128 pixels x 64 channels bf16
+constexpr int kSmemBudget = 227 * 1024 - 1024 /*alignment slack*/ - 512 /*barriers*/;
+
+enum Epilogue { kEpiFwd = 0, kEpiBwd = 1, kEpiAbs = 2 };
+
+// ---- PTX wrappers ---------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ uint32_t cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t local_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::
+                   : "memory");
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+// arrive on a barrier of any CTA of the cluster (cluster address)
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  for (uint32_t spin = 0;; ++spin) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (done) return;
+    if (spin > kSpin) __trap();           // protocol bug: fail loudly instead of hanging the GPU
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+// TMA loads issued by either CTA of the pair; completion bytes go to the barrier at `bar_cluster`
+// (a cluster address, the leader's barrier).
+__device__ __forceinline__ void tma_load_3d_pair(const CUtensorMap* map, uint32_t bar_cluster,
+                                                 void* dst, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap* map, uint32_t bar_cluster,
+                                                 void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void* src, int c0, int c1,
+                                             int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::
+                   "l"(reinterpret_cast<uint64_t>(map)),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;"); }
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void tma_store_wait_all() {
+  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                   smem_u32(dst_smem)),
+               "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+// Arrives (once the MMAs issued so far retire) on the barrier at this smem offset in BOTH CTAs.
+__device__ __forceinline__ void tc_commit_pair(uint64_t* bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64"
+      " [%0], %1;" ::"r"(smem_u32(bar)),
+      "h"((uint16_t)3)
+      : "memory");
+}
+__device__ __forceinline__ void tc_mma_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
+                                            uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32"
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, "
+      "%20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+        "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+// K-major SWIZZLE_128B shared-memory matrix descriptor: 128-byte rows, 8-row groups 1024 B apart.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) |
+         ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+
+struct Tc2Args {
+  int h, w, cin, cout;
+  int tiles_x, tiles_y, tiles_n;   // pair tiles: 8 columns x 32 rows x BN channels
+  const float* bias;               // kEpiFwd
+  const __nv_bfloat16* mask_act;   // kEpiBwd, NHWC [h][w][cout], may be null
+  const __nv_bfloat16* inj;        // kEpiBwd, may be null
+  double* abs_partials;            // kEpiAbs: one double per CTA
+};
+
+template <int BN, int TAPS>
+struct Cfg2 {
+  static constexpr int kHaloRows = TAPS == 9 ? kBH + 2 : kBH;
+  static constexpr int kVariants = TAPS == 9 ? 3 : 1;
+  static constexpr int kAVarBytes = kHaloRows * kRowBytes;
+  static constexpr int kABytes = kVariants * kAVarBytes;         // 54 KB (3x3) / 16 KB (1x1)
+  static constexpr int kBBytes = (BN / 2) * 128;                 // this CTA's half of the B tile
+  static constexpr int kSA = TAPS == 9 ? 2 : 4;
+  static constexpr int kOutBytes = 2 * kOutStageBytes;
+  static constexpr int kSBRaw = (kSmemBudget - kSA * kABytes - kOutBytes) / kBBytes;
+  static constexpr int kSB = kSBRaw > 8 ? 8 : kSBRaw;
+  static constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;    // double-buffered accumulator
+  static constexpr int kSmemBytes = kSA * kABytes + kSB * kBBytes + kOutBytes + 1024 + 512;
+  static constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) |
+                                     ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+  static_assert(kSB >= 3, "not enough shared memory for the weight pipeline");
+};
+
+template <int BN, int TAPS, int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1)
+conv_tc2_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CUtensorMap map_w,
+                const __grid_constant__ CUtensorMap map_out, const Tc2Args a) {
+  using Cfg = Cfg2<BN, TAPS>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~(uintptr_t)1023);
+  uint8_t* a_base = smem;
+  uint8_t* b_base = a_base + Cfg::kSA * Cfg::kABytes;
+  uint8_t* out_base = b_base + Cfg::kSB * Cfg::kBBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(out_base + Cfg::kOutBytes);
+  uint64_t* a_full = bars;
+  uint64_t* a_empty = a_full + Cfg::kSA;
+  uint64_t* b_full = a_empty + Cfg::kSA;
+  uint64_t* b_empty = b_full + Cfg::kSB;
+  uint64_t* t_full = b_empty + Cfg::kSB;
+  uint64_t* t_empty = t_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
+  double* red = reinterpret_cast<double*>(t_empty + 4);       // 4 doubles (kEpiAbs)
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_rank();
+  const bool leader = rank == 0;
+  const int kb_per_tap = a.cin >> 6;
+  const int num_tiles = a.tiles_x * a.tiles_y * a.tiles_n;
+  const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&map_in), prefetch_tmap(&map_w), prefetch_tmap(&map_out);
+    for (int i = 0; i < Cfg::kSA; ++i) mbar_init(&a_full[i], 1), mbar_init(&a_empty[i], 1);
+    for (int i = 0; i < Cfg::kSB; ++i) mbar_init(&b_full[i], 1), mbar_init(&b_empty[i], 1);
+    for (int i = 0; i < 2; ++i) mbar_init(&t_full[i], 1), mbar_init(&t_empty[i], 8);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc_pair(tmem_slot, Cfg::kTmemCols);
+  tc_fence_before();
+  cluster_sync();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================================== A producer ============================================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        const int m_tile = tile / a.tiles_n;
+        const int x0 = (m_tile % a.tiles_x) * kBW;
+        const int y0 = (m_tile / a.tiles_x) * (2 * kBH) + (int)rank * kBH;
+        for (int cb = 0; cb < kb_per_tap; ++cb) {
+          mbar_wait(&a_empty[stage], phase ^ 1);
+          if (leader) mbar_expect_tx(&a_full[stage], 2 * Cfg::kABytes);
+          const uint32_t bar = map_to_cta(smem_u32(&a_full[stage]), 0);
+          uint8_t* dst = a_base + stage * Cfg::kABytes;
+          if constexpr (TAPS == 9) {
+#pragma unroll
+            for (int v = 0; v < 3; ++v)
+              tma_load_3d_pair(&map_in, bar, dst + v * Cfg::kAVarBytes, cb * 64, x0 + v - 1, y0 - 1);
+          } else {
+            tma_load_3d_pair(&map_in, bar, dst, cb * 64, x0, y0);
+          }
+          if (++stage == Cfg::kSA) stage = 0, phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 6) {
+    // ===================================== B producer ============================================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        const int n0 = (tile % a.tiles_n) * BN + (int)rank * (BN / 2);
+        for (int cb = 0; cb < kb_per_tap; ++cb) {
+          for (int tap = 0; tap < TAPS; ++tap) {
+            mbar_wait(&b_empty[stage], phase ^ 1);
+            if (leader) mbar_expect_tx(&b_full[stage], 2 * Cfg::kBBytes);
+            const uint32_t bar = map_to_cta(smem_u32(&b_full[stage]), 0);
+            tma_load_2d_pair(&map_w, bar, b_base + stage * Cfg::kBBytes, tap * a.cin + cb * 64, n0);
+            if (++stage == Cfg::kSB) stage = 0, phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================== MMA issuer (leader) ===================================
+    if (leader && lane == 0) {
+      int sa = 0, sb = 0;
+      uint32_t pa = 0, pb = 0, it = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
+        const uint32_t buf = it & 1, use = it >> 1;
+        mbar_wait(&t_empty[buf], (use & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + buf * BN;
+        for (int cb = 0; cb < kb_per_tap; ++cb) {
+          mbar_wait(&a_full[sa], pa);
+          const uint32_t a_addr = smem_u32(a_base + sa * Cfg::kABytes);
+#pragma unroll 1
+          for (int tap = 0; tap < TAPS; ++tap) {
+            mbar_wait(&b_full[sb], pb);
+            tc_fence_after();
+            uint32_t a_tap = a_addr;
+            if constexpr (TAPS == 9) a_tap += (tap % 3) * Cfg::kAVarBytes + (tap / 3) * kRowBytes;
+            const uint64_t da = make_smem_desc(a_tap);
+            const uint64_t db = make_smem_desc(smem_u32(b_base + sb * Cfg::kBBytes));
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              tc_mma_pair(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), Cfg::kIdesc,
+                          (cb | tap | k) != 0);
+            tc_commit_pair(&b_empty[sb]);
+            if (++sb == Cfg::kSB) sb = 0, pb ^= 1;
+          }
+          tc_commit_pair(&a_empty[sa]);
+          if (++sa == Cfg::kSA) sa = 0, pa ^= 1;
+        }
+        tc_commit_pair(&t_full[buf]);
+      }
+    }
+  } else {
+    // ===================================== epilogue ==============================================
+    const int q = warp & 3;                            // TMEM lane quadrant of this warp
+    const int m = q * 32 + lane;                       // pixel row of the CTA tile
+    const bool issuer = threadIdx.x == 64;
+    double abs_total = 0.0;
+    uint32_t it = 0, store_seq = 0;
+    for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
+      const uint32_t buf = it & 1, use = it >> 1;
+      const int n_tile = tile % a.tiles_n, m_tile = tile / a.tiles_n;
+      const int x0 = (m_tile % a.tiles_x) * kBW;
+      const int y0 = (m_tile / a.tiles_x) * (2 * kBH) + (int)rank * kBH;
+      const int py = y0 + (m >> 3), px = x0 + (m & 7);
+      const bool valid = py < a.h && px < a.w;
+      const size_t gofs = ((size_t)py * a.w + px) * a.cout + (size_t)n_tile * BN;
+      float abs_tile = 0.f;
+
+      mbar_wait(&t_full[buf], use & 1);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + buf * BN + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+      for (int g = 0; g < BN / 64; ++g, ++store_seq) {
+        uint8_t* stage_out = out_base + (store_seq & 1) * kOutStageBytes;
+        if (issuer) tma_store_wait_read<1>();          // the store that used this buffer has read it
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          const int cc = g * 2 + hh;                   // 32-channel chunk
+          uint32_t r[32];
+          tmem_ld32(taddr + cc * 32, r);
+          float v[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+          if constexpr (EPI == kEpiFwd) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              v[i] = fmaxf(v[i] + __ldg(a.bias + n_tile * BN + cc * 32 + i), 0.f);
+          } else if constexpr (EPI == kEpiBwd) {
+            if (a.mask_act != nullptr) {
+#pragma unroll
+              for (int i = 0; i < 32; i += 8) {
+                uint4 raw = make_uint4(0u, 0u, 0u, 0u);
+                if (valid) raw = *reinterpret_cast<const uint4*>(a.mask_act + gofs + cc * 32 + i);
+                const uint32_t w4[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  // bf16 > 0  <=>  sign clear and magnitude non-zero
+                  const uint32_t lo = w4[j] & 0xFFFFu, hi = w4[j] >> 16;
+                  if (!(lo != 0u && lo < 0x8000u)) v[i + 2 * j] = 0.f;
+                  if (!(hi != 0u && hi < 0x8000u)) v[i + 2 * j + 1] = 0.f;
+                }
+              }
+            }
+            if (a.inj != nullptr) {
+#pragma unroll
+              for (int i = 0; i < 32; i += 8) {
+                uint4 raw = make_uint4(0u, 0u, 0u, 0u);
+                if (valid) raw = *reinterpret_cast<const uint4*>(a.inj + gofs + cc * 32 + i);
+                const uint32_t w4[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  v[i + 2 * j] += __uint_as_float(w4[j] << 16);
+                  v[i + 2 * j + 1] += __uint_as_float(w4[j] & 0xFFFF0000u);
+                }
+              }
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) abs_tile += fabsf(v[i]);
+          }
+          // registers -> swizzled staging tile [128 rows][128 B] (SWIZZLE_128B, as TMA expects)
+          uint8_t* row = stage_out + (size_t)m * 128;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            __nv_bfloat162 p0 = __floats2bfloat162_rn(v[8 * j], v[8 * j + 1]);
+            __nv_bfloat162 p1 = __floats2bfloat162_rn(v[8 * j + 2], v[8 * j + 3]);
+            __nv_bfloat162 p2 = __floats2bfloat162_rn(v[8 * j + 4], v[8 * j + 5]);
+            __nv_bfloat162 p3 = __floats2bfloat162_rn(v[8 * j + 6], v[8 * j + 7]);
+            uint4 pk;
+            pk.x = *reinterpret_cast<uint32_t*>(&p0), pk.y = *reinterpret_cast<uint32_t*>(&p1);
+            pk.z = *reinterpret_cast<uint32_t*>(&p2), pk.w = *reinterpret_cast<uint32_t*>(&p3);
+            const int chunk = hh * 4 + j;
+            *reinterpret_cast<uint4*>(row + ((chunk ^ (m & 7)) << 4)) = pk;
+          }
+        }
+        if (g == BN / 64 - 1) {
+          // all TMEM reads of this accumulator are done: hand it back to the MMA warp (leader)
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(map_to_cta(smem_u32(&t_empty[buf]), 0));
+        }
+        fence_proxy_async();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (issuer) {
+          tma_store_3d(&map_out, stage_out, n_tile * BN + g * 64, x0, y0);
+          tma_store_commit();
+        }
+      }
+      if constexpr (EPI == kEpiAbs) abs_total += (double)abs_tile;
+    }
+    if (issuer) tma_store_wait_all();
+    if constexpr (EPI == kEpiAbs) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) abs_total += __shfl_xor_sync(0xffffffffu, abs_total, o);
+      if (lane == 0) red[q] = abs_total;
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (issuer) a.abs_partials[blockIdx.x] = red[0] + red[1] + red[2] + red[3];
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync();
+  if (warp == 1) tmem_dealloc_pair(tmem_base, Cfg::kTmemCols);
+}
+
+// ---- host side --------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int encode_bf16_map(const TcContext& tc, CUtensorMap* map, int rank, const void* base,
+                    const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box) {
+  cuuint64_t gdim[3], gstride[2];
+  cuuint32_t bdim[3], estride[3] = {1, 1, 1};
+  for (int i = 0; i < rank; ++i) gdim[i] = dims[i], bdim[i] = box[i];
+  for (int i = 0; i + 1 < rank; ++i) gstride[i] = strides_bytes[i];
+  CUresult r = reinterpret_cast<EncodeTiledFn>(tc.encode_fn)(
+      map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), gdim, gstride, bdim,
+      estride, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
+    return ST_ERR_CUDA;
+  }
+  return ST_OK;
+}
+
+template <int BN, int TAPS, int EPI>
+int launch2(TcContext& tc, const __nv_bfloat16* in, const __nv_bfloat16* wk, int wk_rows,
+            __nv_bfloat16* out, Tc2Args a, cudaStream_t s) {
+  using Cfg = Cfg2<BN, TAPS>;
+  a.tiles_x = cdiv(a.w, kBW), a.tiles_y = cdiv(a.h, 2 * kBH), a.tiles_n = a.cout / BN;
+  CUtensorMap map_in, map_out, map_w;
+  {
+    const uint64_t dims[3] = {(uint64_t)a.cin, (uint64_t)a.w, (uint64_t)a.h};
+    const uint64_t strides[2] = {(uint64_t)a.cin * 2, (uint64_t)a.w * a.cin * 2};
+    const uint32_t box[3] = {64, (uint32_t)kBW, (uint32_t)Cfg::kHaloRows};
+    int rc = encode_bf16_map(tc, &map_in, 3, in, dims, strides, box);
+    if (rc != ST_OK) return rc;
+  }
+  {
+    const uint64_t dims[3] = {(uint64_t)a.cout, (uint64_t)a.w, (uint64_t)a.h};
+    const uint64_t strides[2] = {(uint64_t)a.cout * 2, (uint64_t)a.w * a.cout * 2};
+    const uint32_t box[3] = {64, (uint32_t)kBW, (uint32_t)kBH};
+    int rc = encode_bf16_map(tc, &map_out, 3, out, dims, strides, box);
+    if (rc != ST_OK) return rc;
+  }
+  {
+    const uint64_t dims[2] = {(uint64_t)TAPS * a.cin, (uint64_t)wk_rows};
+    const uint64_t strides[1] = {(uint64_t)TAPS * a.cin * 2};
+    const uint32_t box[2] = {64, (uint32_t)(BN / 2)};
+    int rc = encode_bf16_map(tc, &map_w, 2, wk, dims, strides, box);
+    if (rc != ST_OK) return rc;
+  }
+  auto kern = conv_tc2_kernel<BN, TAPS, EPI>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    ST_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  const int tiles = a.tiles_x * a.tiles_y * a.tiles_n;
+  const int max_pairs = tc.sm_count / 2;
+  const int pairs = tiles < max_pairs ? tiles : max_pairs;
+  TimerScope ts(s, EPI == kEpiAbs ? kTimeStyleGrad : kTimeConvTc,
+                2.0 * TAPS * a.cin * a.cout * a.h * a.w);
+  ST_LAUNCH(kern, 2 * pairs, kThreads2, Cfg::kSmemBytes, s, map_in, map_w, map_out, a);
+  return ST_OK;
+}
+
+// Output-channel tile: the widest BN that still gives every CTA pair work; wide tiles halve the
+// weight traffic per flop, narrow ones fill the machine on the small feature maps.
+int choose_bn(const TcContext& tc, int h, int w, int cout) {
+  const int px_tiles = cdiv(w, kBW) * cdiv(h, 2 * kBH), pairs = tc.sm_count / 2;
+  if (const char* f = getenv("ST_TC_BN")) {
+    const int bn = atoi(f);
+    if ((bn == 64 || bn == 128 || bn == 256) && cout % bn == 0) return bn;
+  }
+  for (int bn = 256; bn > 64; bn >>= 1) {
+    if (cout % bn != 0) continue;
+    const long tiles = (long)px_tiles * (cout / bn);
+    if (tiles * 10 >= pairs * 8) return bn;     // at least ~0.8 waves of pairs
+  }
+  return 64;
+}
+
+template <int TAPS, int EPI>
+int dispatch_bn(TcContext& tc, int bn, const __nv_bfloat16* in, const __nv_bfloat16* wk, int wk_rows,
+                __nv_bfloat16* out, const Tc2Args& a, cudaStream_t s) {
+  switch (bn) {
+    case 256: return launch2<256, TAPS, EPI>(tc, in, wk, wk_rows, out, a, s);
+    case 128: return launch2<128, TAPS, EPI>(tc, in, wk, wk_rows, out, a, s);
+    default: return launch2<64, TAPS, EPI>(tc, in, wk, wk_rows, out, a, s);
+  }
+}
+
+}  // namespace
+
+int conv3x3_tc_pair(TcContext& tc, const TcWeights& w, const __nv_bfloat16* in, __nv_bfloat16* out,
+                    int h, int wd, int cin, int cout, bool forward, const float* bias,
+                    const __nv_bfloat16* mask_act, const __nv_bfloat16* inj, cudaStream_t s) {
+  Tc2Args a{};
+  a.h = h, a.w = wd, a.cin = cin, a.cout = cout;
+  a.bias = bias, a.mask_act = mask_act, a.inj = inj;
+  const int bn = choose_bn(tc, h, wd, cout);
+  if (forward) return dispatch_bn<9, kEpiFwd>(tc, bn, in, w.fwd, cout, out, a, s);
+  return dispatch_bn<9, kEpiBwd>(tc, bn, in, w.bwd, cout, out, a, s);
+}
+
+// S[p][n] = sum_c F[p][c] * D[n][c]  (D symmetric bf16 [c][c]); abs_partials[i] receives the sum
+// of |S| over the tiles of CTA i; *n_partials = number of CTAs launched.
+int gemm_abs_tc_pair(TcContext& tc, const __nv_bfloat16* f, const __nv_bfloat16* d,
+                     __nv_bfloat16* s_out, int hw_rows, int hw_cols, int c, double* abs_partials,
+                     int* n_partials, cudaStream_t s) {
+  Tc2Args a{};
+  a.h = hw_rows, a.w = hw_cols, a.cin = c, a.cout = c;
+  a.abs_partials = abs_partials;
+  const int bn = choose_bn(tc, hw_rows, hw_cols, c);
+  const int tiles = cdiv(hw_cols, kBW) * cdiv(hw_rows, 2 * kBH) * (c / bn);
+  const int max_pairs = tc.sm_count / 2;
+  *n_partials = 2 * (tiles < max_pairs ? tiles : max_pairs);
+  return dispatch_bn<1, kEpiAbs>(tc, bn, f, d, c, s_out, a, s);
+}
+
+}  // namespace st

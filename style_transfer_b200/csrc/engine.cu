@@ -90,6 +90,8 @@ struct st_ctx {
   void* sbuf = nullptr;
   size_t gcap = 0;           // elements of gbuf[i] / sbuf
   float *gram = nullptr, *delta = nullptr, *part = nullptr;
+  __nv_bfloat16* delta_bf16 = nullptr;   // bf16 copy of delta: B operand of the tcgen05 style GEMM
+  double* abs_partials = nullptr;        // per-CTA sum |S| of that GEMM (sm_count doubles)
   size_t part_floats = 0;
   double* scalars = nullptr; // 64 device doubles
   ReduceScratch rs{nullptr, nullptr};
@@ -253,12 +255,35 @@ int build_injection(st_ctx* ctx, const st_loss_spec& sp, const Dims& d, int star
       auto it = ctx->styles.find({si, sp.blob});
       ST_REQUIRE(it != ctx->styles.end(), "style Gram missing for a style layer");
       const double w = (double)sp.style_weight / ctx->n_styles;
-      rc = gram_full<T>(f, hf * wf, c, false, ctx->gram, ctx->part, ctx->part_floats,
-                        ctx->sm_count, s);
-      if (rc == ST_OK) rc = gram_delta(ctx->gram, it->second, ctx->delta, c, w, loss_accum, ctx->rs, s);
+      bool gram_done = false;
+      if constexpr (std::is_same<T, __nv_bfloat16>::value) {
+        if (gram_tc_ok(ctx->tc, c)) {
+          rc = gram_tc(ctx->tc, f, hf * wf, c, ctx->gram, ctx->part, ctx->part_floats, s);
+          gram_done = true;
+        }
+      }
+      if (!gram_done)
+        rc = gram_full<T>(f, hf * wf, c, false, ctx->gram, ctx->part, ctx->part_floats,
+                          ctx->sm_count, s);
       if (rc == ST_OK)
-        rc = style_grad<T>(f, ctx->delta, static_cast<T*>(ctx->sbuf), hf * wf, c, stats + 2,
-                           ctx->rs, s);
+        rc = gram_delta(ctx->gram, it->second, ctx->delta, ctx->delta_bf16, c, w, loss_accum,
+                        ctx->rs, s);
+      if (rc == ST_OK) {
+        if constexpr (std::is_same<T, __nv_bfloat16>::value) {
+          if (ctx->tc.enabled && ctx->tc.pair_kernel) {
+            int n_part = 0;
+            rc = gemm_abs_tc_pair(ctx->tc, f, ctx->delta_bf16, static_cast<T*>(ctx->sbuf), hf, wf, c,
+                                  ctx->abs_partials, &n_part, s);
+            if (rc == ST_OK) rc = sum_partials(ctx->abs_partials, n_part, stats + 2, s);
+          } else {
+            rc = style_grad<T>(f, ctx->delta, static_cast<T*>(ctx->sbuf), hf * wf, c, stats + 2,
+                               ctx->rs, s);
+          }
+        } else {
+          rc = style_grad<T>(f, ctx->delta, static_cast<T*>(ctx->sbuf), hf * wf, c, stats + 2,
+                             ctx->rs, s);
+        }
+      }
       if (rc == ST_OK)
         rc = inject_scaled<T>(inj, static_cast<const T*>(ctx->sbuf), n, (float)w, stats + 2,
                               accumulate, s);
@@ -441,6 +466,10 @@ int st_create(int device, int precision, int n_layers, const st_layer_desc* laye
   }
   int rc = dev_alloc(ctx, (void**)&ctx->gram, 512 * 512 * sizeof(float));
   if (rc == ST_OK) rc = dev_alloc(ctx, (void**)&ctx->delta, 512 * 512 * sizeof(float));
+  if (rc == ST_OK && precision == ST_PREC_BF16)
+    rc = dev_alloc(ctx, (void**)&ctx->delta_bf16, 512 * 512 * sizeof(__nv_bfloat16));
+  if (rc == ST_OK && precision == ST_PREC_BF16)
+    rc = dev_alloc(ctx, (void**)&ctx->abs_partials, 1024 * sizeof(double));
   ctx->part_floats = (size_t)16 << 20;
   if (rc == ST_OK) rc = dev_alloc(ctx, (void**)&ctx->part, ctx->part_floats * sizeof(float));
   if (rc == ST_OK) rc = dev_alloc(ctx, (void**)&ctx->scalars, 64 * sizeof(double));
@@ -469,6 +498,7 @@ int st_destroy(st_ctx* ctx) {
   for (BlobRt& b : ctx->blobs) cudaFree(b.act), cudaFree(b.inj);
   cudaFree(ctx->gbuf[0]), cudaFree(ctx->gbuf[1]), cudaFree(ctx->sbuf);
   cudaFree(ctx->gram), cudaFree(ctx->delta), cudaFree(ctx->part), cudaFree(ctx->scalars);
+  cudaFree(ctx->delta_bf16), cudaFree(ctx->abs_partials);
   cudaFree(ctx->rs.partials), cudaFree(ctx->rs.counter);
   for (auto& kv : ctx->contents) cudaFree(kv.second.nhwc);
   for (auto& kv : ctx->styles) cudaFree(kv.second);

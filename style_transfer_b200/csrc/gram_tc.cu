@@ -1,0 +1,337 @@
+// Gram matrix G = F^T F / (C * HW) on tcgen05 tensor cores (num_utils.py:143-147, the "C^T C" of the
+// north star) for bf16 NHWC features F [HW][C].
+//
+// GEMM view: D[i][j] = sum_p F[p][i] * F[p][j]: M = N = channels, K = pixels.  F is stored with the
+// channels contiguous, i.e. both operands are "MN-major": a TMA box of 64 pixels x 64 channels
+// (128-byte rows, SWIZZLE_128B) is exactly the canonical MN-major SW128 shared-memory layout
+//   ((8,n),(8,k)) : ((1,LBO),(8,SBO))   [units of 16 bytes]
+// with LBO = 8 KB (next 64-channel group = next box) and SBO = 1 KB (next 8 pixels).  One k-block
+// (64 pixels of all C channels) is loaded ONCE and serves as A (the 128 rows of this CTA's M block)
+// and as B (all C columns).
+//
+// The kernel is HBM-bound for C <= 256 (2*C flop per bf16 byte): the pixels are split over CTAs
+// (split-K), every CTA streams its share once, accumulates a [128][C] fp32 block in TMEM and writes
+// it to a partial buffer; gram_tc_finalize sums the partials in split order (deterministic, no float
+// atomics), scales and mirrors the lower triangle.
+//
+// Warps (192 threads): 0 = TMA producer, 1 = MMA issuer + TMEM owner, 2..5 = TMEM -> global.
+#include <cuda.h>
+
+#include <cstdlib>
+
+#include "style_b200.h"
+#include "common.cuh"
+#include "conv_tc.h"
+#include "kernels.h"
+
+namespace st {
+
+namespace {
+
+constexpr int kGThreads = 192;
+constexpr int kBoxBytes = 64 * 128;       // 64 pixels x 64 channels bf16
+constexpr uint32_t kSpinG = 1u << 26;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  for (uint32_t spin = 0;; ++spin) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (done) return;
+    if (spin > kSpinG) __trap();
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0,
+                                            int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                   smem_u32(dst_smem)),
+               "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                   smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
+                                       uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32"
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, "
+      "%20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+        "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+// MN-major SWIZZLE_128B descriptor: 64-element MN groups kBoxBytes apart (LBO), 8-row K groups
+// 1024 bytes apart (SBO).
+__device__ __forceinline__ uint64_t make_desc_mn(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)(kBoxBytes >> 4) << 16) |
+         ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+
+template <int C>
+struct GramCfg {
+  static constexpr int kGroups = C / 64;                              // boxes per k-block
+  static constexpr int kStageBytes = (kGroups < 2 ? 2 : kGroups) * kBoxBytes;
+  static constexpr int kStagesRaw = (200 * 1024) / kStageBytes;
+  static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
+  static constexpr int kMBlocks = C < 128 ? 1 : C / 128;
+  static constexpr int kN = C > 256 ? 256 : C;                        // columns per MMA
+  static constexpr int kNHalves = C / kN;
+  static constexpr int kTmemCols = C < 32 ? 32 : C;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
+  // c_format f32 | a,b bf16 | A and B MN-major | N | M = 128
+  static constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
+                                     ((uint32_t)(kN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+};
+
+struct GramArgs {
+  int hw;              // pixels
+  int kb_total;        // ceil(hw / 64)
+  int kb_per_split;
+  float* part;         // [nsplit][C][C] fp32 partial sums
+};
+
+template <int C>
+__global__ void __launch_bounds__(kGThreads, 1)
+gram_tc_kernel(const __grid_constant__ CUtensorMap map_f, const GramArgs a) {
+  using Cfg = GramCfg<C>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + Cfg::kStages;
+  uint64_t* tfull = bars + 2 * Cfg::kStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int mb = blockIdx.x % Cfg::kMBlocks, split = blockIdx.x / Cfg::kMBlocks;
+  const int kb_begin = split * a.kb_per_split;
+  const int kb_end = min(a.kb_total, kb_begin + a.kb_per_split);
+
+  if constexpr (C == 64) {
+    // rows 64..127 of the 128-row A operand read the second half of every stage: keep it zero
+    for (int i = threadIdx.x; i < Cfg::kStages * (kBoxBytes / 16); i += kGThreads) {
+      const int st = i / (kBoxBytes / 16), o = i % (kBoxBytes / 16);
+      *reinterpret_cast<uint4*>(smem + st * Cfg::kStageBytes + kBoxBytes + o * 16) =
+          make_uint4(0u, 0u, 0u, 0u);
+    }
+    fence_proxy_async();
+  }
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&map_f);
+    for (int i = 0; i < Cfg::kStages; ++i) mbar_init(&full[i], 1), mbar_init(&empty[i], 1);
+    mbar_init(tfull, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, Cfg::kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = kb_begin; kb < kb_end; ++kb) {
+        mbar_wait(&empty[stage], phase ^ 1);
+        mbar_expect_tx(&full[stage], Cfg::kGroups * kBoxBytes);
+        uint8_t* dst = smem + stage * Cfg::kStageBytes;
+#pragma unroll
+        for (int g = 0; g < Cfg::kGroups; ++g)
+          tma_load_2d(&map_f, &full[stage], dst + g * kBoxBytes, g * 64, kb * 64);
+        if (++stage == Cfg::kStages) stage = 0, phase ^= 1;
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = kb_begin; kb < kb_end; ++kb) {
+        mbar_wait(&full[stage], phase);
+        tc_fence_after();
+        const uint32_t base = smem_u32(smem + stage * Cfg::kStageBytes);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {               // 16 pixels of K per MMA: 2 KB down the box
+          const uint64_t da = make_desc_mn(base + (2 * mb) * kBoxBytes + k * 2048);
+#pragma unroll
+          for (int nh = 0; nh < Cfg::kNHalves; ++nh) {
+            const uint64_t db = make_desc_mn(base + nh * 4 * kBoxBytes + k * 2048);
+            tc_mma(tmem_base + nh * 256, da, db, Cfg::kIdesc, (kb != kb_begin || k != 0) ? 1u : 0u);
+          }
+        }
+        tc_commit(&empty[stage]);
+        if (++stage == Cfg::kStages) stage = 0, phase ^= 1;
+      }
+      tc_commit(tfull);
+    }
+  } else {
+    const int q = warp & 3;
+    const int m = q * 32 + lane;                       // row of this CTA's M block
+    const int row = mb * 128 + m;                      // channel i
+    if (kb_end > kb_begin) {
+      mbar_wait(tfull, 0);
+      tc_fence_after();
+    }
+    float* dst = a.part + ((size_t)split * C + row) * C;
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+    for (int cc = 0; cc < C / 32; ++cc) {
+      uint32_t r[32];
+      if (kb_end > kb_begin) {
+        tmem_ld32(taddr + cc * 32, r);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) r[i] = 0u;
+      }
+      if (row < C) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 4)
+          *reinterpret_cast<uint4*>(dst + cc * 32 + i) = make_uint4(r[i], r[i + 1], r[i + 2], r[i + 3]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, Cfg::kTmemCols);
+}
+
+// gram[i][j] = gram[j][i] = scale * sum_s part[s][max(i,j)][min(i,j)]
+__global__ void gram_tc_finalize_kernel(const float* __restrict__ part, int nsplit, int c,
+                                        double scale, float* __restrict__ gram) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= c * c) return;
+  const int i = idx / c, j = idx % c;
+  const int hi = i > j ? i : j, lo = i > j ? j : i;
+  double sum = 0.0;
+  for (int s = 0; s < nsplit; ++s) sum += (double)part[((size_t)s * c + hi) * c + lo];
+  gram[idx] = (float)(sum * scale);
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+template <int C>
+int launch_gram(TcContext& tc, const __nv_bfloat16* f, int hw, float* gram, float* part,
+                size_t part_floats, cudaStream_t s) {
+  using Cfg = GramCfg<C>;
+  CUtensorMap map_f;
+  {
+    cuuint64_t gdim[2] = {(cuuint64_t)C, (cuuint64_t)hw};
+    cuuint64_t gstride[1] = {(cuuint64_t)C * 2};
+    cuuint32_t box[2] = {64, 64}, estride[2] = {1, 1};
+    CUresult r = reinterpret_cast<EncodeTiledFn>(tc.encode_fn)(
+        &map_f, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(f), gdim, gstride,
+        box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      set_error("cuTensorMapEncodeTiled (gram) failed with CUresult " + std::to_string((int)r));
+      return ST_ERR_CUDA;
+    }
+  }
+  GramArgs a{};
+  a.hw = hw, a.kb_total = cdiv(hw, 64), a.part = part;
+  // split the pixels over the SMs, but keep the partial buffer (written + re-read) below ~8 MB
+  int nsplit = tc.sm_count / Cfg::kMBlocks;
+  const int cap_bytes = (int)(((size_t)8 << 20) / ((size_t)C * C * 4));
+  const int cap_buf = (int)(part_floats / ((size_t)C * C));
+  nsplit = nsplit > cap_bytes ? cap_bytes : nsplit;
+  nsplit = nsplit > cap_buf ? cap_buf : nsplit;
+  nsplit = nsplit > a.kb_total ? a.kb_total : nsplit;
+  nsplit = nsplit < 1 ? 1 : nsplit;
+  a.kb_per_split = cdiv(a.kb_total, nsplit);
+  nsplit = cdiv(a.kb_total, a.kb_per_split);
+  auto kern = gram_tc_kernel<C>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    ST_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  TimerScope ts(s, kTimeGram, 2.0 * C * C * hw);
+  ST_LAUNCH(kern, nsplit * Cfg::kMBlocks, kGThreads, Cfg::kSmemBytes, s, map_f, a);
+  ST_LAUNCH(gram_tc_finalize_kernel, cdiv((long)C * C, 256), 256, 0, s, part, nsplit, C,
+            1.0 / ((double)C * hw), gram);
+  return ST_OK;
+}
+
+}  // namespace
+
+bool gram_tc_ok(const TcContext& tc, int c) {
+  return tc.enabled && tc.pair_kernel && (c == 64 || c == 128 || c == 256 || c == 512);
+}
+
+int gram_tc(TcContext& tc, const __nv_bfloat16* f, int hw, int c, float* gram, float* part,
+            size_t part_floats, cudaStream_t s) {
+  switch (c) {
+    case 64: return launch_gram<64>(tc, f, hw, gram, part, part_floats, s);
+    case 128: return launch_gram<128>(tc, f, hw, gram, part, part_floats, s);
+    case 256: return launch_gram<256>(tc, f, hw, gram, part, part_floats, s);
+    case 512: return launch_gram<512>(tc, f, hw, gram, part, part_floats, s);
+  }
+  set_error("gram_tc: unsupported channel count");
+  return ST_ERR_INVALID;
+}
+
+}  // namespace st

@@ -51,8 +51,9 @@ template <typename T>
 int gram_full(const T* f, int hw, int c, bool channel_major, float* gram, float* part,
               size_t part_floats, int sm_count, cudaStream_t s);
 // delta = gram - target (both symmetric, full); *loss_accum += w * 0.5 * sum_{j<=i} delta_ij^2
-int gram_delta(const float* gram, const float* target, float* delta, int c, double w,
-               double* loss_accum, ReduceScratch rs, cudaStream_t s);
+int gram_delta(const float* gram, const float* target, float* delta, __nv_bfloat16* delta_bf16,
+               int c, double w, double* loss_accum, ReduceScratch rs, cudaStream_t s);
+int sum_partials(const double* partials, int n, double* out, cudaStream_t s);
 // S[p][co] = sum_ci F[p][ci] * delta[ci][co]; *sum_abs = sum |S|
 template <typename T>
 int style_grad(const T* f, const float* delta, T* s_out, int hw, int c, double* sum_abs,

@@ -489,22 +489,36 @@ int gram_full(const T* f, int hw, int c, bool channel_major, float* gram, float*
 
 // delta = G - G_style (symmetric); loss += w * 0.5 * sum_{j<=i} delta^2  (style_transfer.py:587,591)
 __global__ void gram_delta_kernel(const float* __restrict__ gram, const float* __restrict__ target,
-                                  float* __restrict__ delta, int c, double w, double* loss_accum,
-                                  ReduceScratch rs) {
+                                  float* __restrict__ delta, __nv_bfloat16* __restrict__ delta_bf16,
+                                  int c, double w, double* loss_accum, ReduceScratch rs) {
   double v[1] = {0.0};
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < c * c;
        idx += gridDim.x * blockDim.x) {
     const float d = gram[idx] - target[idx];
     delta[idx] = d;
+    if (delta_bf16 != nullptr) delta_bf16[idx] = __float2bfloat16_rn(d);
     if (idx % c <= idx / c) v[0] += (double)d * d;
   }
   if (grid_reduce<1>(v, rs.partials, rs.counter)) atomicAdd(loss_accum, w * 0.5 * v[0]);
 }
 
-int gram_delta(const float* gram, const float* target, float* delta, int c, double w,
-               double* loss_accum, ReduceScratch rs, cudaStream_t s) {
-  ST_LAUNCH(gram_delta_kernel, min(cdiv((long)c * c, 256), 256), 256, 0, s, gram, target, delta, c,
-            w, loss_accum, rs);
+int gram_delta(const float* gram, const float* target, float* delta, __nv_bfloat16* delta_bf16,
+               int c, double w, double* loss_accum, ReduceScratch rs, cudaStream_t s) {
+  ST_LAUNCH(gram_delta_kernel, min(cdiv((long)c * c, 256), 256), 256, 0, s, gram, target, delta,
+            delta_bf16, c, w, loss_accum, rs);
+  return ST_OK;
+}
+
+// out[0] = partials[0] + ... + partials[n-1], summed in index order by one warp (deterministic).
+__global__ void sum_partials_kernel(const double* __restrict__ partials, int n, double* out) {
+  double x = 0.0;
+  for (int i = threadIdx.x; i < n; i += 32) x += partials[i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+  if (threadIdx.x == 0) *out = x;
+}
+int sum_partials(const double* partials, int n, double* out, cudaStream_t s) {
+  ST_LAUNCH(sum_partials_kernel, 1, 32, 0, s, partials, n, out);
   return ST_OK;
 }
 
