@@ -39,29 +39,33 @@ inline bool tc_usable(const TcContext& tc, const TcWeights& w, int cin, int cout
   return false;
 }
 
-// out = epilogue(conv3x3(in)) with in [h][w][cin], out [h][w][cout] (bf16 NHWC).
+// out = epilogue(conv3x3(in)) with in [nb][h][w][cin], out [nb][h][w][cout] (bf16 NHWC).
 //   forward : out = max(acc + bias, 0)
 //   backward: out = (mask_act > 0 ? acc : 0) + inj   (either may be null)
 int conv3x3_tc(TcContext& tc, const TcWeights& w, const __nv_bfloat16* in, __nv_bfloat16* out,
-               int h, int wd, int cin, int cout, bool forward, const float* bias,
+               int nb, int h, int wd, int cin, int cout, bool forward, const float* bias,
                const __nv_bfloat16* mask_act, const __nv_bfloat16* inj, cudaStream_t s);
-// CTA-pair (cta_group::2) kernel of conv_tc2.cu: same contract as conv3x3_tc.
+// CTA-pair (cta_group::2) kernel of conv_tc2.cu; activations are [nb][h][w][c] (a batch of tiles).
 int conv3x3_tc_pair(TcContext& tc, const TcWeights& w, const __nv_bfloat16* in, __nv_bfloat16* out,
-                    int h, int wd, int cin, int cout, bool forward, const float* bias,
+                    int nb, int h, int wd, int cin, int cout, bool forward, const float* bias,
                     const __nv_bfloat16* mask_act, const __nv_bfloat16* inj, cudaStream_t s);
-// S[p][n] = sum_c F[p][c] * D[n][c] for F [h][w][c] (bf16 NHWC) and D [c][c] bf16; the sum of |S|
-// over the tiles of CTA i is written to abs_partials[i], i < *n_partials (<= sm_count).
+// Per batch tile b: S_b[p][n] = sum_c F_b[p][c] * D_b[n][c] for F [nb][h][w][c] and D [nb][c][c]
+// (bf16).  sum |S_b| is left as partial sums abs_partials[b * per_tile + i], i < *per_tile, to be
+// added in index order; the buffer must hold gemm_abs_partials_needed() doubles.
 int gemm_abs_tc_pair(TcContext& tc, const __nv_bfloat16* f, const __nv_bfloat16* d,
-                     __nv_bfloat16* s_out, int h, int w, int c, double* abs_partials,
-                     int* n_partials, cudaStream_t s);
+                     __nv_bfloat16* s_out, int nb, int h, int w, int c, double* abs_partials,
+                     int* per_tile, cudaStream_t s);
+size_t gemm_abs_partials_needed(int nb, int h, int w, int c);
 
-// gram[C][C] (full, symmetric, fp32) = F^T F / (C*hw) for bf16 NHWC F [hw][c] on tcgen05 (gram_tc.cu).
+// gram[b][C][C] (full, symmetric, fp32) = F_b^T F_b / (C*hw) for bf16 NHWC F [nb][hw][c] on tcgen05
+// (gram_tc.cu).  part: split-K scratch of gram_tc_part_floats() floats.
 bool gram_tc_ok(const TcContext& tc, int c);
-int gram_tc(TcContext& tc, const __nv_bfloat16* f, int hw, int c, float* gram, float* part,
-            size_t part_floats, cudaStream_t s);
+size_t gram_tc_part_floats(const TcContext& tc, int nb, int hw, int c);
+int gram_tc(TcContext& tc, const __nv_bfloat16* f, int nb, int hw, int c, float* gram, float* part,
+            cudaStream_t s);
 
-inline int conv3x3_tc(TcContext&, const TcWeights&, const float*, float*, int, int, int, int, bool,
-                      const float*, const float*, const float*, cudaStream_t) {
+inline int conv3x3_tc(TcContext&, const TcWeights&, const float*, float*, int, int, int, int, int,
+                      bool, const float*, const float*, const float*, cudaStream_t) {
   return -1;   // never reached: tc_usable<float> is false
 }
 

@@ -102,6 +102,14 @@ __device__ __forceinline__ void fence_proxy_async() {
 }
 // TMA loads issued by either CTA of the pair; completion bytes go to the barrier at `bar_cluster`
 // (a cluster address, the leader's barrier).
+__device__ __forceinline__ void tma_load_4d_pair(const CUtensorMap* map, uint32_t bar_cluster,
+                                                 void* dst, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
 __device__ __forceinline__ void tma_load_3d_pair(const CUtensorMap* map, uint32_t bar_cluster,
                                                  void* dst, int c0, int c1, int c2) {
   asm volatile(
@@ -110,20 +118,13 @@ __device__ __forceinline__ void tma_load_3d_pair(const CUtensorMap* map, uint32_
       "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
-__device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap* map, uint32_t bar_cluster,
-                                                 void* dst, int c0, int c1) {
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void* src, int c0, int c1,
+                                             int c2, int c3) {
   asm volatile(
-      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
-      " [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)),
-      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster), "r"(c0), "r"(c1)
+      "cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+          reinterpret_cast<uint64_t>(map)),
+      "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
-}
-__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void* src, int c0, int c1,
-                                             int c2) {
-  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::
-                   "l"(reinterpret_cast<uint64_t>(map)),
-               "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2)
-               : "memory");
 }
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;"); }
 template <int N>
@@ -190,13 +191,28 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
 }
 
 struct Tc2Args {
-  int h, w, cin, cout;
-  int tiles_x, tiles_y, tiles_n;   // pair tiles: 8 columns x 32 rows x BN channels
+  int nb, h, w, cin, cout;         // nb tiles of the batch, each [h][w]
+  int w_batched;                   // the B operand has one matrix per batch tile (style GEMM)
+  int tiles_x, tiles_y, tiles_n;   // pair tiles per batch tile: 8 columns x 32 rows x BN channels
   const float* bias;               // kEpiFwd
   const __nv_bfloat16* mask_act;   // kEpiBwd, NHWC [h][w][cout], may be null
   const __nv_bfloat16* inj;        // kEpiBwd, may be null
-  double* abs_partials;            // kEpiAbs: one double per CTA
+  double* abs_partials;            // kEpiAbs: [pair tile][cta rank][epilogue warp]
 };
+
+struct TileCoord {
+  int b, x0, y0, n_tile;
+};
+__device__ __forceinline__ TileCoord decode_tile(const Tc2Args& a, int tile, int rank) {
+  TileCoord t;
+  t.n_tile = tile % a.tiles_n;
+  int m = tile / a.tiles_n;
+  t.x0 = (m % a.tiles_x) * kBW;
+  m /= a.tiles_x;
+  t.y0 = (m % a.tiles_y) * (2 * kBH) + rank * kBH;
+  t.b = m / a.tiles_y;
+  return t;
+}
 
 template <int BN, int TAPS>
 struct Cfg2 {
@@ -235,13 +251,12 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constan
   uint64_t* t_full = b_empty + Cfg::kSB;
   uint64_t* t_empty = t_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
-  double* red = reinterpret_cast<double*>(t_empty + 4);       // 4 doubles (kEpiAbs)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_rank();
   const bool leader = rank == 0;
   const int kb_per_tap = a.cin >> 6;
-  const int num_tiles = a.tiles_x * a.tiles_y * a.tiles_n;
+  const int num_tiles = a.tiles_x * a.tiles_y * a.tiles_n * a.nb;
   const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
 
   if (warp == 0 && lane == 0) {
@@ -263,9 +278,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constan
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = pair; tile < num_tiles; tile += num_pairs) {
-        const int m_tile = tile / a.tiles_n;
-        const int x0 = (m_tile % a.tiles_x) * kBW;
-        const int y0 = (m_tile / a.tiles_x) * (2 * kBH) + (int)rank * kBH;
+        const TileCoord t = decode_tile(a, tile, (int)rank);
         for (int cb = 0; cb < kb_per_tap; ++cb) {
           mbar_wait(&a_empty[stage], phase ^ 1);
           if (leader) mbar_expect_tx(&a_full[stage], 2 * Cfg::kABytes);
@@ -274,9 +287,10 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constan
           if constexpr (TAPS == 9) {
 #pragma unroll
             for (int v = 0; v < 3; ++v)
-              tma_load_3d_pair(&map_in, bar, dst + v * Cfg::kAVarBytes, cb * 64, x0 + v - 1, y0 - 1);
+              tma_load_4d_pair(&map_in, bar, dst + v * Cfg::kAVarBytes, cb * 64, t.x0 + v - 1,
+                               t.y0 - 1, t.b);
           } else {
-            tma_load_3d_pair(&map_in, bar, dst, cb * 64, x0, y0);
+            tma_load_4d_pair(&map_in, bar, dst, cb * 64, t.x0, t.y0, t.b);
           }
           if (++stage == Cfg::kSA) stage = 0, phase ^= 1;
         }
@@ -288,13 +302,16 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constan
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = pair; tile < num_tiles; tile += num_pairs) {
-        const int n0 = (tile % a.tiles_n) * BN + (int)rank * (BN / 2);
+        const TileCoord t = decode_tile(a, tile, (int)rank);
+        const int n0 = t.n_tile * BN + (int)rank * (BN / 2);
+        const int wb = a.w_batched ? t.b : 0;
         for (int cb = 0; cb < kb_per_tap; ++cb) {
           for (int tap = 0; tap < TAPS; ++tap) {
             mbar_wait(&b_empty[stage], phase ^ 1);
             if (leader) mbar_expect_tx(&b_full[stage], 2 * Cfg::kBBytes);
             const uint32_t bar = map_to_cta(smem_u32(&b_full[stage]), 0);
-            tma_load_2d_pair(&map_w, bar, b_base + stage * Cfg::kBBytes, tap * a.cin + cb * 64, n0);
+            tma_load_3d_pair(&map_w, bar, b_base + stage * Cfg::kBBytes, tap * a.cin + cb * 64, n0,
+                             wb);
             if (++stage == Cfg::kSB) stage = 0, phase ^= 1;
           }
         }
@@ -339,16 +356,15 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constan
     const int q = warp & 3;                            // TMEM lane quadrant of this warp
     const int m = q * 32 + lane;                       // pixel row of the CTA tile
     const bool issuer = threadIdx.x == 64;
-    double abs_total = 0.0;
     uint32_t it = 0, store_seq = 0;
     for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
       const uint32_t buf = it & 1, use = it >> 1;
-      const int n_tile = tile % a.tiles_n, m_tile = tile / a.tiles_n;
-      const int x0 = (m_tile % a.tiles_x) * kBW;
-      const int y0 = (m_tile / a.tiles_x) * (2 * kBH) + (int)rank * kBH;
+      const TileCoord t = decode_tile(a, tile, (int)rank);
+      const int n_tile = t.n_tile, x0 = t.x0, y0 = t.y0;
       const int py = y0 + (m >> 3), px = x0 + (m & 7);
       const bool valid = py < a.h && px < a.w;
-      const size_t gofs = ((size_t)py * a.w + px) * a.cout + (size_t)n_tile * BN;
+      const size_t gofs =
+          (((size_t)t.b * a.h + py) * a.w + px) * a.cout + (size_t)n_tile * BN;
       float abs_tile = 0.f;
 
       mbar_wait(&t_full[buf], use & 1);
@@ -428,20 +444,20 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constan
         fence_proxy_async();
         asm volatile("bar.sync 1, 128;" ::: "memory");
         if (issuer) {
-          tma_store_3d(&map_out, stage_out, n_tile * BN + g * 64, x0, y0);
+          tma_store_4d(&map_out, stage_out, n_tile * BN + g * 64, x0, y0, t.b);
           tma_store_commit();
         }
       }
-      if constexpr (EPI == kEpiAbs) abs_total += (double)abs_tile;
+      if constexpr (EPI == kEpiAbs) {
+        // sum |S| of this warp's 32 rows of the tile: one slot per (tile, CTA, warp), summed later
+        // in index order (deterministic whatever the tile -> CTA schedule)
+        double x = (double)abs_tile;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+        if (lane == 0) a.abs_partials[((size_t)tile * 2 + rank) * 4 + q] = x;
+      }
     }
     if (issuer) tma_store_wait_all();
-    if constexpr (EPI == kEpiAbs) {
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) abs_total += __shfl_xor_sync(0xffffffffu, abs_total, o);
-      if (lane == 0) red[q] = abs_total;
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (issuer) a.abs_partials[blockIdx.x] = red[0] + red[1] + red[2] + red[3];
-    }
   }
 
   tc_fence_before();
@@ -457,8 +473,8 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 
 int encode_bf16_map(const TcContext& tc, CUtensorMap* map, int rank, const void* base,
                     const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box) {
-  cuuint64_t gdim[3], gstride[2];
-  cuuint32_t bdim[3], estride[3] = {1, 1, 1};
+  cuuint64_t gdim[4], gstride[3];
+  cuuint32_t bdim[4], estride[4] = {1, 1, 1, 1};
   for (int i = 0; i < rank; ++i) gdim[i] = dims[i], bdim[i] = box[i];
   for (int i = 0; i + 1 < rank; ++i) gstride[i] = strides_bytes[i];
   CUresult r = reinterpret_cast<EncodeTiledFn>(tc.encode_fn)(
@@ -479,24 +495,27 @@ int launch2(TcContext& tc, const __nv_bfloat16* in, const __nv_bfloat16* wk, int
   a.tiles_x = cdiv(a.w, kBW), a.tiles_y = cdiv(a.h, 2 * kBH), a.tiles_n = a.cout / BN;
   CUtensorMap map_in, map_out, map_w;
   {
-    const uint64_t dims[3] = {(uint64_t)a.cin, (uint64_t)a.w, (uint64_t)a.h};
-    const uint64_t strides[2] = {(uint64_t)a.cin * 2, (uint64_t)a.w * a.cin * 2};
-    const uint32_t box[3] = {64, (uint32_t)kBW, (uint32_t)Cfg::kHaloRows};
-    int rc = encode_bf16_map(tc, &map_in, 3, in, dims, strides, box);
+    const uint64_t dims[4] = {(uint64_t)a.cin, (uint64_t)a.w, (uint64_t)a.h, (uint64_t)a.nb};
+    const uint64_t strides[3] = {(uint64_t)a.cin * 2, (uint64_t)a.w * a.cin * 2,
+                                 (uint64_t)a.h * a.w * a.cin * 2};
+    const uint32_t box[4] = {64, (uint32_t)kBW, (uint32_t)Cfg::kHaloRows, 1};
+    int rc = encode_bf16_map(tc, &map_in, 4, in, dims, strides, box);
     if (rc != ST_OK) return rc;
   }
   {
-    const uint64_t dims[3] = {(uint64_t)a.cout, (uint64_t)a.w, (uint64_t)a.h};
-    const uint64_t strides[2] = {(uint64_t)a.cout * 2, (uint64_t)a.w * a.cout * 2};
-    const uint32_t box[3] = {64, (uint32_t)kBW, (uint32_t)kBH};
-    int rc = encode_bf16_map(tc, &map_out, 3, out, dims, strides, box);
+    const uint64_t dims[4] = {(uint64_t)a.cout, (uint64_t)a.w, (uint64_t)a.h, (uint64_t)a.nb};
+    const uint64_t strides[3] = {(uint64_t)a.cout * 2, (uint64_t)a.w * a.cout * 2,
+                                 (uint64_t)a.h * a.w * a.cout * 2};
+    const uint32_t box[4] = {64, (uint32_t)kBW, (uint32_t)kBH, 1};
+    int rc = encode_bf16_map(tc, &map_out, 4, out, dims, strides, box);
     if (rc != ST_OK) return rc;
   }
   {
-    const uint64_t dims[2] = {(uint64_t)TAPS * a.cin, (uint64_t)wk_rows};
-    const uint64_t strides[1] = {(uint64_t)TAPS * a.cin * 2};
-    const uint32_t box[2] = {64, (uint32_t)(BN / 2)};
-    int rc = encode_bf16_map(tc, &map_w, 2, wk, dims, strides, box);
+    const uint64_t k = (uint64_t)TAPS * a.cin;
+    const uint64_t dims[3] = {k, (uint64_t)wk_rows, (uint64_t)(a.w_batched ? a.nb : 1)};
+    const uint64_t strides[2] = {k * 2, k * 2 * wk_rows};
+    const uint32_t box[3] = {64, (uint32_t)(BN / 2), 1};
+    int rc = encode_bf16_map(tc, &map_w, 3, wk, dims, strides, box);
     if (rc != ST_OK) return rc;
   }
   auto kern = conv_tc2_kernel<BN, TAPS, EPI>;
@@ -506,19 +525,19 @@ int launch2(TcContext& tc, const __nv_bfloat16* in, const __nv_bfloat16* wk, int
                                  Cfg::kSmemBytes));
     attr_set = true;
   }
-  const int tiles = a.tiles_x * a.tiles_y * a.tiles_n;
+  const int tiles = a.tiles_x * a.tiles_y * a.tiles_n * a.nb;
   const int max_pairs = tc.sm_count / 2;
   const int pairs = tiles < max_pairs ? tiles : max_pairs;
   TimerScope ts(s, EPI == kEpiAbs ? kTimeStyleGrad : kTimeConvTc,
-                2.0 * TAPS * a.cin * a.cout * a.h * a.w);
+                2.0 * TAPS * a.cin * a.cout * a.h * a.w * a.nb);
   ST_LAUNCH(kern, 2 * pairs, kThreads2, Cfg::kSmemBytes, s, map_in, map_w, map_out, a);
   return ST_OK;
 }
 
 // Output-channel tile: the widest BN that still gives every CTA pair work; wide tiles halve the
 // weight traffic per flop, narrow ones fill the machine on the small feature maps.
-int choose_bn(const TcContext& tc, int h, int w, int cout) {
-  const int px_tiles = cdiv(w, kBW) * cdiv(h, 2 * kBH), pairs = tc.sm_count / 2;
+int choose_bn(const TcContext& tc, int nb, int h, int w, int cout) {
+  const int px_tiles = cdiv(w, kBW) * cdiv(h, 2 * kBH) * nb, pairs = tc.sm_count / 2;
   if (const char* f = getenv("ST_TC_BN")) {
     const int bn = atoi(f);
     if ((bn == 64 || bn == 128 || bn == 256) && cout % bn == 0) return bn;
@@ -544,29 +563,31 @@ int dispatch_bn(TcContext& tc, int bn, const __nv_bfloat16* in, const __nv_bfloa
 }  // namespace
 
 int conv3x3_tc_pair(TcContext& tc, const TcWeights& w, const __nv_bfloat16* in, __nv_bfloat16* out,
-                    int h, int wd, int cin, int cout, bool forward, const float* bias,
+                    int nb, int h, int wd, int cin, int cout, bool forward, const float* bias,
                     const __nv_bfloat16* mask_act, const __nv_bfloat16* inj, cudaStream_t s) {
   Tc2Args a{};
-  a.h = h, a.w = wd, a.cin = cin, a.cout = cout;
+  a.nb = nb, a.h = h, a.w = wd, a.cin = cin, a.cout = cout;
   a.bias = bias, a.mask_act = mask_act, a.inj = inj;
-  const int bn = choose_bn(tc, h, wd, cout);
+  const int bn = choose_bn(tc, nb, h, wd, cout);
   if (forward) return dispatch_bn<9, kEpiFwd>(tc, bn, in, w.fwd, cout, out, a, s);
   return dispatch_bn<9, kEpiBwd>(tc, bn, in, w.bwd, cout, out, a, s);
 }
 
-// S[p][n] = sum_c F[p][c] * D[n][c]  (D symmetric bf16 [c][c]); abs_partials[i] receives the sum
-// of |S| over the tiles of CTA i; *n_partials = number of CTAs launched.
+// Per batch tile b: S_b[p][n] = sum_c F_b[p][c] * D_b[n][c]  (D_b symmetric bf16 [c][c]).  The sum
+// of |S_b| is left as partial sums: abs_partials[b * per_tile + i], i < *per_tile.
 int gemm_abs_tc_pair(TcContext& tc, const __nv_bfloat16* f, const __nv_bfloat16* d,
-                     __nv_bfloat16* s_out, int hw_rows, int hw_cols, int c, double* abs_partials,
-                     int* n_partials, cudaStream_t s) {
+                     __nv_bfloat16* s_out, int nb, int h, int w, int c, double* abs_partials,
+                     int* per_tile, cudaStream_t s) {
   Tc2Args a{};
-  a.h = hw_rows, a.w = hw_cols, a.cin = c, a.cout = c;
+  a.nb = nb, a.h = h, a.w = w, a.cin = c, a.cout = c, a.w_batched = 1;
   a.abs_partials = abs_partials;
-  const int bn = choose_bn(tc, hw_rows, hw_cols, c);
-  const int tiles = cdiv(hw_cols, kBW) * cdiv(hw_rows, 2 * kBH) * (c / bn);
-  const int max_pairs = tc.sm_count / 2;
-  *n_partials = 2 * (tiles < max_pairs ? tiles : max_pairs);
+  const int bn = choose_bn(tc, nb, h, w, c);
+  *per_tile = cdiv(w, kBW) * cdiv(h, 2 * kBH) * (c / bn) * 8;
   return dispatch_bn<1, kEpiAbs>(tc, bn, f, d, c, s_out, a, s);
+}
+
+size_t gemm_abs_partials_needed(int nb, int h, int w, int c) {
+  return (size_t)nb * cdiv(w, kBW) * cdiv(h, 2 * kBH) * (c / 64) * 8;
 }
 
 }  // namespace st

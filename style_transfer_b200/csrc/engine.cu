@@ -89,11 +89,14 @@ struct st_ctx {
   void* gbuf[2] = {nullptr, nullptr};
   void* sbuf = nullptr;
   size_t gcap = 0;           // elements of gbuf[i] / sbuf
+  // per batch tile: Gram [C][C], its difference to the target (fp32 and the bf16 copy that is the
+  // B operand of the tcgen05 style GEMM)
   float *gram = nullptr, *delta = nullptr, *part = nullptr;
-  __nv_bfloat16* delta_bf16 = nullptr;   // bf16 copy of delta: B operand of the tcgen05 style GEMM
-  double* abs_partials = nullptr;        // per-CTA sum |S| of that GEMM (sm_count doubles)
-  size_t part_floats = 0;
-  double* scalars = nullptr; // 64 device doubles
+  __nv_bfloat16* delta_bf16 = nullptr;
+  double* abs_partials = nullptr;        // partial sums of |S| of the style GEMM
+  size_t part_floats = 0, abs_cap = 0;
+  int max_batch = 1;                     // tiles evaluated per launch (1 in fp32 mode)
+  double* scalars = nullptr;             // [kMaxBatch][kStatStride] device doubles
   ReduceScratch rs{nullptr, nullptr};
   std::map<std::pair<int, int>, ContentTarget> contents;   // (content index, blob)
   std::map<std::pair<int, int>, float*> styles;            // (style index, blob) -> full [C][C]
@@ -165,11 +168,11 @@ Dims blob_dims(const st_ctx* ctx, int h, int w) {
   return d;
 }
 
-int reserve_for(st_ctx* ctx, const Dims& d, int last_layer) {
+int reserve_for(st_ctx* ctx, const Dims& d, int last_layer, int nb) {
   size_t gmax = 0;
   for (int i = 0; i <= last_layer; ++i) {
     const int b = ctx->layers[i].top;
-    const size_t n = (size_t)d.h[b] * d.w[b] * ctx->blobs[b].c;
+    const size_t n = (size_t)nb * d.h[b] * d.w[b] * ctx->blobs[b].c;
     int rc = ensure(ctx, &ctx->blobs[b].act, &ctx->blobs[b].act_cap, n, ctx->esize);
     if (rc != ST_OK) return rc;
     gmax = std::max(gmax, n);
@@ -185,9 +188,13 @@ int reserve_for(st_ctx* ctx, const Dims& d, int last_layer) {
   return ST_OK;
 }
 
+constexpr int kStatStride = 8;   // doubles per batch tile in ctx->scalars:
+                                 //   [0] sum c^2  [1] sum |c|  [2] sum |S|  [3] the tile's loss
+
 // ---- forward -------------------------------------------------------------------------------------
 template <typename T>
-int forward(st_ctx* ctx, const ImageView& view, const Dims& d, int last_layer, cudaStream_t s) {
+int forward(st_ctx* ctx, const ImageBatch& view, const Dims& d, int last_layer, cudaStream_t s) {
+  const int nb = view.nb;
   for (int i = 0; i <= last_layer; ++i) {
     const LayerRt& l = ctx->layers[i];
     const int hb = d.h[l.bottom], wb = d.w[l.bottom];
@@ -200,14 +207,14 @@ int forward(st_ctx* ctx, const ImageView& view, const Dims& d, int last_layer, c
       } else {
         const T* in = static_cast<const T*>(ctx->blobs[l.bottom].act);
         if (tc_usable<T>(ctx->tc, l.tc, l.cin, l.cout))
-          rc = conv3x3_tc(ctx->tc, l.tc, in, out, hb, wb, l.cin, l.cout, true, l.bias, nullptr,
+          rc = conv3x3_tc(ctx->tc, l.tc, in, out, nb, hb, wb, l.cin, l.cout, true, l.bias, nullptr,
                           nullptr, s);
         else
-          rc = conv3x3_simt<T>(in, l.w_fwd, l.bias, out, hb, wb, l.cin, l.cout, true, nullptr,
+          rc = conv3x3_simt<T>(in, l.w_fwd, l.bias, out, nb, hb, wb, l.cin, l.cout, true, nullptr,
                                nullptr, s);
       }
     } else {
-      rc = pool_fwd<T>(static_cast<const T*>(ctx->blobs[l.bottom].act), out, hb, wb, l.cin,
+      rc = pool_fwd<T>(static_cast<const T*>(ctx->blobs[l.bottom].act), out, nb, hb, wb, l.cin,
                        l.kind == ST_POOL_MAX, s);
     }
     if (rc != ST_OK) return rc;
@@ -216,18 +223,25 @@ int forward(st_ctx* ctx, const ImageView& view, const Dims& d, int last_layer, c
 }
 
 // ---- loss terms -> injected gradients ----------------------------------------------------------------
+// Geometry of one batch: nb tiles of h x w pixels cut out of one image.
+struct BatchGeom {
+  int nb;
+  int start_y[kMaxBatch], start_x[kMaxBatch];   // tile origin in the rolled image (`start`, :572)
+};
+
 template <typename T>
-int build_injection(st_ctx* ctx, const st_loss_spec& sp, const Dims& d, int start_y, int start_x,
-                    int froll_y, int froll_x, double* loss_accum, cudaStream_t s) {
+int build_injection(st_ctx* ctx, const st_loss_spec& sp, const Dims& d, const BatchGeom& g,
+                    int froll_y, int froll_x, cudaStream_t s) {
   BlobRt& b = ctx->blobs[sp.blob];
-  const int hf = d.h[sp.blob], wf = d.w[sp.blob], c = b.c;
-  const size_t n = (size_t)hf * wf * c;
-  int rc = ensure(ctx, &b.inj, &b.inj_cap, n, ctx->esize);
+  const int nb = g.nb, hf = d.h[sp.blob], wf = d.w[sp.blob], c = b.c;
+  const size_t n = (size_t)hf * wf * c;            // elements per tile
+  int rc = ensure(ctx, &b.inj, &b.inj_cap, n * nb, ctx->esize);
   if (rc != ST_OK) return rc;
   T* inj = static_cast<T*>(b.inj);
   const T* f = static_cast<const T*>(b.act);
   bool accumulate = false;
-  double* stats = ctx->scalars;          // [0..1] content/dd stats, [2] sum|S|
+  double* stats = ctx->scalars;          // per tile: [0..1] content/dd stats, [2] sum|S|, [3] loss
+  double* tile_loss = ctx->scalars + 3;
 
   if (sp.use_content) {
     ST_REQUIRE(ctx->n_contents > 0, "content layer requested but no content features set");
@@ -235,15 +249,19 @@ int build_injection(st_ctx* ctx, const st_loss_spec& sp, const Dims& d, int star
       auto it = ctx->contents.find({ci, sp.blob});
       ST_REQUIRE(it != ctx->contents.end(), "content features missing for a content layer");
       const ContentTarget& t = it->second;
-      const int s0y = start_y / b.scale, s0x = start_x / b.scale;
-      // the reference slices [s0 : s0 + hf] out of the full map; a short slice is a shape error
-      ST_REQUIRE(s0y + hf <= t.hf && s0x + wf <= t.wf,
-                 "tile feature map does not fit into the content feature map at this offset");
-      const int ty0 = s0y - floordiv(froll_y, b.scale), tx0 = s0x - floordiv(froll_x, b.scale);
-      rc = diff_stats<T>(f, hf, wf, c, t.nhwc, t.hf, t.wf, ty0, tx0, stats, ctx->rs, s);
+      TargetOffsets offs{};
+      for (int i = 0; i < nb; ++i) {
+        const int s0y = g.start_y[i] / b.scale, s0x = g.start_x[i] / b.scale;
+        // the reference slices [s0 : s0 + hf] out of the full map; a short slice is a shape error
+        ST_REQUIRE(s0y + hf <= t.hf && s0x + wf <= t.wf,
+                   "tile feature map does not fit into the content feature map at this offset");
+        offs.ty0[i] = s0y - floordiv(froll_y, b.scale), offs.tx0[i] = s0x - floordiv(froll_x, b.scale);
+      }
+      rc = diff_stats<T>(f, nb, hf, wf, c, t.nhwc, t.hf, t.wf, offs, stats, kStatStride, ctx->rs, s);
       if (rc == ST_OK)
-        rc = diff_inject<T>(f, hf, wf, c, t.nhwc, t.hf, t.wf, ty0, tx0, stats, sp.content_weight,
-                            (double)sp.content_weight, loss_accum, inj, accumulate, s);
+        rc = diff_inject<T>(f, nb, hf, wf, c, t.nhwc, t.hf, t.wf, offs, stats, kStatStride,
+                            sp.content_weight, (double)sp.content_weight, tile_loss, kStatStride,
+                            inj, accumulate, s);
       if (rc != ST_OK) return rc;
       accumulate = true;
     }
@@ -255,58 +273,63 @@ int build_injection(st_ctx* ctx, const st_loss_spec& sp, const Dims& d, int star
       auto it = ctx->styles.find({si, sp.blob});
       ST_REQUIRE(it != ctx->styles.end(), "style Gram missing for a style layer");
       const double w = (double)sp.style_weight / ctx->n_styles;
-      bool gram_done = false;
-      if constexpr (std::is_same<T, __nv_bfloat16>::value) {
-        if (gram_tc_ok(ctx->tc, c)) {
-          rc = gram_tc(ctx->tc, f, hf * wf, c, ctx->gram, ctx->part, ctx->part_floats, s);
-          gram_done = true;
+      bool on_tc = false;
+      if constexpr (std::is_same<T, __nv_bfloat16>::value) on_tc = gram_tc_ok(ctx->tc, c);
+      if (on_tc) {
+        if constexpr (std::is_same<T, __nv_bfloat16>::value) {
+          size_t cap = ctx->part_floats;
+          rc = ensure(ctx, (void**)&ctx->part, &cap, gram_tc_part_floats(ctx->tc, nb, hf * wf, c), 4);
+          ctx->part_floats = cap;
+          if (rc == ST_OK) rc = gram_tc(ctx->tc, f, nb, hf * wf, c, ctx->gram, ctx->part, s);
         }
-      }
-      if (!gram_done)
+      } else {
+        ST_REQUIRE(nb == 1, "the SIMT Gram kernel takes one tile at a time");
         rc = gram_full<T>(f, hf * wf, c, false, ctx->gram, ctx->part, ctx->part_floats,
                           ctx->sm_count, s);
-      if (rc == ST_OK)
-        rc = gram_delta(ctx->gram, it->second, ctx->delta, ctx->delta_bf16, c, w, loss_accum,
-                        ctx->rs, s);
-      if (rc == ST_OK) {
-        if constexpr (std::is_same<T, __nv_bfloat16>::value) {
-          if (ctx->tc.enabled && ctx->tc.pair_kernel) {
-            int n_part = 0;
-            rc = gemm_abs_tc_pair(ctx->tc, f, ctx->delta_bf16, static_cast<T*>(ctx->sbuf), hf, wf, c,
-                                  ctx->abs_partials, &n_part, s);
-            if (rc == ST_OK) rc = sum_partials(ctx->abs_partials, n_part, stats + 2, s);
-          } else {
-            rc = style_grad<T>(f, ctx->delta, static_cast<T*>(ctx->sbuf), hf * wf, c, stats + 2,
-                               ctx->rs, s);
-          }
-        } else {
-          rc = style_grad<T>(f, ctx->delta, static_cast<T*>(ctx->sbuf), hf * wf, c, stats + 2,
-                             ctx->rs, s);
-        }
       }
       if (rc == ST_OK)
-        rc = inject_scaled<T>(inj, static_cast<const T*>(ctx->sbuf), n, (float)w, stats + 2,
-                              accumulate, s);
+        rc = gram_delta(ctx->gram, it->second, ctx->delta, ctx->delta_bf16, c, nb, w, tile_loss,
+                        kStatStride, ctx->rs, s);
+      if (rc != ST_OK) return rc;
+      if (on_tc) {
+        if constexpr (std::is_same<T, __nv_bfloat16>::value) {
+          int per_tile = 0;
+          rc = ensure(ctx, (void**)&ctx->abs_partials, &ctx->abs_cap,
+                      gemm_abs_partials_needed(nb, hf, wf, c), sizeof(double));
+          if (rc == ST_OK)
+            rc = gemm_abs_tc_pair(ctx->tc, f, ctx->delta_bf16, static_cast<T*>(ctx->sbuf), nb, hf, wf,
+                                  c, ctx->abs_partials, &per_tile, s);
+          if (rc == ST_OK)
+            rc = sum_partials(ctx->abs_partials, per_tile, nb, stats + 2, kStatStride, s);
+        }
+      } else {
+        rc = style_grad<T>(f, ctx->delta, static_cast<T*>(ctx->sbuf), hf * wf, c, stats + 2,
+                           ctx->rs, s);
+      }
+      if (rc == ST_OK)
+        rc = inject_scaled<T>(inj, static_cast<const T*>(ctx->sbuf), n, nb, (float)w, stats + 2,
+                              kStatStride, accumulate, s);
       if (rc != ST_OK) return rc;
       accumulate = true;
     }
   }
   if (sp.use_dd) {
-    rc = diff_stats<T>(f, hf, wf, c, nullptr, 1, 1, 0, 0, stats, ctx->rs, s);
+    TargetOffsets offs{};
+    rc = diff_stats<T>(f, nb, hf, wf, c, nullptr, 1, 1, offs, stats, kStatStride, ctx->rs, s);
     if (rc == ST_OK)
-      rc = diff_inject<T>(f, hf, wf, c, nullptr, 1, 1, 0, 0, stats, -sp.dd_weight,
-                          -(double)sp.dd_weight, loss_accum, inj, accumulate, s);
+      rc = diff_inject<T>(f, nb, hf, wf, c, nullptr, 1, 1, offs, stats, kStatStride, -sp.dd_weight,
+                          -(double)sp.dd_weight, tile_loss, kStatStride, inj, accumulate, s);
     if (rc != ST_OK) return rc;
     accumulate = true;
   }
-  if (!accumulate) ST_CUDA(cudaMemsetAsync(inj, 0, n * ctx->esize, s));
+  if (!accumulate) ST_CUDA(cudaMemsetAsync(inj, 0, n * nb * ctx->esize, s));
   return ST_OK;
 }
 
 // ---- backward chain to the pixels ----------------------------------------------------------------------
 template <typename T>
-int backward(st_ctx* ctx, const Dims& d, int deepest_blob, const std::vector<char>& has_inj,
-             float* grad, long plane, long rstride, cudaStream_t s) {
+int backward(st_ctx* ctx, const Dims& d, int nb, int deepest_blob, const std::vector<char>& has_inj,
+             float* grad, long batch_stride, long plane, long rstride, cudaStream_t s) {
   int cur = deepest_blob, pp = 0;
   const T* g = static_cast<const T*>(ctx->blobs[cur].inj);
   while (true) {
@@ -314,7 +337,7 @@ int backward(st_ctx* ctx, const Dims& d, int deepest_blob, const std::vector<cha
     const int b = l.bottom;
     const int hb = d.h[b], wb = d.w[b];
     if (l.kind == ST_CONV3X3 && b == 0)
-      return conv_last_bwd<T>(g, hb, wb, l.cout, l.w_bwd, grad, plane, rstride, s);
+      return conv_last_bwd<T>(g, nb, hb, wb, l.cout, l.w_bwd, grad, batch_stride, plane, rstride, s);
     ST_REQUIRE(b != 0, "a pooling layer directly on the image is not supported");
     const BlobRt& bb = ctx->blobs[b];
     const T* mask = bb.relu ? static_cast<const T*>(bb.act) : nullptr;
@@ -323,11 +346,13 @@ int backward(st_ctx* ctx, const Dims& d, int deepest_blob, const std::vector<cha
     int rc;
     if (l.kind == ST_CONV3X3) {
       if (tc_usable<T>(ctx->tc, l.tc, l.cout, l.cin))
-        rc = conv3x3_tc(ctx->tc, l.tc, g, out, hb, wb, l.cout, l.cin, false, nullptr, mask, inj, s);
+        rc = conv3x3_tc(ctx->tc, l.tc, g, out, nb, hb, wb, l.cout, l.cin, false, nullptr, mask, inj,
+                        s);
       else
-        rc = conv3x3_simt<T>(g, l.w_bwd, nullptr, out, hb, wb, l.cout, l.cin, false, mask, inj, s);
+        rc = conv3x3_simt<T>(g, l.w_bwd, nullptr, out, nb, hb, wb, l.cout, l.cin, false, mask, inj,
+                             s);
     } else {
-      rc = pool_bwd<T>(g, static_cast<const T*>(bb.act), out, hb, wb, l.cin,
+      rc = pool_bwd<T>(g, static_cast<const T*>(bb.act), out, nb, hb, wb, l.cin,
                        l.kind == ST_POOL_MAX, bb.relu, inj, s);
     }
     if (rc != ST_OK) return rc;
@@ -335,12 +360,15 @@ int backward(st_ctx* ctx, const Dims& d, int deepest_blob, const std::vector<cha
   }
 }
 
+// One batch of equally sized tiles: forward, loss terms, backward.  The gradient of tile i goes to
+// grad + i * batch_stride.
 template <typename T>
-int eval_tile(st_ctx* ctx, const ImageView& view, int h, int w, int start_y, int start_x,
-              int froll_y, int froll_x, int n_specs, const st_loss_spec* specs, double* loss_accum,
-              float* grad, long plane, long rstride, cudaStream_t s) {
+int eval_batch(st_ctx* ctx, const ImageBatch& view, int h, int w, const BatchGeom& g, int froll_y,
+               int froll_x, int n_specs, const st_loss_spec* specs, double* loss_accum, float* grad,
+               long batch_stride, long plane, long rstride, cudaStream_t s) {
   ST_REQUIRE(n_specs > 0 && specs != nullptr, "no loss layers");
   ST_REQUIRE(h > 0 && w > 0, "empty tile");
+  ST_REQUIRE(g.nb >= 1 && g.nb <= ctx->max_batch, "batch larger than the context allows");
   const int nb = (int)ctx->blobs.size();
   int deepest = -1;
   std::vector<char> has_inj(nb, 0);
@@ -360,22 +388,25 @@ int eval_tile(st_ctx* ctx, const ImageView& view, int h, int w, int start_y, int
   }
   const int last_layer = ctx->blobs[deepest].producer;
   const Dims d = blob_dims(ctx, h, w);
-  int rc = reserve_for(ctx, d, last_layer);
+  int rc = reserve_for(ctx, d, last_layer, g.nb);
   if (rc == ST_OK) rc = forward<T>(ctx, view, d, last_layer, s);
   for (int i = 0; i < n_specs && rc == ST_OK; ++i)
-    rc = build_injection<T>(ctx, specs[i], d, start_y, start_x, froll_y, froll_x, loss_accum, s);
-  if (rc == ST_OK) rc = backward<T>(ctx, d, deepest, has_inj, grad, plane, rstride, s);
+    rc = build_injection<T>(ctx, specs[i], d, g, froll_y, froll_x, s);
+  if (rc == ST_OK) rc = loss_finalize(ctx->scalars + 3, kStatStride, g.nb, loss_accum, s);
+  if (rc == ST_OK)
+    rc = backward<T>(ctx, d, g.nb, deepest, has_inj, grad, batch_stride, plane, rstride, s);
   return rc;
 }
 
-int eval_tile_any(st_ctx* ctx, const ImageView& view, int h, int w, int start_y, int start_x,
-                  int froll_y, int froll_x, int n_specs, const st_loss_spec* specs,
-                  double* loss_accum, float* grad, long plane, long rstride, cudaStream_t s) {
+int eval_batch_any(st_ctx* ctx, const ImageBatch& view, int h, int w, const BatchGeom& g,
+                   int froll_y, int froll_x, int n_specs, const st_loss_spec* specs,
+                   double* loss_accum, float* grad, long batch_stride, long plane, long rstride,
+                   cudaStream_t s) {
   if (ctx->precision == ST_PREC_FP32)
-    return eval_tile<float>(ctx, view, h, w, start_y, start_x, froll_y, froll_x, n_specs, specs,
-                            loss_accum, grad, plane, rstride, s);
-  return eval_tile<__nv_bfloat16>(ctx, view, h, w, start_y, start_x, froll_y, froll_x, n_specs,
-                                  specs, loss_accum, grad, plane, rstride, s);
+    return eval_batch<float>(ctx, view, h, w, g, froll_y, froll_x, n_specs, specs, loss_accum, grad,
+                             batch_stride, plane, rstride, s);
+  return eval_batch<__nv_bfloat16>(ctx, view, h, w, g, froll_y, froll_x, n_specs, specs, loss_accum,
+                                   grad, batch_stride, plane, rstride, s);
 }
 
 struct Grid {
@@ -464,21 +495,31 @@ int st_create(int device, int precision, int n_layers, const st_layer_desc* laye
     t.c = ld.cout, t.producer = i, t.relu = ld.kind == ST_CONV3X3;
     t.scale = ctx->blobs[ld.bottom].scale * (ld.kind == ST_CONV3X3 ? 1 : 2);
   }
-  int rc = dev_alloc(ctx, (void**)&ctx->gram, 512 * 512 * sizeof(float));
-  if (rc == ST_OK) rc = dev_alloc(ctx, (void**)&ctx->delta, 512 * 512 * sizeof(float));
+  int rc = ST_OK;
+  if (precision == ST_PREC_BF16) rc = tc_init(ctx->tc, ctx->sm_count);
+  // tiles of one shape are evaluated as a batch by the tensor-core kernels; the fp32 SIMT parity
+  // path keeps the reference's one-tile-at-a-time order
+  ctx->max_batch = (precision == ST_PREC_BF16 && ctx->tc.enabled && ctx->tc.pair_kernel) ? kMaxBatch : 1;
+  if (const char* e = getenv("ST_MAX_BATCH")) {
+    const int v = atoi(e);
+    if (v >= 1 && v < ctx->max_batch) ctx->max_batch = v;
+  }
+  const size_t gram_floats = (size_t)ctx->max_batch * 512 * 512;
+  if (rc == ST_OK) rc = dev_alloc(ctx, (void**)&ctx->gram, gram_floats * sizeof(float));
+  if (rc == ST_OK) rc = dev_alloc(ctx, (void**)&ctx->delta, gram_floats * sizeof(float));
   if (rc == ST_OK && precision == ST_PREC_BF16)
-    rc = dev_alloc(ctx, (void**)&ctx->delta_bf16, 512 * 512 * sizeof(__nv_bfloat16));
-  if (rc == ST_OK && precision == ST_PREC_BF16)
-    rc = dev_alloc(ctx, (void**)&ctx->abs_partials, 1024 * sizeof(double));
+    rc = dev_alloc(ctx, (void**)&ctx->delta_bf16, gram_floats * sizeof(__nv_bfloat16));
   ctx->part_floats = (size_t)16 << 20;
   if (rc == ST_OK) rc = dev_alloc(ctx, (void**)&ctx->part, ctx->part_floats * sizeof(float));
-  if (rc == ST_OK) rc = dev_alloc(ctx, (void**)&ctx->scalars, 64 * sizeof(double));
+  const size_t n_scalars = (size_t)kMaxBatch * kStatStride;
+  if (rc == ST_OK) rc = dev_alloc(ctx, (void**)&ctx->scalars, n_scalars * sizeof(double));
   if (rc == ST_OK)
     rc = dev_alloc(ctx, (void**)&ctx->rs.partials, (size_t)kMaxReduceBlocks * 4 * sizeof(double));
-  if (rc == ST_OK) rc = dev_alloc(ctx, (void**)&ctx->rs.counter, sizeof(unsigned));
-  if (rc == ST_OK && cudaMemset(ctx->rs.counter, 0, sizeof(unsigned)) != cudaSuccess) rc = ST_ERR_CUDA;
-  if (rc == ST_OK && cudaMemset(ctx->scalars, 0, 64 * sizeof(double)) != cudaSuccess) rc = ST_ERR_CUDA;
-  if (rc == ST_OK && precision == ST_PREC_BF16) rc = tc_init(ctx->tc, ctx->sm_count);
+  if (rc == ST_OK) rc = dev_alloc(ctx, (void**)&ctx->rs.counter, kMaxBatch * sizeof(unsigned));
+  if (rc == ST_OK && cudaMemset(ctx->rs.counter, 0, kMaxBatch * sizeof(unsigned)) != cudaSuccess)
+    rc = ST_ERR_CUDA;
+  if (rc == ST_OK && cudaMemset(ctx->scalars, 0, n_scalars * sizeof(double)) != cudaSuccess)
+    rc = ST_ERR_CUDA;
   if (rc != ST_OK) {
     st_destroy(ctx);
     return rc;
@@ -549,7 +590,7 @@ int st_set_conv_params(st_ctx* ctx, int layer, const float* w, const float* b) {
 int st_reserve(st_ctx* ctx, int max_h, int max_w) {
   ST_GUARD(ctx);
   ST_REQUIRE(max_h > 0 && max_w > 0, "st_reserve: empty tile");
-  return reserve_for(ctx, blob_dims(ctx, max_h, max_w), (int)ctx->layers.size() - 1);
+  return reserve_for(ctx, blob_dims(ctx, max_h, max_w), (int)ctx->layers.size() - 1, 1);
 }
 
 int st_device_info(st_ctx* ctx, int* sm_count, size_t* workspace_bytes) {
@@ -625,9 +666,10 @@ int st_eval_features_tile(st_ctx* ctx, const float* img_dev, int h, int w, int n
   }
   const int last_layer = ctx->blobs[deepest].producer;
   const Dims d = blob_dims(ctx, h, w);
-  int rc = reserve_for(ctx, d, last_layer);
+  int rc = reserve_for(ctx, d, last_layer, 1);
   if (rc != ST_OK) return rc;
-  const ImageView view{img_dev, h, w, 0, 0};
+  ImageBatch view{};
+  view.base = img_dev, view.H = h, view.W = w, view.nb = 1;
   cudaStream_t s = (cudaStream_t)stream;
   rc = ctx->precision == ST_PREC_FP32 ? forward<float>(ctx, view, d, last_layer, s)
                                       : forward<__nv_bfloat16>(ctx, view, d, last_layer, s);
@@ -650,10 +692,13 @@ int st_eval_sc_grad_tile(st_ctx* ctx, const float* img_dev, int h, int w, int st
   ST_GUARD(ctx);
   ST_REQUIRE(img_dev && loss_accum_dev && grad_dev, "st_eval_sc_grad_tile: null pointer");
   ST_REQUIRE(start_y >= 0 && start_x >= 0, "negative tile origin");
-  const ImageView view{img_dev, h, w, 0, 0};
-  return eval_tile_any(ctx, view, h, w, start_y, start_x, feat_roll_y, feat_roll_x, n_specs, specs,
-                       loss_accum_dev, grad_dev, grad_plane_stride, grad_row_stride,
-                       (cudaStream_t)stream);
+  ImageBatch view{};
+  view.base = img_dev, view.H = h, view.W = w, view.nb = 1;
+  BatchGeom g{};
+  g.nb = 1, g.start_y[0] = start_y, g.start_x[0] = start_x;
+  return eval_batch_any(ctx, view, h, w, g, feat_roll_y, feat_roll_x, n_specs, specs,
+                        loss_accum_dev, grad_dev, 0, grad_plane_stride, grad_row_stride,
+                        (cudaStream_t)stream);
 }
 
 int st_tile_grid(int H, int W, int tile_size, int* ntiles_y, int* ntiles_x, int* tile_h_max,
@@ -677,17 +722,36 @@ int st_eval_sc_grad_tiles(st_ctx* ctx, const float* img_dev, int H, int W, int r
              "st_eval_sc_grad_tiles: bad geometry");
   const Grid g = tile_grid(H, W, tile_size);
   const long plane = (long)g.thmax * g.twmax;
-  int slot = 0;
-  for (int t = rank; t < g.nty * g.ntx; t += world, ++slot) {
+  // This rank's tiles, in slot order.  Tiles of equal shape (all of them unless the grid is ragged)
+  // are evaluated together, up to max_batch per launch sequence; slots of one batch must be
+  // consecutive so that the gradient of batch tile i lands in slot first + i.
+  struct Local {
+    int sy, sx, h, w;
+  };
+  std::vector<Local> tiles;
+  for (int t = rank; t < g.nty * g.ntx; t += world) {
     const int ty = t / g.ntx, tx = t % g.ntx;
     const int sy = ty * g.th, sx = tx * g.tw;
-    const int h = ty == g.nty - 1 ? H - sy : g.th, w = tx == g.ntx - 1 ? W - sx : g.tw;
-    // rolled[y][x] = img[(y - roll_y) mod H][(x - roll_x) mod W]  (np.roll, num_utils.py:136-140)
-    const ImageView view{img_dev, H, W, sy - roll_y, sx - roll_x};
-    int rc = eval_tile_any(ctx, view, h, w, sy, sx, roll_y, roll_x, n_specs, specs, loss_accum_dev,
-                           packed_grad_dev + (size_t)slot * 3 * plane, plane, g.twmax,
-                           (cudaStream_t)stream);
+    tiles.push_back({sy, sx, ty == g.nty - 1 ? H - sy : g.th, tx == g.ntx - 1 ? W - sx : g.tw});
+  }
+  for (size_t first = 0; first < tiles.size();) {
+    size_t last = first + 1;
+    while (last < tiles.size() && last - first < (size_t)ctx->max_batch &&
+           tiles[last].h == tiles[first].h && tiles[last].w == tiles[first].w)
+      ++last;
+    ImageBatch view{};
+    BatchGeom bg{};
+    view.base = img_dev, view.H = H, view.W = W, view.nb = bg.nb = (int)(last - first);
+    for (size_t i = first; i < last; ++i) {
+      // rolled[y][x] = img[(y - roll_y) mod H][(x - roll_x) mod W]  (np.roll, num_utils.py:136-140)
+      view.oy[i - first] = tiles[i].sy - roll_y, view.ox[i - first] = tiles[i].sx - roll_x;
+      bg.start_y[i - first] = tiles[i].sy, bg.start_x[i - first] = tiles[i].sx;
+    }
+    int rc = eval_batch_any(ctx, view, tiles[first].h, tiles[first].w, bg, roll_y, roll_x, n_specs,
+                            specs, loss_accum_dev, packed_grad_dev + first * 3 * plane, 3 * plane,
+                            plane, g.twmax, (cudaStream_t)stream);
     if (rc != ST_OK) return rc;
+    first = last;
   }
   return ST_OK;
 }

@@ -64,12 +64,12 @@ __device__ __forceinline__ void fence_barrier_init() {
 __device__ __forceinline__ void fence_proxy_async() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
-__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0,
-                                            int c1) {
+__device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0,
+                                            int c1, int c2) {
   asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes"
-      " [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)),
-      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
@@ -146,7 +146,8 @@ struct GramArgs {
   int hw;              // pixels
   int kb_total;        // ceil(hw / 64)
   int kb_per_split;
-  float* part;         // [nsplit][C][C] fp32 partial sums
+  int nsplit;
+  float* part;         // [nb][nsplit][C][C] fp32 partial sums
 };
 
 template <int C>
@@ -164,6 +165,7 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap map_f, const GramArgs a) {
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int mb = blockIdx.x % Cfg::kMBlocks, split = blockIdx.x / Cfg::kMBlocks;
+  const int b = blockIdx.y;                              // tile of the batch
   const int kb_begin = split * a.kb_per_split;
   const int kb_end = min(a.kb_total, kb_begin + a.kb_per_split);
 
@@ -198,7 +200,7 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap map_f, const GramArgs a) {
         uint8_t* dst = smem + stage * Cfg::kStageBytes;
 #pragma unroll
         for (int g = 0; g < Cfg::kGroups; ++g)
-          tma_load_2d(&map_f, &full[stage], dst + g * kBoxBytes, g * 64, kb * 64);
+          tma_load_3d(&map_f, &full[stage], dst + g * kBoxBytes, g * 64, kb * 64, b);
         if (++stage == Cfg::kStages) stage = 0, phase ^= 1;
       }
     }
@@ -232,7 +234,7 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap map_f, const GramArgs a) {
       mbar_wait(tfull, 0);
       tc_fence_after();
     }
-    float* dst = a.part + ((size_t)split * C + row) * C;
+    float* dst = a.part + (((size_t)b * a.nsplit + split) * C + row) * C;
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
     for (int cc = 0; cc < C / 32; ++cc) {
@@ -255,16 +257,22 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap map_f, const GramArgs a) {
   if (warp == 1) tmem_dealloc(tmem_base, Cfg::kTmemCols);
 }
 
-// gram[i][j] = gram[j][i] = scale * sum_s part[s][max(i,j)][min(i,j)]
-__global__ void gram_tc_finalize_kernel(const float* __restrict__ part, int nsplit, int c,
-                                        double scale, float* __restrict__ gram) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= c * c) return;
-  const int i = idx / c, j = idx % c;
+// gram[b][i][j] = gram[b][j][i] = scale * sum_s part[b][s][max(i,j)][min(i,j)].  Eight lanes share
+// one element: lane l adds splits l, l+8, ... and the eight sums are combined in a fixed shuffle
+// order, so the result does not depend on the launch.  blockIdx.y = tile of the batch.
+__global__ void __launch_bounds__(256)
+gram_tc_finalize_kernel(const float* __restrict__ part, int nsplit, int c, double scale,
+                        float* __restrict__ gram) {
+  const int idx = (blockIdx.x * blockDim.x + threadIdx.x) >> 3, sub = threadIdx.x & 7;
+  const bool ok = idx < c * c;
+  const int i = ok ? idx / c : 0, j = ok ? idx % c : 0;
   const int hi = i > j ? i : j, lo = i > j ? j : i;
+  const float* p = part + (size_t)blockIdx.y * nsplit * c * c + (size_t)hi * c + lo;
   double sum = 0.0;
-  for (int s = 0; s < nsplit; ++s) sum += (double)part[((size_t)s * c + hi) * c + lo];
-  gram[idx] = (float)(sum * scale);
+  for (int s = sub; s < nsplit; s += 8) sum += (double)p[(size_t)s * c * c];
+#pragma unroll
+  for (int o = 4; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  if (ok && sub == 0) gram[(size_t)blockIdx.y * c * c + idx] = (float)(sum * scale);
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
@@ -272,17 +280,31 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
+// split the pixels over the SMs, but keep the partial buffer (written + re-read) below ~8 MB / tile
 template <int C>
-int launch_gram(TcContext& tc, const __nv_bfloat16* f, int hw, float* gram, float* part,
-                size_t part_floats, cudaStream_t s) {
+int gram_splits(const TcContext& tc, int nb, int hw) {
+  using Cfg = GramCfg<C>;
+  const int kb_total = cdiv(hw, 64);
+  int nsplit = cdiv(tc.sm_count, Cfg::kMBlocks * nb);
+  const int cap_bytes = (int)(((size_t)8 << 20) / ((size_t)C * C * 4));
+  nsplit = nsplit > cap_bytes ? cap_bytes : nsplit;
+  nsplit = nsplit > kb_total ? kb_total : nsplit;
+  nsplit = nsplit < 1 ? 1 : nsplit;
+  const int kb_per_split = cdiv(kb_total, nsplit);
+  return cdiv(kb_total, kb_per_split);
+}
+
+template <int C>
+int launch_gram(TcContext& tc, const __nv_bfloat16* f, int nb, int hw, float* gram, float* part,
+                cudaStream_t s) {
   using Cfg = GramCfg<C>;
   CUtensorMap map_f;
   {
-    cuuint64_t gdim[2] = {(cuuint64_t)C, (cuuint64_t)hw};
-    cuuint64_t gstride[1] = {(cuuint64_t)C * 2};
-    cuuint32_t box[2] = {64, 64}, estride[2] = {1, 1};
+    cuuint64_t gdim[3] = {(cuuint64_t)C, (cuuint64_t)hw, (cuuint64_t)nb};
+    cuuint64_t gstride[2] = {(cuuint64_t)C * 2, (cuuint64_t)hw * C * 2};
+    cuuint32_t box[3] = {64, 64, 1}, estride[3] = {1, 1, 1};
     CUresult r = reinterpret_cast<EncodeTiledFn>(tc.encode_fn)(
-        &map_f, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(f), gdim, gstride,
+        &map_f, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<__nv_bfloat16*>(f), gdim, gstride,
         box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
@@ -292,16 +314,8 @@ int launch_gram(TcContext& tc, const __nv_bfloat16* f, int hw, float* gram, floa
   }
   GramArgs a{};
   a.hw = hw, a.kb_total = cdiv(hw, 64), a.part = part;
-  // split the pixels over the SMs, but keep the partial buffer (written + re-read) below ~8 MB
-  int nsplit = tc.sm_count / Cfg::kMBlocks;
-  const int cap_bytes = (int)(((size_t)8 << 20) / ((size_t)C * C * 4));
-  const int cap_buf = (int)(part_floats / ((size_t)C * C));
-  nsplit = nsplit > cap_bytes ? cap_bytes : nsplit;
-  nsplit = nsplit > cap_buf ? cap_buf : nsplit;
-  nsplit = nsplit > a.kb_total ? a.kb_total : nsplit;
-  nsplit = nsplit < 1 ? 1 : nsplit;
-  a.kb_per_split = cdiv(a.kb_total, nsplit);
-  nsplit = cdiv(a.kb_total, a.kb_per_split);
+  a.nsplit = gram_splits<C>(tc, nb, hw);
+  a.kb_per_split = cdiv(a.kb_total, a.nsplit);
   auto kern = gram_tc_kernel<C>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -309,10 +323,10 @@ int launch_gram(TcContext& tc, const __nv_bfloat16* f, int hw, float* gram, floa
                                  Cfg::kSmemBytes));
     attr_set = true;
   }
-  TimerScope ts(s, kTimeGram, 2.0 * C * C * hw);
-  ST_LAUNCH(kern, nsplit * Cfg::kMBlocks, kGThreads, Cfg::kSmemBytes, s, map_f, a);
-  ST_LAUNCH(gram_tc_finalize_kernel, cdiv((long)C * C, 256), 256, 0, s, part, nsplit, C,
-            1.0 / ((double)C * hw), gram);
+  TimerScope ts(s, kTimeGram, 2.0 * C * C * hw * nb);
+  ST_LAUNCH(kern, dim3(a.nsplit * Cfg::kMBlocks, nb), kGThreads, Cfg::kSmemBytes, s, map_f, a);
+  ST_LAUNCH(gram_tc_finalize_kernel, dim3(cdiv((long)C * C * 8, 256), nb), 256, 0, s, part,
+            a.nsplit, C, 1.0 / ((double)C * hw), gram);
   return ST_OK;
 }
 
@@ -322,13 +336,24 @@ bool gram_tc_ok(const TcContext& tc, int c) {
   return tc.enabled && tc.pair_kernel && (c == 64 || c == 128 || c == 256 || c == 512);
 }
 
-int gram_tc(TcContext& tc, const __nv_bfloat16* f, int hw, int c, float* gram, float* part,
-            size_t part_floats, cudaStream_t s) {
+size_t gram_tc_part_floats(const TcContext& tc, int nb, int hw, int c) {
+  int nsplit = 1;
   switch (c) {
-    case 64: return launch_gram<64>(tc, f, hw, gram, part, part_floats, s);
-    case 128: return launch_gram<128>(tc, f, hw, gram, part, part_floats, s);
-    case 256: return launch_gram<256>(tc, f, hw, gram, part, part_floats, s);
-    case 512: return launch_gram<512>(tc, f, hw, gram, part, part_floats, s);
+    case 64: nsplit = gram_splits<64>(tc, nb, hw); break;
+    case 128: nsplit = gram_splits<128>(tc, nb, hw); break;
+    case 256: nsplit = gram_splits<256>(tc, nb, hw); break;
+    case 512: nsplit = gram_splits<512>(tc, nb, hw); break;
+  }
+  return (size_t)nb * nsplit * c * c;
+}
+
+int gram_tc(TcContext& tc, const __nv_bfloat16* f, int nb, int hw, int c, float* gram, float* part,
+            cudaStream_t s) {
+  switch (c) {
+    case 64: return launch_gram<64>(tc, f, nb, hw, gram, part, s);
+    case 128: return launch_gram<128>(tc, f, nb, hw, gram, part, s);
+    case 256: return launch_gram<256>(tc, f, nb, hw, gram, part, s);
+    case 512: return launch_gram<512>(tc, f, nb, hw, gram, part, s);
   }
   set_error("gram_tc: unsupported channel count");
   return ST_ERR_INVALID;

@@ -7,18 +7,27 @@
 
 namespace st {
 
+// Tiles of equal shape are evaluated as one batch: every activation is [nb][h][w][C].
+constexpr int kMaxBatch = 16;
+
 // Where the first convolution reads its pixels: an un-rolled image [3][H][W] addressed circularly
 // (the virtual roll) so that no tile copy is ever materialised.
-struct ImageView {
+struct ImageBatch {
   const float* base;   // [3][H][W]
   int H, W;            // full image size
-  int oy, ox;          // canonical coordinate of tile pixel (0,0), before wrapping
+  int nb;              // tiles in the batch
+  int oy[kMaxBatch], ox[kMaxBatch];   // canonical coordinate of tile pixel (0,0), before wrapping
+};
+
+// Per-tile origin inside the whole-image content feature map (already including the feature roll).
+struct TargetOffsets {
+  int ty0[kMaxBatch], tx0[kMaxBatch];
 };
 
 // Scratch for deterministic reductions, shared by all kernels of one context (single stream).
 struct ReduceScratch {
   double* partials;    // kMaxReduceBlocks * 4 doubles
-  unsigned* counter;   // zero between kernels
+  unsigned* counter;   // kMaxBatch counters (one per tile of the batch), zero between kernels
 };
 constexpr int kMaxReduceBlocks = 1 << 17;
 
@@ -26,22 +35,24 @@ enum BwdEpilogue { kEpiNone = 0, kEpiMask = 1, kEpiInj = 2 };
 
 // ---- convolutions (NHWC activations of type T) -----------------------------------------------
 template <typename T>
-int conv_first_fwd(const ImageView& img, int h, int w, const float* wpack /*[27][cout]*/,
+int conv_first_fwd(const ImageBatch& img, int h, int w, const float* wpack /*[27][cout]*/,
                    const float* bias, T* out, int cout, cudaStream_t s);
+// grad of tile b goes to grad + b * batch_stride as [3][h][w] with the given plane / row strides
 template <typename T>
-int conv_last_bwd(const T* dz, int h, int w, int cin_of_dz, const float* wpack /*[27][cout]*/,
-                  float* grad, long plane_stride, long row_stride, cudaStream_t s);
+int conv_last_bwd(const T* dz, int nb, int h, int w, int cin_of_dz, const float* wpack /*[27][cout]*/,
+                  float* grad, long batch_stride, long plane_stride, long row_stride,
+                  cudaStream_t s);
 // out[p][co] = epilogue(sum_{tap,ci} in[p+tap][ci] * wpack[tap][ci][co])
 template <typename T>
-int conv3x3_simt(const T* in, const float* wpack, const float* bias, T* out, int h, int w, int cin,
-                 int cout, bool forward, const T* mask_act, const T* inj, cudaStream_t s);
+int conv3x3_simt(const T* in, const float* wpack, const float* bias, T* out, int nb, int h, int w,
+                 int cin, int cout, bool forward, const T* mask_act, const T* inj, cudaStream_t s);
 
 // ---- pooling -----------------------------------------------------------------------------------
 template <typename T>
-int pool_fwd(const T* in, T* out, int h, int w, int c, bool is_max, cudaStream_t s);
+int pool_fwd(const T* in, T* out, int nb, int h, int w, int c, bool is_max, cudaStream_t s);
 // d_in = [mask](in>0) * pool_bwd(d_out) + [inj]
 template <typename T>
-int pool_bwd(const T* d_out, const T* in, T* d_in, int h, int w, int c, bool is_max,
+int pool_bwd(const T* d_out, const T* in, T* d_in, int nb, int h, int w, int c, bool is_max,
              bool apply_mask, const T* inj, cudaStream_t s);
 
 // ---- Gram / style ------------------------------------------------------------------------------
@@ -50,33 +61,42 @@ int pool_bwd(const T* d_out, const T* in, T* d_in, int h, int w, int c, bool is_
 template <typename T>
 int gram_full(const T* f, int hw, int c, bool channel_major, float* gram, float* part,
               size_t part_floats, int sm_count, cudaStream_t s);
-// delta = gram - target (both symmetric, full); *loss_accum += w * 0.5 * sum_{j<=i} delta_ij^2
+// delta[b] = gram[b] - target (symmetric, full [C][C] each);
+// tile_loss[b * loss_stride] += w * 0.5 * sum_{j<=i} delta_ij^2
 int gram_delta(const float* gram, const float* target, float* delta, __nv_bfloat16* delta_bf16,
-               int c, double w, double* loss_accum, ReduceScratch rs, cudaStream_t s);
-int sum_partials(const double* partials, int n, double* out, cudaStream_t s);
+               int c, int nb, double w, double* tile_loss, int loss_stride, ReduceScratch rs,
+               cudaStream_t s);
+// out[b * out_stride] = sum(partials[b*n .. b*n+n)) in index order
+int sum_partials(const double* partials, int n, int nb, double* out, int out_stride,
+                 cudaStream_t s);
+// *loss_accum += sum_b tile_loss[b * stride] (tile order); clears the slots
+int loss_finalize(double* tile_loss, int stride, int nb, double* loss_accum, cudaStream_t s);
 // S[p][co] = sum_ci F[p][ci] * delta[ci][co]; *sum_abs = sum |S|
 template <typename T>
 int style_grad(const T* f, const float* delta, T* s_out, int hw, int c, double* sum_abs,
                ReduceScratch rs, cudaStream_t s);
-// inj = (accumulate ? inj : 0) + w / (*sum_abs / n + EPS) * src
+// per tile b (n elements each): inj = (accumulate ? inj : 0) + w / (sum_abs[b*stride] / n + EPS) * src
 template <typename T>
-int inject_scaled(T* inj, const T* src, size_t n, float w, const double* sum_abs, bool accumulate,
-                  cudaStream_t s);
+int inject_scaled(T* inj, const T* src, size_t n, int nb, float w, const double* sum_abs,
+                  int stat_stride, bool accumulate, cudaStream_t s);
 int symmetrize_lower(const float* lower, float* full, int c, cudaStream_t s);
 int extract_lower(const float* full, float* lower, int c, cudaStream_t s);
 
 // ---- content / deep-dream ------------------------------------------------------------------------
-// Target map tgt is NHWC float [Hf][Wf][C] of the whole image, read at ((ty0+y) mod Hf, (tx0+x) mod
-// Wf).  stats[0] = sum c^2, stats[1] = sum |c| with c = F - target (target==nullptr: c = F).
+// Target map tgt is NHWC float [Hf][Wf][C] of the whole image, read for tile b at
+// ((ty0[b]+y) mod Hf, (tx0[b]+x) mod Wf).  stats[b*stride + 0] = sum c^2, [.. + 1] = sum |c| with
+// c = F - target (target==nullptr: c = F).
 template <typename T>
-int diff_stats(const T* f, int hf, int wf, int c, const float* tgt, int Hf, int Wf, int ty0,
-               int tx0, double* stats, ReduceScratch rs, cudaStream_t s);
+int diff_stats(const T* f, int nb, int hf, int wf, int c, const float* tgt, int Hf, int Wf,
+               const TargetOffsets& offs, double* stats, int stat_stride, ReduceScratch rs,
+               cudaStream_t s);
 // inj = (accumulate ? inj : 0) + w / (stats[1]/n + EPS) * (F - target);
-// *loss_accum += loss_w * 0.5 * stats[0]
+// tile_loss[b * loss_stride] += loss_w * 0.5 * stats[0]
 template <typename T>
-int diff_inject(const T* f, int hf, int wf, int c, const float* tgt, int Hf, int Wf, int ty0,
-                int tx0, const double* stats, float w, double loss_w, double* loss_accum, T* inj,
-                bool accumulate, cudaStream_t s);
+int diff_inject(const T* f, int nb, int hf, int wf, int c, const float* tgt, int Hf, int Wf,
+                const TargetOffsets& offs, const double* stats, int stat_stride, float w,
+                double loss_w, double* tile_loss, int loss_stride, T* inj, bool accumulate,
+                cudaStream_t s);
 
 // ---- layout conversion ---------------------------------------------------------------------------
 template <typename T>

@@ -20,8 +20,8 @@ constexpr int kTW = 16, kTH = 8, kCoT = 64;
 
 template <typename T>
 struct ConvArgs {
-  const T* in;          // NHWC (ignored when PLANAR)
-  ImageView img;        // PLANAR source
+  const T* in;          // NHWC [nb][h][w][cin] (ignored when PLANAR)
+  ImageBatch img;       // PLANAR source
   const float* wpack;   // [9][cin][cout]
   const float* bias;    // forward only
   T* out;
@@ -40,6 +40,8 @@ __global__ void __launch_bounds__(256) conv3x3_kernel(ConvArgs<T> a) {
   const int tiles_x = (a.w + kTW - 1) / kTW;
   const int oy = (blockIdx.x / tiles_x) * kTH, ox = (blockIdx.x % tiles_x) * kTW;
   const int co0 = blockIdx.y * kCoT;
+  const int bt = blockIdx.z;                               // tile of the batch
+  const size_t in_b = (size_t)bt * a.h * a.w * a.cin, out_b = (size_t)bt * a.h * a.w * a.cout;
   const int tx = tid & 15, ty = tid >> 4;
   const int row = ty >> 1, x0 = (ty & 1) * 8;
 
@@ -61,7 +63,7 @@ __global__ void __launch_bounds__(256) conv3x3_kernel(ConvArgs<T> a) {
         for (int ci = 0; ci < CI; ++ci) {
           float v = 0.f;
           if (inside) {
-            const int cy = wrap(a.img.oy + gy, a.img.H), cx = wrap(a.img.ox + gx, a.img.W);
+            const int cy = wrap(a.img.oy[bt] + gy, a.img.H), cx = wrap(a.img.ox[bt] + gx, a.img.W);
             v = a.img.base[((size_t)ci * a.img.H + cy) * a.img.W + cx];
           }
           in_s[ci][hr][hc] = v;
@@ -71,7 +73,7 @@ __global__ void __launch_bounds__(256) conv3x3_kernel(ConvArgs<T> a) {
 #pragma unroll
         for (int ci = 0; ci < CI; ++ci) v[ci] = 0.f;
         if (inside) {
-          const T* p = a.in + ((size_t)gy * a.w + gx) * a.cin + ci0;
+          const T* p = a.in + in_b + ((size_t)gy * a.w + gx) * a.cin + ci0;
 #pragma unroll
           for (int q = 0; q < CI / 4; ++q) {
             float4 f = Store<T>::ld4(p + 4 * q);
@@ -122,7 +124,7 @@ __global__ void __launch_bounds__(256) conv3x3_kernel(ConvArgs<T> a) {
   for (int j = 0; j < 8; ++j) {
     const int x = ox + x0 + j;
     if (x >= a.w) break;
-    const size_t o = ((size_t)y * a.w + x) * a.cout + co;
+    const size_t o = out_b + ((size_t)y * a.w + x) * a.cout + co;
     float4 v = make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][3]);
     if (a.forward) {
       v.x = fmaxf(v.x + b.x, 0.f), v.y = fmaxf(v.y + b.y, 0.f);
@@ -143,29 +145,29 @@ __global__ void __launch_bounds__(256) conv3x3_kernel(ConvArgs<T> a) {
 }
 
 template <typename T>
-int conv3x3_simt(const T* in, const float* wpack, const float* bias, T* out, int h, int w, int cin,
-                 int cout, bool forward, const T* mask_act, const T* inj, cudaStream_t s) {
+int conv3x3_simt(const T* in, const float* wpack, const float* bias, T* out, int nb, int h, int w,
+                 int cin, int cout, bool forward, const T* mask_act, const T* inj, cudaStream_t s) {
   ST_REQUIRE(cin % 8 == 0 && cout % kCoT == 0, "conv3x3: cin must be a multiple of 8, cout of 64");
   ConvArgs<T> a{};
   a.in = in, a.wpack = wpack, a.bias = bias, a.out = out, a.mask_act = mask_act, a.inj = inj;
   a.h = h, a.w = w, a.cin = cin, a.cout = cout, a.forward = forward ? 1 : 0;
-  dim3 grid(cdiv(h, kTH) * cdiv(w, kTW), cout / kCoT);
+  dim3 grid(cdiv(h, kTH) * cdiv(w, kTW), cout / kCoT, nb);
   auto k = conv3x3_kernel<T, 8, false>;
-  TimerScope ts(s, kTimeConvSimt, 18.0 * cin * cout * h * w);
+  TimerScope ts(s, kTimeConvSimt, 18.0 * cin * cout * h * w * nb);
   ST_LAUNCH(k, grid, 256, 0, s, a);
   return ST_OK;
 }
 
 template <typename T>
-int conv_first_fwd(const ImageView& img, int h, int w, const float* wpack, const float* bias,
+int conv_first_fwd(const ImageBatch& img, int h, int w, const float* wpack, const float* bias,
                    T* out, int cout, cudaStream_t s) {
   ST_REQUIRE(cout % kCoT == 0, "first conv: cout must be a multiple of 64");
   ConvArgs<T> a{};
   a.img = img, a.wpack = wpack, a.bias = bias, a.out = out;
   a.h = h, a.w = w, a.cin = 3, a.cout = cout, a.forward = 1;
-  dim3 grid(cdiv(h, kTH) * cdiv(w, kTW), cout / kCoT);
+  dim3 grid(cdiv(h, kTH) * cdiv(w, kTW), cout / kCoT, img.nb);
   auto k = conv3x3_kernel<T, 3, true>;
-  TimerScope ts(s, kTimeConvSimt, 18.0 * 3 * cout * h * w);
+  TimerScope ts(s, kTimeConvSimt, 18.0 * 3 * cout * h * w * img.nb);
   ST_LAUNCH(k, grid, 256, 0, s, a);
   return ST_OK;
 }
@@ -180,8 +182,11 @@ constexpr int kLW = 32, kLH = 8, kLC = 16, kLPad = 20;
 template <typename T>
 __global__ void __launch_bounds__(64) conv_last_bwd_kernel(const T* __restrict__ dz, int h, int w,
                                                            int cz, const float* __restrict__ wpack,
-                                                           float* __restrict__ grad, long plane,
+                                                           float* __restrict__ grad,
+                                                           long batch_stride, long plane,
                                                            long rstride) {
+  dz += (size_t)blockIdx.y * h * w * cz;
+  grad += (size_t)blockIdx.y * batch_stride;
   __shared__ __align__(16) float in_s[kLH + 2][kLW + 2][kLPad];
   __shared__ __align__(16) float w_s[9][kLC][4];
   const int tid = threadIdx.x;
@@ -246,13 +251,13 @@ __global__ void __launch_bounds__(64) conv_last_bwd_kernel(const T* __restrict__
 }
 
 template <typename T>
-int conv_last_bwd(const T* dz, int h, int w, int cz, const float* wpack, float* grad,
-                  long plane_stride, long row_stride, cudaStream_t s) {
+int conv_last_bwd(const T* dz, int nb, int h, int w, int cz, const float* wpack, float* grad,
+                  long batch_stride, long plane_stride, long row_stride, cudaStream_t s) {
   ST_REQUIRE(cz % kLC == 0, "last conv backward: channel count must be a multiple of 16");
   auto k = conv_last_bwd_kernel<T>;
-  TimerScope ts(s, kTimeConvSimt, 18.0 * 3 * cz * h * w);
-  ST_LAUNCH(k, cdiv(h, kLH) * cdiv(w, kLW), 64, 0, s, dz, h, w, cz, wpack, grad, plane_stride,
-            row_stride);
+  TimerScope ts(s, kTimeConvSimt, 18.0 * 3 * cz * h * w * nb);
+  ST_LAUNCH(k, dim3(cdiv(h, kLH) * cdiv(w, kLW), nb), 64, 0, s, dz, h, w, cz, wpack, grad,
+            batch_stride, plane_stride, row_stride);
   return ST_OK;
 }
 
@@ -262,15 +267,16 @@ int conv_last_bwd(const T* dz, int h, int w, int cz, const float* wpack, float* 
 // backward pass recomputes that argmax from the stored input instead of saving a mask.
 // =====================================================================================================
 template <typename T>
-__global__ void pool_fwd_kernel(const T* __restrict__ in, T* __restrict__ out, int h, int w, int c,
-                                int ho, int wo, int is_max) {
+__global__ void pool_fwd_kernel(const T* __restrict__ in_all, T* __restrict__ out, int nb, int h,
+                                int w, int c, int ho, int wo, int is_max) {
   const int c4 = c >> 2;
-  const size_t total = (size_t)ho * wo * c4;
+  const size_t total = (size_t)nb * ho * wo * c4;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total;
        i += (size_t)gridDim.x * blockDim.x) {
     const int q = (int)(i % c4);
-    const size_t p = i / c4;
-    const int x = (int)(p % wo), y = (int)(p / wo);
+    const size_t p = i / c4;                                  // pooled pixel over the whole batch
+    const int x = (int)(p % wo), y = (int)((p / wo) % ho);
+    const T* in = in_all + (p / ((size_t)wo * ho)) * ((size_t)h * w * c);
     float4 m = is_max ? make_float4(-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX)
                       : make_float4(0.f, 0.f, 0.f, 0.f);
     int cnt = 0;
@@ -297,16 +303,20 @@ __global__ void pool_fwd_kernel(const T* __restrict__ in, T* __restrict__ out, i
 }
 
 template <typename T>
-__global__ void pool_bwd_kernel(const T* __restrict__ d_out, const T* __restrict__ in,
-                                T* __restrict__ d_in, int h, int w, int c, int ho, int wo,
-                                int is_max, int apply_mask, const T* __restrict__ inj) {
+__global__ void pool_bwd_kernel(const T* __restrict__ d_out, const T* __restrict__ in_all,
+                                T* __restrict__ d_in_all, int nb, int h, int w, int c, int ho,
+                                int wo, int is_max, int apply_mask, const T* __restrict__ inj_all) {
   const int c4 = c >> 2;
-  const size_t total = (size_t)ho * wo * c4;
+  const size_t total = (size_t)nb * ho * wo * c4;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total;
        i += (size_t)gridDim.x * blockDim.x) {
     const int q = (int)(i % c4);
     const size_t p = i / c4;
-    const int x = (int)(p % wo), y = (int)(p / wo);
+    const int x = (int)(p % wo), y = (int)((p / wo) % ho);
+    const size_t boff = (p / ((size_t)wo * ho)) * ((size_t)h * w * c);
+    const T* in = in_all + boff;
+    T* d_in = d_in_all + boff;
+    const T* inj = inj_all ? inj_all + boff : nullptr;
     const float4 g = Store<T>::ld4(d_out + p * c + q * 4);
     float4 v[4];
     bool ok[4];
@@ -364,26 +374,26 @@ static inline int ew_grid(size_t work_items, int block) {
 }
 
 template <typename T>
-int pool_fwd(const T* in, T* out, int h, int w, int c, bool is_max, cudaStream_t s) {
+int pool_fwd(const T* in, T* out, int nb, int h, int w, int c, bool is_max, cudaStream_t s) {
   ST_REQUIRE(c % 4 == 0, "pool: channels must be a multiple of 4");
   const int ho = (h + 1) / 2, wo = (w + 1) / 2;
   auto k = pool_fwd_kernel<T>;
-  TimerScope ts(s, kTimePool, (double)sizeof(T) * c * ((double)h * w + (double)ho * wo));
-  ST_LAUNCH(k, ew_grid((size_t)ho * wo * (c / 4), 256), 256, 0, s, in, out, h, w, c, ho, wo,
-            is_max ? 1 : 0);
+  TimerScope ts(s, kTimePool, (double)sizeof(T) * c * nb * ((double)h * w + (double)ho * wo));
+  ST_LAUNCH(k, ew_grid((size_t)nb * ho * wo * (c / 4), 256), 256, 0, s, in, out, nb, h, w, c, ho,
+            wo, is_max ? 1 : 0);
   return ST_OK;
 }
 
 template <typename T>
-int pool_bwd(const T* d_out, const T* in, T* d_in, int h, int w, int c, bool is_max,
+int pool_bwd(const T* d_out, const T* in, T* d_in, int nb, int h, int w, int c, bool is_max,
              bool apply_mask, const T* inj, cudaStream_t s) {
   ST_REQUIRE(c % 4 == 0, "pool: channels must be a multiple of 4");
   const int ho = (h + 1) / 2, wo = (w + 1) / 2;
   auto k = pool_bwd_kernel<T>;
-  TimerScope ts(s, kTimePool, (double)sizeof(T) * c *
+  TimerScope ts(s, kTimePool, (double)sizeof(T) * c * nb *
                                   ((double)h * w * (2 + (inj ? 1 : 0)) + (double)ho * wo));
-  ST_LAUNCH(k, ew_grid((size_t)ho * wo * (c / 4), 256), 256, 0, s, d_out, in, d_in, h, w, c, ho,
-            wo, is_max ? 1 : 0, apply_mask ? 1 : 0, inj);
+  ST_LAUNCH(k, ew_grid((size_t)nb * ho * wo * (c / 4), 256), 256, 0, s, d_out, in, d_in, nb, h, w,
+            c, ho, wo, is_max ? 1 : 0, apply_mask ? 1 : 0, inj);
   return ST_OK;
 }
 
@@ -487,38 +497,58 @@ int gram_full(const T* f, int hw, int c, bool channel_major, float* gram, float*
   return ST_OK;
 }
 
-// delta = G - G_style (symmetric); loss += w * 0.5 * sum_{j<=i} delta^2  (style_transfer.py:587,591)
+// delta[b] = G[b] - G_style (symmetric); tile_loss[b] += w * 0.5 * sum_{j<=i} delta^2
+// (style_transfer.py:587,591).  blockIdx.y = tile of the batch.
 __global__ void gram_delta_kernel(const float* __restrict__ gram, const float* __restrict__ target,
                                   float* __restrict__ delta, __nv_bfloat16* __restrict__ delta_bf16,
-                                  int c, double w, double* loss_accum, ReduceScratch rs) {
+                                  int c, double w, double* tile_loss, int loss_stride,
+                                  ReduceScratch rs) {
+  const size_t off = (size_t)blockIdx.y * c * c;
   double v[1] = {0.0};
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < c * c;
        idx += gridDim.x * blockDim.x) {
-    const float d = gram[idx] - target[idx];
-    delta[idx] = d;
-    if (delta_bf16 != nullptr) delta_bf16[idx] = __float2bfloat16_rn(d);
+    const float d = gram[off + idx] - target[idx];
+    delta[off + idx] = d;
+    if (delta_bf16 != nullptr) delta_bf16[off + idx] = __float2bfloat16_rn(d);
     if (idx % c <= idx / c) v[0] += (double)d * d;
   }
-  if (grid_reduce<1>(v, rs.partials, rs.counter)) atomicAdd(loss_accum, w * 0.5 * v[0]);
+  if (grid_reduce<1>(v, rs.partials + (size_t)blockIdx.y * gridDim.x, rs.counter + blockIdx.y))
+    tile_loss[(size_t)blockIdx.y * loss_stride] += w * 0.5 * v[0];
 }
 
 int gram_delta(const float* gram, const float* target, float* delta, __nv_bfloat16* delta_bf16,
-               int c, double w, double* loss_accum, ReduceScratch rs, cudaStream_t s) {
-  ST_LAUNCH(gram_delta_kernel, min(cdiv((long)c * c, 256), 256), 256, 0, s, gram, target, delta,
-            delta_bf16, c, w, loss_accum, rs);
+               int c, int nb, double w, double* tile_loss, int loss_stride, ReduceScratch rs,
+               cudaStream_t s) {
+  ST_LAUNCH(gram_delta_kernel, dim3(min(cdiv((long)c * c, 256), 256), nb), 256, 0, s, gram, target,
+            delta, delta_bf16, c, w, tile_loss, loss_stride, rs);
   return ST_OK;
 }
 
-// out[0] = partials[0] + ... + partials[n-1], summed in index order by one warp (deterministic).
-__global__ void sum_partials_kernel(const double* __restrict__ partials, int n, double* out) {
+// out[b * out_stride] = sum of partials[b * n .. b * n + n), summed in index order by one warp
+// (deterministic).  blockIdx.x = tile of the batch.
+__global__ void sum_partials_kernel(const double* __restrict__ partials, int n, double* out,
+                                    int out_stride) {
+  const double* p = partials + (size_t)blockIdx.x * n;
   double x = 0.0;
-  for (int i = threadIdx.x; i < n; i += 32) x += partials[i];
+  for (int i = threadIdx.x; i < n; i += 32) x += p[i];
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-  if (threadIdx.x == 0) *out = x;
+  if (threadIdx.x == 0) out[(size_t)blockIdx.x * out_stride] = x;
 }
-int sum_partials(const double* partials, int n, double* out, cudaStream_t s) {
-  ST_LAUNCH(sum_partials_kernel, 1, 32, 0, s, partials, n, out);
+int sum_partials(const double* partials, int n, int nb, double* out, int out_stride,
+                 cudaStream_t s) {
+  ST_LAUNCH(sum_partials_kernel, nb, 32, 0, s, partials, n, out, out_stride);
+  return ST_OK;
+}
+
+// *loss_accum += tile_loss[0] + tile_loss[stride] + ... (tile order), then clears the slots.
+__global__ void loss_finalize_kernel(double* tile_loss, int stride, int nb, double* loss_accum) {
+  double x = 0.0;
+  for (int b = 0; b < nb; ++b) x += tile_loss[(size_t)b * stride], tile_loss[(size_t)b * stride] = 0.0;
+  *loss_accum += x;
+}
+int loss_finalize(double* tile_loss, int stride, int nb, double* loss_accum, cudaStream_t s) {
+  ST_LAUNCH(loss_finalize_kernel, 1, 1, 0, s, tile_loss, stride, nb, loss_accum);
   return ST_OK;
 }
 
@@ -614,8 +644,12 @@ int style_grad(const T* f, const float* delta, T* s_out, int hw, int c, double* 
 
 template <typename T>
 __global__ void inject_scaled_kernel(T* __restrict__ inj, const T* __restrict__ src, size_t n4,
-                                     float w, const double* __restrict__ sum_abs, int accumulate) {
-  const float coef = w * (1.f / ((float)(*sum_abs / (double)(n4 * 4)) + kEps));
+                                     float w, const double* __restrict__ sum_abs, int stat_stride,
+                                     int accumulate) {
+  // blockIdx.y = tile of the batch; n4 = float4 groups per tile
+  const float coef =
+      w * (1.f / ((float)(sum_abs[(size_t)blockIdx.y * stat_stride] / (double)(n4 * 4)) + kEps));
+  inj += (size_t)blockIdx.y * n4 * 4, src += (size_t)blockIdx.y * n4 * 4;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4;
        i += (size_t)gridDim.x * blockDim.x) {
     const float4 sv = Store<T>::ld4(src + i * 4);
@@ -629,11 +663,12 @@ __global__ void inject_scaled_kernel(T* __restrict__ inj, const T* __restrict__ 
 }
 
 template <typename T>
-int inject_scaled(T* inj, const T* src, size_t n, float w, const double* sum_abs, bool accumulate,
-                  cudaStream_t s) {
+int inject_scaled(T* inj, const T* src, size_t n, int nb, float w, const double* sum_abs,
+                  int stat_stride, bool accumulate, cudaStream_t s) {
   ST_REQUIRE(n % 4 == 0, "inject: size must be a multiple of 4");
   auto k = inject_scaled_kernel<T>;
-  ST_LAUNCH(k, ew_grid(n / 4, 256), 256, 0, s, inj, src, n / 4, w, sum_abs, accumulate ? 1 : 0);
+  ST_LAUNCH(k, dim3(ew_grid(n / 4, 256), nb), 256, 0, s, inj, src, n / 4, w, sum_abs, stat_stride,
+            accumulate ? 1 : 0);
   return ST_OK;
 }
 
@@ -659,42 +694,55 @@ __device__ __forceinline__ float4 diff_at(const T* f, const float* tgt, size_t i
 
 template <typename T>
 __global__ void diff_stats_kernel(const T* __restrict__ f, size_t n4, int wf, int c4,
-                                  const float* __restrict__ tgt, int Hf, int Wf, int ty0, int tx0,
-                                  double* stats, ReduceScratch rs) {
+                                  const float* __restrict__ tgt, int Hf, int Wf, TargetOffsets offs,
+                                  double* stats, int stat_stride, ReduceScratch rs) {
+  const int b = blockIdx.y;
+  f += (size_t)b * n4 * 4;
   float sq = 0.f, ab = 0.f;
   double v[2] = {0.0, 0.0};
   int cnt = 0;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4;
        i += (size_t)gridDim.x * blockDim.x) {
-    const float4 d = diff_at(f, tgt, i, wf, c4, Hf, Wf, ty0, tx0);
+    const float4 d = diff_at(f, tgt, i, wf, c4, Hf, Wf, offs.ty0[b], offs.tx0[b]);
     sq += d.x * d.x + d.y * d.y + d.z * d.z + d.w * d.w;
     ab += fabsf(d.x) + fabsf(d.y) + fabsf(d.z) + fabsf(d.w);
     if (++cnt == 64) v[0] += sq, v[1] += ab, sq = ab = 0.f, cnt = 0;
   }
   v[0] += sq, v[1] += ab;
-  if (grid_reduce<2>(v, rs.partials, rs.counter)) stats[0] = v[0], stats[1] = v[1];
+  if (grid_reduce<2>(v, rs.partials + (size_t)b * gridDim.x * 2, rs.counter + b))
+    stats[(size_t)b * stat_stride] = v[0], stats[(size_t)b * stat_stride + 1] = v[1];
 }
 
 template <typename T>
-int diff_stats(const T* f, int hf, int wf, int c, const float* tgt, int Hf, int Wf, int ty0,
-               int tx0, double* stats, ReduceScratch rs, cudaStream_t s) {
+int diff_stats(const T* f, int nb, int hf, int wf, int c, const float* tgt, int Hf, int Wf,
+               const TargetOffsets& offs, double* stats, int stat_stride, ReduceScratch rs,
+               cudaStream_t s) {
   ST_REQUIRE(c % 4 == 0, "diff_stats: channels must be a multiple of 4");
   const size_t n4 = (size_t)hf * wf * (c / 4);
+  const int gx = min(ew_grid(n4, 256), kMaxReduceBlocks / (nb * 2));
   auto k = diff_stats_kernel<T>;
-  ST_LAUNCH(k, ew_grid(n4, 256), 256, 0, s, f, n4, wf, c / 4, tgt, Hf, Wf, ty0, tx0, stats, rs);
+  TimerScope ts(s, kTimeLoss, (double)nb * n4 * 4 * (sizeof(T) + (tgt ? 4 : 0)));
+  ST_LAUNCH(k, dim3(gx, nb), 256, 0, s, f, n4, wf, c / 4, tgt, Hf, Wf, offs, stats, stat_stride,
+            rs);
   return ST_OK;
 }
 
+// stats[b] = {sum c^2, sum |c|}; inj = (accumulate ? inj : 0) + w / (mean|c| + EPS) * c;
+// tile_loss[b] += loss_w * 0.5 * sum c^2
 template <typename T>
 __global__ void diff_inject_kernel(const T* __restrict__ f, size_t n4, int wf, int c4,
-                                   const float* __restrict__ tgt, int Hf, int Wf, int ty0, int tx0,
-                                   const double* __restrict__ stats, float w, double loss_w,
-                                   double* loss_accum, T* __restrict__ inj, int accumulate) {
-  const float coef = w * (1.f / ((float)(stats[1] / (double)(n4 * 4)) + kEps));
-  if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(loss_accum, loss_w * 0.5 * stats[0]);
+                                   const float* __restrict__ tgt, int Hf, int Wf, TargetOffsets offs,
+                                   const double* __restrict__ stats, int stat_stride, float w,
+                                   double loss_w, double* tile_loss, int loss_stride,
+                                   T* __restrict__ inj, int accumulate) {
+  const int b = blockIdx.y;
+  f += (size_t)b * n4 * 4, inj += (size_t)b * n4 * 4;
+  const double* st = stats + (size_t)b * stat_stride;
+  const float coef = w * (1.f / ((float)(st[1] / (double)(n4 * 4)) + kEps));
+  if (blockIdx.x == 0 && threadIdx.x == 0) tile_loss[(size_t)b * loss_stride] += loss_w * 0.5 * st[0];
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4;
        i += (size_t)gridDim.x * blockDim.x) {
-    const float4 d = diff_at(f, tgt, i, wf, c4, Hf, Wf, ty0, tx0);
+    const float4 d = diff_at(f, tgt, i, wf, c4, Hf, Wf, offs.ty0[b], offs.tx0[b]);
     float4 r = make_float4(coef * d.x, coef * d.y, coef * d.z, coef * d.w);
     if (accumulate) {
       const float4 o = Store<T>::ld4(inj + i * 4);
@@ -705,13 +753,15 @@ __global__ void diff_inject_kernel(const T* __restrict__ f, size_t n4, int wf, i
 }
 
 template <typename T>
-int diff_inject(const T* f, int hf, int wf, int c, const float* tgt, int Hf, int Wf, int ty0,
-                int tx0, const double* stats, float w, double loss_w, double* loss_accum, T* inj,
-                bool accumulate, cudaStream_t s) {
+int diff_inject(const T* f, int nb, int hf, int wf, int c, const float* tgt, int Hf, int Wf,
+                const TargetOffsets& offs, const double* stats, int stat_stride, float w,
+                double loss_w, double* tile_loss, int loss_stride, T* inj, bool accumulate,
+                cudaStream_t s) {
   const size_t n4 = (size_t)hf * wf * (c / 4);
   auto k = diff_inject_kernel<T>;
-  ST_LAUNCH(k, ew_grid(n4, 256), 256, 0, s, f, n4, wf, c / 4, tgt, Hf, Wf, ty0, tx0, stats, w,
-            loss_w, loss_accum, inj, accumulate ? 1 : 0);
+  TimerScope ts(s, kTimeLoss, (double)nb * n4 * 4 * (sizeof(T) * (accumulate ? 3 : 2) + (tgt ? 4 : 0)));
+  ST_LAUNCH(k, dim3(ew_grid(n4, 256), nb), 256, 0, s, f, n4, wf, c / 4, tgt, Hf, Wf, offs, stats,
+            stat_stride, w, loss_w, tile_loss, loss_stride, inj, accumulate ? 1 : 0);
   return ST_OK;
 }
 
@@ -753,23 +803,25 @@ int nchw_to_nhwc_f32(const float* in, float* out, int hw, int c, cudaStream_t s)
 
 // ---- explicit instantiations ---------------------------------------------------------------------
 #define ST_INSTANTIATE(T)                                                                         \
-  template int conv3x3_simt<T>(const T*, const float*, const float*, T*, int, int, int, int, bool, \
-                               const T*, const T*, cudaStream_t);                                 \
-  template int conv_first_fwd<T>(const ImageView&, int, int, const float*, const float*, T*, int, \
-                                 cudaStream_t);                                                   \
-  template int conv_last_bwd<T>(const T*, int, int, int, const float*, float*, long, long,        \
-                                cudaStream_t);                                                    \
-  template int pool_fwd<T>(const T*, T*, int, int, int, bool, cudaStream_t);                      \
-  template int pool_bwd<T>(const T*, const T*, T*, int, int, int, bool, bool, const T*,           \
+  template int conv3x3_simt<T>(const T*, const float*, const float*, T*, int, int, int, int, int, \
+                               bool, const T*, const T*, cudaStream_t);                           \
+  template int conv_first_fwd<T>(const ImageBatch&, int, int, const float*, const float*, T*,     \
+                                 int, cudaStream_t);                                              \
+  template int conv_last_bwd<T>(const T*, int, int, int, int, const float*, float*, long, long,   \
+                                long, cudaStream_t);                                              \
+  template int pool_fwd<T>(const T*, T*, int, int, int, int, bool, cudaStream_t);                 \
+  template int pool_bwd<T>(const T*, const T*, T*, int, int, int, int, bool, bool, const T*,      \
                            cudaStream_t);                                                         \
   template int gram_full<T>(const T*, int, int, bool, float*, float*, size_t, int, cudaStream_t); \
   template int style_grad<T>(const T*, const float*, T*, int, int, double*, ReduceScratch,        \
                              cudaStream_t);                                                       \
-  template int inject_scaled<T>(T*, const T*, size_t, float, const double*, bool, cudaStream_t);  \
-  template int diff_stats<T>(const T*, int, int, int, const float*, int, int, int, int, double*,  \
-                             ReduceScratch, cudaStream_t);                                        \
-  template int diff_inject<T>(const T*, int, int, int, const float*, int, int, int, int,          \
-                              const double*, float, double, double*, T*, bool, cudaStream_t);     \
+  template int inject_scaled<T>(T*, const T*, size_t, int, float, const double*, int, bool,       \
+                                cudaStream_t);                                                    \
+  template int diff_stats<T>(const T*, int, int, int, int, const float*, int, int,                \
+                             const TargetOffsets&, double*, int, ReduceScratch, cudaStream_t);    \
+  template int diff_inject<T>(const T*, int, int, int, int, const float*, int, int,               \
+                              const TargetOffsets&, const double*, int, float, double, double*,   \
+                              int, T*, bool, cudaStream_t);                                       \
   template int nhwc_to_nchw_f32<T>(const T*, float*, int, int, cudaStream_t);
 
 ST_INSTANTIATE(float)
