@@ -419,6 +419,19 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constan
           } else {
 #pragma unroll
             for (int i = 0; i < 32; ++i) abs_tile += fabsf(v[i]);
+            if (hh == 1) {
+              // sum |S| over this warp's 32 rows x this 64-channel group: one slot per (pixel tile,
+              // 64-channel group, CTA, warp), added up later in slot order -- the grouping does not
+              // depend on BN or on the tile -> CTA schedule, so the sum is reproducible
+              double x = (double)abs_tile;
+#pragma unroll
+              for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+              const int m_tile = tile / a.tiles_n;
+              const int g64 = n_tile * (BN / 64) + g;
+              if (lane == 0)
+                a.abs_partials[(((size_t)m_tile * (a.cout >> 6) + g64) * 2 + rank) * 4 + q] = x;
+              abs_tile = 0.f;
+            }
           }
           // registers -> swizzled staging tile [128 rows][128 B] (SWIZZLE_128B, as TMA expects)
           uint8_t* row = stage_out + (size_t)m * 128;
@@ -447,14 +460,6 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constan
           tma_store_4d(&map_out, stage_out, n_tile * BN + g * 64, x0, y0, t.b);
           tma_store_commit();
         }
-      }
-      if constexpr (EPI == kEpiAbs) {
-        // sum |S| of this warp's 32 rows of the tile: one slot per (tile, CTA, warp), summed later
-        // in index order (deterministic whatever the tile -> CTA schedule)
-        double x = (double)abs_tile;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-        if (lane == 0) a.abs_partials[((size_t)tile * 2 + rank) * 4 + q] = x;
       }
     }
     if (issuer) tma_store_wait_all();
@@ -582,7 +587,7 @@ int gemm_abs_tc_pair(TcContext& tc, const __nv_bfloat16* f, const __nv_bfloat16*
   a.nb = nb, a.h = h, a.w = w, a.cin = c, a.cout = c, a.w_batched = 1;
   a.abs_partials = abs_partials;
   const int bn = choose_bn(tc, nb, h, w, c);
-  *per_tile = cdiv(w, kBW) * cdiv(h, 2 * kBH) * (c / bn) * 8;
+  *per_tile = cdiv(w, kBW) * cdiv(h, 2 * kBH) * (c / 64) * 8;
   return dispatch_bn<1, kEpiAbs>(tc, bn, f, d, c, s_out, a, s);
 }
 

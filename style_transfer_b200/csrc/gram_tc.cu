@@ -280,16 +280,15 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-// split the pixels over the SMs, but keep the partial buffer (written + re-read) below ~8 MB / tile
+// Number of pixel splits per tile.  It depends on the layer shape only -- never on the batch size or
+// the SM count -- so that a tile's Gram matrix has the same bits whichever rank / batch computes
+// it.  The cap keeps the partial buffer (written, then re-read by the finalize kernel) at 1-8 MB per
+// tile while a batch of a few tiles still fills the machine.
 template <int C>
-int gram_splits(const TcContext& tc, int nb, int hw) {
-  using Cfg = GramCfg<C>;
+int gram_splits(int hw) {
   const int kb_total = cdiv(hw, 64);
-  int nsplit = cdiv(tc.sm_count, Cfg::kMBlocks * nb);
-  const int cap_bytes = (int)(((size_t)8 << 20) / ((size_t)C * C * 4));
-  nsplit = nsplit > cap_bytes ? cap_bytes : nsplit;
+  int nsplit = C <= 64 ? 64 : (C <= 128 ? 32 : (C <= 256 ? 16 : 8));
   nsplit = nsplit > kb_total ? kb_total : nsplit;
-  nsplit = nsplit < 1 ? 1 : nsplit;
   const int kb_per_split = cdiv(kb_total, nsplit);
   return cdiv(kb_total, kb_per_split);
 }
@@ -314,7 +313,7 @@ int launch_gram(TcContext& tc, const __nv_bfloat16* f, int nb, int hw, float* gr
   }
   GramArgs a{};
   a.hw = hw, a.kb_total = cdiv(hw, 64), a.part = part;
-  a.nsplit = gram_splits<C>(tc, nb, hw);
+  a.nsplit = gram_splits<C>(hw);
   a.kb_per_split = cdiv(a.kb_total, a.nsplit);
   auto kern = gram_tc_kernel<C>;
   static bool attr_set = false;
@@ -339,10 +338,10 @@ bool gram_tc_ok(const TcContext& tc, int c) {
 size_t gram_tc_part_floats(const TcContext& tc, int nb, int hw, int c) {
   int nsplit = 1;
   switch (c) {
-    case 64: nsplit = gram_splits<64>(tc, nb, hw); break;
-    case 128: nsplit = gram_splits<128>(tc, nb, hw); break;
-    case 256: nsplit = gram_splits<256>(tc, nb, hw); break;
-    case 512: nsplit = gram_splits<512>(tc, nb, hw); break;
+    case 64: nsplit = gram_splits<64>(hw); break;
+    case 128: nsplit = gram_splits<128>(hw); break;
+    case 256: nsplit = gram_splits<256>(hw); break;
+    case 512: nsplit = gram_splits<512>(hw); break;
   }
   return (size_t)nb * nsplit * c * c;
 }

@@ -20,7 +20,7 @@ import ctypes as C
 import numpy as np
 import torch
 
-from . import _lib
+from . import _lib, sharding
 from .netdesc import NetDesc
 
 PRECISIONS = {'fp32': _lib.ST_PREC_FP32, 'bf16': _lib.ST_PREC_BF16}
@@ -301,25 +301,13 @@ class TileEngine:
         layers = self.ordered_layers(content_layers, style_layers, dd_layers)
         specs = self._specs(layers, content_layers, style_layers, dd_layers, layer_weights,
                             content_weight, style_weight, dd_weight)
-        nty, ntx, thmax, twmax = C.c_int(), C.c_int(), C.c_int(), C.c_int()
-        _lib.call('st_tile_grid', H, W, tile_size, C.byref(nty), C.byref(ntx), C.byref(thmax),
-                  C.byref(twmax))
-        ntiles = nty.value * ntx.value
-        per_rank = (ntiles + self.world - 1) // self.world
-        shape = (per_rank, 3, thmax.value, twmax.value)
+        shape = sharding.packed_shape(H, W, tile_size, self.world)
         if self._packed is None or self._packed.shape != shape:
             self._packed = torch.zeros(shape, dtype=torch.float32, device=self.device)
-            self._packed_all = torch.zeros((self.world,) + shape, dtype=torch.float32,
-                                           device=self.device) if self.world > 1 else None
         loss = torch.zeros(1, dtype=torch.float64, device=self.device)
         _lib.call('st_eval_sc_grad_tiles', self.ctx, _ptr(img), H, W, ry, rx, tile_size, self.rank,
                   self.world, len(layers), specs, _ptr(loss), _ptr(self._packed), _stream())
-        packed_all = self._packed
-        if self.world > 1:
-            import torch.distributed as dist
-            dist.all_gather_into_tensor(self._packed_all, self._packed, group=self.group)
-            dist.all_reduce(loss, group=self.group)
-            packed_all = self._packed_all
+        packed_all, loss = sharding.exchange(self._packed, loss, self.world, self.group)
         grad = torch.empty_like(img)
         _lib.call('st_unpack_grad', _ptr(packed_all), H, W, ry, rx, tile_size, self.world,
                   _ptr(grad), _stream())

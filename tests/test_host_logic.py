@@ -1,0 +1,188 @@
+"""CPU tests of the host side: the C-ABI library loads and exports what include/style_b200.h
+declares, the tile geometry / sharding logic matches the reference's arithmetic, the network
+descriptions match the reference's deploy files, and a world-size-2 gloo run of the dispatcher
+(CPU oracle as a stand-in for the per-tile operator) reproduces the single-process result."""
+
+import ctypes as C
+import os
+import re
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+# ---- C ABI ------------------------------------------------------------------------------------------
+def declared_symbols():
+    text = open(os.path.join(ROOT, 'include', 'style_b200.h')).read()
+    text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
+    return re.findall(r'ST_API\s+[\w\s\*]+?\b(st_\w+)\s*\(', text)
+
+
+def test_header_symbols_are_exported_and_bound():
+    from style_transfer_b200 import _lib
+    names = declared_symbols()
+    assert len(names) >= 25 and len(set(names)) == len(names)
+    lib = C.CDLL(_lib.LIB_PATH)
+    for name in names:
+        assert hasattr(lib, name), 'libstyle_b200.so does not export %s' % name
+        assert name in _lib.PROTOTYPES, 'no ctypes prototype for %s' % name
+    assert set(_lib.PROTOTYPES) == set(names)
+    assert _lib.load().st_version() >= 100
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device the context cannot be created and the engine refuses to construct."""
+    import torch
+    from style_transfer_b200 import _lib, netdesc, weights
+    from style_transfer_b200.engine import TileEngine
+    if torch.cuda.is_available():
+        pytest.skip('a GPU is present')
+    net = netdesc.from_model('vgg16.prototxt')
+    with pytest.raises(_lib.StError):
+        TileEngine(net, weights.he_normal(net))
+    ctx = C.c_void_p()
+    rc = _lib.load().st_create(0, 0, len(net.layers), net.to_ctypes(), C.byref(ctx))
+    assert rc < 0 and _lib.load().st_last_error()
+
+
+@pytest.mark.parametrize('H,W,tile', [(2048, 2048, 512), (1448, 1448, 512), (724, 724, 512),
+                                      (75, 52, 40), (64, 96, 32), (256, 256, 512), (513, 512, 512)])
+def test_tile_grid_matches_reference_arithmetic(H, W, tile):
+    from oracle.tile_operator import tile_grid as oracle_grid
+    from style_transfer_b200 import _lib, sharding
+    boxes = sharding.tile_boxes(H, W, tile)
+    want = [(int(s[0]), int(s[1]), int(e[0]), int(e[1])) for s, e in oracle_grid((H, W), tile)]
+    assert boxes == want
+    nty, ntx, thm, twm = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+    _lib.call('st_tile_grid', H, W, tile, C.byref(nty), C.byref(ntx), C.byref(thm), C.byref(twm))
+    g = sharding.tile_grid(H, W, tile)
+    assert (nty.value, ntx.value, thm.value, twm.value) == (g[0], g[1], g[4], g[5])
+    assert thm.value == max(b[2] - b[0] for b in boxes) and twm.value == max(b[3] - b[1] for b in boxes)
+    # round-robin placement: every tile exactly once, slots consecutive per rank
+    for world in (1, 2, 3, 4, 8):
+        seen = []
+        for rank in range(world):
+            local = sharding.local_tiles(H, W, tile, rank, world)
+            assert [s for s, _ in local] == list(range(len(local)))
+            seen += [b for _, b in local]
+        assert sorted(seen) == sorted(boxes)
+        assert sharding.packed_shape(H, W, tile, world)[0] == -(-len(boxes) // world)
+
+
+def test_scale_ladder_and_weights():
+    from style_transfer_b200.transfer import default_args, parse_weights, scale_ladder
+    assert scale_ladder(2048, 256) == [256, 362, 512, 724, 1024, 1448, 2048]
+    assert scale_ladder(256, 182) == [256]
+    names, w = parse_weights(['conv4_2:2', 'conv5_1'], 0.05)
+    assert names == ['conv4_2', 'conv5_1']
+    assert w['conv4_2'] == pytest.approx(0.05 * 2 / 3) and w['conv5_1'] == pytest.approx(0.05 / 3)
+    a = default_args()
+    assert (a.size, a.tile_size, a.optimizer, a.step_size, a.avg_window) == (256, 512, 'adam', 15.0, 20.0)
+    assert a.style_layers == ['conv1_1', 'conv2_1', 'conv3_1', 'conv4_1', 'conv5_1']
+
+
+# ---- network descriptions -----------------------------------------------------------------------------
+@pytest.mark.parametrize('name', ['vgg16', 'vgg19', 'vgg16_avgpool', 'vgg19_avgpool', 'vgg16_big',
+                                  'vgg19_big'])
+def test_netdesc_roundtrip_and_reference_prototxt(name):
+    from style_transfer_b200 import netdesc
+    net = netdesc.from_model(name + '.prototxt')
+    again = netdesc.parse_prototxt(netdesc.to_prototxt(net), name)
+    assert [(l.kind, l.name, l.bottom, l.cin, l.cout, l.pool) for l in again.layers] == \
+        [(l.kind, l.name, l.bottom, l.cin, l.cout, l.pool) for l in net.layers]
+    assert net.layer_info('conv4_2') == (8, 512) if 'big' not in name else True
+    ref = os.path.join('/root/reference', name + '.prototxt')
+    if os.path.exists(ref):                       # only in the build container
+        parsed = netdesc.parse_prototxt(open(ref).read(), name)
+        assert [(l.kind, l.name, l.bottom, l.cin, l.cout, l.pool) for l in parsed.layers] == \
+            [(l.kind, l.name, l.bottom, l.cin, l.cout, l.pool) for l in net.layers]
+        assert parsed.shapes == net.shapes
+
+
+def test_reference_shape_tables():
+    """The shape tables the reference hard-codes (style_transfer.py:1030-1073)."""
+    from style_transfer_b200 import netdesc
+    net = netdesc.from_model('vgg19.prototxt')
+    assert net.shapes['conv1_1'] == (64, 224, 224) and net.shapes['pool5'] == (512, 7, 7)
+    assert net.shapes['conv3_4'] == (256, 56, 56) and net.shapes['conv5_1'] == (512, 14, 14)
+    assert [net.layer_info(l)[0] for l in ('conv1_1', 'conv2_1', 'conv3_1', 'conv4_1', 'conv5_1')] == \
+        [1, 2, 4, 8, 16]
+    assert 'conv3_4' not in netdesc.from_model('vgg16.prototxt').shapes
+
+
+# ---- world-size-2 dispatcher run over gloo --------------------------------------------------------------
+def _dispatcher_worker(rank, world, port, H, W, tile, roll, out_path):
+    """One rank: evaluates its round-robin tiles with the CPU oracle (standing in for the CUDA
+    per-tile operator), exchanges them exactly as TileEngine.eval_sc_grad does."""
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    from oracle import numeric as on
+    from oracle.caffe_net import he_normal_weights, model_layers
+    from oracle.tile_operator import OracleModel
+    from oracle.transfer import to_params
+    from style_transfer_b200 import sharding
+    os.environ['MASTER_ADDR'], os.environ['MASTER_PORT'] = '127.0.0.1', str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    model = 'vgg16.prototxt'
+    ora = OracleModel(model, he_normal_weights(model_layers(model)))
+    rs = np.random.RandomState(0)
+    img, content, style = (to_params(rs.randint(0, 256, (H, W, 3))) for _ in range(3))
+    c_layers, s_layers = ['conv2_2'], ['conv1_1', 'conv2_1']
+    ora.img = style
+    ora.styles = [{l: on.gram_lower(f) for l, f in ora.features_once(s_layers, tile).items()}]
+    ora.img = content
+    ora.contents = [ora.features_once(c_layers, tile)]
+    ora.publish()
+    lw = {l: 1.0 for l in ora.layers()}
+    cw, sw = {'conv2_2': 0.05}, {'conv1_1': 0.5, 'conv2_1': 0.5}
+    layers = ora.ordered_layers(c_layers, s_layers)
+    rolled = on.roll2_(img.copy(), np.array(roll))
+    ora.roll_features_all(ora.w_contents, np.array(roll), 1)
+    packed = torch.zeros(sharding.packed_shape(H, W, tile, world), dtype=torch.float32)
+    loss = torch.zeros(1, dtype=torch.float64)
+    for slot, (sy, sx, ey, ex) in sharding.local_tiles(H, W, tile, rank, world):
+        l, g = ora.sc_grad_tile(np.ascontiguousarray(rolled[:, sy:ey, sx:ex]), np.array([sy, sx]),
+                                layers, c_layers, s_layers, [], lw, cw, sw, {})
+        packed[slot, :, :ey - sy, :ex - sx] = torch.from_numpy(g)
+        loss += l
+    packed_all, loss = sharding.exchange(packed, loss, world)
+    grad = sharding.unpack_numpy(packed_all.numpy(), H, W, tile, roll[1], roll[0])
+    if rank == 0:
+        np.savez(out_path, grad=grad, loss=loss.numpy())
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(600)
+def test_two_rank_dispatch_over_gloo(tmp_path):
+    import torch.multiprocessing as mp
+    from oracle import numeric as on
+    from oracle.caffe_net import he_normal_weights, model_layers
+    from oracle.tile_operator import OracleModel
+    from oracle.transfer import to_params
+    H, W, tile, roll = 40, 56, 24, (8, -16)
+    out = str(tmp_path / 'two_rank.npz')
+    port = 29500 + os.getpid() % 400
+    mp.spawn(_dispatcher_worker, args=(2, port, H, W, tile, roll, out), nprocs=2, join=True)
+    got = np.load(out)
+    # single-process oracle of the same evaluation (eval_sc_grad, style_transfer.py:614-645)
+    model = 'vgg16.prototxt'
+    ora = OracleModel(model, he_normal_weights(model_layers(model)))
+    rs = np.random.RandomState(0)
+    img, content, style = (to_params(rs.randint(0, 256, (H, W, 3))) for _ in range(3))
+    c_layers, s_layers = ['conv2_2'], ['conv1_1', 'conv2_1']
+    ora.img = style
+    ora.styles = [{l: on.gram_lower(f) for l, f in ora.features_once(s_layers, tile).items()}]
+    ora.img = content
+    ora.contents = [ora.features_once(c_layers, tile)]
+    ora.publish()
+    lw = {l: 1.0 for l in ora.layers()}
+    ora.img = on.roll2_(img.copy(), np.array(roll))
+    loss, grad = ora.sc_grad(np.array(roll), c_layers, s_layers, [], lw, {'conv2_2': 0.05},
+                             {'conv1_1': 0.5, 'conv2_1': 0.5}, {}, tile)
+    grad = on.roll2_(grad.copy(), -np.array(roll))
+    assert np.array_equal(got['grad'], grad)
+    assert abs(float(got['loss'][0]) - loss) <= 1e-9 * abs(loss)
