@@ -42,7 +42,7 @@ namespace {
 constexpr int kBH = 16, kBW = 8;          // pixels per CTA tile: 16 rows x 8 columns = 128 = TMEM lanes
 constexpr int kRowBytes = kBW * 128;      // one tile row of one 64-channel block: one swizzle atom
 constexpr int kThreads2 = 224;
-constexpr uint32_t kSpin = 1u << 26;
+constexpr uint32_t kSpin = 1u << 24;
 constexpr int kOutStageBytes = 128 * 128; // 128 pixels x 64 channels bf16
 constexpr int kSmemBudget = 227 * 1024 - 1024 /*alignment slack*/ - 512 /*barriers*/;
 
@@ -74,10 +74,21 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
                "r"(bytes)
                : "memory");
 }
-// arrive on a barrier of any CTA of the cluster (cluster address)
+// arrive on a barrier of any CTA of the cluster (cluster address).  Default semantics
+// (release at CTA scope): the explicit .release.cluster form costs a MEMBAR.ALL.GPU per arrive.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr)
-               : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// One lane of a converged warp.  The role loops below run warp-wide with warp-uniform state and
+// only the TMA / MMA / commit instructions sit under elect_one(): that keeps descriptors and
+// coordinates in uniform registers (a lane-0-only loop makes ptxas re-broadcast every operand
+// with R2UR before each UTCHMMA / UTMALDG: ~190 cycles per MMA, profiles/r01_conv_v2_issue.md).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
@@ -274,16 +285,16 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constan
 
   if (warp == 0) {
     // ===================================== A producer ============================================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
-        const TileCoord t = decode_tile(a, tile, (int)rank);
-        for (int cb = 0; cb < kb_per_tap; ++cb) {
-          mbar_wait(&a_empty[stage], phase ^ 1);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+      const TileCoord t = decode_tile(a, tile, (int)rank);
+      for (int cb = 0; cb < kb_per_tap; ++cb) {
+        mbar_wait(&a_empty[stage], phase ^ 1);
+        const uint32_t bar = map_to_cta(smem_u32(&a_full[stage]), 0);
+        uint8_t* dst = a_base + stage * Cfg::kABytes;
+        if (elect_one()) {
           if (leader) mbar_expect_tx(&a_full[stage], 2 * Cfg::kABytes);
-          const uint32_t bar = map_to_cta(smem_u32(&a_full[stage]), 0);
-          uint8_t* dst = a_base + stage * Cfg::kABytes;
           if constexpr (TAPS == 9) {
 #pragma unroll
             for (int v = 0; v < 3; ++v)
@@ -292,34 +303,36 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constan
           } else {
             tma_load_4d_pair(&map_in, bar, dst, cb * 64, t.x0, t.y0, t.b);
           }
-          if (++stage == Cfg::kSA) stage = 0, phase ^= 1;
         }
+        __syncwarp();
+        if (++stage == Cfg::kSA) stage = 0, phase ^= 1;
       }
     }
   } else if (warp == 6) {
     // ===================================== B producer ============================================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
-        const TileCoord t = decode_tile(a, tile, (int)rank);
-        const int n0 = t.n_tile * BN + (int)rank * (BN / 2);
-        const int wb = a.w_batched ? t.b : 0;
-        for (int cb = 0; cb < kb_per_tap; ++cb) {
-          for (int tap = 0; tap < TAPS; ++tap) {
-            mbar_wait(&b_empty[stage], phase ^ 1);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+      const TileCoord t = decode_tile(a, tile, (int)rank);
+      const int n0 = t.n_tile * BN + (int)rank * (BN / 2);
+      const int wb = a.w_batched ? t.b : 0;
+      for (int cb = 0; cb < kb_per_tap; ++cb) {
+        for (int tap = 0; tap < TAPS; ++tap) {
+          mbar_wait(&b_empty[stage], phase ^ 1);
+          const uint32_t bar = map_to_cta(smem_u32(&b_full[stage]), 0);
+          if (elect_one()) {
             if (leader) mbar_expect_tx(&b_full[stage], 2 * Cfg::kBBytes);
-            const uint32_t bar = map_to_cta(smem_u32(&b_full[stage]), 0);
             tma_load_3d_pair(&map_w, bar, b_base + stage * Cfg::kBBytes, tap * a.cin + cb * 64, n0,
                              wb);
-            if (++stage == Cfg::kSB) stage = 0, phase ^= 1;
           }
+          __syncwarp();
+          if (++stage == Cfg::kSB) stage = 0, phase ^= 1;
         }
       }
     }
   } else if (warp == 1) {
     // ===================================== MMA issuer (leader) ===================================
-    if (leader && lane == 0) {
+    if (leader) {
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0, it = 0;
       for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
@@ -338,17 +351,22 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constan
             if constexpr (TAPS == 9) a_tap += (tap % 3) * Cfg::kAVarBytes + (tap / 3) * kRowBytes;
             const uint64_t da = make_smem_desc(a_tap);
             const uint64_t db = make_smem_desc(smem_u32(b_base + sb * Cfg::kBBytes));
+            if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              tc_mma_pair(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), Cfg::kIdesc,
-                          (cb | tap | k) != 0);
-            tc_commit_pair(&b_empty[sb]);
+              for (int k = 0; k < 4; ++k)
+                tc_mma_pair(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), Cfg::kIdesc,
+                            (cb | tap | k) != 0);
+              tc_commit_pair(&b_empty[sb]);
+              if (tap == TAPS - 1) {
+                tc_commit_pair(&a_empty[sa]);
+                if (cb == kb_per_tap - 1) tc_commit_pair(&t_full[buf]);
+              }
+            }
+            __syncwarp();
             if (++sb == Cfg::kSB) sb = 0, pb ^= 1;
           }
-          tc_commit_pair(&a_empty[sa]);
           if (++sa == Cfg::kSA) sa = 0, pa ^= 1;
         }
-        tc_commit_pair(&t_full[buf]);
       }
     }
   } else {

@@ -30,7 +30,7 @@ namespace {
 
 constexpr int kGThreads = 192;
 constexpr int kBoxBytes = 64 * 128;       // 64 pixels x 64 channels bf16
-constexpr uint32_t kSpinG = 1u << 26;
+constexpr uint32_t kSpinG = 1u << 24;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return (uint32_t)__cvta_generic_to_shared(p);
@@ -119,6 +119,13 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "memory");
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 // MN-major SWIZZLE_128B descriptor: 64-element MN groups kBoxBytes apart (LBO), 8-row K groups
 // 1024 bytes apart (SBO).
 __device__ __forceinline__ uint64_t make_desc_mn(uint32_t smem_addr) {
@@ -191,27 +198,29 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap map_f, const GramArgs a) {
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int kb = kb_begin; kb < kb_end; ++kb) {
-        mbar_wait(&empty[stage], phase ^ 1);
+    // warp-wide loops with warp-uniform state; only the TMA / MMA issue is elected (see conv_tc2.cu)
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int kb = kb_begin; kb < kb_end; ++kb) {
+      mbar_wait(&empty[stage], phase ^ 1);
+      uint8_t* dst = smem + stage * Cfg::kStageBytes;
+      if (elect_one()) {
         mbar_expect_tx(&full[stage], Cfg::kGroups * kBoxBytes);
-        uint8_t* dst = smem + stage * Cfg::kStageBytes;
 #pragma unroll
         for (int g = 0; g < Cfg::kGroups; ++g)
           tma_load_3d(&map_f, &full[stage], dst + g * kBoxBytes, g * 64, kb * 64, b);
-        if (++stage == Cfg::kStages) stage = 0, phase ^= 1;
       }
+      __syncwarp();
+      if (++stage == Cfg::kStages) stage = 0, phase ^= 1;
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int kb = kb_begin; kb < kb_end; ++kb) {
-        mbar_wait(&full[stage], phase);
-        tc_fence_after();
-        const uint32_t base = smem_u32(smem + stage * Cfg::kStageBytes);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int kb = kb_begin; kb < kb_end; ++kb) {
+      mbar_wait(&full[stage], phase);
+      tc_fence_after();
+      const uint32_t base = smem_u32(smem + stage * Cfg::kStageBytes);
+      if (elect_one()) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) {               // 16 pixels of K per MMA: 2 KB down the box
           const uint64_t da = make_desc_mn(base + (2 * mb) * kBoxBytes + k * 2048);
@@ -222,9 +231,10 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap map_f, const GramArgs a) {
           }
         }
         tc_commit(&empty[stage]);
-        if (++stage == Cfg::kStages) stage = 0, phase ^= 1;
+        if (kb == kb_end - 1) tc_commit(tfull);
       }
-      tc_commit(tfull);
+      __syncwarp();
+      if (++stage == Cfg::kStages) stage = 0, phase ^= 1;
     }
   } else {
     const int q = warp & 3;

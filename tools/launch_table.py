@@ -10,8 +10,12 @@ with open(path) as f:
 names = [(r['Kernel Name'], float(r['Metric Value'].replace(',', '')) / 1000, r['Grid Size']) for r in rows]
 ends = [i for i, n in enumerate(names) if 'conv_last_bwd' in n[0]]
 start = ends[-2] + 1 if len(ends) > 1 else 0
+stop = ends[-1] + 1
+if '--step' in sys.argv:     # a whole optimizer step: up to and including the last adam kernel
+    adams = [i for i, n in enumerate(names) if 'adam_kernel' in n[0]]
+    start, stop = adams[-2] + 1, adams[-1] + 1
 total, agg = 0.0, OrderedDict()
-for name, us, grid in names[start:ends[-1] + 1]:
+for name, us, grid in names[start:stop]:
     short = re.sub(r'\(.*', '', name).replace('void ', '').replace('st::', '').replace('<unnamed>::', '')[:64]
     if '-v' in sys.argv:
         print('%-66s %8.1f us  grid %s' % (short, us, grid))
