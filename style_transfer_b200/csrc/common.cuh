@@ -109,13 +109,60 @@ template <> struct Store<__nv_bfloat16> {
   }
 };
 
+// 8 consecutive channels at once: 16 bytes of bf16 / 32 bytes of float
+struct F8 {
+  float v[8];
+};
+__device__ __forceinline__ F8 ld8(const float* p) {
+  const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+  return F8{{a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w}};
+}
+__device__ __forceinline__ void st8(float* p, const F8& f) {
+  *reinterpret_cast<float4*>(p) = make_float4(f.v[0], f.v[1], f.v[2], f.v[3]);
+  *reinterpret_cast<float4*>(p + 4) = make_float4(f.v[4], f.v[5], f.v[6], f.v[7]);
+}
+__device__ __forceinline__ F8 ld8(const __nv_bfloat16* p) {
+  const uint4 raw = *reinterpret_cast<const uint4*>(p);
+  const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+  F8 f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    f.v[2 * i] = __uint_as_float(w[i] << 16);
+    f.v[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u);
+  }
+  return f;
+}
+__device__ __forceinline__ void st8(__nv_bfloat16* p, const F8& f) {
+  uint32_t w[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(f.v[2 * i], f.v[2 * i + 1]);
+    w[i] = *reinterpret_cast<uint32_t*>(&h);
+  }
+  *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+}
+
 // ---- deterministic grid reductions ----------------------------------------------------------------
 // Each block reduces K doubles, publishes them, takes a ticket; the last block to arrive sums the
 // per-block partials in index order (fixed grid => bit-reproducible) and returns true on its
 // thread 0 with the totals in `v`.  `partials` must hold gridDim.x*K doubles; `*counter` must be 0
 // on entry and is reset to 0 on exit.  All threads of the block must call it.
 template <int K>
+__device__ __forceinline__ bool grid_reduce_impl(double (&v)[K], double* partials, unsigned* counter,
+                                                 unsigned block_id, unsigned num_blocks);
+template <int K>
 __device__ __forceinline__ bool grid_reduce(double (&v)[K], double* partials, unsigned* counter) {
+  return grid_reduce_impl<K>(v, partials, counter, blockIdx.x, gridDim.x);
+}
+// same, for a (gridDim.x, gridDim.y) grid reduced as one
+template <int K>
+__device__ __forceinline__ bool grid_reduce_2d(double (&v)[K], double* partials, unsigned* counter) {
+  return grid_reduce_impl<K>(v, partials, counter, blockIdx.y * gridDim.x + blockIdx.x,
+                             gridDim.x * gridDim.y);
+}
+template <int K>
+__device__ __forceinline__ bool grid_reduce_impl(double (&v)[K], double* partials, unsigned* counter,
+                                                 unsigned block_id, unsigned num_blocks) {
   __shared__ double sh[K][32];
   __shared__ bool is_last;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = (blockDim.x + 31) >> 5;
@@ -133,13 +180,13 @@ __device__ __forceinline__ bool grid_reduce(double (&v)[K], double* partials, un
       double x = lane < nwarps ? sh[k][lane] : 0.0;
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-      if (lane == 0) partials[(size_t)blockIdx.x * K + k] = x;
+      if (lane == 0) partials[(size_t)block_id * K + k] = x;
     }
   }
   if (threadIdx.x == 0) {
     __threadfence();
     unsigned ticket = atomicAdd(counter, 1u);
-    is_last = (ticket == gridDim.x - 1);
+    is_last = (ticket == num_blocks - 1);
   }
   __syncthreads();
   if (!is_last) return false;
@@ -147,7 +194,7 @@ __device__ __forceinline__ bool grid_reduce(double (&v)[K], double* partials, un
 #pragma unroll
   for (int k = 0; k < K; ++k) {
     double x = 0.0;
-    for (unsigned b = threadIdx.x; b < gridDim.x; b += blockDim.x)
+    for (unsigned b = threadIdx.x; b < num_blocks; b += blockDim.x)
       x += partials[(size_t)b * K + k];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);

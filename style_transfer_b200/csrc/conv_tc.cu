@@ -501,6 +501,22 @@ int tc_pack_weights(TcContext& tc, TcWeights& w, const float* w_host, int cin, i
   return rc;
 }
 
+int tc_pack_first(TcContext& tc, TcWeights& w, const float* w_host, int cout) {
+  if (!tc.enabled || !tc.pair_kernel) return ST_OK;
+  const int rows = 16;
+  std::vector<__nv_bfloat16> host((size_t)rows * 9 * cout, __float2bfloat16_rn(0.f));
+  for (int co = 0; co < cout; ++co)
+    for (int ci = 0; ci < 3; ++ci)
+      for (int ky = 0; ky < 3; ++ky)
+        for (int kx = 0; kx < 3; ++kx)
+          host[(size_t)ci * 9 * cout + (size_t)((2 - ky) * 3 + (2 - kx)) * cout + co] =
+              __float2bfloat16_rn(w_host[(((size_t)co * 3 + ci) * 3 + ky) * 3 + kx]);
+  if (!w.bwd) ST_CUDA(cudaMalloc((void**)&w.bwd, host.size() * sizeof(__nv_bfloat16)));
+  ST_CUDA(cudaMemcpy(w.bwd, host.data(), host.size() * sizeof(__nv_bfloat16),
+                     cudaMemcpyHostToDevice));
+  return ST_OK;
+}
+
 void tc_free_weights(TcWeights& w) {
   cudaFree(w.fwd), cudaFree(w.bwd);
   delete static_cast<CUtensorMap*>(w.map_fwd);

@@ -29,6 +29,8 @@ struct TcContext {
 int tc_init(TcContext& tc, int sm_count);
 void tc_destroy(TcContext& tc);
 int tc_pack_weights(TcContext& tc, TcWeights& w, const float* w_oihw_host, int cin, int cout);
+// First layer (cin = 3): only the backward pack, [16][9*cout] with rows 3..15 zero.
+int tc_pack_first(TcContext& tc, TcWeights& w, const float* w_oihw_host, int cout);
 void tc_free_weights(TcWeights& w);
 
 bool tc_shape_ok(const TcContext& tc, const TcWeights& w, int cin, int cout);
@@ -49,6 +51,16 @@ int conv3x3_tc(TcContext& tc, const TcWeights& w, const __nv_bfloat16* in, __nv_
 int conv3x3_tc_pair(TcContext& tc, const TcWeights& w, const __nv_bfloat16* in, __nv_bfloat16* out,
                     int nb, int h, int wd, int cin, int cout, bool forward, const float* bias,
                     const __nv_bfloat16* mask_act, const __nv_bfloat16* inj, cudaStream_t s);
+// Backward of the first (3-channel) convolution on tensor cores: dz [nb][h][w][cz] bf16 -> planar f32
+// gradient; tile b goes to grad + b * batch_stride.  Needs weights packed by tc_pack_first.
+int conv_last_bwd_tc_pair(TcContext& tc, const TcWeights& w, const __nv_bfloat16* dz, int nb, int h,
+                          int wd, int cz, float* grad, long batch_stride, long plane_stride,
+                          long row_stride, cudaStream_t s);
+// First convolution (3 -> 64 channels) on tensor cores from the planar f32 image (conv_first_tc.cu).
+struct ImageBatch;
+int tc_pack_first_fwd(TcContext& tc, TcWeights& w, const float* w_oihw_host, int cout);
+int conv_first_fwd_tc(TcContext& tc, const TcWeights& w, const ImageBatch& img, int h, int wd,
+                      const float* bias, __nv_bfloat16* out, cudaStream_t s);
 // Per batch tile b: S_b[p][n] = sum_c F_b[p][c] * D_b[n][c] for F [nb][h][w][c] and D [nb][c][c]
 // (bf16).  sum |S_b| is left as partial sums abs_partials[b * per_tile + i], i < *per_tile, to be
 // added in index order; the buffer must hold gemm_abs_partials_needed() doubles.

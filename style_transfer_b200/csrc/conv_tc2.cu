@@ -46,7 +46,7 @@ constexpr uint32_t kSpin = 1u << 24;
 constexpr int kOutStageBytes = 128 * 128; // 128 pixels x 64 channels bf16
 constexpr int kSmemBudget = 227 * 1024 - 1024 /*alignment slack*/ - 512 /*barriers*/;
 
-enum Epilogue { kEpiFwd = 0, kEpiBwd = 1, kEpiAbs = 2 };
+enum Epilogue { kEpiFwd = 0, kEpiBwd = 1, kEpiAbs = 2, kEpiPix = 3 };
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -195,6 +195,17 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "memory");
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32"
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
 // K-major SWIZZLE_128B shared-memory matrix descriptor: 128-byte rows, 8-row groups 1024 B apart.
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
   return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) |
@@ -209,6 +220,8 @@ struct Tc2Args {
   const __nv_bfloat16* mask_act;   // kEpiBwd, NHWC [h][w][cout], may be null
   const __nv_bfloat16* inj;        // kEpiBwd, may be null
   double* abs_partials;            // kEpiAbs: [pair tile][cta rank][epilogue warp]
+  float* pix;                      // kEpiPix: planar f32 output, channels 0..2 of the accumulator
+  long pix_batch, pix_plane, pix_row;   // strides (floats) between batch tiles / planes / rows
 };
 
 struct TileCoord {
@@ -388,6 +401,21 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constan
       mbar_wait(&t_full[buf], use & 1);
       tc_fence_after();
       const uint32_t taddr = tmem_base + buf * BN + ((uint32_t)(q * 32) << 16);
+      if constexpr (EPI == kEpiPix) {
+        // backward of the first convolution: accumulator columns 0..2 are d(loss)/d(pixel) of the
+        // three image planes; written straight to the planar f32 gradient (no staging, no TMA)
+        uint32_t r[16];
+        tmem_ld16(taddr, r);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(map_to_cta(smem_u32(&t_empty[buf]), 0));
+        if (valid) {
+          float* dst = a.pix + (size_t)t.b * a.pix_batch + (size_t)py * a.pix_row + px;
+#pragma unroll
+          for (int ci = 0; ci < 3; ++ci) dst[(size_t)ci * a.pix_plane] = __uint_as_float(r[ci]);
+        }
+        continue;
+      }
 #pragma unroll 1
       for (int g = 0; g < BN / 64; ++g, ++store_seq) {
         uint8_t* stage_out = out_base + (store_seq & 1) * kOutStageBytes;
@@ -525,13 +553,15 @@ int launch2(TcContext& tc, const __nv_bfloat16* in, const __nv_bfloat16* wk, int
     int rc = encode_bf16_map(tc, &map_in, 4, in, dims, strides, box);
     if (rc != ST_OK) return rc;
   }
-  {
+  if (EPI != kEpiPix) {
     const uint64_t dims[4] = {(uint64_t)a.cout, (uint64_t)a.w, (uint64_t)a.h, (uint64_t)a.nb};
     const uint64_t strides[3] = {(uint64_t)a.cout * 2, (uint64_t)a.w * a.cout * 2,
                                  (uint64_t)a.h * a.w * a.cout * 2};
     const uint32_t box[4] = {64, (uint32_t)kBW, (uint32_t)kBH, 1};
     int rc = encode_bf16_map(tc, &map_out, 4, out, dims, strides, box);
     if (rc != ST_OK) return rc;
+  } else {
+    map_out = map_in;            // never dereferenced by the pixel epilogue
   }
   {
     const uint64_t k = (uint64_t)TAPS * a.cin;
@@ -551,8 +581,9 @@ int launch2(TcContext& tc, const __nv_bfloat16* in, const __nv_bfloat16* wk, int
   const int tiles = a.tiles_x * a.tiles_y * a.tiles_n * a.nb;
   const int max_pairs = tc.sm_count / 2;
   const int pairs = tiles < max_pairs ? tiles : max_pairs;
+  // algorithmic flops: the pixel epilogue computes 3 of its 16 accumulator columns for real
   TimerScope ts(s, EPI == kEpiAbs ? kTimeStyleGrad : kTimeConvTc,
-                2.0 * TAPS * a.cin * a.cout * a.h * a.w * a.nb);
+                2.0 * TAPS * a.cin * (EPI == kEpiPix ? 3 : a.cout) * a.h * a.w * a.nb);
   ST_LAUNCH(kern, 2 * pairs, kThreads2, Cfg::kSmemBytes, s, map_in, map_w, map_out, a);
   return ST_OK;
 }
@@ -594,6 +625,17 @@ int conv3x3_tc_pair(TcContext& tc, const TcWeights& w, const __nv_bfloat16* in, 
   const int bn = choose_bn(tc, nb, h, wd, cout);
   if (forward) return dispatch_bn<9, kEpiFwd>(tc, bn, in, w.fwd, cout, out, a, s);
   return dispatch_bn<9, kEpiBwd>(tc, bn, in, w.bwd, cout, out, a, s);
+}
+
+// Backward of the first convolution (cout image planes = 3, padded to 16 accumulator columns):
+// grad[b][ci][y][x] = sum_{tap, co} dz[b][p + off(tap)][co] * Wk[ci][tap*cz + co].
+int conv_last_bwd_tc_pair(TcContext& tc, const TcWeights& w, const __nv_bfloat16* dz, int nb, int h,
+                          int wd, int cz, float* grad, long batch_stride, long plane_stride,
+                          long row_stride, cudaStream_t s) {
+  Tc2Args a{};
+  a.nb = nb, a.h = h, a.w = wd, a.cin = cz, a.cout = 16;
+  a.pix = grad, a.pix_batch = batch_stride, a.pix_plane = plane_stride, a.pix_row = row_stride;
+  return launch2<16, 9, kEpiPix>(tc, dz, w.bwd, 16, nullptr, a, s);
 }
 
 // Per batch tile b: S_b[p][n] = sum_c F_b[p][c] * D_b[n][c]  (D_b symmetric bf16 [c][c]).  The sum

@@ -149,6 +149,10 @@ int ensure(st_ctx* ctx, void** p, size_t* cap, size_t elems, size_t esize) {
 
 inline int pooled(int n) { return (n + 1) / 2; }
 inline int floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
+inline int posmod(int a, int n) {
+  const int r = a % n;
+  return r < 0 ? r + n : r;
+}
 
 struct Dims {
   std::vector<int> h, w;
@@ -203,7 +207,14 @@ int forward(st_ctx* ctx, const ImageBatch& view, const Dims& d, int last_layer, 
     if (l.kind == ST_CONV3X3) {
       ST_REQUIRE(l.has_params, "conv layer has no weights (st_set_conv_params)");
       if (l.bottom == 0) {
-        rc = conv_first_fwd<T>(view, hb, wb, l.w_fwd, l.bias, out, l.cout, s);
+        bool done = false;
+        if constexpr (std::is_same<T, __nv_bfloat16>::value) {
+          if (ctx->tc.enabled && ctx->tc.pair_kernel && l.tc.fwd != nullptr && l.cout == 64) {
+            rc = conv_first_fwd_tc(ctx->tc, l.tc, view, hb, wb, l.bias, out, s);
+            done = true;
+          }
+        }
+        if (!done) rc = conv_first_fwd<T>(view, hb, wb, l.w_fwd, l.bias, out, l.cout, s);
       } else {
         const T* in = static_cast<const T*>(ctx->blobs[l.bottom].act);
         if (tc_usable<T>(ctx->tc, l.tc, l.cin, l.cout))
@@ -255,7 +266,9 @@ int build_injection(st_ctx* ctx, const st_loss_spec& sp, const Dims& d, const Ba
         // the reference slices [s0 : s0 + hf] out of the full map; a short slice is a shape error
         ST_REQUIRE(s0y + hf <= t.hf && s0x + wf <= t.wf,
                    "tile feature map does not fit into the content feature map at this offset");
-        offs.ty0[i] = s0y - floordiv(froll_y, b.scale), offs.tx0[i] = s0x - floordiv(froll_x, b.scale);
+        // reduced to [0, Hf) x [0, Wf): the kernels wrap with a single conditional subtract
+        offs.ty0[i] = posmod(s0y - floordiv(froll_y, b.scale), t.hf);
+        offs.tx0[i] = posmod(s0x - floordiv(froll_x, b.scale), t.wf);
       }
       rc = diff_stats<T>(f, nb, hf, wf, c, t.nhwc, t.hf, t.wf, offs, stats, kStatStride, ctx->rs, s);
       if (rc == ST_OK)
@@ -336,8 +349,14 @@ int backward(st_ctx* ctx, const Dims& d, int nb, int deepest_blob, const std::ve
     const LayerRt& l = ctx->layers[ctx->blobs[cur].producer];
     const int b = l.bottom;
     const int hb = d.h[b], wb = d.w[b];
-    if (l.kind == ST_CONV3X3 && b == 0)
+    if (l.kind == ST_CONV3X3 && b == 0) {
+      if constexpr (std::is_same<T, __nv_bfloat16>::value) {
+        if (ctx->tc.enabled && ctx->tc.pair_kernel && l.tc.bwd != nullptr && l.cout % 64 == 0)
+          return conv_last_bwd_tc_pair(ctx->tc, l.tc, g, nb, hb, wb, l.cout, grad, batch_stride,
+                                       plane, rstride, s);
+      }
       return conv_last_bwd<T>(g, nb, hb, wb, l.cout, l.w_bwd, grad, batch_stride, plane, rstride, s);
+    }
     ST_REQUIRE(b != 0, "a pooling layer directly on the image is not supported");
     const BlobRt& bb = ctx->blobs[b];
     const T* mask = bb.relu ? static_cast<const T*>(bb.act) : nullptr;
@@ -579,8 +598,9 @@ int st_set_conv_params(st_ctx* ctx, int layer, const float* w, const float* b) {
   ST_CUDA(cudaMemcpy(l.w_fwd, fwd.data(), fwd.size() * sizeof(float), cudaMemcpyHostToDevice));
   ST_CUDA(cudaMemcpy(l.w_bwd, bwd.data(), bwd.size() * sizeof(float), cudaMemcpyHostToDevice));
   ST_CUDA(cudaMemcpy(l.bias, b, co_n * sizeof(float), cudaMemcpyHostToDevice));
-  if (ctx->precision == ST_PREC_BF16 && !first) {
-    int rc = tc_pack_weights(ctx->tc, l.tc, w, ci_n, co_n);
+  if (ctx->precision == ST_PREC_BF16) {
+    int rc = first ? tc_pack_first(ctx->tc, l.tc, w, co_n) : tc_pack_weights(ctx->tc, l.tc, w, ci_n, co_n);
+    if (rc == ST_OK && first) rc = tc_pack_first_fwd(ctx->tc, l.tc, w, co_n);
     if (rc != ST_OK) return rc;
   }
   l.has_params = true;

@@ -267,22 +267,23 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap map_f, const GramArgs a) {
   if (warp == 1) tmem_dealloc(tmem_base, Cfg::kTmemCols);
 }
 
-// gram[b][i][j] = gram[b][j][i] = scale * sum_s part[b][s][max(i,j)][min(i,j)].  Eight lanes share
-// one element: lane l adds splits l, l+8, ... and the eight sums are combined in a fixed shuffle
-// order, so the result does not depend on the launch.  blockIdx.y = tile of the batch.
-__global__ void __launch_bounds__(256)
+// gram[b][i][j] = gram[b][j][i] = scale * sum_s part[b][s][i][j] for j <= i: one thread per
+// lower-triangle element (reads coalesced along j, splits added in index order), which also writes
+// the mirrored element so that the matrix is exactly symmetric.  blockIdx.y = row i, blockIdx.z = b.
+__global__ void __launch_bounds__(128)
 gram_tc_finalize_kernel(const float* __restrict__ part, int nsplit, int c, double scale,
                         float* __restrict__ gram) {
-  const int idx = (blockIdx.x * blockDim.x + threadIdx.x) >> 3, sub = threadIdx.x & 7;
-  const bool ok = idx < c * c;
-  const int i = ok ? idx / c : 0, j = ok ? idx % c : 0;
-  const int hi = i > j ? i : j, lo = i > j ? j : i;
-  const float* p = part + (size_t)blockIdx.y * nsplit * c * c + (size_t)hi * c + lo;
+  const int i = blockIdx.y, j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j > i) return;
+  const size_t cc = (size_t)c * c;
+  const float* p = part + (size_t)blockIdx.z * nsplit * cc + (size_t)i * c + j;
   double sum = 0.0;
-  for (int s = sub; s < nsplit; s += 8) sum += (double)p[(size_t)s * c * c];
-#pragma unroll
-  for (int o = 4; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-  if (ok && sub == 0) gram[(size_t)blockIdx.y * c * c + idx] = (float)(sum * scale);
+#pragma unroll 4
+  for (int s = 0; s < nsplit; ++s) sum += (double)p[(size_t)s * cc];
+  const float g = (float)(sum * scale);
+  float* out = gram + (size_t)blockIdx.z * cc;
+  out[(size_t)i * c + j] = g;
+  out[(size_t)j * c + i] = g;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
@@ -334,8 +335,8 @@ int launch_gram(TcContext& tc, const __nv_bfloat16* f, int nb, int hw, float* gr
   }
   TimerScope ts(s, kTimeGram, 2.0 * C * C * hw * nb);
   ST_LAUNCH(kern, dim3(a.nsplit * Cfg::kMBlocks, nb), kGThreads, Cfg::kSmemBytes, s, map_f, a);
-  ST_LAUNCH(gram_tc_finalize_kernel, dim3(cdiv((long)C * C * 8, 256), nb), 256, 0, s, part,
-            a.nsplit, C, 1.0 / ((double)C * hw), gram);
+  ST_LAUNCH(gram_tc_finalize_kernel, dim3(cdiv(C, 128), C, nb), 128, 0, s, part, a.nsplit, C,
+            1.0 / ((double)C * hw), gram);
   return ST_OK;
 }
 

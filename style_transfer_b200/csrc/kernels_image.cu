@@ -21,18 +21,20 @@ __global__ void unpack_grad_kernel(const float* __restrict__ packed, int H, int 
                                    int roll_x, int nty, int ntx, int th, int tw, int thmax,
                                    int twmax, int world, int tiles_per_rank,
                                    float* __restrict__ grad) {
-  const size_t n = (size_t)3 * H * W;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
-       i += (size_t)gridDim.x * blockDim.x) {
-    const int x = (int)(i % W);
-    const int y = (int)((i / W) % H);
-    const int c = (int)(i / ((size_t)W * H));
-    const int yr = wrap(y + roll_y, H), xr = wrap(x + roll_x, W);
-    const int ty = min(yr / th, nty - 1), tx = min(xr / tw, ntx - 1);
+  // blockIdx.y = image row, blockIdx.z = plane: no per-element div/mod on 64-bit indices
+  const int y = blockIdx.y, c = blockIdx.z;
+  int yr = y + roll_y;                                     // host passes the roll reduced to [0, H)
+  yr = yr >= H ? yr - H : yr;
+  const int ty = min(yr / th, nty - 1);
+  float* out = grad + ((size_t)c * H + y) * W;
+  for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < W; x += gridDim.x * blockDim.x) {
+    int xr = x + roll_x;
+    xr = xr >= W ? xr - W : xr;
+    const int tx = min(xr / tw, ntx - 1);
     const int t = ty * ntx + tx;
     const int rank = t % world, slot = t / world;
     const size_t base = ((size_t)(rank * tiles_per_rank + slot) * 3 + c) * thmax * twmax;
-    grad[i] = packed[base + (size_t)(yr - ty * th) * twmax + (xr - tx * tw)];
+    out[x] = packed[base + (size_t)(yr - ty * th) * twmax + (xr - tx * tw)];
   }
 }
 
@@ -40,14 +42,26 @@ int unpack_grad(const float* packed, int H, int W, int roll_y, int roll_x, int n
                 int th, int tw, int thmax, int twmax, int world, int tiles_per_rank, float* grad,
                 cudaStream_t s) {
   TimerScope ts(s, kTimeImage, 8.0 * 3 * H * W);
-  ST_LAUNCH(unpack_grad_kernel, ew_grid((size_t)3 * H * W, 256), 256, 0, s, packed, H, W, roll_y,
-            roll_x, nty, ntx, th, tw, thmax, twmax, world, tiles_per_rank, grad);
+  const int ry = ((roll_y % H) + H) % H, rx = ((roll_x % W) + W) % W;
+  ST_LAUNCH(unpack_grad_kernel, dim3(cdiv(W, 256), H, 3), 256, 0, s, packed, H, W, ry, rx, nty, ntx,
+            th, tw, thmax, twmax, world, tiles_per_rank, grad);
   return ST_OK;
 }
 
 // -----------------------------------------------------------------------------------------------------
 // Fused regularisers on the un-rolled image.
 // -----------------------------------------------------------------------------------------------------
+// |a|^(k) for small integer k by repeated multiplication (p_pow = 6 is the reference's default:
+// two powf per pixel made this kernel compute-bound)
+__device__ __forceinline__ float powi(float x, int k) {
+  float r = 1.f;
+  while (k > 0) {
+    if (k & 1) r *= x;
+    x *= x, k >>= 1;
+  }
+  return r;
+}
+
 struct TvTerm {
   float ddx, ddy, pw;   // d/d(dx), d/d(dy) contributions and g2^(beta/2)
 };
@@ -78,16 +92,16 @@ __global__ void regularizers_kernel(const float* __restrict__ img, int H, int W,
                                     const float* __restrict__ aux, float aux_w, int roll_y,
                                     int roll_x, double* loss_accum, float* __restrict__ grad,
                                     ReduceScratch rs) {
-  const size_t n = (size_t)3 * H * W;
   const float inv = 1.f / 127.5f;
   double v[1] = {0.0};
   float part = 0.f;
   int cnt = 0;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
-       i += (size_t)gridDim.x * blockDim.x) {
-    const int x = (int)(i % W);
-    const int y = (int)((i / W) % H);
-    const int c = (int)(i / ((size_t)W * H));
+  // one block row per (plane, image row) pair: rows are walked with a grid-stride loop over
+  // blockIdx.y so that the reduction grid stays small; no 64-bit div/mod per element
+  for (int rowid = blockIdx.y; rowid < 3 * H; rowid += gridDim.y)
+  for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < W; x += gridDim.x * blockDim.x) {
+    const int c = rowid / H, y = rowid - c * H;
+    const size_t i = ((size_t)c * H + y) * W + x;
     const float* pl = img + (size_t)c * H * W;
     const float raw = pl[(size_t)y * W + x];
     float g = 0.f, l = 0.f;
@@ -114,7 +128,8 @@ __global__ void regularizers_kernel(const float* __restrict__ img, int H, int W,
       } else if (p_pow == 2.f) {
         l += p_w * a * a, g += p_w * 2.f * a;
       } else {
-        const float mp1 = powf(mag, p_pow - 1.f);
+        const int ip = (int)p_pow;
+        const float mp1 = ((float)ip == p_pow && ip <= 16) ? powi(mag, ip - 1) : powf(mag, p_pow - 1.f);
         l += p_w * mp1 * mag, g += p_w * p_pow * sgn * mp1;
       }
     }
@@ -128,14 +143,16 @@ __global__ void regularizers_kernel(const float* __restrict__ img, int H, int W,
     if (++cnt == 32) v[0] += part, part = 0.f, cnt = 0;
   }
   v[0] += part;
-  if (grid_reduce<1>(v, rs.partials, rs.counter)) atomicAdd(loss_accum, v[0]);
+  // fold the 2-D grid into the 1-D layout grid_reduce expects
+  if (grid_reduce_2d<1>(v, rs.partials, rs.counter)) atomicAdd(loss_accum, v[0]);
 }
 
 int regularizers(const float* img, int H, int W, float m0, float m1, float m2, float tv_w,
                  float tv_beta, float p_w, float p_pow, const float* aux, float aux_w, int roll_y,
                  int roll_x, double* loss_accum, float* grad, ReduceScratch rs, cudaStream_t s) {
   TimerScope ts(s, kTimeImage, 4.0 * 3 * H * W * (3 + (aux ? 1 : 0)));
-  ST_LAUNCH(regularizers_kernel, ew_grid((size_t)3 * H * W, 256), 256, 0, s, img, H, W, m0, m1, m2,
+  const int gx = cdiv(W, 256), gy = min(3 * H, max(1, (148 * 16) / gx));
+  ST_LAUNCH(regularizers_kernel, dim3(gx, gy), 256, 0, s, img, H, W, m0, m1, m2,
             tv_w, tv_beta, p_w, p_pow, aux, aux_w, roll_y, roll_x, loss_accum, grad, rs);
   return ST_OK;
 }

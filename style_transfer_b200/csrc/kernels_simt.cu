@@ -267,66 +267,78 @@ int conv_last_bwd(const T* dz, int nb, int h, int w, int cz, const float* wpack,
 // backward pass recomputes that argmax from the stored input instead of saving a mask.
 // =====================================================================================================
 template <typename T>
-__global__ void pool_fwd_kernel(const T* __restrict__ in_all, T* __restrict__ out, int nb, int h,
-                                int w, int c, int ho, int wo, int is_max) {
-  const int c4 = c >> 2;
-  const size_t total = (size_t)nb * ho * wo * c4;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total;
-       i += (size_t)gridDim.x * blockDim.x) {
-    const int q = (int)(i % c4);
-    const size_t p = i / c4;                                  // pooled pixel over the whole batch
-    const int x = (int)(p % wo), y = (int)((p / wo) % ho);
-    const T* in = in_all + (p / ((size_t)wo * ho)) * ((size_t)h * w * c);
-    float4 m = is_max ? make_float4(-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX)
-                      : make_float4(0.f, 0.f, 0.f, 0.f);
+__global__ void __launch_bounds__(256)
+pool_fwd_kernel(const T* __restrict__ in_all, T* __restrict__ out, int nb, int h, int w, int c,
+                int ho, int wo, int is_max) {
+  // 32-bit index arithmetic throughout: 64-bit div/mod made these kernels instruction-bound
+  const unsigned c8 = c >> 3, uwo = wo, uho = ho;
+  const unsigned total = (unsigned)nb * ho * wo * c8;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const unsigned q = i % c8;
+    const unsigned p = i / c8;                                // pooled pixel over the whole batch
+    const unsigned row = p / uwo;
+    const int x = (int)(p - row * uwo), y = (int)(row % uho);
+    const T* in = in_all + (size_t)(row / uho) * ((size_t)h * w * c) + q * 8;
+    F8 v[4];
+    bool ok[4];
+#pragma unroll
+    for (int d = 0; d < 4; ++d) {                             // all four loads in flight together
+      const int yy = 2 * y + (d >> 1), xx = 2 * x + (d & 1);
+      ok[d] = yy < h && xx < w;
+      if (ok[d]) v[d] = ld8(in + ((size_t)yy * w + xx) * c);
+    }
+    F8 m;
     int cnt = 0;
 #pragma unroll
+    for (int k = 0; k < 8; ++k) m.v[k] = is_max ? -FLT_MAX : 0.f;
+#pragma unroll
     for (int d = 0; d < 4; ++d) {
-      const int yy = 2 * y + (d >> 1), xx = 2 * x + (d & 1);
-      if (yy < h && xx < w) {
-        const float4 v = Store<T>::ld4(in + ((size_t)yy * w + xx) * c + q * 4);
-        if (is_max) {
-          m.x = v.x > m.x ? v.x : m.x, m.y = v.y > m.y ? v.y : m.y;
-          m.z = v.z > m.z ? v.z : m.z, m.w = v.w > m.w ? v.w : m.w;
-        } else {
-          m.x += v.x, m.y += v.y, m.z += v.z, m.w += v.w;
-          ++cnt;
-        }
+      if (!ok[d]) continue;
+      ++cnt;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        if (is_max)
+          m.v[k] = v[d].v[k] > m.v[k] ? v[d].v[k] : m.v[k];   // strict '>': first maximum wins
+        else
+          m.v[k] += v[d].v[k];
       }
     }
     if (!is_max) {
       const float inv = (float)cnt;
-      m.x /= inv, m.y /= inv, m.z /= inv, m.w /= inv;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) m.v[k] /= inv;
     }
-    Store<T>::st4(out + p * c + q * 4, m);
+    st8(out + (size_t)p * c + q * 8, m);
   }
 }
 
 template <typename T>
-__global__ void pool_bwd_kernel(const T* __restrict__ d_out, const T* __restrict__ in_all,
-                                T* __restrict__ d_in_all, int nb, int h, int w, int c, int ho,
-                                int wo, int is_max, int apply_mask, const T* __restrict__ inj_all) {
-  const int c4 = c >> 2;
-  const size_t total = (size_t)nb * ho * wo * c4;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total;
-       i += (size_t)gridDim.x * blockDim.x) {
-    const int q = (int)(i % c4);
-    const size_t p = i / c4;
-    const int x = (int)(p % wo), y = (int)((p / wo) % ho);
-    const size_t boff = (p / ((size_t)wo * ho)) * ((size_t)h * w * c);
+__global__ void __launch_bounds__(256)
+pool_bwd_kernel(const T* __restrict__ d_out, const T* __restrict__ in_all, T* __restrict__ d_in_all,
+                int nb, int h, int w, int c, int ho, int wo, int is_max, int apply_mask,
+                const T* __restrict__ inj_all) {
+  const unsigned c4 = c >> 2, uwo = wo, uho = ho;
+  const unsigned total = (unsigned)nb * ho * wo * c4;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const unsigned q = i % c4;
+    const unsigned p = i / c4;
+    const unsigned row = p / uwo;
+    const int x = (int)(p - row * uwo), y = (int)(row % uho);
+    const size_t boff = (size_t)(row / uho) * ((size_t)h * w * c) + q * 4;
     const T* in = in_all + boff;
     T* d_in = d_in_all + boff;
     const T* inj = inj_all ? inj_all + boff : nullptr;
-    const float4 g = Store<T>::ld4(d_out + p * c + q * 4);
-    float4 v[4];
+    const float4 g = Store<T>::ld4(d_out + (size_t)p * c + q * 4);
+    float4 v[4], e[4];
     bool ok[4];
     int cnt = 0;
 #pragma unroll
     for (int d = 0; d < 4; ++d) {
       const int yy = 2 * y + (d >> 1), xx = 2 * x + (d & 1);
       ok[d] = yy < h && xx < w;
-      v[d] = ok[d] ? Store<T>::ld4(in + ((size_t)yy * w + xx) * c + q * 4)
-                   : make_float4(0.f, 0.f, 0.f, 0.f);
+      const size_t o = ((size_t)yy * w + xx) * c;
+      v[d] = ok[d] ? Store<T>::ld4(in + o) : make_float4(0.f, 0.f, 0.f, 0.f);
+      e[d] = (ok[d] && inj) ? Store<T>::ld4(inj + o) : make_float4(0.f, 0.f, 0.f, 0.f);
       cnt += ok[d];
     }
     int ax = 0, ay = 0, az = 0, aw = 0;
@@ -346,7 +358,6 @@ __global__ void pool_bwd_kernel(const T* __restrict__ d_out, const T* __restrict
     for (int d = 0; d < 4; ++d) {
       if (!ok[d]) continue;
       const int yy = 2 * y + (d >> 1), xx = 2 * x + (d & 1);
-      const size_t o = ((size_t)yy * w + xx) * c + q * 4;
       float4 r;
       if (is_max) {
         r.x = ax == d ? g.x : 0.f, r.y = ay == d ? g.y : 0.f;
@@ -358,11 +369,8 @@ __global__ void pool_bwd_kernel(const T* __restrict__ d_out, const T* __restrict
         r.x = v[d].x > 0.f ? r.x : 0.f, r.y = v[d].y > 0.f ? r.y : 0.f;
         r.z = v[d].z > 0.f ? r.z : 0.f, r.w = v[d].w > 0.f ? r.w : 0.f;
       }
-      if (inj) {
-        const float4 e = Store<T>::ld4(inj + o);
-        r.x += e.x, r.y += e.y, r.z += e.z, r.w += e.w;
-      }
-      Store<T>::st4(d_in + o, r);
+      r.x += e[d].x, r.y += e[d].y, r.z += e[d].z, r.w += e[d].w;
+      Store<T>::st4(d_in + ((size_t)yy * w + xx) * c, r);
     }
   }
 }
@@ -375,11 +383,12 @@ static inline int ew_grid(size_t work_items, int block) {
 
 template <typename T>
 int pool_fwd(const T* in, T* out, int nb, int h, int w, int c, bool is_max, cudaStream_t s) {
-  ST_REQUIRE(c % 4 == 0, "pool: channels must be a multiple of 4");
+  ST_REQUIRE(c % 8 == 0, "pool: channels must be a multiple of 8");
   const int ho = (h + 1) / 2, wo = (w + 1) / 2;
+  ST_REQUIRE((size_t)nb * ho * wo * c < ((size_t)1 << 31), "pool: batch too large for 32-bit indexing");
   auto k = pool_fwd_kernel<T>;
   TimerScope ts(s, kTimePool, (double)sizeof(T) * c * nb * ((double)h * w + (double)ho * wo));
-  ST_LAUNCH(k, ew_grid((size_t)nb * ho * wo * (c / 4), 256), 256, 0, s, in, out, nb, h, w, c, ho,
+  ST_LAUNCH(k, ew_grid((size_t)nb * ho * wo * (c / 8), 256), 256, 0, s, in, out, nb, h, w, c, ho,
             wo, is_max ? 1 : 0);
   return ST_OK;
 }
@@ -387,8 +396,9 @@ int pool_fwd(const T* in, T* out, int nb, int h, int w, int c, bool is_max, cuda
 template <typename T>
 int pool_bwd(const T* d_out, const T* in, T* d_in, int nb, int h, int w, int c, bool is_max,
              bool apply_mask, const T* inj, cudaStream_t s) {
-  ST_REQUIRE(c % 4 == 0, "pool: channels must be a multiple of 4");
+  ST_REQUIRE(c % 8 == 0, "pool: channels must be a multiple of 8");
   const int ho = (h + 1) / 2, wo = (w + 1) / 2;
+  ST_REQUIRE((size_t)nb * ho * wo * c < ((size_t)1 << 31), "pool: batch too large for 32-bit indexing");
   auto k = pool_bwd_kernel<T>;
   TimerScope ts(s, kTimePool, (double)sizeof(T) * c * nb *
                                   ((double)h * w * (2 + (inj ? 1 : 0)) + (double)ho * wo));
@@ -677,14 +687,17 @@ int inject_scaled(T* inj, const T* src, size_t n, int nb, float w, const double*
 // loss 0.5*sum c^2, gradient c / (mean|c| + EPS).  Two passes, c is never stored.
 // =====================================================================================================
 template <typename T>
-__device__ __forceinline__ float4 diff_at(const T* f, const float* tgt, size_t i4, int wf, int c4,
+__device__ __forceinline__ float4 diff_at(const T* f, const float* tgt, size_t i4_, int wf, int c4,
                                           int Hf, int Wf, int ty0, int tx0) {
-  float4 v = Store<T>::ld4(f + i4 * 4);
+  const unsigned i4 = (unsigned)i4_;         // per-tile element index: fits 32 bits (checked on host)
+  float4 v = Store<T>::ld4(f + (size_t)i4 * 4);
   if (tgt) {
-    const int q = (int)(i4 % c4);
-    const size_t p = i4 / c4;
-    const int x = (int)(p % wf), y = (int)(p / wf);
-    const int yy = wrap(ty0 + y, Hf), xx = wrap(tx0 + x, Wf);
+    const unsigned q = i4 % (unsigned)c4;
+    const unsigned p = i4 / (unsigned)c4;
+    const int y = (int)(p / (unsigned)wf), x = (int)(p - (unsigned)y * (unsigned)wf);
+    // the offsets are reduced on the host to [0, Hf) x [0, Wf): one conditional subtract wraps
+    int yy = ty0 + y, xx = tx0 + x;
+    yy = yy >= Hf ? yy - Hf : yy, xx = xx >= Wf ? xx - Wf : xx;
     const float4 t =
         *reinterpret_cast<const float4*>(tgt + ((size_t)yy * Wf + xx) * (c4 * 4) + q * 4);
     v.x -= t.x, v.y -= t.y, v.z -= t.z, v.w -= t.w;
