@@ -311,7 +311,7 @@ def run_engine(a):
     tsteps = min(a.steps, 3)
     ms_timing = timed(st.step, tsteps)
     lib.st_timing_enable(0)
-    cats = ['conv_tc', 'conv_simt', 'pool', 'gram', 'style_grad', 'loss', 'image']
+    cats = ['conv_tc', 'conv_edge', 'pool', 'gram', 'style_grad', 'loss', 'image']
     breakdown = {}
     for i, name in enumerate(cats):
         t, w, k = C.c_double(), C.c_double(), C.c_uint64()
@@ -319,7 +319,7 @@ def run_engine(a):
         breakdown[name] = {'ms_per_step': t.value / tsteps, 'work_per_step': w.value / tsteps,
                            'launch_groups_per_step': k.value / tsteps}
     lib.st_timing_reset()
-    dom = 'conv_tc' if breakdown['conv_tc']['ms_per_step'] > 0 else 'conv_simt'
+    dom = 'conv_tc' if breakdown['conv_tc']['ms_per_step'] > 0 else 'conv_edge'
     d = breakdown[dom]
     if d['ms_per_step'] > 0:
         if a.precision == 'bf16':
@@ -328,9 +328,13 @@ def run_engine(a):
         else:
             peak, src = 0.5 * 148 * 128 * 2 * 1.965e-3 * 2, 'nominal fp32 FFMA peak (no tensor cores in fp32 mode)'
         ach = d['work_per_step'] / (d['ms_per_step'] * 1e-3) / 1e12
-        roofline = {'bound': 'tensor', 'kernel': 'conv3x3_tc_kernel' if dom == 'conv_tc' else 'conv3x3_kernel',
+        # dram__bytes_read.sum + dram__bytes_write.sum per launch, averaged over the 24 3x3 conv
+        # launches of one step in the ncu --set full capture summarised in profiles/r01_conv_step_ncu.md
+        traffic = 378.0e6 if (dom == 'conv_tc' and a.size == 2048 and a.tile_size == 512 and world == 1) else None
+        roofline = {'bound': 'tensor', 'kernel': 'conv_tc2_kernel' if dom == 'conv_tc' else 'conv3x3_kernel',
                     'achieved': ach, 'peak': peak, 'unit': 'TFLOP/s', 'frac': ach / peak,
-                    'traffic': None, 'peak_source': src,
+                    'traffic': traffic, 'traffic_source': 'profiles/r01_conv_step_ncu.md (ncu --set full, per launch)',
+                    'peak_source': src,
                     'flops_per_launch': d['work_per_step'] / max(d['launch_groups_per_step'], 1),
                     'avg_launch_ms': d['ms_per_step'] / max(d['launch_groups_per_step'], 1),
                     'share_of_step': d['ms_per_step'] / (ms_timing / tsteps)}

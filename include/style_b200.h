@@ -183,7 +183,7 @@ ST_API int st_axpby(float a, const float* x, float b, float* y, size_t n, st_str
  * Process-wide, not thread-safe: enable it from the thread that drives the context. */
 enum st_timing_category {
   ST_TIME_CONV_TC = 0,      /* tcgen05 implicit-GEMM convolutions, flops */
-  ST_TIME_CONV_SIMT = 1,    /* SIMT convolutions (fp32 mode; 3-channel first/last layer), flops */
+  ST_TIME_CONV_SIMT = 1,    /* first/last 3-channel layer (any kernel) + fp32-mode SIMT convolutions, flops */
   ST_TIME_POOL = 2,         /* pooling fwd/bwd, bytes */
   ST_TIME_GRAM = 3,         /* Gram F^T F, flops */
   ST_TIME_STYLE_GRAD = 4,   /* delta-Gram x F, flops */

@@ -50,7 +50,7 @@ inline int cdiv(long a, long b) { return (int)((a + b - 1) / b); }
 // ALGORITHMIC work of those launches: flops for the tensor categories, bytes for the HBM ones.
 enum TimingCategory {
   kTimeConvTc = 0,     // tcgen05 implicit-GEMM convolutions (flops)
-  kTimeConvSimt = 1,   // SIMT convolutions incl. the 3-channel first/last layer (flops)
+  kTimeConvSimt = 1,   // the 3-channel first/last layer (any kernel) and the fp32 SIMT convolutions (flops)
   kTimePool = 2,       // pooling forward / backward (bytes)
   kTimeGram = 3,       // Gram F^T F (flops)
   kTimeStyleGrad = 4,  // delta-Gram x F (flops)

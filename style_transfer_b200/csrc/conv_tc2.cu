@@ -44,7 +44,8 @@ constexpr int kRowBytes = kBW * 128;      // one tile row of one 64-channel bloc
 constexpr int kThreads2 = 224;
 constexpr uint32_t kSpin = 1u << 24;
 constexpr int kOutStageBytes = 128 * 128; // 128 pixels x 64 channels bf16
-constexpr int kSmemBudget = 227 * 1024 - 1024 /*alignment slack*/ - 512 /*barriers*/;
+constexpr int kTailBytes = 3072;          // barriers (256 B) + tmem slot + bias copy (2 KB)
+constexpr int kSmemBudget = 227 * 1024 - 1024 /*alignment slack*/ - kTailBytes;
 
 enum Epilogue { kEpiFwd = 0, kEpiBwd = 1, kEpiAbs = 2, kEpiPix = 3 };
 
@@ -215,6 +216,7 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
 struct Tc2Args {
   int nb, h, w, cin, cout;         // nb tiles of the batch, each [h][w]
   int w_batched;                   // the B operand has one matrix per batch tile (style GEMM)
+  int resb_bytes;                  // RESB: bytes of the resident weight block (multiple of 1024)
   int tiles_x, tiles_y, tiles_n;   // pair tiles per batch tile: 8 columns x 32 rows x BN channels
   const float* bias;               // kEpiFwd
   const __nv_bfloat16* mask_act;   // kEpiBwd, NHWC [h][w][cout], may be null
@@ -238,7 +240,10 @@ __device__ __forceinline__ TileCoord decode_tile(const Tc2Args& a, int tile, int
   return t;
 }
 
-template <int BN, int TAPS>
+// RESB: the whole weight matrix of this CTA (its BN/2 rows x all K) stays resident in shared
+// memory for the life of the kernel -- for the small layers (conv1_2, conv2_1, the 3-channel
+// backward) where one TMA round trip per tap costs more than the MMAs of that tap.
+template <int BN, int TAPS, bool RESB = false>
 struct Cfg2 {
   static constexpr int kHaloRows = TAPS == 9 ? kBH + 2 : kBH;
   static constexpr int kVariants = TAPS == 9 ? 3 : 1;
@@ -248,26 +253,29 @@ struct Cfg2 {
   static constexpr int kSA = TAPS == 9 ? 2 : 4;
   static constexpr int kOutBytes = 2 * kOutStageBytes;
   static constexpr int kSBRaw = (kSmemBudget - kSA * kABytes - kOutBytes) / kBBytes;
-  static constexpr int kSB = kSBRaw > 8 ? 8 : kSBRaw;
+  static constexpr int kSB = RESB ? 1 : (kSBRaw > 8 ? 8 : kSBRaw);
+  static constexpr int kResMax = kSmemBudget - kSA * kABytes - kOutBytes;   // bytes for resident B
   static constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;    // double-buffered accumulator
-  static constexpr int kSmemBytes = kSA * kABytes + kSB * kBBytes + kOutBytes + 1024 + 512;
+  static constexpr int kFixedBytes = kSA * kABytes + kOutBytes + 1024 + kTailBytes;
+  static constexpr int kSmemBytes = kFixedBytes + kSB * kBBytes;           // staged-B variant
   static constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) |
                                      ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
-  static_assert(kSB >= 3, "not enough shared memory for the weight pipeline");
+  static_assert(RESB || kSB >= 3, "not enough shared memory for the weight pipeline");
 };
 
-template <int BN, int TAPS, int EPI>
+template <int BN, int TAPS, int EPI, bool RESB>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1)
 conv_tc2_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CUtensorMap map_w,
                 const __grid_constant__ CUtensorMap map_out, const Tc2Args a) {
-  using Cfg = Cfg2<BN, TAPS>;
+  using Cfg = Cfg2<BN, TAPS, RESB>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~(uintptr_t)1023);
   uint8_t* a_base = smem;
-  uint8_t* b_base = a_base + Cfg::kSA * Cfg::kABytes;
-  uint8_t* out_base = b_base + Cfg::kSB * Cfg::kBBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(out_base + Cfg::kOutBytes);
+  uint8_t* out_base = a_base + Cfg::kSA * Cfg::kABytes;
+  uint8_t* b_base = out_base + Cfg::kOutBytes;
+  const int b_bytes = RESB ? a.resb_bytes : Cfg::kSB * Cfg::kBBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(b_base + b_bytes);
   uint64_t* a_full = bars;
   uint64_t* a_empty = a_full + Cfg::kSA;
   uint64_t* b_full = a_empty + Cfg::kSA;
@@ -275,6 +283,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constan
   uint64_t* t_full = b_empty + Cfg::kSB;
   uint64_t* t_empty = t_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
+  float* bias_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 512);   // [cout] <= 512
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_rank();
@@ -291,6 +300,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constan
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc_pair(tmem_slot, Cfg::kTmemCols);
+  if constexpr (EPI == kEpiFwd) {
+    for (int i = threadIdx.x; i < a.cout; i += kThreads2) bias_s[i] = a.bias[i];
+  }
   tc_fence_before();
   cluster_sync();
   tc_fence_after();
@@ -323,23 +335,36 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constan
     }
   } else if (warp == 6) {
     // ===================================== B producer ============================================
-    int stage = 0;
-    uint32_t phase = 0;
-    for (int tile = pair; tile < num_tiles; tile += num_pairs) {
-      const TileCoord t = decode_tile(a, tile, (int)rank);
-      const int n0 = t.n_tile * BN + (int)rank * (BN / 2);
-      const int wb = a.w_batched ? t.b : 0;
-      for (int cb = 0; cb < kb_per_tap; ++cb) {
-        for (int tap = 0; tap < TAPS; ++tap) {
-          mbar_wait(&b_empty[stage], phase ^ 1);
-          const uint32_t bar = map_to_cta(smem_u32(&b_full[stage]), 0);
-          if (elect_one()) {
-            if (leader) mbar_expect_tx(&b_full[stage], 2 * Cfg::kBBytes);
-            tma_load_3d_pair(&map_w, bar, b_base + stage * Cfg::kBBytes, tap * a.cin + cb * 64, n0,
-                             wb);
+    if constexpr (RESB) {
+      // one shot: every (channel block, tap) slab of this CTA's weight rows, one barrier
+      const uint32_t bar = map_to_cta(smem_u32(&b_full[0]), 0);
+      if (elect_one()) {
+        if (leader) mbar_expect_tx(&b_full[0], 2 * a.resb_bytes);
+        for (int cb = 0; cb < kb_per_tap; ++cb)
+          for (int tap = 0; tap < TAPS; ++tap)
+            tma_load_3d_pair(&map_w, bar, b_base + (cb * TAPS + tap) * Cfg::kBBytes,
+                             tap * a.cin + cb * 64, (int)rank * (BN / 2), 0);
+      }
+      __syncwarp();
+    } else {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        const TileCoord t = decode_tile(a, tile, (int)rank);
+        const int n0 = t.n_tile * BN + (int)rank * (BN / 2);
+        const int wb = a.w_batched ? t.b : 0;
+        for (int cb = 0; cb < kb_per_tap; ++cb) {
+          for (int tap = 0; tap < TAPS; ++tap) {
+            mbar_wait(&b_empty[stage], phase ^ 1);
+            const uint32_t bar = map_to_cta(smem_u32(&b_full[stage]), 0);
+            if (elect_one()) {
+              if (leader) mbar_expect_tx(&b_full[stage], 2 * Cfg::kBBytes);
+              tma_load_3d_pair(&map_w, bar, b_base + stage * Cfg::kBBytes, tap * a.cin + cb * 64,
+                               n0, wb);
+            }
+            __syncwarp();
+            if (++stage == Cfg::kSB) stage = 0, phase ^= 1;
           }
-          __syncwarp();
-          if (++stage == Cfg::kSB) stage = 0, phase ^= 1;
         }
       }
     }
@@ -348,6 +373,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constan
     if (leader) {
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0, it = 0;
+      if constexpr (RESB) mbar_wait(&b_full[0], 0);      // the resident weights have landed
       for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
         const uint32_t buf = it & 1, use = it >> 1;
         mbar_wait(&t_empty[buf], (use & 1) ^ 1);
@@ -358,18 +384,19 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constan
           const uint32_t a_addr = smem_u32(a_base + sa * Cfg::kABytes);
 #pragma unroll 1
           for (int tap = 0; tap < TAPS; ++tap) {
-            mbar_wait(&b_full[sb], pb);
+            if constexpr (!RESB) mbar_wait(&b_full[sb], pb);
             tc_fence_after();
             uint32_t a_tap = a_addr;
             if constexpr (TAPS == 9) a_tap += (tap % 3) * Cfg::kAVarBytes + (tap / 3) * kRowBytes;
             const uint64_t da = make_smem_desc(a_tap);
-            const uint64_t db = make_smem_desc(smem_u32(b_base + sb * Cfg::kBBytes));
+            const uint64_t db = make_smem_desc(
+                smem_u32(b_base + (RESB ? (cb * TAPS + tap) : sb) * Cfg::kBBytes));
             if (elect_one()) {
 #pragma unroll
               for (int k = 0; k < 4; ++k)
                 tc_mma_pair(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), Cfg::kIdesc,
                             (cb | tap | k) != 0);
-              tc_commit_pair(&b_empty[sb]);
+              if constexpr (!RESB) tc_commit_pair(&b_empty[sb]);
               if (tap == TAPS - 1) {
                 tc_commit_pair(&a_empty[sa]);
                 if (cb == kb_per_tap - 1) tc_commit_pair(&t_full[buf]);
@@ -397,6 +424,23 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constan
       const size_t gofs =
           (((size_t)t.b * a.h + py) * a.w + px) * a.cout + (size_t)n_tile * BN;
       float abs_tile = 0.f;
+      // backward epilogue operands of the first 32-channel chunk: requested before the wait on the
+      // accumulator, the following chunks one chunk ahead (their latency hides behind the MMAs)
+      uint4 pm[4], pe[4];
+      auto prefetch = [&](int cc) {
+        if constexpr (EPI == kEpiBwd) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            pm[i] = make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u);   // "positive"
+            pe[i] = make_uint4(0u, 0u, 0u, 0u);
+            if (valid && a.mask_act != nullptr)
+              pm[i] = *reinterpret_cast<const uint4*>(a.mask_act + gofs + cc * 32 + i * 8);
+            if (valid && a.inj != nullptr)
+              pe[i] = *reinterpret_cast<const uint4*>(a.inj + gofs + cc * 32 + i * 8);
+          }
+        }
+      };
+      prefetch(0);
 
       mbar_wait(&t_full[buf], use & 1);
       tc_fence_after();
@@ -430,36 +474,27 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constan
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
           if constexpr (EPI == kEpiFwd) {
+            const float* bs = bias_s + n_tile * BN + cc * 32;
 #pragma unroll
-            for (int i = 0; i < 32; ++i)
-              v[i] = fmaxf(v[i] + __ldg(a.bias + n_tile * BN + cc * 32 + i), 0.f);
+            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i] + bs[i], 0.f);
           } else if constexpr (EPI == kEpiBwd) {
-            if (a.mask_act != nullptr) {
+            uint4 cm[4], ce[4];
 #pragma unroll
-              for (int i = 0; i < 32; i += 8) {
-                uint4 raw = make_uint4(0u, 0u, 0u, 0u);
-                if (valid) raw = *reinterpret_cast<const uint4*>(a.mask_act + gofs + cc * 32 + i);
-                const uint32_t w4[4] = {raw.x, raw.y, raw.z, raw.w};
+            for (int i = 0; i < 4; ++i) cm[i] = pm[i], ce[i] = pe[i];
+            if (cc + 1 < BN / 32) prefetch(cc + 1);
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  // bf16 > 0  <=>  sign clear and magnitude non-zero
-                  const uint32_t lo = w4[j] & 0xFFFFu, hi = w4[j] >> 16;
-                  if (!(lo != 0u && lo < 0x8000u)) v[i + 2 * j] = 0.f;
-                  if (!(hi != 0u && hi < 0x8000u)) v[i + 2 * j + 1] = 0.f;
-                }
-              }
-            }
-            if (a.inj != nullptr) {
+            for (int i = 0; i < 4; ++i) {
+              const uint32_t m4[4] = {cm[i].x, cm[i].y, cm[i].z, cm[i].w};
+              const uint32_t e4[4] = {ce[i].x, ce[i].y, ce[i].z, ce[i].w};
 #pragma unroll
-              for (int i = 0; i < 32; i += 8) {
-                uint4 raw = make_uint4(0u, 0u, 0u, 0u);
-                if (valid) raw = *reinterpret_cast<const uint4*>(a.inj + gofs + cc * 32 + i);
-                const uint32_t w4[4] = {raw.x, raw.y, raw.z, raw.w};
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  v[i + 2 * j] += __uint_as_float(w4[j] << 16);
-                  v[i + 2 * j + 1] += __uint_as_float(w4[j] & 0xFFFF0000u);
-                }
+              for (int j = 0; j < 4; ++j) {
+                // bf16 > 0  <=>  sign clear and magnitude non-zero
+                const uint32_t lo = m4[j] & 0xFFFFu, hi = m4[j] >> 16;
+                float x0 = v[8 * i + 2 * j], x1 = v[8 * i + 2 * j + 1];
+                if (!(lo != 0u && lo < 0x8000u)) x0 = 0.f;
+                if (!(hi != 0u && hi < 0x8000u)) x1 = 0.f;
+                v[8 * i + 2 * j] = x0 + __uint_as_float(e4[j] << 16);
+                v[8 * i + 2 * j + 1] = x1 + __uint_as_float(e4[j] & 0xFFFF0000u);
               }
             }
           } else {
@@ -539,10 +574,10 @@ int encode_bf16_map(const TcContext& tc, CUtensorMap* map, int rank, const void*
   return ST_OK;
 }
 
-template <int BN, int TAPS, int EPI>
-int launch2(TcContext& tc, const __nv_bfloat16* in, const __nv_bfloat16* wk, int wk_rows,
-            __nv_bfloat16* out, Tc2Args a, cudaStream_t s) {
-  using Cfg = Cfg2<BN, TAPS>;
+template <int BN, int TAPS, int EPI, bool RESB>
+int launch2r(TcContext& tc, const __nv_bfloat16* in, const __nv_bfloat16* wk, int wk_rows,
+             __nv_bfloat16* out, Tc2Args a, cudaStream_t s) {
+  using Cfg = Cfg2<BN, TAPS, RESB>;
   a.tiles_x = cdiv(a.w, kBW), a.tiles_y = cdiv(a.h, 2 * kBH), a.tiles_n = a.cout / BN;
   CUtensorMap map_in, map_out, map_w;
   {
@@ -571,21 +606,36 @@ int launch2(TcContext& tc, const __nv_bfloat16* in, const __nv_bfloat16* wk, int
     int rc = encode_bf16_map(tc, &map_w, 3, wk, dims, strides, box);
     if (rc != ST_OK) return rc;
   }
-  auto kern = conv_tc2_kernel<BN, TAPS, EPI>;
+  auto kern = conv_tc2_kernel<BN, TAPS, EPI, RESB>;
   static bool attr_set = false;
   if (!attr_set) {
-    ST_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 Cfg::kSmemBytes));
+    ST_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
+  a.resb_bytes = RESB ? TAPS * (a.cin / 64) * Cfg::kBBytes : 0;
+  const int smem_bytes = RESB ? Cfg::kFixedBytes + a.resb_bytes : Cfg::kSmemBytes;
   const int tiles = a.tiles_x * a.tiles_y * a.tiles_n * a.nb;
   const int max_pairs = tc.sm_count / 2;
   const int pairs = tiles < max_pairs ? tiles : max_pairs;
   // algorithmic flops: the pixel epilogue computes 3 of its 16 accumulator columns for real
-  TimerScope ts(s, EPI == kEpiAbs ? kTimeStyleGrad : kTimeConvTc,
+  TimerScope ts(s, EPI == kEpiAbs ? kTimeStyleGrad : (EPI == kEpiPix ? kTimeConvSimt : kTimeConvTc),
                 2.0 * TAPS * a.cin * (EPI == kEpiPix ? 3 : a.cout) * a.h * a.w * a.nb);
-  ST_LAUNCH(kern, 2 * pairs, kThreads2, Cfg::kSmemBytes, s, map_in, map_w, map_out, a);
+  ST_LAUNCH(kern, 2 * pairs, kThreads2, smem_bytes, s, map_in, map_w, map_out, a);
   return ST_OK;
+}
+
+// Resident weights when one output-channel tile covers the layer, the weights are shared by the
+// batch and this CTA's share of them fits beside the A stages.
+template <int BN, int TAPS, int EPI>
+int launch2(TcContext& tc, const __nv_bfloat16* in, const __nv_bfloat16* wk, int wk_rows,
+            __nv_bfloat16* out, const Tc2Args& a, cudaStream_t s) {
+  if constexpr (BN <= 128) {
+    const long res = (long)TAPS * (a.cin / 64) * Cfg2<BN, TAPS, true>::kBBytes;
+    if (a.cout == BN && !a.w_batched && res <= Cfg2<BN, TAPS, true>::kResMax &&
+        getenv("ST_TC_NO_RESB") == nullptr)
+      return launch2r<BN, TAPS, EPI, true>(tc, in, wk, wk_rows, out, a, s);
+  }
+  return launch2r<BN, TAPS, EPI, false>(tc, in, wk, wk_rows, out, a, s);
 }
 
 // Output-channel tile: the widest BN that still gives every CTA pair work; wide tiles halve the
