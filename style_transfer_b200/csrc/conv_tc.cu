@@ -530,10 +530,13 @@ bool tc_shape_ok(const TcContext& tc, const TcWeights& w, int cin, int cout) {
 
 int conv3x3_tc(TcContext& tc, const TcWeights& w, const __nv_bfloat16* in, __nv_bfloat16* out,
                int nb, int h, int wd, int cin, int cout, bool forward, const float* bias,
-               const __nv_bfloat16* mask_act, const __nv_bfloat16* inj, cudaStream_t s) {
+               const __nv_bfloat16* mask_act, const __nv_bfloat16* inj, const float* inj_scale,
+               cudaStream_t s) {
   if (tc.pair_kernel)
-    return conv3x3_tc_pair(tc, w, in, out, nb, h, wd, cin, cout, forward, bias, mask_act, inj, s);
-  ST_REQUIRE(nb == 1, "the single-CTA convolution kernel (ST_CONV_V1) takes one tile at a time");
+    return conv3x3_tc_pair(tc, w, in, out, nb, h, wd, cin, cout, forward, bias, mask_act, inj,
+                           inj_scale, s);
+  ST_REQUIRE(nb == 1 && inj_scale == nullptr,
+             "the single-CTA convolution kernel (ST_CONV_V1) takes one tile and a pre-scaled injection");
   TcArgs a{};
   a.h = h, a.w = wd, a.cin = cin, a.cout = cout, a.forward = forward ? 1 : 0;
   a.bias = bias, a.mask_act = mask_act, a.inj = inj;

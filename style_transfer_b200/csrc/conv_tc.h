@@ -43,14 +43,16 @@ inline bool tc_usable(const TcContext& tc, const TcWeights& w, int cin, int cout
 
 // out = epilogue(conv3x3(in)) with in [nb][h][w][cin], out [nb][h][w][cout] (bf16 NHWC).
 //   forward : out = max(acc + bias, 0)
-//   backward: out = (mask_act > 0 ? acc : 0) + inj   (either may be null)
+//   backward: out = (mask_act > 0 ? acc : 0) + inj_scale[tile] * inj   (each may be null)
 int conv3x3_tc(TcContext& tc, const TcWeights& w, const __nv_bfloat16* in, __nv_bfloat16* out,
                int nb, int h, int wd, int cin, int cout, bool forward, const float* bias,
-               const __nv_bfloat16* mask_act, const __nv_bfloat16* inj, cudaStream_t s);
+               const __nv_bfloat16* mask_act, const __nv_bfloat16* inj, const float* inj_scale,
+               cudaStream_t s);
 // CTA-pair (cta_group::2) kernel of conv_tc2.cu; activations are [nb][h][w][c] (a batch of tiles).
 int conv3x3_tc_pair(TcContext& tc, const TcWeights& w, const __nv_bfloat16* in, __nv_bfloat16* out,
                     int nb, int h, int wd, int cin, int cout, bool forward, const float* bias,
-                    const __nv_bfloat16* mask_act, const __nv_bfloat16* inj, cudaStream_t s);
+                    const __nv_bfloat16* mask_act, const __nv_bfloat16* inj, const float* inj_scale,
+                    cudaStream_t s);
 // Backward of the first (3-channel) convolution on tensor cores: dz [nb][h][w][cz] bf16 -> planar f32
 // gradient; tile b goes to grad + b * batch_stride.  Needs weights packed by tc_pack_first.
 int conv_last_bwd_tc_pair(TcContext& tc, const TcWeights& w, const __nv_bfloat16* dz, int nb, int h,
@@ -77,7 +79,7 @@ int gram_tc(TcContext& tc, const __nv_bfloat16* f, int nb, int hw, int c, float*
             cudaStream_t s);
 
 inline int conv3x3_tc(TcContext&, const TcWeights&, const float*, float*, int, int, int, int, int,
-                      bool, const float*, const float*, const float*, cudaStream_t) {
+                      bool, const float*, const float*, const float*, const float*, cudaStream_t) {
   return -1;   // never reached: tc_usable<float> is false
 }
 

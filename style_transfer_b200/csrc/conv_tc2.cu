@@ -221,6 +221,7 @@ struct Tc2Args {
   const float* bias;               // kEpiFwd
   const __nv_bfloat16* mask_act;   // kEpiBwd, NHWC [h][w][cout], may be null
   const __nv_bfloat16* inj;        // kEpiBwd, may be null
+  const float* inj_scale;          // kEpiBwd: per batch tile factor applied to inj, may be null
   double* abs_partials;            // kEpiAbs: [pair tile][cta rank][epilogue warp]
   float* pix;                      // kEpiPix: planar f32 output, channels 0..2 of the accumulator
   long pix_batch, pix_plane, pix_row;   // strides (floats) between batch tiles / planes / rows
@@ -441,6 +442,10 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constan
         }
       };
       prefetch(0);
+      float inj_sc = 1.f;
+      if constexpr (EPI == kEpiBwd) {
+        if (a.inj_scale != nullptr) inj_sc = __ldg(a.inj_scale + t.b);
+      }
 
       mbar_wait(&t_full[buf], use & 1);
       tc_fence_after();
@@ -493,8 +498,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constan
                 float x0 = v[8 * i + 2 * j], x1 = v[8 * i + 2 * j + 1];
                 if (!(lo != 0u && lo < 0x8000u)) x0 = 0.f;
                 if (!(hi != 0u && hi < 0x8000u)) x1 = 0.f;
-                v[8 * i + 2 * j] = x0 + __uint_as_float(e4[j] << 16);
-                v[8 * i + 2 * j + 1] = x1 + __uint_as_float(e4[j] & 0xFFFF0000u);
+                v[8 * i + 2 * j] = fmaf(inj_sc, __uint_as_float(e4[j] << 16), x0);
+                v[8 * i + 2 * j + 1] = fmaf(inj_sc, __uint_as_float(e4[j] & 0xFFFF0000u), x1);
               }
             }
           } else {
@@ -668,10 +673,11 @@ int dispatch_bn(TcContext& tc, int bn, const __nv_bfloat16* in, const __nv_bfloa
 
 int conv3x3_tc_pair(TcContext& tc, const TcWeights& w, const __nv_bfloat16* in, __nv_bfloat16* out,
                     int nb, int h, int wd, int cin, int cout, bool forward, const float* bias,
-                    const __nv_bfloat16* mask_act, const __nv_bfloat16* inj, cudaStream_t s) {
+                    const __nv_bfloat16* mask_act, const __nv_bfloat16* inj, const float* inj_scale,
+                    cudaStream_t s) {
   Tc2Args a{};
   a.nb = nb, a.h = h, a.w = wd, a.cin = cin, a.cout = cout;
-  a.bias = bias, a.mask_act = mask_act, a.inj = inj;
+  a.bias = bias, a.mask_act = mask_act, a.inj = inj, a.inj_scale = inj_scale;
   const int bn = choose_bn(tc, nb, h, wd, cout);
   if (forward) return dispatch_bn<9, kEpiFwd>(tc, bn, in, w.fwd, cout, out, a, s);
   return dispatch_bn<9, kEpiBwd>(tc, bn, in, w.bwd, cout, out, a, s);

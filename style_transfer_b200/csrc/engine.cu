@@ -70,6 +70,11 @@ struct BlobRt {
   size_t act_cap = 0;        // elements
   void* inj = nullptr;
   size_t inj_cap = 0;
+  // When the only loss term of a blob is one style term, the style GEMM writes its raw output S
+  // into `inj` and the per-tile factor w / (mean|S| + EPS) is applied by the consumer's epilogue
+  // (`inj_scale`, kMaxBatch floats) instead of a separate scale-and-copy pass over S.
+  float* inj_scale = nullptr;
+  bool inj_deferred = false;
 };
 
 struct ContentTarget {
@@ -219,7 +224,7 @@ int forward(st_ctx* ctx, const ImageBatch& view, const Dims& d, int last_layer, 
         const T* in = static_cast<const T*>(ctx->blobs[l.bottom].act);
         if (tc_usable<T>(ctx->tc, l.tc, l.cin, l.cout))
           rc = conv3x3_tc(ctx->tc, l.tc, in, out, nb, hb, wb, l.cin, l.cout, true, l.bias, nullptr,
-                          nullptr, s);
+                          nullptr, nullptr, s);
         else
           rc = conv3x3_simt<T>(in, l.w_fwd, l.bias, out, nb, hb, wb, l.cin, l.cout, true, nullptr,
                                nullptr, s);
@@ -242,8 +247,9 @@ struct BatchGeom {
 
 template <typename T>
 int build_injection(st_ctx* ctx, const st_loss_spec& sp, const Dims& d, const BatchGeom& g,
-                    int froll_y, int froll_x, cudaStream_t s) {
+                    int froll_y, int froll_x, bool is_deepest, cudaStream_t s) {
   BlobRt& b = ctx->blobs[sp.blob];
+  b.inj_deferred = false;
   const int nb = g.nb, hf = d.h[sp.blob], wf = d.w[sp.blob], c = b.c;
   const size_t n = (size_t)hf * wf * c;            // elements per tile
   int rc = ensure(ctx, &b.inj, &b.inj_cap, n * nb, ctx->esize);
@@ -304,16 +310,28 @@ int build_injection(st_ctx* ctx, const st_loss_spec& sp, const Dims& d, const Ba
         rc = gram_delta(ctx->gram, it->second, ctx->delta, ctx->delta_bf16, c, nb, w, tile_loss,
                         kStatStride, ctx->rs, s);
       if (rc != ST_OK) return rc;
+      // the scale-and-copy pass over S can be skipped when S is this blob's whole injection and a
+      // kernel epilogue (not a TMA operand load) consumes it
+      const bool defer = on_tc && !sp.use_content && !sp.use_dd && ctx->n_styles == 1 && !is_deepest &&
+                         getenv("ST_NO_DEFER") == nullptr;
       if (on_tc) {
         if constexpr (std::is_same<T, __nv_bfloat16>::value) {
           int per_tile = 0;
           rc = ensure(ctx, (void**)&ctx->abs_partials, &ctx->abs_cap,
                       gemm_abs_partials_needed(nb, hf, wf, c), sizeof(double));
+          if (rc == ST_OK && defer && b.inj_scale == nullptr)
+            rc = dev_alloc(ctx, (void**)&b.inj_scale, kMaxBatch * sizeof(float));
           if (rc == ST_OK)
-            rc = gemm_abs_tc_pair(ctx->tc, f, ctx->delta_bf16, static_cast<T*>(ctx->sbuf), nb, hf, wf,
-                                  c, ctx->abs_partials, &per_tile, s);
+            rc = gemm_abs_tc_pair(ctx->tc, f, ctx->delta_bf16, defer ? inj : static_cast<T*>(ctx->sbuf),
+                                  nb, hf, wf, c, ctx->abs_partials, &per_tile, s);
           if (rc == ST_OK)
-            rc = sum_partials(ctx->abs_partials, per_tile, nb, stats + 2, kStatStride, s);
+            rc = sum_partials(ctx->abs_partials, per_tile, nb, stats + 2, kStatStride,
+                              defer ? b.inj_scale : nullptr, (float)w, (double)n, s);
+          if (rc == ST_OK && defer) {
+            b.inj_deferred = true;
+            accumulate = true;
+            continue;
+          }
         }
       } else {
         rc = style_grad<T>(f, ctx->delta, static_cast<T*>(ctx->sbuf), hf * wf, c, stats + 2,
@@ -361,18 +379,21 @@ int backward(st_ctx* ctx, const Dims& d, int nb, int deepest_blob, const std::ve
     const BlobRt& bb = ctx->blobs[b];
     const T* mask = bb.relu ? static_cast<const T*>(bb.act) : nullptr;
     const T* inj = has_inj[b] ? static_cast<const T*>(bb.inj) : nullptr;
+    const float* inj_scale = (has_inj[b] && bb.inj_deferred) ? bb.inj_scale : nullptr;
     T* out = static_cast<T*>(ctx->gbuf[pp]);
     int rc;
     if (l.kind == ST_CONV3X3) {
       if (tc_usable<T>(ctx->tc, l.tc, l.cout, l.cin))
         rc = conv3x3_tc(ctx->tc, l.tc, g, out, nb, hb, wb, l.cout, l.cin, false, nullptr, mask, inj,
-                        s);
-      else
+                        inj_scale, s);
+      else {
+        ST_REQUIRE(inj_scale == nullptr, "deferred injection scale needs the tensor-core convolution");
         rc = conv3x3_simt<T>(g, l.w_bwd, nullptr, out, nb, hb, wb, l.cout, l.cin, false, mask, inj,
                              s);
+      }
     } else {
       rc = pool_bwd<T>(g, static_cast<const T*>(bb.act), out, nb, hb, wb, l.cin,
-                       l.kind == ST_POOL_MAX, bb.relu, inj, s);
+                       l.kind == ST_POOL_MAX, bb.relu, inj, inj_scale, s);
     }
     if (rc != ST_OK) return rc;
     g = out, pp ^= 1, cur = b;
@@ -410,7 +431,7 @@ int eval_batch(st_ctx* ctx, const ImageBatch& view, int h, int w, const BatchGeo
   int rc = reserve_for(ctx, d, last_layer, g.nb);
   if (rc == ST_OK) rc = forward<T>(ctx, view, d, last_layer, s);
   for (int i = 0; i < n_specs && rc == ST_OK; ++i)
-    rc = build_injection<T>(ctx, specs[i], d, g, froll_y, froll_x, s);
+    rc = build_injection<T>(ctx, specs[i], d, g, froll_y, froll_x, specs[i].blob == deepest, s);
   if (rc == ST_OK) rc = loss_finalize(ctx->scalars + 3, kStatStride, g.nb, loss_accum, s);
   if (rc == ST_OK)
     rc = backward<T>(ctx, d, g.nb, deepest, has_inj, grad, batch_stride, plane, rstride, s);
@@ -555,7 +576,7 @@ int st_destroy(st_ctx* ctx) {
     cudaFree(l.w_fwd), cudaFree(l.w_bwd), cudaFree(l.bias);
     tc_free_weights(l.tc);
   }
-  for (BlobRt& b : ctx->blobs) cudaFree(b.act), cudaFree(b.inj);
+  for (BlobRt& b : ctx->blobs) cudaFree(b.act), cudaFree(b.inj), cudaFree(b.inj_scale);
   cudaFree(ctx->gbuf[0]), cudaFree(ctx->gbuf[1]), cudaFree(ctx->sbuf);
   cudaFree(ctx->gram), cudaFree(ctx->delta), cudaFree(ctx->part), cudaFree(ctx->scalars);
   cudaFree(ctx->delta_bf16), cudaFree(ctx->abs_partials);

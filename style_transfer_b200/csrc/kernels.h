@@ -50,10 +50,10 @@ int conv3x3_simt(const T* in, const float* wpack, const float* bias, T* out, int
 // ---- pooling -----------------------------------------------------------------------------------
 template <typename T>
 int pool_fwd(const T* in, T* out, int nb, int h, int w, int c, bool is_max, cudaStream_t s);
-// d_in = [mask](in>0) * pool_bwd(d_out) + [inj]
+// d_in = [mask](in>0) * pool_bwd(d_out) + [inj_scale[tile]] * [inj]
 template <typename T>
 int pool_bwd(const T* d_out, const T* in, T* d_in, int nb, int h, int w, int c, bool is_max,
-             bool apply_mask, const T* inj, cudaStream_t s);
+             bool apply_mask, const T* inj, const float* inj_scale, cudaStream_t s);
 
 // ---- Gram / style ------------------------------------------------------------------------------
 // gram_full[C][C] (symmetric, float) = F^T F / (C*HW).  F is NHWC [hw][c] (channel_major=false) or
@@ -66,9 +66,10 @@ int gram_full(const T* f, int hw, int c, bool channel_major, float* gram, float*
 int gram_delta(const float* gram, const float* target, float* delta, __nv_bfloat16* delta_bf16,
                int c, int nb, double w, double* tile_loss, int loss_stride, ReduceScratch rs,
                cudaStream_t s);
-// out[b * out_stride] = sum(partials[b*n .. b*n+n)) in index order
-int sum_partials(const double* partials, int n, int nb, double* out, int out_stride,
-                 cudaStream_t s);
+// out[b * out_stride] = sum(partials[b*n .. b*n+n)) in a launch-independent order; if scale is not
+// null also scale[b] = w / (sum / count + EPS)
+int sum_partials(const double* partials, int n, int nb, double* out, int out_stride, float* scale,
+                 float w, double count, cudaStream_t s);
 // *loss_accum += sum_b tile_loss[b * stride] (tile order); clears the slots
 int loss_finalize(double* tile_loss, int stride, int nb, double* loss_accum, cudaStream_t s);
 // S[p][co] = sum_ci F[p][ci] * delta[ci][co]; *sum_abs = sum |S|

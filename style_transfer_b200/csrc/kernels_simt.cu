@@ -316,7 +316,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 pool_bwd_kernel(const T* __restrict__ d_out, const T* __restrict__ in_all, T* __restrict__ d_in_all,
                 int nb, int h, int w, int c, int ho, int wo, int is_max, int apply_mask,
-                const T* __restrict__ inj_all) {
+                const T* __restrict__ inj_all, const float* __restrict__ inj_scale) {
   const unsigned c4 = c >> 2, uwo = wo, uho = ho;
   const unsigned total = (unsigned)nb * ho * wo * c4;
   for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
@@ -324,10 +324,12 @@ pool_bwd_kernel(const T* __restrict__ d_out, const T* __restrict__ in_all, T* __
     const unsigned p = i / c4;
     const unsigned row = p / uwo;
     const int x = (int)(p - row * uwo), y = (int)(row % uho);
-    const size_t boff = (size_t)(row / uho) * ((size_t)h * w * c) + q * 4;
+    const unsigned bt = row / uho;                            // tile of the batch
+    const size_t boff = (size_t)bt * ((size_t)h * w * c) + q * 4;
     const T* in = in_all + boff;
     T* d_in = d_in_all + boff;
     const T* inj = inj_all ? inj_all + boff : nullptr;
+    const float isc = inj_scale ? inj_scale[bt] : 1.f;
     const float4 g = Store<T>::ld4(d_out + (size_t)p * c + q * 4);
     float4 v[4], e[4];
     bool ok[4];
@@ -369,7 +371,7 @@ pool_bwd_kernel(const T* __restrict__ d_out, const T* __restrict__ in_all, T* __
         r.x = v[d].x > 0.f ? r.x : 0.f, r.y = v[d].y > 0.f ? r.y : 0.f;
         r.z = v[d].z > 0.f ? r.z : 0.f, r.w = v[d].w > 0.f ? r.w : 0.f;
       }
-      r.x += e[d].x, r.y += e[d].y, r.z += e[d].z, r.w += e[d].w;
+      r.x += isc * e[d].x, r.y += isc * e[d].y, r.z += isc * e[d].z, r.w += isc * e[d].w;
       Store<T>::st4(d_in + ((size_t)yy * w + xx) * c, r);
     }
   }
@@ -395,7 +397,7 @@ int pool_fwd(const T* in, T* out, int nb, int h, int w, int c, bool is_max, cuda
 
 template <typename T>
 int pool_bwd(const T* d_out, const T* in, T* d_in, int nb, int h, int w, int c, bool is_max,
-             bool apply_mask, const T* inj, cudaStream_t s) {
+             bool apply_mask, const T* inj, const float* inj_scale, cudaStream_t s) {
   ST_REQUIRE(c % 8 == 0, "pool: channels must be a multiple of 8");
   const int ho = (h + 1) / 2, wo = (w + 1) / 2;
   ST_REQUIRE((size_t)nb * ho * wo * c < ((size_t)1 << 31), "pool: batch too large for 32-bit indexing");
@@ -403,7 +405,7 @@ int pool_bwd(const T* d_out, const T* in, T* d_in, int nb, int h, int w, int c, 
   TimerScope ts(s, kTimePool, (double)sizeof(T) * c * nb *
                                   ((double)h * w * (2 + (inj ? 1 : 0)) + (double)ho * wo));
   ST_LAUNCH(k, ew_grid((size_t)nb * ho * wo * (c / 4), 256), 256, 0, s, d_out, in, d_in, nb, h, w,
-            c, ho, wo, is_max ? 1 : 0, apply_mask ? 1 : 0, inj);
+            c, ho, wo, is_max ? 1 : 0, apply_mask ? 1 : 0, inj, inj_scale);
   return ST_OK;
 }
 
@@ -534,20 +536,31 @@ int gram_delta(const float* gram, const float* target, float* delta, __nv_bfloat
   return ST_OK;
 }
 
-// out[b * out_stride] = sum of partials[b * n .. b * n + n), summed in index order by one warp
-// (deterministic).  blockIdx.x = tile of the batch.
-__global__ void sum_partials_kernel(const double* __restrict__ partials, int n, double* out,
-                                    int out_stride) {
+// out[b * out_stride] = sum of partials[b * n .. b * n + n).  One block per tile: thread t adds the
+// strided subsequence t, t+256, ... and the 256 sums are combined by a fixed tree, so the result does
+// not depend on the launch.  Optionally also scale[b] = w / (sum / count + EPS): the factor
+// normalize() + the layer weight apply to the style gradient (num_utils.py:85-87, :591-593).
+__global__ void __launch_bounds__(256)
+sum_partials_kernel(const double* __restrict__ partials, int n, double* out, int out_stride,
+                    float* scale, float w, double count) {
+  __shared__ double sh[256];
   const double* p = partials + (size_t)blockIdx.x * n;
   double x = 0.0;
-  for (int i = threadIdx.x; i < n; i += 32) x += p[i];
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-  if (threadIdx.x == 0) out[(size_t)blockIdx.x * out_stride] = x;
+  for (int i = threadIdx.x; i < n; i += 256) x += p[i];
+  sh[threadIdx.x] = x;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    out[(size_t)blockIdx.x * out_stride] = sh[0];
+    if (scale != nullptr) scale[blockIdx.x] = w * (1.f / ((float)(sh[0] / count) + kEps));
+  }
 }
-int sum_partials(const double* partials, int n, int nb, double* out, int out_stride,
-                 cudaStream_t s) {
-  ST_LAUNCH(sum_partials_kernel, nb, 32, 0, s, partials, n, out, out_stride);
+int sum_partials(const double* partials, int n, int nb, double* out, int out_stride, float* scale,
+                 float w, double count, cudaStream_t s) {
+  ST_LAUNCH(sum_partials_kernel, nb, 256, 0, s, partials, n, out, out_stride, scale, w, count);
   return ST_OK;
 }
 
@@ -824,7 +837,7 @@ int nchw_to_nhwc_f32(const float* in, float* out, int hw, int c, cudaStream_t s)
                                 long, cudaStream_t);                                              \
   template int pool_fwd<T>(const T*, T*, int, int, int, int, bool, cudaStream_t);                 \
   template int pool_bwd<T>(const T*, const T*, T*, int, int, int, int, bool, bool, const T*,      \
-                           cudaStream_t);                                                         \
+                           const float*, cudaStream_t);                                           \
   template int gram_full<T>(const T*, int, int, bool, float*, float*, size_t, int, cudaStream_t); \
   template int style_grad<T>(const T*, const float*, T*, int, int, double*, ReduceScratch,        \
                              cudaStream_t);                                                       \

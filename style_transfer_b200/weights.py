@@ -26,3 +26,11 @@ def load_npz(path):
     data = np.load(path)
     names = sorted({k[:-2] for k in data.files})
     return OrderedDict((n, (data[n + '_w'], data[n + '_b'])) for n in names)
+
+
+def save_npz(path, params):
+    """Writes weights in the layout ``load_npz`` reads (``<layer>_w`` OIHW f32, ``<layer>_b``)."""
+    arrays = {}
+    for name, (w, b) in params.items():
+        arrays[name + '_w'], arrays[name + '_b'] = np.float32(w), np.float32(b)
+    np.savez(path, **arrays)

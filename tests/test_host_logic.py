@@ -186,3 +186,42 @@ def test_two_rank_dispatch_over_gloo(tmp_path):
     grad = on.roll2_(grad.copy(), -np.array(roll))
     assert np.array_equal(got['grad'], grad)
     assert abs(float(got['loss'][0]) - loss) <= 1e-9 * abs(loss)
+
+
+# ---- flag surface ----------------------------------------------------------------------------------------
+def test_flag_table_matches_reference_defaults(tmp_path, monkeypatch):
+    from style_transfer_b200 import config_system
+    monkeypatch.chdir(tmp_path)
+    a = config_system.parse_args(['-ci', 'c.png', '-si', 's1.png', 's2.png'])
+    assert (a.size, a.min_size, a.tile_size, a.optimizer) == (256, 182, 512, 'adam')
+    assert (a.step_size, a.step_decay, a.avg_window) == (15, [0.05, 0.5], 20)
+    assert (a.content_weight, a.dd_weight, a.tv_weight, a.tv_power) == (0.05, 0, 5, 2)
+    assert (a.p_weight, a.p_power, a.aux_weight) == (2, 6, 10)
+    assert a.iterations == [200, 100] and a.devices == [-1] and a.seed == 0 and a.div == 1
+    assert tuple(a.mean) == (103.939, 116.779, 123.68)
+    assert a.style_images == ['s1.png', 's2.png'] and a.model == 'vgg19.prototxt'
+    # fractions (ffloat), short forms, layer lists with weights
+    b = config_system.parse_args(['-ci', 'c', '-si', 's', '-s', '2048', '-cw', '1/20', '-o', 'lbfgs',
+                                  '--devices', '0', '1', '2', '3', '--content-layers', 'conv4_2:2',
+                                  'conv5_2', '-i', '300'])
+    assert b.size == 2048 and b.content_weight == 0.05 and b.optimizer == 'lbfgs'
+    assert b.devices == [0, 1, 2, 3] and b.content_layers == ['conv4_2:2', 'conv5_2']
+    assert b.iterations == [300]
+    if os.path.exists('/root/reference/config_system.py'):
+        # every flag of the reference exists here with the same default
+        src = open('/root/reference/config_system.py').read()
+        for flag in re.findall(r"arg\('(--[\w-]+)'", src):
+            name = flag[2:].replace('-', '_')
+            assert hasattr(a, name), flag
+
+
+def test_config_precedence(tmp_path, monkeypatch):
+    """defaults < config.py < argv (values that differ from the default) < --config FILE."""
+    from style_transfer_b200 import config_system
+    monkeypatch.chdir(tmp_path)
+    (tmp_path / 'config.py').write_text('size = 512\ntile_size = 256\ntv_weight = 1\n')
+    (tmp_path / 'extra.py').write_text('tv_weight = 7\n')
+    a = config_system.parse_args(['-ci', 'c', '-si', 's', '--tile-size', '384'])
+    assert (a.size, a.tile_size, a.tv_weight) == (512, 384, 1)
+    b = config_system.parse_args(['-ci', 'c', '-si', 's', '--config', str(tmp_path / 'extra.py')])
+    assert (b.size, b.tile_size, b.tv_weight) == (512, 256, 7)
