@@ -156,6 +156,13 @@ ST_API int st_regularizers(const float* img_dev, int H, int W, const float mean[
                     int roll_y, int roll_x, double* loss_accum_dev, float* grad_dev,
                     st_stream stream);
 
+/* st_unpack_grad followed by st_regularizers in ONE pass over the image: grad_dev is written (not
+ * accumulated), the gradient tiles are gathered from the all-gather buffer on the fly. */
+ST_API int st_unpack_regularize(const float* packed_all_dev, const float* img_dev, int H, int W,
+                         int roll_y, int roll_x, int tile_size, int world, const float mean[3],
+                         float tv_w, float tv_beta, float p_w, float p_pow, const float* aux_dev,
+                         float aux_w, double* loss_accum_dev, float* grad_dev, st_stream stream);
+
 /* ---- optimizers (optimizers.py) -------------------------------------------------------------
  * AdamOptimizer.update :26-42 after opfunc returned `grad`: EWMA moments (state g1,g2,p1 hold the
  * EWMA .value arrays), in-place parameter step, iterate averaging; avg_out = p1 / p1_corr.

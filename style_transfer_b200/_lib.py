@@ -57,6 +57,8 @@ PROTOTYPES = {
     'st_gram': (_i, [_vp, _vp, _i, _i, _vp, _vp]),
     'st_regularizers': (_i, [_vp, _i, _i, C.POINTER(_f), _f, _f, _f, _f, _vp, _f, _i, _i, _vp,
                              _vp, _vp]),
+    'st_unpack_regularize': (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, C.POINTER(_f), _f, _f, _f, _f,
+                                  _vp, _f, _vp, _vp, _vp]),
     'st_adam_step': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _sz, _f, _f, _f, _f, _f, _f, _f, _vp]),
     'st_lbfgs_inv_hv': (_i, [_vp, _sz, _i, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(C.c_double),
                              _vp, _vp, _vp]),

@@ -53,6 +53,15 @@ int conv3x3_tc_pair(TcContext& tc, const TcWeights& w, const __nv_bfloat16* in, 
                     int nb, int h, int wd, int cin, int cout, bool forward, const float* bias,
                     const __nv_bfloat16* mask_act, const __nv_bfloat16* inj, const float* inj_scale,
                     cudaStream_t s);
+// Forward convolution + the 2x2/2 pooling layer behind it in one kernel.  pool_out [nb][ho][wo][cout]
+// receives the pooled map, pool_mask (bytes, same shape) what pool_bwd_mask needs:
+//   max: bits 0-1 = window position of the first maximum, bit 2 = maximum > 0
+//   ave: bit d    = window input d > 0
+// `out` is written only when write_full.
+int conv3x3_pool_tc_pair(TcContext& tc, const TcWeights& w, const __nv_bfloat16* in,
+                         __nv_bfloat16* out, __nv_bfloat16* pool_out, uint8_t* pool_mask, int nb, int h,
+                         int wd, int cin, int cout, const float* bias, bool is_max, bool write_full,
+                         cudaStream_t s);
 // Backward of the first (3-channel) convolution on tensor cores: dz [nb][h][w][cz] bf16 -> planar f32
 // gradient; tile b goes to grad + b * batch_stride.  Needs weights packed by tc_pack_first.
 int conv_last_bwd_tc_pair(TcContext& tc, const TcWeights& w, const __nv_bfloat16* dz, int nb, int h,

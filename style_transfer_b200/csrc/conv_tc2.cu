@@ -47,7 +47,10 @@ constexpr int kOutStageBytes = 128 * 128; // 128 pixels x 64 channels bf16
 constexpr int kTailBytes = 3072;          // barriers (256 B) + tmem slot + bias copy (2 KB)
 constexpr int kSmemBudget = 227 * 1024 - 1024 /*alignment slack*/ - kTailBytes;
 
-enum Epilogue { kEpiFwd = 0, kEpiBwd = 1, kEpiAbs = 2, kEpiPix = 3 };
+// kEpiFwdPool = kEpiFwd + the 2x2/2 pooling layer that follows: the pooled map and a one-byte
+// arg-max / ReLU mask per pooled element are produced from the staged output tile
+enum Epilogue { kEpiFwd = 0, kEpiBwd = 1, kEpiAbs = 2, kEpiPix = 3, kEpiFwdPool = 4 };
+constexpr int kPoolStageBytes = 32 * 128;   // 8 x 4 pooled pixels x 64 channels bf16
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -223,6 +226,9 @@ struct Tc2Args {
   const __nv_bfloat16* inj;        // kEpiBwd, may be null
   const float* inj_scale;          // kEpiBwd: per batch tile factor applied to inj, may be null
   double* abs_partials;            // kEpiAbs: [pair tile][cta rank][epilogue warp]
+  int pool_mode;                   // kEpiFwdPool: 1 = max, 2 = average
+  int write_full;                  // kEpiFwdPool: also store the un-pooled output
+  uint8_t* pool_mask;              // kEpiFwdPool: [nb][ho][wo][cout] bytes (see pool_mask_byte)
   float* pix;                      // kEpiPix: planar f32 output, channels 0..2 of the accumulator
   long pix_batch, pix_plane, pix_row;   // strides (floats) between batch tiles / planes / rows
 };
@@ -244,7 +250,7 @@ __device__ __forceinline__ TileCoord decode_tile(const Tc2Args& a, int tile, int
 // RESB: the whole weight matrix of this CTA (its BN/2 rows x all K) stays resident in shared
 // memory for the life of the kernel -- for the small layers (conv1_2, conv2_1, the 3-channel
 // backward) where one TMA round trip per tap costs more than the MMAs of that tap.
-template <int BN, int TAPS, bool RESB = false>
+template <int BN, int TAPS, bool RESB = false, bool POOL = false>
 struct Cfg2 {
   static constexpr int kHaloRows = TAPS == 9 ? kBH + 2 : kBH;
   static constexpr int kVariants = TAPS == 9 ? 3 : 1;
@@ -252,7 +258,8 @@ struct Cfg2 {
   static constexpr int kABytes = kVariants * kAVarBytes;         // 54 KB (3x3) / 16 KB (1x1)
   static constexpr int kBBytes = (BN / 2) * 128;                 // this CTA's half of the B tile
   static constexpr int kSA = TAPS == 9 ? 2 : 4;
-  static constexpr int kOutBytes = 2 * kOutStageBytes;
+  static constexpr int kPoolBytes = POOL ? 2 * kPoolStageBytes : 0;
+  static constexpr int kOutBytes = 2 * kOutStageBytes + kPoolBytes;
   static constexpr int kSBRaw = (kSmemBudget - kSA * kABytes - kOutBytes) / kBBytes;
   static constexpr int kSB = RESB ? 1 : (kSBRaw > 8 ? 8 : kSBRaw);
   static constexpr int kResMax = kSmemBudget - kSA * kABytes - kOutBytes;   // bytes for resident B
@@ -267,8 +274,11 @@ struct Cfg2 {
 template <int BN, int TAPS, int EPI, bool RESB>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1)
 conv_tc2_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CUtensorMap map_w,
-                const __grid_constant__ CUtensorMap map_out, const Tc2Args a) {
-  using Cfg = Cfg2<BN, TAPS, RESB>;
+                const __grid_constant__ CUtensorMap map_out,
+                const __grid_constant__ CUtensorMap map_pool, const Tc2Args a) {
+  constexpr bool kPool = EPI == kEpiFwdPool;
+  constexpr bool kFwd = EPI == kEpiFwd || EPI == kEpiFwdPool;
+  using Cfg = Cfg2<BN, TAPS, RESB, kPool>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~(uintptr_t)1023);
@@ -301,7 +311,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constan
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc_pair(tmem_slot, Cfg::kTmemCols);
-  if constexpr (EPI == kEpiFwd) {
+  if constexpr (kFwd) {
     for (int i = threadIdx.x; i < a.cout; i += kThreads2) bias_s[i] = a.bias[i];
   }
   tc_fence_before();
@@ -478,7 +488,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constan
           float v[32];
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-          if constexpr (EPI == kEpiFwd) {
+          if constexpr (kFwd) {
             const float* bs = bias_s + n_tile * BN + cc * 32;
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i] + bs[i], 0.f);
@@ -542,9 +552,80 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constan
         }
         fence_proxy_async();
         asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (issuer) {
-          tma_store_4d(&map_out, stage_out, n_tile * BN + g * 64, x0, y0, t.b);
-          tma_store_commit();
+        if constexpr (kPool) {
+          // The staged tile holds complete 2x2 windows (tile origins are even).  Each thread pools
+          // two (pooled pixel, 8-channel) items: pooled values -> a second swizzled staging tile
+          // for a TMA store, one mask byte per pooled element -> global memory.
+          //   max: bits 0-1 = position of the first maximum (scan order), bit 2 = maximum > 0
+          //   ave: bit d = input d of the window > 0            (what the backward pass needs)
+          uint8_t* pstage = out_base + 2 * kOutStageBytes + (store_seq & 1) * kPoolStageBytes;
+          const int et = threadIdx.x - 64;                       // 0..127 among the epilogue warps
+          const int ho = (a.h + 1) >> 1, wo = (a.w + 1) >> 1;
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {
+            const int item = et + k * 128, pp = item >> 3, j = item & 7;
+            const int pr = pp >> 2, pc = pp & 3;                 // pooled row / column in the tile
+            float best[8], sum[8];
+            uint32_t code[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) best[e] = -3.4e38f, sum[e] = 0.f, code[e] = 0u;
+            int cnt = 0;
+#pragma unroll
+            for (int d = 0; d < 4; ++d) {
+              const int r = 2 * pr + (d >> 1), cx = 2 * pc + (d & 1);
+              if (y0 + r >= a.h || x0 + cx >= a.w) continue;      // ceil mode: clipped window
+              ++cnt;
+              const int mm = r * 8 + cx;
+              const uint4 raw =
+                  *reinterpret_cast<const uint4*>(stage_out + mm * 128 + ((j ^ (mm & 7)) << 4));
+              const uint32_t w4[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                const float x = __uint_as_float((e & 1) ? (w4[e >> 1] & 0xFFFF0000u) : (w4[e >> 1] << 16));
+                if (a.pool_mode == 1) {
+                  if (x > best[e]) best[e] = x, code[e] = (uint32_t)d;       // strict: first max wins
+                } else {
+                  sum[e] += x;
+                  if (x > 0.f) code[e] |= 1u << d;
+                }
+              }
+            }
+            const int pyo = (y0 >> 1) + pr, pxo = (x0 >> 1) + pc;
+            uint32_t ow[4], mk[2] = {0u, 0u};
+#pragma unroll
+            for (int e = 0; e < 8; e += 2) {
+              float o0, o1;
+              if (a.pool_mode == 1) {
+                o0 = best[e], o1 = best[e + 1];
+                if (o0 > 0.f) code[e] |= 4u;
+                if (o1 > 0.f) code[e + 1] |= 4u;
+              } else {
+                const float inv = (float)(cnt > 0 ? cnt : 1);
+                o0 = sum[e] / inv, o1 = sum[e + 1] / inv;
+              }
+              __nv_bfloat162 h2 = __floats2bfloat162_rn(o0, o1);
+              ow[e >> 1] = *reinterpret_cast<uint32_t*>(&h2);
+            }
+#pragma unroll
+            for (int e = 0; e < 8; ++e) mk[e >> 2] |= code[e] << (8 * (e & 3));
+            *reinterpret_cast<uint4*>(pstage + pp * 128 + ((j ^ (pp & 7)) << 4)) =
+                make_uint4(ow[0], ow[1], ow[2], ow[3]);
+            if (pyo < ho && pxo < wo)
+              *reinterpret_cast<uint2*>(a.pool_mask + (((size_t)t.b * ho + pyo) * wo + pxo) * a.cout +
+                                        n_tile * BN + g * 64 + j * 8) = make_uint2(mk[0], mk[1]);
+          }
+          fence_proxy_async();
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (issuer) {
+            if (a.write_full) tma_store_4d(&map_out, stage_out, n_tile * BN + g * 64, x0, y0, t.b);
+            tma_store_4d(&map_pool, pstage, n_tile * BN + g * 64, x0 >> 1, y0 >> 1, t.b);
+            tma_store_commit();
+          }
+        } else {
+          if (issuer) {
+            tma_store_4d(&map_out, stage_out, n_tile * BN + g * 64, x0, y0, t.b);
+            tma_store_commit();
+          }
         }
       }
     }
@@ -581,10 +662,10 @@ int encode_bf16_map(const TcContext& tc, CUtensorMap* map, int rank, const void*
 
 template <int BN, int TAPS, int EPI, bool RESB>
 int launch2r(TcContext& tc, const __nv_bfloat16* in, const __nv_bfloat16* wk, int wk_rows,
-             __nv_bfloat16* out, Tc2Args a, cudaStream_t s) {
-  using Cfg = Cfg2<BN, TAPS, RESB>;
+             __nv_bfloat16* out, __nv_bfloat16* pool_out, Tc2Args a, cudaStream_t s) {
+  using Cfg = Cfg2<BN, TAPS, RESB, EPI == kEpiFwdPool>;
   a.tiles_x = cdiv(a.w, kBW), a.tiles_y = cdiv(a.h, 2 * kBH), a.tiles_n = a.cout / BN;
-  CUtensorMap map_in, map_out, map_w;
+  CUtensorMap map_in, map_out, map_w, map_pool;
   {
     const uint64_t dims[4] = {(uint64_t)a.cin, (uint64_t)a.w, (uint64_t)a.h, (uint64_t)a.nb};
     const uint64_t strides[3] = {(uint64_t)a.cin * 2, (uint64_t)a.w * a.cin * 2,
@@ -602,6 +683,15 @@ int launch2r(TcContext& tc, const __nv_bfloat16* in, const __nv_bfloat16* wk, in
     if (rc != ST_OK) return rc;
   } else {
     map_out = map_in;            // never dereferenced by the pixel epilogue
+  }
+  map_pool = map_out;
+  if (EPI == kEpiFwdPool) {
+    const uint64_t ho = (a.h + 1) / 2, wo = (a.w + 1) / 2;
+    const uint64_t dims[4] = {(uint64_t)a.cout, wo, ho, (uint64_t)a.nb};
+    const uint64_t strides[3] = {(uint64_t)a.cout * 2, wo * a.cout * 2, ho * wo * a.cout * 2};
+    const uint32_t box[4] = {64, (uint32_t)(kBW / 2), (uint32_t)(kBH / 2), 1};
+    int rc = encode_bf16_map(tc, &map_pool, 4, pool_out, dims, strides, box);
+    if (rc != ST_OK) return rc;
   }
   {
     const uint64_t k = (uint64_t)TAPS * a.cin;
@@ -625,7 +715,7 @@ int launch2r(TcContext& tc, const __nv_bfloat16* in, const __nv_bfloat16* wk, in
   // algorithmic flops: the pixel epilogue computes 3 of its 16 accumulator columns for real
   TimerScope ts(s, EPI == kEpiAbs ? kTimeStyleGrad : (EPI == kEpiPix ? kTimeConvSimt : kTimeConvTc),
                 2.0 * TAPS * a.cin * (EPI == kEpiPix ? 3 : a.cout) * a.h * a.w * a.nb);
-  ST_LAUNCH(kern, 2 * pairs, kThreads2, smem_bytes, s, map_in, map_w, map_out, a);
+  ST_LAUNCH(kern, 2 * pairs, kThreads2, smem_bytes, s, map_in, map_w, map_out, map_pool, a);
   return ST_OK;
 }
 
@@ -633,14 +723,14 @@ int launch2r(TcContext& tc, const __nv_bfloat16* in, const __nv_bfloat16* wk, in
 // batch and this CTA's share of them fits beside the A stages.
 template <int BN, int TAPS, int EPI>
 int launch2(TcContext& tc, const __nv_bfloat16* in, const __nv_bfloat16* wk, int wk_rows,
-            __nv_bfloat16* out, const Tc2Args& a, cudaStream_t s) {
+            __nv_bfloat16* out, const Tc2Args& a, cudaStream_t s, __nv_bfloat16* pool_out = nullptr) {
   if constexpr (BN <= 128) {
-    const long res = (long)TAPS * (a.cin / 64) * Cfg2<BN, TAPS, true>::kBBytes;
-    if (a.cout == BN && !a.w_batched && res <= Cfg2<BN, TAPS, true>::kResMax &&
-        getenv("ST_TC_NO_RESB") == nullptr)
-      return launch2r<BN, TAPS, EPI, true>(tc, in, wk, wk_rows, out, a, s);
+    using CfgR = Cfg2<BN, TAPS, true, EPI == kEpiFwdPool>;
+    const long res = (long)TAPS * (a.cin / 64) * CfgR::kBBytes;
+    if (a.cout == BN && !a.w_batched && res <= CfgR::kResMax && getenv("ST_TC_NO_RESB") == nullptr)
+      return launch2r<BN, TAPS, EPI, true>(tc, in, wk, wk_rows, out, pool_out, a, s);
   }
-  return launch2r<BN, TAPS, EPI, false>(tc, in, wk, wk_rows, out, a, s);
+  return launch2r<BN, TAPS, EPI, false>(tc, in, wk, wk_rows, out, pool_out, a, s);
 }
 
 // Output-channel tile: the widest BN that still gives every CTA pair work; wide tiles halve the
@@ -661,11 +751,12 @@ int choose_bn(const TcContext& tc, int nb, int h, int w, int cout) {
 
 template <int TAPS, int EPI>
 int dispatch_bn(TcContext& tc, int bn, const __nv_bfloat16* in, const __nv_bfloat16* wk, int wk_rows,
-                __nv_bfloat16* out, const Tc2Args& a, cudaStream_t s) {
+                __nv_bfloat16* out, const Tc2Args& a, cudaStream_t s,
+                __nv_bfloat16* pool_out = nullptr) {
   switch (bn) {
-    case 256: return launch2<256, TAPS, EPI>(tc, in, wk, wk_rows, out, a, s);
-    case 128: return launch2<128, TAPS, EPI>(tc, in, wk, wk_rows, out, a, s);
-    default: return launch2<64, TAPS, EPI>(tc, in, wk, wk_rows, out, a, s);
+    case 256: return launch2<256, TAPS, EPI>(tc, in, wk, wk_rows, out, a, s, pool_out);
+    case 128: return launch2<128, TAPS, EPI>(tc, in, wk, wk_rows, out, a, s, pool_out);
+    default: return launch2<64, TAPS, EPI>(tc, in, wk, wk_rows, out, a, s, pool_out);
   }
 }
 
@@ -681,6 +772,19 @@ int conv3x3_tc_pair(TcContext& tc, const TcWeights& w, const __nv_bfloat16* in, 
   const int bn = choose_bn(tc, nb, h, wd, cout);
   if (forward) return dispatch_bn<9, kEpiFwd>(tc, bn, in, w.fwd, cout, out, a, s);
   return dispatch_bn<9, kEpiBwd>(tc, bn, in, w.bwd, cout, out, a, s);
+}
+
+// Forward convolution fused with the 2x2/2 pooling layer that consumes it: writes the pooled map,
+// the backward mask and (write_full) the un-pooled output.
+int conv3x3_pool_tc_pair(TcContext& tc, const TcWeights& w, const __nv_bfloat16* in,
+                         __nv_bfloat16* out, __nv_bfloat16* pool_out, uint8_t* pool_mask, int nb, int h,
+                         int wd, int cin, int cout, const float* bias, bool is_max, bool write_full,
+                         cudaStream_t s) {
+  Tc2Args a{};
+  a.nb = nb, a.h = h, a.w = wd, a.cin = cin, a.cout = cout, a.bias = bias;
+  a.pool_mode = is_max ? 1 : 2, a.write_full = write_full ? 1 : 0, a.pool_mask = pool_mask;
+  const int bn = choose_bn(tc, nb, h, wd, cout);
+  return dispatch_bn<9, kEpiFwdPool>(tc, bn, in, w.fwd, cout, out, a, s, pool_out);
 }
 
 // Backward of the first convolution (cout image planes = 3, padded to 16 accumulator columns):

@@ -59,6 +59,10 @@ struct LayerRt {
   float* bias = nullptr;
   TcWeights tc;              // bf16 packs for the tcgen05 path
   bool has_params = false;
+  // pooling layers: byte mask written when the forward ran fused into the producing convolution
+  uint8_t* pool_mask = nullptr;
+  size_t pool_mask_cap = 0;
+  bool pool_mask_valid = false;
 };
 
 struct BlobRt {
@@ -201,11 +205,26 @@ constexpr int kStatStride = 8;   // doubles per batch tile in ctx->scalars:
                                  //   [0] sum c^2  [1] sum |c|  [2] sum |S|  [3] the tile's loss
 
 // ---- forward -------------------------------------------------------------------------------------
+// A convolution whose output feeds exactly one pooling layer runs fused with it (tensor-core path):
+// the pooled map and a byte mask for the backward pass come out of the conv epilogue; the un-pooled
+// map is only written when somebody else needs it (`need_full`: loss layers, requested features).
 template <typename T>
-int forward(st_ctx* ctx, const ImageBatch& view, const Dims& d, int last_layer, cudaStream_t s) {
+int fused_pool_layer(const st_ctx* ctx, int i, int last_layer) {
+  if (!std::is_same<T, __nv_bfloat16>::value || getenv("ST_NO_POOL_FUSION") != nullptr) return -1;
+  const LayerRt& l = ctx->layers[i];
+  if (l.bottom == 0 || i + 1 > last_layer) return -1;
+  const LayerRt& p = ctx->layers[i + 1];
+  if (p.kind == ST_CONV3X3 || p.bottom != l.top) return -1;
+  return i + 1;
+}
+
+template <typename T>
+int forward(st_ctx* ctx, const ImageBatch& view, const Dims& d, int last_layer,
+            const std::vector<char>& need_full, cudaStream_t s) {
   const int nb = view.nb;
+  for (LayerRt& l : ctx->layers) l.pool_mask_valid = false;
   for (int i = 0; i <= last_layer; ++i) {
-    const LayerRt& l = ctx->layers[i];
+    LayerRt& l = ctx->layers[i];
     const int hb = d.h[l.bottom], wb = d.w[l.bottom];
     T* out = static_cast<T*>(ctx->blobs[l.top].act);
     int rc;
@@ -222,7 +241,24 @@ int forward(st_ctx* ctx, const ImageBatch& view, const Dims& d, int last_layer, 
         if (!done) rc = conv_first_fwd<T>(view, hb, wb, l.w_fwd, l.bias, out, l.cout, s);
       } else {
         const T* in = static_cast<const T*>(ctx->blobs[l.bottom].act);
-        if (tc_usable<T>(ctx->tc, l.tc, l.cin, l.cout))
+        const int pl = tc_usable<T>(ctx->tc, l.tc, l.cin, l.cout) && ctx->tc.pair_kernel
+                           ? fused_pool_layer<T>(ctx, i, last_layer) : -1;
+        if (pl >= 0) {
+          if constexpr (std::is_same<T, __nv_bfloat16>::value) {
+            LayerRt& p = ctx->layers[pl];
+            // other readers of the un-pooled map: loss / feature requests, or another layer (_big)
+            bool full = need_full[l.top] != 0;
+            for (int j = pl + 1; j <= last_layer; ++j) full = full || ctx->layers[j].bottom == l.top;
+            const size_t pooled = (size_t)nb * d.h[p.top] * d.w[p.top] * l.cout;
+            rc = ensure(ctx, (void**)&p.pool_mask, &p.pool_mask_cap, pooled, 1);
+            if (rc == ST_OK)
+              rc = conv3x3_pool_tc_pair(ctx->tc, l.tc, in, out, static_cast<T*>(ctx->blobs[p.top].act),
+                                        p.pool_mask, nb, hb, wb, l.cin, l.cout, l.bias,
+                                        p.kind == ST_POOL_MAX, full, s);
+            p.pool_mask_valid = rc == ST_OK;
+            ++i;                                  // the pooling layer is done
+          }
+        } else if (tc_usable<T>(ctx->tc, l.tc, l.cin, l.cout))
           rc = conv3x3_tc(ctx->tc, l.tc, in, out, nb, hb, wb, l.cin, l.cout, true, l.bias, nullptr,
                           nullptr, nullptr, s);
         else
@@ -391,6 +427,9 @@ int backward(st_ctx* ctx, const Dims& d, int nb, int deepest_blob, const std::ve
         rc = conv3x3_simt<T>(g, l.w_bwd, nullptr, out, nb, hb, wb, l.cout, l.cin, false, mask, inj,
                              s);
       }
+    } else if (l.pool_mask_valid) {
+      rc = pool_bwd_mask<T>(g, l.pool_mask, out, nb, hb, wb, l.cin, l.kind == ST_POOL_MAX, inj,
+                            inj_scale, s);
     } else {
       rc = pool_bwd<T>(g, static_cast<const T*>(bb.act), out, nb, hb, wb, l.cin,
                        l.kind == ST_POOL_MAX, bb.relu, inj, inj_scale, s);
@@ -429,7 +468,7 @@ int eval_batch(st_ctx* ctx, const ImageBatch& view, int h, int w, const BatchGeo
   const int last_layer = ctx->blobs[deepest].producer;
   const Dims d = blob_dims(ctx, h, w);
   int rc = reserve_for(ctx, d, last_layer, g.nb);
-  if (rc == ST_OK) rc = forward<T>(ctx, view, d, last_layer, s);
+  if (rc == ST_OK) rc = forward<T>(ctx, view, d, last_layer, has_inj, s);
   for (int i = 0; i < n_specs && rc == ST_OK; ++i)
     rc = build_injection<T>(ctx, specs[i], d, g, froll_y, froll_x, specs[i].blob == deepest, s);
   if (rc == ST_OK) rc = loss_finalize(ctx->scalars + 3, kStatStride, g.nb, loss_accum, s);
@@ -573,7 +612,7 @@ int st_destroy(st_ctx* ctx) {
   DeviceGuard guard(ctx->device);
   cudaDeviceSynchronize();
   for (LayerRt& l : ctx->layers) {
-    cudaFree(l.w_fwd), cudaFree(l.w_bwd), cudaFree(l.bias);
+    cudaFree(l.w_fwd), cudaFree(l.w_bwd), cudaFree(l.bias), cudaFree(l.pool_mask);
     tc_free_weights(l.tc);
   }
   for (BlobRt& b : ctx->blobs) cudaFree(b.act), cudaFree(b.inj), cudaFree(b.inj_scale);
@@ -712,8 +751,10 @@ int st_eval_features_tile(st_ctx* ctx, const float* img_dev, int h, int w, int n
   ImageBatch view{};
   view.base = img_dev, view.H = h, view.W = w, view.nb = 1;
   cudaStream_t s = (cudaStream_t)stream;
-  rc = ctx->precision == ST_PREC_FP32 ? forward<float>(ctx, view, d, last_layer, s)
-                                      : forward<__nv_bfloat16>(ctx, view, d, last_layer, s);
+  std::vector<char> need_full(ctx->blobs.size(), 0);
+  for (int i = 0; i < n_blobs; ++i) need_full[blob_ids[i]] = 1;
+  rc = ctx->precision == ST_PREC_FP32 ? forward<float>(ctx, view, d, last_layer, need_full, s)
+                                      : forward<__nv_bfloat16>(ctx, view, d, last_layer, need_full, s);
   for (int i = 0; i < n_blobs && rc == ST_OK; ++i) {
     const int b = blob_ids[i];
     const int hw = d.h[b] * d.w[b];
@@ -825,7 +866,8 @@ static int global_scratch(ReduceScratch* out) {
   ST_CUDA(cudaGetDevice(&dev));
   ST_REQUIRE(dev < 16, "device index too large");
   if (!g_scratch[dev].partials) {
-    ST_CUDA(cudaMalloc((void**)&g_scratch[dev].partials, (size_t)4096 * 4 * sizeof(double)));
+    ST_CUDA(cudaMalloc((void**)&g_scratch[dev].partials,
+                       (size_t)kMaxReduceBlocks * 4 * sizeof(double)));
     ST_CUDA(cudaMalloc((void**)&g_scratch[dev].counter, sizeof(unsigned)));
     ST_CUDA(cudaMemset(g_scratch[dev].counter, 0, sizeof(unsigned)));
   }
@@ -844,6 +886,24 @@ int st_regularizers(const float* img_dev, int H, int W, const float mean[3], flo
   if (rc != ST_OK) return rc;
   return regularizers(img_dev, H, W, mean[0], mean[1], mean[2], tv_w, tv_beta, p_w, p_pow, aux_dev,
                       aux_w, roll_y, roll_x, loss_accum_dev, grad_dev, rs, (cudaStream_t)stream);
+}
+
+int st_unpack_regularize(const float* packed_all_dev, const float* img_dev, int H, int W,
+                         int roll_y, int roll_x, int tile_size, int world, const float mean[3],
+                         float tv_w, float tv_beta, float p_w, float p_pow, const float* aux_dev,
+                         float aux_w, double* loss_accum_dev, float* grad_dev, st_stream stream) {
+  ST_REQUIRE(packed_all_dev && img_dev && mean && loss_accum_dev && grad_dev && H > 0 && W > 0 &&
+                 tile_size > 0 && world > 0,
+             "st_unpack_regularize: bad arguments");
+  ReduceScratch rs;
+  int rc = global_scratch(&rs);
+  if (rc != ST_OK) return rc;
+  const Grid g = tile_grid(H, W, tile_size);
+  const int tpr = (g.nty * g.ntx + world - 1) / world;
+  return unpack_regularizers(packed_all_dev, H, W, g.nty, g.ntx, g.th, g.tw, g.thmax, g.twmax, world,
+                             tpr, img_dev, mean[0], mean[1], mean[2], tv_w, tv_beta, p_w, p_pow,
+                             aux_dev, aux_w, roll_y, roll_x, loss_accum_dev, grad_dev, rs,
+                             (cudaStream_t)stream);
 }
 
 int st_adam_step(float* params, const float* grad, float* g1, float* g2, float* p1, float* avg_out,

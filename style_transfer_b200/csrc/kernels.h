@@ -55,6 +55,12 @@ template <typename T>
 int pool_bwd(const T* d_out, const T* in, T* d_in, int nb, int h, int w, int c, bool is_max,
              bool apply_mask, const T* inj, const float* inj_scale, cudaStream_t s);
 
+// backward of a pooling layer from the one-byte mask the fused conv+pool kernel stored
+// (conv_tc.h: conv3x3_pool_tc_pair); the ReLU mask of the pooled layer is part of the byte
+template <typename T>
+int pool_bwd_mask(const T* d_out, const uint8_t* mask, T* d_in, int nb, int h, int w, int c,
+                  bool is_max, const T* inj, const float* inj_scale, cudaStream_t s);
+
 // ---- Gram / style ------------------------------------------------------------------------------
 // gram_full[C][C] (symmetric, float) = F^T F / (C*HW).  F is NHWC [hw][c] (channel_major=false) or
 // [c][hw] (channel_major=true).  part: scratch for split-K partials (part_floats floats).
@@ -111,6 +117,12 @@ int unpack_grad(const float* packed, int H, int W, int roll_y, int roll_x, int n
 int regularizers(const float* img, int H, int W, float m0, float m1, float m2, float tv_w,
                  float tv_beta, float p_w, float p_pow, const float* aux, float aux_w, int roll_y,
                  int roll_x, double* loss_accum, float* grad, ReduceScratch rs, cudaStream_t s);
+// st_unpack_grad + st_regularizers in one pass over the image
+int unpack_regularizers(const float* packed, int H, int W, int nty, int ntx, int th, int tw,
+                        int thmax, int twmax, int world, int tiles_per_rank, const float* img,
+                        float m0, float m1, float m2, float tv_w, float tv_beta, float p_w,
+                        float p_pow, const float* aux, float aux_w, int roll_y, int roll_x,
+                        double* loss_accum, float* grad, ReduceScratch rs, cudaStream_t s);
 int adam_step(float* params, const float* grad, float* g1, float* g2, float* p1, float* avg_out,
               size_t n, float step_size, float b1, float b2, float bp1, float g1_corr,
               float g2_corr, float p1_corr, cudaStream_t s);

@@ -377,6 +377,55 @@ pool_bwd_kernel(const T* __restrict__ d_out, const T* __restrict__ in_all, T* __
   }
 }
 
+// Backward of a pooling layer whose forward ran fused into the convolution (conv_tc2.cu): the input
+// activations are never read, one mask byte per pooled element says where the gradient goes
+// (max: bits 0-1 arg-max position, bit 2 maximum > 0) or which inputs pass the ReLU (ave: bit d).
+template <typename T>
+__global__ void __launch_bounds__(256)
+pool_bwd_mask_kernel(const T* __restrict__ d_out, const uint8_t* __restrict__ mask,
+                     T* __restrict__ d_in_all, int nb, int h, int w, int c, int ho, int wo, int is_max,
+                     const T* __restrict__ inj_all, const float* __restrict__ inj_scale) {
+  const unsigned c8 = c >> 3, uwo = wo, uho = ho;
+  const unsigned total = (unsigned)nb * ho * wo * c8;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const unsigned q = i % c8, p = i / c8;
+    const unsigned row = p / uwo;
+    const int x = (int)(p - row * uwo), y = (int)(row % uho);
+    const unsigned bt = row / uho;
+    const size_t boff = (size_t)bt * ((size_t)h * w * c) + q * 8;
+    T* d_in = d_in_all + boff;
+    const T* inj = inj_all ? inj_all + boff : nullptr;
+    const float isc = inj_scale ? inj_scale[bt] : 1.f;
+    const F8 g = ld8(d_out + (size_t)p * c + q * 8);
+    const uint2 mk = *reinterpret_cast<const uint2*>(mask + (size_t)p * c + q * 8);
+    int cnt = 0;
+#pragma unroll
+    for (int d = 0; d < 4; ++d) cnt += (2 * y + (d >> 1) < h && 2 * x + (d & 1) < w) ? 1 : 0;
+    const float inv = (float)cnt;
+#pragma unroll
+    for (int d = 0; d < 4; ++d) {
+      const int yy = 2 * y + (d >> 1), xx = 2 * x + (d & 1);
+      if (yy >= h || xx >= w) continue;
+      const size_t o = ((size_t)yy * w + xx) * c;
+      F8 r;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const uint32_t code = ((k < 4 ? mk.x : mk.y) >> (8 * (k & 3))) & 0xFFu;
+        if (is_max)
+          r.v[k] = ((code & 3u) == (uint32_t)d && (code & 4u)) ? g.v[k] : 0.f;
+        else
+          r.v[k] = ((code >> d) & 1u) ? g.v[k] / inv : 0.f;
+      }
+      if (inj) {
+        const F8 e = ld8(inj + o);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) r.v[k] += isc * e.v[k];
+      }
+      st8(d_in + o, r);
+    }
+  }
+}
+
 static inline int ew_grid(size_t work_items, int block) {
   size_t b = (work_items + block - 1) / block;
   const size_t cap = 148 * 16;
@@ -406,6 +455,20 @@ int pool_bwd(const T* d_out, const T* in, T* d_in, int nb, int h, int w, int c, 
                                   ((double)h * w * (2 + (inj ? 1 : 0)) + (double)ho * wo));
   ST_LAUNCH(k, ew_grid((size_t)nb * ho * wo * (c / 4), 256), 256, 0, s, d_out, in, d_in, nb, h, w,
             c, ho, wo, is_max ? 1 : 0, apply_mask ? 1 : 0, inj, inj_scale);
+  return ST_OK;
+}
+
+template <typename T>
+int pool_bwd_mask(const T* d_out, const uint8_t* mask, T* d_in, int nb, int h, int w, int c,
+                  bool is_max, const T* inj, const float* inj_scale, cudaStream_t s) {
+  ST_REQUIRE(c % 8 == 0, "pool: channels must be a multiple of 8");
+  const int ho = (h + 1) / 2, wo = (w + 1) / 2;
+  ST_REQUIRE((size_t)nb * ho * wo * c < ((size_t)1 << 31), "pool: batch too large for 32-bit indexing");
+  auto k = pool_bwd_mask_kernel<T>;
+  TimerScope ts(s, kTimePool, (double)c * nb * ((double)sizeof(T) * h * w * (1 + (inj ? 1 : 0)) +
+                                                (double)(sizeof(T) + 1) * ho * wo));
+  ST_LAUNCH(k, ew_grid((size_t)nb * ho * wo * (c / 8), 256), 256, 0, s, d_out, mask, d_in, nb, h, w,
+            c, ho, wo, is_max ? 1 : 0, inj, inj_scale);
   return ST_OK;
 }
 
@@ -838,6 +901,8 @@ int nchw_to_nhwc_f32(const float* in, float* out, int hw, int c, cudaStream_t s)
   template int pool_fwd<T>(const T*, T*, int, int, int, int, bool, cudaStream_t);                 \
   template int pool_bwd<T>(const T*, const T*, T*, int, int, int, int, bool, bool, const T*,      \
                            const float*, cudaStream_t);                                           \
+  template int pool_bwd_mask<T>(const T*, const uint8_t*, T*, int, int, int, int, bool, const T*,  \
+                                const float*, cudaStream_t);                                      \
   template int gram_full<T>(const T*, int, int, bool, float*, float*, size_t, int, cudaStream_t); \
   template int style_grad<T>(const T*, const float*, T*, int, int, double*, ReduceScratch,        \
                              cudaStream_t);                                                       \

@@ -291,7 +291,7 @@ class TileEngine:
         return float(self._loss.item()), grad
 
     def eval_sc_grad(self, roll, content_layers, style_layers, dd_layers, layer_weights,
-                     content_weight, style_weight, dd_weight, tile_size, img=None):
+                     content_weight, style_weight, dd_weight, tile_size, img=None, regularizers=None):
         """Evaluates the summed style and content gradients (:614-645) of ``img`` (default
         ``self.img``) under the virtual roll ``roll`` = (x, y) pixels.  Returns (loss, grad) as
         CUDA tensors (float64[1], float32[3,H,W]) in the UN-rolled frame; nothing is synchronised."""
@@ -309,8 +309,16 @@ class TileEngine:
                   self.world, len(layers), specs, _ptr(loss), _ptr(self._packed), _stream())
         packed_all, loss = sharding.exchange(self._packed, loss, self.world, self.group)
         grad = torch.empty_like(img)
-        _lib.call('st_unpack_grad', _ptr(packed_all), H, W, ry, rx, tile_size, self.world,
-                  _ptr(grad), _stream())
+        if regularizers is None:
+            _lib.call('st_unpack_grad', _ptr(packed_all), H, W, ry, rx, tile_size, self.world,
+                      _ptr(grad), _stream())
+        else:
+            # StyleTransfer.eval_loss_and_grad's full-image terms (:700-736) in the same pass
+            mean, tv_w, tv_beta, p_w, p_pow, aux, aux_w = regularizers
+            _lib.call('st_unpack_regularize', _ptr(packed_all), _ptr(img), H, W, ry, rx, tile_size,
+                      self.world, mean, tv_w, tv_beta, p_w, p_pow,
+                      C.c_void_p(aux.data_ptr()) if aux is not None else None, aux_w, _ptr(loss),
+                      _ptr(grad), _stream())
         return loss, grad
 
     # ---- roll -----------------------------------------------------------------------------------

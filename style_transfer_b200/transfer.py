@@ -90,17 +90,14 @@ class StyleTransfer:
         content_weight, style_weight, dd_weight, tile_size) as in the reference minus the pool."""
         a = self.args
         lw = self.layer_weights['data']
-        loss, grad = self.model.eval_sc_grad(*sc_grad_args, img=img)
-        roll = sc_grad_args[0]
         tv_w = lw * a.tv_weight if a.tv_weight else 0.0
         p_w = lw * a.p_weight if a.p_weight else 0.0
         aux_w = lw * a.aux_weight if self.aux_image is not None else 0.0
+        reg = None
         if tv_w or p_w or self.aux_image is not None:
-            H, W = img.shape[-2:]
-            _lib.call('st_regularizers', _ptr(img), H, W, self._mean, tv_w, a.tv_power, p_w,
-                      a.p_power, _ptr(self.aux_image), aux_w, int(roll[1]), int(roll[0]),
-                      _ptr(loss), _ptr(grad), _stream())
-        return loss, grad
+            reg = (self._mean, tv_w, a.tv_power, p_w, a.p_power, self.aux_image, aux_w)
+        # the regularisers ride on the pass that stitches the gradient tiles (st_unpack_regularize)
+        return self.model.eval_sc_grad(*sc_grad_args, img=img, regularizers=reg)
 
     # ---- first-scale initialisation (:882-901) ---------------------------------------------------
     def init_first_scale(self, h, w, initial_image=None):
