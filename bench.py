@@ -277,17 +277,24 @@ def run_engine(a):
     # ---- end to end: host buffers in, host buffers out, every step --------------------------------
     e2e = None
     if not a.no_e2e:
-        host_params = torch.empty(eng.img.shape, dtype=torch.float32).pin_memory()
-        host_avg = torch.empty(eng.img.shape, dtype=torch.float32).pin_memory()
-        host_loss = torch.empty(1, dtype=torch.float64).pin_memory()
-        host_params.copy_(eng.img)
+        # Only rank 0 talks to the host (as the reference's master process does); the image reaches
+        # the other ranks over NVLink (one NCCL broadcast), results leave from rank 0.
+        if rank == 0:
+            host_params = torch.empty(eng.img.shape, dtype=torch.float32).pin_memory()
+            host_avg = torch.empty(eng.img.shape, dtype=torch.float32).pin_memory()
+            host_loss = torch.empty(1, dtype=torch.float64).pin_memory()
+            host_params.copy_(eng.img)
 
         def e2e_step():
-            eng.img.copy_(host_params, non_blocking=True)            # H2D: this step's image
+            if rank == 0:
+                eng.img.copy_(host_params, non_blocking=True)        # H2D: this step's image
+            if world > 1:
+                dist.broadcast(eng.img, src=0)
             avg, loss = st.step()
-            host_avg.copy_(avg, non_blocking=True)                   # D2H: averaged iterate
-            host_params.copy_(eng.img, non_blocking=True)            # D2H: updated parameters
-            host_loss.copy_(loss, non_blocking=True)                 # D2H: loss
+            if rank == 0:
+                host_avg.copy_(avg, non_blocking=True)               # D2H: averaged iterate
+                host_params.copy_(eng.img, non_blocking=True)        # D2H: updated parameters
+                host_loss.copy_(loss, non_blocking=True)             # D2H: loss
             torch.cuda.current_stream().synchronize()
         for _ in range(2):
             e2e_step()
@@ -296,7 +303,8 @@ def run_engine(a):
                'h2d_bytes_per_step': n * 4, 'd2h_bytes_per_step': 2 * n * 4 + 8,
                'ms_per_step': ms_e2e / a.steps,
                'boundary': 'pinned host f32[3,H,W] image in; averaged iterate, updated image and '
-                           'loss out (StyleTransfer.step through the C ABI), every step'}
+                           'loss out (StyleTransfer.step through the C ABI), every step; with N > 1 '
+                           'rank 0 owns the host side and broadcasts the image over NCCL'}
 
     # ---- roofline of the dominant kernel (per-launch CUDA events on the launching stream) ---------
     roofline, breakdown = None, None

@@ -109,6 +109,20 @@ template <> struct Store<__nv_bfloat16> {
   }
 };
 
+// Division of n < 2^31 by a runtime constant without the ~30-instruction integer divide:
+// q = (umulhi(n, M) + n) >> s with s = ceil(log2 d), M = floor(2^32 * (2^s - d) / d) + 1.
+struct FastDiv {
+  unsigned d, M, s;
+  FastDiv() : d(1), M(1), s(0) {}
+  explicit FastDiv(unsigned div) : d(div) {
+    s = 0;
+    while ((1u << s) < d) ++s;
+    M = (unsigned)((((unsigned long long)1 << 32) * (((unsigned long long)1 << s) - d)) / d + 1);
+  }
+  __device__ __forceinline__ unsigned div(unsigned n) const { return (__umulhi(n, M) + n) >> s; }
+  __device__ __forceinline__ unsigned mod(unsigned n) const { return n - div(n) * d; }
+};
+
 // 8 consecutive channels at once: 16 bytes of bf16 / 32 bytes of float
 struct F8 {
   float v[8];

@@ -87,16 +87,21 @@ __device__ __forceinline__ TvTerm tv_term(float xc, float xr, float xd, float be
   return t;
 }
 
-// One 32 x 8 pixel tile of one plane per block.  The scaled pixels (img / 127.5) of the tile plus a
-// one-pixel rim are staged in shared memory and the TV term of every position is computed ONCE
-// (the first version recomputed it for the left and upper neighbour: 760 instructions per pixel,
-// instruction-bound at 4 % of the HBM bandwidth).  When `packed` is given the tiled gradient is
+// Persistent blocks, one 32 x 8 pixel tile of one plane at a time.  The scaled pixels (img / 127.5,
+// an IEEE division to match the reference) of the tile plus a one-pixel rim are staged in shared
+// memory once; index arithmetic uses FastDiv (the first version spent 760 instructions per pixel on
+// seven divisions and 64-bit div/mod: instruction-bound at 4 % of the HBM bandwidth).  When `packed` is given the tiled gradient is
 // gathered from the all-gather buffer in the same pass (st_unpack_grad fused in).
 constexpr int kRTW = 32, kRTH = 8;
 
 struct UnpackGeom {
   int roll_y, roll_x;          // reduced to [0, H) x [0, W)
   int nty, ntx, th, tw, thmax, twmax, world, tiles_per_rank;
+  FastDiv div_th, div_tw, div_world;
+};
+struct RegTiles {
+  int tiles_x, num_tiles;
+  FastDiv div_tiles_x, div_plane;    // by tiles_x and by tiles_x * tiles_y
 };
 
 __global__ void __launch_bounds__(kRTW* kRTH)
@@ -104,20 +109,19 @@ regularizers_kernel(const float* __restrict__ img, int H, int W, float m0, float
                     float tv_w, float tv_beta, float p_w, float p_pow,
                     const float* __restrict__ aux, float aux_w, int roll_y, int roll_x,
                     double* loss_accum, float* __restrict__ grad,
-                    const float* __restrict__ packed, UnpackGeom ug, ReduceScratch rs) {
+                    const float* __restrict__ packed, UnpackGeom ug, RegTiles rt, ReduceScratch rs) {
   __shared__ float xs[kRTH + 2][kRTW + 2];       // scaled pixels, origin (y0-1, x0-1)
-  __shared__ float sdx[kRTH + 1][kRTW + 1];      // d/d(dx) term of positions (y0-1.., x0-1..)
-  __shared__ float sdy[kRTH + 1][kRTW + 1];
   const int tx = threadIdx.x % kRTW, ty = threadIdx.x / kRTW;
-  const int tiles_x = (W + kRTW - 1) / kRTW, tiles_y = (H + kRTH - 1) / kRTH;
-  const int num_tiles = 3 * tiles_x * tiles_y;
+  const int num_tiles = rt.num_tiles;
   const bool do_tv = tv_w != 0.f;
   double v[1] = {0.0};
   float part = 0.f;
+  int since_flush = 0;
   // persistent blocks walk the tile list: one grid-wide reduction per block, not per tile
   for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-    const int c = tile / (tiles_x * tiles_y), rem = tile - c * tiles_x * tiles_y;
-    const int y0 = (rem / tiles_x) * kRTH, x0 = (rem % tiles_x) * kRTW;
+    const int c = (int)rt.div_plane.div(tile), rem = tile - c * (int)rt.div_plane.d;
+    const int trow = (int)rt.div_tiles_x.div(rem);
+    const int y0 = trow * kRTH, x0 = (rem - trow * rt.tiles_x) * kRTW;
     const float* pl = img + (size_t)c * H * W;
     if (do_tv) {
       __syncthreads();                                      // previous tile's readers are done
@@ -130,12 +134,6 @@ regularizers_kernel(const float* __restrict__ img, int H, int W, float m0, float
         xs[r][q] = pl[(size_t)yy * W + xx] / 127.5f;
       }
       __syncthreads();
-      for (int i = threadIdx.x; i < (kRTH + 1) * (kRTW + 1); i += kRTW * kRTH) {
-        const int r = i / (kRTW + 1), q = i % (kRTW + 1);   // position (y0-1+r, x0-1+q)
-        const TvTerm t = tv_term(xs[r][q], xs[r][q + 1], xs[r + 1][q], tv_beta);
-        sdx[r][q] = t.ddx, sdy[r][q] = t.ddy;
-      }
-      __syncthreads();
     }
     const int x = x0 + tx, y = y0 + ty;
     if (x < W && y < H) {
@@ -143,9 +141,12 @@ regularizers_kernel(const float* __restrict__ img, int H, int W, float m0, float
       const float raw = pl[(size_t)y * W + x];
       float g = 0.f, l = 0.f;
       if (do_tv) {
-        const TvTerm t0 =
-            tv_term(xs[ty + 1][tx + 1], xs[ty + 1][tx + 2], xs[ty + 2][tx + 1], tv_beta);
-        g += tv_w * (sdx[ty + 1][tx + 1] + sdy[ty + 1][tx + 1] - sdx[ty + 1][tx] - sdy[ty][tx + 1]);
+        // own term and the terms of the left / upper neighbour (their d/d(dx), d/d(dy) reach here)
+        const float xc = xs[ty + 1][tx + 1];
+        const TvTerm t0 = tv_term(xc, xs[ty + 1][tx + 2], xs[ty + 2][tx + 1], tv_beta);
+        const TvTerm tl = tv_term(xs[ty + 1][tx], xc, xs[ty + 2][tx], tv_beta);
+        const TvTerm tu = tv_term(xs[ty][tx + 1], xs[ty][tx + 2], xc, tv_beta);
+        g += tv_w * (t0.ddx + t0.ddy - tl.ddx - tu.ddy);
         l += tv_w * t0.pw;
       }
       if (p_w != 0.f) {
@@ -172,9 +173,10 @@ regularizers_kernel(const float* __restrict__ img, int H, int W, float m0, float
       if (packed != nullptr) {               // fused st_unpack_grad
         int yr = y + ug.roll_y, xr = x + ug.roll_x;
         yr = yr >= H ? yr - H : yr, xr = xr >= W ? xr - W : xr;
-        const int tyy = min(yr / ug.th, ug.nty - 1), txx = min(xr / ug.tw, ug.ntx - 1);
+        const int tyy = min((int)ug.div_th.div(yr), ug.nty - 1);
+        const int txx = min((int)ug.div_tw.div(xr), ug.ntx - 1);
         const int t = tyy * ug.ntx + txx;
-        const int rank = t % ug.world, slot = t / ug.world;
+        const int slot = (int)ug.div_world.div(t), rank = t - slot * ug.world;
         const size_t pb = ((size_t)(rank * ug.tiles_per_rank + slot) * 3 + c) * ug.thmax * ug.twmax;
         base = packed[pb + (size_t)(yr - tyy * ug.th) * ug.twmax + (xr - txx * ug.tw)];
       } else {
@@ -183,7 +185,7 @@ regularizers_kernel(const float* __restrict__ img, int H, int W, float m0, float
       grad[i] = base + g;
       part += l;
     }
-    if ((tile / gridDim.x) % 16 == 15) v[0] += (double)part, part = 0.f;
+    if (++since_flush == 16) v[0] += (double)part, part = 0.f, since_flush = 0;
   }
   v[0] += (double)part;
   if (grid_reduce<1>(v, rs.partials, rs.counter)) atomicAdd(loss_accum, v[0]);
@@ -194,11 +196,16 @@ static int launch_regularizers(const float* img, int H, int W, float m0, float m
                                float aux_w, int roll_y, int roll_x, double* loss_accum, float* grad,
                                const float* packed, const UnpackGeom& ug, ReduceScratch rs,
                                cudaStream_t s) {
-  const int num_tiles = 3 * cdiv(W, kRTW) * cdiv(H, kRTH);
+  RegTiles rt;
+  rt.tiles_x = cdiv(W, kRTW);
+  const int tiles_y = cdiv(H, kRTH);
+  rt.num_tiles = 3 * rt.tiles_x * tiles_y;
+  rt.div_tiles_x = FastDiv(rt.tiles_x), rt.div_plane = FastDiv(rt.tiles_x * tiles_y);
+  const int num_tiles = rt.num_tiles;
   const int grid = num_tiles < 148 * 8 ? num_tiles : 148 * 8;
   TimerScope ts(s, kTimeImage, 4.0 * 3 * H * W * (3 + (aux ? 1 : 0)));
   ST_LAUNCH(regularizers_kernel, grid, kRTW * kRTH, 0, s, img, H, W, m0, m1, m2, tv_w, tv_beta, p_w,
-            p_pow, aux, aux_w, roll_y, roll_x, loss_accum, grad, packed, ug, rs);
+            p_pow, aux, aux_w, roll_y, roll_x, loss_accum, grad, packed, ug, rt, rs);
   return ST_OK;
 }
 
@@ -215,7 +222,7 @@ int unpack_regularizers(const float* packed, int H, int W, int nty, int ntx, int
                         float p_pow, const float* aux, float aux_w, int roll_y, int roll_x,
                         double* loss_accum, float* grad, ReduceScratch rs, cudaStream_t s) {
   UnpackGeom ug{((roll_y % H) + H) % H, ((roll_x % W) + W) % W, nty, ntx, th, tw, thmax, twmax,
-                world, tiles_per_rank};
+                world, tiles_per_rank, FastDiv(th), FastDiv(tw), FastDiv(world)};
   return launch_regularizers(img, H, W, m0, m1, m2, tv_w, tv_beta, p_w, p_pow, aux, aux_w, roll_y,
                              roll_x, loss_accum, grad, packed, ug, rs, s);
 }

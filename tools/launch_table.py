@@ -8,9 +8,9 @@ path = sys.argv[1] if len(sys.argv) > 1 else 'gpurun_out/launches_tile.csv'
 with open(path) as f:
     rows = list(csv.DictReader([l for l in f if not l.startswith('==')]))
 names = [(r['Kernel Name'], float(r['Metric Value'].replace(',', '')) / 1000, r['Grid Size']) for r in rows]
-ends = [i for i, n in enumerate(names) if 'conv_last_bwd' in n[0]]
+ends = [i for i, n in enumerate(names) if 'conv_last_bwd' in n[0] or ', 9, 3, ' in n[0]]
 start = ends[-2] + 1 if len(ends) > 1 else 0
-stop = ends[-1] + 1
+stop = ends[-1] + 1 if ends else len(names)
 if '--step' in sys.argv:     # a whole optimizer step: up to and including the last adam kernel
     adams = [i for i, n in enumerate(names) if 'adam_kernel' in n[0]]
     start, stop = adams[-2] + 1, adams[-1] + 1
