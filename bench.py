@@ -46,7 +46,7 @@ def parse_args():
     p.add_argument('--steps', type=int, default=10)
     p.add_argument('--warmup', type=int, default=3)
     p.add_argument('--impl', default='engine', choices=['engine', 'reference'])
-    p.add_argument('--precision', default='bf16', choices=['bf16', 'fp32'])
+    p.add_argument('--precision', default='fp16', choices=['bf16', 'fp16', 'fp32'])
     p.add_argument('--size', type=int, default=2048)
     p.add_argument('--tile-size', type=int, default=512)
     p.add_argument('--optimizer', default='adam', choices=['adam', 'lbfgs'])
@@ -330,7 +330,7 @@ def run_engine(a):
     dom = 'conv_tc' if breakdown['conv_tc']['ms_per_step'] > 0 else 'conv_edge'
     d = breakdown[dom]
     if d['ms_per_step'] > 0:
-        if a.precision == 'bf16':
+        if a.precision in ('bf16', 'fp16'):
             peak = peaks.get('bf16_tflops_sustained', 1400.0)
             src = 'MEASURED_PEAKS.json bf16_tflops_sustained' if peaks else 'fallback 1400 (recipe)'
         else:
@@ -362,13 +362,13 @@ def run_engine(a):
         cfg = workload_config(a, world)
         cfg['l2'] = ('no explicit flush: one step streams the %d MB of image + optimizer state and '
                      '~%d MB of activations per tile, both larger than the 126 MB L2'
-                     % (6 * n * 4 >> 20, 152 if a.precision == 'bf16' else 304))
+                     % (6 * n * 4 >> 20, 304 if a.precision == 'fp32' else 152))
         cfg['precision'] = a.precision
         line = {
             'metric': METRIC, 'value': value, 'unit': 'iterations/s', 'n_gpus': world,
             'steps': a.steps, 'warmup': a.warmup, 'ms_per_step': ms / a.steps,
             'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
-            'dtype': 'bf16' if a.precision == 'bf16' else 'f32', 'data': 'synthetic', 'config': cfg,
+            'dtype': {'bf16': 'bf16', 'fp16': 'f16 forward / bf16 backward', 'fp32': 'f32'}[a.precision], 'data': 'synthetic', 'config': cfg,
             'clocks': clocks, 'e2e': e2e, 'gpu_launches': launches, 'roofline': roofline,
             'cpu_baseline': cpu, 'breakdown': breakdown,
             'tile_eval_ms': breakdown and sum(v['ms_per_step'] for k, v in breakdown.items()

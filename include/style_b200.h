@@ -53,8 +53,11 @@ enum st_status {
 /* Arithmetic of the convolution / Gram contractions.  Reductions, losses, regularisers and the
  * optimizers are float32 (double accumulators) in both modes. */
 enum st_precision {
-  ST_PREC_FP32 = 0,                 /* float32 SIMT everywhere: the parity mode                */
-  ST_PREC_BF16 = 1                  /* bf16 operands, fp32 accumulate on tcgen05 tensor cores  */
+  ST_PREC_FP32 = 0,                 /* float32 SIMT everywhere: the parity mode                   */
+  ST_PREC_BF16 = 1,                 /* bf16 operands, fp32 accumulate on tcgen05 tensor cores     */
+  ST_PREC_FP16 = 2                  /* tensor cores with fp16 forward activations / weights (11-bit
+                                       significand, range 6e-5 .. 65504) and bf16 gradients: same
+                                       speed as ST_PREC_BF16, ~4x smaller gradient error          */
 };
 
 enum st_layer_kind { ST_CONV3X3 = 0, ST_POOL_MAX = 1, ST_POOL_AVE = 2 };

@@ -81,8 +81,8 @@ def build_parser():
     arg('--div', metavar='FACTOR', type=int, default=1, help='ensure all images are divisible by FACTOR')
     arg('--jitter', action='store_true', help='not supported (out of the hot-path scope)')
     arg('--debug', action='store_true', help='enable debug messages')
-    arg('--precision', default='bf16', choices=['bf16', 'fp32'],
-        help='bf16: tcgen05 tensor cores; fp32: exact SIMT parity mode')
+    arg('--precision', default='fp16', choices=['bf16', 'fp16', 'fp32'],
+        help='bf16 / fp16 (fp16 forward, bf16 backward): tcgen05 tensor cores; fp32: exact SIMT parity mode')
     return p
 
 

@@ -2,6 +2,7 @@
 #pragma once
 
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -109,6 +110,24 @@ template <> struct Store<__nv_bfloat16> {
   }
 };
 
+template <> struct Store<__half> {
+  static __device__ __forceinline__ float ld(const __half* p) { return __half2float(*p); }
+  static __device__ __forceinline__ void st(__half* p, float v) { *p = __float2half_rn(v); }
+  static __device__ __forceinline__ float4 ld4(const __half* p) {
+    uint2 raw = *reinterpret_cast<const uint2*>(p);
+    const float2 fa = __half22float2(*reinterpret_cast<__half2*>(&raw.x));
+    const float2 fb = __half22float2(*reinterpret_cast<__half2*>(&raw.y));
+    return make_float4(fa.x, fa.y, fb.x, fb.y);
+  }
+  static __device__ __forceinline__ void st4(__half* p, float4 v) {
+    __half2 a = __floats2half2_rn(v.x, v.y), b = __floats2half2_rn(v.z, v.w);
+    uint2 raw;
+    raw.x = *reinterpret_cast<uint32_t*>(&a);
+    raw.y = *reinterpret_cast<uint32_t*>(&b);
+    *reinterpret_cast<uint2*>(p) = raw;
+  }
+};
+
 // Division of n < 2^31 by a runtime constant without the ~30-instruction integer divide:
 // q = (umulhi(n, M) + n) >> s with s = ceil(log2 d), M = floor(2^32 * (2^s - d) / d) + 1.
 struct FastDiv {
@@ -154,6 +173,42 @@ __device__ __forceinline__ void st8(__nv_bfloat16* p, const F8& f) {
     w[i] = *reinterpret_cast<uint32_t*>(&h);
   }
   *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+__device__ __forceinline__ F8 ld8(const __half* p) {
+  const uint4 raw = *reinterpret_cast<const uint4*>(p);
+  const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+  F8 f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 t = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+    f.v[2 * i] = t.x, f.v[2 * i + 1] = t.y;
+  }
+  return f;
+}
+__device__ __forceinline__ void st8(__half* p, const F8& f) {
+  uint32_t w[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    __half2 h = __floats2half2_rn(f.v[2 * i], f.v[2 * i + 1]);
+    w[i] = *reinterpret_cast<uint32_t*>(&h);
+  }
+  *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+}
+// two floats <-> one 32-bit word of 16-bit storage; `half` selects fp16 (true) or bf16 (false)
+__device__ __forceinline__ uint32_t pack16(float lo, float hi, bool half) {
+  if (half) {
+    // saturate instead of producing inf: fp16 tops out at 65504
+    __half2 h = __floats2half2_rn(fminf(fmaxf(lo, -65504.f), 65504.f),
+                                  fminf(fmaxf(hi, -65504.f), 65504.f));
+    return *reinterpret_cast<uint32_t*>(&h);
+  }
+  __nv_bfloat162 b = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&b);
+}
+__device__ __forceinline__ float2 unpack16(uint32_t w, bool half) {
+  if (half) return __half22float2(*reinterpret_cast<const __half2*>(&w));
+  return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xFFFF0000u));
 }
 
 // ---- deterministic grid reductions ----------------------------------------------------------------

@@ -107,23 +107,20 @@ __device__ __forceinline__ bool elect_one() {
       : "=r"(pred));
   return pred != 0;
 }
-__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
-  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
-  return *reinterpret_cast<uint32_t*>(&h);
-}
 
-// c_format f32 | a,b bf16 | K-major | N = 64 | M = 128
-constexpr uint32_t kFirstIdesc = (1u << 4) | (1u << 7) | (1u << 10) |
-                                 ((uint32_t)(kFirstCout >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+// c_format f32 | K-major | N = 64 | M = 128; operand formats (bits 7, 10: 0 = f16, 1 = bf16) at run time
+constexpr uint32_t kFirstIdescBase = (1u << 4) | ((uint32_t)(kFirstCout >> 3) << 17) |
+                                     ((uint32_t)(128 >> 4) << 24);
 
 struct FirstArgs {
   ImageBatch img;
   int h, w;                         // tile size
   int tiles_x;                      // ceil(w / 128)
   int num_tiles;                    // nb * h * tiles_x
-  const __nv_bfloat16* wk;          // [64][64] K-major, k = tap*3 + ci for the hi half, 27 + that for lo
+  const void* wk;                   // [64][64] K-major, k = tap*3 + ci for the hi half, 27 + that for lo
   const float* bias;
-  __nv_bfloat16* out;               // [nb][h][w][64]
+  void* out;                        // [nb][h][w][64], bf16 or fp16 (half)
+  int half;                         // operands and output are fp16
 };
 
 __global__ void __launch_bounds__(kFirstThreads)
@@ -140,7 +137,7 @@ conv_first_tc_kernel(const FirstArgs a) {
   for (int i = tid; i < 64 * 8; i += kFirstThreads) {
     const int n = i >> 3, j = i & 7;
     *reinterpret_cast<uint4*>(b_s + n * 128 + ((j ^ (n & 7)) << 4)) =
-        *reinterpret_cast<const uint4*>(a.wk + n * 64 + j * 8);
+        *reinterpret_cast<const uint4*>(static_cast<const uint8_t*>(a.wk) + n * 128 + j * 16);
   }
   if (tid == 0) {
     mbar_init(&bar, 1);
@@ -153,6 +150,9 @@ conv_first_tc_kernel(const FirstArgs a) {
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
   const uint64_t db = make_smem_desc(smem_u32(b_s)), da = make_smem_desc(smem_u32(a_s));
+  const bool half = a.half != 0;
+  const uint32_t fmt = half ? 0u : 1u;
+  const uint32_t idesc = kFirstIdescBase | (fmt << 7) | (fmt << 10);
   const float* base = a.img.base;
   const size_t plane = (size_t)a.img.H * a.img.W;
   uint32_t phase = 0;
@@ -185,21 +185,21 @@ conv_first_tc_kernel(const FirstArgs a) {
     // Pixels span +-150 grey levels: one bf16 (8 significant bits) would quantise them to 0.5-1
     // level.  Each value enters as hi + lo (lo = bf16(v - hi)), the weights are repeated for the lo
     // half: K = 54 of the 64 padded columns, ~16 significant bits, no extra MMA.
-    uint32_t kv[32];                       // 64 bf16: k in [0,27) hi, [27,54) lo, rest zero
+    uint32_t kv[32];                       // 64 x 16 bit: k in [0,27) hi, [27,54) lo, rest zero
     {
-      __nv_bfloat16 e[64];
-#pragma unroll
-      for (int k = 0; k < 64; ++k) e[k] = __float2bfloat16_rn(0.f);
+      float hi[27], lo[27];
 #pragma unroll
       for (int k = 0; k < 27; ++k) {
-        const __nv_bfloat16 hi = __float2bfloat16_rn(v[k]);
-        e[k] = hi;
-        e[27 + k] = __float2bfloat16_rn(v[k] - __bfloat162float(hi));
+        hi[k] = half ? __half2float(__float2half_rn(v[k])) : __bfloat162float(__float2bfloat16_rn(v[k]));
+        lo[k] = v[k] - hi[k];
       }
 #pragma unroll
-      for (int k = 0; k < 32; ++k)
-        kv[k] = (uint32_t)__bfloat16_as_ushort(e[2 * k]) |
-                ((uint32_t)__bfloat16_as_ushort(e[2 * k + 1]) << 16);
+      for (int k = 0; k < 32; ++k) {
+        const int k0 = 2 * k, k1 = 2 * k + 1;
+        const float x0 = k0 < 27 ? hi[k0] : (k0 < 54 ? lo[k0 - 27] : 0.f);
+        const float x1 = k1 < 27 ? hi[k1] : (k1 < 54 ? lo[k1 - 27] : 0.f);
+        kv[k] = pack16(x0, x1, half);
+      }
     }
     uint8_t* row = a_s + tid * 128;
 #pragma unroll
@@ -215,7 +215,7 @@ conv_first_tc_kernel(const FirstArgs a) {
       if (elect_one()) {
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          tc_mma(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), kFirstIdesc, k != 0);
+          tc_mma(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, k != 0);
         tc_commit(&bar);
       }
       __syncwarp();
@@ -236,8 +236,8 @@ conv_first_tc_kernel(const FirstArgs a) {
         for (int i = 0; i < 8; ++i)
           f[i] = fmaxf(__uint_as_float(r[8 * j + i]) + bias_s[cc * 32 + 8 * j + i], 0.f);
         uint4 pk;
-        pk.x = pack_bf16(f[0], f[1]), pk.y = pack_bf16(f[2], f[3]);
-        pk.z = pack_bf16(f[4], f[5]), pk.w = pack_bf16(f[6], f[7]);
+        pk.x = pack16(f[0], f[1], half), pk.y = pack16(f[2], f[3], half);
+        pk.z = pack16(f[4], f[5], half), pk.w = pack16(f[6], f[7], half);
         *reinterpret_cast<uint4*>(row + (((cc * 4 + j) ^ (tid & 7)) << 4)) = pk;
       }
     }
@@ -247,8 +247,8 @@ conv_first_tc_kernel(const FirstArgs a) {
     // is chunk (g & 7) of row (g >> 3)
     {
       const int valid_rows = min(128, a.w - tx * 128);
-      uint4* dst = reinterpret_cast<uint4*>(a.out + (((size_t)b * a.h + y) * a.w + tx * 128) *
-                                                        kFirstCout);
+      uint4* dst = reinterpret_cast<uint4*>(static_cast<uint8_t*>(a.out) +
+                                            (((size_t)b * a.h + y) * a.w + tx * 128) * kFirstCout * 2);
 #pragma unroll
       for (int it = 0; it < 8; ++it) {
         const int g = it * kFirstThreads + tid, r = g >> 3, j = g & 7;
@@ -264,23 +264,33 @@ conv_first_tc_kernel(const FirstArgs a) {
 
 }  // namespace
 
-int tc_pack_first_fwd(TcContext& tc, TcWeights& w, const float* w_host, int cout) {
+int tc_pack_first_fwd(TcContext& tc, TcWeights& w, const float* w_host, int cout, bool half) {
   if (!tc.enabled || !tc.pair_kernel || cout != kFirstCout) return ST_OK;
-  std::vector<__nv_bfloat16> host((size_t)64 * 64, __float2bfloat16_rn(0.f));
+  std::vector<uint16_t> host((size_t)64 * 64, 0);
   for (int co = 0; co < cout; ++co)
     for (int ci = 0; ci < 3; ++ci)
-      for (int tap = 0; tap < 9; ++tap)
-        host[(size_t)co * 64 + tap * 3 + ci] = host[(size_t)co * 64 + 27 + tap * 3 + ci] =
-            __float2bfloat16_rn(w_host[((size_t)co * 3 + ci) * 9 + tap]);
-  if (!w.fwd) ST_CUDA(cudaMalloc((void**)&w.fwd, host.size() * sizeof(__nv_bfloat16)));
-  ST_CUDA(cudaMemcpy(w.fwd, host.data(), host.size() * sizeof(__nv_bfloat16),
-                     cudaMemcpyHostToDevice));
+      for (int tap = 0; tap < 9; ++tap) {
+        const float v = w_host[((size_t)co * 3 + ci) * 9 + tap];
+        uint16_t bits;
+        if (half) {
+          const __half h = __float2half_rn(v);
+          bits = *reinterpret_cast<const uint16_t*>(&h);
+        } else {
+          const __nv_bfloat16 h = __float2bfloat16_rn(v);
+          bits = *reinterpret_cast<const uint16_t*>(&h);
+        }
+        host[(size_t)co * 64 + tap * 3 + ci] = host[(size_t)co * 64 + 27 + tap * 3 + ci] = bits;
+      }
+  if (!w.fwd) ST_CUDA(cudaMalloc(&w.fwd, host.size() * 2));
+  ST_CUDA(cudaMemcpy(w.fwd, host.data(), host.size() * 2, cudaMemcpyHostToDevice));
+  w.fwd_half = half;
   return ST_OK;
 }
 
 int conv_first_fwd_tc(TcContext& tc, const TcWeights& w, const ImageBatch& img, int h, int wd,
-                      const float* bias, __nv_bfloat16* out, cudaStream_t s) {
+                      const float* bias, void* out, cudaStream_t s) {
   FirstArgs a{};
+  a.half = w.fwd_half ? 1 : 0;
   a.img = img, a.h = h, a.w = wd, a.tiles_x = cdiv(wd, 128);
   a.num_tiles = img.nb * h * a.tiles_x;
   a.wk = w.fwd, a.bias = bias, a.out = out;

@@ -19,6 +19,7 @@
 // The element type T is __nv_bfloat16 (kind::f16, K=16 per MMA) or float (kind::tf32, K=8 per
 // MMA); everything is expressed in 128-byte K chunks so both share the code.
 #include <cuda.h>
+#include <cuda_fp16.h>
 
 #include <cstdlib>
 #include <vector>
@@ -494,9 +495,26 @@ int tc_init(TcContext& tc, int sm_count) {
 
 void tc_destroy(TcContext& tc) { tc.enabled = false; }
 
-int tc_pack_weights(TcContext& tc, TcWeights& w, const float* w_host, int cin, int cout) {
+int tc_pack_weights(TcContext& tc, TcWeights& w, const float* w_host, int cin, int cout,
+                    bool fwd_half) {
   if (!tc.enabled) return ST_OK;
-  int rc = pack_one<__nv_bfloat16>(tc, w_host, cin, cout, false, &w.fwd, &w.map_fwd);
+  w.fwd_half = fwd_half;
+  int rc;
+  if (fwd_half) {
+    // forward weights as fp16 [cout][9*cin] (the pair kernel builds its own tensor maps)
+    std::vector<__half> host((size_t)cout * 9 * cin);
+    for (int co = 0; co < cout; ++co)
+      for (int ci = 0; ci < cin; ++ci)
+        for (int t = 0; t < 9; ++t)
+          host[(size_t)co * 9 * cin + (size_t)t * cin + ci] =
+              __float2half_rn(w_host[((size_t)co * cin + ci) * 9 + t]);
+    if (!w.fwd) ST_CUDA(cudaMalloc(&w.fwd, host.size() * sizeof(__half)));
+    ST_CUDA(cudaMemcpy(w.fwd, host.data(), host.size() * sizeof(__half), cudaMemcpyHostToDevice));
+    rc = ST_OK;
+  } else {
+    rc = pack_one<__nv_bfloat16>(tc, w_host, cin, cout, false,
+                                 reinterpret_cast<__nv_bfloat16**>(&w.fwd), &w.map_fwd);
+  }
   if (rc == ST_OK) rc = pack_one<__nv_bfloat16>(tc, w_host, cin, cout, true, &w.bwd, &w.map_bwd);
   return rc;
 }
@@ -528,15 +546,17 @@ bool tc_shape_ok(const TcContext& tc, const TcWeights& w, int cin, int cout) {
   return tc.enabled && w.fwd != nullptr && cin % 64 == 0 && cout % 64 == 0;
 }
 
-int conv3x3_tc(TcContext& tc, const TcWeights& w, const __nv_bfloat16* in, __nv_bfloat16* out,
-               int nb, int h, int wd, int cin, int cout, bool forward, const float* bias,
-               const __nv_bfloat16* mask_act, const __nv_bfloat16* inj, const float* inj_scale,
-               cudaStream_t s) {
+int conv3x3_tc(TcContext& tc, const TcWeights& w, const void* in_v, void* out_v, int nb, int h,
+               int wd, int cin, int cout, bool forward, const float* bias, const void* mask_v,
+               const __nv_bfloat16* inj, const float* inj_scale, cudaStream_t s) {
   if (tc.pair_kernel)
-    return conv3x3_tc_pair(tc, w, in, out, nb, h, wd, cin, cout, forward, bias, mask_act, inj,
+    return conv3x3_tc_pair(tc, w, in_v, out_v, nb, h, wd, cin, cout, forward, bias, mask_v, inj,
                            inj_scale, s);
-  ST_REQUIRE(nb == 1 && inj_scale == nullptr,
-             "the single-CTA convolution kernel (ST_CONV_V1) takes one tile and a pre-scaled injection");
+  ST_REQUIRE(nb == 1 && inj_scale == nullptr && !w.fwd_half,
+             "the single-CTA convolution kernel (ST_CONV_V1) takes one bf16 tile and a pre-scaled injection");
+  const __nv_bfloat16* in = static_cast<const __nv_bfloat16*>(in_v);
+  __nv_bfloat16* out = static_cast<__nv_bfloat16*>(out_v);
+  const __nv_bfloat16* mask_act = static_cast<const __nv_bfloat16*>(mask_v);
   TcArgs a{};
   a.h = h, a.w = wd, a.cin = cin, a.cout = cout, a.forward = forward ? 1 : 0;
   a.bias = bias, a.mask_act = mask_act, a.inj = inj;

@@ -2,6 +2,7 @@
 #pragma once
 
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -13,8 +14,9 @@ namespace st {
 //   fwd [cout][9*cin]  : B operand of  out[p][co] = sum_k A[p][k] * Wf[co][k],  k = tap*cin + ci
 //   bwd [cin][9*cout]  : same GEMM with flipped taps and in/out channels exchanged
 struct TcWeights {
-  __nv_bfloat16* fwd = nullptr;
-  __nv_bfloat16* bwd = nullptr;
+  void* fwd = nullptr;             // 16-bit: bf16, or fp16 when fwd_half (ST_PREC_FP16)
+  __nv_bfloat16* bwd = nullptr;    // always bf16: the backward pass runs on bf16 gradients
+  bool fwd_half = false;
   void* map_fwd = nullptr;     // host copies of the CUtensorMap descriptors (128 B each)
   void* map_bwd = nullptr;
 };
@@ -28,7 +30,8 @@ struct TcContext {
 
 int tc_init(TcContext& tc, int sm_count);
 void tc_destroy(TcContext& tc);
-int tc_pack_weights(TcContext& tc, TcWeights& w, const float* w_oihw_host, int cin, int cout);
+int tc_pack_weights(TcContext& tc, TcWeights& w, const float* w_oihw_host, int cin, int cout,
+                    bool fwd_half);
 // First layer (cin = 3): only the backward pack, [16][9*cout] with rows 3..15 zero.
 int tc_pack_first(TcContext& tc, TcWeights& w, const float* w_oihw_host, int cout);
 void tc_free_weights(TcWeights& w);
@@ -37,31 +40,29 @@ bool tc_shape_ok(const TcContext& tc, const TcWeights& w, int cin, int cout);
 
 template <typename T>
 inline bool tc_usable(const TcContext& tc, const TcWeights& w, int cin, int cout) {
-  if constexpr (std::is_same<T, __nv_bfloat16>::value) return tc_shape_ok(tc, w, cin, cout);
+  if constexpr (sizeof(T) == 2) return tc_shape_ok(tc, w, cin, cout);
   return false;
 }
 
-// out = epilogue(conv3x3(in)) with in [nb][h][w][cin], out [nb][h][w][cout] (bf16 NHWC).
-//   forward : out = max(acc + bias, 0)
-//   backward: out = (mask_act > 0 ? acc : 0) + inj_scale[tile] * inj   (each may be null)
-int conv3x3_tc(TcContext& tc, const TcWeights& w, const __nv_bfloat16* in, __nv_bfloat16* out,
-               int nb, int h, int wd, int cin, int cout, bool forward, const float* bias,
-               const __nv_bfloat16* mask_act, const __nv_bfloat16* inj, const float* inj_scale,
-               cudaStream_t s);
+// out = epilogue(conv3x3(in)) with in [nb][h][w][cin], out [nb][h][w][cout] (16-bit NHWC).
+//   forward : out = max(acc + bias, 0); operands/outputs are fp16 when w.fwd_half, else bf16
+//   backward: out = (mask_act > 0 ? acc : 0) + inj_scale[tile] * inj   (each may be null); gradients
+//             and backward weights are bf16, mask_act is the forward activation (either format)
+int conv3x3_tc(TcContext& tc, const TcWeights& w, const void* in, void* out, int nb, int h, int wd,
+               int cin, int cout, bool forward, const float* bias, const void* mask_act,
+               const __nv_bfloat16* inj, const float* inj_scale, cudaStream_t s);
 // CTA-pair (cta_group::2) kernel of conv_tc2.cu; activations are [nb][h][w][c] (a batch of tiles).
-int conv3x3_tc_pair(TcContext& tc, const TcWeights& w, const __nv_bfloat16* in, __nv_bfloat16* out,
-                    int nb, int h, int wd, int cin, int cout, bool forward, const float* bias,
-                    const __nv_bfloat16* mask_act, const __nv_bfloat16* inj, const float* inj_scale,
-                    cudaStream_t s);
+int conv3x3_tc_pair(TcContext& tc, const TcWeights& w, const void* in, void* out, int nb, int h,
+                    int wd, int cin, int cout, bool forward, const float* bias, const void* mask_act,
+                    const __nv_bfloat16* inj, const float* inj_scale, cudaStream_t s);
 // Forward convolution + the 2x2/2 pooling layer behind it in one kernel.  pool_out [nb][ho][wo][cout]
 // receives the pooled map, pool_mask (bytes, same shape) what pool_bwd_mask needs:
 //   max: bits 0-1 = window position of the first maximum, bit 2 = maximum > 0
 //   ave: bit d    = window input d > 0
 // `out` is written only when write_full.
-int conv3x3_pool_tc_pair(TcContext& tc, const TcWeights& w, const __nv_bfloat16* in,
-                         __nv_bfloat16* out, __nv_bfloat16* pool_out, uint8_t* pool_mask, int nb, int h,
-                         int wd, int cin, int cout, const float* bias, bool is_max, bool write_full,
-                         cudaStream_t s);
+int conv3x3_pool_tc_pair(TcContext& tc, const TcWeights& w, const void* in, void* out,
+                         void* pool_out, uint8_t* pool_mask, int nb, int h, int wd, int cin, int cout,
+                         const float* bias, bool is_max, bool write_full, cudaStream_t s);
 // Backward of the first (3-channel) convolution on tensor cores: dz [nb][h][w][cz] bf16 -> planar f32
 // gradient; tile b goes to grad + b * batch_stride.  Needs weights packed by tc_pack_first.
 int conv_last_bwd_tc_pair(TcContext& tc, const TcWeights& w, const __nv_bfloat16* dz, int nb, int h,
@@ -69,27 +70,25 @@ int conv_last_bwd_tc_pair(TcContext& tc, const TcWeights& w, const __nv_bfloat16
                           long row_stride, cudaStream_t s);
 // First convolution (3 -> 64 channels) on tensor cores from the planar f32 image (conv_first_tc.cu).
 struct ImageBatch;
-int tc_pack_first_fwd(TcContext& tc, TcWeights& w, const float* w_oihw_host, int cout);
+int tc_pack_first_fwd(TcContext& tc, TcWeights& w, const float* w_oihw_host, int cout, bool half);
 int conv_first_fwd_tc(TcContext& tc, const TcWeights& w, const ImageBatch& img, int h, int wd,
-                      const float* bias, __nv_bfloat16* out, cudaStream_t s);
-// Per batch tile b: S_b[p][n] = sum_c F_b[p][c] * D_b[n][c] for F [nb][h][w][c] and D [nb][c][c]
-// (bf16).  sum |S_b| is left as partial sums abs_partials[b * per_tile + i], i < *per_tile, to be
-// added in index order; the buffer must hold gemm_abs_partials_needed() doubles.
-int gemm_abs_tc_pair(TcContext& tc, const __nv_bfloat16* f, const __nv_bfloat16* d,
-                     __nv_bfloat16* s_out, int nb, int h, int w, int c, double* abs_partials,
-                     int* per_tile, cudaStream_t s);
+                      const float* bias, void* out, cudaStream_t s);
+// Per batch tile b: S_b[p][n] = sum_c F_b[p][c] * D_b[n][c] for F [nb][h][w][c] and D [nb][c][c],
+// both bf16 or both fp16 (half_in); S is written as bf16.  sum |S_b| is left as partial sums
+// abs_partials[b * per_tile + i], i < *per_tile, to be added in index order; the buffer must hold
+// gemm_abs_partials_needed() doubles.
+int gemm_abs_tc_pair(TcContext& tc, const void* f, const void* d, bool half_in, __nv_bfloat16* s_out,
+                     int nb, int h, int w, int c, double* abs_partials, int* per_tile,
+                     cudaStream_t s);
 size_t gemm_abs_partials_needed(int nb, int h, int w, int c);
 
 // gram[b][C][C] (full, symmetric, fp32) = F_b^T F_b / (C*hw) for bf16 NHWC F [nb][hw][c] on tcgen05
 // (gram_tc.cu).  part: split-K scratch of gram_tc_part_floats() floats.
 bool gram_tc_ok(const TcContext& tc, int c);
 size_t gram_tc_part_floats(const TcContext& tc, int nb, int hw, int c);
-int gram_tc(TcContext& tc, const __nv_bfloat16* f, int nb, int hw, int c, float* gram, float* part,
+int gram_tc(TcContext& tc, const void* f, bool half, int nb, int hw, int c, float* gram, float* part,
             cudaStream_t s);
 
-inline int conv3x3_tc(TcContext&, const TcWeights&, const float*, float*, int, int, int, int, int,
-                      bool, const float*, const float*, const float*, const float*, cudaStream_t) {
-  return -1;   // never reached: tc_usable<float> is false
-}
+
 
 }  // namespace st

@@ -218,6 +218,7 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
 
 struct Tc2Args {
   int nb, h, w, cin, cout;         // nb tiles of the batch, each [h][w]
+  int in_half, out_half;           // operands (A and B) / stored output are fp16 instead of bf16
   int w_batched;                   // the B operand has one matrix per batch tile (style GEMM)
   int resb_bytes;                  // RESB: bytes of the resident weight block (multiple of 1024)
   int tiles_x, tiles_y, tiles_n;   // pair tiles per batch tile: 8 columns x 32 rows x BN channels
@@ -266,8 +267,9 @@ struct Cfg2 {
   static constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;    // double-buffered accumulator
   static constexpr int kFixedBytes = kSA * kABytes + kOutBytes + 1024 + kTailBytes;
   static constexpr int kSmemBytes = kFixedBytes + kSB * kBBytes;           // staged-B variant
-  static constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) |
-                                     ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+  // instruction descriptor without the operand formats (0 = f16, 1 = bf16 at bits 7 and 10)
+  static constexpr uint32_t kIdescBase = (1u << 4) | ((uint32_t)(BN >> 3) << 17) |
+                                         ((uint32_t)(256 >> 4) << 24);
   static_assert(RESB || kSB >= 3, "not enough shared memory for the weight pipeline");
 };
 
@@ -384,6 +386,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constan
     if (leader) {
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0, it = 0;
+      const uint32_t fmt = a.in_half ? 0u : 1u;
+      const uint32_t idesc = Cfg::kIdescBase | (fmt << 7) | (fmt << 10);
       if constexpr (RESB) mbar_wait(&b_full[0], 0);      // the resident weights have landed
       for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
         const uint32_t buf = it & 1, use = it >> 1;
@@ -405,7 +409,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constan
             if (elect_one()) {
 #pragma unroll
               for (int k = 0; k < 4; ++k)
-                tc_mma_pair(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), Cfg::kIdesc,
+                tc_mma_pair(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc,
                             (cb | tap | k) != 0);
               if constexpr (!RESB) tc_commit_pair(&b_empty[sb]);
               if (tap == TAPS - 1) {
@@ -425,6 +429,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constan
     const int q = warp & 3;                            // TMEM lane quadrant of this warp
     const int m = q * 32 + lane;                       // pixel row of the CTA tile
     const bool issuer = threadIdx.x == 64;
+    const bool out_half = a.out_half != 0;
     uint32_t it = 0, store_seq = 0;
     for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
       const uint32_t buf = it & 1, use = it >> 1;
@@ -533,13 +538,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constan
           uint8_t* row = stage_out + (size_t)m * 128;
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            __nv_bfloat162 p0 = __floats2bfloat162_rn(v[8 * j], v[8 * j + 1]);
-            __nv_bfloat162 p1 = __floats2bfloat162_rn(v[8 * j + 2], v[8 * j + 3]);
-            __nv_bfloat162 p2 = __floats2bfloat162_rn(v[8 * j + 4], v[8 * j + 5]);
-            __nv_bfloat162 p3 = __floats2bfloat162_rn(v[8 * j + 6], v[8 * j + 7]);
             uint4 pk;
-            pk.x = *reinterpret_cast<uint32_t*>(&p0), pk.y = *reinterpret_cast<uint32_t*>(&p1);
-            pk.z = *reinterpret_cast<uint32_t*>(&p2), pk.w = *reinterpret_cast<uint32_t*>(&p3);
+            pk.x = pack16(v[8 * j], v[8 * j + 1], out_half), pk.y = pack16(v[8 * j + 2], v[8 * j + 3], out_half);
+            pk.z = pack16(v[8 * j + 4], v[8 * j + 5], out_half), pk.w = pack16(v[8 * j + 6], v[8 * j + 7], out_half);
             const int chunk = hh * 4 + j;
             *reinterpret_cast<uint4*>(row + ((chunk ^ (m & 7)) << 4)) = pk;
           }
@@ -581,7 +582,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constan
               const uint32_t w4[4] = {raw.x, raw.y, raw.z, raw.w};
 #pragma unroll
               for (int e = 0; e < 8; ++e) {
-                const float x = __uint_as_float((e & 1) ? (w4[e >> 1] & 0xFFFF0000u) : (w4[e >> 1] << 16));
+                const float2 x2 = unpack16(w4[e >> 1], out_half);
+                const float x = (e & 1) ? x2.y : x2.x;
                 if (a.pool_mode == 1) {
                   if (x > best[e]) best[e] = x, code[e] = (uint32_t)d;       // strict: first max wins
                 } else {
@@ -603,8 +605,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constan
                 const float inv = (float)(cnt > 0 ? cnt : 1);
                 o0 = sum[e] / inv, o1 = sum[e + 1] / inv;
               }
-              __nv_bfloat162 h2 = __floats2bfloat162_rn(o0, o1);
-              ow[e >> 1] = *reinterpret_cast<uint32_t*>(&h2);
+              ow[e >> 1] = pack16(o0, o1, out_half);
             }
 #pragma unroll
             for (int e = 0; e < 8; ++e) mk[e >> 2] |= code[e] << (8 * (e & 3));
@@ -644,13 +645,15 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 int encode_bf16_map(const TcContext& tc, CUtensorMap* map, int rank, const void* base,
-                    const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box) {
+                    const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box,
+                    bool half = false) {
   cuuint64_t gdim[4], gstride[3];
   cuuint32_t bdim[4], estride[4] = {1, 1, 1, 1};
   for (int i = 0; i < rank; ++i) gdim[i] = dims[i], bdim[i] = box[i];
   for (int i = 0; i + 1 < rank; ++i) gstride[i] = strides_bytes[i];
   CUresult r = reinterpret_cast<EncodeTiledFn>(tc.encode_fn)(
-      map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), gdim, gstride, bdim,
+      map, half ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank,
+      const_cast<void*>(base), gdim, gstride, bdim,
       estride, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
       CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -661,8 +664,8 @@ int encode_bf16_map(const TcContext& tc, CUtensorMap* map, int rank, const void*
 }
 
 template <int BN, int TAPS, int EPI, bool RESB>
-int launch2r(TcContext& tc, const __nv_bfloat16* in, const __nv_bfloat16* wk, int wk_rows,
-             __nv_bfloat16* out, __nv_bfloat16* pool_out, Tc2Args a, cudaStream_t s) {
+int launch2r(TcContext& tc, const void* in, const void* wk, int wk_rows,
+             void* out, void* pool_out, Tc2Args a, cudaStream_t s) {
   using Cfg = Cfg2<BN, TAPS, RESB, EPI == kEpiFwdPool>;
   a.tiles_x = cdiv(a.w, kBW), a.tiles_y = cdiv(a.h, 2 * kBH), a.tiles_n = a.cout / BN;
   CUtensorMap map_in, map_out, map_w, map_pool;
@@ -671,7 +674,7 @@ int launch2r(TcContext& tc, const __nv_bfloat16* in, const __nv_bfloat16* wk, in
     const uint64_t strides[3] = {(uint64_t)a.cin * 2, (uint64_t)a.w * a.cin * 2,
                                  (uint64_t)a.h * a.w * a.cin * 2};
     const uint32_t box[4] = {64, (uint32_t)kBW, (uint32_t)Cfg::kHaloRows, 1};
-    int rc = encode_bf16_map(tc, &map_in, 4, in, dims, strides, box);
+    int rc = encode_bf16_map(tc, &map_in, 4, in, dims, strides, box, a.in_half != 0);
     if (rc != ST_OK) return rc;
   }
   if (EPI != kEpiPix) {
@@ -679,7 +682,7 @@ int launch2r(TcContext& tc, const __nv_bfloat16* in, const __nv_bfloat16* wk, in
     const uint64_t strides[3] = {(uint64_t)a.cout * 2, (uint64_t)a.w * a.cout * 2,
                                  (uint64_t)a.h * a.w * a.cout * 2};
     const uint32_t box[4] = {64, (uint32_t)kBW, (uint32_t)kBH, 1};
-    int rc = encode_bf16_map(tc, &map_out, 4, out, dims, strides, box);
+    int rc = encode_bf16_map(tc, &map_out, 4, out, dims, strides, box, a.out_half != 0);
     if (rc != ST_OK) return rc;
   } else {
     map_out = map_in;            // never dereferenced by the pixel epilogue
@@ -690,7 +693,7 @@ int launch2r(TcContext& tc, const __nv_bfloat16* in, const __nv_bfloat16* wk, in
     const uint64_t dims[4] = {(uint64_t)a.cout, wo, ho, (uint64_t)a.nb};
     const uint64_t strides[3] = {(uint64_t)a.cout * 2, wo * a.cout * 2, ho * wo * a.cout * 2};
     const uint32_t box[4] = {64, (uint32_t)(kBW / 2), (uint32_t)(kBH / 2), 1};
-    int rc = encode_bf16_map(tc, &map_pool, 4, pool_out, dims, strides, box);
+    int rc = encode_bf16_map(tc, &map_pool, 4, pool_out, dims, strides, box, a.out_half != 0);
     if (rc != ST_OK) return rc;
   }
   {
@@ -698,7 +701,7 @@ int launch2r(TcContext& tc, const __nv_bfloat16* in, const __nv_bfloat16* wk, in
     const uint64_t dims[3] = {k, (uint64_t)wk_rows, (uint64_t)(a.w_batched ? a.nb : 1)};
     const uint64_t strides[2] = {k * 2, k * 2 * wk_rows};
     const uint32_t box[3] = {64, (uint32_t)(BN / 2), 1};
-    int rc = encode_bf16_map(tc, &map_w, 3, wk, dims, strides, box);
+    int rc = encode_bf16_map(tc, &map_w, 3, wk, dims, strides, box, a.in_half != 0);
     if (rc != ST_OK) return rc;
   }
   auto kern = conv_tc2_kernel<BN, TAPS, EPI, RESB>;
@@ -722,8 +725,8 @@ int launch2r(TcContext& tc, const __nv_bfloat16* in, const __nv_bfloat16* wk, in
 // Resident weights when one output-channel tile covers the layer, the weights are shared by the
 // batch and this CTA's share of them fits beside the A stages.
 template <int BN, int TAPS, int EPI>
-int launch2(TcContext& tc, const __nv_bfloat16* in, const __nv_bfloat16* wk, int wk_rows,
-            __nv_bfloat16* out, const Tc2Args& a, cudaStream_t s, __nv_bfloat16* pool_out = nullptr) {
+int launch2(TcContext& tc, const void* in, const void* wk, int wk_rows, void* out, const Tc2Args& a,
+            cudaStream_t s, void* pool_out = nullptr) {
   if constexpr (BN <= 128) {
     using CfgR = Cfg2<BN, TAPS, true, EPI == kEpiFwdPool>;
     const long res = (long)TAPS * (a.cin / 64) * CfgR::kBBytes;
@@ -750,9 +753,8 @@ int choose_bn(const TcContext& tc, int nb, int h, int w, int cout) {
 }
 
 template <int TAPS, int EPI>
-int dispatch_bn(TcContext& tc, int bn, const __nv_bfloat16* in, const __nv_bfloat16* wk, int wk_rows,
-                __nv_bfloat16* out, const Tc2Args& a, cudaStream_t s,
-                __nv_bfloat16* pool_out = nullptr) {
+int dispatch_bn(TcContext& tc, int bn, const void* in, const void* wk, int wk_rows, void* out,
+                const Tc2Args& a, cudaStream_t s, void* pool_out = nullptr) {
   switch (bn) {
     case 256: return launch2<256, TAPS, EPI>(tc, in, wk, wk_rows, out, a, s, pool_out);
     case 128: return launch2<128, TAPS, EPI>(tc, in, wk, wk_rows, out, a, s, pool_out);
@@ -762,13 +764,15 @@ int dispatch_bn(TcContext& tc, int bn, const __nv_bfloat16* in, const __nv_bfloa
 
 }  // namespace
 
-int conv3x3_tc_pair(TcContext& tc, const TcWeights& w, const __nv_bfloat16* in, __nv_bfloat16* out,
-                    int nb, int h, int wd, int cin, int cout, bool forward, const float* bias,
-                    const __nv_bfloat16* mask_act, const __nv_bfloat16* inj, const float* inj_scale,
-                    cudaStream_t s) {
+int conv3x3_tc_pair(TcContext& tc, const TcWeights& w, const void* in, void* out, int nb, int h,
+                    int wd, int cin, int cout, bool forward, const float* bias, const void* mask_act,
+                    const __nv_bfloat16* inj, const float* inj_scale, cudaStream_t s) {
   Tc2Args a{};
   a.nb = nb, a.h = h, a.w = wd, a.cin = cin, a.cout = cout;
-  a.bias = bias, a.mask_act = mask_act, a.inj = inj, a.inj_scale = inj_scale;
+  // forward: activations in the context's activation format; backward: gradients are always bf16
+  a.in_half = a.out_half = (forward && w.fwd_half) ? 1 : 0;
+  a.bias = bias, a.mask_act = static_cast<const __nv_bfloat16*>(mask_act), a.inj = inj,
+  a.inj_scale = inj_scale;
   const int bn = choose_bn(tc, nb, h, wd, cout);
   if (forward) return dispatch_bn<9, kEpiFwd>(tc, bn, in, w.fwd, cout, out, a, s);
   return dispatch_bn<9, kEpiBwd>(tc, bn, in, w.bwd, cout, out, a, s);
@@ -776,12 +780,12 @@ int conv3x3_tc_pair(TcContext& tc, const TcWeights& w, const __nv_bfloat16* in, 
 
 // Forward convolution fused with the 2x2/2 pooling layer that consumes it: writes the pooled map,
 // the backward mask and (write_full) the un-pooled output.
-int conv3x3_pool_tc_pair(TcContext& tc, const TcWeights& w, const __nv_bfloat16* in,
-                         __nv_bfloat16* out, __nv_bfloat16* pool_out, uint8_t* pool_mask, int nb, int h,
-                         int wd, int cin, int cout, const float* bias, bool is_max, bool write_full,
-                         cudaStream_t s) {
+int conv3x3_pool_tc_pair(TcContext& tc, const TcWeights& w, const void* in, void* out,
+                         void* pool_out, uint8_t* pool_mask, int nb, int h, int wd, int cin, int cout,
+                         const float* bias, bool is_max, bool write_full, cudaStream_t s) {
   Tc2Args a{};
   a.nb = nb, a.h = h, a.w = wd, a.cin = cin, a.cout = cout, a.bias = bias;
+  a.in_half = a.out_half = w.fwd_half ? 1 : 0;
   a.pool_mode = is_max ? 1 : 2, a.write_full = write_full ? 1 : 0, a.pool_mask = pool_mask;
   const int bn = choose_bn(tc, nb, h, wd, cout);
   return dispatch_bn<9, kEpiFwdPool>(tc, bn, in, w.fwd, cout, out, a, s, pool_out);
@@ -800,11 +804,12 @@ int conv_last_bwd_tc_pair(TcContext& tc, const TcWeights& w, const __nv_bfloat16
 
 // Per batch tile b: S_b[p][n] = sum_c F_b[p][c] * D_b[n][c]  (D_b symmetric bf16 [c][c]).  The sum
 // of |S_b| is left as partial sums: abs_partials[b * per_tile + i], i < *per_tile.
-int gemm_abs_tc_pair(TcContext& tc, const __nv_bfloat16* f, const __nv_bfloat16* d,
-                     __nv_bfloat16* s_out, int nb, int h, int w, int c, double* abs_partials,
-                     int* per_tile, cudaStream_t s) {
+int gemm_abs_tc_pair(TcContext& tc, const void* f, const void* d, bool half_in, __nv_bfloat16* s_out,
+                     int nb, int h, int w, int c, double* abs_partials, int* per_tile,
+                     cudaStream_t s) {
   Tc2Args a{};
   a.nb = nb, a.h = h, a.w = w, a.cin = c, a.cout = c, a.w_batched = 1;
+  a.in_half = half_in ? 1 : 0, a.out_half = 0;          // S is a gradient: bf16
   a.abs_partials = abs_partials;
   const int bn = choose_bn(tc, nb, h, w, c);
   *per_tile = cdiv(w, kBW) * cdiv(h, 2 * kBH) * (c / 64) * 8;

@@ -101,7 +101,9 @@ struct st_ctx {
   // per batch tile: Gram [C][C], its difference to the target (fp32 and the bf16 copy that is the
   // B operand of the tcgen05 style GEMM)
   float *gram = nullptr, *delta = nullptr, *part = nullptr;
-  __nv_bfloat16* delta_bf16 = nullptr;
+  void* delta_16 = nullptr;              // bf16, or per-tile scaled fp16 in ST_PREC_FP16
+  float* eps_eff = nullptr;              // [kMaxBatch] EPS of normalize() under that scaling
+  unsigned* delta_max = nullptr;         // [kMaxBatch] max |delta| as float bits
   double* abs_partials = nullptr;        // partial sums of |S| of the style GEMM
   size_t part_floats = 0, abs_cap = 0;
   int max_batch = 1;                     // tiles evaluated per launch (1 in fp32 mode)
@@ -210,7 +212,7 @@ constexpr int kStatStride = 8;   // doubles per batch tile in ctx->scalars:
 // map is only written when somebody else needs it (`need_full`: loss layers, requested features).
 template <typename T>
 int fused_pool_layer(const st_ctx* ctx, int i, int last_layer) {
-  if (!std::is_same<T, __nv_bfloat16>::value || getenv("ST_NO_POOL_FUSION") != nullptr) return -1;
+  if (sizeof(T) != 2 || getenv("ST_NO_POOL_FUSION") != nullptr) return -1;
   const LayerRt& l = ctx->layers[i];
   if (l.bottom == 0 || i + 1 > last_layer) return -1;
   const LayerRt& p = ctx->layers[i + 1];
@@ -232,7 +234,7 @@ int forward(st_ctx* ctx, const ImageBatch& view, const Dims& d, int last_layer,
       ST_REQUIRE(l.has_params, "conv layer has no weights (st_set_conv_params)");
       if (l.bottom == 0) {
         bool done = false;
-        if constexpr (std::is_same<T, __nv_bfloat16>::value) {
+        if constexpr (sizeof(T) == 2) {
           if (ctx->tc.enabled && ctx->tc.pair_kernel && l.tc.fwd != nullptr && l.cout == 64) {
             rc = conv_first_fwd_tc(ctx->tc, l.tc, view, hb, wb, l.bias, out, s);
             done = true;
@@ -244,7 +246,7 @@ int forward(st_ctx* ctx, const ImageBatch& view, const Dims& d, int last_layer,
         const int pl = tc_usable<T>(ctx->tc, l.tc, l.cin, l.cout) && ctx->tc.pair_kernel
                            ? fused_pool_layer<T>(ctx, i, last_layer) : -1;
         if (pl >= 0) {
-          if constexpr (std::is_same<T, __nv_bfloat16>::value) {
+          if constexpr (sizeof(T) == 2) {
             LayerRt& p = ctx->layers[pl];
             // other readers of the un-pooled map: loss / feature requests, or another layer (_big)
             bool full = need_full[l.top] != 0;
@@ -258,12 +260,18 @@ int forward(st_ctx* ctx, const ImageBatch& view, const Dims& d, int last_layer,
             p.pool_mask_valid = rc == ST_OK;
             ++i;                                  // the pooling layer is done
           }
-        } else if (tc_usable<T>(ctx->tc, l.tc, l.cin, l.cout))
+        } else if (tc_usable<T>(ctx->tc, l.tc, l.cin, l.cout)) {
           rc = conv3x3_tc(ctx->tc, l.tc, in, out, nb, hb, wb, l.cin, l.cout, true, l.bias, nullptr,
                           nullptr, nullptr, s);
-        else
-          rc = conv3x3_simt<T>(in, l.w_fwd, l.bias, out, nb, hb, wb, l.cin, l.cout, true, nullptr,
-                               nullptr, s);
+        } else {
+          if constexpr (std::is_same<T, __half>::value) {
+            set_error("invalid: ST_PREC_FP16 has no SIMT convolution (channels must be multiples of 64)");
+            rc = ST_ERR_INVALID;
+          } else {
+            rc = conv3x3_simt<T>(in, l.w_fwd, l.bias, out, nb, hb, wb, l.cin, l.cout, true, nullptr,
+                                 nullptr, s);
+          }
+        }
       }
     } else {
       rc = pool_fwd<T>(static_cast<const T*>(ctx->blobs[l.bottom].act), out, nb, hb, wb, l.cin,
@@ -281,7 +289,7 @@ struct BatchGeom {
   int start_y[kMaxBatch], start_x[kMaxBatch];   // tile origin in the rolled image (`start`, :572)
 };
 
-template <typename T>
+template <typename TA, typename T>
 int build_injection(st_ctx* ctx, const st_loss_spec& sp, const Dims& d, const BatchGeom& g,
                     int froll_y, int froll_x, bool is_deepest, cudaStream_t s) {
   BlobRt& b = ctx->blobs[sp.blob];
@@ -291,7 +299,8 @@ int build_injection(st_ctx* ctx, const st_loss_spec& sp, const Dims& d, const Ba
   int rc = ensure(ctx, &b.inj, &b.inj_cap, n * nb, ctx->esize);
   if (rc != ST_OK) return rc;
   T* inj = static_cast<T*>(b.inj);
-  const T* f = static_cast<const T*>(b.act);
+  const TA* f = static_cast<const TA*>(b.act);
+  constexpr bool kHalf = std::is_same<TA, __half>::value;
   bool accumulate = false;
   double* stats = ctx->scalars;          // per tile: [0..1] content/dd stats, [2] sum|S|, [3] loss
   double* tile_loss = ctx->scalars + 3;
@@ -312,9 +321,9 @@ int build_injection(st_ctx* ctx, const st_loss_spec& sp, const Dims& d, const Ba
         offs.ty0[i] = posmod(s0y - floordiv(froll_y, b.scale), t.hf);
         offs.tx0[i] = posmod(s0x - floordiv(froll_x, b.scale), t.wf);
       }
-      rc = diff_stats<T>(f, nb, hf, wf, c, t.nhwc, t.hf, t.wf, offs, stats, kStatStride, ctx->rs, s);
+      rc = diff_stats<TA>(f, nb, hf, wf, c, t.nhwc, t.hf, t.wf, offs, stats, kStatStride, ctx->rs, s);
       if (rc == ST_OK)
-        rc = diff_inject<T>(f, nb, hf, wf, c, t.nhwc, t.hf, t.wf, offs, stats, kStatStride,
+        rc = diff_inject<TA, T>(f, nb, hf, wf, c, t.nhwc, t.hf, t.wf, offs, stats, kStatStride,
                             sp.content_weight, (double)sp.content_weight, tile_loss, kStatStride,
                             inj, accumulate, s);
       if (rc != ST_OK) return rc;
@@ -329,40 +338,47 @@ int build_injection(st_ctx* ctx, const st_loss_spec& sp, const Dims& d, const Ba
       ST_REQUIRE(it != ctx->styles.end(), "style Gram missing for a style layer");
       const double w = (double)sp.style_weight / ctx->n_styles;
       bool on_tc = false;
-      if constexpr (std::is_same<T, __nv_bfloat16>::value) on_tc = gram_tc_ok(ctx->tc, c);
+      if constexpr (sizeof(TA) == 2) on_tc = gram_tc_ok(ctx->tc, c);
       if (on_tc) {
-        if constexpr (std::is_same<T, __nv_bfloat16>::value) {
+        if constexpr (sizeof(TA) == 2) {
           size_t cap = ctx->part_floats;
           rc = ensure(ctx, (void**)&ctx->part, &cap, gram_tc_part_floats(ctx->tc, nb, hf * wf, c), 4);
           ctx->part_floats = cap;
-          if (rc == ST_OK) rc = gram_tc(ctx->tc, f, nb, hf * wf, c, ctx->gram, ctx->part, s);
+          if (rc == ST_OK) rc = gram_tc(ctx->tc, f, kHalf, nb, hf * wf, c, ctx->gram, ctx->part, s);
         }
       } else {
-        ST_REQUIRE(nb == 1, "the SIMT Gram kernel takes one tile at a time");
-        rc = gram_full<T>(f, hf * wf, c, false, ctx->gram, ctx->part, ctx->part_floats,
-                          ctx->sm_count, s);
+        if constexpr (kHalf) {
+          set_error("invalid: ST_PREC_FP16 has no SIMT Gram kernel (channels must be 64/128/256/512)");
+          return ST_ERR_INVALID;
+        } else {
+          ST_REQUIRE(nb == 1, "the SIMT Gram kernel takes one tile at a time");
+          rc = gram_full<TA>(f, hf * wf, c, false, ctx->gram, ctx->part, ctx->part_floats,
+                             ctx->sm_count, s);
+        }
       }
       if (rc == ST_OK)
-        rc = gram_delta(ctx->gram, it->second, ctx->delta, ctx->delta_bf16, c, nb, w, tile_loss,
-                        kStatStride, ctx->rs, s);
+        rc = gram_delta(ctx->gram, it->second, ctx->delta, on_tc ? ctx->delta_16 : nullptr, kHalf,
+                        ctx->delta_max, ctx->eps_eff, c, nb, w, tile_loss, kStatStride, ctx->rs, s);
       if (rc != ST_OK) return rc;
+      const float* eps_eff = on_tc ? ctx->eps_eff : nullptr;
       // the scale-and-copy pass over S can be skipped when S is this blob's whole injection and a
       // kernel epilogue (not a TMA operand load) consumes it
       const bool defer = on_tc && !sp.use_content && !sp.use_dd && ctx->n_styles == 1 && !is_deepest &&
                          getenv("ST_NO_DEFER") == nullptr;
       if (on_tc) {
-        if constexpr (std::is_same<T, __nv_bfloat16>::value) {
+        if constexpr (sizeof(TA) == 2) {
           int per_tile = 0;
           rc = ensure(ctx, (void**)&ctx->abs_partials, &ctx->abs_cap,
                       gemm_abs_partials_needed(nb, hf, wf, c), sizeof(double));
           if (rc == ST_OK && defer && b.inj_scale == nullptr)
             rc = dev_alloc(ctx, (void**)&b.inj_scale, kMaxBatch * sizeof(float));
           if (rc == ST_OK)
-            rc = gemm_abs_tc_pair(ctx->tc, f, ctx->delta_bf16, defer ? inj : static_cast<T*>(ctx->sbuf),
-                                  nb, hf, wf, c, ctx->abs_partials, &per_tile, s);
+            rc = gemm_abs_tc_pair(ctx->tc, f, ctx->delta_16, kHalf,
+                                  defer ? inj : static_cast<T*>(ctx->sbuf), nb, hf, wf, c,
+                                  ctx->abs_partials, &per_tile, s);
           if (rc == ST_OK)
             rc = sum_partials(ctx->abs_partials, per_tile, nb, stats + 2, kStatStride,
-                              defer ? b.inj_scale : nullptr, (float)w, (double)n, s);
+                              defer ? b.inj_scale : nullptr, (float)w, (double)n, eps_eff, s);
           if (rc == ST_OK && defer) {
             b.inj_deferred = true;
             accumulate = true;
@@ -370,21 +386,22 @@ int build_injection(st_ctx* ctx, const st_loss_spec& sp, const Dims& d, const Ba
           }
         }
       } else {
-        rc = style_grad<T>(f, ctx->delta, static_cast<T*>(ctx->sbuf), hf * wf, c, stats + 2,
-                           ctx->rs, s);
+        if constexpr (std::is_same<TA, T>::value)
+          rc = style_grad<T>(f, ctx->delta, static_cast<T*>(ctx->sbuf), hf * wf, c, stats + 2,
+                             ctx->rs, s);
       }
       if (rc == ST_OK)
         rc = inject_scaled<T>(inj, static_cast<const T*>(ctx->sbuf), n, nb, (float)w, stats + 2,
-                              kStatStride, accumulate, s);
+                              kStatStride, eps_eff, accumulate, s);
       if (rc != ST_OK) return rc;
       accumulate = true;
     }
   }
   if (sp.use_dd) {
     TargetOffsets offs{};
-    rc = diff_stats<T>(f, nb, hf, wf, c, nullptr, 1, 1, offs, stats, kStatStride, ctx->rs, s);
+    rc = diff_stats<TA>(f, nb, hf, wf, c, nullptr, 1, 1, offs, stats, kStatStride, ctx->rs, s);
     if (rc == ST_OK)
-      rc = diff_inject<T>(f, nb, hf, wf, c, nullptr, 1, 1, offs, stats, kStatStride, -sp.dd_weight,
+      rc = diff_inject<TA, T>(f, nb, hf, wf, c, nullptr, 1, 1, offs, stats, kStatStride, -sp.dd_weight,
                           -(double)sp.dd_weight, tile_loss, kStatStride, inj, accumulate, s);
     if (rc != ST_OK) return rc;
     accumulate = true;
@@ -394,7 +411,7 @@ int build_injection(st_ctx* ctx, const st_loss_spec& sp, const Dims& d, const Ba
 }
 
 // ---- backward chain to the pixels ----------------------------------------------------------------------
-template <typename T>
+template <typename TA, typename T>
 int backward(st_ctx* ctx, const Dims& d, int nb, int deepest_blob, const std::vector<char>& has_inj,
              float* grad, long batch_stride, long plane, long rstride, cudaStream_t s) {
   int cur = deepest_blob, pp = 0;
@@ -404,7 +421,7 @@ int backward(st_ctx* ctx, const Dims& d, int nb, int deepest_blob, const std::ve
     const int b = l.bottom;
     const int hb = d.h[b], wb = d.w[b];
     if (l.kind == ST_CONV3X3 && b == 0) {
-      if constexpr (std::is_same<T, __nv_bfloat16>::value) {
+      if constexpr (sizeof(T) == 2) {
         if (ctx->tc.enabled && ctx->tc.pair_kernel && l.tc.bwd != nullptr && l.cout % 64 == 0)
           return conv_last_bwd_tc_pair(ctx->tc, l.tc, g, nb, hb, wb, l.cout, grad, batch_stride,
                                        plane, rstride, s);
@@ -413,26 +430,34 @@ int backward(st_ctx* ctx, const Dims& d, int nb, int deepest_blob, const std::ve
     }
     ST_REQUIRE(b != 0, "a pooling layer directly on the image is not supported");
     const BlobRt& bb = ctx->blobs[b];
-    const T* mask = bb.relu ? static_cast<const T*>(bb.act) : nullptr;
+    const TA* mask = bb.relu ? static_cast<const TA*>(bb.act) : nullptr;
     const T* inj = has_inj[b] ? static_cast<const T*>(bb.inj) : nullptr;
     const float* inj_scale = (has_inj[b] && bb.inj_deferred) ? bb.inj_scale : nullptr;
     T* out = static_cast<T*>(ctx->gbuf[pp]);
     int rc;
     if (l.kind == ST_CONV3X3) {
-      if (tc_usable<T>(ctx->tc, l.tc, l.cout, l.cin))
-        rc = conv3x3_tc(ctx->tc, l.tc, g, out, nb, hb, wb, l.cout, l.cin, false, nullptr, mask, inj,
-                        inj_scale, s);
-      else {
+      if (tc_usable<T>(ctx->tc, l.tc, l.cout, l.cin)) {
+        if constexpr (sizeof(T) == 2)
+          rc = conv3x3_tc(ctx->tc, l.tc, g, out, nb, hb, wb, l.cout, l.cin, false, nullptr, mask, inj,
+                          inj_scale, s);
+        else
+          rc = ST_ERR_INVALID;
+      } else {
         ST_REQUIRE(inj_scale == nullptr, "deferred injection scale needs the tensor-core convolution");
-        rc = conv3x3_simt<T>(g, l.w_bwd, nullptr, out, nb, hb, wb, l.cout, l.cin, false, mask, inj,
-                             s);
+        if constexpr (std::is_same<TA, T>::value) {
+          rc = conv3x3_simt<T>(g, l.w_bwd, nullptr, out, nb, hb, wb, l.cout, l.cin, false, mask, inj,
+                               s);
+        } else {
+          set_error("invalid: ST_PREC_FP16 has no SIMT convolution (channels must be multiples of 64)");
+          rc = ST_ERR_INVALID;
+        }
       }
     } else if (l.pool_mask_valid) {
       rc = pool_bwd_mask<T>(g, l.pool_mask, out, nb, hb, wb, l.cin, l.kind == ST_POOL_MAX, inj,
                             inj_scale, s);
     } else {
-      rc = pool_bwd<T>(g, static_cast<const T*>(bb.act), out, nb, hb, wb, l.cin,
-                       l.kind == ST_POOL_MAX, bb.relu, inj, inj_scale, s);
+      rc = pool_bwd<TA, T>(g, static_cast<const TA*>(bb.act), out, nb, hb, wb, l.cin,
+                           l.kind == ST_POOL_MAX, bb.relu, inj, inj_scale, s);
     }
     if (rc != ST_OK) return rc;
     g = out, pp ^= 1, cur = b;
@@ -441,7 +466,7 @@ int backward(st_ctx* ctx, const Dims& d, int nb, int deepest_blob, const std::ve
 
 // One batch of equally sized tiles: forward, loss terms, backward.  The gradient of tile i goes to
 // grad + i * batch_stride.
-template <typename T>
+template <typename TA, typename T>
 int eval_batch(st_ctx* ctx, const ImageBatch& view, int h, int w, const BatchGeom& g, int froll_y,
                int froll_x, int n_specs, const st_loss_spec* specs, double* loss_accum, float* grad,
                long batch_stride, long plane, long rstride, cudaStream_t s) {
@@ -468,12 +493,12 @@ int eval_batch(st_ctx* ctx, const ImageBatch& view, int h, int w, const BatchGeo
   const int last_layer = ctx->blobs[deepest].producer;
   const Dims d = blob_dims(ctx, h, w);
   int rc = reserve_for(ctx, d, last_layer, g.nb);
-  if (rc == ST_OK) rc = forward<T>(ctx, view, d, last_layer, has_inj, s);
+  if (rc == ST_OK) rc = forward<TA>(ctx, view, d, last_layer, has_inj, s);
   for (int i = 0; i < n_specs && rc == ST_OK; ++i)
-    rc = build_injection<T>(ctx, specs[i], d, g, froll_y, froll_x, specs[i].blob == deepest, s);
+    rc = build_injection<TA, T>(ctx, specs[i], d, g, froll_y, froll_x, specs[i].blob == deepest, s);
   if (rc == ST_OK) rc = loss_finalize(ctx->scalars + 3, kStatStride, g.nb, loss_accum, s);
   if (rc == ST_OK)
-    rc = backward<T>(ctx, d, g.nb, deepest, has_inj, grad, batch_stride, plane, rstride, s);
+    rc = backward<TA, T>(ctx, d, g.nb, deepest, has_inj, grad, batch_stride, plane, rstride, s);
   return rc;
 }
 
@@ -482,10 +507,14 @@ int eval_batch_any(st_ctx* ctx, const ImageBatch& view, int h, int w, const Batc
                    double* loss_accum, float* grad, long batch_stride, long plane, long rstride,
                    cudaStream_t s) {
   if (ctx->precision == ST_PREC_FP32)
-    return eval_batch<float>(ctx, view, h, w, g, froll_y, froll_x, n_specs, specs, loss_accum, grad,
-                             batch_stride, plane, rstride, s);
-  return eval_batch<__nv_bfloat16>(ctx, view, h, w, g, froll_y, froll_x, n_specs, specs, loss_accum,
-                                   grad, batch_stride, plane, rstride, s);
+    return eval_batch<float, float>(ctx, view, h, w, g, froll_y, froll_x, n_specs, specs, loss_accum,
+                                    grad, batch_stride, plane, rstride, s);
+  if (ctx->precision == ST_PREC_FP16)
+    return eval_batch<__half, __nv_bfloat16>(ctx, view, h, w, g, froll_y, froll_x, n_specs, specs,
+                                             loss_accum, grad, batch_stride, plane, rstride, s);
+  return eval_batch<__nv_bfloat16, __nv_bfloat16>(ctx, view, h, w, g, froll_y, froll_x, n_specs,
+                                                  specs, loss_accum, grad, batch_stride, plane,
+                                                  rstride, s);
 }
 
 struct Grid {
@@ -542,7 +571,8 @@ uint64_t st_launch_count(void) { return g_launches.load(); }
 
 int st_create(int device, int precision, int n_layers, const st_layer_desc* layers, st_ctx** out) {
   ST_REQUIRE(out != nullptr && layers != nullptr && n_layers > 0, "st_create: bad arguments");
-  ST_REQUIRE(precision == ST_PREC_FP32 || precision == ST_PREC_BF16, "unknown precision");
+  ST_REQUIRE(precision == ST_PREC_FP32 || precision == ST_PREC_BF16 || precision == ST_PREC_FP16,
+             "unknown precision");
   int ndev = 0;
   ST_CUDA(cudaGetDeviceCount(&ndev));
   ST_REQUIRE(device >= 0 && device < ndev, "no such CUDA device");
@@ -575,10 +605,14 @@ int st_create(int device, int precision, int n_layers, const st_layer_desc* laye
     t.scale = ctx->blobs[ld.bottom].scale * (ld.kind == ST_CONV3X3 ? 1 : 2);
   }
   int rc = ST_OK;
-  if (precision == ST_PREC_BF16) rc = tc_init(ctx->tc, ctx->sm_count);
+  if (precision != ST_PREC_FP32) rc = tc_init(ctx->tc, ctx->sm_count);
+  if (rc == ST_OK && precision == ST_PREC_FP16 && !(ctx->tc.enabled && ctx->tc.pair_kernel)) {
+    set_error("invalid: ST_PREC_FP16 needs the tensor-core kernels (unset ST_DISABLE_TC / ST_CONV_V1)");
+    rc = ST_ERR_INVALID;
+  }
   // tiles of one shape are evaluated as a batch by the tensor-core kernels; the fp32 SIMT parity
   // path keeps the reference's one-tile-at-a-time order
-  ctx->max_batch = (precision == ST_PREC_BF16 && ctx->tc.enabled && ctx->tc.pair_kernel) ? kMaxBatch : 1;
+  ctx->max_batch = (precision != ST_PREC_FP32 && ctx->tc.enabled && ctx->tc.pair_kernel) ? kMaxBatch : 1;
   if (const char* e = getenv("ST_MAX_BATCH")) {
     const int v = atoi(e);
     if (v >= 1 && v < ctx->max_batch) ctx->max_batch = v;
@@ -586,8 +620,11 @@ int st_create(int device, int precision, int n_layers, const st_layer_desc* laye
   const size_t gram_floats = (size_t)ctx->max_batch * 512 * 512;
   if (rc == ST_OK) rc = dev_alloc(ctx, (void**)&ctx->gram, gram_floats * sizeof(float));
   if (rc == ST_OK) rc = dev_alloc(ctx, (void**)&ctx->delta, gram_floats * sizeof(float));
-  if (rc == ST_OK && precision == ST_PREC_BF16)
-    rc = dev_alloc(ctx, (void**)&ctx->delta_bf16, gram_floats * sizeof(__nv_bfloat16));
+  if (rc == ST_OK && precision != ST_PREC_FP32) {
+    rc = dev_alloc(ctx, (void**)&ctx->delta_16, gram_floats * 2);
+    if (rc == ST_OK) rc = dev_alloc(ctx, (void**)&ctx->eps_eff, kMaxBatch * sizeof(float));
+    if (rc == ST_OK) rc = dev_alloc(ctx, (void**)&ctx->delta_max, kMaxBatch * sizeof(unsigned));
+  }
   ctx->part_floats = (size_t)16 << 20;
   if (rc == ST_OK) rc = dev_alloc(ctx, (void**)&ctx->part, ctx->part_floats * sizeof(float));
   const size_t n_scalars = (size_t)kMaxBatch * kStatStride;
@@ -618,7 +655,8 @@ int st_destroy(st_ctx* ctx) {
   for (BlobRt& b : ctx->blobs) cudaFree(b.act), cudaFree(b.inj), cudaFree(b.inj_scale);
   cudaFree(ctx->gbuf[0]), cudaFree(ctx->gbuf[1]), cudaFree(ctx->sbuf);
   cudaFree(ctx->gram), cudaFree(ctx->delta), cudaFree(ctx->part), cudaFree(ctx->scalars);
-  cudaFree(ctx->delta_bf16), cudaFree(ctx->abs_partials);
+  cudaFree(ctx->delta_16), cudaFree(ctx->abs_partials), cudaFree(ctx->eps_eff);
+  cudaFree(ctx->delta_max);
   cudaFree(ctx->rs.partials), cudaFree(ctx->rs.counter);
   for (auto& kv : ctx->contents) cudaFree(kv.second.nhwc);
   for (auto& kv : ctx->styles) cudaFree(kv.second);
@@ -658,9 +696,11 @@ int st_set_conv_params(st_ctx* ctx, int layer, const float* w, const float* b) {
   ST_CUDA(cudaMemcpy(l.w_fwd, fwd.data(), fwd.size() * sizeof(float), cudaMemcpyHostToDevice));
   ST_CUDA(cudaMemcpy(l.w_bwd, bwd.data(), bwd.size() * sizeof(float), cudaMemcpyHostToDevice));
   ST_CUDA(cudaMemcpy(l.bias, b, co_n * sizeof(float), cudaMemcpyHostToDevice));
-  if (ctx->precision == ST_PREC_BF16) {
-    int rc = first ? tc_pack_first(ctx->tc, l.tc, w, co_n) : tc_pack_weights(ctx->tc, l.tc, w, ci_n, co_n);
-    if (rc == ST_OK && first) rc = tc_pack_first_fwd(ctx->tc, l.tc, w, co_n);
+  if (ctx->precision != ST_PREC_FP32) {
+    const bool half = ctx->precision == ST_PREC_FP16;
+    int rc = first ? tc_pack_first(ctx->tc, l.tc, w, co_n)
+                   : tc_pack_weights(ctx->tc, l.tc, w, ci_n, co_n, half);
+    if (rc == ST_OK && first) rc = tc_pack_first_fwd(ctx->tc, l.tc, w, co_n, half);
     if (rc != ST_OK) return rc;
   }
   l.has_params = true;
@@ -753,16 +793,22 @@ int st_eval_features_tile(st_ctx* ctx, const float* img_dev, int h, int w, int n
   cudaStream_t s = (cudaStream_t)stream;
   std::vector<char> need_full(ctx->blobs.size(), 0);
   for (int i = 0; i < n_blobs; ++i) need_full[blob_ids[i]] = 1;
-  rc = ctx->precision == ST_PREC_FP32 ? forward<float>(ctx, view, d, last_layer, need_full, s)
-                                      : forward<__nv_bfloat16>(ctx, view, d, last_layer, need_full, s);
+  rc = ctx->precision == ST_PREC_FP32
+           ? forward<float>(ctx, view, d, last_layer, need_full, s)
+           : (ctx->precision == ST_PREC_FP16 ? forward<__half>(ctx, view, d, last_layer, need_full, s)
+                                             : forward<__nv_bfloat16>(ctx, view, d, last_layer,
+                                                                      need_full, s));
   for (int i = 0; i < n_blobs && rc == ST_OK; ++i) {
     const int b = blob_ids[i];
     const int hw = d.h[b] * d.w[b];
-    rc = ctx->precision == ST_PREC_FP32
-             ? nhwc_to_nchw_f32<float>((const float*)ctx->blobs[b].act, out_dev[i], hw,
-                                       ctx->blobs[b].c, s)
-             : nhwc_to_nchw_f32<__nv_bfloat16>((const __nv_bfloat16*)ctx->blobs[b].act, out_dev[i],
-                                               hw, ctx->blobs[b].c, s);
+    if (ctx->precision == ST_PREC_FP32)
+      rc = nhwc_to_nchw_f32<float>((const float*)ctx->blobs[b].act, out_dev[i], hw, ctx->blobs[b].c, s);
+    else if (ctx->precision == ST_PREC_FP16)
+      rc = nhwc_to_nchw_f32<__half>((const __half*)ctx->blobs[b].act, out_dev[i], hw, ctx->blobs[b].c,
+                                    s);
+    else
+      rc = nhwc_to_nchw_f32<__nv_bfloat16>((const __nv_bfloat16*)ctx->blobs[b].act, out_dev[i], hw,
+                                           ctx->blobs[b].c, s);
   }
   return rc;
 }

@@ -144,9 +144,9 @@ struct GramCfg {
   static constexpr int kNHalves = C / kN;
   static constexpr int kTmemCols = C < 32 ? 32 : C;
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
-  // c_format f32 | a,b bf16 | A and B MN-major | N | M = 128
-  static constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
-                                     ((uint32_t)(kN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  // c_format f32 | A and B MN-major | N | M = 128; operand formats (bits 7, 10) are set at run time
+  static constexpr uint32_t kIdescBase = (1u << 4) | (1u << 15) | (1u << 16) |
+                                         ((uint32_t)(kN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 };
 
 struct GramArgs {
@@ -154,6 +154,7 @@ struct GramArgs {
   int kb_total;        // ceil(hw / 64)
   int kb_per_split;
   int nsplit;
+  int half;            // features are fp16 instead of bf16
   float* part;         // [nb][nsplit][C][C] fp32 partial sums
 };
 
@@ -216,6 +217,8 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap map_f, const GramArgs a) {
   } else if (warp == 1) {
     int stage = 0;
     uint32_t phase = 0;
+    const uint32_t fmt = a.half ? 0u : 1u;
+    const uint32_t idesc = Cfg::kIdescBase | (fmt << 7) | (fmt << 10);
     for (int kb = kb_begin; kb < kb_end; ++kb) {
       mbar_wait(&full[stage], phase);
       tc_fence_after();
@@ -227,7 +230,7 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap map_f, const GramArgs a) {
 #pragma unroll
           for (int nh = 0; nh < Cfg::kNHalves; ++nh) {
             const uint64_t db = make_desc_mn(base + nh * 4 * kBoxBytes + k * 2048);
-            tc_mma(tmem_base + nh * 256, da, db, Cfg::kIdesc, (kb != kb_begin || k != 0) ? 1u : 0u);
+            tc_mma(tmem_base + nh * 256, da, db, idesc, (kb != kb_begin || k != 0) ? 1u : 0u);
           }
         }
         tc_commit(&empty[stage]);
@@ -305,7 +308,7 @@ int gram_splits(int hw) {
 }
 
 template <int C>
-int launch_gram(TcContext& tc, const __nv_bfloat16* f, int nb, int hw, float* gram, float* part,
+int launch_gram(TcContext& tc, const void* f, bool half, int nb, int hw, float* gram, float* part,
                 cudaStream_t s) {
   using Cfg = GramCfg<C>;
   CUtensorMap map_f;
@@ -314,7 +317,8 @@ int launch_gram(TcContext& tc, const __nv_bfloat16* f, int nb, int hw, float* gr
     cuuint64_t gstride[2] = {(cuuint64_t)C * 2, (cuuint64_t)hw * C * 2};
     cuuint32_t box[3] = {64, 64, 1}, estride[3] = {1, 1, 1};
     CUresult r = reinterpret_cast<EncodeTiledFn>(tc.encode_fn)(
-        &map_f, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<__nv_bfloat16*>(f), gdim, gstride,
+        &map_f, half ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3,
+        const_cast<void*>(f), gdim, gstride,
         box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
@@ -323,7 +327,7 @@ int launch_gram(TcContext& tc, const __nv_bfloat16* f, int nb, int hw, float* gr
     }
   }
   GramArgs a{};
-  a.hw = hw, a.kb_total = cdiv(hw, 64), a.part = part;
+  a.hw = hw, a.kb_total = cdiv(hw, 64), a.part = part, a.half = half ? 1 : 0;
   a.nsplit = gram_splits<C>(hw);
   a.kb_per_split = cdiv(a.kb_total, a.nsplit);
   auto kern = gram_tc_kernel<C>;
@@ -357,13 +361,13 @@ size_t gram_tc_part_floats(const TcContext& tc, int nb, int hw, int c) {
   return (size_t)nb * nsplit * c * c;
 }
 
-int gram_tc(TcContext& tc, const __nv_bfloat16* f, int nb, int hw, int c, float* gram, float* part,
+int gram_tc(TcContext& tc, const void* f, bool half, int nb, int hw, int c, float* gram, float* part,
             cudaStream_t s) {
   switch (c) {
-    case 64: return launch_gram<64>(tc, f, nb, hw, gram, part, s);
-    case 128: return launch_gram<128>(tc, f, nb, hw, gram, part, s);
-    case 256: return launch_gram<256>(tc, f, nb, hw, gram, part, s);
-    case 512: return launch_gram<512>(tc, f, nb, hw, gram, part, s);
+    case 64: return launch_gram<64>(tc, f, half, nb, hw, gram, part, s);
+    case 128: return launch_gram<128>(tc, f, half, nb, hw, gram, part, s);
+    case 256: return launch_gram<256>(tc, f, half, nb, hw, gram, part, s);
+    case 512: return launch_gram<512>(tc, f, half, nb, hw, gram, part, s);
   }
   set_error("gram_tc: unsupported channel count");
   return ST_ERR_INVALID;

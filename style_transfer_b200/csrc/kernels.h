@@ -2,6 +2,7 @@
 #pragma once
 
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -51,8 +52,8 @@ int conv3x3_simt(const T* in, const float* wpack, const float* bias, T* out, int
 template <typename T>
 int pool_fwd(const T* in, T* out, int nb, int h, int w, int c, bool is_max, cudaStream_t s);
 // d_in = [mask](in>0) * pool_bwd(d_out) + [inj_scale[tile]] * [inj]
-template <typename T>
-int pool_bwd(const T* d_out, const T* in, T* d_in, int nb, int h, int w, int c, bool is_max,
+template <typename TA, typename T>
+int pool_bwd(const T* d_out, const TA* in, T* d_in, int nb, int h, int w, int c, bool is_max,
              bool apply_mask, const T* inj, const float* inj_scale, cudaStream_t s);
 
 // backward of a pooling layer from the one-byte mask the fused conv+pool kernel stored
@@ -68,14 +69,16 @@ template <typename T>
 int gram_full(const T* f, int hw, int c, bool channel_major, float* gram, float* part,
               size_t part_floats, int sm_count, cudaStream_t s);
 // delta[b] = gram[b] - target (symmetric, full [C][C] each);
-// tile_loss[b * loss_stride] += w * 0.5 * sum_{j<=i} delta_ij^2
-int gram_delta(const float* gram, const float* target, float* delta, __nv_bfloat16* delta_bf16,
-               int c, int nb, double w, double* tile_loss, int loss_stride, ReduceScratch rs,
-               cudaStream_t s);
+// tile_loss[b * loss_stride] += w * 0.5 * sum_{j<=i} delta_ij^2.  delta_16 (optional) receives the
+// 16-bit copy for the tensor-core style GEMM: bf16, or fp16 scaled per tile by a power of two
+// (half) -- eps_eff[b] is the EPS that compensates that scaling in normalize().
+int gram_delta(const float* gram, const float* target, float* delta, void* delta_16, bool half,
+               unsigned* max_bits, float* eps_eff, int c, int nb, double w, double* tile_loss,
+               int loss_stride, ReduceScratch rs, cudaStream_t s);
 // out[b * out_stride] = sum(partials[b*n .. b*n+n)) in a launch-independent order; if scale is not
 // null also scale[b] = w / (sum / count + EPS)
 int sum_partials(const double* partials, int n, int nb, double* out, int out_stride, float* scale,
-                 float w, double count, cudaStream_t s);
+                 float w, double count, const float* eps_eff, cudaStream_t s);
 // *loss_accum += sum_b tile_loss[b * stride] (tile order); clears the slots
 int loss_finalize(double* tile_loss, int stride, int nb, double* loss_accum, cudaStream_t s);
 // S[p][co] = sum_ci F[p][ci] * delta[ci][co]; *sum_abs = sum |S|
@@ -85,7 +88,7 @@ int style_grad(const T* f, const float* delta, T* s_out, int hw, int c, double* 
 // per tile b (n elements each): inj = (accumulate ? inj : 0) + w / (sum_abs[b*stride] / n + EPS) * src
 template <typename T>
 int inject_scaled(T* inj, const T* src, size_t n, int nb, float w, const double* sum_abs,
-                  int stat_stride, bool accumulate, cudaStream_t s);
+                  int stat_stride, const float* eps_eff, bool accumulate, cudaStream_t s);
 int symmetrize_lower(const float* lower, float* full, int c, cudaStream_t s);
 int extract_lower(const float* full, float* lower, int c, cudaStream_t s);
 
@@ -99,8 +102,8 @@ int diff_stats(const T* f, int nb, int hf, int wf, int c, const float* tgt, int 
                cudaStream_t s);
 // inj = (accumulate ? inj : 0) + w / (stats[1]/n + EPS) * (F - target);
 // tile_loss[b * loss_stride] += loss_w * 0.5 * stats[0]
-template <typename T>
-int diff_inject(const T* f, int nb, int hf, int wf, int c, const float* tgt, int Hf, int Wf,
+template <typename TA, typename T>
+int diff_inject(const TA* f, int nb, int hf, int wf, int c, const float* tgt, int Hf, int Wf,
                 const TargetOffsets& offs, const double* stats, int stat_stride, float w,
                 double loss_w, double* tile_loss, int loss_stride, T* inj, bool accumulate,
                 cudaStream_t s);

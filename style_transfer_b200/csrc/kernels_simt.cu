@@ -312,9 +312,9 @@ pool_fwd_kernel(const T* __restrict__ in_all, T* __restrict__ out, int nb, int h
   }
 }
 
-template <typename T>
+template <typename TA, typename T>
 __global__ void __launch_bounds__(256)
-pool_bwd_kernel(const T* __restrict__ d_out, const T* __restrict__ in_all, T* __restrict__ d_in_all,
+pool_bwd_kernel(const T* __restrict__ d_out, const TA* __restrict__ in_all, T* __restrict__ d_in_all,
                 int nb, int h, int w, int c, int ho, int wo, int is_max, int apply_mask,
                 const T* __restrict__ inj_all, const float* __restrict__ inj_scale) {
   const unsigned c4 = c >> 2, uwo = wo, uho = ho;
@@ -326,7 +326,7 @@ pool_bwd_kernel(const T* __restrict__ d_out, const T* __restrict__ in_all, T* __
     const int x = (int)(p - row * uwo), y = (int)(row % uho);
     const unsigned bt = row / uho;                            // tile of the batch
     const size_t boff = (size_t)bt * ((size_t)h * w * c) + q * 4;
-    const T* in = in_all + boff;
+    const TA* in = in_all + boff;
     T* d_in = d_in_all + boff;
     const T* inj = inj_all ? inj_all + boff : nullptr;
     const float isc = inj_scale ? inj_scale[bt] : 1.f;
@@ -339,7 +339,7 @@ pool_bwd_kernel(const T* __restrict__ d_out, const T* __restrict__ in_all, T* __
       const int yy = 2 * y + (d >> 1), xx = 2 * x + (d & 1);
       ok[d] = yy < h && xx < w;
       const size_t o = ((size_t)yy * w + xx) * c;
-      v[d] = ok[d] ? Store<T>::ld4(in + o) : make_float4(0.f, 0.f, 0.f, 0.f);
+      v[d] = ok[d] ? Store<TA>::ld4(in + o) : make_float4(0.f, 0.f, 0.f, 0.f);
       e[d] = (ok[d] && inj) ? Store<T>::ld4(inj + o) : make_float4(0.f, 0.f, 0.f, 0.f);
       cnt += ok[d];
     }
@@ -444,13 +444,13 @@ int pool_fwd(const T* in, T* out, int nb, int h, int w, int c, bool is_max, cuda
   return ST_OK;
 }
 
-template <typename T>
-int pool_bwd(const T* d_out, const T* in, T* d_in, int nb, int h, int w, int c, bool is_max,
+template <typename TA, typename T>
+int pool_bwd(const T* d_out, const TA* in, T* d_in, int nb, int h, int w, int c, bool is_max,
              bool apply_mask, const T* inj, const float* inj_scale, cudaStream_t s) {
   ST_REQUIRE(c % 8 == 0, "pool: channels must be a multiple of 8");
   const int ho = (h + 1) / 2, wo = (w + 1) / 2;
   ST_REQUIRE((size_t)nb * ho * wo * c < ((size_t)1 << 31), "pool: batch too large for 32-bit indexing");
-  auto k = pool_bwd_kernel<T>;
+  auto k = pool_bwd_kernel<TA, T>;
   TimerScope ts(s, kTimePool, (double)sizeof(T) * c * nb *
                                   ((double)h * w * (2 + (inj ? 1 : 0)) + (double)ho * wo));
   ST_LAUNCH(k, ew_grid((size_t)nb * ho * wo * (c / 4), 256), 256, 0, s, d_out, in, d_in, nb, h, w,
@@ -573,29 +573,71 @@ int gram_full(const T* f, int hw, int c, bool channel_major, float* gram, float*
 }
 
 // delta[b] = G[b] - G_style (symmetric); tile_loss[b] += w * 0.5 * sum_{j<=i} delta^2
-// (style_transfer.py:587,591).  blockIdx.y = tile of the batch.
+// (style_transfer.py:587,591).  blockIdx.y = tile of the batch.  max_bits[b] (optional) collects
+// max |delta| as float bits (atomicMax on non-negative floats is order independent).
 __global__ void gram_delta_kernel(const float* __restrict__ gram, const float* __restrict__ target,
-                                  float* __restrict__ delta, __nv_bfloat16* __restrict__ delta_bf16,
-                                  int c, double w, double* tile_loss, int loss_stride,
-                                  ReduceScratch rs) {
+                                  float* __restrict__ delta, unsigned* max_bits, int c, double w,
+                                  double* tile_loss, int loss_stride, ReduceScratch rs) {
   const size_t off = (size_t)blockIdx.y * c * c;
   double v[1] = {0.0};
+  float mx = 0.f;
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < c * c;
        idx += gridDim.x * blockDim.x) {
     const float d = gram[off + idx] - target[idx];
     delta[off + idx] = d;
-    if (delta_bf16 != nullptr) delta_bf16[off + idx] = __float2bfloat16_rn(d);
+    mx = fmaxf(mx, fabsf(d));
     if (idx % c <= idx / c) v[0] += (double)d * d;
+  }
+  if (max_bits != nullptr) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(max_bits + blockIdx.y, __float_as_uint(mx));
   }
   if (grid_reduce<1>(v, rs.partials + (size_t)blockIdx.y * gridDim.x, rs.counter + blockIdx.y))
     tile_loss[(size_t)blockIdx.y * loss_stride] += w * 0.5 * v[0];
 }
 
-int gram_delta(const float* gram, const float* target, float* delta, __nv_bfloat16* delta_bf16,
-               int c, int nb, double w, double* tile_loss, int loss_stride, ReduceScratch rs,
-               cudaStream_t s) {
+// The 16-bit copy of delta that is the B operand of the tensor-core style GEMM.  bf16: plain
+// rounding, eps_eff[b] = EPS.  fp16 (half): delta is first multiplied by sigma_b = 2^-ceil(log2 max
+// |delta_b|), an exact power-of-two scaling that keeps it inside the fp16 range; S then comes out
+// scaled by sigma_b too, which normalize() cancels except in its EPS term, hence eps_eff[b] =
+// EPS * sigma_b (w / (mean|S| + EPS) * S  ==  w / (mean|sigma S| + EPS sigma) * sigma S).
+__global__ void delta_pack_kernel(const float* __restrict__ delta, uint16_t* __restrict__ out,
+                                  unsigned* max_bits, float* eps_eff, int c, int half) {
+  const size_t off = (size_t)blockIdx.y * c * c;
+  float sigma = 1.f;
+  if (half) {
+    const float mx = __uint_as_float(max_bits[blockIdx.y]);
+    if (mx > 0.f && isfinite(mx)) {
+      int e;
+      frexpf(mx, &e);                       // mx = m * 2^e, 0.5 <= m < 1
+      sigma = ldexpf(1.f, -e);              // max |delta| * sigma in [0.5, 1)
+    }
+  }
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < c * c;
+       idx += gridDim.x * blockDim.x) {
+    const float d = delta[off + idx] * sigma;
+    if (half) {
+      const __half hv = __float2half_rn(d);
+      out[off + idx] = *reinterpret_cast<const uint16_t*>(&hv);
+    } else {
+      const __nv_bfloat16 bv = __float2bfloat16_rn(d);
+      out[off + idx] = *reinterpret_cast<const uint16_t*>(&bv);
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) eps_eff[blockIdx.y] = kEps * sigma;
+}
+
+int gram_delta(const float* gram, const float* target, float* delta, void* delta_16, bool half,
+               unsigned* max_bits, float* eps_eff, int c, int nb, double w, double* tile_loss,
+               int loss_stride, ReduceScratch rs, cudaStream_t s) {
+  const bool track = delta_16 != nullptr && half;
+  if (track) ST_CUDA(cudaMemsetAsync(max_bits, 0, nb * sizeof(unsigned), s));
   ST_LAUNCH(gram_delta_kernel, dim3(min(cdiv((long)c * c, 256), 256), nb), 256, 0, s, gram, target,
-            delta, delta_bf16, c, w, tile_loss, loss_stride, rs);
+            delta, track ? max_bits : nullptr, c, w, tile_loss, loss_stride, rs);
+  if (delta_16 != nullptr)
+    ST_LAUNCH(delta_pack_kernel, dim3(min(cdiv((long)c * c, 256), 64), nb), 256, 0, s, delta,
+              static_cast<uint16_t*>(delta_16), max_bits, eps_eff, c, half ? 1 : 0);
   return ST_OK;
 }
 
@@ -605,7 +647,7 @@ int gram_delta(const float* gram, const float* target, float* delta, __nv_bfloat
 // normalize() + the layer weight apply to the style gradient (num_utils.py:85-87, :591-593).
 __global__ void __launch_bounds__(256)
 sum_partials_kernel(const double* __restrict__ partials, int n, double* out, int out_stride,
-                    float* scale, float w, double count) {
+                    float* scale, float w, double count, const float* __restrict__ eps_eff) {
   __shared__ double sh[256];
   const double* p = partials + (size_t)blockIdx.x * n;
   double x = 0.0;
@@ -618,12 +660,14 @@ sum_partials_kernel(const double* __restrict__ partials, int n, double* out, int
   }
   if (threadIdx.x == 0) {
     out[(size_t)blockIdx.x * out_stride] = sh[0];
-    if (scale != nullptr) scale[blockIdx.x] = w * (1.f / ((float)(sh[0] / count) + kEps));
+    const float eps = eps_eff ? eps_eff[blockIdx.x] : kEps;
+    if (scale != nullptr) scale[blockIdx.x] = w * (1.f / ((float)(sh[0] / count) + eps));
   }
 }
 int sum_partials(const double* partials, int n, int nb, double* out, int out_stride, float* scale,
-                 float w, double count, cudaStream_t s) {
-  ST_LAUNCH(sum_partials_kernel, nb, 256, 0, s, partials, n, out, out_stride, scale, w, count);
+                 float w, double count, const float* eps_eff, cudaStream_t s) {
+  ST_LAUNCH(sum_partials_kernel, nb, 256, 0, s, partials, n, out, out_stride, scale, w, count,
+            eps_eff);
   return ST_OK;
 }
 
@@ -731,10 +775,11 @@ int style_grad(const T* f, const float* delta, T* s_out, int hw, int c, double* 
 template <typename T>
 __global__ void inject_scaled_kernel(T* __restrict__ inj, const T* __restrict__ src, size_t n4,
                                      float w, const double* __restrict__ sum_abs, int stat_stride,
-                                     int accumulate) {
+                                     const float* __restrict__ eps_eff, int accumulate) {
   // blockIdx.y = tile of the batch; n4 = float4 groups per tile
+  const float eps = eps_eff ? eps_eff[blockIdx.y] : kEps;
   const float coef =
-      w * (1.f / ((float)(sum_abs[(size_t)blockIdx.y * stat_stride] / (double)(n4 * 4)) + kEps));
+      w * (1.f / ((float)(sum_abs[(size_t)blockIdx.y * stat_stride] / (double)(n4 * 4)) + eps));
   inj += (size_t)blockIdx.y * n4 * 4, src += (size_t)blockIdx.y * n4 * 4;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4;
        i += (size_t)gridDim.x * blockDim.x) {
@@ -750,11 +795,11 @@ __global__ void inject_scaled_kernel(T* __restrict__ inj, const T* __restrict__ 
 
 template <typename T>
 int inject_scaled(T* inj, const T* src, size_t n, int nb, float w, const double* sum_abs,
-                  int stat_stride, bool accumulate, cudaStream_t s) {
+                  int stat_stride, const float* eps_eff, bool accumulate, cudaStream_t s) {
   ST_REQUIRE(n % 4 == 0, "inject: size must be a multiple of 4");
   auto k = inject_scaled_kernel<T>;
   ST_LAUNCH(k, dim3(ew_grid(n / 4, 256), nb), 256, 0, s, inj, src, n / 4, w, sum_abs, stat_stride,
-            accumulate ? 1 : 0);
+            eps_eff, accumulate ? 1 : 0);
   return ST_OK;
 }
 
@@ -818,8 +863,8 @@ int diff_stats(const T* f, int nb, int hf, int wf, int c, const float* tgt, int 
 
 // stats[b] = {sum c^2, sum |c|}; inj = (accumulate ? inj : 0) + w / (mean|c| + EPS) * c;
 // tile_loss[b] += loss_w * 0.5 * sum c^2
-template <typename T>
-__global__ void diff_inject_kernel(const T* __restrict__ f, size_t n4, int wf, int c4,
+template <typename TA, typename T>
+__global__ void diff_inject_kernel(const TA* __restrict__ f, size_t n4, int wf, int c4,
                                    const float* __restrict__ tgt, int Hf, int Wf, TargetOffsets offs,
                                    const double* __restrict__ stats, int stat_stride, float w,
                                    double loss_w, double* tile_loss, int loss_stride,
@@ -841,13 +886,13 @@ __global__ void diff_inject_kernel(const T* __restrict__ f, size_t n4, int wf, i
   }
 }
 
-template <typename T>
-int diff_inject(const T* f, int nb, int hf, int wf, int c, const float* tgt, int Hf, int Wf,
+template <typename TA, typename T>
+int diff_inject(const TA* f, int nb, int hf, int wf, int c, const float* tgt, int Hf, int Wf,
                 const TargetOffsets& offs, const double* stats, int stat_stride, float w,
                 double loss_w, double* tile_loss, int loss_stride, T* inj, bool accumulate,
                 cudaStream_t s) {
   const size_t n4 = (size_t)hf * wf * (c / 4);
-  auto k = diff_inject_kernel<T>;
+  auto k = diff_inject_kernel<TA, T>;
   TimerScope ts(s, kTimeLoss, (double)nb * n4 * 4 * (sizeof(T) * (accumulate ? 3 : 2) + (tgt ? 4 : 0)));
   ST_LAUNCH(k, dim3(ew_grid(n4, 256), nb), 256, 0, s, f, n4, wf, c / 4, tgt, Hf, Wf, offs, stats,
             stat_stride, w, loss_w, tile_loss, loss_stride, inj, accumulate ? 1 : 0);
@@ -891,31 +936,48 @@ int nchw_to_nhwc_f32(const float* in, float* out, int hw, int c, cudaStream_t s)
 }
 
 // ---- explicit instantiations ---------------------------------------------------------------------
-#define ST_INSTANTIATE(T)                                                                         \
-  template int conv3x3_simt<T>(const T*, const float*, const float*, T*, int, int, int, int, int, \
-                               bool, const T*, const T*, cudaStream_t);                           \
-  template int conv_first_fwd<T>(const ImageBatch&, int, int, const float*, const float*, T*,     \
-                                 int, cudaStream_t);                                              \
-  template int conv_last_bwd<T>(const T*, int, int, int, int, const float*, float*, long, long,   \
-                                long, cudaStream_t);                                              \
-  template int pool_fwd<T>(const T*, T*, int, int, int, int, bool, cudaStream_t);                 \
-  template int pool_bwd<T>(const T*, const T*, T*, int, int, int, int, bool, bool, const T*,      \
-                           const float*, cudaStream_t);                                           \
-  template int pool_bwd_mask<T>(const T*, const uint8_t*, T*, int, int, int, int, bool, const T*,  \
-                                const float*, cudaStream_t);                                      \
-  template int gram_full<T>(const T*, int, int, bool, float*, float*, size_t, int, cudaStream_t); \
-  template int style_grad<T>(const T*, const float*, T*, int, int, double*, ReduceScratch,        \
-                             cudaStream_t);                                                       \
-  template int inject_scaled<T>(T*, const T*, size_t, int, float, const double*, int, bool,       \
-                                cudaStream_t);                                                    \
-  template int diff_stats<T>(const T*, int, int, int, int, const float*, int, int,                \
-                             const TargetOffsets&, double*, int, ReduceScratch, cudaStream_t);    \
-  template int diff_inject<T>(const T*, int, int, int, int, const float*, int, int,               \
-                              const TargetOffsets&, const double*, int, float, double, double*,   \
-                              int, T*, bool, cudaStream_t);                                       \
-  template int nhwc_to_nchw_f32<T>(const T*, float*, int, int, cudaStream_t);
+// TA = activation storage, TG = gradient storage: (float, float) in ST_PREC_FP32, (bf16, bf16) in
+// ST_PREC_BF16, (fp16, bf16) in ST_PREC_FP16.
+#define ST_INSTANTIATE_ACT(TA)                                                                     \
+  template int conv_first_fwd<TA>(const ImageBatch&, int, int, const float*, const float*, TA*,    \
+                                  int, cudaStream_t);                                              \
+  template int pool_fwd<TA>(const TA*, TA*, int, int, int, int, bool, cudaStream_t);               \
+  template int diff_stats<TA>(const TA*, int, int, int, int, const float*, int, int,               \
+                              const TargetOffsets&, double*, int, ReduceScratch, cudaStream_t);    \
+  template int nhwc_to_nchw_f32<TA>(const TA*, float*, int, int, cudaStream_t);
 
-ST_INSTANTIATE(float)
-ST_INSTANTIATE(__nv_bfloat16)
+#define ST_INSTANTIATE_GRAD(TG)                                                                    \
+  template int conv_last_bwd<TG>(const TG*, int, int, int, int, const float*, float*, long, long,  \
+                                 long, cudaStream_t);                                              \
+  template int pool_bwd_mask<TG>(const TG*, const uint8_t*, TG*, int, int, int, int, bool,         \
+                                 const TG*, const float*, cudaStream_t);                           \
+  template int inject_scaled<TG>(TG*, const TG*, size_t, int, float, const double*, int,           \
+                                 const float*, bool, cudaStream_t);
+
+#define ST_INSTANTIATE_PAIR(TA, TG)                                                                \
+  template int pool_bwd<TA, TG>(const TG*, const TA*, TG*, int, int, int, int, bool, bool,         \
+                                const TG*, const float*, cudaStream_t);                            \
+  template int diff_inject<TA, TG>(const TA*, int, int, int, int, const float*, int, int,          \
+                                   const TargetOffsets&, const double*, int, float, double,        \
+                                   double*, int, TG*, bool, cudaStream_t);
+
+// single-type SIMT kernels of the fp32 parity mode and of the bf16 fallback
+#define ST_INSTANTIATE_SIMT(T)                                                                     \
+  template int conv3x3_simt<T>(const T*, const float*, const float*, T*, int, int, int, int, int,  \
+                               bool, const T*, const T*, cudaStream_t);                            \
+  template int gram_full<T>(const T*, int, int, bool, float*, float*, size_t, int, cudaStream_t);  \
+  template int style_grad<T>(const T*, const float*, T*, int, int, double*, ReduceScratch,         \
+                             cudaStream_t);
+
+ST_INSTANTIATE_ACT(float)
+ST_INSTANTIATE_ACT(__nv_bfloat16)
+ST_INSTANTIATE_ACT(__half)
+ST_INSTANTIATE_GRAD(float)
+ST_INSTANTIATE_GRAD(__nv_bfloat16)
+ST_INSTANTIATE_PAIR(float, float)
+ST_INSTANTIATE_PAIR(__nv_bfloat16, __nv_bfloat16)
+ST_INSTANTIATE_PAIR(__half, __nv_bfloat16)
+ST_INSTANTIATE_SIMT(float)
+ST_INSTANTIATE_SIMT(__nv_bfloat16)
 
 }  // namespace st

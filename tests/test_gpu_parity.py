@@ -3,6 +3,10 @@ seeded inputs.  Stated tolerances:
 
   fp32 mode  : max|d| <= 2e-4 * max|ref| for feature maps and gradients, 1e-4 relative for
                losses (float32 round-off + different summation order);
+  fp16 mode  : tensor cores with fp16 forward activations / weights and bf16 gradients: feature
+               maps within 2e-3 relative L2, losses within 5e-3; gradients relative L2 <= 2e-2
+               (average-pool nets) / <= 6e-2 (max-pool nets) -- same mechanism as below, 8x finer
+               forward rounding.
   bf16 mode  : bf16 operands and stored activations, fp32 accumulation: feature maps within
                2e-2 relative L2, losses within 2e-2 relative.  Gradients: relative L2 error
                <= 5e-2 on the average-pool nets and <= 1.5e-1 on the max-pool nets.  The max-pool
@@ -63,6 +67,18 @@ def test_features_tile(model, hw):
         assert maxrel(got[l], want[l]) < 2e-4, l
 
 
+@pytest.mark.parametrize('precision,tol', [('fp16', 2e-3), ('bf16', 2e-2)])
+def test_features_tile_tensor_core_modes(precision, tol):
+    eng, ora = engine_for('vgg19.prototxt', precision)
+    img = rand_img(np.random.RandomState(1), 45, 77)
+    layers = ['conv1_1', 'conv1_2', 'pool1', 'conv2_2', 'conv3_4', 'pool3', 'conv4_2', 'conv5_1']
+    got = eng.eval_features_tile(img, layers)
+    want = ora.features_tile(img, layers)
+    for l in layers:
+        assert got[l].shape == want[l].shape, l
+        assert l2rel(got[l], want[l]) < tol, (l, l2rel(got[l], want[l]))
+
+
 def setup_targets(eng, ora, rs, H, W, c_layers, s_layers, n_styles=1, n_contents=1, tile=512):
     contents = [rand_img(rs, H, W) for _ in range(n_contents)]
     styles = [rand_img(rs, H, W) for _ in range(n_styles)]
@@ -95,7 +111,7 @@ CASES = [
 
 
 @pytest.mark.parametrize('case', CASES, ids=[c[0].split('.')[0] + '-%dx%d' % c[1] for c in CASES])
-@pytest.mark.parametrize('precision', ['fp32', 'bf16'])
+@pytest.mark.parametrize('precision', ['fp32', 'bf16', 'fp16'])
 def test_sc_grad_tile(case, precision):
     model, (h, w), c_layers, s_layers, d_layers, start, roll = case
     eng, ora = engine_for(model, precision)
@@ -116,6 +132,9 @@ def test_sc_grad_tile(case, precision):
     if precision == 'fp32':
         assert abs(loss_g - loss_o) <= 1e-4 * abs(loss_o), (loss_g, loss_o)
         assert maxrel(grad_g, grad_o) < 2e-4
+    elif precision == 'fp16':
+        assert abs(loss_g - loss_o) <= 5e-3 * abs(loss_o), (loss_g, loss_o)
+        assert l2rel(grad_g, grad_o) < (2e-2 if 'avgpool' in model else 6e-2)
     else:
         assert abs(loss_g - loss_o) <= 2e-2 * abs(loss_o), (loss_g, loss_o)
         assert l2rel(grad_g, grad_o) < (5e-2 if 'avgpool' in model else 1.5e-1)

@@ -34,7 +34,7 @@ CONFIGS = {
 def main():
     p = argparse.ArgumentParser()
     p.add_argument('configs', nargs='*', default=list(CONFIGS))
-    p.add_argument('--precision', default='bf16')
+    p.add_argument('--precision', default='fp16')
     a = p.parse_args()
     rs = np.random.RandomState(0)
     out = {}

@@ -13,3 +13,6 @@ try:
 except Exception as e:
     print('bench parse failed', e)
 PY
+timeout 300 python bench.py --no-cpu-baseline --no-e2e --precision fp16 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('fp16 mode: it/s %.2f  conv frac %.3f' % (d['value'], d['roofline']['frac']))"

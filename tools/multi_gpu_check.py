@@ -26,7 +26,7 @@ def main():
     content, style = (rs.randint(0, 256, (size, size, 3)).astype(np.uint8) for _ in range(2))
     results = []
     for r, w in ((rank, world), (0, 1)):
-        eng = TileEngine(net, params, mean=args.mean, device=local, precision='bf16', rank=r, world=w)
+        eng = TileEngine(net, params, mean=args.mean, device=local, precision='fp16', rank=r, world=w)
         st = StyleTransfer(eng, args)
         np.random.seed(0)
         st.init_first_scale(size, size)

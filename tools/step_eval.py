@@ -18,7 +18,7 @@ def main():
     p.add_argument('--size', type=int, default=2048)
     p.add_argument('--tile-size', type=int, default=512)
     p.add_argument('--steps', type=int, default=3)
-    p.add_argument('--precision', default='bf16')
+    p.add_argument('--precision', default='fp16')
     p.add_argument('--optimizer', default='adam')
     a = p.parse_args()
     args = default_args(size=a.size, min_size=a.size, tile_size=a.tile_size, optimizer=a.optimizer)

@@ -30,19 +30,22 @@ def main():
         for (h, w) in [(64, 64), (96, 160), (45, 77), (256, 256)]:
             img = torch.from_numpy(rs.rand(3, h, w).astype(np.float32) * 255 - 120).cuda()
             e_tc, e_simt, e_f32 = engine('vgg19.prototxt', 'bf16', True), engine('vgg19.prototxt', 'bf16', False), engine('vgg19.prototxt', 'fp32')
+            e_h = engine('vgg19.prototxt', 'fp16', True)
             f_tc, f_s, f_32 = (e.eval_features_tile(img, LAYERS) for e in (e_tc, e_simt, e_f32))
             torch.cuda.synchronize()
             print('features %dx%d' % (h, w), ' '.join('%s tc/simt %.1e tc/f32 %.1e |' % (l, rel(f_tc[l], f_s[l]), rel(f_tc[l], f_32[l])) for l in LAYERS[1:]), flush=True)
             lw = {l: 1.0 for l in e_tc.layers()}
             cw, sw = {'conv4_2': 0.05}, {l: 0.2 for l in STYLE}
+            f_h = e_h.eval_features_tile(img, LAYERS)
+            print('   fp16/f32 ', ' '.join('%s %.1e |' % (l, rel(f_h[l], f_32[l])) for l in LAYERS[1:]), flush=True)
             grads = []
-            for e in (e_tc, e_simt, e_f32):
+            for e in (e_tc, e_simt, e_f32, e_h):
                 targets(e, h, w, np.random.RandomState(1))
                 layers = e.ordered_layers(STYLE, ['conv4_2'])
                 loss, g = e.eval_sc_grad_tile(img, (0, 0), layers, ['conv4_2'], STYLE, [], lw, cw, sw, {})
                 grads.append((loss, g.clone()))
-            print('  sc_grad loss tc %.6e simt %.6e f32 %.6e | grad tc/simt %.2e tc/f32 %.2e simt/f32 %.2e' % (
-                grads[0][0], grads[1][0], grads[2][0], rel(grads[0][1], grads[1][1]), rel(grads[0][1], grads[2][1]), rel(grads[1][1], grads[2][1])), flush=True)
+            print('  sc_grad loss tc %.6e simt %.6e f32 %.6e fp16 %.6e | grad tc/simt %.2e tc/f32 %.2e simt/f32 %.2e fp16/f32 %.2e' % (
+                grads[0][0], grads[1][0], grads[2][0], grads[3][0], rel(grads[0][1], grads[1][1]), rel(grads[0][1], grads[2][1]), rel(grads[1][1], grads[2][1]), rel(grads[3][1], grads[2][1])), flush=True)
     if which in ('all', 'time'):
         for prec in ('bf16', 'fp32'):
             e = engine('vgg19.prototxt', prec)

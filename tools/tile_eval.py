@@ -16,7 +16,7 @@ STYLE = ['conv1_1', 'conv2_1', 'conv3_1', 'conv4_1', 'conv5_1']
 
 def main():
     p = argparse.ArgumentParser()
-    p.add_argument('--precision', default='bf16')
+    p.add_argument('--precision', default='fp16')
     p.add_argument('--size', type=int, default=512)
     p.add_argument('--evals', type=int, default=3)
     p.add_argument('--model', default='vgg19.prototxt')
