@@ -148,8 +148,11 @@ def main(argv=None):
         if args.weights != 'random' and rank == 0:
             print('weights file %s not found: using random He-normal weights' % args.weights)
         params = weights.he_normal(net)
-    else:
+    elif args.weights.endswith('.npz'):
         params = weights.load_npz(args.weights)
+    else:
+        from .caffemodel import load_caffemodel
+        params = load_caffemodel(args.weights, net)
     layer_weights = None
     if args.layer_weights:
         with open(args.layer_weights) as f:

@@ -73,7 +73,7 @@ def build_parser():
     arg('--browser', default=None, help='ignored')
     arg('--model', default='vgg19.prototxt', help='the deploy.prototxt of the model to use')
     arg('--weights', default='vgg19.caffemodel',
-        help='model weights: an .npz written by weights.save_npz, or "random" for He-normal weights')
+        help='the .caffemodel of the model (or an .npz written by weights.save_npz, or "random")')
     arg('--mean', nargs=3, metavar=('B_MEAN', 'G_MEAN', 'R_MEAN'), type=float,
         default=(103.939, 116.779, 123.68), help='the per-channel means of the model (BGR order)')
     arg('--save-every', metavar='N', type=int, default=0, help='save the image every n steps')

@@ -336,3 +336,29 @@ def test_n_iterations_match_oracle(optimizer, iters):
         assert rms <= 0.25 and float((err > 1.0).mean()) <= 1e-2, (rms, q, float(err.max()))
     else:
         assert err.max() <= 0.5, float(err.max())
+
+
+@pytest.mark.parametrize('precision', ['fp16', 'bf16'])
+def test_batching_does_not_change_bits(precision, monkeypatch):
+    """Tiles evaluated 16, 3 or 1 at a time give bit-identical gradients: split-K and |S| partial
+    sums are grouped by layer shape only, never by batch size (what makes N-rank == 1-rank)."""
+    rs = np.random.RandomState(2)
+    H, W, tile = 96, 128, 32                     # 3 x 4 = 12 equal tiles
+    c_layers, s_layers = ['conv3_2'], ['conv1_1', 'conv2_1', 'conv3_1']
+    results = []
+    for max_batch in (None, '3', '1'):
+        if max_batch is None:
+            monkeypatch.delenv('ST_MAX_BATCH', raising=False)
+        else:
+            monkeypatch.setenv('ST_MAX_BATCH', max_batch)
+        eng, ora = engine_for('vgg16.prototxt', precision)
+        setup_targets(eng, ora, np.random.RandomState(4), H, W, c_layers, s_layers, tile=tile)
+        eng.img = eng.to_device(rand_img(np.random.RandomState(5), H, W))
+        lw = {l: 1.0 for l in ora.layers()}
+        loss, grad = eng.eval_sc_grad((8, -16), c_layers, s_layers, [], lw, {'conv3_2': 0.05},
+                                      {l: 1 / 3 for l in s_layers}, {}, tile)
+        torch.cuda.synchronize()
+        results.append((float(loss), grad.clone()))
+    for loss, grad in results[1:]:
+        assert torch.equal(grad, results[0][1])
+        assert abs(loss - results[0][0]) <= 1e-12 * abs(results[0][0])
