@@ -43,8 +43,8 @@ GRAM_GFLOP_PER_TILE = 18.25           # F^T F and dG x F on the five style layer
 def parse_args():
     p = argparse.ArgumentParser()
     p.add_argument('--gpus', type=int, default=1)
-    p.add_argument('--steps', type=int, default=10)
-    p.add_argument('--warmup', type=int, default=3)
+    p.add_argument('--steps', type=int, default=50)
+    p.add_argument('--warmup', type=int, default=5)
     p.add_argument('--impl', default='engine', choices=['engine', 'reference'])
     p.add_argument('--precision', default='fp16', choices=['bf16', 'fp16', 'fp32'])
     p.add_argument('--size', type=int, default=2048)
@@ -77,7 +77,7 @@ class CpuReference:
     """One tile-evaluation of the reference's path (forward, losses, backward incl. the dW Caffe
     computes and discards) + the full-image regularisers/Adam, on the host cores."""
 
-    def __init__(self, a):
+    def __init__(self, a, crop=None):
         from oracle import numeric as on
         from oracle.caffe_net import he_normal_weights, model_layers
         from oracle.optimizers import Adam
@@ -87,7 +87,10 @@ class CpuReference:
         model = 'vgg19.prototxt'
         params = he_normal_weights(model_layers(model))
         self.ora = ora = OracleModel(model, params, compute_weight_grads=True)
+        # the sampled unit: one tile, or (to bound the run time) a crop x crop corner of one
         t = min(a.tile_size, a.size)
+        self.crop = t = min(t, crop) if crop else t
+        self.tile_px = min(a.tile_size, a.size)
         content = to_params(synthetic_rgb(1, a.size)[:t, :t])
         style = to_params(synthetic_rgb(2, a.size)[:t, :t])
         np.random.seed(0)
@@ -126,19 +129,31 @@ class CpuReference:
         return time.perf_counter() - t0
 
     def iteration_seconds(self, t_tile, t_tail):
-        return self.ntiles * t_tile + t_tail
+        """Seconds per iteration from the time of one sampled unit (work is linear in pixels)."""
+        return self.ntiles * (self.tile_px / self.crop) ** 2 * t_tile + t_tail
 
     def sample_text(self, n):
-        return ('%d of the %d tile-evaluations of one iteration (512x512 VGG-19 forward + losses + '
-                'backward incl. dW, as Caffe does) timed and scaled x%d, plus one full-image '
-                'regulariser+Adam pass; numpy/OpenBLAS oracle port' % (n, self.ntiles, self.ntiles))
+        unit = ('%dx%d tile-evaluation' % (self.crop, self.crop) if self.crop == self.tile_px else
+                '%dx%d corner of one %dx%d tile-evaluation' % (self.crop, self.crop, self.tile_px,
+                                                              self.tile_px))
+        return ('%d x one %s (VGG-19 forward + losses + backward incl. dW, as Caffe does) timed and '
+                'scaled to the %d tiles of an iteration (x%d in pixels), plus one full-image '
+                'regulariser+Adam pass; numpy/OpenBLAS oracle port' %
+                (n, unit, self.ntiles, round(self.ntiles * (self.tile_px / self.crop) ** 2)))
 
 
 def run_reference(a):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
+    # size the per-step sample so that warm-up + K steps stay within ~3 minutes on this host
     ref = CpuReference(a)
+    t_probe = ref.tile_eval()
+    crop = ref.crop
+    while crop > 64 and (a.steps + a.warmup) * t_probe * (crop / ref.tile_px) ** 2 > 180.0:
+        crop //= 2
+    if crop != ref.crop:
+        ref = CpuReference(a, crop=crop)
     t_tail = ref.full_image_tail()
     for _ in range(a.warmup):
         ref.tile_eval()
@@ -164,45 +179,74 @@ def run_reference(a):
 # clocks
 # =======================================================================================================
 class ClockSampler:
+    """SM clock and throttle reasons sampled DURING the timed region: NVML polled every few
+    milliseconds from a thread (the timed region is ~0.1-1 s), nvidia-smi -lms as a fallback."""
     FIELDS = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
               'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
               'clocks_event_reasons.sw_power_cap')
+    REASONS = (('hw_slowdown', 0x8), ('hw_thermal_slowdown', 0x40), ('sw_thermal_slowdown', 0x20),
+               ('sw_power_cap', 0x4))
 
     def __init__(self, index):
-        self.rows, self.proc = [], None
+        self.rows, self.proc, self.nvml, self.stop_flag = [], None, None, False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml, self.handle = pynvml, pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(
                 ['nvidia-smi', '-i', str(index), '--query-gpu=' + self.FIELDS,
-                 '--format=csv,noheader,nounits', '-lms', '100'],
+                 '--format=csv,noheader,nounits', '-lms', '20'],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except OSError:
             self.proc = None
 
+    def _poll(self):
+        n = self.nvml
+        while not self.stop_flag:
+            try:
+                mhz = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+                try:
+                    mask = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+                except Exception:
+                    mask = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+                self.rows.append((time.perf_counter(), mhz, mask))
+            except Exception:
+                pass
+            time.sleep(0.004)
+
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(',')]))
-
-    def stop(self, t0, t1):
-        if self.proc is None:
-            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
-        time.sleep(0.15)
-        self.proc.terminate()
-        rows = [r for t, r in self.rows if t0 <= t <= t1] or [r for _, r in self.rows[-3:]]
-        sm, mx, reasons = [], [], set()
-        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        for r in rows:
+            r = [c.strip() for c in line.split(',')]
             try:
-                sm.append(float(r[0])), mx.append(float(r[1]))
+                mask = sum(bit for (name, bit), v in zip(self.REASONS, r[3:7])
+                           if v.lower().startswith('active'))
+                self.max_mhz = float(r[1])
+                self.rows.append((time.perf_counter(), float(r[0]), mask))
             except (ValueError, IndexError):
                 continue
-            for name, v in zip(names, r[3:7]):
-                if v.lower().startswith('active'):
-                    reasons.add(name)
+
+    def stop(self, t0, t1):
+        self.stop_flag = True
+        if self.nvml is None and self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['no NVML / nvidia-smi']}
+        if self.proc is not None:
+            time.sleep(0.05)
+            self.proc.terminate()
+        rows = [r for r in self.rows if t0 <= r[0] <= t1] or self.rows[-3:]
+        reasons = sorted({name for _, _, mask in rows for name, bit in self.REASONS if mask & bit})
+        sm = [r[1] for r in rows]
         return {'sm_mhz': float(np.median(sm)) if sm else None,
-                'sm_max_mhz': max(mx) if mx else None, 'reasons': sorted(reasons),
-                'samples': len(sm)}
+                'sm_max_mhz': getattr(self, 'max_mhz', None), 'reasons': reasons,
+                'samples': len(sm), 'source': 'nvml' if self.nvml is not None else 'nvidia-smi'}
 
 
 # =======================================================================================================
