@@ -329,17 +329,30 @@ def run_engine(a):
             host_loss = torch.empty(1, dtype=torch.float64).pin_memory()
             host_params.copy_(eng.img)
 
+        copy_stream = torch.cuda.Stream()
+        ev_step, ev_avg = torch.cuda.Event(), torch.cuda.Event()
+        ev_avg.record()
+
         def e2e_step():
+            main = torch.cuda.current_stream()
             if rank == 0:
                 eng.img.copy_(host_params, non_blocking=True)        # H2D: this step's image
+                main.wait_event(ev_avg)      # the previous iterate has left the device buffer
             if world > 1:
                 dist.broadcast(eng.img, src=0)
             avg, loss = st.step()
             if rank == 0:
-                host_avg.copy_(avg, non_blocking=True)               # D2H: averaged iterate
+                # the averaged iterate goes out on a second stream: its D2H (full duplex with the
+                # next step's H2D) overlaps the start of the next step; everything is inside the
+                # timed region, which ends with a device-wide synchronisation
+                ev_step.record(main)
+                copy_stream.wait_event(ev_step)
+                with torch.cuda.stream(copy_stream):
+                    host_avg.copy_(avg, non_blocking=True)           # D2H: averaged iterate
+                    ev_avg.record(copy_stream)
                 host_params.copy_(eng.img, non_blocking=True)        # D2H: updated parameters
                 host_loss.copy_(loss, non_blocking=True)             # D2H: loss
-            torch.cuda.current_stream().synchronize()
+            main.synchronize()
         for _ in range(2):
             e2e_step()
         ms_e2e = timed(e2e_step, a.steps)

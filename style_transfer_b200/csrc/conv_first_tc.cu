@@ -294,7 +294,7 @@ int conv_first_fwd_tc(TcContext& tc, const TcWeights& w, const ImageBatch& img, 
   a.img = img, a.h = h, a.w = wd, a.tiles_x = cdiv(wd, 128);
   a.num_tiles = img.nb * h * a.tiles_x;
   a.wk = w.fwd, a.bias = bias, a.out = out;
-  const int grid = a.num_tiles < tc.sm_count * 6 ? a.num_tiles : tc.sm_count * 6;
+  const int grid = a.num_tiles < tc.sm_count * 8 ? a.num_tiles : tc.sm_count * 8;   // 8 x 64 TMEM columns
   TimerScope ts(s, kTimeConvSimt, 18.0 * 3 * kFirstCout * h * wd * img.nb);
   ST_LAUNCH(conv_first_tc_kernel, grid, kFirstThreads, 0, s, a);
   return ST_OK;

@@ -92,7 +92,7 @@ __device__ __forceinline__ TvTerm tv_term(float xc, float xr, float xd, float be
 // memory once; index arithmetic uses FastDiv (the first version spent 760 instructions per pixel on
 // seven divisions and 64-bit div/mod: instruction-bound at 4 % of the HBM bandwidth).  When `packed` is given the tiled gradient is
 // gathered from the all-gather buffer in the same pass (st_unpack_grad fused in).
-constexpr int kRTW = 32, kRTH = 8;
+constexpr int kRTW = 32, kRTH = 32, kRThreads = 256, kRRows = kRTH / (kRThreads / kRTW);   // 4 rows / thread
 
 struct UnpackGeom {
   int roll_y, roll_x;          // reduced to [0, H) x [0, W)
@@ -104,16 +104,19 @@ struct RegTiles {
   FastDiv div_tiles_x, div_plane;    // by tiles_x and by tiles_x * tiles_y
 };
 
-__global__ void __launch_bounds__(kRTW* kRTH)
+__global__ void __launch_bounds__(kRThreads)
 regularizers_kernel(const float* __restrict__ img, int H, int W, float m0, float m1, float m2,
                     float tv_w, float tv_beta, float p_w, float p_pow,
                     const float* __restrict__ aux, float aux_w, int roll_y, int roll_x,
                     double* loss_accum, float* __restrict__ grad,
                     const float* __restrict__ packed, UnpackGeom ug, RegTiles rt, ReduceScratch rs) {
   __shared__ float xs[kRTH + 2][kRTW + 2];       // scaled pixels, origin (y0-1, x0-1)
-  const int tx = threadIdx.x % kRTW, ty = threadIdx.x / kRTW;
+  const int tx = threadIdx.x % kRTW, ty0 = threadIdx.x / kRTW;
   const int num_tiles = rt.num_tiles;
   const bool do_tv = tv_w != 0.f;
+  // img / 127.5 as a multiplication by the rounded reciprocal: within 1 ulp of the reference's
+  // division, and the IEEE division sequence was a fifth of this kernel's issue slots
+  const float inv = 1.f / 127.5f;
   double v[1] = {0.0};
   float part = 0.f;
   int since_flush = 0;
@@ -125,18 +128,28 @@ regularizers_kernel(const float* __restrict__ img, int H, int W, float m0, float
     const float* pl = img + (size_t)c * H * W;
     if (do_tv) {
       __syncthreads();                                      // previous tile's readers are done
-      for (int i = threadIdx.x; i < (kRTH + 2) * (kRTW + 2); i += kRTW * kRTH) {
-        const int r = i / (kRTW + 2), q = i % (kRTW + 2);
+      for (int i = threadIdx.x; i < (kRTH + 2) * (kRTW + 2); i += kRThreads) {
+        const int r = i / (kRTW + 2), q = i - r * (kRTW + 2);
         int yy = y0 - 1 + r, xx = x0 - 1 + q;               // periodic (num_utils.py:150-162)
         if (yy < 0 || yy >= H) yy = wrap(yy, H);
         if (xx < 0 || xx >= W) xx = wrap(xx, W);
-        // a division, not a multiplication by 1/127.5: the reference computes img / 127.5
-        xs[r][q] = pl[(size_t)yy * W + xx] / 127.5f;
+        xs[r][q] = pl[(size_t)yy * W + xx] * inv;
       }
       __syncthreads();
     }
-    const int x = x0 + tx, y = y0 + ty;
-    if (x < W && y < H) {
+    const int x = x0 + tx;
+    // column part of the gradient-tile lookup: the same for the four rows of this thread
+    int xr = 0, txx = 0;
+    if (packed != nullptr) {
+      xr = x + ug.roll_x;
+      xr = xr >= W ? xr - W : xr;
+      txx = min((int)ug.div_tw.div(xr), ug.ntx - 1);
+    }
+    const float mean = c == 0 ? m0 : (c == 1 ? m1 : m2);
+#pragma unroll
+    for (int k = 0; k < kRRows; ++k) {
+      const int ty = ty0 + k * (kRThreads / kRTW), y = y0 + ty;
+      if (x >= W || y >= H) continue;
       const size_t i = ((size_t)c * H + y) * W + x;
       const float raw = pl[(size_t)y * W + x];
       float g = 0.f, l = 0.f;
@@ -150,13 +163,15 @@ regularizers_kernel(const float* __restrict__ img, int H, int W, float m0, float
         l += tv_w * t0.pw;
       }
       if (p_w != 0.f) {
-        const float mean = c == 0 ? m0 : (c == 1 ? m1 : m2);
-        const float a = (raw + mean - 127.5f) / 127.5f;
+        const float a = (raw + mean - 127.5f) * inv;
         const float mag = fabsf(a), sgn = a > 0.f ? 1.f : (a < 0.f ? -1.f : 0.f);
         if (p_pow == 1.f) {
           l += p_w * mag, g += p_w * sgn;
         } else if (p_pow == 2.f) {
           l += p_w * a * a, g += p_w * 2.f * a;
+        } else if (p_pow == 6.f) {                          // the reference's default
+          const float a2 = a * a, m5 = a2 * a2 * mag;
+          l += p_w * m5 * mag, g += p_w * 6.f * sgn * m5;
         } else {
           const int ip = (int)p_pow;
           const float mp1 =
@@ -166,15 +181,14 @@ regularizers_kernel(const float* __restrict__ img, int H, int W, float m0, float
       }
       if (aux != nullptr) {
         const int ya = wrap(y + roll_y, H), xa = wrap(x + roll_x, W);
-        const float d = (raw - aux[((size_t)c * H + ya) * W + xa]) * (1.f / 127.5f);
+        const float d = (raw - aux[((size_t)c * H + ya) * W + xa]) * inv;
         l += aux_w * 0.5f * d * d, g += aux_w * d;
       }
       float base;
       if (packed != nullptr) {               // fused st_unpack_grad
-        int yr = y + ug.roll_y, xr = x + ug.roll_x;
-        yr = yr >= H ? yr - H : yr, xr = xr >= W ? xr - W : xr;
+        int yr = y + ug.roll_y;
+        yr = yr >= H ? yr - H : yr;
         const int tyy = min((int)ug.div_th.div(yr), ug.nty - 1);
-        const int txx = min((int)ug.div_tw.div(xr), ug.ntx - 1);
         const int t = tyy * ug.ntx + txx;
         const int slot = (int)ug.div_world.div(t), rank = t - slot * ug.world;
         const size_t pb = ((size_t)(rank * ug.tiles_per_rank + slot) * 3 + c) * ug.thmax * ug.twmax;
@@ -185,7 +199,7 @@ regularizers_kernel(const float* __restrict__ img, int H, int W, float m0, float
       grad[i] = base + g;
       part += l;
     }
-    if (++since_flush == 16) v[0] += (double)part, part = 0.f, since_flush = 0;
+    if (++since_flush == 4) v[0] += (double)part, part = 0.f, since_flush = 0;
   }
   v[0] += (double)part;
   if (grid_reduce<1>(v, rs.partials, rs.counter)) atomicAdd(loss_accum, v[0]);
@@ -204,7 +218,7 @@ static int launch_regularizers(const float* img, int H, int W, float m0, float m
   const int num_tiles = rt.num_tiles;
   const int grid = num_tiles < 148 * 8 ? num_tiles : 148 * 8;
   TimerScope ts(s, kTimeImage, 4.0 * 3 * H * W * (3 + (aux ? 1 : 0)));
-  ST_LAUNCH(regularizers_kernel, grid, kRTW * kRTH, 0, s, img, H, W, m0, m1, m2, tv_w, tv_beta, p_w,
+  ST_LAUNCH(regularizers_kernel, grid, kRThreads, 0, s, img, H, W, m0, m1, m2, tv_w, tv_beta, p_w,
             p_pow, aux, aux_w, roll_y, roll_x, loss_accum, grad, packed, ug, rt, rs);
   return ST_OK;
 }
