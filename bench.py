@@ -404,6 +404,19 @@ def run_engine(a):
                     'avg_launch_ms': d['ms_per_step'] / max(d['launch_groups_per_step'], 1),
                     'share_of_step': d['ms_per_step'] / (ms_timing / tsteps)}
 
+    # Gram kernels against the HBM roofline: algorithmic bytes = every style layer's 16-bit feature
+    # map read once (64.9 MB per 512x512 VGG-19 tile) over gram_tc_kernel + finalize time
+    roofline_gram = None
+    if breakdown['gram']['ms_per_step'] > 0 and a.tile_size == 512 and a.precision != 'fp32':
+        tiles_here = -(-(((a.size - 1) // a.tile_size + 1) ** 2) // world)
+        gbytes = 64.9e6 * tiles_here
+        ach = gbytes / (breakdown['gram']['ms_per_step'] * 1e-3) / 1e9
+        hbm = peaks.get('hbm_gbs', 6650.0)
+        roofline_gram = {'bound': 'hbm', 'kernel': 'gram_tc_kernel + gram_tc_finalize_kernel',
+                         'achieved': ach, 'peak': hbm, 'unit': 'GB/s', 'frac': ach / hbm,
+                         'traffic': None, 'algorithmic_bytes_per_step': gbytes,
+                         'peak_source': 'MEASURED_PEAKS.json hbm_gbs' if peaks else 'fallback 6650 (recipe)'}
+
     # ---- CPU baseline (rank 0, N = 1) ---------------------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
@@ -427,6 +440,7 @@ def run_engine(a):
             'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
             'dtype': {'bf16': 'bf16', 'fp16': 'f16 forward / bf16 backward', 'fp32': 'f32'}[a.precision], 'data': 'synthetic', 'config': cfg,
             'clocks': clocks, 'e2e': e2e, 'gpu_launches': launches, 'roofline': roofline,
+            'roofline_gram': roofline_gram,
             'cpu_baseline': cpu, 'breakdown': breakdown,
             'tile_eval_ms': breakdown and sum(v['ms_per_step'] for k, v in breakdown.items()
                                               if k != 'image') / cfg['tiles_per_gpu'],

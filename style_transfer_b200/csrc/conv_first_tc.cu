@@ -188,17 +188,23 @@ conv_first_tc_kernel(const FirstArgs a) {
     uint32_t kv[32];                       // 64 x 16 bit: k in [0,27) hi, [27,54) lo, rest zero
     {
       float hi[27], lo[27];
+      if (half) {
 #pragma unroll
-      for (int k = 0; k < 27; ++k) {
-        hi[k] = half ? __half2float(__float2half_rn(v[k])) : __bfloat162float(__float2bfloat16_rn(v[k]));
-        lo[k] = v[k] - hi[k];
+        for (int k = 0; k < 27; ++k) hi[k] = __half2float(__float2half_rn(v[k])), lo[k] = v[k] - hi[k];
+      } else {
+#pragma unroll
+        for (int k = 0; k < 27; ++k)
+          hi[k] = __bfloat162float(__float2bfloat16_rn(v[k])), lo[k] = v[k] - hi[k];
       }
+      float xk[64];
 #pragma unroll
-      for (int k = 0; k < 32; ++k) {
-        const int k0 = 2 * k, k1 = 2 * k + 1;
-        const float x0 = k0 < 27 ? hi[k0] : (k0 < 54 ? lo[k0 - 27] : 0.f);
-        const float x1 = k1 < 27 ? hi[k1] : (k1 < 54 ? lo[k1 - 27] : 0.f);
-        kv[k] = pack16(x0, x1, half);
+      for (int k = 0; k < 64; ++k) xk[k] = k < 27 ? hi[k] : (k < 54 ? lo[k - 27] : 0.f);
+      if (half) {                            // one uniform branch, not one per packed word
+#pragma unroll
+        for (int k = 0; k < 32; ++k) kv[k] = pack16(xk[2 * k], xk[2 * k + 1], true);
+      } else {
+#pragma unroll
+        for (int k = 0; k < 32; ++k) kv[k] = pack16(xk[2 * k], xk[2 * k + 1], false);
       }
     }
     uint8_t* row = a_s + tid * 128;
@@ -229,17 +235,21 @@ conv_first_tc_kernel(const FirstArgs a) {
     for (int cc = 0; cc < 2; ++cc) {
       uint32_t r[32];
       tmem_ld32(taddr + cc * 32, r);
+      float f[32];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        float f[8];
+      for (int i = 0; i < 32; ++i) f[i] = fmaxf(__uint_as_float(r[i]) + bias_s[cc * 32 + i], 0.f);
+      uint32_t pw[16];
+      if (half) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
-          f[i] = fmaxf(__uint_as_float(r[8 * j + i]) + bias_s[cc * 32 + 8 * j + i], 0.f);
-        uint4 pk;
-        pk.x = pack16(f[0], f[1], half), pk.y = pack16(f[2], f[3], half);
-        pk.z = pack16(f[4], f[5], half), pk.w = pack16(f[6], f[7], half);
-        *reinterpret_cast<uint4*>(row + (((cc * 4 + j) ^ (tid & 7)) << 4)) = pk;
+        for (int i = 0; i < 16; ++i) pw[i] = pack16(f[2 * i], f[2 * i + 1], true);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) pw[i] = pack16(f[2 * i], f[2 * i + 1], false);
       }
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        *reinterpret_cast<uint4*>(row + (((cc * 4 + j) ^ (tid & 7)) << 4)) =
+            make_uint4(pw[4 * j], pw[4 * j + 1], pw[4 * j + 2], pw[4 * j + 3]);
     }
     tc_fence_before();
     __syncthreads();

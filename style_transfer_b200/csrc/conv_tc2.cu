@@ -537,12 +537,21 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constan
           // registers -> swizzled staging tile [128 rows][128 B] (SWIZZLE_128B, as TMA expects)
           uint8_t* row = stage_out + (size_t)m * 128;
 #pragma unroll
+          // one warp-uniform branch per chunk (a branch inside every pack cost the short-K
+          // kernels half their speed)
+          uint32_t pw[16];
+          if (out_half) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) pw[i] = pack16(v[2 * i], v[2 * i + 1], true);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) pw[i] = pack16(v[2 * i], v[2 * i + 1], false);
+          }
+#pragma unroll
           for (int j = 0; j < 4; ++j) {
-            uint4 pk;
-            pk.x = pack16(v[8 * j], v[8 * j + 1], out_half), pk.y = pack16(v[8 * j + 2], v[8 * j + 3], out_half);
-            pk.z = pack16(v[8 * j + 4], v[8 * j + 5], out_half), pk.w = pack16(v[8 * j + 6], v[8 * j + 7], out_half);
             const int chunk = hh * 4 + j;
-            *reinterpret_cast<uint4*>(row + ((chunk ^ (m & 7)) << 4)) = pk;
+            *reinterpret_cast<uint4*>(row + ((chunk ^ (m & 7)) << 4)) =
+                make_uint4(pw[4 * j], pw[4 * j + 1], pw[4 * j + 2], pw[4 * j + 3]);
           }
         }
         if (g == BN / 64 - 1) {
@@ -580,10 +589,23 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constan
               const uint4 raw =
                   *reinterpret_cast<const uint4*>(stage_out + mm * 128 + ((j ^ (mm & 7)) << 4));
               const uint32_t w4[4] = {raw.x, raw.y, raw.z, raw.w};
+              float xv[8];
+              if (out_half) {                                    // one uniform branch per load
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float2 t2 = unpack16(w4[e], true);
+                  xv[2 * e] = t2.x, xv[2 * e + 1] = t2.y;
+                }
+              } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float2 t2 = unpack16(w4[e], false);
+                  xv[2 * e] = t2.x, xv[2 * e + 1] = t2.y;
+                }
+              }
 #pragma unroll
               for (int e = 0; e < 8; ++e) {
-                const float2 x2 = unpack16(w4[e >> 1], out_half);
-                const float x = (e & 1) ? x2.y : x2.x;
+                const float x = xv[e];
                 if (a.pool_mode == 1) {
                   if (x > best[e]) best[e] = x, code[e] = (uint32_t)d;       // strict: first max wins
                 } else {
@@ -594,6 +616,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constan
             }
             const int pyo = (y0 >> 1) + pr, pxo = (x0 >> 1) + pc;
             uint32_t ow[4], mk[2] = {0u, 0u};
+            float po[8];
 #pragma unroll
             for (int e = 0; e < 8; e += 2) {
               float o0, o1;
@@ -605,7 +628,14 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constan
                 const float inv = (float)(cnt > 0 ? cnt : 1);
                 o0 = sum[e] / inv, o1 = sum[e + 1] / inv;
               }
-              ow[e >> 1] = pack16(o0, o1, out_half);
+              po[e] = o0, po[e + 1] = o1;
+            }
+            if (out_half) {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) ow[e] = pack16(po[2 * e], po[2 * e + 1], true);
+            } else {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) ow[e] = pack16(po[2 * e], po[2 * e + 1], false);
             }
 #pragma unroll
             for (int e = 0; e < 8; ++e) mk[e >> 2] |= code[e] << (8 * (e & 3));

@@ -302,7 +302,9 @@ template <int C>
 int gram_splits(int hw) {
   const int kb_total = cdiv(hw, 64);
   int nsplit = C <= 64 ? 64 : (C <= 128 ? 32 : (C <= 256 ? 16 : 8));
-  nsplit = nsplit > kb_total ? kb_total : nsplit;
+  // at least 8 k-blocks (512 pixels) per split: shorter streams are all pipeline fill and drain
+  nsplit = nsplit > kb_total / 8 ? kb_total / 8 : nsplit;
+  nsplit = nsplit < 1 ? 1 : nsplit;
   const int kb_per_split = cdiv(kb_total, nsplit);
   return cdiv(kb_total, kb_per_split);
 }
