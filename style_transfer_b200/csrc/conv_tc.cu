@@ -22,6 +22,8 @@
 #include <cuda_fp16.h>
 
 #include <cstdlib>
+#include <map>
+#include <mutex>
 #include <vector>
 
 #include "style_b200.h"
@@ -427,12 +429,7 @@ int launch(TcContext& tc, const CUtensorMap& map_w, const T* in, T* out, const T
     if (rc != ST_OK) return rc;
   }
   auto kern = conv3x3_tc_kernel<T, BN>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    ST_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 Cfg::kSmemBytes));
-    attr_set = true;
-  }
+  ST_CUDA(tc_allow_smem(kern, Cfg::kSmemBytes));
   const int tiles = a.tiles_x * a.tiles_y * a.tiles_n;
   const int grid = tiles < tc.sm_count ? tiles : tc.sm_count;
   TimerScope ts(s, kTimeConvTc, 18.0 * a.cin * a.cout * a.h * a.w);
@@ -474,6 +471,20 @@ int pack_one(const TcContext& tc, const float* w, int cin, int cout, bool backwa
 
 }  // namespace
 
+cudaError_t tc_allow_smem_impl(const void* kernel, int bytes) {
+  static std::mutex mu;
+  static std::map<const void*, uint64_t> done;      // kernel -> bit mask of devices already set
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  std::lock_guard<std::mutex> lock(mu);
+  uint64_t& mask = done[kernel];
+  if (dev < 64 && (mask >> dev) & 1) return cudaSuccess;
+  e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess && dev < 64) mask |= (uint64_t)1 << dev;
+  return e;
+}
+
 int tc_init(TcContext& tc, int sm_count) {
   tc.sm_count = sm_count;
   if (getenv("ST_DISABLE_TC") != nullptr) {   // debugging aid: bf16 storage with the SIMT convolution
@@ -490,6 +501,10 @@ int tc_init(TcContext& tc, int sm_count) {
   tc.encode_fn = fn;
   tc.enabled = true;
   tc.pair_kernel = getenv("ST_CONV_V1") == nullptr;
+  tc.resident_weights = getenv("ST_TC_NO_RESB") == nullptr;
+  tc.defer_scale = getenv("ST_NO_DEFER") == nullptr;
+  tc.pool_fusion = getenv("ST_NO_POOL_FUSION") == nullptr;
+  if (const char* f = getenv("ST_TC_BN")) tc.force_bn = atoi(f);
   return ST_OK;
 }
 

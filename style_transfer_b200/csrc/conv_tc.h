@@ -24,11 +24,22 @@ struct TcWeights {
 struct TcContext {
   bool enabled = false;
   bool pair_kernel = true;     // conv_tc2.cu (cta_group::2); ST_CONV_V1=1 selects the single-CTA kernel
+  // debugging switches, read once from the environment in tc_init
+  bool resident_weights = true;   // ST_TC_NO_RESB=1 disables
+  bool defer_scale = true;        // ST_NO_DEFER=1 disables
+  bool pool_fusion = true;        // ST_NO_POOL_FUSION=1 disables
+  int force_bn = 0;               // ST_TC_BN=64|128|256
   int sm_count = 0;
   void* encode_fn = nullptr;   // cuTensorMapEncodeTiled, fetched through cudaGetDriverEntryPoint
 };
 
 int tc_init(TcContext& tc, int sm_count);
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per (kernel, device): set it once for each.
+cudaError_t tc_allow_smem_impl(const void* kernel, int bytes);
+template <typename K>
+inline cudaError_t tc_allow_smem(K kernel, int bytes) {
+  return tc_allow_smem_impl(reinterpret_cast<const void*>(kernel), bytes);
+}
 void tc_destroy(TcContext& tc);
 int tc_pack_weights(TcContext& tc, TcWeights& w, const float* w_oihw_host, int cin, int cout,
                     bool fwd_half);

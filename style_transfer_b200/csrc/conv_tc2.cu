@@ -735,11 +735,7 @@ int launch2r(TcContext& tc, const void* in, const void* wk, int wk_rows,
     if (rc != ST_OK) return rc;
   }
   auto kern = conv_tc2_kernel<BN, TAPS, EPI, RESB>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    ST_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
-  }
+  ST_CUDA(tc_allow_smem(kern, 227 * 1024));
   a.resb_bytes = RESB ? TAPS * (a.cin / 64) * Cfg::kBBytes : 0;
   const int smem_bytes = RESB ? Cfg::kFixedBytes + a.resb_bytes : Cfg::kSmemBytes;
   const int tiles = a.tiles_x * a.tiles_y * a.tiles_n * a.nb;
@@ -760,7 +756,7 @@ int launch2(TcContext& tc, const void* in, const void* wk, int wk_rows, void* ou
   if constexpr (BN <= 128) {
     using CfgR = Cfg2<BN, TAPS, true, EPI == kEpiFwdPool>;
     const long res = (long)TAPS * (a.cin / 64) * CfgR::kBBytes;
-    if (a.cout == BN && !a.w_batched && res <= CfgR::kResMax && getenv("ST_TC_NO_RESB") == nullptr)
+    if (a.cout == BN && !a.w_batched && res <= CfgR::kResMax && tc.resident_weights)
       return launch2r<BN, TAPS, EPI, true>(tc, in, wk, wk_rows, out, pool_out, a, s);
   }
   return launch2r<BN, TAPS, EPI, false>(tc, in, wk, wk_rows, out, pool_out, a, s);
@@ -770,10 +766,8 @@ int launch2(TcContext& tc, const void* in, const void* wk, int wk_rows, void* ou
 // weight traffic per flop, narrow ones fill the machine on the small feature maps.
 int choose_bn(const TcContext& tc, int nb, int h, int w, int cout) {
   const int px_tiles = cdiv(w, kBW) * cdiv(h, 2 * kBH) * nb, pairs = tc.sm_count / 2;
-  if (const char* f = getenv("ST_TC_BN")) {
-    const int bn = atoi(f);
-    if ((bn == 64 || bn == 128 || bn == 256) && cout % bn == 0) return bn;
-  }
+  if ((tc.force_bn == 64 || tc.force_bn == 128 || tc.force_bn == 256) && cout % tc.force_bn == 0)
+    return tc.force_bn;
   for (int bn = 256; bn > 64; bn >>= 1) {
     if (cout % bn != 0) continue;
     const long tiles = (long)px_tiles * (cout / bn);

@@ -212,7 +212,7 @@ constexpr int kStatStride = 8;   // doubles per batch tile in ctx->scalars:
 // map is only written when somebody else needs it (`need_full`: loss layers, requested features).
 template <typename T>
 int fused_pool_layer(const st_ctx* ctx, int i, int last_layer) {
-  if (sizeof(T) != 2 || getenv("ST_NO_POOL_FUSION") != nullptr) return -1;
+  if (sizeof(T) != 2 || !ctx->tc.pool_fusion) return -1;
   const LayerRt& l = ctx->layers[i];
   if (l.bottom == 0 || i + 1 > last_layer) return -1;
   const LayerRt& p = ctx->layers[i + 1];
@@ -364,7 +364,7 @@ int build_injection(st_ctx* ctx, const st_loss_spec& sp, const Dims& d, const Ba
       // the scale-and-copy pass over S can be skipped when S is this blob's whole injection and a
       // kernel epilogue (not a TMA operand load) consumes it
       const bool defer = on_tc && !sp.use_content && !sp.use_dd && ctx->n_styles == 1 && !is_deepest &&
-                         getenv("ST_NO_DEFER") == nullptr;
+                         ctx->tc.defer_scale;
       if (on_tc) {
         if constexpr (sizeof(TA) == 2) {
           int per_tile = 0;

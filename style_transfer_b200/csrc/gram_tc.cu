@@ -333,12 +333,7 @@ int launch_gram(TcContext& tc, const void* f, bool half, int nb, int hw, float* 
   a.nsplit = gram_splits<C>(hw);
   a.kb_per_split = cdiv(a.kb_total, a.nsplit);
   auto kern = gram_tc_kernel<C>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    ST_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 Cfg::kSmemBytes));
-    attr_set = true;
-  }
+  ST_CUDA(tc_allow_smem(kern, Cfg::kSmemBytes));
   TimerScope ts(s, kTimeGram, 2.0 * C * C * hw * nb);
   ST_LAUNCH(kern, dim3(a.nsplit * Cfg::kMBlocks, nb), kGThreads, Cfg::kSmemBytes, s, map_f, a);
   ST_LAUNCH(gram_tc_finalize_kernel, dim3(cdiv(C, 128), C, nb), 128, 0, s, part, a.nsplit, C,
