@@ -25,6 +25,13 @@ import sys
 import threading
 import time
 
+# torchrun exports OMP_NUM_THREADS=1; the CPU legs (reference arm, cpu_baseline) are meant to use
+# every host core, and OpenBLAS reads the variable when numpy loads -- so fix it before that import.
+_HOST_CORES = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1)
+if '--impl' in sys.argv and 'reference' in sys.argv or int(os.environ.get('WORLD_SIZE', '1')) == 1:
+    for _v in ('OMP_NUM_THREADS', 'OPENBLAS_NUM_THREADS', 'MKL_NUM_THREADS'):
+        os.environ[_v] = str(_HOST_CORES)
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -107,7 +114,16 @@ class CpuReference:
         self.sw = {l: 1.0 / len(STYLE_LAYERS) for l in STYLE_LAYERS}
         self.adam = Adam(self.full.copy(), step_size=15.0, bp1=1 - 1 / 20.0, decay=0.05, power=0.5)
         self.ntiles = ((a.size - 1) // a.tile_size + 1) ** 2
-        self.cores = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else os.cpu_count()
+        # threads the BLAS behind numpy / scipy will really use
+        self.cores = _HOST_CORES
+        try:
+            from threadpoolctl import threadpool_info, threadpool_limits
+            threadpool_limits(limits=_HOST_CORES)
+            blas = [p['num_threads'] for p in threadpool_info() if p.get('user_api') == 'blas']
+            if blas:
+                self.cores = max(blas)
+        except Exception:
+            pass
 
     def tile_eval(self):
         t0 = time.perf_counter()
