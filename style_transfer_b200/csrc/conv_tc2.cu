@@ -9,21 +9,30 @@
 // that traffic ~3.5x:
 //   * two CTAs of a cluster form one tcgen05 `cta_group::2` MMA: 256 pixels x BN channels per
 //     instruction, each CTA staging only its own 128 pixels of A and HALF of the weight tile B;
-//   * the A operand of one 64-channel block is loaded once per tile as three x-shifted copies of
-//     the (16+2) x 8 pixel halo window; the nine taps are then nine shared-memory descriptors into
-//     those copies (a y shift is a whole number of 1024-byte swizzle atoms because a tile row is
-//     exactly 8 pixels x 128 bytes), so A moves 3 x 18/16 instead of 9 times.
+//   * the A operand of one 64-channel block is loaded ONCE per tile: the (16+2) x (8+2) pixel halo
+//     window, one TMA box, pixel (y, x) of the window at byte (y*10 + x)*128 of the stage.  The nine
+//     taps are nine shared-memory descriptors into that one copy: start address shifted by
+//     (dy*10 + dx)*128 bytes, 8-row groups 10*128 = 1280 bytes apart (the stride-byte-offset of the
+//     descriptor).  Neither is a multiple of the 1024-byte swizzle period, and that is fine: the
+//     SWIZZLE_128B XOR is a function of the absolute shared-memory address bits for TMA and for
+//     tcgen05.mma alike (descriptor base-offset field left 0; measured on B200 with
+//     tools/experiments/desc_offset.cu, profiles/r01_desc_offset.md).  A moves 18*10/(16*8) = 1.4
+//     times per 64-channel block instead of 9 (one load per tap) or 3.4 (three x-shifted copies, the
+//     previous version of this kernel).
 //
 // Work split: pair tile = 32 rows x 8 columns of pixels (CTA rank r owns rows [16r, 16r+16)) x BN
 // output channels; persistent pairs walk the tile list round-robin.  K loop: 64-channel blocks,
 // inside each the 9 taps, inside each 4 MMAs of K = 16.
 //
-// Warps (224 threads per CTA):
+// Warps (352 threads per CTA):
 //   0      A producer   (TMA, one lane)            both CTAs
 //   1      MMA issuer   (one lane, leader CTA only) + TMEM allocation (both CTAs)
-//   2..5   epilogue     TMEM -> registers -> bias/ReLU | mask/inject | abs-sum -> swizzled smem
-//                       -> TMA store; accumulators are double-buffered in TMEM
-//   6      B producer   (TMA, one lane)            both CTAs
+//   2      B producer   (TMA, one lane)            both CTAs
+//   3..10  epilogue     TMEM -> registers -> bias/ReLU | mask/inject | abs-sum -> swizzled smem
+//                       -> TMA store; accumulators are double-buffered in TMEM.  Two warps per TMEM
+//                       lane quadrant (warp % 4), each taking one 32-channel half of every
+//                       64-channel group: with four warps the BN = 64 layers (36 MMAs of 32 cycles
+//                       per tile) were paced by their epilogue, not by the tensor pipe
 // All "full" barriers live in the leader CTA (TMA of the peer signals them through the cluster
 // address); "empty" barriers are signalled in both CTAs by multicast tcgen05.commit.
 #include <cuda.h>
@@ -40,8 +49,8 @@ namespace st {
 namespace {
 
 constexpr int kBH = 16, kBW = 8;          // pixels per CTA tile: 16 rows x 8 columns = 128 = TMEM lanes
-constexpr int kRowBytes = kBW * 128;      // one tile row of one 64-channel block: one swizzle atom
-constexpr int kThreads2 = 224;
+constexpr int kThreads2 = 352;
+constexpr int kEpiWarp0 = 3;             // first of the eight epilogue warps
 constexpr uint32_t kSpin = 1u << 24;
 constexpr int kOutStageBytes = 128 * 128; // 128 pixels x 64 channels bf16
 constexpr int kTailBytes = 3072;          // barriers (256 B) + tmem slot + bias copy (2 KB)
@@ -210,10 +219,11 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
       : "memory");
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
-// K-major SWIZZLE_128B shared-memory matrix descriptor: 128-byte rows, 8-row groups 1024 B apart.
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+// K-major SWIZZLE_128B shared-memory matrix descriptor: 128-byte rows, 8-row groups `sbo` bytes
+// apart (1024 for a dense tile; 1280 for the 10-pixel-wide halo window, see the file comment).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t sbo = 1024) {
   return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) |
-         ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+         ((uint64_t)(sbo >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
 }
 
 struct Tc2Args {
@@ -254,11 +264,12 @@ __device__ __forceinline__ TileCoord decode_tile(const Tc2Args& a, int tile, int
 template <int BN, int TAPS, bool RESB = false, bool POOL = false>
 struct Cfg2 {
   static constexpr int kHaloRows = TAPS == 9 ? kBH + 2 : kBH;
-  static constexpr int kVariants = TAPS == 9 ? 3 : 1;
-  static constexpr int kAVarBytes = kHaloRows * kRowBytes;
-  static constexpr int kABytes = kVariants * kAVarBytes;         // 54 KB (3x3) / 16 KB (1x1)
+  static constexpr int kWinW = TAPS == 9 ? kBW + 2 : kBW;        // pixels per window row
+  static constexpr int kAPitch = kWinW * 128;                    // bytes between 8-pixel row groups
+  static constexpr int kALoadBytes = kHaloRows * kAPitch;        // 22.5 KB (3x3) / 16 KB (1x1)
+  static constexpr int kABytes = (kALoadBytes + 1023) / 1024 * 1024;   // stages stay 1024-aligned
   static constexpr int kBBytes = (BN / 2) * 128;                 // this CTA's half of the B tile
-  static constexpr int kSA = TAPS == 9 ? 2 : 4;
+  static constexpr int kSA = 4;
   static constexpr int kPoolBytes = POOL ? 2 * kPoolStageBytes : 0;
   static constexpr int kOutBytes = 2 * kOutStageBytes + kPoolBytes;
   static constexpr int kSBRaw = (kSmemBudget - kSA * kABytes - kOutBytes) / kBBytes;
@@ -309,7 +320,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constan
     prefetch_tmap(&map_in), prefetch_tmap(&map_w), prefetch_tmap(&map_out);
     for (int i = 0; i < Cfg::kSA; ++i) mbar_init(&a_full[i], 1), mbar_init(&a_empty[i], 1);
     for (int i = 0; i < Cfg::kSB; ++i) mbar_init(&b_full[i], 1), mbar_init(&b_empty[i], 1);
-    for (int i = 0; i < 2; ++i) mbar_init(&t_full[i], 1), mbar_init(&t_empty[i], 8);
+    for (int i = 0; i < 2; ++i) mbar_init(&t_full[i], 1), mbar_init(&t_empty[i], 16);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc_pair(tmem_slot, Cfg::kTmemCols);
@@ -332,21 +343,17 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constan
         const uint32_t bar = map_to_cta(smem_u32(&a_full[stage]), 0);
         uint8_t* dst = a_base + stage * Cfg::kABytes;
         if (elect_one()) {
-          if (leader) mbar_expect_tx(&a_full[stage], 2 * Cfg::kABytes);
-          if constexpr (TAPS == 9) {
-#pragma unroll
-            for (int v = 0; v < 3; ++v)
-              tma_load_4d_pair(&map_in, bar, dst + v * Cfg::kAVarBytes, cb * 64, t.x0 + v - 1,
-                               t.y0 - 1, t.b);
-          } else {
+          if (leader) mbar_expect_tx(&a_full[stage], 2 * Cfg::kALoadBytes);
+          if constexpr (TAPS == 9)
+            tma_load_4d_pair(&map_in, bar, dst, cb * 64, t.x0 - 1, t.y0 - 1, t.b);
+          else
             tma_load_4d_pair(&map_in, bar, dst, cb * 64, t.x0, t.y0, t.b);
-          }
         }
         __syncwarp();
         if (++stage == Cfg::kSA) stage = 0, phase ^= 1;
       }
     }
-  } else if (warp == 6) {
+  } else if (warp == 2) {
     // ===================================== B producer ============================================
     if constexpr (RESB) {
       // one shot: every (channel block, tap) slab of this CTA's weight rows, one barrier
@@ -402,8 +409,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constan
             if constexpr (!RESB) mbar_wait(&b_full[sb], pb);
             tc_fence_after();
             uint32_t a_tap = a_addr;
-            if constexpr (TAPS == 9) a_tap += (tap % 3) * Cfg::kAVarBytes + (tap / 3) * kRowBytes;
-            const uint64_t da = make_smem_desc(a_tap);
+            if constexpr (TAPS == 9) a_tap += ((tap / 3) * Cfg::kWinW + (tap % 3)) * 128;
+            const uint64_t da = make_smem_desc(a_tap, Cfg::kAPitch);
             const uint64_t db = make_smem_desc(
                 smem_u32(b_base + (RESB ? (cb * TAPS + tap) : sb) * Cfg::kBBytes));
             if (elect_one()) {
@@ -427,8 +434,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constan
   } else {
     // ===================================== epilogue ==============================================
     const int q = warp & 3;                            // TMEM lane quadrant of this warp
+    const int hsel = (warp - kEpiWarp0) >> 2;          // which 32-channel half of a 64-channel group
     const int m = q * 32 + lane;                       // pixel row of the CTA tile
-    const bool issuer = threadIdx.x == 64;
+    const bool issuer = threadIdx.x == kEpiWarp0 * 32;
     const bool out_half = a.out_half != 0;
     uint32_t it = 0, store_seq = 0;
     for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
@@ -456,7 +464,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constan
           }
         }
       };
-      prefetch(0);
+      prefetch(hsel);
       float inj_sc = 1.f;
       if constexpr (EPI == kEpiBwd) {
         if (a.inj_scale != nullptr) inj_sc = __ldg(a.inj_scale + t.b);
@@ -468,12 +476,12 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constan
       if constexpr (EPI == kEpiPix) {
         // backward of the first convolution: accumulator columns 0..2 are d(loss)/d(pixel) of the
         // three image planes; written straight to the planar f32 gradient (no staging, no TMA)
-        uint32_t r[16];
-        tmem_ld16(taddr, r);
+        uint32_t r[16] = {0u, 0u, 0u};
+        if (hsel == 0) tmem_ld16(taddr, r);            // the second warp of the quadrant only arrives
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(map_to_cta(smem_u32(&t_empty[buf]), 0));
-        if (valid) {
+        if (valid && hsel == 0) {
           float* dst = a.pix + (size_t)t.b * a.pix_batch + (size_t)py * a.pix_row + px;
 #pragma unroll
           for (int ci = 0; ci < 3; ++ci) dst[(size_t)ci * a.pix_plane] = __uint_as_float(r[ci]);
@@ -484,10 +492,10 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constan
       for (int g = 0; g < BN / 64; ++g, ++store_seq) {
         uint8_t* stage_out = out_base + (store_seq & 1) * kOutStageBytes;
         if (issuer) tma_store_wait_read<1>();          // the store that used this buffer has read it
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-#pragma unroll
-        for (int hh = 0; hh < 2; ++hh) {
-          const int cc = g * 2 + hh;                   // 32-channel chunk
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        {
+          const int hh = hsel;
+          const int cc = g * 2 + hh;                   // 32-channel chunk of this warp
           uint32_t r[32];
           tmem_ld32(taddr + cc * 32, r);
           float v[32];
@@ -501,7 +509,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constan
             uint4 cm[4], ce[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) cm[i] = pm[i], ce[i] = pe[i];
-            if (cc + 1 < BN / 32) prefetch(cc + 1);
+            if (cc + 2 < BN / 32) prefetch(cc + 2);
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               const uint32_t m4[4] = {cm[i].x, cm[i].y, cm[i].z, cm[i].w};
@@ -520,23 +528,22 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constan
           } else {
 #pragma unroll
             for (int i = 0; i < 32; ++i) abs_tile += fabsf(v[i]);
-            if (hh == 1) {
-              // sum |S| over this warp's 32 rows x this 64-channel group: one slot per (pixel tile,
-              // 64-channel group, CTA, warp), added up later in slot order -- the grouping does not
-              // depend on BN or on the tile -> CTA schedule, so the sum is reproducible
+            {
+              // sum |S| over this warp's 32 rows x 32 channels: one slot per (pixel tile, 64-channel
+              // group, CTA, warp), added up later in slot order -- the grouping does not depend on
+              // BN or on the tile -> CTA schedule, so the sum is reproducible
               double x = (double)abs_tile;
 #pragma unroll
               for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
               const int m_tile = tile / a.tiles_n;
               const int g64 = n_tile * (BN / 64) + g;
               if (lane == 0)
-                a.abs_partials[(((size_t)m_tile * (a.cout >> 6) + g64) * 2 + rank) * 4 + q] = x;
+                a.abs_partials[(((size_t)m_tile * (a.cout >> 6) + g64) * 2 + rank) * 8 + hsel * 4 + q] = x;
               abs_tile = 0.f;
             }
           }
           // registers -> swizzled staging tile [128 rows][128 B] (SWIZZLE_128B, as TMA expects)
           uint8_t* row = stage_out + (size_t)m * 128;
-#pragma unroll
           // one warp-uniform branch per chunk (a branch inside every pack cost the short-K
           // kernels half their speed)
           uint32_t pw[16];
@@ -561,19 +568,18 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constan
           if (lane == 0) mbar_arrive_cluster(map_to_cta(smem_u32(&t_empty[buf]), 0));
         }
         fence_proxy_async();
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, 256;" ::: "memory");
         if constexpr (kPool) {
           // The staged tile holds complete 2x2 windows (tile origins are even).  Each thread pools
-          // two (pooled pixel, 8-channel) items: pooled values -> a second swizzled staging tile
+          // one (pooled pixel, 8-channel) item: pooled values -> a second swizzled staging tile
           // for a TMA store, one mask byte per pooled element -> global memory.
           //   max: bits 0-1 = position of the first maximum (scan order), bit 2 = maximum > 0
           //   ave: bit d = input d of the window > 0            (what the backward pass needs)
           uint8_t* pstage = out_base + 2 * kOutStageBytes + (store_seq & 1) * kPoolStageBytes;
-          const int et = threadIdx.x - 64;                       // 0..127 among the epilogue warps
+          const int et = threadIdx.x - kEpiWarp0 * 32;           // 0..255 among the epilogue warps
           const int ho = (a.h + 1) >> 1, wo = (a.w + 1) >> 1;
-#pragma unroll
-          for (int k = 0; k < 2; ++k) {
-            const int item = et + k * 128, pp = item >> 3, j = item & 7;
+          {
+            const int item = et, pp = item >> 3, j = item & 7;
             const int pr = pp >> 2, pc = pp & 3;                 // pooled row / column in the tile
             float best[8], sum[8];
             uint32_t code[8];
@@ -646,7 +652,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constan
                                         n_tile * BN + g * 64 + j * 8) = make_uint2(mk[0], mk[1]);
           }
           fence_proxy_async();
-          asm volatile("bar.sync 1, 128;" ::: "memory");
+          asm volatile("bar.sync 1, 256;" ::: "memory");
           if (issuer) {
             if (a.write_full) tma_store_4d(&map_out, stage_out, n_tile * BN + g * 64, x0, y0, t.b);
             tma_store_4d(&map_pool, pstage, n_tile * BN + g * 64, x0 >> 1, y0 >> 1, t.b);
@@ -703,7 +709,7 @@ int launch2r(TcContext& tc, const void* in, const void* wk, int wk_rows,
     const uint64_t dims[4] = {(uint64_t)a.cin, (uint64_t)a.w, (uint64_t)a.h, (uint64_t)a.nb};
     const uint64_t strides[3] = {(uint64_t)a.cin * 2, (uint64_t)a.w * a.cin * 2,
                                  (uint64_t)a.h * a.w * a.cin * 2};
-    const uint32_t box[4] = {64, (uint32_t)kBW, (uint32_t)Cfg::kHaloRows, 1};
+    const uint32_t box[4] = {64, (uint32_t)Cfg::kWinW, (uint32_t)Cfg::kHaloRows, 1};
     int rc = encode_bf16_map(tc, &map_in, 4, in, dims, strides, box, a.in_half != 0);
     if (rc != ST_OK) return rc;
   }
@@ -836,12 +842,12 @@ int gemm_abs_tc_pair(TcContext& tc, const void* f, const void* d, bool half_in, 
   a.in_half = half_in ? 1 : 0, a.out_half = 0;          // S is a gradient: bf16
   a.abs_partials = abs_partials;
   const int bn = choose_bn(tc, nb, h, w, c);
-  *per_tile = cdiv(w, kBW) * cdiv(h, 2 * kBH) * (c / 64) * 8;
+  *per_tile = cdiv(w, kBW) * cdiv(h, 2 * kBH) * (c / 64) * 16;
   return dispatch_bn<1, kEpiAbs>(tc, bn, f, d, c, s_out, a, s);
 }
 
 size_t gemm_abs_partials_needed(int nb, int h, int w, int c) {
-  return (size_t)nb * cdiv(w, kBW) * cdiv(h, 2 * kBH) * (c / 64) * 8;
+  return (size_t)nb * cdiv(w, kBW) * cdiv(h, 2 * kBH) * (c / 64) * 16;
 }
 
 }  // namespace st

@@ -807,82 +807,110 @@ int inject_scaled(T* inj, const T* src, size_t n, int nb, float w, const double*
 // Content / Deep-Dream terms (style_transfer.py:575-580, 602-604): c = F - target slice (or F),
 // loss 0.5*sum c^2, gradient c / (mean|c| + EPS).  Two passes, c is never stored.
 // =====================================================================================================
+// One feature row of a tile (wf pixels x c channels, contiguous in NHWC) against the matching row of
+// the whole-image target: blocks walk the rows, threads walk the row in groups of 8 channels, so the
+// only index arithmetic per 8 elements is one FastDiv (the first version did two 32-bit divisions
+// per 4 elements and was instruction-bound at 90 % SM busy / 17 % of the HBM bandwidth,
+// profiles/r01_laggards_ncu.md).
+struct DiffGeom {
+  int hf, wf, c8;            // tile feature map: rows, pixels per row, 8-channel groups per pixel
+  int Hf, Wf;                // whole-image target map
+  FastDiv div_c8;
+};
+
 template <typename T>
-__device__ __forceinline__ float4 diff_at(const T* f, const float* tgt, size_t i4_, int wf, int c4,
-                                          int Hf, int Wf, int ty0, int tx0) {
-  const unsigned i4 = (unsigned)i4_;         // per-tile element index: fits 32 bits (checked on host)
-  float4 v = Store<T>::ld4(f + (size_t)i4 * 4);
-  if (tgt) {
-    const unsigned q = i4 % (unsigned)c4;
-    const unsigned p = i4 / (unsigned)c4;
-    const int y = (int)(p / (unsigned)wf), x = (int)(p - (unsigned)y * (unsigned)wf);
-    // the offsets are reduced on the host to [0, Hf) x [0, Wf): one conditional subtract wraps
-    int yy = ty0 + y, xx = tx0 + x;
-    yy = yy >= Hf ? yy - Hf : yy, xx = xx >= Wf ? xx - Wf : xx;
-    const float4 t =
-        *reinterpret_cast<const float4*>(tgt + ((size_t)yy * Wf + xx) * (c4 * 4) + q * 4);
-    v.x -= t.x, v.y -= t.y, v.z -= t.z, v.w -= t.w;
+__device__ __forceinline__ F8 diff_row8(const T* __restrict__ frow, const float* __restrict__ trow,
+                                        unsigned i, const DiffGeom& g, int tx0) {
+  F8 v = ld8(frow + (size_t)i * 8);
+  if (trow) {
+    const unsigned x = g.div_c8.div(i), q = i - x * (unsigned)g.c8;
+    int xx = tx0 + (int)x;                       // offsets are reduced on the host to [0, Wf)
+    xx = xx >= g.Wf ? xx - g.Wf : xx;
+    const F8 t = ld8(trow + ((size_t)xx * g.c8 + q) * 8);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v.v[e] -= t.v[e];
   }
   return v;
 }
 
 template <typename T>
-__global__ void diff_stats_kernel(const T* __restrict__ f, size_t n4, int wf, int c4,
-                                  const float* __restrict__ tgt, int Hf, int Wf, TargetOffsets offs,
-                                  double* stats, int stat_stride, ReduceScratch rs) {
+__global__ void __launch_bounds__(256)
+diff_stats_kernel(const T* __restrict__ f, DiffGeom g, const float* __restrict__ tgt,
+                  TargetOffsets offs, double* stats, int stat_stride, ReduceScratch rs) {
   const int b = blockIdx.y;
-  f += (size_t)b * n4 * 4;
+  const unsigned row8 = (unsigned)g.wf * g.c8;
+  f += (size_t)b * g.hf * row8 * 8;
   float sq = 0.f, ab = 0.f;
   double v[2] = {0.0, 0.0};
   int cnt = 0;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4;
-       i += (size_t)gridDim.x * blockDim.x) {
-    const float4 d = diff_at(f, tgt, i, wf, c4, Hf, Wf, offs.ty0[b], offs.tx0[b]);
-    sq += d.x * d.x + d.y * d.y + d.z * d.z + d.w * d.w;
-    ab += fabsf(d.x) + fabsf(d.y) + fabsf(d.z) + fabsf(d.w);
-    if (++cnt == 64) v[0] += sq, v[1] += ab, sq = ab = 0.f, cnt = 0;
+  for (int y = blockIdx.x; y < g.hf; y += gridDim.x) {
+    int yy = offs.ty0[b] + y;
+    yy = yy >= g.Hf ? yy - g.Hf : yy;
+    const T* frow = f + (size_t)y * row8 * 8;
+    const float* trow = tgt ? tgt + (size_t)yy * g.Wf * g.c8 * 8 : nullptr;
+    for (unsigned i = threadIdx.x; i < row8; i += blockDim.x) {
+      const F8 d = diff_row8(frow, trow, i, g, offs.tx0[b]);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) sq += d.v[e] * d.v[e], ab += fabsf(d.v[e]);
+      if (++cnt == 32) v[0] += sq, v[1] += ab, sq = ab = 0.f, cnt = 0;
+    }
   }
   v[0] += sq, v[1] += ab;
   if (grid_reduce<2>(v, rs.partials + (size_t)b * gridDim.x * 2, rs.counter + b))
     stats[(size_t)b * stat_stride] = v[0], stats[(size_t)b * stat_stride + 1] = v[1];
 }
 
+static DiffGeom diff_geom(int hf, int wf, int c, int Hf, int Wf) {
+  DiffGeom g;
+  g.hf = hf, g.wf = wf, g.c8 = c / 8, g.Hf = Hf, g.Wf = Wf, g.div_c8 = FastDiv(c / 8);
+  return g;
+}
+
 template <typename T>
 int diff_stats(const T* f, int nb, int hf, int wf, int c, const float* tgt, int Hf, int Wf,
                const TargetOffsets& offs, double* stats, int stat_stride, ReduceScratch rs,
                cudaStream_t s) {
-  ST_REQUIRE(c % 4 == 0, "diff_stats: channels must be a multiple of 4");
-  const size_t n4 = (size_t)hf * wf * (c / 4);
-  const int gx = min(ew_grid(n4, 256), kMaxReduceBlocks / (nb * 2));
+  ST_REQUIRE(c % 8 == 0, "diff_stats: channels must be a multiple of 8");
+  // rows per tile fix the grid: the summation order depends on the layer shape only
+  const int gx = min(hf, kMaxReduceBlocks / (nb * 2));
   auto k = diff_stats_kernel<T>;
-  TimerScope ts(s, kTimeLoss, (double)nb * n4 * 4 * (sizeof(T) + (tgt ? 4 : 0)));
-  ST_LAUNCH(k, dim3(gx, nb), 256, 0, s, f, n4, wf, c / 4, tgt, Hf, Wf, offs, stats, stat_stride,
-            rs);
+  TimerScope ts(s, kTimeLoss, (double)nb * hf * wf * c * (sizeof(T) + (tgt ? 4 : 0)));
+  ST_LAUNCH(k, dim3(gx, nb), 256, 0, s, f, diff_geom(hf, wf, c, Hf, Wf), tgt, offs, stats,
+            stat_stride, rs);
   return ST_OK;
 }
 
 // stats[b] = {sum c^2, sum |c|}; inj = (accumulate ? inj : 0) + w / (mean|c| + EPS) * c;
 // tile_loss[b] += loss_w * 0.5 * sum c^2
 template <typename TA, typename T>
-__global__ void diff_inject_kernel(const TA* __restrict__ f, size_t n4, int wf, int c4,
-                                   const float* __restrict__ tgt, int Hf, int Wf, TargetOffsets offs,
-                                   const double* __restrict__ stats, int stat_stride, float w,
-                                   double loss_w, double* tile_loss, int loss_stride,
-                                   T* __restrict__ inj, int accumulate) {
+__global__ void __launch_bounds__(256)
+diff_inject_kernel(const TA* __restrict__ f, DiffGeom g, const float* __restrict__ tgt,
+                   TargetOffsets offs, const double* __restrict__ stats, int stat_stride, float w,
+                   double loss_w, double* tile_loss, int loss_stride, T* __restrict__ inj,
+                   int accumulate) {
   const int b = blockIdx.y;
-  f += (size_t)b * n4 * 4, inj += (size_t)b * n4 * 4;
+  const unsigned row8 = (unsigned)g.wf * g.c8;
+  f += (size_t)b * g.hf * row8 * 8, inj += (size_t)b * g.hf * row8 * 8;
   const double* st = stats + (size_t)b * stat_stride;
-  const float coef = w * (1.f / ((float)(st[1] / (double)(n4 * 4)) + kEps));
+  const float coef = w * (1.f / ((float)(st[1] / ((double)g.hf * row8 * 8)) + kEps));
   if (blockIdx.x == 0 && threadIdx.x == 0) tile_loss[(size_t)b * loss_stride] += loss_w * 0.5 * st[0];
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4;
-       i += (size_t)gridDim.x * blockDim.x) {
-    const float4 d = diff_at(f, tgt, i, wf, c4, Hf, Wf, offs.ty0[b], offs.tx0[b]);
-    float4 r = make_float4(coef * d.x, coef * d.y, coef * d.z, coef * d.w);
-    if (accumulate) {
-      const float4 o = Store<T>::ld4(inj + i * 4);
-      r.x += o.x, r.y += o.y, r.z += o.z, r.w += o.w;
+  for (int y = blockIdx.x; y < g.hf; y += gridDim.x) {
+    int yy = offs.ty0[b] + y;
+    yy = yy >= g.Hf ? yy - g.Hf : yy;
+    const TA* frow = f + (size_t)y * row8 * 8;
+    T* irow = inj + (size_t)y * row8 * 8;
+    const float* trow = tgt ? tgt + (size_t)yy * g.Wf * g.c8 * 8 : nullptr;
+    for (unsigned i = threadIdx.x; i < row8; i += blockDim.x) {
+      F8 r = diff_row8(frow, trow, i, g, offs.tx0[b]);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) r.v[e] *= coef;
+      if (accumulate) {
+        const F8 o = ld8(irow + (size_t)i * 8);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) r.v[e] += o.v[e];
+      }
+      st8(irow + (size_t)i * 8, r);
     }
-    Store<T>::st4(inj + i * 4, r);
   }
 }
 
@@ -891,10 +919,11 @@ int diff_inject(const TA* f, int nb, int hf, int wf, int c, const float* tgt, in
                 const TargetOffsets& offs, const double* stats, int stat_stride, float w,
                 double loss_w, double* tile_loss, int loss_stride, T* inj, bool accumulate,
                 cudaStream_t s) {
-  const size_t n4 = (size_t)hf * wf * (c / 4);
+  ST_REQUIRE(c % 8 == 0, "diff_inject: channels must be a multiple of 8");
   auto k = diff_inject_kernel<TA, T>;
-  TimerScope ts(s, kTimeLoss, (double)nb * n4 * 4 * (sizeof(T) * (accumulate ? 3 : 2) + (tgt ? 4 : 0)));
-  ST_LAUNCH(k, dim3(ew_grid(n4, 256), nb), 256, 0, s, f, n4, wf, c / 4, tgt, Hf, Wf, offs, stats,
+  TimerScope ts(s, kTimeLoss,
+                (double)nb * hf * wf * c * (sizeof(T) * (accumulate ? 3 : 2) + (tgt ? 4 : 0)));
+  ST_LAUNCH(k, dim3(hf, nb), 256, 0, s, f, diff_geom(hf, wf, c, Hf, Wf), tgt, offs, stats,
             stat_stride, w, loss_w, tile_loss, loss_stride, inj, accumulate ? 1 : 0);
   return ST_OK;
 }

@@ -14,6 +14,8 @@ stop = ends[-1] + 1 if ends else len(names)
 if '--step' in sys.argv:     # a whole optimizer step: up to and including the last adam kernel
     adams = [i for i, n in enumerate(names) if 'adam_kernel' in n[0]]
     start, stop = adams[-2] + 1, adams[-1] + 1
+if '--all' in sys.argv:      # the whole list (e.g. one step bracketed by cudaProfilerStart/Stop)
+    start, stop = 0, len(names)
 total, agg = 0.0, OrderedDict()
 for name, us, grid in names[start:stop]:
     short = re.sub(r'\(.*', '', name).replace('void ', '').replace('st::', '').replace('<unnamed>::', '')[:64]

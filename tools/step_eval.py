@@ -20,6 +20,8 @@ def main():
     p.add_argument('--steps', type=int, default=3)
     p.add_argument('--precision', default='fp16')
     p.add_argument('--optimizer', default='adam')
+    p.add_argument('--profile-last', action='store_true',
+                   help='bracket the last step with cudaProfilerStart/Stop (ncu --profile-from-start off)')
     a = p.parse_args()
     args = default_args(size=a.size, min_size=a.size, tile_size=a.tile_size, optimizer=a.optimizer)
     net = netdesc.from_model(args.model)
@@ -43,9 +45,14 @@ def main():
     for i in range(a.steps):
         if i == a.steps - 1:
             e0.record()
+            if a.profile_last:
+                torch.cuda.synchronize()
+                torch.cuda.profiler.start()
         avg, loss = st.step()
     e1.record()
     torch.cuda.synchronize()
+    if a.profile_last:
+        torch.cuda.profiler.stop()
     print('step %dx%d/%d %s: last step %.3f ms, loss %.6e' %
           (a.size, a.size, a.tile_size, a.precision, e0.elapsed_time(e1), float(loss)), flush=True)
 
