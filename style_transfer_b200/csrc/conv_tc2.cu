@@ -226,12 +226,81 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t 
          ((uint64_t)(sbo >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
 }
 
+// ReLU + saturation + rounding + packing of two fp32 values in one F2FP (hi lands in the upper half)
+__device__ __forceinline__ uint32_t pack16_relu(float lo, float hi, bool half) {
+  uint32_t d;
+  if (half)
+    asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  else
+    asm("cvt.rn.relu.satfinite.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+// packed 16-bit pairs: per-half (a > b) ? 0xFFFF : 0, and the per-half maximum
+template <bool HALF>
+__device__ __forceinline__ uint32_t gt2_mask(uint32_t a, uint32_t b) {
+  if constexpr (HALF)
+    return __hgt2_mask(*reinterpret_cast<const __half2*>(&a), *reinterpret_cast<const __half2*>(&b));
+  else
+    return __hgt2_mask(*reinterpret_cast<const __nv_bfloat162*>(&a),
+                       *reinterpret_cast<const __nv_bfloat162*>(&b));
+}
+template <bool HALF>
+__device__ __forceinline__ uint32_t max2(uint32_t a, uint32_t b) {
+  if constexpr (HALF) {
+    const __half2 r = __hmax2(*reinterpret_cast<const __half2*>(&a), *reinterpret_cast<const __half2*>(&b));
+    return *reinterpret_cast<const uint32_t*>(&r);
+  } else {
+    const __nv_bfloat162 r = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&a),
+                                     *reinterpret_cast<const __nv_bfloat162*>(&b));
+    return *reinterpret_cast<const uint32_t*>(&r);
+  }
+}
+
+// 2x2/2 max pooling of one (pooled pixel, 8-channel) item straight on the packed 16-bit values of the
+// staged tile: per window position one HSET2 (mask of "greater than the running maximum": strict,
+// so the first maximum in scan order wins like Caffe's), one HMNMX2 and one LOP3 per channel pair.
+// The values were rounded when they were staged, so this equals comparing their fp32 images.
+// Returns the four packed maxima in ow[] and the eight mask bytes (bits 0-1 = arg-max position,
+// bit 2 = maximum > 0) in mk[].
+template <bool HALF>
+__device__ __forceinline__ void pool_max_item(const uint8_t* stage_out, int pr, int pc, int j,
+                                              int rows_left, int cols_left, uint32_t (&ow)[4],
+                                              uint32_t (&mk)[2]) {
+  const uint32_t neg = HALF ? 0xFBFFFBFFu : 0xFF7FFF7Fu;      // most negative finite value, twice
+  uint32_t best[4] = {neg, neg, neg, neg}, code[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+  for (int d = 0; d < 4; ++d) {
+    const int r = 2 * pr + (d >> 1), cx = 2 * pc + (d & 1);
+    if (r >= rows_left || cx >= cols_left) continue;          // ceil mode: clipped window
+    const int mm = r * 8 + cx;
+    const uint4 raw = *reinterpret_cast<const uint4*>(stage_out + mm * 128 + ((j ^ (mm & 7)) << 4));
+    const uint32_t w4[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const uint32_t gt = gt2_mask<HALF>(w4[e], best[e]);
+      best[e] = max2<HALF>(w4[e], best[e]);
+      code[e] = (code[e] & ~gt) | ((uint32_t)(d * 0x00010001) & gt);
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    code[e] |= gt2_mask<HALF>(best[e], 0u) & 0x00040004u;
+    ow[e] = best[e];
+  }
+  // one byte per element: bytes 0 and 2 of each code word
+  mk[0] = __byte_perm(code[0], code[1], 0x6420);
+  mk[1] = __byte_perm(code[2], code[3], 0x6420);
+}
+
 struct Tc2Args {
   int nb, h, w, cin, cout;         // nb tiles of the batch, each [h][w]
   int in_half, out_half;           // operands (A and B) / stored output are fp16 instead of bf16
   int w_batched;                   // the B operand has one matrix per batch tile (style GEMM)
   int resb_bytes;                  // RESB: bytes of the resident weight block (multiple of 1024)
   int tiles_x, tiles_y, tiles_n;   // pair tiles per batch tile: 8 columns x 32 rows x BN channels
+  FastDiv div_x, div_y, div_n;     // by tiles_x / tiles_y / tiles_n (decode_tile runs once per tile
+                                   // in every warp role: three hardware divisions were ~100
+                                   // instructions of the ~700 an epilogue warp spent per tile)
   const float* bias;               // kEpiFwd
   const __nv_bfloat16* mask_act;   // kEpiBwd, NHWC [h][w][cout], may be null
   const __nv_bfloat16* inj;        // kEpiBwd, may be null
@@ -249,12 +318,12 @@ struct TileCoord {
 };
 __device__ __forceinline__ TileCoord decode_tile(const Tc2Args& a, int tile, int rank) {
   TileCoord t;
-  t.n_tile = tile % a.tiles_n;
-  int m = tile / a.tiles_n;
-  t.x0 = (m % a.tiles_x) * kBW;
-  m /= a.tiles_x;
-  t.y0 = (m % a.tiles_y) * (2 * kBH) + rank * kBH;
-  t.b = m / a.tiles_y;
+  int m = (int)a.div_n.div((unsigned)tile);
+  t.n_tile = tile - m * a.tiles_n;
+  int r = (int)a.div_x.div((unsigned)m);
+  t.x0 = (m - r * a.tiles_x) * kBW;
+  t.b = (int)a.div_y.div((unsigned)r);
+  t.y0 = (r - t.b * a.tiles_y) * (2 * kBH) + rank * kBH;
   return t;
 }
 
@@ -268,16 +337,21 @@ struct Cfg2 {
   static constexpr int kAPitch = kWinW * 128;                    // bytes between 8-pixel row groups
   static constexpr int kALoadBytes = kHaloRows * kAPitch;        // 22.5 KB (3x3) / 16 KB (1x1)
   static constexpr int kABytes = (kALoadBytes + 1023) / 1024 * 1024;   // stages stay 1024-aligned
-  static constexpr int kBBytes = (BN / 2) * 128;                 // this CTA's half of the B tile
+  static constexpr int kBBytes = (BN / 2) * 128;                 // this CTA's half of one tap's B tile
+  // taps per B pipeline stage: the narrow tiles have little tensor time per tap (4 MMAs of BN/2
+  // cycles), so one barrier round trip per TAP made their MMA warp issue-bound; one per kernel row
+  // (three taps) amortises it.  BN = 256 keeps one tap per stage (48 KB stages would not fit).
+  static constexpr int kTB = (TAPS == 9 && BN <= 128) ? 3 : 1;
+  static constexpr int kBStage = kTB * kBBytes;
   static constexpr int kSA = 4;
   static constexpr int kPoolBytes = POOL ? 2 * kPoolStageBytes : 0;
   static constexpr int kOutBytes = 2 * kOutStageBytes + kPoolBytes;
-  static constexpr int kSBRaw = (kSmemBudget - kSA * kABytes - kOutBytes) / kBBytes;
+  static constexpr int kSBRaw = (kSmemBudget - kSA * kABytes - kOutBytes) / kBStage;
   static constexpr int kSB = RESB ? 1 : (kSBRaw > 8 ? 8 : kSBRaw);
   static constexpr int kResMax = kSmemBudget - kSA * kABytes - kOutBytes;   // bytes for resident B
   static constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;    // double-buffered accumulator
   static constexpr int kFixedBytes = kSA * kABytes + kOutBytes + 1024 + kTailBytes;
-  static constexpr int kSmemBytes = kFixedBytes + kSB * kBBytes;           // staged-B variant
+  static constexpr int kSmemBytes = kFixedBytes + kSB * kBStage;           // staged-B variant
   // instruction descriptor without the operand formats (0 = f16, 1 = bf16 at bits 7 and 10)
   static constexpr uint32_t kIdescBase = (1u << 4) | ((uint32_t)(BN >> 3) << 17) |
                                          ((uint32_t)(256 >> 4) << 24);
@@ -298,7 +372,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constan
   uint8_t* a_base = smem;
   uint8_t* out_base = a_base + Cfg::kSA * Cfg::kABytes;
   uint8_t* b_base = out_base + Cfg::kOutBytes;
-  const int b_bytes = RESB ? a.resb_bytes : Cfg::kSB * Cfg::kBBytes;
+  const int b_bytes = RESB ? a.resb_bytes : Cfg::kSB * Cfg::kBStage;
   uint64_t* bars = reinterpret_cast<uint64_t*>(b_base + b_bytes);
   uint64_t* a_full = bars;
   uint64_t* a_empty = a_full + Cfg::kSA;
@@ -374,13 +448,15 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constan
         const int n0 = t.n_tile * BN + (int)rank * (BN / 2);
         const int wb = a.w_batched ? t.b : 0;
         for (int cb = 0; cb < kb_per_tap; ++cb) {
-          for (int tap = 0; tap < TAPS; ++tap) {
+          for (int tap = 0; tap < TAPS; tap += Cfg::kTB) {
             mbar_wait(&b_empty[stage], phase ^ 1);
             const uint32_t bar = map_to_cta(smem_u32(&b_full[stage]), 0);
             if (elect_one()) {
-              if (leader) mbar_expect_tx(&b_full[stage], 2 * Cfg::kBBytes);
-              tma_load_3d_pair(&map_w, bar, b_base + stage * Cfg::kBBytes, tap * a.cin + cb * 64,
-                               n0, wb);
+              if (leader) mbar_expect_tx(&b_full[stage], 2 * Cfg::kBStage);
+#pragma unroll
+              for (int j = 0; j < Cfg::kTB; ++j)
+                tma_load_3d_pair(&map_w, bar, b_base + stage * Cfg::kBStage + j * Cfg::kBBytes,
+                                 (tap + j) * a.cin + cb * 64, n0, wb);
             }
             __syncwarp();
             if (++stage == Cfg::kSB) stage = 0, phase ^= 1;
@@ -403,29 +479,57 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constan
         const uint32_t d_tmem = tmem_base + buf * BN;
         for (int cb = 0; cb < kb_per_tap; ++cb) {
           mbar_wait(&a_full[sa], pa);
-          const uint32_t a_addr = smem_u32(a_base + sa * Cfg::kABytes);
-#pragma unroll 1
-          for (int tap = 0; tap < TAPS; ++tap) {
-            if constexpr (!RESB) mbar_wait(&b_full[sb], pb);
-            tc_fence_after();
-            uint32_t a_tap = a_addr;
-            if constexpr (TAPS == 9) a_tap += ((tap / 3) * Cfg::kWinW + (tap % 3)) * 128;
-            const uint64_t da = make_smem_desc(a_tap, Cfg::kAPitch);
-            const uint64_t db = make_smem_desc(
-                smem_u32(b_base + (RESB ? (cb * TAPS + tap) : sb) * Cfg::kBBytes));
+          tc_fence_after();
+          // Descriptors are built once per 64-channel block; the taps and the four K = 16 steps are
+          // compile-time offsets of their 14-bit address fields (the whole block is unrolled).  A
+          // rolled tap loop computed every descriptor from scratch: ~65 instructions (~450 cycles)
+          // per tap in this one warp, against 128 cycles of tensor time per tap at BN = 64 -- the
+          // small layers were bound by MMA *issue* (profiles/r01_conv_small_ncu.md).
+          const uint64_t da0 = make_smem_desc(smem_u32(a_base + sa * Cfg::kABytes), Cfg::kAPitch);
+          const bool last_cb = cb == kb_per_tap - 1;
+          if constexpr (RESB) {
+            const uint64_t db0 = make_smem_desc(smem_u32(b_base + cb * TAPS * Cfg::kBBytes));
             if (elect_one()) {
 #pragma unroll
-              for (int k = 0; k < 4; ++k)
-                tc_mma_pair(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc,
-                            (cb | tap | k) != 0);
-              if constexpr (!RESB) tc_commit_pair(&b_empty[sb]);
-              if (tap == TAPS - 1) {
-                tc_commit_pair(&a_empty[sa]);
-                if (cb == kb_per_tap - 1) tc_commit_pair(&t_full[buf]);
+              for (int tap = 0; tap < TAPS; ++tap) {
+                const uint64_t da = da0 + (uint64_t)(TAPS == 9 ? ((tap / 3) * Cfg::kWinW + tap % 3) * 8 : 0);
+                const uint64_t db = db0 + (uint64_t)(tap * (Cfg::kBBytes >> 4));
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  tc_mma_pair(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc,
+                              (tap | k) != 0 ? 1u : (uint32_t)(cb != 0));
               }
+              tc_commit_pair(&a_empty[sa]);
+              if (last_cb) tc_commit_pair(&t_full[buf]);
             }
             __syncwarp();
-            if (++sb == Cfg::kSB) sb = 0, pb ^= 1;
+          } else {
+#pragma unroll
+            for (int tg = 0; tg < TAPS; tg += Cfg::kTB) {
+              mbar_wait(&b_full[sb], pb);
+              tc_fence_after();
+              const uint64_t db0 = make_smem_desc(smem_u32(b_base + sb * Cfg::kBStage));
+              if (elect_one()) {
+#pragma unroll
+                for (int j = 0; j < Cfg::kTB; ++j) {
+                  const int tap = tg + j;
+                  const uint64_t da =
+                      da0 + (uint64_t)(TAPS == 9 ? ((tap / 3) * Cfg::kWinW + tap % 3) * 8 : 0);
+                  const uint64_t db = db0 + (uint64_t)(j * (Cfg::kBBytes >> 4));
+#pragma unroll
+                  for (int k = 0; k < 4; ++k)
+                    tc_mma_pair(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc,
+                                (tap | k) != 0 ? 1u : (uint32_t)(cb != 0));
+                }
+                tc_commit_pair(&b_empty[sb]);
+                if (tg + Cfg::kTB >= TAPS) {
+                  tc_commit_pair(&a_empty[sa]);
+                  if (last_cb) tc_commit_pair(&t_full[buf]);
+                }
+              }
+              __syncwarp();
+              if (++sb == Cfg::kSB) sb = 0, pb ^= 1;
+            }
           }
           if (++sa == Cfg::kSA) sa = 0, pa ^= 1;
         }
@@ -439,32 +543,71 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constan
     const bool issuer = threadIdx.x == kEpiWarp0 * 32;
     const bool out_half = a.out_half != 0;
     uint32_t it = 0, store_seq = 0;
+    // Backward epilogue operands (ReLU mask = the forward activation, injected loss gradient): this
+    // thread's pixel row of a tile, 64 bytes per 32-channel chunk and array.  They come from HBM, and
+    // a load issued at the start of a tile made every tile wait a full DRAM latency (48 % of the
+    // epilogue warps' samples sat on the first use, profiles/r01_conv_small_ncu.md).  Now the chunk
+    // sequence is pipelined ACROSS tiles: while chunk i is processed the registers already receive
+    // chunk i+1 (of this tile or the next), and the lines of the tile after that are pulled into L2.
+    struct RowRef {
+      size_t gofs;
+      bool valid;
+    };
+    auto row_of = [&](int tl) {
+      RowRef r{0, false};
+      if (tl < num_tiles) {
+        const TileCoord tc = decode_tile(a, tl, (int)rank);
+        const int py = tc.y0 + (m >> 3), px = tc.x0 + (m & 7);
+        r.valid = py < a.h && px < a.w;
+        r.gofs = (((size_t)tc.b * a.h + py) * a.w + px) * a.cout + (size_t)tc.n_tile * BN;
+      }
+      return r;
+    };
+    uint4 pm[4], pe[4];
+    auto prefetch = [&](const RowRef& rr, int cc) {
+      if constexpr (EPI == kEpiBwd) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          pm[i] = make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u);   // "positive"
+          pe[i] = make_uint4(0u, 0u, 0u, 0u);
+          if (rr.valid && a.mask_act != nullptr)
+            pm[i] = *reinterpret_cast<const uint4*>(a.mask_act + rr.gofs + cc * 32 + i * 8);
+          if (rr.valid && a.inj != nullptr)
+            pe[i] = *reinterpret_cast<const uint4*>(a.inj + rr.gofs + cc * 32 + i * 8);
+        }
+      }
+    };
+    auto prefetch_l2 = [&](const RowRef& rr) {
+      if constexpr (EPI == kEpiBwd) {
+        if (rr.valid) {
+#pragma unroll
+          for (int g = 0; g < BN / 64; ++g) {
+            const size_t o = rr.gofs + (size_t)(g * 2 + hsel) * 32;
+            if (a.mask_act != nullptr)
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(a.mask_act + o));
+            if (a.inj != nullptr) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.inj + o));
+          }
+        }
+      }
+    };
+    if constexpr (EPI == kEpiBwd) {
+      prefetch(row_of(pair), hsel);
+      prefetch_l2(row_of(pair + num_pairs));
+    }
     for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
       const uint32_t buf = it & 1, use = it >> 1;
       const TileCoord t = decode_tile(a, tile, (int)rank);
       const int n_tile = t.n_tile, x0 = t.x0, y0 = t.y0;
       const int py = y0 + (m >> 3), px = x0 + (m & 7);
       const bool valid = py < a.h && px < a.w;
-      const size_t gofs =
-          (((size_t)t.b * a.h + py) * a.w + px) * a.cout + (size_t)n_tile * BN;
+      const RowRef cur{(((size_t)t.b * a.h + py) * a.w + px) * a.cout + (size_t)n_tile * BN, valid};
+      RowRef nxt{0, false};
+      (void)cur;
+      if constexpr (EPI == kEpiBwd) {
+        nxt = row_of(tile + num_pairs);
+        prefetch_l2(row_of(tile + 2 * num_pairs));
+      }
       float abs_tile = 0.f;
-      // backward epilogue operands of the first 32-channel chunk: requested before the wait on the
-      // accumulator, the following chunks one chunk ahead (their latency hides behind the MMAs)
-      uint4 pm[4], pe[4];
-      auto prefetch = [&](int cc) {
-        if constexpr (EPI == kEpiBwd) {
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            pm[i] = make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u);   // "positive"
-            pe[i] = make_uint4(0u, 0u, 0u, 0u);
-            if (valid && a.mask_act != nullptr)
-              pm[i] = *reinterpret_cast<const uint4*>(a.mask_act + gofs + cc * 32 + i * 8);
-            if (valid && a.inj != nullptr)
-              pe[i] = *reinterpret_cast<const uint4*>(a.inj + gofs + cc * 32 + i * 8);
-          }
-        }
-      };
-      prefetch(hsel);
       float inj_sc = 1.f;
       if constexpr (EPI == kEpiBwd) {
         if (a.inj_scale != nullptr) inj_sc = __ldg(a.inj_scale + t.b);
@@ -504,12 +647,15 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constan
           if constexpr (kFwd) {
             const float* bs = bias_s + n_tile * BN + cc * 32;
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i] + bs[i], 0.f);
+            for (int i = 0; i < 32; ++i) v[i] += bs[i];      // ReLU happens in the pack below
           } else if constexpr (EPI == kEpiBwd) {
             uint4 cm[4], ce[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) cm[i] = pm[i], ce[i] = pe[i];
-            if (cc + 2 < BN / 32) prefetch(cc + 2);
+            if (cc + 2 < BN / 32)
+              prefetch(cur, cc + 2);
+            else
+              prefetch(nxt, hsel);                   // first chunk of this warp in the next tile
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               const uint32_t m4[4] = {cm[i].x, cm[i].y, cm[i].z, cm[i].w};
@@ -547,7 +693,15 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constan
           // one warp-uniform branch per chunk (a branch inside every pack cost the short-K
           // kernels half their speed)
           uint32_t pw[16];
-          if (out_half) {
+          if constexpr (kFwd) {
+            if (out_half) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) pw[i] = pack16_relu(v[2 * i], v[2 * i + 1], true);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) pw[i] = pack16_relu(v[2 * i], v[2 * i + 1], false);
+            }
+          } else if (out_half) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) pw[i] = pack16(v[2 * i], v[2 * i + 1], true);
           } else {
@@ -581,70 +735,44 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constan
           {
             const int item = et, pp = item >> 3, j = item & 7;
             const int pr = pp >> 2, pc = pp & 3;                 // pooled row / column in the tile
-            float best[8], sum[8];
-            uint32_t code[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) best[e] = -3.4e38f, sum[e] = 0.f, code[e] = 0u;
-            int cnt = 0;
-#pragma unroll
-            for (int d = 0; d < 4; ++d) {
-              const int r = 2 * pr + (d >> 1), cx = 2 * pc + (d & 1);
-              if (y0 + r >= a.h || x0 + cx >= a.w) continue;      // ceil mode: clipped window
-              ++cnt;
-              const int mm = r * 8 + cx;
-              const uint4 raw =
-                  *reinterpret_cast<const uint4*>(stage_out + mm * 128 + ((j ^ (mm & 7)) << 4));
-              const uint32_t w4[4] = {raw.x, raw.y, raw.z, raw.w};
-              float xv[8];
-              if (out_half) {                                    // one uniform branch per load
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  const float2 t2 = unpack16(w4[e], true);
-                  xv[2 * e] = t2.x, xv[2 * e + 1] = t2.y;
-                }
-              } else {
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  const float2 t2 = unpack16(w4[e], false);
-                  xv[2 * e] = t2.x, xv[2 * e + 1] = t2.y;
-                }
-              }
-#pragma unroll
-              for (int e = 0; e < 8; ++e) {
-                const float x = xv[e];
-                if (a.pool_mode == 1) {
-                  if (x > best[e]) best[e] = x, code[e] = (uint32_t)d;       // strict: first max wins
-                } else {
-                  sum[e] += x;
-                  if (x > 0.f) code[e] |= 1u << d;
-                }
-              }
-            }
             const int pyo = (y0 >> 1) + pr, pxo = (x0 >> 1) + pc;
             uint32_t ow[4], mk[2] = {0u, 0u};
-            float po[8];
-#pragma unroll
-            for (int e = 0; e < 8; e += 2) {
-              float o0, o1;
-              if (a.pool_mode == 1) {
-                o0 = best[e], o1 = best[e + 1];
-                if (o0 > 0.f) code[e] |= 4u;
-                if (o1 > 0.f) code[e + 1] |= 4u;
-              } else {
-                const float inv = (float)(cnt > 0 ? cnt : 1);
-                o0 = sum[e] / inv, o1 = sum[e + 1] / inv;
-              }
-              po[e] = o0, po[e + 1] = o1;
-            }
-            if (out_half) {
-#pragma unroll
-              for (int e = 0; e < 4; ++e) ow[e] = pack16(po[2 * e], po[2 * e + 1], true);
+            if (a.pool_mode == 1) {
+              if (out_half)
+                pool_max_item<true>(stage_out, pr, pc, j, a.h - y0, a.w - x0, ow, mk);
+              else
+                pool_max_item<false>(stage_out, pr, pc, j, a.h - y0, a.w - x0, ow, mk);
             } else {
+              // average pooling: fp32 sum of the staged values / clipped window size
+              float sum[8];
+              uint32_t code[8];
 #pragma unroll
-              for (int e = 0; e < 4; ++e) ow[e] = pack16(po[2 * e], po[2 * e + 1], false);
+              for (int e = 0; e < 8; ++e) sum[e] = 0.f, code[e] = 0u;
+              int cnt = 0;
+#pragma unroll
+              for (int d = 0; d < 4; ++d) {
+                const int r = 2 * pr + (d >> 1), cx = 2 * pc + (d & 1);
+                if (y0 + r >= a.h || x0 + cx >= a.w) continue;    // ceil mode: clipped window
+                ++cnt;
+                const int mm = r * 8 + cx;
+                const uint4 raw =
+                    *reinterpret_cast<const uint4*>(stage_out + mm * 128 + ((j ^ (mm & 7)) << 4));
+                const uint32_t w4[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float2 t2 = unpack16(w4[e], out_half);
+                  sum[2 * e] += t2.x, sum[2 * e + 1] += t2.y;
+                  if (t2.x > 0.f) code[2 * e] |= 1u << d;
+                  if (t2.y > 0.f) code[2 * e + 1] |= 1u << d;
+                }
+              }
+              const float inv = (float)(cnt > 0 ? cnt : 1);
+#pragma unroll
+              for (int e = 0; e < 4; ++e)
+                ow[e] = pack16(sum[2 * e] / inv, sum[2 * e + 1] / inv, out_half);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) mk[e >> 2] |= code[e] << (8 * (e & 3));
             }
-#pragma unroll
-            for (int e = 0; e < 8; ++e) mk[e >> 2] |= code[e] << (8 * (e & 3));
             *reinterpret_cast<uint4*>(pstage + pp * 128 + ((j ^ (pp & 7)) << 4)) =
                 make_uint4(ow[0], ow[1], ow[2], ow[3]);
             if (pyo < ho && pxo < wo)
@@ -704,6 +832,7 @@ int launch2r(TcContext& tc, const void* in, const void* wk, int wk_rows,
              void* out, void* pool_out, Tc2Args a, cudaStream_t s) {
   using Cfg = Cfg2<BN, TAPS, RESB, EPI == kEpiFwdPool>;
   a.tiles_x = cdiv(a.w, kBW), a.tiles_y = cdiv(a.h, 2 * kBH), a.tiles_n = a.cout / BN;
+  a.div_x = FastDiv(a.tiles_x), a.div_y = FastDiv(a.tiles_y), a.div_n = FastDiv(a.tiles_n);
   CUtensorMap map_in, map_out, map_w, map_pool;
   {
     const uint64_t dims[4] = {(uint64_t)a.cin, (uint64_t)a.w, (uint64_t)a.h, (uint64_t)a.nb};
