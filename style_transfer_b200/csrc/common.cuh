@@ -211,6 +211,36 @@ __device__ __forceinline__ float2 unpack16(uint32_t w, bool half) {
   return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xFFFF0000u));
 }
 
+// ReLU + saturation + rounding + packing of two fp32 values in one F2FP (hi lands in the upper half)
+__device__ __forceinline__ uint32_t pack16_relu(float lo, float hi, bool half) {
+  uint32_t d;
+  if (half)
+    asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  else
+    asm("cvt.rn.relu.satfinite.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+// packed 16-bit pairs: per-half (a > b) ? 0xFFFF : 0, and the per-half maximum
+template <bool HALF>
+__device__ __forceinline__ uint32_t gt2_mask(uint32_t a, uint32_t b) {
+  if constexpr (HALF)
+    return __hgt2_mask(*reinterpret_cast<const __half2*>(&a), *reinterpret_cast<const __half2*>(&b));
+  else
+    return __hgt2_mask(*reinterpret_cast<const __nv_bfloat162*>(&a),
+                       *reinterpret_cast<const __nv_bfloat162*>(&b));
+}
+template <bool HALF>
+__device__ __forceinline__ uint32_t max2(uint32_t a, uint32_t b) {
+  if constexpr (HALF) {
+    const __half2 r = __hmax2(*reinterpret_cast<const __half2*>(&a), *reinterpret_cast<const __half2*>(&b));
+    return *reinterpret_cast<const uint32_t*>(&r);
+  } else {
+    const __nv_bfloat162 r = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&a),
+                                     *reinterpret_cast<const __nv_bfloat162*>(&b));
+    return *reinterpret_cast<const uint32_t*>(&r);
+  }
+}
+
 // ---- deterministic grid reductions ----------------------------------------------------------------
 // Each block reduces K doubles, publishes them, takes a ticket; the last block to arrive sums the
 // per-block partials in index order (fixed grid => bit-reproducible) and returns true on its

@@ -120,6 +120,7 @@ struct FirstArgs {
   const void* wk;                   // [64][64] K-major, k = tap*3 + ci for the hi half, 27 + that for lo
   const float* bias;
   void* out;                        // [nb][h][w][64], bf16 or fp16 (half)
+  uint32_t* bits;                   // ReLU bit mask of the output, [nb][h][w][2] words (may be null)
   int half;                         // operands and output are fp16
 };
 
@@ -237,15 +238,24 @@ conv_first_tc_kernel(const FirstArgs a) {
       tmem_ld32(taddr + cc * 32, r);
       float f[32];
 #pragma unroll
-      for (int i = 0; i < 32; ++i) f[i] = fmaxf(__uint_as_float(r[i]) + bias_s[cc * 32 + i], 0.f);
-      uint32_t pw[16];
+      for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(r[i]) + bias_s[cc * 32 + i];
+      // ReLU, saturation and rounding in the pack; the mask bits of the backward pass from the pairs
+      uint32_t pw[16], bits = 0u;
       if (half) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) pw[i] = pack16(f[2 * i], f[2 * i + 1], true);
+        for (int i = 0; i < 16; ++i) {
+          pw[i] = pack16_relu(f[2 * i], f[2 * i + 1], true);
+          bits |= gt2_mask<true>(pw[i], 0u) & (0x00010001u << i);
+        }
       } else {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) pw[i] = pack16(f[2 * i], f[2 * i + 1], false);
+        for (int i = 0; i < 16; ++i) {
+          pw[i] = pack16_relu(f[2 * i], f[2 * i + 1], false);
+          bits |= gt2_mask<false>(pw[i], 0u) & (0x00010001u << i);
+        }
       }
+      if (a.bits != nullptr && tx * 128 + tid < a.w)
+        a.bits[(((size_t)b * a.h + y) * a.w + tx * 128 + tid) * 2 + cc] = bits;
 #pragma unroll
       for (int j = 0; j < 4; ++j)
         *reinterpret_cast<uint4*>(row + (((cc * 4 + j) ^ (tid & 7)) << 4)) =
@@ -298,8 +308,9 @@ int tc_pack_first_fwd(TcContext& tc, TcWeights& w, const float* w_host, int cout
 }
 
 int conv_first_fwd_tc(TcContext& tc, const TcWeights& w, const ImageBatch& img, int h, int wd,
-                      const float* bias, void* out, cudaStream_t s) {
+                      const float* bias, void* out, uint32_t* relu_bits, cudaStream_t s) {
   FirstArgs a{};
+  a.bits = relu_bits;
   a.half = w.fwd_half ? 1 : 0;
   a.img = img, a.h = h, a.w = wd, a.tiles_x = cdiv(wd, 128);
   a.num_tiles = img.nb * h * a.tiles_x;

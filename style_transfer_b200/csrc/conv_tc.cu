@@ -563,9 +563,10 @@ bool tc_shape_ok(const TcContext& tc, const TcWeights& w, int cin, int cout) {
 
 int conv3x3_tc(TcContext& tc, const TcWeights& w, const void* in_v, void* out_v, int nb, int h,
                int wd, int cin, int cout, bool forward, const float* bias, const void* mask_v,
-               const __nv_bfloat16* inj, const float* inj_scale, cudaStream_t s) {
+               uint32_t* relu_bits, const __nv_bfloat16* inj, const float* inj_scale,
+               cudaStream_t s) {
   if (tc.pair_kernel)
-    return conv3x3_tc_pair(tc, w, in_v, out_v, nb, h, wd, cin, cout, forward, bias, mask_v, inj,
+    return conv3x3_tc_pair(tc, w, in_v, out_v, nb, h, wd, cin, cout, forward, bias, relu_bits, inj,
                            inj_scale, s);
   ST_REQUIRE(nb == 1 && inj_scale == nullptr && !w.fwd_half,
              "the single-CTA convolution kernel (ST_CONV_V1) takes one bf16 tile and a pre-scaled injection");

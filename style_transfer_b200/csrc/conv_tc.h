@@ -57,15 +57,22 @@ inline bool tc_usable(const TcContext& tc, const TcWeights& w, int cin, int cout
 
 // out = epilogue(conv3x3(in)) with in [nb][h][w][cin], out [nb][h][w][cout] (16-bit NHWC).
 //   forward : out = max(acc + bias, 0); operands/outputs are fp16 when w.fwd_half, else bf16
-//   backward: out = (mask_act > 0 ? acc : 0) + inj_scale[tile] * inj   (each may be null); gradients
-//             and backward weights are bf16, mask_act is the forward activation (either format)
+//   backward: out = (mask > 0 ? acc : 0) + inj_scale[tile] * inj   (each may be null); gradients
+//             and backward weights are bf16
+// The ReLU mask travels as ONE BIT per element, `relu_bits` [nb][h][w][cout/32] words (relu_bit()
+// gives the position of a channel inside its word): written by the forward kernel that produced the
+// blob (may be null: not wanted), read by the backward kernel of the layer that consumes it (may be
+// null: no ReLU).  The single-CTA kernel (ST_CONV_V1) still reads the activation `mask_act`.
 int conv3x3_tc(TcContext& tc, const TcWeights& w, const void* in, void* out, int nb, int h, int wd,
                int cin, int cout, bool forward, const float* bias, const void* mask_act,
-               const __nv_bfloat16* inj, const float* inj_scale, cudaStream_t s);
+               uint32_t* relu_bits, const __nv_bfloat16* inj, const float* inj_scale,
+               cudaStream_t s);
 // CTA-pair (cta_group::2) kernel of conv_tc2.cu; activations are [nb][h][w][c] (a batch of tiles).
 int conv3x3_tc_pair(TcContext& tc, const TcWeights& w, const void* in, void* out, int nb, int h,
-                    int wd, int cin, int cout, bool forward, const float* bias, const void* mask_act,
+                    int wd, int cin, int cout, bool forward, const float* bias, uint32_t* relu_bits,
                     const __nv_bfloat16* inj, const float* inj_scale, cudaStream_t s);
+// channel c of a 32-channel chunk sits at this bit of the chunk's mask word
+inline int relu_bit(int c) { return ((c & 31) >> 1) + 16 * (c & 1); }
 // Forward convolution + the 2x2/2 pooling layer behind it in one kernel.  pool_out [nb][ho][wo][cout]
 // receives the pooled map, pool_mask (bytes, same shape) what pool_bwd_mask needs:
 //   max: bits 0-1 = window position of the first maximum, bit 2 = maximum > 0
@@ -73,7 +80,8 @@ int conv3x3_tc_pair(TcContext& tc, const TcWeights& w, const void* in, void* out
 // `out` is written only when write_full.
 int conv3x3_pool_tc_pair(TcContext& tc, const TcWeights& w, const void* in, void* out,
                          void* pool_out, uint8_t* pool_mask, int nb, int h, int wd, int cin, int cout,
-                         const float* bias, bool is_max, bool write_full, cudaStream_t s);
+                         const float* bias, bool is_max, bool write_full, uint32_t* relu_bits,
+                         cudaStream_t s);
 // Backward of the first (3-channel) convolution on tensor cores: dz [nb][h][w][cz] bf16 -> planar f32
 // gradient; tile b goes to grad + b * batch_stride.  Needs weights packed by tc_pack_first.
 int conv_last_bwd_tc_pair(TcContext& tc, const TcWeights& w, const __nv_bfloat16* dz, int nb, int h,
@@ -83,7 +91,7 @@ int conv_last_bwd_tc_pair(TcContext& tc, const TcWeights& w, const __nv_bfloat16
 struct ImageBatch;
 int tc_pack_first_fwd(TcContext& tc, TcWeights& w, const float* w_oihw_host, int cout, bool half);
 int conv_first_fwd_tc(TcContext& tc, const TcWeights& w, const ImageBatch& img, int h, int wd,
-                      const float* bias, void* out, cudaStream_t s);
+                      const float* bias, void* out, uint32_t* relu_bits, cudaStream_t s);
 // Per batch tile b: S_b[p][n] = sum_c F_b[p][c] * D_b[n][c] for F [nb][h][w][c] and D [nb][c][c],
 // both bf16 or both fp16 (half_in); S is written as bf16.  sum |S_b| is left as partial sums
 // abs_partials[b * per_tile + i], i < *per_tile, to be added in index order; the buffer must hold
@@ -99,6 +107,13 @@ bool gram_tc_ok(const TcContext& tc, int c);
 size_t gram_tc_part_floats(const TcContext& tc, int nb, int hw, int c);
 int gram_tc(TcContext& tc, const void* f, bool half, int nb, int hw, int c, float* gram, float* part,
             cudaStream_t s);
+// The same contraction finished straight into the style term: delta[b] = G_b - target (full [C][C]),
+// tile_loss[b * loss_stride] += w * 0.5 * sum_{j<=i} delta_ij^2, max_bits[b] (optional) = max |delta_b|
+// as float bits.  G itself is not stored.
+struct ReduceScratch;
+int gram_tc_delta(TcContext& tc, const void* f, bool half, int nb, int hw, int c, float* part,
+                  const float* target, float* delta, unsigned* max_bits, double w,
+                  double* tile_loss, int loss_stride, ReduceScratch rs, cudaStream_t s);
 
 
 

@@ -226,36 +226,6 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t 
          ((uint64_t)(sbo >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
 }
 
-// ReLU + saturation + rounding + packing of two fp32 values in one F2FP (hi lands in the upper half)
-__device__ __forceinline__ uint32_t pack16_relu(float lo, float hi, bool half) {
-  uint32_t d;
-  if (half)
-    asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
-  else
-    asm("cvt.rn.relu.satfinite.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
-  return d;
-}
-// packed 16-bit pairs: per-half (a > b) ? 0xFFFF : 0, and the per-half maximum
-template <bool HALF>
-__device__ __forceinline__ uint32_t gt2_mask(uint32_t a, uint32_t b) {
-  if constexpr (HALF)
-    return __hgt2_mask(*reinterpret_cast<const __half2*>(&a), *reinterpret_cast<const __half2*>(&b));
-  else
-    return __hgt2_mask(*reinterpret_cast<const __nv_bfloat162*>(&a),
-                       *reinterpret_cast<const __nv_bfloat162*>(&b));
-}
-template <bool HALF>
-__device__ __forceinline__ uint32_t max2(uint32_t a, uint32_t b) {
-  if constexpr (HALF) {
-    const __half2 r = __hmax2(*reinterpret_cast<const __half2*>(&a), *reinterpret_cast<const __half2*>(&b));
-    return *reinterpret_cast<const uint32_t*>(&r);
-  } else {
-    const __nv_bfloat162 r = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&a),
-                                     *reinterpret_cast<const __nv_bfloat162*>(&b));
-    return *reinterpret_cast<const uint32_t*>(&r);
-  }
-}
-
 // 2x2/2 max pooling of one (pooled pixel, 8-channel) item straight on the packed 16-bit values of the
 // staged tile: per window position one HSET2 (mask of "greater than the running maximum": strict,
 // so the first maximum in scan order wins like Caffe's), one HMNMX2 and one LOP3 per channel pair.
@@ -302,7 +272,8 @@ struct Tc2Args {
                                    // in every warp role: three hardware divisions were ~100
                                    // instructions of the ~700 an epilogue warp spent per tile)
   const float* bias;               // kEpiFwd
-  const __nv_bfloat16* mask_act;   // kEpiBwd, NHWC [h][w][cout], may be null
+  const uint32_t* mask_bits;       // kEpiBwd: ReLU bit mask of the output blob (see relu_bit), may be null
+  uint32_t* bits_out;              // forward: ReLU bit mask of the output, [pixel][cout/32], may be null
   const __nv_bfloat16* inj;        // kEpiBwd, may be null
   const float* inj_scale;          // kEpiBwd: per batch tile factor applied to inj, may be null
   double* abs_partials;            // kEpiAbs: [pair tile][cta rank][epilogue warp]
@@ -563,37 +534,21 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constan
       }
       return r;
     };
-    uint4 pm[4], pe[4];
+    uint32_t pbits = 0xFFFFFFFFu;
+    uint4 pe[4];
     auto prefetch = [&](const RowRef& rr, int cc) {
       if constexpr (EPI == kEpiBwd) {
+        pbits = 0xFFFFFFFFu;                               // no mask: everything passes
+        if (rr.valid && a.mask_bits != nullptr) pbits = __ldg(a.mask_bits + (rr.gofs >> 5) + cc);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          pm[i] = make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u);   // "positive"
           pe[i] = make_uint4(0u, 0u, 0u, 0u);
-          if (rr.valid && a.mask_act != nullptr)
-            pm[i] = *reinterpret_cast<const uint4*>(a.mask_act + rr.gofs + cc * 32 + i * 8);
           if (rr.valid && a.inj != nullptr)
             pe[i] = *reinterpret_cast<const uint4*>(a.inj + rr.gofs + cc * 32 + i * 8);
         }
       }
     };
-    auto prefetch_l2 = [&](const RowRef& rr) {
-      if constexpr (EPI == kEpiBwd) {
-        if (rr.valid) {
-#pragma unroll
-          for (int g = 0; g < BN / 64; ++g) {
-            const size_t o = rr.gofs + (size_t)(g * 2 + hsel) * 32;
-            if (a.mask_act != nullptr)
-              asm volatile("prefetch.global.L2 [%0];" ::"l"(a.mask_act + o));
-            if (a.inj != nullptr) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.inj + o));
-          }
-        }
-      }
-    };
-    if constexpr (EPI == kEpiBwd) {
-      prefetch(row_of(pair), hsel);
-      prefetch_l2(row_of(pair + num_pairs));
-    }
+    if constexpr (EPI == kEpiBwd) prefetch(row_of(pair), hsel);
     for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
       const uint32_t buf = it & 1, use = it >> 1;
       const TileCoord t = decode_tile(a, tile, (int)rank);
@@ -602,11 +557,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constan
       const bool valid = py < a.h && px < a.w;
       const RowRef cur{(((size_t)t.b * a.h + py) * a.w + px) * a.cout + (size_t)n_tile * BN, valid};
       RowRef nxt{0, false};
-      (void)cur;
-      if constexpr (EPI == kEpiBwd) {
-        nxt = row_of(tile + num_pairs);
-        prefetch_l2(row_of(tile + 2 * num_pairs));
-      }
+      if constexpr (EPI == kEpiBwd) nxt = row_of(tile + num_pairs);
       float abs_tile = 0.f;
       float inj_sc = 1.f;
       if constexpr (EPI == kEpiBwd) {
@@ -649,24 +600,24 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constan
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] += bs[i];      // ReLU happens in the pack below
           } else if constexpr (EPI == kEpiBwd) {
-            uint4 cm[4], ce[4];
+            uint4 ce[4];
+            const uint32_t cbits = pbits;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) cm[i] = pm[i], ce[i] = pe[i];
+            for (int i = 0; i < 4; ++i) ce[i] = pe[i];
             if (cc + 2 < BN / 32)
               prefetch(cur, cc + 2);
             else
               prefetch(nxt, hsel);                   // first chunk of this warp in the next tile
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-              const uint32_t m4[4] = {cm[i].x, cm[i].y, cm[i].z, cm[i].w};
               const uint32_t e4[4] = {ce[i].x, ce[i].y, ce[i].z, ce[i].w};
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
-                // bf16 > 0  <=>  sign clear and magnitude non-zero
-                const uint32_t lo = m4[j] & 0xFFFFu, hi = m4[j] >> 16;
+                // ReLU mask of the forward activation: bit (pair index) = even channel of the pair,
+                // bit (16 + pair index) = odd channel (relu_bit)
                 float x0 = v[8 * i + 2 * j], x1 = v[8 * i + 2 * j + 1];
-                if (!(lo != 0u && lo < 0x8000u)) x0 = 0.f;
-                if (!(hi != 0u && hi < 0x8000u)) x1 = 0.f;
+                if (!(cbits & (1u << (4 * i + j)))) x0 = 0.f;
+                if (!(cbits & (0x10000u << (4 * i + j)))) x1 = 0.f;
                 v[8 * i + 2 * j] = fmaf(inj_sc, __uint_as_float(e4[j] << 16), x0);
                 v[8 * i + 2 * j + 1] = fmaf(inj_sc, __uint_as_float(e4[j] & 0xFFFF0000u), x1);
               }
@@ -713,6 +664,21 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constan
             const int chunk = hh * 4 + j;
             *reinterpret_cast<uint4*>(row + ((chunk ^ (m & 7)) << 4)) =
                 make_uint4(pw[4 * j], pw[4 * j + 1], pw[4 * j + 2], pw[4 * j + 3]);
+          }
+          if constexpr (kFwd) {
+            // ReLU bit mask of this pixel's 32 channels for the backward pass: 16x less HBM traffic
+            // than re-reading the activation there (one HSET2 + one LOP3 per channel pair)
+            if (a.bits_out != nullptr) {
+              uint32_t bits = 0u;
+              if (out_half) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) bits |= gt2_mask<true>(pw[i], 0u) & (0x00010001u << i);
+              } else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) bits |= gt2_mask<false>(pw[i], 0u) & (0x00010001u << i);
+              }
+              if (valid) a.bits_out[(cur.gofs >> 5) + cc] = bits;
+            }
           }
         }
         if (g == BN / 64 - 1) {
@@ -924,14 +890,17 @@ int dispatch_bn(TcContext& tc, int bn, const void* in, const void* wk, int wk_ro
 }  // namespace
 
 int conv3x3_tc_pair(TcContext& tc, const TcWeights& w, const void* in, void* out, int nb, int h,
-                    int wd, int cin, int cout, bool forward, const float* bias, const void* mask_act,
+                    int wd, int cin, int cout, bool forward, const float* bias, uint32_t* relu_bits,
                     const __nv_bfloat16* inj, const float* inj_scale, cudaStream_t s) {
   Tc2Args a{};
   a.nb = nb, a.h = h, a.w = wd, a.cin = cin, a.cout = cout;
   // forward: activations in the context's activation format; backward: gradients are always bf16
   a.in_half = a.out_half = (forward && w.fwd_half) ? 1 : 0;
-  a.bias = bias, a.mask_act = static_cast<const __nv_bfloat16*>(mask_act), a.inj = inj,
-  a.inj_scale = inj_scale;
+  a.bias = bias, a.inj = inj, a.inj_scale = inj_scale;
+  if (forward)
+    a.bits_out = relu_bits;
+  else
+    a.mask_bits = relu_bits;
   const int bn = choose_bn(tc, nb, h, wd, cout);
   if (forward) return dispatch_bn<9, kEpiFwd>(tc, bn, in, w.fwd, cout, out, a, s);
   return dispatch_bn<9, kEpiBwd>(tc, bn, in, w.bwd, cout, out, a, s);
@@ -941,9 +910,10 @@ int conv3x3_tc_pair(TcContext& tc, const TcWeights& w, const void* in, void* out
 // the backward mask and (write_full) the un-pooled output.
 int conv3x3_pool_tc_pair(TcContext& tc, const TcWeights& w, const void* in, void* out,
                          void* pool_out, uint8_t* pool_mask, int nb, int h, int wd, int cin, int cout,
-                         const float* bias, bool is_max, bool write_full, cudaStream_t s) {
+                         const float* bias, bool is_max, bool write_full, uint32_t* relu_bits,
+                         cudaStream_t s) {
   Tc2Args a{};
-  a.nb = nb, a.h = h, a.w = wd, a.cin = cin, a.cout = cout, a.bias = bias;
+  a.nb = nb, a.h = h, a.w = wd, a.cin = cin, a.cout = cout, a.bias = bias, a.bits_out = relu_bits;
   a.in_half = a.out_half = w.fwd_half ? 1 : 0;
   a.pool_mode = is_max ? 1 : 2, a.write_full = write_full ? 1 : 0, a.pool_mask = pool_mask;
   const int bn = choose_bn(tc, nb, h, wd, cout);

@@ -72,6 +72,12 @@ struct BlobRt {
   bool relu = false;         // conv output (carries an in-place ReLU)
   void* act = nullptr;
   size_t act_cap = 0;        // elements
+  // ReLU bit mask of `act` ([pixel][c/32] words) for the tensor-core backward pass: written by the
+  // forward kernel that produced the blob; 16x smaller than the activation the backward epilogue
+  // would otherwise re-read
+  uint32_t* bits = nullptr;
+  size_t bits_cap = 0;       // words
+  bool bits_valid = false;
   void* inj = nullptr;
   size_t inj_cap = 0;
   // When the only loss term of a blob is one style term, the style GEMM writes its raw output S
@@ -222,21 +228,37 @@ int fused_pool_layer(const st_ctx* ctx, int i, int last_layer) {
 
 template <typename T>
 int forward(st_ctx* ctx, const ImageBatch& view, const Dims& d, int last_layer,
-            const std::vector<char>& need_full, cudaStream_t s) {
+            const std::vector<char>& need_full, bool for_backward, cudaStream_t s) {
   const int nb = view.nb;
   for (LayerRt& l : ctx->layers) l.pool_mask_valid = false;
+  for (BlobRt& b : ctx->blobs) b.bits_valid = false;
   for (int i = 0; i <= last_layer; ++i) {
     LayerRt& l = ctx->layers[i];
     const int hb = d.h[l.bottom], wb = d.w[l.bottom];
     T* out = static_cast<T*>(ctx->blobs[l.top].act);
     int rc;
+    // the ReLU bit mask of this layer's output is wanted when a convolution consumes the blob and a
+    // backward pass follows (its backward epilogue applies the mask)
+    uint32_t* bits_out = nullptr;
+    if (for_backward && l.kind == ST_CONV3X3 && sizeof(T) == 2 && ctx->tc.enabled && ctx->tc.pair_kernel) {
+      bool wanted = false;
+      for (int j = i + 1; j <= last_layer; ++j)
+        wanted = wanted || (ctx->layers[j].kind == ST_CONV3X3 && ctx->layers[j].bottom == l.top);
+      if (wanted) {
+        BlobRt& tb = ctx->blobs[l.top];
+        rc = ensure(ctx, (void**)&tb.bits, &tb.bits_cap, (size_t)nb * hb * wb * (l.cout / 32), 4);
+        if (rc != ST_OK) return rc;
+        bits_out = tb.bits;
+      }
+    }
     if (l.kind == ST_CONV3X3) {
       ST_REQUIRE(l.has_params, "conv layer has no weights (st_set_conv_params)");
       if (l.bottom == 0) {
         bool done = false;
         if constexpr (sizeof(T) == 2) {
           if (ctx->tc.enabled && ctx->tc.pair_kernel && l.tc.fwd != nullptr && l.cout == 64) {
-            rc = conv_first_fwd_tc(ctx->tc, l.tc, view, hb, wb, l.bias, out, s);
+            rc = conv_first_fwd_tc(ctx->tc, l.tc, view, hb, wb, l.bias, out, bits_out, s);
+            ctx->blobs[l.top].bits_valid = bits_out != nullptr && rc == ST_OK;
             done = true;
           }
         }
@@ -256,13 +278,15 @@ int forward(st_ctx* ctx, const ImageBatch& view, const Dims& d, int last_layer,
             if (rc == ST_OK)
               rc = conv3x3_pool_tc_pair(ctx->tc, l.tc, in, out, static_cast<T*>(ctx->blobs[p.top].act),
                                         p.pool_mask, nb, hb, wb, l.cin, l.cout, l.bias,
-                                        p.kind == ST_POOL_MAX, full, s);
+                                        p.kind == ST_POOL_MAX, full, full ? bits_out : nullptr, s);
+            ctx->blobs[l.top].bits_valid = full && bits_out != nullptr && rc == ST_OK;
             p.pool_mask_valid = rc == ST_OK;
             ++i;                                  // the pooling layer is done
           }
         } else if (tc_usable<T>(ctx->tc, l.tc, l.cin, l.cout)) {
           rc = conv3x3_tc(ctx->tc, l.tc, in, out, nb, hb, wb, l.cin, l.cout, true, l.bias, nullptr,
-                          nullptr, nullptr, s);
+                          bits_out, nullptr, nullptr, s);
+          ctx->blobs[l.top].bits_valid = bits_out != nullptr && rc == ST_OK;
         } else {
           if constexpr (std::is_same<T, __half>::value) {
             set_error("invalid: ST_PREC_FP16 has no SIMT convolution (channels must be multiples of 64)");
@@ -344,7 +368,12 @@ int build_injection(st_ctx* ctx, const st_loss_spec& sp, const Dims& d, const Ba
           size_t cap = ctx->part_floats;
           rc = ensure(ctx, (void**)&ctx->part, &cap, gram_tc_part_floats(ctx->tc, nb, hf * wf, c), 4);
           ctx->part_floats = cap;
-          if (rc == ST_OK) rc = gram_tc(ctx->tc, f, kHalf, nb, hf * wf, c, ctx->gram, ctx->part, s);
+          // Gram contraction, then split reduction + delta + loss + max |delta| in one kernel
+          if (rc == ST_OK)
+            rc = gram_tc_delta(ctx->tc, f, kHalf, nb, hf * wf, c, ctx->part, it->second, ctx->delta,
+                               kHalf ? ctx->delta_max : nullptr, w, tile_loss, kStatStride, ctx->rs, s);
+          if (rc == ST_OK)
+            rc = delta_pack(ctx->delta, ctx->delta_16, kHalf, ctx->delta_max, ctx->eps_eff, c, nb, s);
         }
       } else {
         if constexpr (kHalf) {
@@ -356,9 +385,9 @@ int build_injection(st_ctx* ctx, const st_loss_spec& sp, const Dims& d, const Ba
                              ctx->sm_count, s);
         }
       }
-      if (rc == ST_OK)
-        rc = gram_delta(ctx->gram, it->second, ctx->delta, on_tc ? ctx->delta_16 : nullptr, kHalf,
-                        ctx->delta_max, ctx->eps_eff, c, nb, w, tile_loss, kStatStride, ctx->rs, s);
+      if (rc == ST_OK && !on_tc)
+        rc = gram_delta(ctx->gram, it->second, ctx->delta, nullptr, kHalf, ctx->delta_max,
+                        ctx->eps_eff, c, nb, w, tile_loss, kStatStride, ctx->rs, s);
       if (rc != ST_OK) return rc;
       const float* eps_eff = on_tc ? ctx->eps_eff : nullptr;
       // the scale-and-copy pass over S can be skipped when S is this blob's whole injection and a
@@ -437,11 +466,28 @@ int backward(st_ctx* ctx, const Dims& d, int nb, int deepest_blob, const std::ve
     int rc;
     if (l.kind == ST_CONV3X3) {
       if (tc_usable<T>(ctx->tc, l.tc, l.cout, l.cin)) {
-        if constexpr (sizeof(T) == 2)
-          rc = conv3x3_tc(ctx->tc, l.tc, g, out, nb, hb, wb, l.cout, l.cin, false, nullptr, mask, inj,
-                          inj_scale, s);
-        else
+        if constexpr (sizeof(T) == 2) {
+          // ReLU mask of the bottom blob as bits; made here from the activation when the kernel
+          // that produced the blob did not write them
+          BlobRt& bm = ctx->blobs[b];
+          uint32_t* bits = nullptr;
+          rc = ST_OK;
+          if (bb.relu && ctx->tc.pair_kernel) {
+            if (!bm.bits_valid) {
+              rc = ensure(ctx, (void**)&bm.bits, &bm.bits_cap, (size_t)nb * hb * wb * (l.cin / 32), 4);
+              if (rc == ST_OK)
+                rc = relu_bits_from_act<TA>(static_cast<const TA*>(bm.act), bm.bits,
+                                            (size_t)nb * hb * wb, l.cin, s);
+              bm.bits_valid = rc == ST_OK;
+            }
+            bits = bm.bits;
+          }
+          if (rc == ST_OK)
+            rc = conv3x3_tc(ctx->tc, l.tc, g, out, nb, hb, wb, l.cout, l.cin, false, nullptr, mask,
+                            bits, inj, inj_scale, s);
+        } else {
           rc = ST_ERR_INVALID;
+        }
       } else {
         ST_REQUIRE(inj_scale == nullptr, "deferred injection scale needs the tensor-core convolution");
         if constexpr (std::is_same<TA, T>::value) {
@@ -493,7 +539,7 @@ int eval_batch(st_ctx* ctx, const ImageBatch& view, int h, int w, const BatchGeo
   const int last_layer = ctx->blobs[deepest].producer;
   const Dims d = blob_dims(ctx, h, w);
   int rc = reserve_for(ctx, d, last_layer, g.nb);
-  if (rc == ST_OK) rc = forward<TA>(ctx, view, d, last_layer, has_inj, s);
+  if (rc == ST_OK) rc = forward<TA>(ctx, view, d, last_layer, has_inj, true, s);
   for (int i = 0; i < n_specs && rc == ST_OK; ++i)
     rc = build_injection<TA, T>(ctx, specs[i], d, g, froll_y, froll_x, specs[i].blob == deepest, s);
   if (rc == ST_OK) rc = loss_finalize(ctx->scalars + 3, kStatStride, g.nb, loss_accum, s);
@@ -652,7 +698,7 @@ int st_destroy(st_ctx* ctx) {
     cudaFree(l.w_fwd), cudaFree(l.w_bwd), cudaFree(l.bias), cudaFree(l.pool_mask);
     tc_free_weights(l.tc);
   }
-  for (BlobRt& b : ctx->blobs) cudaFree(b.act), cudaFree(b.inj), cudaFree(b.inj_scale);
+  for (BlobRt& b : ctx->blobs) cudaFree(b.act), cudaFree(b.inj), cudaFree(b.inj_scale), cudaFree(b.bits);
   cudaFree(ctx->gbuf[0]), cudaFree(ctx->gbuf[1]), cudaFree(ctx->sbuf);
   cudaFree(ctx->gram), cudaFree(ctx->delta), cudaFree(ctx->part), cudaFree(ctx->scalars);
   cudaFree(ctx->delta_16), cudaFree(ctx->abs_partials), cudaFree(ctx->eps_eff);
@@ -794,10 +840,10 @@ int st_eval_features_tile(st_ctx* ctx, const float* img_dev, int h, int w, int n
   std::vector<char> need_full(ctx->blobs.size(), 0);
   for (int i = 0; i < n_blobs; ++i) need_full[blob_ids[i]] = 1;
   rc = ctx->precision == ST_PREC_FP32
-           ? forward<float>(ctx, view, d, last_layer, need_full, s)
-           : (ctx->precision == ST_PREC_FP16 ? forward<__half>(ctx, view, d, last_layer, need_full, s)
-                                             : forward<__nv_bfloat16>(ctx, view, d, last_layer,
-                                                                      need_full, s));
+           ? forward<float>(ctx, view, d, last_layer, need_full, false, s)
+           : (ctx->precision == ST_PREC_FP16
+                  ? forward<__half>(ctx, view, d, last_layer, need_full, false, s)
+                  : forward<__nv_bfloat16>(ctx, view, d, last_layer, need_full, false, s));
   for (int i = 0; i < n_blobs && rc == ST_OK; ++i) {
     const int b = blob_ids[i];
     const int hw = d.h[b] * d.w[b];

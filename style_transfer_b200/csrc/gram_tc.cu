@@ -289,6 +289,52 @@ gram_tc_finalize_kernel(const float* __restrict__ part, int nsplit, int c, doubl
   out[(size_t)j * c + i] = g;
 }
 
+// The same reduction of the split partials fused with what the style term needs from the Gram matrix
+// (style_transfer.py:587,591): delta = G - G_style (both triangles), the tile's loss term
+// w * 0.5 * sum_{j<=i} delta^2 (blocks reduced in index order: deterministic) and max |delta| (float
+// bits, for the fp16 scaling of the style GEMM operand).  Replaces gram_tc_finalize + gram_delta: one
+// launch and no round trip of G through memory per style layer.
+struct GramFinish {
+  const float* target;     // [C][C] symmetric
+  float* delta;            // [nb][C][C]
+  unsigned* max_bits;      // [nb] or null
+  double w;
+  double* tile_loss;
+  int loss_stride;
+  ReduceScratch rs;
+};
+
+__global__ void __launch_bounds__(128)
+gram_tc_finish_kernel(const float* __restrict__ part, int nsplit, int c, double scale,
+                      const GramFinish fin) {
+  const int i = blockIdx.y, j = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.z;
+  double v[1] = {0.0};
+  float mx = 0.f;
+  if (j <= i) {
+    const size_t cc = (size_t)c * c;
+    const float* p = part + (size_t)b * nsplit * cc + (size_t)i * c + j;
+    double sum = 0.0;
+#pragma unroll 4
+    for (int s = 0; s < nsplit; ++s) sum += (double)p[(size_t)s * cc];
+    const float g = (float)(sum * scale);
+    const float d = g - fin.target[(size_t)i * c + j];
+    float* out = fin.delta + (size_t)b * cc;
+    out[(size_t)i * c + j] = d;
+    out[(size_t)j * c + i] = d;
+    mx = fabsf(d);
+    v[0] = (double)d * d;
+  }
+  if (fin.max_bits != nullptr) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((threadIdx.x & 31) == 0 && mx > 0.f) atomicMax(fin.max_bits + b, __float_as_uint(mx));
+  }
+  const unsigned nblk = gridDim.x * gridDim.y;
+  if (grid_reduce_impl<1>(v, fin.rs.partials + (size_t)b * nblk, fin.rs.counter + b,
+                          blockIdx.y * gridDim.x + blockIdx.x, nblk))
+    fin.tile_loss[(size_t)b * fin.loss_stride] += fin.w * 0.5 * v[0];
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
                                   const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -311,7 +357,7 @@ int gram_splits(int hw) {
 
 template <int C>
 int launch_gram(TcContext& tc, const void* f, bool half, int nb, int hw, float* gram, float* part,
-                cudaStream_t s) {
+                const GramFinish* fin, cudaStream_t s) {
   using Cfg = GramCfg<C>;
   CUtensorMap map_f;
   {
@@ -336,8 +382,13 @@ int launch_gram(TcContext& tc, const void* f, bool half, int nb, int hw, float* 
   ST_CUDA(tc_allow_smem(kern, Cfg::kSmemBytes));
   TimerScope ts(s, kTimeGram, 2.0 * C * C * hw * nb);
   ST_LAUNCH(kern, dim3(a.nsplit * Cfg::kMBlocks, nb), kGThreads, Cfg::kSmemBytes, s, map_f, a);
-  ST_LAUNCH(gram_tc_finalize_kernel, dim3(cdiv(C, 128), C, nb), 128, 0, s, part, a.nsplit, C,
-            1.0 / ((double)C * hw), gram);
+  if (fin != nullptr) {
+    ST_LAUNCH(gram_tc_finish_kernel, dim3(cdiv(C, 128), C, nb), 128, 0, s, part, a.nsplit, C,
+              1.0 / ((double)C * hw), *fin);
+  } else {
+    ST_LAUNCH(gram_tc_finalize_kernel, dim3(cdiv(C, 128), C, nb), 128, 0, s, part, a.nsplit, C,
+              1.0 / ((double)C * hw), gram);
+  }
   return ST_OK;
 }
 
@@ -358,16 +409,31 @@ size_t gram_tc_part_floats(const TcContext& tc, int nb, int hw, int c) {
   return (size_t)nb * nsplit * c * c;
 }
 
-int gram_tc(TcContext& tc, const void* f, bool half, int nb, int hw, int c, float* gram, float* part,
-            cudaStream_t s) {
+static int gram_dispatch(TcContext& tc, const void* f, bool half, int nb, int hw, int c, float* gram,
+                         float* part, const GramFinish* fin, cudaStream_t s) {
   switch (c) {
-    case 64: return launch_gram<64>(tc, f, half, nb, hw, gram, part, s);
-    case 128: return launch_gram<128>(tc, f, half, nb, hw, gram, part, s);
-    case 256: return launch_gram<256>(tc, f, half, nb, hw, gram, part, s);
-    case 512: return launch_gram<512>(tc, f, half, nb, hw, gram, part, s);
+    case 64: return launch_gram<64>(tc, f, half, nb, hw, gram, part, fin, s);
+    case 128: return launch_gram<128>(tc, f, half, nb, hw, gram, part, fin, s);
+    case 256: return launch_gram<256>(tc, f, half, nb, hw, gram, part, fin, s);
+    case 512: return launch_gram<512>(tc, f, half, nb, hw, gram, part, fin, s);
   }
   set_error("gram_tc: unsupported channel count");
   return ST_ERR_INVALID;
+}
+
+int gram_tc(TcContext& tc, const void* f, bool half, int nb, int hw, int c, float* gram, float* part,
+            cudaStream_t s) {
+  return gram_dispatch(tc, f, half, nb, hw, c, gram, part, nullptr, s);
+}
+
+int gram_tc_delta(TcContext& tc, const void* f, bool half, int nb, int hw, int c, float* part,
+                  const float* target, float* delta, unsigned* max_bits, double w,
+                  double* tile_loss, int loss_stride, ReduceScratch rs, cudaStream_t s) {
+  ST_REQUIRE((size_t)nb * cdiv(c, 128) * c <= (size_t)kMaxReduceBlocks,
+             "gram_tc_delta: batch too large for the reduction scratch");
+  if (max_bits != nullptr) ST_CUDA(cudaMemsetAsync(max_bits, 0, nb * sizeof(unsigned), s));
+  const GramFinish fin{target, delta, max_bits, w, tile_loss, loss_stride, rs};
+  return gram_dispatch(tc, f, half, nb, hw, c, nullptr, part, &fin, s);
 }
 
 }  // namespace st

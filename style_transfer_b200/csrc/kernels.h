@@ -75,6 +75,10 @@ int gram_full(const T* f, int hw, int c, bool channel_major, float* gram, float*
 int gram_delta(const float* gram, const float* target, float* delta, void* delta_16, bool half,
                unsigned* max_bits, float* eps_eff, int c, int nb, double w, double* tile_loss,
                int loss_stride, ReduceScratch rs, cudaStream_t s);
+// The 16-bit copy of delta alone (second half of gram_delta): bf16, or fp16 scaled per tile by the
+// power of two derived from max_bits[b]; eps_eff[b] as in gram_delta.
+int delta_pack(const float* delta, void* delta_16, bool half, unsigned* max_bits, float* eps_eff,
+               int c, int nb, cudaStream_t s);
 // out[b * out_stride] = sum(partials[b*n .. b*n+n)) in a launch-independent order; if scale is not
 // null also scale[b] = w / (sum / count + EPS)
 int sum_partials(const double* partials, int n, int nb, double* out, int out_stride, float* scale,
@@ -107,6 +111,11 @@ int diff_inject(const TA* f, int nb, int hf, int wf, int c, const float* tgt, in
                 const TargetOffsets& offs, const double* stats, int stat_stride, float w,
                 double loss_w, double* tile_loss, int loss_stride, T* inj, bool accumulate,
                 cudaStream_t s);
+
+// bits[p][c/32] = ReLU mask of act [p][c] (one bit per element, position relu_bit() of conv_tc.h):
+// the fallback for blobs whose producing kernel did not write the mask itself.
+template <typename T>
+int relu_bits_from_act(const T* act, uint32_t* bits, size_t pixels, int c, cudaStream_t s);
 
 // ---- layout conversion ---------------------------------------------------------------------------
 template <typename T>

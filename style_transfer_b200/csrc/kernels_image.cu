@@ -127,13 +127,31 @@ regularizers_kernel(const float* __restrict__ img, int H, int W, float m0, float
     const int y0 = trow * kRTH, x0 = (rem - trow * rt.tiles_x) * kRTW;
     const float* pl = img + (size_t)c * H * W;
     if (do_tv) {
+      // all of a thread's halo loads are issued before the first one is used (a rolled load ->
+      // store loop paid one DRAM latency per element: 27 % of this kernel's stall samples,
+      // profiles/r01_laggards_ncu.md)
+      constexpr int kHalo = (kRTH + 2) * (kRTW + 2), kHaloIt = (kHalo + kRThreads - 1) / kRThreads;
+      float hv[kHaloIt];
+#pragma unroll
+      for (int u = 0; u < kHaloIt; ++u) {
+        const int i = threadIdx.x + u * kRThreads;
+        hv[u] = 0.f;
+        if (i < kHalo) {
+          const int r = i / (kRTW + 2), q = i - r * (kRTW + 2);
+          int yy = y0 - 1 + r, xx = x0 - 1 + q;             // periodic (num_utils.py:150-162)
+          if (yy < 0 || yy >= H) yy = wrap(yy, H);
+          if (xx < 0 || xx >= W) xx = wrap(xx, W);
+          hv[u] = pl[(size_t)yy * W + xx];
+        }
+      }
       __syncthreads();                                      // previous tile's readers are done
-      for (int i = threadIdx.x; i < (kRTH + 2) * (kRTW + 2); i += kRThreads) {
-        const int r = i / (kRTW + 2), q = i - r * (kRTW + 2);
-        int yy = y0 - 1 + r, xx = x0 - 1 + q;               // periodic (num_utils.py:150-162)
-        if (yy < 0 || yy >= H) yy = wrap(yy, H);
-        if (xx < 0 || xx >= W) xx = wrap(xx, W);
-        xs[r][q] = pl[(size_t)yy * W + xx] * inv;
+#pragma unroll
+      for (int u = 0; u < kHaloIt; ++u) {
+        const int i = threadIdx.x + u * kRThreads;
+        if (i < kHalo) {
+          const int r = i / (kRTW + 2), q = i - r * (kRTW + 2);
+          xs[r][q] = hv[u] * inv;
+        }
       }
       __syncthreads();
     }
@@ -146,12 +164,36 @@ regularizers_kernel(const float* __restrict__ img, int H, int W, float m0, float
       txx = min((int)ug.div_tw.div(xr), ug.ntx - 1);
     }
     const float mean = c == 0 ? m0 : (c == 1 ? m1 : m2);
+    // the global operands of this thread's four rows are requested together, then consumed
+    float raw_k[kRRows], base_k[kRRows], aux_k[kRRows];
+#pragma unroll
+    for (int k = 0; k < kRRows; ++k) {
+      const int y = y0 + ty0 + k * (kRThreads / kRTW);
+      raw_k[k] = base_k[k] = aux_k[k] = 0.f;
+      if (x >= W || y >= H) continue;
+      raw_k[k] = pl[(size_t)y * W + x];
+      if (packed != nullptr) {               // fused st_unpack_grad
+        int yr = y + ug.roll_y;
+        yr = yr >= H ? yr - H : yr;
+        const int tyy = min((int)ug.div_th.div(yr), ug.nty - 1);
+        const int t = tyy * ug.ntx + txx;
+        const int slot = (int)ug.div_world.div(t), rank = t - slot * ug.world;
+        const size_t pb = ((size_t)(rank * ug.tiles_per_rank + slot) * 3 + c) * ug.thmax * ug.twmax;
+        base_k[k] = packed[pb + (size_t)(yr - tyy * ug.th) * ug.twmax + (xr - txx * ug.tw)];
+      } else {
+        base_k[k] = grad[((size_t)c * H + y) * W + x];
+      }
+      if (aux != nullptr) {
+        const int ya = wrap(y + roll_y, H), xa = wrap(x + roll_x, W);
+        aux_k[k] = aux[((size_t)c * H + ya) * W + xa];
+      }
+    }
 #pragma unroll
     for (int k = 0; k < kRRows; ++k) {
       const int ty = ty0 + k * (kRThreads / kRTW), y = y0 + ty;
       if (x >= W || y >= H) continue;
       const size_t i = ((size_t)c * H + y) * W + x;
-      const float raw = pl[(size_t)y * W + x];
+      const float raw = raw_k[k];
       float g = 0.f, l = 0.f;
       if (do_tv) {
         // own term and the terms of the left / upper neighbour (their d/d(dx), d/d(dy) reach here)
@@ -180,23 +222,10 @@ regularizers_kernel(const float* __restrict__ img, int H, int W, float m0, float
         }
       }
       if (aux != nullptr) {
-        const int ya = wrap(y + roll_y, H), xa = wrap(x + roll_x, W);
-        const float d = (raw - aux[((size_t)c * H + ya) * W + xa]) * inv;
+        const float d = (raw - aux_k[k]) * inv;
         l += aux_w * 0.5f * d * d, g += aux_w * d;
       }
-      float base;
-      if (packed != nullptr) {               // fused st_unpack_grad
-        int yr = y + ug.roll_y;
-        yr = yr >= H ? yr - H : yr;
-        const int tyy = min((int)ug.div_th.div(yr), ug.nty - 1);
-        const int t = tyy * ug.ntx + txx;
-        const int slot = (int)ug.div_world.div(t), rank = t - slot * ug.world;
-        const size_t pb = ((size_t)(rank * ug.tiles_per_rank + slot) * 3 + c) * ug.thmax * ug.twmax;
-        base = packed[pb + (size_t)(yr - tyy * ug.th) * ug.twmax + (xr - txx * ug.tw)];
-      } else {
-        base = grad[i];
-      }
-      grad[i] = base + g;
+      grad[i] = base_k[k] + g;
       part += l;
     }
     if (++since_flush == 4) v[0] += (double)part, part = 0.f, since_flush = 0;

@@ -635,9 +635,14 @@ int gram_delta(const float* gram, const float* target, float* delta, void* delta
   if (track) ST_CUDA(cudaMemsetAsync(max_bits, 0, nb * sizeof(unsigned), s));
   ST_LAUNCH(gram_delta_kernel, dim3(min(cdiv((long)c * c, 256), 256), nb), 256, 0, s, gram, target,
             delta, track ? max_bits : nullptr, c, w, tile_loss, loss_stride, rs);
-  if (delta_16 != nullptr)
-    ST_LAUNCH(delta_pack_kernel, dim3(min(cdiv((long)c * c, 256), 64), nb), 256, 0, s, delta,
-              static_cast<uint16_t*>(delta_16), max_bits, eps_eff, c, half ? 1 : 0);
+  if (delta_16 != nullptr) return delta_pack(delta, delta_16, half, max_bits, eps_eff, c, nb, s);
+  return ST_OK;
+}
+
+int delta_pack(const float* delta, void* delta_16, bool half, unsigned* max_bits, float* eps_eff,
+               int c, int nb, cudaStream_t s) {
+  ST_LAUNCH(delta_pack_kernel, dim3(min(cdiv((long)c * c, 256), 64), nb), 256, 0, s, delta,
+            static_cast<uint16_t*>(delta_16), max_bits, eps_eff, c, half ? 1 : 0);
   return ST_OK;
 }
 
@@ -927,6 +932,34 @@ int diff_inject(const TA* f, int nb, int hf, int wf, int c, const float* tgt, in
             stat_stride, w, loss_w, tile_loss, loss_stride, inj, accumulate ? 1 : 0);
   return ST_OK;
 }
+
+// One thread per 32-channel chunk: bit (e >> 1) + 16 * (e & 1) of the word = act[chunk * 32 + e] > 0.
+template <typename T>
+__global__ void relu_bits_kernel(const T* __restrict__ act, uint32_t* __restrict__ bits, size_t words) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < words;
+       i += (size_t)gridDim.x * blockDim.x) {
+    uint32_t w = 0u;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const F8 v = ld8(act + i * 32 + q * 8);
+#pragma unroll
+      for (int e = 0; e < 8; ++e)
+        if (v.v[e] > 0.f) w |= 1u << (((q * 8 + e) >> 1) + 16 * (e & 1));
+    }
+    bits[i] = w;
+  }
+}
+
+template <typename T>
+int relu_bits_from_act(const T* act, uint32_t* bits, size_t pixels, int c, cudaStream_t s) {
+  ST_REQUIRE(c % 32 == 0, "relu_bits: channels must be a multiple of 32");
+  const size_t words = pixels * (size_t)(c / 32);
+  auto k = relu_bits_kernel<T>;
+  ST_LAUNCH(k, ew_grid(words, 256), 256, 0, s, act, bits, words);
+  return ST_OK;
+}
+template int relu_bits_from_act<__nv_bfloat16>(const __nv_bfloat16*, uint32_t*, size_t, int, cudaStream_t);
+template int relu_bits_from_act<__half>(const __half*, uint32_t*, size_t, int, cudaStream_t);
 
 // =====================================================================================================
 // Layout conversion at the C-ABI boundary: NHWC (internal) <-> NCHW float32 (reference layout).
