@@ -167,16 +167,22 @@ conv_first_tc_kernel(const FirstArgs a) {
 #pragma unroll
     for (int k = 0; k < 32; ++k) v[k] = 0.f;
     if (x < a.w) {
+      // the tile origin arrives reduced to [0, H) x [0, W) (host) and a tile is no larger than the
+      // image, so the virtual roll wraps with one conditional add / subtract (an integer modulo per
+      // neighbour was a fifth of this kernel's instructions)
+      const int oy = a.img.oy[b], ox = a.img.ox[b];
 #pragma unroll
       for (int ky = 0; ky < 3; ++ky) {
         const int yy = y + ky - 1;
         if (yy < 0 || yy >= a.h) continue;                      // zero padding of the TILE
-        const int cy = wrap(a.img.oy[b] + yy, a.img.H);        // virtual roll of the image
+        int cy = oy + yy;                                       // virtual roll of the image
+        cy = cy < 0 ? cy + a.img.H : (cy >= a.img.H ? cy - a.img.H : cy);
 #pragma unroll
         for (int kx = 0; kx < 3; ++kx) {
           const int xx = x + kx - 1;
           if (xx < 0 || xx >= a.w) continue;
-          const int cx = wrap(a.img.ox[b] + xx, a.img.W);
+          int cx = ox + xx;
+          cx = cx < 0 ? cx + a.img.W : (cx >= a.img.W ? cx - a.img.W : cx);
           const float* p = base + (size_t)cy * a.img.W + cx;
 #pragma unroll
           for (int ci = 0; ci < 3; ++ci) v[(ky * 3 + kx) * 3 + ci] = __ldg(p + ci * plane);
@@ -200,9 +206,13 @@ conv_first_tc_kernel(const FirstArgs a) {
       float xk[64];
 #pragma unroll
       for (int k = 0; k < 64; ++k) xk[k] = k < 27 ? hi[k] : (k < 54 ? lo[k - 27] : 0.f);
+      // pixels are a few hundred grey levels at most: no saturation needed (pack16 clamps fp16)
       if (half) {                            // one uniform branch, not one per packed word
 #pragma unroll
-        for (int k = 0; k < 32; ++k) kv[k] = pack16(xk[2 * k], xk[2 * k + 1], true);
+        for (int k = 0; k < 32; ++k) {
+          const __half2 h2 = __floats2half2_rn(xk[2 * k], xk[2 * k + 1]);
+          kv[k] = *reinterpret_cast<const uint32_t*>(&h2);
+        }
       } else {
 #pragma unroll
         for (int k = 0; k < 32; ++k) kv[k] = pack16(xk[2 * k], xk[2 * k + 1], false);
@@ -309,10 +319,15 @@ int tc_pack_first_fwd(TcContext& tc, TcWeights& w, const float* w_host, int cout
 
 int conv_first_fwd_tc(TcContext& tc, const TcWeights& w, const ImageBatch& img, int h, int wd,
                       const float* bias, void* out, uint32_t* relu_bits, cudaStream_t s) {
+  ST_REQUIRE(h <= img.H && wd <= img.W, "conv_first_fwd_tc: tile larger than the image");
   FirstArgs a{};
   a.bits = relu_bits;
   a.half = w.fwd_half ? 1 : 0;
   a.img = img, a.h = h, a.w = wd, a.tiles_x = cdiv(wd, 128);
+  for (int i = 0; i < img.nb; ++i) {       // tile origins reduced to the image (see the gather)
+    a.img.oy[i] = ((img.oy[i] % img.H) + img.H) % img.H;
+    a.img.ox[i] = ((img.ox[i] % img.W) + img.W) % img.W;
+  }
   a.num_tiles = img.nb * h * a.tiles_x;
   a.wk = w.fwd, a.bias = bias, a.out = out;
   const int grid = a.num_tiles < tc.sm_count * 8 ? a.num_tiles : tc.sm_count * 8;   // 8 x 64 TMEM columns

@@ -108,12 +108,12 @@ size_t gram_tc_part_floats(const TcContext& tc, int nb, int hw, int c);
 int gram_tc(TcContext& tc, const void* f, bool half, int nb, int hw, int c, float* gram, float* part,
             cudaStream_t s);
 // The same contraction finished straight into the style term: delta[b] = G_b - target (full [C][C]),
-// tile_loss[b * loss_stride] += w * 0.5 * sum_{j<=i} delta_ij^2, max_bits[b] (optional) = max |delta_b|
-// as float bits.  G itself is not stored.
-struct ReduceScratch;
+// max_bits[b] (optional) = max |delta_b| as float bits, and loss_part[b * *parts_per_tile + i] =
+// partial sums of delta_ij^2 over j <= i, to be added in index order (delta_pack does).  G itself is
+// not stored.  loss_part must hold nb * cdiv(c, 128) * c doubles.
 int gram_tc_delta(TcContext& tc, const void* f, bool half, int nb, int hw, int c, float* part,
-                  const float* target, float* delta, unsigned* max_bits, double w,
-                  double* tile_loss, int loss_stride, ReduceScratch rs, cudaStream_t s);
+                  const float* target, float* delta, unsigned* max_bits, double* loss_part,
+                  int* parts_per_tile, cudaStream_t s);
 
 
 

@@ -24,10 +24,12 @@
 // output channels; persistent pairs walk the tile list round-robin.  K loop: 64-channel blocks,
 // inside each the 9 taps, inside each 4 MMAs of K = 16.
 //
-// Warps (352 threads per CTA):
+// Warps (384 threads per CTA):
 //   0      A producer   (TMA, one lane)            both CTAs
 //   1      MMA issuer   (one lane, leader CTA only) + TMEM allocation (both CTAs)
 //   2      B producer   (TMA, one lane)            both CTAs
+//   11     operand producer of the backward epilogue (TMA, one lane): the injected loss gradient
+//          of each (tile, 64-channel group) lands in a two-stage shared-memory ring
 //   3..10  epilogue     TMEM -> registers -> bias/ReLU | mask/inject | abs-sum -> swizzled smem
 //                       -> TMA store; accumulators are double-buffered in TMEM.  Two warps per TMEM
 //                       lane quadrant (warp % 4), each taking one 32-channel half of every
@@ -49,8 +51,9 @@ namespace st {
 namespace {
 
 constexpr int kBH = 16, kBW = 8;          // pixels per CTA tile: 16 rows x 8 columns = 128 = TMEM lanes
-constexpr int kThreads2 = 352;
+constexpr int kThreads2 = 384;
 constexpr int kEpiWarp0 = 3;             // first of the eight epilogue warps
+constexpr int kInjWarp = 11, kSE = 2;    // operand producer warp of the backward epilogue, its stages
 constexpr uint32_t kSpin = 1u << 24;
 constexpr int kOutStageBytes = 128 * 128; // 128 pixels x 64 channels bf16
 constexpr int kTailBytes = 3072;          // barriers (256 B) + tmem slot + bias copy (2 KB)
@@ -141,6 +144,18 @@ __device__ __forceinline__ void tma_load_3d_pair(const CUtensorMap* map, uint32_
       " [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smem_u32(dst)),
       "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
+}
+// plain (single-CTA) load: data and completion bytes stay in this CTA
+__device__ __forceinline__ void tma_load_4d_local(const CUtensorMap* map, uint64_t* bar, void* dst,
+                                                  int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_local(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void* src, int c0, int c1,
                                              int c2, int c3) {
@@ -301,7 +316,7 @@ __device__ __forceinline__ TileCoord decode_tile(const Tc2Args& a, int tile, int
 // RESB: the whole weight matrix of this CTA (its BN/2 rows x all K) stays resident in shared
 // memory for the life of the kernel -- for the small layers (conv1_2, conv2_1, the 3-channel
 // backward) where one TMA round trip per tap costs more than the MMAs of that tap.
-template <int BN, int TAPS, bool RESB = false, bool POOL = false>
+template <int BN, int TAPS, bool RESB = false, bool POOL = false, bool BWD = false>
 struct Cfg2 {
   static constexpr int kHaloRows = TAPS == 9 ? kBH + 2 : kBH;
   static constexpr int kWinW = TAPS == 9 ? kBW + 2 : kBW;        // pixels per window row
@@ -314,9 +329,12 @@ struct Cfg2 {
   // (three taps) amortises it.  BN = 256 keeps one tap per stage (48 KB stages would not fit).
   static constexpr int kTB = (TAPS == 9 && BN <= 128) ? 3 : 1;
   static constexpr int kBStage = kTB * kBBytes;
-  static constexpr int kSA = 4;
+  // A stages: one stage is nine taps of tensor time (9 x 4 MMAs of BN/2 cycles), so the wide tile
+  // needs fewer of them; the backward kernels give one up for the injected-gradient ring
+  static constexpr int kSA = (BN == 256 || BWD) ? 3 : 4;
+  static constexpr int kInjBytes = BWD ? kSE * kOutStageBytes : 0;
   static constexpr int kPoolBytes = POOL ? 2 * kPoolStageBytes : 0;
-  static constexpr int kOutBytes = 2 * kOutStageBytes + kPoolBytes;
+  static constexpr int kOutBytes = 2 * kOutStageBytes + kPoolBytes + kInjBytes;
   static constexpr int kSBRaw = (kSmemBudget - kSA * kABytes - kOutBytes) / kBStage;
   static constexpr int kSB = RESB ? 1 : (kSBRaw > 8 ? 8 : kSBRaw);
   static constexpr int kResMax = kSmemBudget - kSA * kABytes - kOutBytes;   // bytes for resident B
@@ -333,10 +351,11 @@ template <int BN, int TAPS, int EPI, bool RESB>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1)
 conv_tc2_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CUtensorMap map_w,
                 const __grid_constant__ CUtensorMap map_out,
-                const __grid_constant__ CUtensorMap map_pool, const Tc2Args a) {
+                const __grid_constant__ CUtensorMap map_aux, const Tc2Args a) {
+  // map_aux: the pooled output (kEpiFwdPool) or the injected gradient (kEpiBwd, same geometry as out)
   constexpr bool kPool = EPI == kEpiFwdPool;
   constexpr bool kFwd = EPI == kEpiFwd || EPI == kEpiFwdPool;
-  using Cfg = Cfg2<BN, TAPS, RESB, kPool>;
+  using Cfg = Cfg2<BN, TAPS, RESB, kPool, EPI == kEpiBwd>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~(uintptr_t)1023);
@@ -351,7 +370,10 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constan
   uint64_t* b_empty = b_full + Cfg::kSB;
   uint64_t* t_full = b_empty + Cfg::kSB;
   uint64_t* t_empty = t_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
+  uint64_t* e_full = t_empty + 2;          // injected-gradient ring (backward epilogue)
+  uint64_t* e_empty = e_full + kSE;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(e_empty + kSE);
+  uint8_t* inj_base = out_base + 2 * kOutStageBytes;     // kEpiBwd only (no pooling stages there)
   float* bias_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 512);   // [cout] <= 512
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -366,6 +388,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constan
     for (int i = 0; i < Cfg::kSA; ++i) mbar_init(&a_full[i], 1), mbar_init(&a_empty[i], 1);
     for (int i = 0; i < Cfg::kSB; ++i) mbar_init(&b_full[i], 1), mbar_init(&b_empty[i], 1);
     for (int i = 0; i < 2; ++i) mbar_init(&t_full[i], 1), mbar_init(&t_empty[i], 16);
+    for (int i = 0; i < kSE; ++i) mbar_init(&e_full[i], 1), mbar_init(&e_empty[i], 8);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc_pair(tmem_slot, Cfg::kTmemCols);
@@ -506,6 +529,32 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constan
         }
       }
     }
+  } else if (warp == kInjWarp) {
+    // ========================== operand producer of the backward epilogue ========================
+    // The injected loss gradient (style / content term of the output blob) of this CTA's 128 pixels
+    // x 64 channels, one TMA box per (tile, channel group) into a ring the epilogue warps drain.
+    // Per-thread global loads of it (16 bytes per lane, a DRAM round trip of ~2 us under load with
+    // at most one chunk in flight per warp) capped the conv1_2 backward at 1 TB/s of operand reads.
+    if constexpr (EPI == kEpiBwd) {
+      if (a.inj != nullptr) {
+        prefetch_tmap(&map_aux);
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+          const TileCoord t = decode_tile(a, tile, (int)rank);
+          for (int g = 0; g < BN / 64; ++g) {
+            mbar_wait(&e_empty[stage], phase ^ 1);
+            if (elect_one()) {
+              mbar_expect_tx(&e_full[stage], kOutStageBytes);
+              tma_load_4d_local(&map_aux, &e_full[stage], inj_base + stage * kOutStageBytes,
+                                t.n_tile * BN + g * 64, t.x0, t.y0, t.b);
+            }
+            __syncwarp();
+            if (++stage == kSE) stage = 0, phase ^= 1;
+          }
+        }
+      }
+    }
   } else {
     // ===================================== epilogue ==============================================
     const int q = warp & 3;                            // TMEM lane quadrant of this warp
@@ -535,17 +584,16 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constan
       return r;
     };
     uint32_t pbits = 0xFFFFFFFFu;
-    uint4 pe[4];
+    int es = 0;                                            // injected-gradient ring position
+    uint32_t ep = 0;
     auto prefetch = [&](const RowRef& rr, int cc) {
       if constexpr (EPI == kEpiBwd) {
         pbits = 0xFFFFFFFFu;                               // no mask: everything passes
-        if (rr.valid && a.mask_bits != nullptr) pbits = __ldg(a.mask_bits + (rr.gofs >> 5) + cc);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          pe[i] = make_uint4(0u, 0u, 0u, 0u);
-          if (rr.valid && a.inj != nullptr)
-            pe[i] = *reinterpret_cast<const uint4*>(a.inj + rr.gofs + cc * 32 + i * 8);
-        }
+        // volatile asm: keeps the load where it is written (see the call site in the chunk loop)
+        if (rr.valid && a.mask_bits != nullptr)
+          asm volatile("ld.global.nc.u32 %0, [%1];"
+                       : "=r"(pbits)
+                       : "l"(a.mask_bits + (rr.gofs >> 5) + cc));
       }
     };
     if constexpr (EPI == kEpiBwd) prefetch(row_of(pair), hsel);
@@ -602,12 +650,17 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constan
           } else if constexpr (EPI == kEpiBwd) {
             uint4 ce[4];
             const uint32_t cbits = pbits;
+            if (a.inj != nullptr) {
+              // this thread's pixel row of the staged tile (SWIZZLE_128B as TMA wrote it)
+              mbar_wait(&e_full[es], ep);
+              const uint8_t* irow = inj_base + es * kOutStageBytes + (size_t)m * 128;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) ce[i] = pe[i];
-            if (cc + 2 < BN / 32)
-              prefetch(cur, cc + 2);
-            else
-              prefetch(nxt, hsel);                   // first chunk of this warp in the next tile
+              for (int i = 0; i < 4; ++i)
+                ce[i] = *reinterpret_cast<const uint4*>(irow + (((hh * 4 + i) ^ (m & 7)) << 4));
+            } else {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) ce[i] = make_uint4(0u, 0u, 0u, 0u);
+            }
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               const uint32_t e4[4] = {ce[i].x, ce[i].y, ce[i].z, ce[i].w};
@@ -622,6 +675,20 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constan
                 v[8 * i + 2 * j + 1] = fmaf(inj_sc, __uint_as_float(e4[j] & 0xFFFF0000u), x1);
               }
             }
+            if (a.inj != nullptr) {
+              // the staged values are in registers and used: hand the ring stage back
+              __syncwarp();
+              if (lane == 0) mbar_arrive_local(&e_empty[es]);
+              if (++es == kSE) es = 0, ep ^= 1;
+            }
+            // mask bits of the next chunk (this tile's or the next tile's).  Issued AFTER the math:
+            // placed before it, the load shared a hardware scoreboard with the shared-memory reads
+            // of the ring and every chunk waited for a DRAM round trip (ncu: 26 % of all samples on
+            // the first use of the ring data, stall_long_scoreboard)
+            if (cc + 2 < BN / 32)
+              prefetch(cur, cc + 2);
+            else
+              prefetch(nxt, hsel);                   // first chunk of this warp in the next tile
           } else {
 #pragma unroll
             for (int i = 0; i < 32; ++i) abs_tile += fabsf(v[i]);
@@ -749,7 +816,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constan
           asm volatile("bar.sync 1, 256;" ::: "memory");
           if (issuer) {
             if (a.write_full) tma_store_4d(&map_out, stage_out, n_tile * BN + g * 64, x0, y0, t.b);
-            tma_store_4d(&map_pool, pstage, n_tile * BN + g * 64, x0 >> 1, y0 >> 1, t.b);
+            tma_store_4d(&map_aux, pstage, n_tile * BN + g * 64, x0 >> 1, y0 >> 1, t.b);
             tma_store_commit();
           }
         } else {
@@ -796,7 +863,7 @@ int encode_bf16_map(const TcContext& tc, CUtensorMap* map, int rank, const void*
 template <int BN, int TAPS, int EPI, bool RESB>
 int launch2r(TcContext& tc, const void* in, const void* wk, int wk_rows,
              void* out, void* pool_out, Tc2Args a, cudaStream_t s) {
-  using Cfg = Cfg2<BN, TAPS, RESB, EPI == kEpiFwdPool>;
+  using Cfg = Cfg2<BN, TAPS, RESB, EPI == kEpiFwdPool, EPI == kEpiBwd>;
   a.tiles_x = cdiv(a.w, kBW), a.tiles_y = cdiv(a.h, 2 * kBH), a.tiles_n = a.cout / BN;
   a.div_x = FastDiv(a.tiles_x), a.div_y = FastDiv(a.tiles_y), a.div_n = FastDiv(a.tiles_n);
   CUtensorMap map_in, map_out, map_w, map_pool;
@@ -819,6 +886,15 @@ int launch2r(TcContext& tc, const void* in, const void* wk, int wk_rows,
     map_out = map_in;            // never dereferenced by the pixel epilogue
   }
   map_pool = map_out;
+  if (EPI == kEpiBwd && a.inj != nullptr) {
+    // the injected gradient has the geometry of the output: same box, its own base address
+    const uint64_t dims[4] = {(uint64_t)a.cout, (uint64_t)a.w, (uint64_t)a.h, (uint64_t)a.nb};
+    const uint64_t strides[3] = {(uint64_t)a.cout * 2, (uint64_t)a.w * a.cout * 2,
+                                 (uint64_t)a.h * a.w * a.cout * 2};
+    const uint32_t box[4] = {64, (uint32_t)kBW, (uint32_t)kBH, 1};
+    int rc = encode_bf16_map(tc, &map_pool, 4, a.inj, dims, strides, box, false);
+    if (rc != ST_OK) return rc;
+  }
   if (EPI == kEpiFwdPool) {
     const uint64_t ho = (a.h + 1) / 2, wo = (a.w + 1) / 2;
     const uint64_t dims[4] = {(uint64_t)a.cout, wo, ho, (uint64_t)a.nb};
@@ -855,7 +931,7 @@ template <int BN, int TAPS, int EPI>
 int launch2(TcContext& tc, const void* in, const void* wk, int wk_rows, void* out, const Tc2Args& a,
             cudaStream_t s, void* pool_out = nullptr) {
   if constexpr (BN <= 128) {
-    using CfgR = Cfg2<BN, TAPS, true, EPI == kEpiFwdPool>;
+    using CfgR = Cfg2<BN, TAPS, true, EPI == kEpiFwdPool, EPI == kEpiBwd>;
     const long res = (long)TAPS * (a.cin / 64) * CfgR::kBBytes;
     if (a.cout == BN && !a.w_batched && res <= CfgR::kResMax && tc.resident_weights)
       return launch2r<BN, TAPS, EPI, true>(tc, in, wk, wk_rows, out, pool_out, a, s);

@@ -369,11 +369,13 @@ int build_injection(st_ctx* ctx, const st_loss_spec& sp, const Dims& d, const Ba
           rc = ensure(ctx, (void**)&ctx->part, &cap, gram_tc_part_floats(ctx->tc, nb, hf * wf, c), 4);
           ctx->part_floats = cap;
           // Gram contraction, then split reduction + delta + loss + max |delta| in one kernel
+          int n_part = 0;
           if (rc == ST_OK)
             rc = gram_tc_delta(ctx->tc, f, kHalf, nb, hf * wf, c, ctx->part, it->second, ctx->delta,
-                               kHalf ? ctx->delta_max : nullptr, w, tile_loss, kStatStride, ctx->rs, s);
+                               kHalf ? ctx->delta_max : nullptr, ctx->rs.partials, &n_part, s);
           if (rc == ST_OK)
-            rc = delta_pack(ctx->delta, ctx->delta_16, kHalf, ctx->delta_max, ctx->eps_eff, c, nb, s);
+            rc = delta_pack(ctx->delta, ctx->delta_16, kHalf, ctx->delta_max, ctx->eps_eff, c, nb,
+                            ctx->rs.partials, n_part, w, tile_loss, kStatStride, s);
         }
       } else {
         if constexpr (kHalf) {

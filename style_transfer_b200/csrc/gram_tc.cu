@@ -290,18 +290,16 @@ gram_tc_finalize_kernel(const float* __restrict__ part, int nsplit, int c, doubl
 }
 
 // The same reduction of the split partials fused with what the style term needs from the Gram matrix
-// (style_transfer.py:587,591): delta = G - G_style (both triangles), the tile's loss term
-// w * 0.5 * sum_{j<=i} delta^2 (blocks reduced in index order: deterministic) and max |delta| (float
-// bits, for the fp16 scaling of the style GEMM operand).  Replaces gram_tc_finalize + gram_delta: one
-// launch and no round trip of G through memory per style layer.
+// (style_transfer.py:587,591): delta = G - G_style (both triangles), per block the partial sum of
+// delta^2 over j <= i (added up in block order by delta_pack: deterministic, and no ticket / fence per
+// block -- a grid_reduce in each of the 32768 blocks of a C = 512 batch doubled this kernel's time)
+// and max |delta| (float bits, for the fp16 scaling of the style GEMM operand).  Replaces
+// gram_tc_finalize + gram_delta: one launch and no round trip of G through memory per style layer.
 struct GramFinish {
   const float* target;     // [C][C] symmetric
   float* delta;            // [nb][C][C]
   unsigned* max_bits;      // [nb] or null
-  double w;
-  double* tile_loss;
-  int loss_stride;
-  ReduceScratch rs;
+  double* loss_part;       // [nb][blocks per tile]
 };
 
 __global__ void __launch_bounds__(128)
@@ -329,10 +327,18 @@ gram_tc_finish_kernel(const float* __restrict__ part, int nsplit, int c, double 
     for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
     if ((threadIdx.x & 31) == 0 && mx > 0.f) atomicMax(fin.max_bits + b, __float_as_uint(mx));
   }
-  const unsigned nblk = gridDim.x * gridDim.y;
-  if (grid_reduce_impl<1>(v, fin.rs.partials + (size_t)b * nblk, fin.rs.counter + b,
-                          blockIdx.y * gridDim.x + blockIdx.x, nblk))
-    fin.tile_loss[(size_t)b * fin.loss_stride] += fin.w * 0.5 * v[0];
+  // block sum (4 warps) -> one slot per block
+  __shared__ double sh[4];
+  double x = v[0];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = x;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned nblk = gridDim.x * gridDim.y;
+    fin.loss_part[(size_t)b * nblk + blockIdx.y * gridDim.x + blockIdx.x] =
+        (sh[0] + sh[1]) + (sh[2] + sh[3]);
+  }
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
@@ -427,12 +433,13 @@ int gram_tc(TcContext& tc, const void* f, bool half, int nb, int hw, int c, floa
 }
 
 int gram_tc_delta(TcContext& tc, const void* f, bool half, int nb, int hw, int c, float* part,
-                  const float* target, float* delta, unsigned* max_bits, double w,
-                  double* tile_loss, int loss_stride, ReduceScratch rs, cudaStream_t s) {
-  ST_REQUIRE((size_t)nb * cdiv(c, 128) * c <= (size_t)kMaxReduceBlocks,
+                  const float* target, float* delta, unsigned* max_bits, double* loss_part,
+                  int* parts_per_tile, cudaStream_t s) {
+  *parts_per_tile = cdiv(c, 128) * c;
+  ST_REQUIRE((size_t)nb * *parts_per_tile <= (size_t)kMaxReduceBlocks * 4,
              "gram_tc_delta: batch too large for the reduction scratch");
   if (max_bits != nullptr) ST_CUDA(cudaMemsetAsync(max_bits, 0, nb * sizeof(unsigned), s));
-  const GramFinish fin{target, delta, max_bits, w, tile_loss, loss_stride, rs};
+  const GramFinish fin{target, delta, max_bits, loss_part};
   return gram_dispatch(tc, f, half, nb, hw, c, nullptr, part, &fin, s);
 }
 

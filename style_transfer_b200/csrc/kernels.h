@@ -77,8 +77,11 @@ int gram_delta(const float* gram, const float* target, float* delta, void* delta
                int loss_stride, ReduceScratch rs, cudaStream_t s);
 // The 16-bit copy of delta alone (second half of gram_delta): bf16, or fp16 scaled per tile by the
 // power of two derived from max_bits[b]; eps_eff[b] as in gram_delta.
+// With loss_part (optional): tile_loss[b * loss_stride] += w * 0.5 * sum_i loss_part[b * n_part + i],
+// the partials added in a fixed order by one block per tile.
 int delta_pack(const float* delta, void* delta_16, bool half, unsigned* max_bits, float* eps_eff,
-               int c, int nb, cudaStream_t s);
+               int c, int nb, const double* loss_part, int n_part, double w, double* tile_loss,
+               int loss_stride, cudaStream_t s);
 // out[b * out_stride] = sum(partials[b*n .. b*n+n)) in a launch-independent order; if scale is not
 // null also scale[b] = w / (sum / count + EPS)
 int sum_partials(const double* partials, int n, int nb, double* out, int out_stride, float* scale,

@@ -602,9 +602,26 @@ __global__ void gram_delta_kernel(const float* __restrict__ gram, const float* _
 // |delta_b|), an exact power-of-two scaling that keeps it inside the fp16 range; S then comes out
 // scaled by sigma_b too, which normalize() cancels except in its EPS term, hence eps_eff[b] =
 // EPS * sigma_b (w / (mean|S| + EPS) * S  ==  w / (mean|sigma S| + EPS sigma) * sigma S).
-__global__ void delta_pack_kernel(const float* __restrict__ delta, uint16_t* __restrict__ out,
-                                  unsigned* max_bits, float* eps_eff, int c, int half) {
+__global__ void __launch_bounds__(256)
+delta_pack_kernel(const float* __restrict__ delta, uint16_t* __restrict__ out, unsigned* max_bits,
+                  float* eps_eff, int c, int half, const double* __restrict__ loss_part, int n_part,
+                  double w, double* tile_loss, int loss_stride) {
   const size_t off = (size_t)blockIdx.y * c * c;
+  if (loss_part != nullptr && blockIdx.x == 0) {
+    // the style loss of this tile from the block partials of gram_tc_finish: thread t adds the
+    // strided subsequence t, t + 256, ..., then a fixed tree -- independent of the launch
+    __shared__ double sh[256];
+    const double* p = loss_part + (size_t)blockIdx.y * n_part;
+    double x = 0.0;
+    for (int i = threadIdx.x; i < n_part; i += 256) x += p[i];
+    sh[threadIdx.x] = x;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+      if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) tile_loss[(size_t)blockIdx.y * loss_stride] += w * 0.5 * sh[0];
+  }
   float sigma = 1.f;
   if (half) {
     const float mx = __uint_as_float(max_bits[blockIdx.y]);
@@ -635,14 +652,17 @@ int gram_delta(const float* gram, const float* target, float* delta, void* delta
   if (track) ST_CUDA(cudaMemsetAsync(max_bits, 0, nb * sizeof(unsigned), s));
   ST_LAUNCH(gram_delta_kernel, dim3(min(cdiv((long)c * c, 256), 256), nb), 256, 0, s, gram, target,
             delta, track ? max_bits : nullptr, c, w, tile_loss, loss_stride, rs);
-  if (delta_16 != nullptr) return delta_pack(delta, delta_16, half, max_bits, eps_eff, c, nb, s);
+  if (delta_16 != nullptr)
+    return delta_pack(delta, delta_16, half, max_bits, eps_eff, c, nb, nullptr, 0, 0.0, nullptr, 0, s);
   return ST_OK;
 }
 
 int delta_pack(const float* delta, void* delta_16, bool half, unsigned* max_bits, float* eps_eff,
-               int c, int nb, cudaStream_t s) {
+               int c, int nb, const double* loss_part, int n_part, double w, double* tile_loss,
+               int loss_stride, cudaStream_t s) {
   ST_LAUNCH(delta_pack_kernel, dim3(min(cdiv((long)c * c, 256), 64), nb), 256, 0, s, delta,
-            static_cast<uint16_t*>(delta_16), max_bits, eps_eff, c, half ? 1 : 0);
+            static_cast<uint16_t*>(delta_16), max_bits, eps_eff, c, half ? 1 : 0, loss_part, n_part, w,
+            tile_loss, loss_stride);
   return ST_OK;
 }
 
