@@ -169,7 +169,8 @@ ST_API int st_unpack_regularize(const float* packed_all_dev, const float* img_de
 /* ---- optimizers (optimizers.py) -------------------------------------------------------------
  * AdamOptimizer.update :26-42 after opfunc returned `grad`: EWMA moments (state g1,g2,p1 hold the
  * EWMA .value arrays), in-place parameter step, iterate averaging; avg_out = p1 / p1_corr.
- * g1_corr/g2_corr/p1_corr = 1 - beta^t (or 1 when bias correction is off). */
+ * g1_corr/g2_corr/p1_corr = 1 - beta^t (or 1 when bias correction is off).  All six arrays must be
+ * 16-byte aligned (whole allocations are): the kernel moves float4. */
 ST_API int st_adam_step(float* params, const float* grad, float* g1, float* g2, float* p1, float* avg_out,
                  size_t n, float step_size, float b1, float b2, float bp1, float g1_corr,
                  float g2_corr, float p1_corr, st_stream stream);

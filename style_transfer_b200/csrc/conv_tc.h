@@ -110,7 +110,7 @@ int gram_tc(TcContext& tc, const void* f, bool half, int nb, int hw, int c, floa
 // The same contraction finished straight into the style term: delta[b] = G_b - target (full [C][C]),
 // max_bits[b] (optional) = max |delta_b| as float bits, and loss_part[b * *parts_per_tile + i] =
 // partial sums of delta_ij^2 over j <= i, to be added in index order (delta_pack does).  G itself is
-// not stored.  loss_part must hold nb * cdiv(c, 128) * c doubles.
+// not stored.  loss_part must hold nb * (c / 32)^2 doubles.
 int gram_tc_delta(TcContext& tc, const void* f, bool half, int nb, int hw, int c, float* part,
                   const float* target, float* delta, unsigned* max_bits, double* loss_part,
                   int* parts_per_tile, cudaStream_t s);

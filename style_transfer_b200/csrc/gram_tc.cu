@@ -138,7 +138,9 @@ struct GramCfg {
   static constexpr int kGroups = C / 64;                              // boxes per k-block
   static constexpr int kStageBytes = (kGroups < 2 ? 2 : kGroups) * kBoxBytes;
   static constexpr int kStagesRaw = (200 * 1024) / kStageBytes;
-  static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
+  // C <= 128 (16 KB stages): six stages = 97 KB, so TWO CTAs share an SM and one streams while the
+  // other runs its prologue / epilogue (these layers are HBM-bound streams of ~1 MB per CTA)
+  static constexpr int kStages = C <= 128 ? 6 : (kStagesRaw > 8 ? 8 : kStagesRaw);
   static constexpr int kMBlocks = C < 128 ? 1 : C / 128;
   static constexpr int kN = C > 256 ? 256 : C;                        // columns per MMA
   static constexpr int kNHalves = C / kN;
@@ -159,7 +161,7 @@ struct GramArgs {
 };
 
 template <int C>
-__global__ void __launch_bounds__(kGThreads, 1)
+__global__ void __launch_bounds__(kGThreads, C <= 128 ? 2 : 1)
 gram_tc_kernel(const __grid_constant__ CUtensorMap map_f, const GramArgs a) {
   using Cfg = GramCfg<C>;
   extern __shared__ uint8_t smem_raw[];
@@ -302,42 +304,59 @@ struct GramFinish {
   double* loss_part;       // [nb][blocks per tile]
 };
 
-__global__ void __launch_bounds__(128)
+// One block per 32 x 32 tile (ti, tj) of the matrix with tj <= ti, one thread per element (the small
+// layers have few tiles but up to 64 splits: with four rows per thread their reduction was a chain
+// of 256 dependent-latency loads on 48 blocks).  The tile is summed over the splits with coalesced
+// reads, written, and its mirror image (tj, ti) written from a shared-memory transpose, so both
+// triangles are stored with full 128-byte lines (writing out[j][i] straight from the thread that
+// owns (i, j) cost a 32-way scattered store per warp).
+__global__ void __launch_bounds__(1024)
 gram_tc_finish_kernel(const float* __restrict__ part, int nsplit, int c, double scale,
                       const GramFinish fin) {
-  const int i = blockIdx.y, j = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.z;
-  double v[1] = {0.0};
+  __shared__ float tile[32][33];
+  __shared__ double sh[32];
+  const int tj = blockIdx.x, ti = blockIdx.y, b = blockIdx.z;
+  const int tx = threadIdx.x, ty = threadIdx.y, warp = ty;
+  const unsigned nblk = gridDim.x * gridDim.y, blk = blockIdx.y * gridDim.x + blockIdx.x;
+  if (tj > ti) {                                       // upper-triangle tiles are written by their mirror
+    if (tx == 0 && ty == 0) fin.loss_part[(size_t)b * nblk + blk] = 0.0;
+    return;
+  }
+  const size_t cc = (size_t)c * c;
+  float* out = fin.delta + (size_t)b * cc;
+  const int i = ti * 32 + ty, j = tj * 32 + tx;
+  const float* p = part + (size_t)b * nsplit * cc + (size_t)i * c + j;
+  double sum = 0.0;
+#pragma unroll 8
+  for (int s = 0; s < nsplit; ++s) sum += (double)p[(size_t)s * cc];
+  const float g = (float)(sum * scale);
+  const float d = g - fin.target[(size_t)i * c + j];
+  tile[ty][tx] = d;
+  double v = 0.0;
   float mx = 0.f;
-  if (j <= i) {
-    const size_t cc = (size_t)c * c;
-    const float* p = part + (size_t)b * nsplit * cc + (size_t)i * c + j;
-    double sum = 0.0;
-#pragma unroll 4
-    for (int s = 0; s < nsplit; ++s) sum += (double)p[(size_t)s * cc];
-    const float g = (float)(sum * scale);
-    const float d = g - fin.target[(size_t)i * c + j];
-    float* out = fin.delta + (size_t)b * cc;
+  if (j <= i) mx = fabsf(d), v = (double)d * d;        // lower triangle incl. the diagonal
+  __syncthreads();
+  if (ti != tj) {
     out[(size_t)i * c + j] = d;
-    out[(size_t)j * c + i] = d;
-    mx = fabsf(d);
-    v[0] = (double)d * d;
+    out[(size_t)(tj * 32 + ty) * c + ti * 32 + tx] = tile[tx][ty];        // mirror tile
+  } else {
+    // diagonal tile: the lower triangle is authoritative, the upper one its mirror
+    out[(size_t)i * c + j] = tx <= ty ? d : tile[tx][ty];
   }
   if (fin.max_bits != nullptr) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    if ((threadIdx.x & 31) == 0 && mx > 0.f) atomicMax(fin.max_bits + b, __float_as_uint(mx));
+    if (tx == 0 && mx > 0.f) atomicMax(fin.max_bits + b, __float_as_uint(mx));
   }
-  // block sum (4 warps) -> one slot per block
-  __shared__ double sh[4];
-  double x = v[0];
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = x;
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if (tx == 0) sh[warp] = v;
   __syncthreads();
-  if (threadIdx.x == 0) {
-    const unsigned nblk = gridDim.x * gridDim.y;
-    fin.loss_part[(size_t)b * nblk + blockIdx.y * gridDim.x + blockIdx.x] =
-        (sh[0] + sh[1]) + (sh[2] + sh[3]);
+  if (ty == 0) {                                       // fixed tree over the 32 warp sums
+    double x = sh[tx];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    if (tx == 0) fin.loss_part[(size_t)b * nblk + blk] = x;
   }
 }
 
@@ -389,7 +408,7 @@ int launch_gram(TcContext& tc, const void* f, bool half, int nb, int hw, float* 
   TimerScope ts(s, kTimeGram, 2.0 * C * C * hw * nb);
   ST_LAUNCH(kern, dim3(a.nsplit * Cfg::kMBlocks, nb), kGThreads, Cfg::kSmemBytes, s, map_f, a);
   if (fin != nullptr) {
-    ST_LAUNCH(gram_tc_finish_kernel, dim3(cdiv(C, 128), C, nb), 128, 0, s, part, a.nsplit, C,
+    ST_LAUNCH(gram_tc_finish_kernel, dim3(C / 32, C / 32, nb), dim3(32, 32), 0, s, part, a.nsplit, C,
               1.0 / ((double)C * hw), *fin);
   } else {
     ST_LAUNCH(gram_tc_finalize_kernel, dim3(cdiv(C, 128), C, nb), 128, 0, s, part, a.nsplit, C,
@@ -435,7 +454,7 @@ int gram_tc(TcContext& tc, const void* f, bool half, int nb, int hw, int c, floa
 int gram_tc_delta(TcContext& tc, const void* f, bool half, int nb, int hw, int c, float* part,
                   const float* target, float* delta, unsigned* max_bits, double* loss_part,
                   int* parts_per_tile, cudaStream_t s) {
-  *parts_per_tile = cdiv(c, 128) * c;
+  *parts_per_tile = (c / 32) * (c / 32);
   ST_REQUIRE((size_t)nb * *parts_per_tile <= (size_t)kMaxReduceBlocks * 4,
              "gram_tc_delta: batch too large for the reduction scratch");
   if (max_bits != nullptr) ST_CUDA(cudaMemsetAsync(max_bits, 0, nb * sizeof(unsigned), s));

@@ -66,13 +66,14 @@ struct TvTerm {
   float ddx, ddy, pw;   // d/d(dx), d/d(dy) contributions and g2^(beta/2)
 };
 
+template <bool BETA2 = false>
 __device__ __forceinline__ TvTerm tv_term(float xc, float xr, float xd, float beta) {
   // xc = X[y][x], xr = X[y][x+1], xd = X[y+1][x]  (already divided by 127.5)
   const float dx = xc - xr, dy = xc - xd;
   const float g2 = dx * dx + dy * dy + kEps;
   TvTerm t;
   float dg;
-  if (beta == 2.f) {
+  if (BETA2 || beta == 2.f) {
     t.pw = g2;
     dg = 1.f;
   } else if (beta == 1.f) {
@@ -104,6 +105,11 @@ struct RegTiles {
   FastDiv div_tiles_x, div_plane;    // by tiles_x and by tiles_x * tiles_y
 };
 
+// FAST: the reference's default configuration (tv_power = 2, p_power = 6 or no p-norm, no aux
+// image) with every per-pixel branch on the parameters resolved at compile time -- 57 % of the
+// generic kernel's executed instructions were integer / constant-load / branch overhead
+// (profiles/r01_laggards_ncu.md).  Same arithmetic, same operation order.
+template <bool FAST, bool PACKED>
 __global__ void __launch_bounds__(kRThreads)
 regularizers_kernel(const float* __restrict__ img, int H, int W, float m0, float m1, float m2,
                     float tv_w, float tv_beta, float p_w, float p_pow,
@@ -113,7 +119,7 @@ regularizers_kernel(const float* __restrict__ img, int H, int W, float m0, float
   __shared__ float xs[kRTH + 2][kRTW + 2];       // scaled pixels, origin (y0-1, x0-1)
   const int tx = threadIdx.x % kRTW, ty0 = threadIdx.x / kRTW;
   const int num_tiles = rt.num_tiles;
-  const bool do_tv = tv_w != 0.f;
+  const bool do_tv = FAST || tv_w != 0.f;
   // img / 127.5 as a multiplication by the rounded reciprocal: within 1 ulp of the reference's
   // division, and the IEEE division sequence was a fifth of this kernel's issue slots
   const float inv = 1.f / 127.5f;
@@ -158,7 +164,7 @@ regularizers_kernel(const float* __restrict__ img, int H, int W, float m0, float
     const int x = x0 + tx;
     // column part of the gradient-tile lookup: the same for the four rows of this thread
     int xr = 0, txx = 0;
-    if (packed != nullptr) {
+    if (PACKED) {
       xr = x + ug.roll_x;
       xr = xr >= W ? xr - W : xr;
       txx = min((int)ug.div_tw.div(xr), ug.ntx - 1);
@@ -172,7 +178,7 @@ regularizers_kernel(const float* __restrict__ img, int H, int W, float m0, float
       raw_k[k] = base_k[k] = aux_k[k] = 0.f;
       if (x >= W || y >= H) continue;
       raw_k[k] = pl[(size_t)y * W + x];
-      if (packed != nullptr) {               // fused st_unpack_grad
+      if (PACKED) {                          // fused st_unpack_grad
         int yr = y + ug.roll_y;
         yr = yr >= H ? yr - H : yr;
         const int tyy = min((int)ug.div_th.div(yr), ug.nty - 1);
@@ -183,7 +189,7 @@ regularizers_kernel(const float* __restrict__ img, int H, int W, float m0, float
       } else {
         base_k[k] = grad[((size_t)c * H + y) * W + x];
       }
-      if (aux != nullptr) {
+      if (!FAST && aux != nullptr) {
         const int ya = wrap(y + roll_y, H), xa = wrap(x + roll_x, W);
         aux_k[k] = aux[((size_t)c * H + ya) * W + xa];
       }
@@ -198,20 +204,20 @@ regularizers_kernel(const float* __restrict__ img, int H, int W, float m0, float
       if (do_tv) {
         // own term and the terms of the left / upper neighbour (their d/d(dx), d/d(dy) reach here)
         const float xc = xs[ty + 1][tx + 1];
-        const TvTerm t0 = tv_term(xc, xs[ty + 1][tx + 2], xs[ty + 2][tx + 1], tv_beta);
-        const TvTerm tl = tv_term(xs[ty + 1][tx], xc, xs[ty + 2][tx], tv_beta);
-        const TvTerm tu = tv_term(xs[ty][tx + 1], xs[ty][tx + 2], xc, tv_beta);
+        const TvTerm t0 = tv_term<FAST>(xc, xs[ty + 1][tx + 2], xs[ty + 2][tx + 1], tv_beta);
+        const TvTerm tl = tv_term<FAST>(xs[ty + 1][tx], xc, xs[ty + 2][tx], tv_beta);
+        const TvTerm tu = tv_term<FAST>(xs[ty][tx + 1], xs[ty][tx + 2], xc, tv_beta);
         g += tv_w * (t0.ddx + t0.ddy - tl.ddx - tu.ddy);
         l += tv_w * t0.pw;
       }
       if (p_w != 0.f) {
         const float a = (raw + mean - 127.5f) * inv;
         const float mag = fabsf(a), sgn = a > 0.f ? 1.f : (a < 0.f ? -1.f : 0.f);
-        if (p_pow == 1.f) {
+        if (!FAST && p_pow == 1.f) {
           l += p_w * mag, g += p_w * sgn;
-        } else if (p_pow == 2.f) {
+        } else if (!FAST && p_pow == 2.f) {
           l += p_w * a * a, g += p_w * 2.f * a;
-        } else if (p_pow == 6.f) {                          // the reference's default
+        } else if (FAST || p_pow == 6.f) {                  // the reference's default
           const float a2 = a * a, m5 = a2 * a2 * mag;
           l += p_w * m5 * mag, g += p_w * 6.f * sgn * m5;
         } else {
@@ -221,7 +227,7 @@ regularizers_kernel(const float* __restrict__ img, int H, int W, float m0, float
           l += p_w * mp1 * mag, g += p_w * p_pow * sgn * mp1;
         }
       }
-      if (aux != nullptr) {
+      if (!FAST && aux != nullptr) {
         const float d = (raw - aux_k[k]) * inv;
         l += aux_w * 0.5f * d * d, g += aux_w * d;
       }
@@ -247,9 +253,14 @@ static int launch_regularizers(const float* img, int H, int W, float m0, float m
   const int num_tiles = rt.num_tiles;
   const int grid = num_tiles < 148 * 8 ? num_tiles : 148 * 8;
   TimerScope ts(s, kTimeImage, 4.0 * 3 * H * W * (3 + (aux ? 1 : 0)));
-  ST_LAUNCH(regularizers_kernel, grid, kRThreads, 0, s, img, H, W, m0, m1, m2, tv_w, tv_beta, p_w,
-            p_pow, aux, aux_w, roll_y, roll_x, loss_accum, grad, packed, ug, rt, rs);
-  return ST_OK;
+  const bool fast = tv_w != 0.f && tv_beta == 2.f && (p_w == 0.f || p_pow == 6.f) && aux == nullptr;
+  auto launch = [&](auto kern) -> int {
+    ST_LAUNCH(kern, grid, kRThreads, 0, s, img, H, W, m0, m1, m2, tv_w, tv_beta, p_w, p_pow, aux,
+              aux_w, roll_y, roll_x, loss_accum, grad, packed, ug, rt, rs);
+    return ST_OK;
+  };
+  if (fast) return packed ? launch(regularizers_kernel<true, true>) : launch(regularizers_kernel<true, false>);
+  return packed ? launch(regularizers_kernel<false, true>) : launch(regularizers_kernel<false, false>);
 }
 
 int regularizers(const float* img, int H, int W, float m0, float m1, float m2, float tv_w,
@@ -278,24 +289,43 @@ __device__ __forceinline__ float ewma(float value, float beta, float omb, float 
   return __fadd_rn(__fmul_rn(value, beta), __fmul_rn(omb, x));
 }
 
+__device__ __forceinline__ void adam_one(float& p, float g, float& m1, float& m2, float& a1,
+                                         float& avg, float neg_step, float b1, float omb1, float b2,
+                                         float omb2, float bp1, float ombp1, float g1c, float g2c,
+                                         float p1c) {
+  m1 = ewma(m1, b1, omb1, g);
+  m2 = ewma(m2, b2, omb2, __fmul_rn(g, g));
+  const float step = __fdiv_rn(__fdiv_rn(m1, g1c), __fadd_rn(__fsqrt_rn(__fdiv_rn(m2, g2c)), kEps));
+  p = __fadd_rn(p, __fmul_rn(neg_step, step));
+  a1 = ewma(a1, bp1, ombp1, p);
+  avg = __fdiv_rn(a1, p1c);
+}
+
+// float4 per thread and array (the state arrays come from the allocator: 16-byte aligned); the
+// n % 4 tail is done by the first threads.  Element-wise arithmetic identical to the scalar form.
 __global__ void adam_kernel(float* __restrict__ params, const float* __restrict__ grad,
                             float* __restrict__ g1, float* __restrict__ g2, float* __restrict__ p1,
                             float* __restrict__ avg, size_t n, float neg_step, float b1, float omb1,
                             float b2, float omb2, float bp1, float ombp1, float g1c, float g2c,
                             float p1c) {
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
+  const size_t n4 = n >> 2;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4;
        i += (size_t)gridDim.x * blockDim.x) {
-    const float g = grad[i];
-    const float m1 = ewma(g1[i], b1, omb1, g);
-    const float m2 = ewma(g2[i], b2, omb2, __fmul_rn(g, g));
-    g1[i] = m1, g2[i] = m2;
-    const float step = __fdiv_rn(__fdiv_rn(m1, g1c), __fadd_rn(__fsqrt_rn(__fdiv_rn(m2, g2c)), kEps));
-    const float p = __fadd_rn(params[i], __fmul_rn(neg_step, step));
-    params[i] = p;
-    const float a = ewma(p1[i], bp1, ombp1, p);
-    p1[i] = a;
-    avg[i] = __fdiv_rn(a, p1c);
+    const float4 g = reinterpret_cast<const float4*>(grad)[i];
+    float4 m1 = reinterpret_cast<float4*>(g1)[i], m2 = reinterpret_cast<float4*>(g2)[i];
+    float4 p = reinterpret_cast<float4*>(params)[i], a1 = reinterpret_cast<float4*>(p1)[i], av;
+    adam_one(p.x, g.x, m1.x, m2.x, a1.x, av.x, neg_step, b1, omb1, b2, omb2, bp1, ombp1, g1c, g2c, p1c);
+    adam_one(p.y, g.y, m1.y, m2.y, a1.y, av.y, neg_step, b1, omb1, b2, omb2, bp1, ombp1, g1c, g2c, p1c);
+    adam_one(p.z, g.z, m1.z, m2.z, a1.z, av.z, neg_step, b1, omb1, b2, omb2, bp1, ombp1, g1c, g2c, p1c);
+    adam_one(p.w, g.w, m1.w, m2.w, a1.w, av.w, neg_step, b1, omb1, b2, omb2, bp1, ombp1, g1c, g2c, p1c);
+    reinterpret_cast<float4*>(g1)[i] = m1, reinterpret_cast<float4*>(g2)[i] = m2;
+    reinterpret_cast<float4*>(params)[i] = p, reinterpret_cast<float4*>(p1)[i] = a1;
+    reinterpret_cast<float4*>(avg)[i] = av;
   }
+  const size_t t = (n4 << 2) + blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (t < n)
+    adam_one(params[t], grad[t], g1[t], g2[t], p1[t], avg[t], neg_step, b1, omb1, b2, omb2, bp1, ombp1,
+             g1c, g2c, p1c);
 }
 
 int adam_step(float* params, const float* grad, float* g1, float* g2, float* p1, float* avg_out,
@@ -305,7 +335,11 @@ int adam_step(float* params, const float* grad, float* g1, float* g2, float* p1,
   const float omb1 = (float)(1.0 - (double)b1), omb2 = (float)(1.0 - (double)b2);
   const float ombp1 = (float)(1.0 - (double)bp1);
   TimerScope ts(s, kTimeImage, 40.0 * n);
-  ST_LAUNCH(adam_kernel, ew_grid(n, 256), 256, 0, s, params, grad, g1, g2, p1, avg_out, n,
+  const uintptr_t align = reinterpret_cast<uintptr_t>(params) | reinterpret_cast<uintptr_t>(grad) |
+                          reinterpret_cast<uintptr_t>(g1) | reinterpret_cast<uintptr_t>(g2) |
+                          reinterpret_cast<uintptr_t>(p1) | reinterpret_cast<uintptr_t>(avg_out);
+  ST_REQUIRE((align & 15) == 0, "st_adam_step: arrays must be 16-byte aligned");
+  ST_LAUNCH(adam_kernel, ew_grid((n + 3) / 4, 256), 256, 0, s, params, grad, g1, g2, p1, avg_out, n,
             -step_size, b1, omb1, b2, omb2, bp1, ombp1, g1_corr, g2_corr, p1_corr);
   return ST_OK;
 }
