@@ -304,19 +304,22 @@ struct GramFinish {
   double* loss_part;       // [nb][blocks per tile]
 };
 
-// One block per 32 x 32 tile (ti, tj) of the matrix with tj <= ti, one thread per element (the small
-// layers have few tiles but up to 64 splits: with four rows per thread their reduction was a chain
-// of 256 dependent-latency loads on 48 blocks).  The tile is summed over the splits with coalesced
-// reads, written, and its mirror image (tj, ti) written from a shared-memory transpose, so both
-// triangles are stored with full 128-byte lines (writing out[j][i] straight from the thread that
-// owns (i, j) cost a 32-way scattered store per warp).
-__global__ void __launch_bounds__(1024)
+// One block per 32 x 32 tile (ti, tj) of the matrix with tj <= ti; 32 x (32 / R) threads, R rows each.
+// R = 1 on the narrow layers (few tiles but up to 64 splits: with four rows per thread their
+// reduction was a chain of 256 dependent-latency loads on 48 blocks), R = 4 on the wide ones (many
+// tiles, few splits: 1024-thread blocks were twice slower there).  The tile is summed over the
+// splits with coalesced reads, written, and its mirror image (tj, ti) written from a shared-memory
+// transpose, so both triangles are stored with full 128-byte lines (writing out[j][i] straight from
+// the thread that owns (i, j) cost a 32-way scattered store per warp).
+template <int R>
+__global__ void __launch_bounds__(1024 / R)
 gram_tc_finish_kernel(const float* __restrict__ part, int nsplit, int c, double scale,
                       const GramFinish fin) {
+  constexpr int kRowsPerPass = 32 / R, kWarps = 32 / R;
   __shared__ float tile[32][33];
-  __shared__ double sh[32];
+  __shared__ double sh[kWarps];
   const int tj = blockIdx.x, ti = blockIdx.y, b = blockIdx.z;
-  const int tx = threadIdx.x, ty = threadIdx.y, warp = ty;
+  const int tx = threadIdx.x, ty = threadIdx.y;
   const unsigned nblk = gridDim.x * gridDim.y, blk = blockIdx.y * gridDim.x + blockIdx.x;
   if (tj > ti) {                                       // upper-triangle tiles are written by their mirror
     if (tx == 0 && ty == 0) fin.loss_part[(size_t)b * nblk + blk] = 0.0;
@@ -324,24 +327,34 @@ gram_tc_finish_kernel(const float* __restrict__ part, int nsplit, int c, double 
   }
   const size_t cc = (size_t)c * c;
   float* out = fin.delta + (size_t)b * cc;
-  const int i = ti * 32 + ty, j = tj * 32 + tx;
-  const float* p = part + (size_t)b * nsplit * cc + (size_t)i * c + j;
-  double sum = 0.0;
-#pragma unroll 8
-  for (int s = 0; s < nsplit; ++s) sum += (double)p[(size_t)s * cc];
-  const float g = (float)(sum * scale);
-  const float d = g - fin.target[(size_t)i * c + j];
-  tile[ty][tx] = d;
   double v = 0.0;
   float mx = 0.f;
-  if (j <= i) mx = fabsf(d), v = (double)d * d;        // lower triangle incl. the diagonal
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const int il = ty + kRowsPerPass * r, i = ti * 32 + il, j = tj * 32 + tx;
+    const float* p = part + (size_t)b * nsplit * cc + (size_t)i * c + j;
+    double sum = 0.0;
+#pragma unroll 8
+    for (int s = 0; s < nsplit; ++s) sum += (double)p[(size_t)s * cc];
+    const float g = (float)(sum * scale);
+    const float d = g - fin.target[(size_t)i * c + j];
+    tile[il][tx] = d;
+    if (j <= i) {                                      // lower triangle incl. the diagonal
+      mx = fmaxf(mx, fabsf(d));
+      v += (double)d * d;
+    }
+  }
   __syncthreads();
-  if (ti != tj) {
-    out[(size_t)i * c + j] = d;
-    out[(size_t)(tj * 32 + ty) * c + ti * 32 + tx] = tile[tx][ty];        // mirror tile
-  } else {
-    // diagonal tile: the lower triangle is authoritative, the upper one its mirror
-    out[(size_t)i * c + j] = tx <= ty ? d : tile[tx][ty];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const int il = ty + kRowsPerPass * r;
+    if (ti != tj) {
+      out[(size_t)(ti * 32 + il) * c + tj * 32 + tx] = tile[il][tx];
+      out[(size_t)(tj * 32 + il) * c + ti * 32 + tx] = tile[tx][il];      // mirror tile
+    } else {
+      // diagonal tile: the lower triangle is authoritative, the upper one its mirror
+      out[(size_t)(ti * 32 + il) * c + tj * 32 + tx] = tx <= il ? tile[il][tx] : tile[tx][il];
+    }
   }
   if (fin.max_bits != nullptr) {
 #pragma unroll
@@ -350,10 +363,10 @@ gram_tc_finish_kernel(const float* __restrict__ part, int nsplit, int c, double 
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  if (tx == 0) sh[warp] = v;
+  if (tx == 0) sh[ty] = v;
   __syncthreads();
-  if (ty == 0) {                                       // fixed tree over the 32 warp sums
-    double x = sh[tx];
+  if (ty == 0) {                                       // fixed tree over the warp sums
+    double x = tx < kWarps ? sh[tx] : 0.0;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
     if (tx == 0) fin.loss_part[(size_t)b * nblk + blk] = x;
@@ -372,7 +385,9 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 template <int C>
 int gram_splits(int hw) {
   const int kb_total = cdiv(hw, 64);
-  int nsplit = C <= 64 ? 64 : (C <= 128 ? 32 : (C <= 256 ? 16 : 8));
+  // wide layers: few splits -- a split's partial block is [128][C] fp32, so at C >= 256 the partials
+  // written and re-read by the finish kernel outweighed the 16-bit features themselves
+  int nsplit = C <= 64 ? 64 : (C <= 128 ? 32 : (C <= 256 ? 8 : 4));
   // at least 8 k-blocks (512 pixels) per split: shorter streams are all pipeline fill and drain
   nsplit = nsplit > kb_total / 8 ? kb_total / 8 : nsplit;
   nsplit = nsplit < 1 ? 1 : nsplit;
@@ -408,8 +423,9 @@ int launch_gram(TcContext& tc, const void* f, bool half, int nb, int hw, float* 
   TimerScope ts(s, kTimeGram, 2.0 * C * C * hw * nb);
   ST_LAUNCH(kern, dim3(a.nsplit * Cfg::kMBlocks, nb), kGThreads, Cfg::kSmemBytes, s, map_f, a);
   if (fin != nullptr) {
-    ST_LAUNCH(gram_tc_finish_kernel, dim3(C / 32, C / 32, nb), dim3(32, 32), 0, s, part, a.nsplit, C,
-              1.0 / ((double)C * hw), *fin);
+    constexpr int kR = C >= 256 ? 4 : 1;
+    ST_LAUNCH(gram_tc_finish_kernel<kR>, dim3(C / 32, C / 32, nb), dim3(32, 32 / kR), 0, s, part,
+              a.nsplit, C, 1.0 / ((double)C * hw), *fin);
   } else {
     ST_LAUNCH(gram_tc_finalize_kernel, dim3(cdiv(C, 128), C, nb), 128, 0, s, part, a.nsplit, C,
               1.0 / ((double)C * hw), gram);

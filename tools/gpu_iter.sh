@@ -18,6 +18,8 @@ PY
 timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv \
   --log-file gpurun_out/launches_step.csv python tools/step_eval.py --steps 3 --profile-last > gpurun_out/ncu_list.log 2>&1; echo "ncu list rc=$?"
 python tools/launch_table.py gpurun_out/launches_step.csv --all -v 2>/dev/null | head -120
+timeout 120 python tools/step_eval.py --steps 3 2>&1 | tail -2
+timeout 120 python tools/step_eval.py --steps 3 --size 1024 2>&1 | tail -2
 if [ "${FULL:-1}" = "1" ]; then
 timeout 600 ncu --set full --clock-control none --import-source on --profile-from-start off --kernel-name-base mangled \
   -k 'regex:conv_tc2_kernelILi(64|128|16)ELi9' -o gpurun_out/prof_conv_small -f \

@@ -53,6 +53,14 @@ def main():
     torch.cuda.synchronize()
     if a.profile_last:
         torch.cuda.profiler.stop()
+    # host time to ENQUEUE one step (no synchronisation inside): the launch-bound floor of a step
+    import time
+    t0 = time.perf_counter()
+    for _ in range(5):
+        st.step()
+    t_host = (time.perf_counter() - t0) / 5
+    torch.cuda.synchronize()
+    print('host enqueue time per step: %.3f ms' % (t_host * 1e3), flush=True)
     print('step %dx%d/%d %s: last step %.3f ms, loss %.6e' %
           (a.size, a.size, a.tile_size, a.precision, e0.elapsed_time(e1), float(loss)), flush=True)
 
