@@ -409,15 +409,16 @@ def run_engine(a):
         else:
             peak, src = 0.5 * 148 * 128 * 2 * 1.965e-3 * 2, 'nominal fp32 FFMA peak (no tensor cores in fp32 mode)'
         ach = d['work_per_step'] / (d['ms_per_step'] * 1e-3) / 1e12
-        # dram__bytes_read.sum + dram__bytes_write.sum per launch, averaged over the 24 3x3 conv
-        # launches of one step in the ncu --set full capture summarised in profiles/r01_conv_step_ncu.md
-        traffic = 378.0e6 if (dom == 'conv_tc' and a.size == 2048 and a.tile_size == 512 and world == 1) else None
+        # dram__bytes_read.sum + dram__bytes_write.sum per launch, averaged over the 24 3x3 conv launches
+        # of one step in the ncu --set full capture summarised in profiles/r01_conv_step_ncu_final.md
+        traffic = 290.4e6 if (dom == 'conv_tc' and a.size == 2048 and a.tile_size == 512 and world == 1
+                              and a.precision == 'fp16') else None
         burst = peaks.get('bf16_tflops') if a.precision in ('bf16', 'fp16') else None
         roofline = {'bound': 'tensor', 'kernel': 'conv_tc2_kernel' if dom == 'conv_tc' else 'conv3x3_kernel',
                     'achieved': ach, 'peak': peak, 'unit': 'TFLOP/s', 'frac': ach / peak,
                     # the same against the burst figure of MEASURED_PEAKS.json (a kernel timed alone)
                     'frac_of_burst_peak': (ach / burst) if burst else None,
-                    'traffic': traffic, 'traffic_source': 'profiles/r01_conv_step_ncu.md (ncu --set full, per launch)',
+                    'traffic': traffic, 'traffic_source': 'profiles/r01_conv_step_ncu_final.md (ncu --set full, per launch)',
                     'peak_source': src,
                     'flops_per_launch': d['work_per_step'] / max(d['launch_groups_per_step'], 1),
                     'avg_launch_ms': d['ms_per_step'] / max(d['launch_groups_per_step'], 1),
