@@ -432,7 +432,7 @@ def run_engine(a):
         gbytes = 64.9e6 * tiles_here
         ach = gbytes / (breakdown['gram']['ms_per_step'] * 1e-3) / 1e9
         hbm = peaks.get('hbm_gbs', 6650.0)
-        roofline_gram = {'bound': 'hbm', 'kernel': 'gram_tc_kernel + gram_tc_finalize_kernel',
+        roofline_gram = {'bound': 'hbm', 'kernel': 'gram_tc_kernel + gram_tc_finish_kernel + delta_pack_kernel',
                          'achieved': ach, 'peak': hbm, 'unit': 'GB/s', 'frac': ach / hbm,
                          'traffic': None, 'algorithmic_bytes_per_step': gbytes,
                          'peak_source': 'MEASURED_PEAKS.json hbm_gbs' if peaks else 'fallback 6650 (recipe)'}

@@ -177,6 +177,20 @@ ST_API int st_adam_step(float* params, const float* grad, float* g1, float* g2, 
 /* LBFGSOptimizer.inv_hv :105-121: two-loop recursion over m (<= 16) curvature pairs.  s_dev/y_dev
  * are HOST arrays of m device pointers (oldest first), sy_host the stored s.y products; p_dev
  * receives H*grad.  scratch_dev: >= 64 doubles. */
+/* ---- per-iteration output step (style_transfer.py:808-821, :378-386) ------------------------------
+ * st_iter_stats: the two statistics of StyleTransfer.transfer in one pass over the averaged iterate:
+ *   stats_dev[0] = sum |avg - old|                      (update_size = stats[0] / (3*H*W), :809)
+ *   stats_dev[1] = sum (x_diff^2 + y_diff^2),  x_diff = avg - roll(avg, -1, axis=-1), y_diff likewise
+ *                                                       (tv_loss = sqrt(stats[1] / (3*H*W)), :813-815)
+ * and old := avg (:810).  avg_dev / old_dev are f32 [3][H][W].
+ * st_get_image_u8: CaffeModel.get_image (:378-386): out[y][x][k] = uint8(clip(params[c][y][x] +
+ * mean[c], 0, 255)) with c = 2 - k when bgr (the model is BGR, the picture RGB), else c = k;
+ * out_dev is uint8 [H][W][3]. */
+ST_API int st_iter_stats(const float* avg_dev, float* old_dev, int H, int W, double* stats_dev,
+                         st_stream stream);
+ST_API int st_get_image_u8(const float* params_dev, int H, int W, const float mean[3], int bgr,
+                           uint8_t* out_dev, st_stream stream);
+
 ST_API int st_lbfgs_inv_hv(const float* grad_dev, size_t n, int m, const float* const* s_dev,
                     const float* const* y_dev, const double* sy_host, float* p_dev,
                     double* scratch_dev, st_stream stream);

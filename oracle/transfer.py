@@ -50,6 +50,26 @@ def to_params(rgb_hwc, mean=DEFAULT_MEAN):
     return np.ascontiguousarray(arr - np.float32(mean).reshape(3, 1, 1))
 
 
+def iter_stats(avg_img, old_img):
+    """Per-iteration statistics of ``StyleTransfer.transfer`` (style_transfer.py:808-815): returns
+    (update_size, tv_loss) and performs ``old_img[...] = avg_img`` like :810."""
+    update_size = np.mean(abs(avg_img - old_img))
+    old_img[...] = avg_img
+    x_diff = avg_img - np.roll(avg_img, -1, axis=-1)
+    y_diff = avg_img - np.roll(avg_img, -1, axis=-2)
+    tv_loss = np.sqrt(np.mean(x_diff**2 + y_diff**2))
+    return float(update_size), float(tv_loss)
+
+
+def get_image_array(params, mean=DEFAULT_MEAN, bgr=True):
+    """``CaffeModel.get_image`` (style_transfer.py:378-386) up to the PIL wrapper: uint8 HxWx3."""
+    arr = params + np.float32(mean).reshape((3, 1, 1))
+    if bgr:
+        arr = arr[::-1]
+    arr = arr.transpose((1, 2, 0))
+    return np.uint8(np.clip(arr, 0, 255))
+
+
 class OracleTransfer:
     def __init__(self, model, args, layer_weights=None):
         self.model = model

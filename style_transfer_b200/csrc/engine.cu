@@ -1008,6 +1008,21 @@ int st_adam_step(float* params, const float* grad, float* g1, float* g2, float* 
                    p1_corr, (cudaStream_t)stream);
 }
 
+int st_iter_stats(const float* avg_dev, float* old_dev, int H, int W, double* stats_dev,
+                  st_stream stream) {
+  ST_REQUIRE(avg_dev && old_dev && stats_dev && H > 0 && W > 0, "st_iter_stats: bad arguments");
+  ReduceScratch rs;
+  int rc = global_scratch(&rs);
+  return rc != ST_OK ? rc : iter_stats(avg_dev, old_dev, H, W, stats_dev, rs, (cudaStream_t)stream);
+}
+
+int st_get_image_u8(const float* params_dev, int H, int W, const float mean[3], int bgr,
+                    uint8_t* out_dev, st_stream stream) {
+  ST_REQUIRE(params_dev && mean && out_dev && H > 0 && W > 0, "st_get_image_u8: bad arguments");
+  return get_image_u8(params_dev, H, W, mean[0], mean[1], mean[2], bgr != 0, out_dev,
+                      (cudaStream_t)stream);
+}
+
 int st_dot(const float* x, const float* y, size_t n, double* out_dev, st_stream stream) {
   ST_REQUIRE(x && y && out_dev && n > 0, "st_dot: bad arguments");
   ReduceScratch rs;

@@ -141,6 +141,12 @@ int unpack_regularizers(const float* packed, int H, int W, int nty, int ntx, int
 int adam_step(float* params, const float* grad, float* g1, float* g2, float* p1, float* avg_out,
               size_t n, float step_size, float b1, float b2, float bp1, float g1_corr,
               float g2_corr, float p1_corr, cudaStream_t s);
+// stats[0] = sum |avg - old|, stats[1] = sum of squared periodic forward differences; old := avg
+int iter_stats(const float* avg, float* old, int H, int W, double* stats, ReduceScratch rs,
+               cudaStream_t s);
+// out[y][x][k] = uint8(clip(params[c][y][x] + mean[c], 0, 255)), c = bgr ? 2 - k : k
+int get_image_u8(const float* params, int H, int W, float m0, float m1, float m2, bool bgr,
+                 uint8_t* out, cudaStream_t s);
 int dot_to(const float* x, const float* y, size_t n, double* out, ReduceScratch rs,
            cudaStream_t s);
 int asum_to(const float* x, size_t n, double* out, ReduceScratch rs, cudaStream_t s);

@@ -345,6 +345,66 @@ int adam_step(float* params, const float* grad, float* g1, float* g2, float* p1,
 }
 
 // -----------------------------------------------------------------------------------------------------
+// Per-iteration output step: statistics of the averaged iterate (style_transfer.py:808-815) and the
+// uint8 picture (CaffeModel.get_image :378-386).
+// -----------------------------------------------------------------------------------------------------
+// Blocks walk the 3*H image rows (fixed grid => the block-ordered reduction is reproducible), threads
+// walk a row; the right neighbour wraps inside the row, the lower neighbour is the next row (mod H).
+__global__ void __launch_bounds__(256)
+iter_stats_kernel(const float* __restrict__ avg, float* __restrict__ old, int H, int W, double* stats,
+                  ReduceScratch rs) {
+  double v[2] = {0.0, 0.0};
+  for (int row = blockIdx.x; row < 3 * H; row += gridDim.x) {
+    const int c = row / H, y = row - c * H;
+    const float* r0 = avg + (size_t)row * W;
+    const float* r1 = avg + ((size_t)c * H + (y + 1 == H ? 0 : y + 1)) * W;
+    float* o = old + (size_t)row * W;
+    float ab = 0.f, sq = 0.f;
+    for (int x = threadIdx.x; x < W; x += blockDim.x) {
+      const float a = r0[x], xd = a - r0[x + 1 == W ? 0 : x + 1], yd = a - r1[x];
+      ab += fabsf(a - o[x]);
+      sq += xd * xd + yd * yd;
+      o[x] = a;
+    }
+    v[0] += (double)ab, v[1] += (double)sq;
+  }
+  if (grid_reduce<2>(v, rs.partials, rs.counter)) stats[0] = v[0], stats[1] = v[1];
+}
+
+int iter_stats(const float* avg, float* old, int H, int W, double* stats, ReduceScratch rs,
+               cudaStream_t s) {
+  TimerScope ts(s, kTimeImage, 4.0 * 3 * H * W * 3);
+  const int grid = 3 * H < 148 * 8 ? 3 * H : 148 * 8;
+  ST_LAUNCH(iter_stats_kernel, grid, 256, 0, s, avg, old, H, W, stats, rs);
+  return ST_OK;
+}
+
+// One thread per pixel: three plane reads (coalesced along x), three consecutive bytes written.
+// float32 add, clip, truncation toward zero -- np.uint8(np.clip(params + mean, 0, 255)) exactly.
+__global__ void __launch_bounds__(256)
+get_image_u8_kernel(const float* __restrict__ params, int H, int W, float m0, float m1, float m2,
+                    int bgr, uint8_t* __restrict__ out) {
+  const size_t n = (size_t)H * W;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const float v0 = __fadd_rn(params[i], m0), v1 = __fadd_rn(params[n + i], m1),
+                v2 = __fadd_rn(params[2 * n + i], m2);
+    const uint8_t b0 = (uint8_t)fminf(fmaxf(v0, 0.f), 255.f), b1 = (uint8_t)fminf(fmaxf(v1, 0.f), 255.f),
+                  b2 = (uint8_t)fminf(fmaxf(v2, 0.f), 255.f);
+    uint8_t* o = out + i * 3;
+    o[0] = bgr ? b2 : b0, o[1] = b1, o[2] = bgr ? b0 : b2;
+  }
+}
+
+int get_image_u8(const float* params, int H, int W, float m0, float m1, float m2, bool bgr,
+                 uint8_t* out, cudaStream_t s) {
+  TimerScope ts(s, kTimeImage, 15.0 * H * W);
+  ST_LAUNCH(get_image_u8_kernel, ew_grid((size_t)H * W, 256), 256, 0, s, params, H, W, m0, m1, m2,
+            bgr ? 1 : 0, out);
+  return ST_OK;
+}
+
+// -----------------------------------------------------------------------------------------------------
 // BLAS-1 on the device for L-BFGS.
 // -----------------------------------------------------------------------------------------------------
 template <bool ABS>

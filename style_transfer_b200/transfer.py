@@ -150,17 +150,23 @@ class StyleTransfer:
         """Performs style transfer at the current scale; returns the averaged raw iterate."""
         self.prepare(content_images, style_images)
         old_img = self.model.img.clone()
+        stats = torch.zeros(2, dtype=torch.float64, device=old_img.device)
         avg_img = None
         for step in range(1, iterations + 1):
             avg_img, loss = self.step()
             if callback is not None:
-                # statistics of :808-817, evaluated on the device, synchronised here
-                update_size = float((avg_img - old_img).abs().mean())
-                old_img.copy_(avg_img)
-                x_diff = avg_img - torch.roll(avg_img, -1, dims=-1)
-                y_diff = avg_img - torch.roll(avg_img, -1, dims=-2)
-                tv_loss = float(torch.sqrt((x_diff ** 2 + y_diff ** 2).mean()))
+                update_size, tv_loss = self.iter_stats(avg_img, old_img, stats)
                 callback(step=step, update_size=update_size, loss=float(loss), tv_loss=tv_loss,
                          image=avg_img)
             self.current_raw = avg_img
         return avg_img
+
+    @staticmethod
+    def iter_stats(avg_img, old_img, stats):
+        """The update-size and total-variation statistics of :808-815 in one device pass
+        (st_iter_stats), which also performs ``old_img[...] = avg_img``; two doubles come back."""
+        h, w = avg_img.shape[-2:]
+        _lib.call('st_iter_stats', _ptr(avg_img), _ptr(old_img), h, w, _ptr(stats), _stream())
+        s = stats.cpu().numpy()
+        n = float(avg_img.numel())
+        return float(s[0] / n), float(np.sqrt(s[1] / n))

@@ -424,3 +424,30 @@ def test_n_iterations_tensor_core_modes(precision, optimizer, iters):
     bound = {('fp16', 'adam'): 6.0, ('fp16', 'lbfgs'): 2.5, ('bf16', 'adam'): 9.0,
              ('bf16', 'lbfgs'): 6.0}[(precision, optimizer)]
     assert rms <= bound, rms
+
+
+@pytest.mark.parametrize('HW', [(37, 53), (64, 96)])
+def test_iter_stats_and_picture_match_oracle(HW):
+    """Output step of the loop (style_transfer.py:808-821, :378-386): update-size / TV statistics in
+    one device pass (with the old := avg side effect) and the uint8 picture, against the oracle
+    restatement.  Statistics: 1e-6 relative (float32 sums in another order); picture: bit-exact."""
+    from oracle.transfer import get_image_array, iter_stats
+    from style_transfer_b200.transfer import StyleTransfer
+    eng, _ = engine_for('vgg16.prototxt')
+    rs = np.random.RandomState(11)
+    H, W = HW
+    avg = np.float32(rs.uniform(-140, 160, (3, H, W)))
+    old = np.float32(avg + rs.normal(0, 3, (3, H, W)))
+    old_o = old.copy()
+    us_o, tv_o = iter_stats(avg, old_o)
+    d_avg, d_old = torch.from_numpy(avg).cuda(), torch.from_numpy(old).cuda()
+    stats = torch.zeros(2, dtype=torch.float64, device='cuda')
+    us_g, tv_g = StyleTransfer.iter_stats(d_avg, d_old, stats)
+    assert abs(us_g - us_o) <= 1e-6 * abs(us_o)
+    assert abs(tv_g - tv_o) <= 1e-6 * abs(tv_o)
+    assert torch.equal(d_old, d_avg) and np.array_equal(old_o, avg)
+    mean = (103.939, 116.779, 123.68)
+    eng.mean = np.float32(mean).reshape((3, 1, 1))
+    pic = eng.get_image_array(d_avg)
+    assert pic.dtype == np.uint8 and pic.shape == (H, W, 3)
+    assert np.array_equal(pic, get_image_array(avg, mean))

@@ -225,3 +225,23 @@ def test_config_precedence(tmp_path, monkeypatch):
     assert (a.size, a.tile_size, a.tv_weight) == (512, 384, 1)
     b = config_system.parse_args(['-ci', 'c', '-si', 's', '--config', str(tmp_path / 'extra.py')])
     assert (b.size, b.tile_size, b.tv_weight) == (512, 256, 7)
+
+
+def test_oracle_output_step_restates_reference_lines():
+    """oracle.transfer.iter_stats / get_image_array against the literal numpy expressions of
+    style_transfer.py:808-815 and :378-386 on a hand-made case (incl. clipping and BGR reversal)."""
+    from oracle.transfer import get_image_array, iter_stats
+    avg = np.float32(np.arange(3 * 2 * 3).reshape(3, 2, 3)) * np.float32(20) - np.float32(150)
+    old = avg + np.float32(1.5)
+    us, tv = iter_stats(avg, old)
+    assert abs(us - 1.5) < 1e-6 and np.array_equal(old, avg)
+    xd = avg - np.roll(avg, -1, axis=-1)
+    yd = avg - np.roll(avg, -1, axis=-2)
+    assert abs(tv - float(np.sqrt(np.mean(xd ** 2 + yd ** 2)))) < 1e-6
+    pic = get_image_array(avg)
+    mean = np.float32((103.939, 116.779, 123.68))
+    assert pic.shape == (2, 3, 3) and pic.dtype == np.uint8
+    # picture channel 0 (R) is model plane 2 (the model is BGR); values clip to [0, 255] and truncate
+    assert pic[0, 0, 0] == np.uint8(np.clip(avg[2, 0, 0] + mean[2], 0, 255))
+    assert pic[1, 2, 2] == np.uint8(np.clip(avg[0, 1, 2] + mean[0], 0, 255))
+    assert pic.min() == 0          # plane 0 starts at -150 + 103.9 < 0
