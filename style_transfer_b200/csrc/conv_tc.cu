@@ -504,6 +504,7 @@ int tc_init(TcContext& tc, int sm_count) {
   tc.resident_weights = getenv("ST_TC_NO_RESB") == nullptr;
   tc.defer_scale = getenv("ST_NO_DEFER") == nullptr;
   tc.pool_fusion = getenv("ST_NO_POOL_FUSION") == nullptr;
+  tc.pix_rows_kernel = getenv("ST_NO_PIX_ROWS") == nullptr;
   if (const char* f = getenv("ST_TC_BN")) tc.force_bn = atoi(f);
   return ST_OK;
 }
@@ -551,7 +552,7 @@ int tc_pack_first(TcContext& tc, TcWeights& w, const float* w_host, int cout) {
 }
 
 void tc_free_weights(TcWeights& w) {
-  cudaFree(w.fwd), cudaFree(w.bwd);
+  cudaFree(w.fwd), cudaFree(w.bwd), cudaFree(w.bwd_rows);
   delete static_cast<CUtensorMap*>(w.map_fwd);
   delete static_cast<CUtensorMap*>(w.map_bwd);
   w = TcWeights{};

@@ -16,6 +16,8 @@ namespace st {
 struct TcWeights {
   void* fwd = nullptr;             // 16-bit: bf16, or fp16 when fwd_half (ST_PREC_FP16)
   __nv_bfloat16* bwd = nullptr;    // always bf16: the backward pass runs on bf16 gradients
+  __nv_bfloat16* bwd_rows = nullptr;   // first layer only: [48][3*cout], the three x taps of a kernel
+                                       // row side by side (conv_pix_tc.cu)
   bool fwd_half = false;
   void* map_fwd = nullptr;     // host copies of the CUtensorMap descriptors (128 B each)
   void* map_bwd = nullptr;
@@ -28,6 +30,7 @@ struct TcContext {
   bool resident_weights = true;   // ST_TC_NO_RESB=1 disables
   bool defer_scale = true;        // ST_NO_DEFER=1 disables
   bool pool_fusion = true;        // ST_NO_POOL_FUSION=1 disables
+  bool pix_rows_kernel = true;    // ST_NO_PIX_ROWS=1: first-layer backward through conv_tc2.cu instead
   int force_bn = 0;               // ST_TC_BN=64|128|256
   int sm_count = 0;
   void* encode_fn = nullptr;   // cuTensorMapEncodeTiled, fetched through cudaGetDriverEntryPoint
@@ -87,6 +90,13 @@ int conv3x3_pool_tc_pair(TcContext& tc, const TcWeights& w, const void* in, void
 int conv_last_bwd_tc_pair(TcContext& tc, const TcWeights& w, const __nv_bfloat16* dz, int nb, int h,
                           int wd, int cz, float* grad, long batch_stride, long plane_stride,
                           long row_stride, cudaStream_t s);
+// The same on the dedicated kernel of conv_pix_tc.cu (one MMA per kernel ROW, the x shift in the
+// epilogue); needs tc_pack_first_rows.
+int tc_pack_first_rows(TcContext& tc, TcWeights& w, const float* w_oihw_host, int cout);
+bool conv_pix_bwd_tc_ok(const TcContext& tc, const TcWeights& w, int cz);
+int conv_pix_bwd_tc(TcContext& tc, const TcWeights& w, const __nv_bfloat16* dz, int nb, int h, int wd,
+                    int cz, float* grad, long batch_stride, long plane_stride, long row_stride,
+                    cudaStream_t s);
 // First convolution (3 -> 64 channels) on tensor cores from the planar f32 image (conv_first_tc.cu).
 struct ImageBatch;
 int tc_pack_first_fwd(TcContext& tc, TcWeights& w, const float* w_oihw_host, int cout, bool half);
@@ -101,13 +111,11 @@ int gemm_abs_tc_pair(TcContext& tc, const void* f, const void* d, bool half_in, 
                      cudaStream_t s);
 size_t gemm_abs_partials_needed(int nb, int h, int w, int c);
 
-// gram[b][C][C] (full, symmetric, fp32) = F_b^T F_b / (C*hw) for bf16 NHWC F [nb][hw][c] on tcgen05
-// (gram_tc.cu).  part: split-K scratch of gram_tc_part_floats() floats.
+// G_b = F_b^T F_b / (C*hw) for 16-bit NHWC F [nb][hw][c] on tcgen05 (gram_tc.cu), finished straight
+// into the style term.  part: split-K scratch of gram_tc_part_floats() floats.
 bool gram_tc_ok(const TcContext& tc, int c);
 size_t gram_tc_part_floats(const TcContext& tc, int nb, int hw, int c);
-int gram_tc(TcContext& tc, const void* f, bool half, int nb, int hw, int c, float* gram, float* part,
-            cudaStream_t s);
-// The same contraction finished straight into the style term: delta[b] = G_b - target (full [C][C]),
+// delta[b] = G_b - target (full [C][C]),
 // max_bits[b] (optional) = max |delta_b| as float bits, and loss_part[b * *parts_per_tile + i] =
 // partial sums of delta_ij^2 over j <= i, to be added in index order (delta_pack does).  G itself is
 // not stored.  loss_part must hold nb * (c / 32)^2 doubles.

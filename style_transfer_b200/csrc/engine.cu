@@ -453,6 +453,9 @@ int backward(st_ctx* ctx, const Dims& d, int nb, int deepest_blob, const std::ve
     const int hb = d.h[b], wb = d.w[b];
     if (l.kind == ST_CONV3X3 && b == 0) {
       if constexpr (sizeof(T) == 2) {
+        if (conv_pix_bwd_tc_ok(ctx->tc, l.tc, l.cout))
+          return conv_pix_bwd_tc(ctx->tc, l.tc, g, nb, hb, wb, l.cout, grad, batch_stride, plane,
+                                 rstride, s);
         if (ctx->tc.enabled && ctx->tc.pair_kernel && l.tc.bwd != nullptr && l.cout % 64 == 0)
           return conv_last_bwd_tc_pair(ctx->tc, l.tc, g, nb, hb, wb, l.cout, grad, batch_stride,
                                        plane, rstride, s);
@@ -749,6 +752,7 @@ int st_set_conv_params(st_ctx* ctx, int layer, const float* w, const float* b) {
     int rc = first ? tc_pack_first(ctx->tc, l.tc, w, co_n)
                    : tc_pack_weights(ctx->tc, l.tc, w, ci_n, co_n, half);
     if (rc == ST_OK && first) rc = tc_pack_first_fwd(ctx->tc, l.tc, w, co_n, half);
+    if (rc == ST_OK && first) rc = tc_pack_first_rows(ctx->tc, l.tc, w, co_n);
     if (rc != ST_OK) return rc;
   }
   l.has_params = true;

@@ -11,8 +11,8 @@
 //
 // The kernel is HBM-bound for C <= 256 (2*C flop per bf16 byte): the pixels are split over CTAs
 // (split-K), every CTA streams its share once, accumulates a [128][C] fp32 block in TMEM and writes
-// it to a partial buffer; gram_tc_finalize sums the partials in split order (deterministic, no float
-// atomics), scales and mirrors the lower triangle.
+// it to a partial buffer; gram_tc_finish sums the partials in split order (deterministic, no float
+// atomics), scales, mirrors the lower triangle and subtracts the style target in the same pass.
 //
 // Warps (192 threads): 0 = TMA producer, 1 = MMA issuer + TMEM owner, 2..5 = TMEM -> global.
 #include <cuda.h>
@@ -272,31 +272,12 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap map_f, const GramArgs a) {
   if (warp == 1) tmem_dealloc(tmem_base, Cfg::kTmemCols);
 }
 
-// gram[b][i][j] = gram[b][j][i] = scale * sum_s part[b][s][i][j] for j <= i: one thread per
-// lower-triangle element (reads coalesced along j, splits added in index order), which also writes
-// the mirrored element so that the matrix is exactly symmetric.  blockIdx.y = row i, blockIdx.z = b.
-__global__ void __launch_bounds__(128)
-gram_tc_finalize_kernel(const float* __restrict__ part, int nsplit, int c, double scale,
-                        float* __restrict__ gram) {
-  const int i = blockIdx.y, j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j > i) return;
-  const size_t cc = (size_t)c * c;
-  const float* p = part + (size_t)blockIdx.z * nsplit * cc + (size_t)i * c + j;
-  double sum = 0.0;
-#pragma unroll 4
-  for (int s = 0; s < nsplit; ++s) sum += (double)p[(size_t)s * cc];
-  const float g = (float)(sum * scale);
-  float* out = gram + (size_t)blockIdx.z * cc;
-  out[(size_t)i * c + j] = g;
-  out[(size_t)j * c + i] = g;
-}
-
-// The same reduction of the split partials fused with what the style term needs from the Gram matrix
+// Reduction of the split partials fused with what the style term needs from the Gram matrix
 // (style_transfer.py:587,591): delta = G - G_style (both triangles), per block the partial sum of
 // delta^2 over j <= i (added up in block order by delta_pack: deterministic, and no ticket / fence per
 // block -- a grid_reduce in each of the 32768 blocks of a C = 512 batch doubled this kernel's time)
 // and max |delta| (float bits, for the fp16 scaling of the style GEMM operand).  Replaces
-// gram_tc_finalize + gram_delta: one launch and no round trip of G through memory per style layer.
+// a separate finalize + gram_delta pair: one launch and no round trip of G through memory per style layer.
 struct GramFinish {
   const float* target;     // [C][C] symmetric
   float* delta;            // [nb][C][C]
@@ -396,8 +377,8 @@ int gram_splits(int hw) {
 }
 
 template <int C>
-int launch_gram(TcContext& tc, const void* f, bool half, int nb, int hw, float* gram, float* part,
-                const GramFinish* fin, cudaStream_t s) {
+int launch_gram(TcContext& tc, const void* f, bool half, int nb, int hw, float* part,
+                const GramFinish& fin, cudaStream_t s) {
   using Cfg = GramCfg<C>;
   CUtensorMap map_f;
   {
@@ -422,14 +403,9 @@ int launch_gram(TcContext& tc, const void* f, bool half, int nb, int hw, float* 
   ST_CUDA(tc_allow_smem(kern, Cfg::kSmemBytes));
   TimerScope ts(s, kTimeGram, 2.0 * C * C * hw * nb);
   ST_LAUNCH(kern, dim3(a.nsplit * Cfg::kMBlocks, nb), kGThreads, Cfg::kSmemBytes, s, map_f, a);
-  if (fin != nullptr) {
-    constexpr int kR = C >= 256 ? 4 : 1;
-    ST_LAUNCH(gram_tc_finish_kernel<kR>, dim3(C / 32, C / 32, nb), dim3(32, 32 / kR), 0, s, part,
-              a.nsplit, C, 1.0 / ((double)C * hw), *fin);
-  } else {
-    ST_LAUNCH(gram_tc_finalize_kernel, dim3(cdiv(C, 128), C, nb), 128, 0, s, part, a.nsplit, C,
-              1.0 / ((double)C * hw), gram);
-  }
+  constexpr int kR = C >= 256 ? 4 : 1;
+  ST_LAUNCH(gram_tc_finish_kernel<kR>, dim3(C / 32, C / 32, nb), dim3(32, 32 / kR), 0, s, part,
+            a.nsplit, C, 1.0 / ((double)C * hw), fin);
   return ST_OK;
 }
 
@@ -450,23 +426,6 @@ size_t gram_tc_part_floats(const TcContext& tc, int nb, int hw, int c) {
   return (size_t)nb * nsplit * c * c;
 }
 
-static int gram_dispatch(TcContext& tc, const void* f, bool half, int nb, int hw, int c, float* gram,
-                         float* part, const GramFinish* fin, cudaStream_t s) {
-  switch (c) {
-    case 64: return launch_gram<64>(tc, f, half, nb, hw, gram, part, fin, s);
-    case 128: return launch_gram<128>(tc, f, half, nb, hw, gram, part, fin, s);
-    case 256: return launch_gram<256>(tc, f, half, nb, hw, gram, part, fin, s);
-    case 512: return launch_gram<512>(tc, f, half, nb, hw, gram, part, fin, s);
-  }
-  set_error("gram_tc: unsupported channel count");
-  return ST_ERR_INVALID;
-}
-
-int gram_tc(TcContext& tc, const void* f, bool half, int nb, int hw, int c, float* gram, float* part,
-            cudaStream_t s) {
-  return gram_dispatch(tc, f, half, nb, hw, c, gram, part, nullptr, s);
-}
-
 int gram_tc_delta(TcContext& tc, const void* f, bool half, int nb, int hw, int c, float* part,
                   const float* target, float* delta, unsigned* max_bits, double* loss_part,
                   int* parts_per_tile, cudaStream_t s) {
@@ -475,7 +434,14 @@ int gram_tc_delta(TcContext& tc, const void* f, bool half, int nb, int hw, int c
              "gram_tc_delta: batch too large for the reduction scratch");
   if (max_bits != nullptr) ST_CUDA(cudaMemsetAsync(max_bits, 0, nb * sizeof(unsigned), s));
   const GramFinish fin{target, delta, max_bits, loss_part};
-  return gram_dispatch(tc, f, half, nb, hw, c, nullptr, part, &fin, s);
+  switch (c) {
+    case 64: return launch_gram<64>(tc, f, half, nb, hw, part, fin, s);
+    case 128: return launch_gram<128>(tc, f, half, nb, hw, part, fin, s);
+    case 256: return launch_gram<256>(tc, f, half, nb, hw, part, fin, s);
+    case 512: return launch_gram<512>(tc, f, half, nb, hw, part, fin, s);
+  }
+  set_error("gram_tc_delta: unsupported channel count");
+  return ST_ERR_INVALID;
 }
 
 }  // namespace st
