@@ -31,6 +31,8 @@ struct TcContext {
   bool defer_scale = true;        // ST_NO_DEFER=1 disables
   bool pool_fusion = true;        // ST_NO_POOL_FUSION=1 disables
   bool pix_rows_kernel = true;    // ST_NO_PIX_ROWS=1: first-layer backward through conv_tc2.cu instead
+  bool fwd_bits = true;           // ST_NO_FWD_BITS=1: ReLU bit masks made from the activations by
+                                  // relu_bits_from_act instead of the forward epilogues
   int force_bn = 0;               // ST_TC_BN=64|128|256
   int sm_count = 0;
   void* encode_fn = nullptr;   // cuTensorMapEncodeTiled, fetched through cudaGetDriverEntryPoint

@@ -240,7 +240,8 @@ int forward(st_ctx* ctx, const ImageBatch& view, const Dims& d, int last_layer,
     // the ReLU bit mask of this layer's output is wanted when a convolution consumes the blob and a
     // backward pass follows (its backward epilogue applies the mask)
     uint32_t* bits_out = nullptr;
-    if (for_backward && l.kind == ST_CONV3X3 && sizeof(T) == 2 && ctx->tc.enabled && ctx->tc.pair_kernel) {
+    if (for_backward && l.kind == ST_CONV3X3 && sizeof(T) == 2 && ctx->tc.enabled && ctx->tc.pair_kernel &&
+        ctx->tc.fwd_bits) {
       bool wanted = false;
       for (int j = i + 1; j <= last_layer; ++j)
         wanted = wanted || (ctx->layers[j].kind == ST_CONV3X3 && ctx->layers[j].bottom == l.top);

@@ -451,3 +451,30 @@ def test_iter_stats_and_picture_match_oracle(HW):
     pic = eng.get_image_array(d_avg)
     assert pic.dtype == np.uint8 and pic.shape == (H, W, 3)
     assert np.array_equal(pic, get_image_array(avg, mean))
+
+
+@pytest.mark.parametrize('precision', ['fp16', 'bf16'])
+def test_fallback_kernels_agree_with_the_default_path(precision, monkeypatch):
+    """ST_NO_FWD_BITS=1 (ReLU bit masks derived from the stored activations instead of written by the
+    forward epilogues) must give the same bits, hence a bit-identical gradient; ST_NO_PIX_ROWS=1 (the
+    first-layer backward through the generic pair kernel) sums the same products in another order:
+    1e-5 relative L2."""
+    H, W, tile = 96, 64, 48
+    c_layers, s_layers = ['conv3_2'], ['conv1_1', 'conv2_1', 'conv3_1']
+    results = []
+    for env in ({}, {'ST_NO_FWD_BITS': '1'}, {'ST_NO_PIX_ROWS': '1'}):
+        for k in ('ST_NO_FWD_BITS', 'ST_NO_PIX_ROWS'):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        eng, ora = engine_for('vgg16.prototxt', precision)
+        setup_targets(eng, ora, np.random.RandomState(4), H, W, c_layers, s_layers, tile=tile)
+        eng.img = eng.to_device(rand_img(np.random.RandomState(5), H, W))
+        lw = {l: 1.0 for l in ora.layers()}
+        loss, grad = eng.eval_sc_grad((8, -16), c_layers, s_layers, [], lw, {'conv3_2': 0.05},
+                                      {l: 1 / 3 for l in s_layers}, {}, tile)
+        torch.cuda.synchronize()
+        results.append((float(loss), grad.clone()))
+    assert torch.equal(results[1][1], results[0][1])
+    assert abs(results[1][0] - results[0][0]) <= 1e-12 * abs(results[0][0])
+    assert l2rel(results[2][1], results[0][1].cpu().numpy()) < 1e-5
