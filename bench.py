@@ -158,6 +158,49 @@ class CpuReference:
                 (n, unit, self.ntiles, round(self.ntiles * (self.tile_px / self.crop) ** 2)))
 
 
+class OneDnnConvs:
+    """Context manager for the "best-case CPU" stand-in of SURVEY section 8d: the oracle's three
+    convolution ops (Caffe's im2col + SGEMM restated in numpy / OpenBLAS) are replaced by torch's CPU
+    convolutions (oneDNN, all host cores) for the duration of a timing, so that the reported speed-up
+    is not inflated by a naive im2col.  Everything else (ReLU, pooling, Gram / loss code, the dW that
+    Caffe computes and discards) stays the oracle's.  Timing infrastructure only."""
+
+    def __enter__(self):
+        import torch
+        import torch.nn.functional as F
+        from oracle import caffe_ops as ops
+        self.ops, self.saved = ops, (ops.conv3x3_forward, ops.conv3x3_backward_data,
+                                     ops.conv3x3_backward_weight)
+        torch.set_num_threads(_HOST_CORES)
+
+        def fwd(x, weight, bias):
+            y = F.conv2d(torch.from_numpy(x)[None], torch.from_numpy(weight), torch.from_numpy(bias),
+                         padding=1)
+            return np.ascontiguousarray(y[0].numpy())
+
+        def bwd_data(top_diff, weight):
+            cin = weight.shape[1]
+            g = torch.nn.grad.conv2d_input((1, cin) + top_diff.shape[1:], torch.from_numpy(weight),
+                                           torch.from_numpy(np.ascontiguousarray(top_diff))[None],
+                                           padding=1)
+            return np.ascontiguousarray(g[0].numpy())
+
+        def bwd_weight(top_diff, x):
+            cout, cin = top_diff.shape[0], x.shape[0]
+            td = torch.from_numpy(np.ascontiguousarray(top_diff))[None]
+            dw = torch.nn.grad.conv2d_weight(torch.from_numpy(np.ascontiguousarray(x))[None],
+                                             (cout, cin, 3, 3), td, padding=1)
+            return dw.numpy(), top_diff.reshape(cout, -1).sum(axis=1)
+
+        ops.conv3x3_forward, ops.conv3x3_backward_data, ops.conv3x3_backward_weight = fwd, bwd_data, bwd_weight
+        return self
+
+    def __exit__(self, *exc):
+        (self.ops.conv3x3_forward, self.ops.conv3x3_backward_data,
+         self.ops.conv3x3_backward_weight) = self.saved
+        return False
+
+
 def run_reference(a):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
@@ -447,6 +490,17 @@ def run_engine(a):
         cpu = {'value': 1.0 / ref.iteration_seconds(t_tile, t_tail), 'unit': 'iterations/s',
                'cores': ref.cores, 'kind': 'port', 'sample': ref.sample_text(2),
                'tile_eval_s': t_tile, 'full_image_tail_s': t_tail}
+        # "best-case CPU" beside it: the same evaluation with oneDNN convolutions (torch CPU)
+        try:
+            with OneDnnConvs():
+                ref.tile_eval()
+                t_best = float(np.mean([ref.tile_eval() for _ in range(2)]))
+            cpu['best_case'] = {'value': 1.0 / ref.iteration_seconds(t_best, t_tail),
+                                'unit': 'iterations/s', 'tile_eval_s': t_best,
+                                'what': 'same sample with the convolutions (forward, backward-data, '
+                                        'dW) on torch CPU / oneDNN instead of im2col + OpenBLAS SGEMM'}
+        except Exception as e:                       # a reporting extra: never fail the bench line
+            cpu['best_case'] = {'unavailable': repr(e)[:200]}
 
     if rank == 0:
         cfg = workload_config(a, world)
