@@ -191,6 +191,24 @@ ST_API int st_iter_stats(const float* avg_dev, float* old_dev, int H, int W, dou
 ST_API int st_get_image_u8(const float* params_dev, int H, int W, const float mean[3], int bgr,
                            uint8_t* out_dev, st_stream stream);
 
+/* ---- scale change (num_utils.resize :90-108, optimizers.py:53-61, style_transfer.py:877-881) ------
+ * Per-channel float resampling of in_dev f32 [channels][h][w] to out_dev f32 [channels][out_h][out_w]
+ * with Pillow's algorithm for 'F' images, which is what the reference calls: horizontal pass first
+ * into a float32 intermediate, then vertical; per output sample the source samples are weighted in
+ * source order with float64 coefficients (normalised Lanczos-3 or bilinear, support scaled when
+ * shrinking) and float64 accumulation without fused multiply-add.  method: 0 = Lanczos, 1 = bilinear.
+ * tmp_dev: scratch of channels*h*out_w floats (unused when out_w == w).  Coefficient tables are built
+ * on the host per call.  STATUS: the arithmetic is pinned on the CPU (oracle.numeric.resize == PIL ==
+ * the reference's num_utils.resize, bit for bit); the CUDA kernel has not run on a GPU yet, so the
+ * command line keeps resizing through PIL unless ST_DEVICE_RESIZE=1. */
+ST_API int st_resize_f32(const float* in_dev, int channels, int h, int w, int out_h, int out_w,
+                         int method, float* out_dev, float* tmp_dev, st_stream stream);
+/* The coefficient table st_resize_f32 uses for one axis (host only, no device needed): *ksize weights
+ * per output sample.  Call with bounds_out = kk_out = NULL to get *ksize, then with int
+ * bounds_out[out_size][2] (first source index, count) and double kk_out[out_size][*ksize]. */
+ST_API int st_resample_coeffs(int in_size, int out_size, int method, int* ksize, int* bounds_out,
+                              double* kk_out);
+
 ST_API int st_lbfgs_inv_hv(const float* grad_dev, size_t n, int m, const float* const* s_dev,
                     const float* const* y_dev, const double* sy_host, float* p_dev,
                     double* scratch_dev, st_stream stream);

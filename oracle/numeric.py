@@ -78,3 +78,79 @@ def tv_norm(x, beta=2):
     ddy = 2 * dy * dg
     grad = ddx + ddy - np.roll(ddx, 1, axis=2) - np.roll(ddy, 1, axis=1)
     return loss, grad
+
+
+# ---------------------------------------------------------------------------------------------
+# resize (num_utils.py:90-108): per-channel float resampling through PIL 'F' images.  Restated from
+# Pillow's published algorithm (libImaging/Resample.c: precompute_coeffs + the 32-bit-per-channel
+# horizontal / vertical passes) so that the device kernel has something other than PIL itself to be
+# checked against; pinned bit for bit against PIL and against the reference's own num_utils.resize
+# (tests/golden/resize.npz, tests/test_oracle_golden.py).
+# ---------------------------------------------------------------------------------------------
+def _resample_filter(kind):
+    import math
+
+    def sinc(t):
+        if t == 0.0:
+            return 1.0
+        t = t * math.pi
+        return math.sin(t) / t
+
+    def lanczos(x):
+        return sinc(x) * sinc(x / 3) if -3.0 <= x < 3.0 else 0.0
+
+    def bilinear(x):
+        x = abs(x)
+        return 1.0 - x if x < 1.0 else 0.0
+    return {'lanczos': (lanczos, 3.0), 'bilinear': (bilinear, 1.0)}[kind]
+
+
+def resample_coeffs(in_size, out_size, kind='lanczos'):
+    """Pillow's precompute_coeffs for the full source range: returns (bounds int32[out, 2] =
+    (first source index, count), weights float64[out, ksize]), weights normalised per output."""
+    import math
+    filt, support0 = _resample_filter(kind)
+    scale = in_size / out_size
+    filterscale = max(scale, 1.0)
+    support = support0 * filterscale
+    ksize = int(math.ceil(support)) * 2 + 1
+    bounds = np.zeros((out_size, 2), np.int32)
+    kk = np.zeros((out_size, ksize), np.float64)
+    ss = 1.0 / filterscale
+    for xx in range(out_size):
+        center = (xx + 0.5) * scale
+        xmin = max(int(center - support + 0.5), 0)
+        xmax = min(int(center + support + 0.5), in_size) - xmin
+        ww = 0.0
+        for x in range(xmax):
+            w = filt((x + xmin - center + 0.5) * ss)
+            kk[xx, x] = w
+            ww += w
+        if ww != 0.0:
+            kk[xx, :xmax] /= ww
+        bounds[xx] = (xmin, xmax)
+    return bounds, kk
+
+
+def _resample_rows(a, out_w, kind):
+    """One pass along the last axis: float64 accumulation in source order, float32 store."""
+    bounds, kk = resample_coeffs(a.shape[-1], out_w, kind)
+    out = np.zeros(a.shape[:-1] + (out_w,), np.float32)
+    for xx, (xmin, count) in enumerate(bounds):
+        acc = np.zeros(a.shape[:-1], np.float64)
+        for x in range(count):
+            acc += a[..., x + xmin].astype(np.float64) * kk[xx, x]
+        out[..., xx] = acc
+    return out
+
+
+def resize(a, hw, method='lanczos'):
+    """Resamples [C,H,W] (or [H,W]) float32 to hw like ``num_utils.resize``: horizontal pass first
+    (float32 intermediate), then vertical; a pass whose size does not change is skipped."""
+    a = np.float32(a)
+    h, w = hw
+    t = _resample_rows(a, w, method) if w != a.shape[-1] else a
+    if h != a.shape[-2]:
+        t = np.swapaxes(_resample_rows(np.ascontiguousarray(np.swapaxes(t, -1, -2)), h, method), -1, -2)
+    return np.ascontiguousarray(t, dtype=np.float32)
+

@@ -34,15 +34,34 @@ def resize_to_fit(image, size, div=1, scale_up=False):
 
 
 def resize_f32(tensor, hw, method='lanczos'):
-    """``num_utils.resize`` (:90-108): per-channel float resampling through PIL 'F' images.  The
-    scale change happens once per scale, on the host."""
+    """``num_utils.resize`` (:90-108): per-channel float resampling of a CUDA f32 [C][H][W] tensor.
+    Default: through PIL 'F' images on the host, exactly as the reference does (once per scale).
+    ``ST_DEVICE_RESIZE=1`` keeps the data on the device (``st_resize_f32``: the same algorithm, its
+    coefficient tables pinned against PIL on the CPU; opt-in until the kernel has a GPU parity run)."""
     import torch
+    if os.environ.get('ST_DEVICE_RESIZE') == '1' and tensor.is_cuda:
+        return resize_f32_device(tensor, hw, method)
     from PIL import Image
     m = {'lanczos': Image.LANCZOS, 'bilinear': Image.BILINEAR}[method]
     a = tensor.detach().cpu().numpy().astype(np.float32)
     out = np.stack([np.asarray(Image.fromarray(ch).resize((hw[1], hw[0]), m), dtype=np.float32)
                     for ch in a])
     return torch.from_numpy(np.ascontiguousarray(out)).to(tensor.device)
+
+
+def resize_f32_device(tensor, hw, method='lanczos'):
+    """The scale change without leaving the GPU (``st_resize_f32``)."""
+    import ctypes as C
+    import torch
+    from . import _lib
+    t = tensor.detach().contiguous().float()
+    c, h, w = t.shape
+    out = torch.empty((c, hw[0], hw[1]), dtype=torch.float32, device=t.device)
+    tmp = torch.empty((c, h, hw[1]), dtype=torch.float32, device=t.device)
+    _lib.call('st_resize_f32', C.c_void_p(t.data_ptr()), c, h, w, int(hw[0]), int(hw[1]),
+              {'lanczos': 0, 'bilinear': 1}[method], C.c_void_p(out.data_ptr()),
+              C.c_void_p(tmp.data_ptr()), C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    return out
 
 
 class StatLogger:

@@ -1013,6 +1013,105 @@ int st_adam_step(float* params, const float* grad, float* g1, float* g2, float* 
                    p1_corr, (cudaStream_t)stream);
 }
 
+namespace {
+// Pillow's precompute_coeffs (libImaging/Resample.c) for the full source range, in double.
+struct ResampleTable {
+  int ksize = 0;
+  std::vector<int> bounds;      // [out][2] = first source index, count
+  std::vector<double> kk;       // [out][ksize], normalised
+};
+ResampleTable resample_table(int in_size, int out_size, int method) {
+  const double kPi = 3.14159265358979323846;
+  auto sinc = [&](double t) {
+    if (t == 0.0) return 1.0;
+    t *= kPi;
+    return sin(t) / t;
+  };
+  auto filt = [&](double x) {
+    if (method == 0) return (-3.0 <= x && x < 3.0) ? sinc(x) * sinc(x / 3) : 0.0;
+    if (x < 0.0) x = -x;
+    return x < 1.0 ? 1.0 - x : 0.0;
+  };
+  const double scale = (double)in_size / out_size, filterscale = scale < 1.0 ? 1.0 : scale;
+  const double support = (method == 0 ? 3.0 : 1.0) * filterscale, ss = 1.0 / filterscale;
+  ResampleTable t;
+  t.ksize = (int)ceil(support) * 2 + 1;
+  t.bounds.assign((size_t)out_size * 2, 0);
+  t.kk.assign((size_t)out_size * t.ksize, 0.0);
+  for (int xx = 0; xx < out_size; ++xx) {
+    const double center = (xx + 0.5) * scale;
+    int xmin = (int)(center - support + 0.5);
+    if (xmin < 0) xmin = 0;
+    int xmax = (int)(center + support + 0.5);
+    if (xmax > in_size) xmax = in_size;
+    xmax -= xmin;
+    double* k = &t.kk[(size_t)xx * t.ksize];
+    double ww = 0.0;
+    for (int x = 0; x < xmax; ++x) {
+      const double w = filt((x + xmin - center + 0.5) * ss);
+      k[x] = w;
+      ww += w;
+    }
+    if (ww != 0.0)
+      for (int x = 0; x < xmax; ++x) k[x] /= ww;
+    t.bounds[2 * xx] = xmin, t.bounds[2 * xx + 1] = xmax;
+  }
+  return t;
+}
+
+int run_resample(const float* in, float* out, int channels, int in_h, int in_w, int out_size,
+                 bool along_y, int method, cudaStream_t s) {
+  const ResampleTable t = resample_table(along_y ? in_h : in_w, out_size, method);
+  int* bounds_dev = nullptr;
+  double* kk_dev = nullptr;
+  ST_CUDA(cudaMallocAsync((void**)&bounds_dev, t.bounds.size() * sizeof(int), s));
+  ST_CUDA(cudaMallocAsync((void**)&kk_dev, t.kk.size() * sizeof(double), s));
+  // pageable sources: the copies are staged before the call returns, so the vectors may die here
+  ST_CUDA(cudaMemcpyAsync(bounds_dev, t.bounds.data(), t.bounds.size() * sizeof(int),
+                          cudaMemcpyHostToDevice, s));
+  ST_CUDA(cudaMemcpyAsync(kk_dev, t.kk.data(), t.kk.size() * sizeof(double), cudaMemcpyHostToDevice, s));
+  int rc = resample_pass(in, out, channels, in_h, in_w, out_size, along_y, bounds_dev, kk_dev, t.ksize, s);
+  ST_CUDA(cudaFreeAsync(bounds_dev, s));
+  ST_CUDA(cudaFreeAsync(kk_dev, s));
+  return rc;
+}
+}  // namespace
+
+int st_resample_coeffs(int in_size, int out_size, int method, int* ksize, int* bounds_out,
+                       double* kk_out) {
+  ST_REQUIRE(in_size > 0 && out_size > 0 && (method == 0 || method == 1) && ksize,
+             "st_resample_coeffs: bad arguments");
+  const ResampleTable t = resample_table(in_size, out_size, method);
+  *ksize = t.ksize;
+  if (bounds_out) std::memcpy(bounds_out, t.bounds.data(), t.bounds.size() * sizeof(int));
+  if (kk_out) std::memcpy(kk_out, t.kk.data(), t.kk.size() * sizeof(double));
+  return ST_OK;
+}
+
+int st_resize_f32(const float* in_dev, int channels, int h, int w, int out_h, int out_w, int method,
+                  float* out_dev, float* tmp_dev, st_stream stream) {
+  ST_REQUIRE(in_dev && out_dev && channels > 0 && h > 0 && w > 0 && out_h > 0 && out_w > 0,
+             "st_resize_f32: bad arguments");
+  ST_REQUIRE(method == 0 || method == 1, "st_resize_f32: method must be 0 (Lanczos) or 1 (bilinear)");
+  cudaStream_t s = (cudaStream_t)stream;
+  const bool need_x = out_w != w, need_y = out_h != h;
+  if (!need_x && !need_y) {
+    ST_CUDA(cudaMemcpyAsync(out_dev, in_dev, (size_t)channels * h * w * sizeof(float),
+                            cudaMemcpyDeviceToDevice, s));
+    return ST_OK;
+  }
+  ST_REQUIRE(!(need_x && need_y) || tmp_dev != nullptr, "st_resize_f32: tmp_dev needed for two passes");
+  int rc = ST_OK;
+  const float* src = in_dev;
+  if (need_x) {                                         // horizontal first, like ImagingResample
+    float* dst = need_y ? tmp_dev : out_dev;
+    rc = run_resample(src, dst, channels, h, w, out_w, false, method, s);
+    src = dst;
+  }
+  if (rc == ST_OK && need_y) rc = run_resample(src, out_dev, channels, h, out_w, out_h, true, method, s);
+  return rc;
+}
+
 int st_iter_stats(const float* avg_dev, float* old_dev, int H, int W, double* stats_dev,
                   st_stream stream) {
   ST_REQUIRE(avg_dev && old_dev && stats_dev && H > 0 && W > 0, "st_iter_stats: bad arguments");

@@ -141,6 +141,10 @@ int unpack_regularizers(const float* packed, int H, int W, int nty, int ntx, int
 int adam_step(float* params, const float* grad, float* g1, float* g2, float* p1, float* avg_out,
               size_t n, float step_size, float b1, float b2, float bp1, float g1_corr,
               float g2_corr, float p1_corr, cudaStream_t s);
+// One resampling pass along x (transposed = false: out[c][y][xx]) or along y (transposed = true:
+// out[c][yy][x]) with per-output (first source index, count) bounds and ksize float64 weights.
+int resample_pass(const float* in, float* out, int channels, int in_h, int in_w, int out_size,
+                  bool along_y, const int* bounds_dev, const double* kk_dev, int ksize, cudaStream_t s);
 // stats[0] = sum |avg - old|, stats[1] = sum of squared periodic forward differences; old := avg
 int iter_stats(const float* avg, float* old, int H, int W, double* stats, ReduceScratch rs,
                cudaStream_t s);

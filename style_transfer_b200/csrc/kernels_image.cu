@@ -405,6 +405,44 @@ int get_image_u8(const float* params, int H, int W, float m0, float m1, float m2
 }
 
 // -----------------------------------------------------------------------------------------------------
+// Scale change: one pass of Pillow's float resampling (num_utils.resize :90-108).  One thread per
+// output sample; the weights of an output index are shared by a whole row (x pass) or column (y
+// pass).  double multiply and add kept separate (__dmul_rn / __dadd_rn): PIL's C loop is not
+// contracted into FMAs, and the result is rounded to float32 once per pass, as PIL stores it.
+// -----------------------------------------------------------------------------------------------------
+template <bool ALONG_Y>
+__global__ void __launch_bounds__(256)
+resample_kernel(const float* __restrict__ in, float* __restrict__ out, int in_h, int in_w, int out_h,
+                int out_w, const int* __restrict__ bounds, const double* __restrict__ kk, int ksize) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, c = blockIdx.z;
+  if (x >= out_w) return;
+  const float* src = in + (size_t)c * in_h * in_w;
+  const int o = ALONG_Y ? y : x;                       // index of the output sample along the pass
+  const int first = bounds[2 * o], count = bounds[2 * o + 1];
+  const double* k = kk + (size_t)o * ksize;
+  double ss = 0.0;
+  for (int i = 0; i < count; ++i) {
+    const float v = ALONG_Y ? src[(size_t)(first + i) * in_w + x] : src[(size_t)y * in_w + first + i];
+    ss = __dadd_rn(ss, __dmul_rn((double)v, k[i]));
+  }
+  out[((size_t)c * out_h + y) * out_w + x] = (float)ss;
+}
+
+int resample_pass(const float* in, float* out, int channels, int in_h, int in_w, int out_size,
+                  bool along_y, const int* bounds_dev, const double* kk_dev, int ksize, cudaStream_t s) {
+  const int out_h = along_y ? out_size : in_h, out_w = along_y ? in_w : out_size;
+  const dim3 grid(cdiv(out_w, 256), out_h, channels);
+  if (along_y) {
+    ST_LAUNCH(resample_kernel<true>, grid, 256, 0, s, in, out, in_h, in_w, out_h, out_w, bounds_dev,
+              kk_dev, ksize);
+  } else {
+    ST_LAUNCH(resample_kernel<false>, grid, 256, 0, s, in, out, in_h, in_w, out_h, out_w, bounds_dev,
+              kk_dev, ksize);
+  }
+  return ST_OK;
+}
+
+// -----------------------------------------------------------------------------------------------------
 // BLAS-1 on the device for L-BFGS.
 // -----------------------------------------------------------------------------------------------------
 template <bool ABS>

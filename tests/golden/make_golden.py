@@ -134,6 +134,20 @@ def main():
     out['lbfgs_params'], out['lbfgs_loss'] = np.stack(traj), np.float64(losses)
     out['lbfgs_mem'] = np.int32(len(opt.sk))
     np.savez(os.path.join(OUT, 'optimizers.npz'), **out)
+
+    # ---- num_utils.resize (its own RNG and file: the fixtures above stay bit-identical) -----------
+    from PIL import Image
+    rr = np.random.RandomState(77)
+    out = {}
+    cases = [((3, 37, 53), (52, 75)), ((3, 64, 48), (91, 68)), ((2, 50, 70), (36, 49)),
+             ((1, 45, 45), (45, 64))]
+    for i, (shape, hw) in enumerate(cases):
+        x = (rr.rand(*shape) * 300 - 120).astype(np.float32)
+        out['in_%d' % i], out['hw_%d' % i] = x, np.int32(hw)
+        out['lanczos_%d' % i] = nu.resize(x, hw)
+        out['bilinear_%d' % i] = nu.resize(x, hw, method=Image.BILINEAR)
+    out['n_cases'] = np.int32(len(cases))
+    np.savez(os.path.join(OUT, 'resize.npz'), **out)
     print('wrote', sorted(os.listdir(OUT)))
 
 

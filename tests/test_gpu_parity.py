@@ -478,3 +478,17 @@ def test_fallback_kernels_agree_with_the_default_path(precision, monkeypatch):
     assert torch.equal(results[1][1], results[0][1])
     assert abs(results[1][0] - results[0][0]) <= 1e-12 * abs(results[0][0])
     assert l2rel(results[2][1], results[0][1].cpu().numpy()) < 1e-5
+
+
+@pytest.mark.skipif(os.environ.get('ST_TEST_DEVICE_RESIZE') != '1',
+                    reason='st_resize_f32 is opt-in until its first GPU parity run (set ST_TEST_DEVICE_RESIZE=1)')
+@pytest.mark.parametrize('method', ['lanczos', 'bilinear'])
+def test_device_resize_matches_oracle(method):
+    """st_resize_f32 against oracle.numeric.resize (== PIL == the reference's num_utils.resize,
+    tests/test_oracle_golden.py): bit for bit, up- and down-scaling."""
+    from style_transfer_b200.cli import resize_f32_device
+    rs = np.random.RandomState(9)
+    for shape, hw in (((3, 37, 53), (52, 75)), ((3, 64, 48), (45, 34)), ((1, 45, 45), (45, 64))):
+        a = (rs.rand(*shape) * 300 - 120).astype(np.float32)
+        got = resize_f32_device(torch.from_numpy(a).cuda(), hw, method).cpu().numpy()
+        assert np.array_equal(got, on.resize(a, hw, method)), (shape, hw)

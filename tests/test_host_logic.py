@@ -245,3 +245,23 @@ def test_oracle_output_step_restates_reference_lines():
     assert pic[0, 0, 0] == np.uint8(np.clip(avg[2, 0, 0] + mean[2], 0, 255))
     assert pic[1, 2, 2] == np.uint8(np.clip(avg[0, 1, 2] + mean[0], 0, 255))
     assert pic.min() == 0          # plane 0 starts at -150 + 103.9 < 0
+
+
+@pytest.mark.parametrize('method,name', [(0, 'lanczos'), (1, 'bilinear')])
+def test_resample_coefficient_table_matches_oracle(method, name):
+    """st_resample_coeffs (host half of st_resize_f32; no device needed) against the oracle's
+    restatement of Pillow's precompute_coeffs: same bounds, the float64 weights bit for bit -- up-
+    and down-scaling, including the ragged supports at the image borders."""
+    import ctypes as C
+    from oracle import numeric as on
+    from style_transfer_b200 import _lib
+    for in_size, out_size in ((53, 75), (64, 91), (70, 49), (181, 256), (512, 362), (7, 3)):
+        ksize = C.c_int()
+        _lib.call('st_resample_coeffs', in_size, out_size, method, C.byref(ksize), None, None)
+        bounds = np.zeros((out_size, 2), np.int32)
+        kk = np.zeros((out_size, ksize.value), np.float64)
+        _lib.call('st_resample_coeffs', in_size, out_size, method, C.byref(ksize),
+                  bounds.ctypes.data_as(C.c_void_p), kk.ctypes.data_as(C.c_void_p))
+        b_o, k_o = on.resample_coeffs(in_size, out_size, name)
+        assert k_o.shape == kk.shape and np.array_equal(bounds, b_o)
+        assert np.array_equal(kk, k_o), (in_size, out_size, np.abs(kk - k_o).max())

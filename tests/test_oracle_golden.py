@@ -109,3 +109,26 @@ def test_lbfgs_trajectory(og):
         tol = 1e-4 if it < 8 else 2e-2
         close(params, og['lbfgs_params'][it], rtol=tol)
     assert len(opt.sk) == int(og['lbfgs_mem'])
+
+
+def test_resize_matches_reference_golden(golden_dir):
+    """oracle.numeric.resize (a restatement of Pillow's float resampling) against outputs of the
+    reference's own num_utils.resize (:90-108): bit for bit, Lanczos and bilinear, up and down."""
+    g = np.load(os.path.join(golden_dir, 'resize.npz'))
+    for i in range(int(g['n_cases'])):
+        hw = tuple(int(v) for v in g['hw_%d' % i])
+        for method in ('lanczos', 'bilinear'):
+            got = on.resize(g['in_%d' % i], hw, method)
+            assert got.dtype == np.float32 and got.shape == g['%s_%d' % (method, i)].shape
+            assert np.array_equal(got, g['%s_%d' % (method, i)]), (i, method)
+
+
+def test_resize_matches_pil_directly():
+    """The same against PIL itself on a fresh case (PIL is present on both machines)."""
+    from PIL import Image
+    rs = np.random.RandomState(5)
+    a = (rs.rand(41, 29) * 255 - 100).astype(np.float32)
+    for hw in ((58, 41), (29, 20), (41, 50)):
+        for method, pil in (('lanczos', Image.LANCZOS), ('bilinear', Image.BILINEAR)):
+            want = np.asarray(Image.fromarray(a).resize((hw[1], hw[0]), pil), dtype=np.float32)
+            assert np.array_equal(on.resize(a, hw, method), want), (hw, method)
