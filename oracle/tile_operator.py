@@ -109,16 +109,19 @@ class OracleModel:
         return feats
 
     def preprocess(self, content_imgs, style_imgs, content_layers, style_layers, tile_size=512):
-        """content_imgs / style_imgs: lists of preprocessed f32[3,H,W] arrays."""
+        """content_imgs / style_imgs: lists of preprocessed f32[3,H,W] arrays.  A style entry may be
+        a list of arrays: the scaled copies of ``--style-multiscale`` (style_transfer.py:501-524),
+        each adding its Gram matrices and counting once in the average."""
         if not self.styles:
             grams, count = {}, 0
-            for img in style_imgs:
-                self.img = img.copy()
-                feats = self.prepare_features(style_layers, tile_size, passes=1)
-                for layer in feats:
-                    g = gram_lower(feats[layer])
-                    grams[layer] = g if layer not in grams else grams[layer] + g
-                count += 1
+            for entry in style_imgs:
+                for img in (entry if isinstance(entry, (list, tuple)) else [entry]):
+                    self.img = img.copy()
+                    feats = self.prepare_features(style_layers, tile_size, passes=1)
+                    for layer in feats:
+                        g = gram_lower(feats[layer])
+                        grams[layer] = g if layer not in grams else grams[layer] + g
+                    count += 1
             for g in grams.values():
                 g /= count
             self.styles.append(grams)

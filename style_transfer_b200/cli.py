@@ -64,6 +64,30 @@ def resize_f32_device(tensor, hw, method='lanczos'):
     return out
 
 
+def style_multiscale_variants(image, vmin, vmax, div=1):
+    """The scaled copies of one style image whose Gram matrices ``--style-multiscale MIN MAX``
+    averages (preprocess_images :501-524): sizes from MAX down by sqrt(2) while >= max(32, MIN),
+    visited smallest first, stopping after the first size that no longer shrinks the image and
+    skipping copies whose short side falls below 32 pixels."""
+    size, sizes = vmax, [vmax]
+    while True:
+        size = int(round(size / np.sqrt(2)))
+        if size < max(32, vmin):
+            break
+        sizes.append(size)
+    out, too_big = [], False
+    for size in reversed(sizes):
+        if too_big:
+            break
+        scaled = resize_to_fit(image, size, div)
+        if max(scaled.size) == max(image.size):
+            too_big = True
+        if min(scaled.size) < 32:
+            continue
+        out.append(scaled)
+    return out
+
+
 class StatLogger:
     """Per-iteration CSV with the reference's columns (style_transfer.py:101-130)."""
     columns = ['iteration', 'scale', 'step', 'time', 'content_h', 'content_w', 'update_size', 'loss',
@@ -116,10 +140,18 @@ def transfer_multiscale(st, args, content_images, style_images, initial_image=No
         else:
             init = initial_image.resize((w, h), Image.LANCZOS) if initial_image is not None else None
             st.init_first_scale(h, w, init)
-        model.styles = []                                            # recomputed at every scale
+        multiscale = getattr(args, 'style_multiscale', None)
+        if multiscale:
+            # every style image becomes the list of its scaled copies; the Grams are computed once,
+            # at the first scale, and kept (:754-755: styles are only reset without the flag)
+            style_arrays = [[model.pil_to_image(v) for v in
+                             style_multiscale_variants(im, multiscale[0], multiscale[1], args.div)]
+                            for im in style_scaled]
+        else:
+            model.styles = []                                        # recomputed at every scale
+            style_arrays = [model.pil_to_image(im) for im in style_scaled]
         iters = args.iterations[min(i, len(args.iterations) - 1)]
-        output = st.transfer(iters, [model.pil_to_image(im) for im in content_scaled],
-                             [model.pil_to_image(im) for im in style_scaled],
+        output = st.transfer(iters, [model.pil_to_image(im) for im in content_scaled], style_arrays,
                              callback=(lambda **kw: callback(scale=i + 1, size=(h, w), **kw))
                              if callback else None)
     return output
@@ -146,8 +178,7 @@ def main(argv=None):
         for name, shape in net.shapes.items():
             print('% 25s %s' % (name, shape))
         return 0
-    for flag, bad in (('--jitter', args.jitter), ('--style-multiscale', args.style_multiscale),
-                      ('--swt-weight', args.swt_weight)):
+    for flag, bad in (('--jitter', args.jitter), ('--swt-weight', args.swt_weight)):
         if bad:
             raise SystemExit('%s is outside the scope of this engine (see DESIGN.md section 7)' % flag)
     relaunch_multi_device(args, argv)

@@ -42,7 +42,8 @@ def build_parser():
     arg('--max-style-size', type=int, help='the maximum style size')
     arg('--style-scale-up', default=False, action='store_true', help='allow scaling style images up')
     arg('--style-multiscale', '-sm', type=int, nargs=2, metavar=('MIN_SCALE', 'MAX_SCALE'),
-        default=None, help='not supported (out of the hot-path scope)')
+        default=None, help='average the style Gram matrices over copies of each style image '
+        'scaled from MAX_SCALE down by sqrt(2) to MIN_SCALE (computed once, at the first scale)')
     arg('--tile-size', type=int, default=512, help='the maximum rendering tile size')
     arg('--optimizer', '-o', default='adam', choices=['adam', 'lbfgs'], help='the optimizer to use')
     arg('--step-size', '-st', type=ffloat, default=15, help='the initial step size for Adam')

@@ -243,19 +243,22 @@ class TileEngine:
 
     def preprocess_images(self, content_images, style_images, content_layers, style_layers,
                           tile_size=512):
-        """Style Grams and content features (:488-554; arrays in ``pil_to_image`` format; the
-        ``--style-multiscale`` and ``--jitter`` branches are not part of the hot path)."""
+        """Style Grams and content features (:488-554; arrays in ``pil_to_image`` format).  An entry
+        of ``style_images`` may be a LIST of arrays -- the scaled copies of one style image under
+        ``--style-multiscale`` (:501-524, built by cli.style_multiscale_variants): every copy adds its
+        Gram matrices and counts once in the average.  The ``--jitter`` branch is not implemented."""
         saved_img, saved_roll = self.img, self.roll_px.copy()
         self.roll_px[:] = 0
         if not self.styles:
             grams, count = {}, 0
-            for image in style_images:
-                self.img = self.to_device(image)
-                feats = self.prepare_features(style_layers, tile_size, passes=1)
-                for layer in feats:
-                    gram = self.gram_matrix(feats[layer])
-                    grams[layer] = gram if layer not in grams else grams[layer] + gram
-                count += 1
+            for entry in style_images:
+                for image in (entry if isinstance(entry, (list, tuple)) else [entry]):
+                    self.img = self.to_device(image)
+                    feats = self.prepare_features(style_layers, tile_size, passes=1)
+                    for layer in feats:
+                        gram = self.gram_matrix(feats[layer])
+                        grams[layer] = gram if layer not in grams else grams[layer] + gram
+                    count += 1
             for gram in grams.values():
                 gram /= count
             self.styles.append(StyleData(grams))

@@ -122,7 +122,9 @@ class StyleTransfer:
         self.c_layers, self.c_weight = parse_weights(a.content_layers, a.content_weight)
         self.s_layers, self.s_weight = parse_weights(a.style_layers, 1)
         self.d_layers, self.d_weight = parse_weights(a.dd_layers, a.dd_weight)
-        model.contents, model.styles = [], []
+        model.contents = []
+        if not getattr(a, 'style_multiscale', None):                 # (:754-755)
+            model.styles = []
         model.preprocess_images(content_images, style_images, self.c_layers, self.s_layers,
                                 a.tile_size)
         model.set_contents_and_styles()

@@ -492,3 +492,23 @@ def test_device_resize_matches_oracle(method):
         a = (rs.rand(*shape) * 300 - 120).astype(np.float32)
         got = resize_f32_device(torch.from_numpy(a).cuda(), hw, method).cpu().numpy()
         assert np.array_equal(got, on.resize(a, hw, method)), (shape, hw)
+
+
+@pytest.mark.skipif(os.environ.get('ST_TEST_STYLE_MULTISCALE') != '1',
+                    reason='--style-multiscale was added without a GPU at hand (set ST_TEST_STYLE_MULTISCALE=1)')
+def test_style_multiscale_grams_match_oracle():
+    """Style Grams averaged over the scaled copies of a style image (--style-multiscale,
+    style_transfer.py:501-524): engine preprocessing against the oracle's, fp32 mode."""
+    from PIL import Image
+    from style_transfer_b200.cli import style_multiscale_variants
+    eng, ora = engine_for('vgg16.prototxt')
+    rs = np.random.RandomState(13)
+    pil = Image.fromarray(rs.randint(0, 256, (96, 80, 3)).astype(np.uint8))
+    variants = [to_params(np.asarray(v)) for v in style_multiscale_variants(pil, 40, 128)]
+    assert len(variants) >= 3
+    layers = ['conv1_1', 'conv2_1', 'conv3_1']
+    eng.contents, eng.styles, ora.contents, ora.styles = [], [], [], []
+    eng.preprocess_images([], [variants], [], layers, 48)
+    ora.preprocess([], [variants], [], layers, 48)
+    for l in layers:
+        assert maxrel(eng.styles[0].grams[l], ora.styles[0][l]) < 2e-4, l

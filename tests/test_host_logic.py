@@ -265,3 +265,22 @@ def test_resample_coefficient_table_matches_oracle(method, name):
         b_o, k_o = on.resample_coeffs(in_size, out_size, name)
         assert k_o.shape == kk.shape and np.array_equal(bounds, b_o)
         assert np.array_equal(kk, k_o), (in_size, out_size, np.abs(kk - k_o).max())
+
+
+def test_style_multiscale_variants_follow_reference_loop():
+    """cli.style_multiscale_variants against the loop of preprocess_images (:501-524) worked by
+    hand: sizes 512, 362, 256, 181, 128, 91, 64 visited smallest first; the 300x200 image stops
+    shrinking at 362 (returned unscaled, processed, then the loop ends); a 40-pixel short side is
+    kept, a 28-pixel one skipped."""
+    from PIL import Image
+    from style_transfer_b200.cli import style_multiscale_variants
+    im = Image.new('RGB', (300, 200))
+    got = [v.size for v in style_multiscale_variants(im, 64, 512)]
+    assert got == [(64, 43), (91, 61), (128, 85), (181, 121), (256, 171), (300, 200)]
+    # MIN below 32 is clamped to 32; copies whose short side is < 32 are skipped, larger ones kept
+    im = Image.new('RGB', (400, 100))
+    got = [v.size for v in style_multiscale_variants(im, 1, 256)]
+    assert got == [(128, 32), (181, 45), (256, 64)]
+    # div quantises both sides like resize_to_fit (:965-975)
+    im = Image.new('RGB', (300, 200))
+    assert [v.size for v in style_multiscale_variants(im, 128, 181, div=8)] == [(128, 80), (176, 112)]
