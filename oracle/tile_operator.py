@@ -108,7 +108,8 @@ class OracleModel:
             self.roll_features(feats, -xy)
         return feats
 
-    def preprocess(self, content_imgs, style_imgs, content_layers, style_layers, tile_size=512):
+    def preprocess(self, content_imgs, style_imgs, content_layers, style_layers, tile_size=512,
+                   roll=None):
         """content_imgs / style_imgs: lists of preprocessed f32[3,H,W] arrays.  A style entry may be
         a list of arrays: the scaled copies of ``--style-multiscale`` (style_transfer.py:501-524),
         each adding its Gram matrices and counting once in the average."""
@@ -125,9 +126,14 @@ class OracleModel:
             for g in grams.values():
                 g /= count
             self.styles.append(grams)
+        # ``roll`` given = the per-iteration preprocessing of --jitter (:526, :545-552): the image is
+        # rolled before its features are taken, in ONE pass
         for img in content_imgs:
             self.img = img.copy()
-            self.contents.append(self.prepare_features(content_layers, tile_size, passes=10))
+            if roll is not None:
+                roll2_(self.img, roll)
+            self.contents.append(self.prepare_features(content_layers, tile_size,
+                                                       passes=10 if roll is None else 1))
 
     def publish(self):
         """``TileWorkerPool.set_contents_and_styles`` (:309-332): every worker receives its own

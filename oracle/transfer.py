@@ -122,18 +122,31 @@ class OracleTransfer:
         c_layers, c_weight = parse_weights(a.content_layers, a.content_weight)
         s_layers, s_weight = parse_weights(a.style_layers, 1)
         d_layers, d_weight = parse_weights(a.dd_layers, a.dd_weight)
+        jitter = bool(getattr(a, 'jitter', False))
         model.contents, model.styles = [], []
-        model.preprocess(content_imgs, style_imgs, c_layers, s_layers, a.tile_size)
+        if jitter:                                                              # :757-759
+            model.preprocess([], style_imgs, [], s_layers, a.tile_size)
+        else:
+            model.preprocess(content_imgs, style_imgs, c_layers, s_layers, a.tile_size)
         model.publish()
         model.img = params
         avg_img = None
         for step in range(1, iterations + 1):
             js, _ = model.layer_info([l for l in reversed(model.layers()) if l in c_layers][0])
+            if jitter:                                                          # :780-782
+                js = 1
+                model.contents = []
             img_size = np.array(model.img.shape[-2:])
             xy = np.int32(np.random.uniform(-0.5, 0.5, size=2) * img_size) // js   # :784
             model.roll(xy, jitter_scale=js)
             self.optimizer.roll(xy * js)
-            sc_args = (xy * js, c_layers, s_layers, d_layers, self.layer_weights, c_weight,
+            xy_ = xy
+            if jitter:                                                          # :788-794
+                model.preprocess(content_imgs, [], c_layers, [], a.tile_size, roll=xy)
+                model.img = params
+                model.publish()
+                xy_ = np.asarray((0, 0))
+            sc_args = (xy_ * js, c_layers, s_layers, d_layers, self.layer_weights, c_weight,
                        s_weight, d_weight, a.tile_size)
             avg_img, loss = self.optimizer.update(lambda p: self.loss_and_grad(p, sc_args))
             model.roll(-xy, jitter_scale=js)

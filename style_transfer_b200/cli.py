@@ -178,7 +178,7 @@ def main(argv=None):
         for name, shape in net.shapes.items():
             print('% 25s %s' % (name, shape))
         return 0
-    for flag, bad in (('--jitter', args.jitter), ('--swt-weight', args.swt_weight)):
+    for flag, bad in (('--swt-weight', args.swt_weight),):
         if bad:
             raise SystemExit('%s is outside the scope of this engine (see DESIGN.md section 7)' % flag)
     relaunch_multi_device(args, argv)

@@ -80,7 +80,9 @@ def build_parser():
     arg('--save-every', metavar='N', type=int, default=0, help='save the image every n steps')
     arg('--seed', type=int, default=0, help='the random seed')
     arg('--div', metavar='FACTOR', type=int, default=1, help='ensure all images are divisible by FACTOR')
-    arg('--jitter', action='store_true', help='not supported (out of the hot-path scope)')
+    arg('--jitter', action='store_true',
+        help='roll by whole pixels and recompute the content features from the rolled content '
+        'image in every iteration (slower; avoids the feature-grid quantisation of the roll)')
     arg('--debug', action='store_true', help='enable debug messages')
     arg('--precision', default='fp16', choices=['bf16', 'fp16', 'fp32'],
         help='bf16 / fp16 (fp16 forward, bf16 backward): tcgen05 tensor cores; fp32: exact SIMT parity mode')

@@ -242,11 +242,12 @@ class TileEngine:
         return out
 
     def preprocess_images(self, content_images, style_images, content_layers, style_layers,
-                          tile_size=512):
+                          tile_size=512, content_passes=10):
         """Style Grams and content features (:488-554; arrays in ``pil_to_image`` format).  An entry
         of ``style_images`` may be a LIST of arrays -- the scaled copies of one style image under
         ``--style-multiscale`` (:501-524, built by cli.style_multiscale_variants): every copy adds its
-        Gram matrices and counts once in the average.  The ``--jitter`` branch is not implemented."""
+        Gram matrices and counts once in the average.  ``content_passes`` = 1 is the ``roll is not
+        None`` case of the reference (:545-549): the per-iteration preprocessing of ``--jitter``."""
         saved_img, saved_roll = self.img, self.roll_px.copy()
         self.roll_px[:] = 0
         if not self.styles:
@@ -264,7 +265,7 @@ class TileEngine:
             self.styles.append(StyleData(grams))
         for image in content_images:
             self.img = self.to_device(image)
-            feats = self.prepare_features(content_layers, tile_size, passes=10)
+            feats = self.prepare_features(content_layers, tile_size, passes=content_passes)
             self.contents.append(ContentData(feats))
         self.img, self.roll_px = saved_img, saved_roll
 

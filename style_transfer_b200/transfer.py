@@ -125,16 +125,27 @@ class StyleTransfer:
         model.contents = []
         if not getattr(a, 'style_multiscale', None):                 # (:754-755)
             model.styles = []
-        model.preprocess_images(content_images, style_images, self.c_layers, self.s_layers,
-                                a.tile_size)
+        self.jitter = bool(getattr(a, 'jitter', False))
+        if self.jitter:
+            # --jitter (:757-759): only the styles now; the content features are recomputed from the
+            # rolled content image(s) in every iteration
+            self._content_images = [model.to_device(c) for c in content_images]
+            model.preprocess_images([], style_images, [], self.s_layers, a.tile_size)
+        else:
+            model.preprocess_images(content_images, style_images, self.c_layers, self.s_layers,
+                                    a.tile_size)
         model.set_contents_and_styles()
         deepest_content = [l for l in reversed(model.layers()) if l in self.c_layers]
         self.jitter_scale = model.layer_info(deepest_content[0])[0] if deepest_content else 1
+        if self.jitter:
+            self.jitter_scale = 1                                    # (:780-781)
 
     def step(self):
         """One pass of the loop body (:777-806): draw the roll, update, roll back.  Returns
         (averaged iterate, loss) on the device."""
         a, model = self.args, self.model
+        if getattr(self, 'jitter', False):
+            return self._step_jitter()
         js = self.jitter_scale
         img_size = np.array(model.img.shape[-2:])
         xy = np.int32(np.random.uniform(-0.5, 0.5, size=2) * img_size) // js       # (:784)
@@ -147,6 +158,30 @@ class StyleTransfer:
         model.roll(-xy, jitter_scale=js)
         self.optimizer.roll(-xy * js)
         return avg_img, loss
+
+    def _step_jitter(self):
+        """One iteration under ``--jitter`` (:778-797): the roll is drawn at PIXEL granularity
+        (jitter_scale = 1), the content features are recomputed from the content image(s) rolled by
+        it (one pass, no RNG draw), and the objective is evaluated with no feature roll.  The
+        reference rolls the iterate and the optimizer state in place and back; here the objective
+        sees a rolled COPY of the parameters and its gradient is rolled back, which is the same
+        thing for element-wise optimizer updates (the un-rolled frame never moves).  The aux image
+        stays un-rolled against the rolled iterate, as in the reference (:730-733)."""
+        a, model = self.args, self.model
+        img_size = np.array(model.img.shape[-2:])
+        xy = np.int32(np.random.uniform(-0.5, 0.5, size=2) * img_size) // 1        # (:784)
+        sh = (int(xy[1]), int(xy[0]))        # roll2: xy[0] along the width, xy[1] along the height
+        model.contents = []
+        model.preprocess_images([torch.roll(c, sh, dims=(-2, -1)) for c in self._content_images], [],
+                                self.c_layers, [], a.tile_size, content_passes=1)
+        model.set_contents_and_styles()
+        sc_args = (np.zeros(2, dtype=np.int64), self.c_layers, self.s_layers, self.d_layers,
+                   self.layer_weights, self.c_weight, self.s_weight, self.d_weight, a.tile_size)
+
+        def opfunc(params):
+            loss, grad = self.eval_loss_and_grad(torch.roll(params, sh, dims=(-2, -1)), sc_args)
+            return loss, torch.roll(grad, (-sh[0], -sh[1]), dims=(-2, -1))
+        return self.optimizer.update(opfunc)
 
     def transfer(self, iterations, content_images, style_images, callback=None):
         """Performs style transfer at the current scale; returns the averaged raw iterate."""

@@ -512,3 +512,30 @@ def test_style_multiscale_grams_match_oracle():
     ora.preprocess([], [variants], [], layers, 48)
     for l in layers:
         assert maxrel(eng.styles[0].grams[l], ora.styles[0][l]) < 2e-4, l
+
+
+@pytest.mark.skipif(os.environ.get('ST_TEST_JITTER') != '1',
+                    reason='--jitter was added without a GPU at hand (set ST_TEST_JITTER=1)')
+def test_jitter_iterations_match_oracle():
+    """--jitter (style_transfer.py:757-759, 778-797): pixel-granular rolls with the content features
+    recomputed every iteration; L-BFGS, 4 iterations, fp32 mode, same tolerance as the default loop
+    (max |d| <= 0.5 grey levels)."""
+    from style_transfer_b200.transfer import StyleTransfer
+    model = 'vgg16.prototxt'
+    eng, ora = engine_for(model, mean=(103.939, 116.779, 123.68))
+    rs = np.random.RandomState(22)
+    H, W = 64, 80
+    content, style = rand_img(rs, H, W), rand_img(rs, H, W)
+    args = default_args(tile_size=48, optimizer='lbfgs', content_layers=['conv4_2'],
+                        style_layers=['conv3_1'])
+    args.jitter = True
+    ot = OracleTransfer(ora, args)
+    np.random.seed(0)
+    ot.init_first_scale(H, W)
+    want = ot.run(4, [content], [style]).copy()
+    st = StyleTransfer(eng, args)
+    np.random.seed(0)
+    st.init_first_scale(H, W)
+    got = st.transfer(4, [content], [style])
+    err = np.abs(got.cpu().numpy() - want)
+    assert err.max() <= 0.5, float(err.max())

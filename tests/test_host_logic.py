@@ -284,3 +284,58 @@ def test_style_multiscale_variants_follow_reference_loop():
     # div quantises both sides like resize_to_fit (:965-975)
     im = Image.new('RGB', (300, 200))
     assert [v.size for v in style_multiscale_variants(im, 128, 181, div=8)] == [(128, 80), (176, 112)]
+
+
+def test_jitter_copy_formulation_equals_in_place_rolls():
+    """--jitter (style_transfer.py:757-759, 778-797).  The reference rolls the iterate and the
+    optimizer state in place, evaluates, and rolls back; the engine's host loop
+    (StyleTransfer._step_jitter) evaluates a rolled COPY and rolls the gradient back.  Both
+    formulations are run here on the CPU oracle (restated reference semantics vs the engine's
+    formulation built from the same oracle pieces): identical averaged iterates, bit for bit."""
+    from oracle.caffe_net import he_normal_weights, model_layers
+    from oracle import numeric as on
+    from oracle.optimizers import Adam
+    from oracle.tile_operator import OracleModel
+    from oracle.transfer import OracleTransfer, default_args, parse_weights, to_params
+    model = 'vgg16.prototxt'
+    params_w = he_normal_weights(model_layers(model))
+    rs = np.random.RandomState(21)
+    H, W = 24, 32
+    content, style = (to_params(rs.randint(0, 256, (H, W, 3))) for _ in range(2))
+    args = default_args(size=W, min_size=W, tile_size=512, content_layers=['conv2_1'],
+                        style_layers=['conv1_1'], model=model)
+    args.jitter = True
+
+    # (A) the oracle's restatement of the reference loop
+    ora = OracleModel(model, params_w)
+    tr = OracleTransfer(ora, args)
+    np.random.seed(0)
+    tr.init_first_scale(H, W)
+    avg_a = tr.run(3, [content], [style]).copy()
+
+    # (B) the engine's formulation on the same oracle pieces
+    ora = OracleModel(model, params_w)
+    tr = OracleTransfer(ora, args)
+    np.random.seed(0)
+    tr.init_first_scale(H, W)
+    p = ora.img
+    c_layers, c_weight = parse_weights(args.content_layers, args.content_weight)
+    s_layers, s_weight = parse_weights(args.style_layers, 1)
+    ora.contents, ora.styles = [], []
+    ora.preprocess([], [style], [], s_layers, args.tile_size)
+    ora.img = p
+    avg_b = None
+    for _ in range(3):
+        xy = np.int32(np.random.uniform(-0.5, 0.5, size=2) * np.array([H, W])) // 1
+        ora.contents = []
+        ora.preprocess([content], [], c_layers, [], args.tile_size, roll=xy)
+        ora.img = p
+        ora.publish()
+        sc_args = (np.zeros(2, dtype=np.int64), c_layers, s_layers, [], tr.layer_weights, c_weight,
+                   s_weight, {}, args.tile_size)
+
+        def opfunc(x):
+            loss, grad = tr.loss_and_grad(on.roll2_(x.copy(), xy), sc_args)
+            return loss, on.roll2_(grad.copy(), -xy)
+        avg_b, _ = tr.optimizer.update(opfunc)
+    assert np.array_equal(avg_a, avg_b)
