@@ -198,9 +198,9 @@ ST_API int st_get_image_u8(const float* params_dev, int H, int W, const float me
  * source order with float64 coefficients (normalised Lanczos-3 or bilinear, support scaled when
  * shrinking) and float64 accumulation without fused multiply-add.  method: 0 = Lanczos, 1 = bilinear.
  * tmp_dev: scratch of channels*h*out_w floats (unused when out_w == w).  Coefficient tables are built
- * on the host per call.  STATUS: the arithmetic is pinned on the CPU (oracle.numeric.resize == PIL ==
- * the reference's num_utils.resize, bit for bit); the CUDA kernel has not run on a GPU yet, so the
- * command line keeps resizing through PIL unless ST_DEVICE_RESIZE=1. */
+ * on the host per call.  Pinned: oracle.numeric.resize == PIL == the reference's num_utils.resize bit
+ * for bit (CPU), and this kernel == the oracle bit for bit (B200).  The command line keeps resizing
+ * through PIL unless ST_DEVICE_RESIZE=1. */
 ST_API int st_resize_f32(const float* in_dev, int channels, int h, int w, int out_h, int out_w,
                          int method, float* out_dev, float* tmp_dev, st_stream stream);
 /* The coefficient table st_resize_f32 uses for one axis (host only, no device needed): *ksize weights

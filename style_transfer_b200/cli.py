@@ -36,8 +36,8 @@ def resize_to_fit(image, size, div=1, scale_up=False):
 def resize_f32(tensor, hw, method='lanczos'):
     """``num_utils.resize`` (:90-108): per-channel float resampling of a CUDA f32 [C][H][W] tensor.
     Default: through PIL 'F' images on the host, exactly as the reference does (once per scale).
-    ``ST_DEVICE_RESIZE=1`` keeps the data on the device (``st_resize_f32``: the same algorithm, its
-    coefficient tables pinned against PIL on the CPU; opt-in until the kernel has a GPU parity run)."""
+    ``ST_DEVICE_RESIZE=1`` keeps the data on the device (``st_resize_f32``: the same algorithm,
+    bit-identical to PIL on the B200)."""
     import torch
     if os.environ.get('ST_DEVICE_RESIZE') == '1' and tensor.is_cuda:
         return resize_f32_device(tensor, hw, method)
