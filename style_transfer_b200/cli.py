@@ -1,7 +1,7 @@
 """Command-line front end with the reference's surface (style_transfer.py:1076-1167): parse the
 flags, run ``transfer_multiscale`` (:832-909) on the CUDA engine, save the result.
 
-    python style_transfer.py CONTENT -si STYLE [-s 2048 --tile-size 512 --devices 0 1 2 3 ...]
+    python style_transfer.py -ci CONTENT -si STYLE [-s 2048 --tile-size 512 --devices 0 1 2 3 ...]
 
 ``--devices`` with several entries re-launches the script under ``torch.distributed.run`` with one
 rank per listed GPU (the reference fork()s one worker per device, :179-181); every rank holds the
@@ -123,8 +123,12 @@ def transfer_multiscale(st, args, content_images, style_images, initial_image=No
         if model.rank == 0:
             print('\nScale %d, image size %dx%d.\n' % (i + 1, w, h), flush=True)
         style_scaled = []
+        multiscale = getattr(args, 'style_multiscale', None)
         for im in style_images:
-            if args.style_scale >= 32:
+            if multiscale:
+                # --style-multiscale scales the ORIGINAL style image itself (:857-858)
+                style_scaled.append(im)
+            elif args.style_scale >= 32:
                 style_scaled.append(resize_to_fit(im, args.style_scale, args.div, scale_up=True))
             else:
                 style_size = round(size * args.style_scale)
@@ -140,7 +144,6 @@ def transfer_multiscale(st, args, content_images, style_images, initial_image=No
         else:
             init = initial_image.resize((w, h), Image.LANCZOS) if initial_image is not None else None
             st.init_first_scale(h, w, init)
-        multiscale = getattr(args, 'style_multiscale', None)
         if multiscale:
             # every style image becomes the list of its scaled copies; the Grams are computed once,
             # at the first scale, and kept (:754-755: styles are only reset without the flag)
@@ -170,7 +173,9 @@ def relaunch_multi_device(args, argv):
 
 def main(argv=None):
     argv = sys.argv[1:] if argv is None else argv
-    args = config_system.parse_args(argv)
+    import argparse
+    state = argparse.Namespace()                 # the reference's STATE (:48): scale, step, steps, img_size
+    args = config_system.parse_args(argv, state)
     from . import netdesc, weights
     net = netdesc.from_model(args.model)
     if args.list_layers:
@@ -194,10 +199,12 @@ def main(argv=None):
     torch.cuda.set_device(device)
     if world > 1:
         dist.init_process_group('nccl', device_id=torch.device('cuda', device))
-    if args.weights == 'random' or not os.path.exists(args.weights):
-        if args.weights != 'random' and rank == 0:
-            print('weights file %s not found: using random He-normal weights' % args.weights)
+    if args.weights == 'random':
         params = weights.he_normal(net)
+    elif not os.path.exists(args.weights):
+        # the reference fails hard here too (caffe.Net raises on a missing .caffemodel, :370)
+        raise SystemExit('weights file %s not found (pass --weights random for He-normal random '
+                         'weights)' % args.weights)
     elif args.weights.endswith('.npz'):
         params = weights.load_npz(args.weights)
     else:
@@ -210,6 +217,10 @@ def main(argv=None):
     eng = TileEngine(net, params, mean=args.mean, device=device, precision=args.precision,
                      rank=rank, world=world)
     st = StyleTransfer(eng, args, layer_weights)
+    st.state = state
+    if args.display != 'none' and rank == 0:
+        print('note: --display %s is not available in this engine (no web / GUI display); running '
+              'headless' % args.display)
     content = Image.open(args.content_image).convert('RGB')
     styles = [Image.open(p).convert('RGB') for p in args.style_images]
     init = Image.open(args.init_image).convert('RGB') if args.init_image else None

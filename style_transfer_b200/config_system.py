@@ -1,19 +1,40 @@
 """Flag table of the reference (config_system.py:42-119): same names, short forms, types and
 defaults, so command lines written for the reference run unchanged.  Flags of subsystems that are
 out of scope here (web / GUI display, SWT regulariser, Caffe path) are accepted and ignored with a
-note; ``--precision`` is the one addition (fp32 parity mode vs. bf16 tensor-core mode).
+note; ``--precision`` is the one addition (tensor-core modes vs. the fp32 SIMT parity mode).
 
-Precedence as in the reference (:121-136): defaults < ``config.py`` in the working directory <
+Precedence as in the reference (:121-136): defaults < ``config.py`` beside the entry script (the
+reference looks beside its ``config_system.py``, which sits beside ``style_transfer.py``; :14) <
 command line (only values that differ from the default) < ``--config FILE``.  A config file is
-Python source executed with the already-parsed flags visible; every public name it defines that
-matches a flag overrides it.
+Python source executed with ``CONFIG_GLOBALS`` = {detect_devices, math, np} visible (:187-194);
+every name it defines becomes an argument.  A callable value is called with the state object each
+time it is read (``AutocallNamespace``, :151-184), so a config can say
+``step_size = lambda st: 15 if st.scale < 3 else 10``.
 """
 
 import argparse
 from fractions import Fraction
+import math
+import os
 from pathlib import Path
+import re
+import subprocess
 
-CONFIG_PY = Path('config.py')
+import numpy as np
+
+# beside style_transfer.py (the drop-in entry script at the repository root)
+CONFIG_PY = Path(__file__).resolve().parent.parent / 'config.py'
+
+
+def detect_devices():
+    """GPU indices reported by ``nvidia-smi -L``, or [-1] (config_system.py:17-24)."""
+    try:
+        gpu_list = subprocess.run(['nvidia-smi', '-L'], stdout=subprocess.PIPE, check=True,
+                                  universal_newlines=True)
+        gpus = [int(g) for g in re.findall(r'^GPU (\d+)', gpu_list.stdout, re.M)]
+        return gpus if gpus else [-1]
+    except (subprocess.CalledProcessError, FileNotFoundError):
+        return [-1]
 
 
 def ffloat(s):
@@ -70,7 +91,8 @@ def build_parser():
         help='the layers to use for style')
     arg('--dd-layers', nargs='*', metavar='LAYER', default=[], help='the layers to use for Deep Dream')
     arg('--port', '-p', type=int, default=8000, help='ignored (no web interface)')
-    arg('--display', default='none', choices=['browser', 'gui', 'none'], help='only "none" is supported')
+    arg('--display', default='browser', choices=['browser', 'gui', 'none'],
+        help='accepted for compatibility; this engine has no web / GUI display (always "none")')
     arg('--browser', default=None, help='ignored')
     arg('--model', default='vgg19.prototxt', help='the deploy.prototxt of the model to use')
     arg('--weights', default='vgg19.caffemodel',
@@ -89,29 +111,72 @@ def build_parser():
     return p
 
 
-def eval_config(path, visible):
-    """Executes a config file; returns the public names it defines (config_system.py:151-178)."""
-    scope = dict(visible)
-    before = set(scope)
-    exec(compile(Path(path).read_text(), str(path), 'exec'), scope)
-    return {k: v for k, v in scope.items()
-            if not k.startswith('_') and (k not in before or scope[k] is not visible.get(k))}
+class ValuePlaceholder:
+    """What a callable argument evaluates to while the state it asks for does not exist yet
+    (config_system.py:147-148)."""
 
 
-def parse_args(argv=None):
+class AutocallNamespace:
+    """Argument namespace whose callable values are called with ``state_obj`` on every read
+    (config_system.py:151-184)."""
+
+    def __init__(self, state_obj, **kwargs):
+        self.state_obj = state_obj
+        self.ns = argparse.Namespace(**kwargs)
+
+    def __getattr__(self, name):
+        value = getattr(self.ns, name)
+        if callable(value):
+            try:
+                return value(self.state_obj)
+            except AttributeError:
+                return ValuePlaceholder()
+        return value
+
+    def __setattr__(self, name, value):
+        if name in ('state_obj', 'ns'):
+            object.__setattr__(self, name, value)
+            return
+        setattr(self.ns, name, value)
+
+    def __iter__(self):
+        yield from vars(self.ns)
+
+    def __contains__(self, key):
+        return key in self.ns
+
+    def __repr__(self):
+        return 'Autocall' + repr(self.ns)
+
+
+CONFIG_GLOBALS = dict(detect_devices=detect_devices, math=math, np=np)
+
+
+def eval_config(config_file):
+    """Executes a config file with CONFIG_GLOBALS visible; returns the names it defines
+    (config_system.py:190-194)."""
+    config_file = Path(config_file)
+    code = compile(config_file.read_text(), config_file.name, 'exec')
+    locs = {}
+    exec(code, dict(CONFIG_GLOBALS), locs)
+    return locs
+
+
+def parse_args(argv=None, state_obj=None):
     parser = build_parser()
     defaults = vars(parser.parse_args([]))
-    args = dict(defaults)
-    known = set(defaults)
-    if CONFIG_PY.exists():
-        args.update({k: v for k, v in eval_config(CONFIG_PY, args).items() if k in known})
+    config_args = eval_config(CONFIG_PY) if CONFIG_PY.exists() else {}
     sysv = vars(parser.parse_args(argv))
+    config2_args = eval_config(sysv['config']) if sysv['config'] else {}
+    args = dict(defaults)
+    args.update(config_args)
     for k, v in sysv.items():
         if defaults[k] != v:
             args[k] = v
-    if sysv['config']:
-        args.update({k: v for k, v in eval_config(sysv['config'], args).items() if k in known})
-    ns = argparse.Namespace(**args)
+    args.update(config2_args)
+    ns = AutocallNamespace(state_obj, **args)
+    if ns.debug:
+        os.environ['DEBUG'] = '1'
     if not ns.list_layers and (not ns.content_image or not ns.style_images):
         parser.print_help()
         raise SystemExit(1)

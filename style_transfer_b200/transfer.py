@@ -79,6 +79,7 @@ class StyleTransfer:
         if layer_weights:
             self.layer_weights.update(layer_weights)
         self.aux_image = None            # CUDA f32[3,H,W] in pil_to_image format
+        self.state = None                # the reference's STATE namespace (:48, :740-746), if any
         self.current_raw = None
         self.optimizer = None
         self._mean = (C.c_float * 3)(*[float(m) for m in np.ravel(model.mean)])
@@ -185,11 +186,18 @@ class StyleTransfer:
 
     def transfer(self, iterations, content_images, style_images, callback=None):
         """Performs style transfer at the current scale; returns the averaged raw iterate."""
+        st = self.state
+        if st is not None:                       # STATE bookkeeping read by callable config values
+            st.scale = st.scale + 1 if 'scale' in st else 0                  # (:740-743)
+            st.step, st.steps = 0, iterations
+            st.img_size = tuple(self.model.img.shape[1:])
         self.prepare(content_images, style_images)
         old_img = self.model.img.clone()
         stats = torch.zeros(2, dtype=torch.float64, device=old_img.device)
         avg_img = None
         for step in range(1, iterations + 1):
+            if st is not None:
+                st.step = step - 1                                           # (:772)
             avg_img, loss = self.step()
             if callback is not None:
                 update_size, tv_loss = self.iter_stats(avg_img, old_img, stats)

@@ -191,8 +191,9 @@ def test_two_rank_dispatch_over_gloo(tmp_path):
 # ---- flag surface ----------------------------------------------------------------------------------------
 def test_flag_table_matches_reference_defaults(tmp_path, monkeypatch):
     from style_transfer_b200 import config_system
-    monkeypatch.chdir(tmp_path)
+    monkeypatch.setattr(config_system, 'CONFIG_PY', tmp_path / 'config.py')
     a = config_system.parse_args(['-ci', 'c.png', '-si', 's1.png', 's2.png'])
+    assert a.display == 'browser'                     # the reference's default (config_system.py:56)
     assert (a.size, a.min_size, a.tile_size, a.optimizer) == (256, 182, 512, 'adam')
     assert (a.step_size, a.step_decay, a.avg_window) == (15, [0.05, 0.5], 20)
     assert (a.content_weight, a.dd_weight, a.tv_weight, a.tv_power) == (0.05, 0, 5, 2)
@@ -216,15 +217,91 @@ def test_flag_table_matches_reference_defaults(tmp_path, monkeypatch):
 
 
 def test_config_precedence(tmp_path, monkeypatch):
-    """defaults < config.py < argv (values that differ from the default) < --config FILE."""
+    """defaults < config.py beside the entry script < argv (values that differ from the default)
+    < --config FILE (config_system.py:121-136)."""
     from style_transfer_b200 import config_system
-    monkeypatch.chdir(tmp_path)
+    # the default location is beside style_transfer.py, as the reference's is (config_system.py:14)
+    assert config_system.CONFIG_PY == __import__('pathlib').Path(ROOT) / 'config.py'
+    monkeypatch.setattr(config_system, 'CONFIG_PY', tmp_path / 'config.py')
     (tmp_path / 'config.py').write_text('size = 512\ntile_size = 256\ntv_weight = 1\n')
     (tmp_path / 'extra.py').write_text('tv_weight = 7\n')
     a = config_system.parse_args(['-ci', 'c', '-si', 's', '--tile-size', '384'])
     assert (a.size, a.tile_size, a.tv_weight) == (512, 384, 1)
     b = config_system.parse_args(['-ci', 'c', '-si', 's', '--config', str(tmp_path / 'extra.py')])
     assert (b.size, b.tile_size, b.tv_weight) == (512, 256, 7)
+
+
+def test_config_globals_and_callable_values(tmp_path, monkeypatch):
+    """Config files see detect_devices / math / np (config_system.py:187) and may define callables
+    that are evaluated against the STATE object on every read (AutocallNamespace, :151-184).  The
+    reference's own docker/config.py (``devices = detect_devices()``) is the first case."""
+    import argparse
+    from style_transfer_b200 import config_system
+    monkeypatch.setattr(config_system, 'CONFIG_PY', tmp_path / 'config.py')
+    docker_config = ("caffe_path = '/root/caffe'\ndevices = detect_devices()\n"
+                     "display = 'none'\ndiv = 8\n")                     # docker/config.py verbatim
+    ref = '/root/reference/docker/config.py'
+    if os.path.exists(ref):
+        assert open(ref).read() == docker_config
+    (tmp_path / 'config.py').write_text(docker_config)
+    a = config_system.parse_args(['-ci', 'c', '-si', 's'])
+    assert a.div == 8 and a.display == 'none' and a.caffe_path == '/root/caffe'
+    assert isinstance(a.devices, list) and all(isinstance(d, int) for d in a.devices)
+    (tmp_path / 'dyn.py').write_text(
+        'size = int(np.sqrt(512 * 512))\n'
+        'tv_weight = lambda st: 5 if st.scale < 2 else 2 * math.pi\n')
+    state = argparse.Namespace()
+    b = config_system.parse_args(['-ci', 'c', '-si', 's', '--config', str(tmp_path / 'dyn.py')], state)
+    assert b.size == 512
+    assert isinstance(b.tv_weight, config_system.ValuePlaceholder)     # STATE.scale does not exist yet
+    state.scale = 0
+    assert b.tv_weight == 5
+    state.scale = 3
+    assert abs(b.tv_weight - 2 * np.pi) < 1e-12
+    assert 'tv_weight' in b and 'nonsense' not in b
+    assert getattr(b, 'jitter', None) is False and getattr(b, 'not_a_flag', 7) == 7
+
+
+def test_cli_style_multiscale_scales_the_original_style_image(monkeypatch):
+    """--style-multiscale hands the ORIGINAL style image to the variant loop (style_transfer.py:
+    857-858 + :501-524), not the copy resized for the current scale: with -sm 64 256 on a 300x200
+    style image at a 96-px first scale the Grams average the 64..256-px copies of the original."""
+    from types import SimpleNamespace
+    from PIL import Image
+    from style_transfer_b200 import cli
+    rs = np.random.RandomState(3)
+    style = Image.fromarray(rs.randint(0, 256, (200, 300, 3)).astype(np.uint8))
+    content = Image.fromarray(rs.randint(0, 256, (80, 120, 3)).astype(np.uint8))
+    seen = []
+
+    class FakeModel:
+        rank, styles = 0, []
+
+        def pil_to_image(self, im):
+            return im.size                                # (w, h) stands for the array
+
+    class FakeTransfer:
+        model = FakeModel()
+        current_raw, optimizer = None, None
+
+        def init_first_scale(self, h, w, init):
+            pass
+
+        def transfer(self, iters, contents, styles, callback=None):
+            seen.append(styles)
+            return 'out'
+
+    args = SimpleNamespace(size=96, min_size=96, div=1, style_scale=1.0, max_style_size=None,
+                           style_scale_up=False, style_multiscale=[64, 256], iterations=[1])
+    cli.transfer_multiscale(FakeTransfer(), args, [content], [style])
+    assert len(seen) == 1 and len(seen[0]) == 1
+    sizes = [max(wh) for wh in seen[0][0]]
+    assert sizes == [64, 91, 128, 181, 256], sizes        # reference loop: 256 down by sqrt(2) to >= 64
+    # without the flag the style is resized for the scale (96 * style_scale)
+    seen.clear()
+    args.style_multiscale = None
+    cli.transfer_multiscale(FakeTransfer(), args, [content], [style])
+    assert seen[0] == [(96, 64)]
 
 
 def test_oracle_output_step_restates_reference_lines():
