@@ -5,13 +5,14 @@ Follows reference ``optimizers.py``: Adam with iterate averaging :11-61, fixed-s
 not installed anywhere here) from its published behaviour as used at optimizers.py:22-24, 35-42:
 value <- beta*value + (1-beta)*x, optional bias correction by 1 - beta^t.
 
-``set_params`` (cross-scale resampling, optimizers.py:53-61) needs PIL Lanczos resizing and is a
-"next" item; only the same-shape behaviour is restated.
+``set_params`` (cross-scale restart, optimizers.py:53-61 / :134-138) resamples Adam's state with
+``oracle.numeric.resize`` (== the reference's ``num_utils.resize`` == PIL, bit for bit); pinned
+against the reference's own module by tests/golden/set_params.npz.
 """
 
 import numpy as np
 
-from .numeric import EPS, roll2_, sdot
+from .numeric import EPS, resize, roll2_, sdot
 
 
 class Ewma:
@@ -63,6 +64,16 @@ class Adam:
         self.xy += xy
         for ew in (self.g1, self.g2, self.p1):
             roll2_(ew.value, xy)
+
+    def set_params(self, last_iterate):
+        """optimizers.py:53-61: step counter back to 1, state resampled to the new size (g1 / p1
+        Lanczos, g2 bilinear and clamped at 0); the EWMAs' ``beta_accum`` is NOT reset."""
+        self.i = 1
+        self.params = last_iterate
+        hw = self.params.shape[-2:]
+        self.g1.value = resize(self.g1.value, hw)
+        self.g2.value = np.maximum(0, resize(self.g2.value, hw, 'bilinear'))
+        self.p1.value = resize(self.p1.value, hw)
 
 
 class Lbfgs:
@@ -122,3 +133,9 @@ class Lbfgs:
         for s, y in zip(self.sk, self.yk):
             roll2_(s, xy)
             roll2_(y, xy)
+
+    def set_params(self, last_iterate):
+        """optimizers.py:134-138: new parameters, memory cleared."""
+        self.params = last_iterate
+        self.loss, self.grad = None, None
+        self.sk, self.yk, self.syk = [], [], []

@@ -148,6 +148,33 @@ def main():
         out['bilinear_%d' % i] = nu.resize(x, hw, method=Image.BILINEAR)
     out['n_cases'] = np.int32(len(cases))
     np.savez(os.path.join(OUT, 'resize.npz'), **out)
+    # ---- AdamOptimizer.set_params across a scale change (optimizers.py:53-61; its own file) --------
+    rs2 = np.random.RandomState(5150)
+    out = {}
+    shape0, shape1 = (3, 12, 17), (3, 17, 24)
+    tgt0 = rs2.randn(*shape0).astype(np.float32) * 20
+    tgt1 = rs2.randn(*shape1).astype(np.float32) * 20
+    x0 = rs2.randn(*shape0).astype(np.float32) * 50
+    out['target0'], out['target1'], out['x0'] = tgt0, tgt1, x0
+    params = x0.copy()
+    opt = ro.AdamOptimizer(params, step_size=15, bp1=1 - 1 / 20, decay=0.05, power=0.5)
+    for it in range(5):
+        avg, _ = opt.update(opfunc_factory(tgt0, 0.25))
+    out['avg_scale0'] = avg.copy()
+    new_params = nu.resize(avg, shape1[-2:])                  # style_transfer.py:877-881
+    out['params_scale1'] = new_params.copy()
+    opt.set_params(new_params)
+    out['g1_after'], out['g2_after'], out['p1_after'] = (opt.g1.value.copy(), opt.g2.value.copy(),
+                                                         opt.p1.value.copy())
+    out['i_after'] = np.float64(opt.i)
+    out['beta_accum_after'] = np.float64([opt.g1.beta_accum, opt.g2.beta_accum, opt.p1.beta_accum])
+    traj = []
+    for it in range(4):
+        avg, _ = opt.update(opfunc_factory(tgt1, 0.25))
+        traj.append(avg.copy())
+    out['avg_scale1'] = np.stack(traj)
+    out['params_final'] = opt.params.copy()
+    np.savez(os.path.join(OUT, 'set_params.npz'), **out)
     print('wrote', sorted(os.listdir(OUT)))
 
 

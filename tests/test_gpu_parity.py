@@ -302,6 +302,34 @@ def test_lbfgs_against_reference_golden(golden_dir):
     assert len(opt.sk) == int(og['lbfgs_mem'])
 
 
+def test_adam_set_params_against_reference_golden(golden_dir):
+    """AdamOptimizer.set_params across a scale change (optimizers.py:53-61) with the device-side
+    resampling, against the trajectory of the reference's own module (tests/golden/set_params.npz):
+    state arrays after the restart and the four averaged iterates that follow."""
+    from style_transfer_b200.cli import resize_f32_device
+    from style_transfer_b200.optimizers import AdamOptimizer
+    g = np.load(os.path.join(golden_dir, 'set_params.npz'))
+    params = torch.from_numpy(g['x0'].copy()).cuda()
+    t0, t1 = torch.from_numpy(g['target0']).cuda(), torch.from_numpy(g['target1']).cuda()
+    opt = AdamOptimizer(params, step_size=15, bp1=1 - 1 / 20, decay=0.05, power=0.5)
+    for it in range(5):
+        avg, _ = opt.update(_opfunc(t0, (0, 0)))
+    assert maxrel(avg, g['avg_scale0']) < 1e-5
+    new_params = resize_f32_device(avg, tuple(g['target1'].shape[-2:]))
+    assert maxrel(new_params, g['params_scale1']) < 1e-5
+    opt.set_params(new_params, resize=resize_f32_device)
+    assert opt.i == 1
+    assert maxrel(opt.g1.value, g['g1_after']) < 1e-5
+    assert maxrel(opt.g2.value, g['g2_after']) < 1e-5 and float(opt.g2.value.min()) >= 0
+    assert maxrel(opt.p1.value, g['p1_after']) < 1e-5
+    accum = np.float64([opt.g1.beta_accum, opt.g2.beta_accum, opt.p1.beta_accum])
+    assert np.abs(accum - g['beta_accum_after']).max() < 1e-12
+    for it in range(4):
+        avg, _ = opt.update(_opfunc(t1, (0, 0)))
+        assert maxrel(avg, g['avg_scale1'][it]) < 1e-5, it
+    assert maxrel(opt.params, g['params_final']) < 1e-5
+
+
 @pytest.mark.parametrize('optimizer,iters', [('adam', 6), ('lbfgs', 5)])
 def test_n_iterations_match_oracle(optimizer, iters):
     """cfg1-shaped path parity: VGG-16, 1 content + 1 style layer, after N iterations.
@@ -510,15 +538,13 @@ def test_style_multiscale_grams_match_oracle():
         assert maxrel(eng.styles[0].grams[l], ora.styles[0][l]) < 2e-4, l
 
 
-@pytest.mark.skipif(os.environ.get('ST_TEST_JITTER') != '1',
-                    reason='tolerance of the --jitter loop not settled yet: one GPU run so far '
-                           '(set ST_TEST_JITTER=1)')
 def test_jitter_iterations_match_oracle():
     """--jitter (style_transfer.py:757-759, 778-797): pixel-granular rolls with the content features
-    recomputed every iteration; L-BFGS, 4 iterations, fp32 mode.  The one B200 run so far: typical
-    |d| 1e-3 .. 1e-2 grey levels, max 1.25 (the default loop's bound of 0.5 is exceeded by a few
-    pixels: the per-iteration content features add fp32 round-off that L-BFGS amplifies), hence a
-    median / maximum bound until the distribution has been measured properly."""
+    recomputed every iteration; L-BFGS, 4 iterations, fp32 mode, 64x80 image in 48-px tiles.
+    Stated tolerance (grey levels of 0..255): median |d| <= 0.05, 99.9 % of the pixels within 0.5,
+    max |d| <= 2.5 (measured on B200: typical |d| 1e-3 .. 1e-2, max 1.25 -- looser than the 0.5 of the
+    default loop because the per-iteration content features add their own fp32 round-off, which the
+    fixed-step L-BFGS amplifies on a few pixels)."""
     from style_transfer_b200.transfer import StyleTransfer
     model = 'vgg16.prototxt'
     eng, ora = engine_for(model, mean=(103.939, 116.779, 123.68))
@@ -537,4 +563,6 @@ def test_jitter_iterations_match_oracle():
     st.init_first_scale(H, W)
     got = st.transfer(4, [content], [style])
     err = np.abs(got.cpu().numpy() - want)
-    assert float(np.median(err)) <= 0.05 and err.max() <= 2.5, (float(np.median(err)), float(err.max()))
+    q = np.quantile(err, [0.5, 0.999])
+    print('jitter: median %.3g, 99.9%% %.3g, max %.3g' % (q[0], q[1], err.max()))
+    assert q[0] <= 0.05 and q[1] <= 0.5 and err.max() <= 2.5, (q, float(err.max()))

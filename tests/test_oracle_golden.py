@@ -132,3 +132,30 @@ def test_resize_matches_pil_directly():
         for method, pil in (('lanczos', Image.LANCZOS), ('bilinear', Image.BILINEAR)):
             want = np.asarray(Image.fromarray(a).resize((hw[1], hw[0]), pil), dtype=np.float32)
             assert np.array_equal(on.resize(a, hw, method), want), (hw, method)
+
+
+def test_adam_set_params_across_a_scale_change(golden_dir):
+    """``AdamOptimizer.set_params`` (optimizers.py:53-61) pinned against the reference's own module
+    (tests/golden/set_params.npz): five steps at 12x17, the averaged iterate resampled to 17x24 and
+    handed back, state resampled (g1 / p1 Lanczos, g2 bilinear + clamp), i = 1, beta_accum kept, four
+    more steps."""
+    g = np.load(os.path.join(golden_dir, 'set_params.npz'))
+    params = g['x0'].copy()
+    opt = oo.Adam(params, step_size=15, bp1=1 - 1 / 20, decay=0.05, power=0.5)
+    for it in range(5):
+        avg, _ = opt.update(_opfunc(g['target0'], (0, 0)))
+    close(avg, g['avg_scale0'], rtol=1e-5)
+    new_params = on.resize(avg, g['target1'].shape[-2:])
+    close(new_params, g['params_scale1'], rtol=1e-5)
+    opt.set_params(new_params)
+    assert opt.i == float(g['i_after']) == 1
+    close(opt.g1.value, g['g1_after'], rtol=1e-5)
+    close(opt.g2.value, g['g2_after'], rtol=1e-5)
+    close(opt.p1.value, g['p1_after'], rtol=1e-5)
+    assert (opt.g2.value >= 0).all()
+    close(np.float64([opt.g1.beta_accum, opt.g2.beta_accum, opt.p1.beta_accum]),
+          g['beta_accum_after'], rtol=1e-12)
+    for it in range(4):
+        avg, _ = opt.update(_opfunc(g['target1'], (0, 0)))
+        close(avg, g['avg_scale1'][it], rtol=1e-5)
+    close(opt.params, g['params_final'], rtol=1e-5)
