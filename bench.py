@@ -53,7 +53,7 @@ def parse_args():
     p.add_argument('--steps', type=int, default=50)
     p.add_argument('--warmup', type=int, default=5)
     p.add_argument('--impl', default='engine', choices=['engine', 'reference'])
-    p.add_argument('--precision', default='fp16', choices=['bf16', 'fp16', 'fp32'])
+    p.add_argument('--precision', default='fp16', choices=['bf16', 'fp16', 'tc32', 'fp32'])
     p.add_argument('--size', type=int, default=2048)
     p.add_argument('--tile-size', type=int, default=512)
     p.add_argument('--optimizer', default='adam', choices=['adam', 'lbfgs'])
@@ -446,7 +446,7 @@ def run_engine(a):
     dom = 'conv_tc' if breakdown['conv_tc']['ms_per_step'] > 0 else 'conv_edge'
     d = breakdown[dom]
     if d['ms_per_step'] > 0:
-        if a.precision in ('bf16', 'fp16'):
+        if a.precision in ('bf16', 'fp16', 'tc32'):
             peak = peaks.get('bf16_tflops_sustained', 1400.0)
             src = 'MEASURED_PEAKS.json bf16_tflops_sustained' if peaks else 'fallback 1400 (recipe)'
         else:
@@ -456,7 +456,7 @@ def run_engine(a):
         # of one step in the ncu --set full capture summarised in profiles/r01_conv_step_ncu_final.md
         traffic = 290.4e6 if (dom == 'conv_tc' and a.size == 2048 and a.tile_size == 512 and world == 1
                               and a.precision == 'fp16') else None
-        burst = peaks.get('bf16_tflops') if a.precision in ('bf16', 'fp16') else None
+        burst = peaks.get('bf16_tflops') if a.precision in ('bf16', 'fp16', 'tc32') else None
         roofline = {'bound': 'tensor', 'kernel': 'conv_tc2_kernel' if dom == 'conv_tc' else 'conv3x3_kernel',
                     'achieved': ach, 'peak': peak, 'unit': 'TFLOP/s', 'frac': ach / peak,
                     # the same against the burst figure of MEASURED_PEAKS.json (a kernel timed alone)
@@ -512,7 +512,8 @@ def run_engine(a):
             'metric': METRIC, 'value': value, 'unit': 'iterations/s', 'n_gpus': world,
             'steps': a.steps, 'warmup': a.warmup, 'ms_per_step': ms / a.steps,
             'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
-            'dtype': {'bf16': 'bf16', 'fp16': 'f16 forward / bf16 backward', 'fp32': 'f32'}[a.precision], 'data': 'synthetic', 'config': cfg,
+            'dtype': {'bf16': 'bf16', 'fp16': 'f16 forward / bf16 backward', 'fp32': 'f32',
+                      'tc32': 'f32 storage, split f16 hi+lo tensor-core operands, f32 accumulate'}[a.precision], 'data': 'synthetic', 'config': cfg,
             'clocks': clocks, 'e2e': e2e, 'gpu_launches': launches, 'roofline': roofline,
             'roofline_gram': roofline_gram,
             'cpu_baseline': cpu, 'breakdown': breakdown,

@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libstyle_b200.so')
 
-ST_PREC_FP32, ST_PREC_BF16, ST_PREC_FP16 = 0, 1, 2
+ST_PREC_FP32, ST_PREC_BF16, ST_PREC_FP16, ST_PREC_TC32 = 0, 1, 2, 3
 ST_CONV3X3, ST_POOL_MAX, ST_POOL_AVE = 0, 1, 2
 
 

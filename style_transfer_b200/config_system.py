@@ -106,8 +106,9 @@ def build_parser():
         help='roll by whole pixels and recompute the content features from the rolled content '
         'image in every iteration (slower; avoids the feature-grid quantisation of the roll)')
     arg('--debug', action='store_true', help='enable debug messages')
-    arg('--precision', default='fp16', choices=['bf16', 'fp16', 'fp32'],
-        help='bf16 / fp16 (fp16 forward, bf16 backward): tcgen05 tensor cores; fp32: exact SIMT parity mode')
+    arg('--precision', default='fp16', choices=['bf16', 'fp16', 'tc32', 'fp32'],
+        help='bf16 / fp16 (fp16 forward, bf16 backward): tcgen05 tensor cores, 16-bit operands; tc32: '
+        'tensor cores with split fp16 hi+lo operands (fp32-class results); fp32: exact SIMT parity mode')
     return p
 
 

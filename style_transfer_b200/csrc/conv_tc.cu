@@ -553,7 +553,7 @@ int tc_pack_first(TcContext& tc, TcWeights& w, const float* w_host, int cout) {
 }
 
 void tc_free_weights(TcWeights& w) {
-  cudaFree(w.fwd), cudaFree(w.bwd), cudaFree(w.bwd_rows);
+  cudaFree(w.fwd), cudaFree(w.bwd), cudaFree(w.bwd_rows), cudaFree(w.fwd32), cudaFree(w.bwd32);
   delete static_cast<CUtensorMap*>(w.map_fwd);
   delete static_cast<CUtensorMap*>(w.map_bwd);
   w = TcWeights{};

@@ -19,6 +19,11 @@ struct TcWeights {
   __nv_bfloat16* bwd_rows = nullptr;   // first layer only: [48][3*cout], the three x taps of a kernel
                                        // row side by side (conv_pix_tc.cu)
   bool fwd_half = false;
+  // split-operand mode (ST_PREC_TC32, conv_tc2.cu): fp16 [rows][9 * 3K] packs, K segments
+  // [Whi | Whi | Wlo] per tap, weights pre-scaled by the power of two split_scale
+  void* fwd32 = nullptr;
+  void* bwd32 = nullptr;
+  float split_scale = 1.f;
   void* map_fwd = nullptr;     // host copies of the CUtensorMap descriptors (128 B each)
   void* map_bwd = nullptr;
 };
@@ -78,6 +83,13 @@ int conv3x3_tc_pair(TcContext& tc, const TcWeights& w, const void* in, void* out
                     const __nv_bfloat16* inj, const float* inj_scale, cudaStream_t s);
 // channel c of a 32-channel chunk sits at this bit of the chunk's mask word
 inline int relu_bit(int c) { return ((c & 31) >> 1) + 16 * (c & 1); }
+// Split-operand mode (ST_PREC_TC32): fp32 NHWC in / out, fp16 hi + lo operands, three MMAs per product
+// (fp32-class result on the tensor cores).  See conv_tc2.cu.
+int tc_pack_split(TcContext& tc, TcWeights& w, const float* w_oihw_host, int cin, int cout);
+int split_f32(const float* in, void* out_hi_lo, size_t pixels, int c, float scale, cudaStream_t s);
+int conv3x3_tc32(TcContext& tc, const TcWeights& w, const float* in, float* out, int nb, int h,
+                 int wd, int cin, int cout, bool forward, const float* bias, const float* mask_act,
+                 const float* inj, float in_scale, void* split_buf, cudaStream_t s);
 // Forward convolution + the 2x2/2 pooling layer behind it in one kernel.  pool_out [nb][ho][wo][cout]
 // receives the pooled map, pool_mask (bytes, same shape) what pool_bwd_mask needs:
 //   max: bits 0-1 = window position of the first maximum, bit 2 = maximum > 0

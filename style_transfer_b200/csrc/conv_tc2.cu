@@ -39,6 +39,8 @@
 // address); "empty" barriers are signalled in both CTAs by multicast tcgen05.commit.
 #include <cuda.h>
 
+#include <algorithm>
+#include <cmath>
 #include <cstdlib>
 #include <vector>
 
@@ -61,7 +63,13 @@ constexpr int kSmemBudget = 227 * 1024 - 1024 /*alignment slack*/ - kTailBytes;
 
 // kEpiFwdPool = kEpiFwd + the 2x2/2 pooling layer that follows: the pooled map and a one-byte
 // arg-max / ReLU mask per pooled element are produced from the staged output tile
-enum Epilogue { kEpiFwd = 0, kEpiBwd = 1, kEpiAbs = 2, kEpiPix = 3, kEpiFwdPool = 4 };
+// kEpiFwd32 / kEpiBwd32: the split-operand mode (ST_PREC_TC32).  The A operand is an fp16 [hi | lo]
+// pair of channel planes of an fp32 activation, the weights are packed [Whi | Whi | Wlo] per tap, so
+// the K loop accumulates a_hi*w_hi + a_lo*w_hi + a_hi*w_lo in the fp32 accumulator (three MMAs per
+// product, ~22 significant bits per operand); the epilogue works in fp32 and stores fp32 straight
+// from registers (each thread owns 32 consecutive channels of one pixel = one 128-byte line).
+enum Epilogue { kEpiFwd = 0, kEpiBwd = 1, kEpiAbs = 2, kEpiPix = 3, kEpiFwdPool = 4, kEpiFwd32 = 5,
+                kEpiBwd32 = 6 };
 constexpr int kPoolStageBytes = 32 * 128;   // 8 x 4 pooled pixels x 64 channels bf16
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------
@@ -281,6 +289,13 @@ struct Tc2Args {
   int nb, h, w, cin, cout;         // nb tiles of the batch, each [h][w]
   int in_half, out_half;           // operands (A and B) / stored output are fp16 instead of bf16
   int w_batched;                   // the B operand has one matrix per batch tile (style GEMM)
+  int cin_map;                     // channels of the input tensor (0: = cin).  Split mode: 2 * real cin
+  int a_wrap;                      // split mode: A channel block of K block cb is cb - a_wrap once
+                                   // cb >= a_wrap (the third K segment re-reads the hi planes); else 1 << 30
+  float out_scale;                 // split mode: accumulator factor (1 / (weight scale * input scale))
+  const float* mask_f32;           // kEpiBwd32: fp32 activation whose sign is the ReLU mask, may be null
+  const float* inj_f32;            // kEpiBwd32: fp32 injected gradient, may be null
+  float* out_f32;                  // kEpiFwd32 / kEpiBwd32: fp32 NHWC output
   int resb_bytes;                  // RESB: bytes of the resident weight block (multiple of 1024)
   int tiles_x, tiles_y, tiles_n;   // pair tiles per batch tile: 8 columns x 32 rows x BN channels
   FastDiv div_x, div_y, div_n;     // by tiles_x / tiles_y / tiles_n (decode_tile runs once per tile
@@ -355,6 +370,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constan
   // map_aux: the pooled output (kEpiFwdPool) or the injected gradient (kEpiBwd, same geometry as out)
   constexpr bool kPool = EPI == kEpiFwdPool;
   constexpr bool kFwd = EPI == kEpiFwd || EPI == kEpiFwdPool;
+  constexpr bool k32 = EPI == kEpiFwd32 || EPI == kEpiBwd32;
   using Cfg = Cfg2<BN, TAPS, RESB, kPool, EPI == kEpiBwd>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -392,7 +408,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constan
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc_pair(tmem_slot, Cfg::kTmemCols);
-  if constexpr (kFwd) {
+  if constexpr (kFwd || EPI == kEpiFwd32) {
     for (int i = threadIdx.x; i < a.cout; i += kThreads2) bias_s[i] = a.bias[i];
   }
   tc_fence_before();
@@ -410,12 +426,13 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constan
         mbar_wait(&a_empty[stage], phase ^ 1);
         const uint32_t bar = map_to_cta(smem_u32(&a_full[stage]), 0);
         uint8_t* dst = a_base + stage * Cfg::kABytes;
+        const int ca = (cb >= a.a_wrap ? cb - a.a_wrap : cb) * 64;
         if (elect_one()) {
           if (leader) mbar_expect_tx(&a_full[stage], 2 * Cfg::kALoadBytes);
           if constexpr (TAPS == 9)
-            tma_load_4d_pair(&map_in, bar, dst, cb * 64, t.x0 - 1, t.y0 - 1, t.b);
+            tma_load_4d_pair(&map_in, bar, dst, ca, t.x0 - 1, t.y0 - 1, t.b);
           else
-            tma_load_4d_pair(&map_in, bar, dst, cb * 64, t.x0, t.y0, t.b);
+            tma_load_4d_pair(&map_in, bar, dst, ca, t.x0, t.y0, t.b);
         }
         __syncwarp();
         if (++stage == Cfg::kSA) stage = 0, phase ^= 1;
@@ -627,6 +644,63 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constan
           float* dst = a.pix + (size_t)t.b * a.pix_batch + (size_t)py * a.pix_row + px;
 #pragma unroll
           for (int ci = 0; ci < 3; ++ci) dst[(size_t)ci * a.pix_plane] = __uint_as_float(r[ci]);
+        }
+        continue;
+      }
+      if constexpr (k32) {
+        // fp32 epilogue of the split-operand mode: no staging, no TMA store -- this thread's 32
+        // channels of its pixel are one 128-byte line of the NHWC fp32 output
+#pragma unroll 1
+        for (int g = 0; g < BN / 64; ++g) {
+          const int cc = g * 2 + hsel;
+          const size_t eofs = cur.gofs + (size_t)cc * 32;
+          float4 mk[8], ij[8];
+          if constexpr (EPI == kEpiBwd32) {
+            // operands of this chunk first: their DRAM latency overlaps the TMEM read
+            if (valid && a.mask_f32 != nullptr) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) mk[i] = __ldg(reinterpret_cast<const float4*>(a.mask_f32 + eofs) + i);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) mk[i] = make_float4(1.f, 1.f, 1.f, 1.f);
+            }
+            if (valid && a.inj_f32 != nullptr) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) ij[i] = __ldg(reinterpret_cast<const float4*>(a.inj_f32 + eofs) + i);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) ij[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+          }
+          uint32_t r[32];
+          tmem_ld32(taddr + cc * 32, r);
+          if (g == BN / 64 - 1) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(map_to_cta(smem_u32(&t_empty[buf]), 0));
+          }
+          float v[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * a.out_scale;
+          if constexpr (EPI == kEpiFwd32) {
+            const float* bs = bias_s + n_tile * BN + cc * 32;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i] + bs[i], 0.f);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              v[4 * i + 0] = (mk[i].x > 0.f ? v[4 * i + 0] : 0.f) + ij[i].x;
+              v[4 * i + 1] = (mk[i].y > 0.f ? v[4 * i + 1] : 0.f) + ij[i].y;
+              v[4 * i + 2] = (mk[i].z > 0.f ? v[4 * i + 2] : 0.f) + ij[i].z;
+              v[4 * i + 3] = (mk[i].w > 0.f ? v[4 * i + 3] : 0.f) + ij[i].w;
+            }
+          }
+          if (valid) {
+            float4* dst = reinterpret_cast<float4*>(a.out_f32 + eofs);
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+          }
         }
         continue;
       }
@@ -868,14 +942,16 @@ int launch2r(TcContext& tc, const void* in, const void* wk, int wk_rows,
   a.div_x = FastDiv(a.tiles_x), a.div_y = FastDiv(a.tiles_y), a.div_n = FastDiv(a.tiles_n);
   CUtensorMap map_in, map_out, map_w, map_pool;
   {
-    const uint64_t dims[4] = {(uint64_t)a.cin, (uint64_t)a.w, (uint64_t)a.h, (uint64_t)a.nb};
-    const uint64_t strides[3] = {(uint64_t)a.cin * 2, (uint64_t)a.w * a.cin * 2,
-                                 (uint64_t)a.h * a.w * a.cin * 2};
+    const uint64_t cm = (uint64_t)(a.cin_map ? a.cin_map : a.cin);
+    const uint64_t dims[4] = {cm, (uint64_t)a.w, (uint64_t)a.h, (uint64_t)a.nb};
+    const uint64_t strides[3] = {cm * 2, (uint64_t)a.w * cm * 2, (uint64_t)a.h * a.w * cm * 2};
     const uint32_t box[4] = {64, (uint32_t)Cfg::kWinW, (uint32_t)Cfg::kHaloRows, 1};
     int rc = encode_bf16_map(tc, &map_in, 4, in, dims, strides, box, a.in_half != 0);
     if (rc != ST_OK) return rc;
   }
-  if (EPI != kEpiPix) {
+  if (a.a_wrap == 0) a.a_wrap = 1 << 30;
+  constexpr bool k32 = EPI == kEpiFwd32 || EPI == kEpiBwd32;
+  if (EPI != kEpiPix && !k32) {
     const uint64_t dims[4] = {(uint64_t)a.cout, (uint64_t)a.w, (uint64_t)a.h, (uint64_t)a.nb};
     const uint64_t strides[3] = {(uint64_t)a.cout * 2, (uint64_t)a.w * a.cout * 2,
                                  (uint64_t)a.h * a.w * a.cout * 2};
@@ -919,8 +995,9 @@ int launch2r(TcContext& tc, const void* in, const void* wk, int wk_rows,
   const int max_pairs = tc.sm_count / 2;
   const int pairs = tiles < max_pairs ? tiles : max_pairs;
   // algorithmic flops: the pixel epilogue computes 3 of its 16 accumulator columns for real
+  // (split mode: a.cin counts the three K segments; the algorithmic flops are a third of the executed)
   TimerScope ts(s, EPI == kEpiAbs ? kTimeStyleGrad : (EPI == kEpiPix ? kTimeConvSimt : kTimeConvTc),
-                2.0 * TAPS * a.cin * (EPI == kEpiPix ? 3 : a.cout) * a.h * a.w * a.nb);
+                2.0 * TAPS * (k32 ? a.cin / 3 : a.cin) * (EPI == kEpiPix ? 3 : a.cout) * a.h * a.w * a.nb);
   ST_LAUNCH(kern, 2 * pairs, kThreads2, smem_bytes, s, map_in, map_w, map_out, map_pool, a);
   return ST_OK;
 }
@@ -1005,6 +1082,105 @@ int conv_last_bwd_tc_pair(TcContext& tc, const TcWeights& w, const __nv_bfloat16
   a.nb = nb, a.h = h, a.w = wd, a.cin = cz, a.cout = 16;
   a.pix = grad, a.pix_batch = batch_stride, a.pix_plane = plane_stride, a.pix_row = row_stride;
   return launch2<16, 9, kEpiPix>(tc, dz, w.bwd, 16, nullptr, a, s);
+}
+
+// ---- split-operand mode (ST_PREC_TC32) -------------------------------------------------------------
+namespace {
+// fp32 NHWC [pixels][c] -> fp16 [pixels][2c]: channels [0, c) = hi = fp16(x * scale), [c, 2c) = lo =
+// fp16(x * scale - hi).  hi saturates at the largest finite fp16 (lo then carries the rest).
+__global__ void __launch_bounds__(256) split_f32_kernel(const float* __restrict__ in,
+                                                        __half* __restrict__ out, size_t groups,
+                                                        int c8, float scale) {
+  // one thread per 8 channels of one pixel
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < groups; i += stride) {
+    const size_t px = i / c8;
+    const int cg = (int)(i - px * c8);
+    const float4 x0 = __ldg(reinterpret_cast<const float4*>(in + i * 8));
+    const float4 x1 = __ldg(reinterpret_cast<const float4*>(in + i * 8) + 1);
+    const float x[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float a0 = x[2 * j] * scale, a1 = x[2 * j + 1] * scale;
+      const __half2 h = __floats2half2_rn(fminf(fmaxf(a0, -65504.f), 65504.f),
+                                          fminf(fmaxf(a1, -65504.f), 65504.f));
+      const float2 hf = __half22float2(h);
+      const __half2 l = __floats2half2_rn(fminf(fmaxf(a0 - hf.x, -65504.f), 65504.f),
+                                          fminf(fmaxf(a1 - hf.y, -65504.f), 65504.f));
+      hi[j] = *reinterpret_cast<const uint32_t*>(&h);
+      lo[j] = *reinterpret_cast<const uint32_t*>(&l);
+    }
+    __half* o = out + px * (size_t)(c8 * 16) + (size_t)cg * 8;
+    *reinterpret_cast<uint4*>(o) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(o + c8 * 8) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  }
+}
+}  // namespace
+
+int split_f32(const float* in, void* out, size_t pixels, int c, float scale, cudaStream_t s) {
+  ST_REQUIRE(c % 8 == 0, "split_f32: channels must be a multiple of 8");
+  const size_t groups = pixels * (size_t)(c / 8);
+  const int blocks = (int)std::min<size_t>((groups + 255) / 256, (size_t)148 * 16);
+  TimerScope ts(s, kTimeConvSimt, 0.0);
+  ST_LAUNCH(split_f32_kernel, blocks, 256, 0, s, in, static_cast<__half*>(out), groups, c / 8, scale);
+  return ST_OK;
+}
+
+// fp16 split packs of one conv layer for both directions: rows [cout][9 * 3cin] with, per tap, the
+// K segments [Whi | Whi | Wlo] (matching the A channel order hi, lo, hi of the kernel's wrap), weights
+// pre-multiplied by the power of two *scale that brings max|w| to ~2^13 (keeps Wlo out of the fp16
+// subnormals).  backward: taps flipped, in/out channels exchanged.
+int tc_pack_split(TcContext& tc, TcWeights& w, const float* w_host, int cin, int cout) {
+  if (!tc.enabled) return ST_OK;
+  float wmax = 0.f;
+  for (size_t i = 0; i < (size_t)cout * cin * 9; ++i) wmax = std::max(wmax, std::fabs(w_host[i]));
+  int e = 0;
+  if (wmax > 0.f) {
+    std::frexp(wmax, &e);                  // wmax = m * 2^e, m in [0.5, 1)
+    e = 13 - e;
+  }
+  const float scale = std::ldexp(1.f, e);
+  w.split_scale = scale;
+  for (int dir = 0; dir < 2; ++dir) {
+    const int rows = dir == 0 ? cout : cin, kc = dir == 0 ? cin : cout;   // output rows, K channels
+    std::vector<__half> host((size_t)rows * 9 * 3 * kc);
+    for (int r = 0; r < rows; ++r)
+      for (int t = 0; t < 9; ++t)
+        for (int k = 0; k < kc; ++k) {
+          const int co = dir == 0 ? r : k, ci = dir == 0 ? k : r;
+          const int ts = dir == 0 ? t : 8 - t;                 // flipped tap for the transposed conv
+          const float v = w_host[((size_t)co * cin + ci) * 9 + ts] * scale;
+          const __half hi = __float2half_rn(v);
+          const __half lo = __float2half_rn(v - __half2float(hi));
+          __half* row = host.data() + ((size_t)r * 9 + t) * 3 * kc;
+          row[k] = hi, row[kc + k] = hi, row[2 * kc + k] = lo;
+        }
+    void** dst = dir == 0 ? &w.fwd32 : &w.bwd32;
+    if (!*dst) ST_CUDA(cudaMalloc(dst, host.size() * sizeof(__half)));
+    ST_CUDA(cudaMemcpy(*dst, host.data(), host.size() * sizeof(__half), cudaMemcpyHostToDevice));
+  }
+  return ST_OK;
+}
+
+// out = epilogue(conv3x3(in)) on fp32 NHWC tensors through the split-operand tensor-core kernel:
+//   forward : out = max(acc + bias, 0)
+//   backward: out = (mask_act > 0 ? acc : 0) + inj          (mask_act / inj fp32, may be null)
+// `split_buf` (2 * nb*h*w*cin fp16 elements) receives the [hi | lo] copy of `in * in_scale`.
+int conv3x3_tc32(TcContext& tc, const TcWeights& w, const float* in, float* out, int nb, int h,
+                 int wd, int cin, int cout, bool forward, const float* bias, const float* mask_act,
+                 const float* inj, float in_scale, void* split_buf, cudaStream_t s) {
+  int rc = split_f32(in, split_buf, (size_t)nb * h * wd, cin, in_scale, s);
+  if (rc != ST_OK) return rc;
+  Tc2Args a{};
+  a.nb = nb, a.h = h, a.w = wd, a.cin = 3 * cin, a.cout = cout;
+  a.cin_map = 2 * cin, a.a_wrap = 2 * (cin / 64);
+  a.in_half = 1, a.out_half = 0;
+  a.out_scale = 1.f / (w.split_scale * in_scale);
+  a.bias = bias, a.mask_f32 = mask_act, a.inj_f32 = inj, a.out_f32 = out;
+  const int bn = choose_bn(tc, nb, h, wd, cout);
+  if (forward) return dispatch_bn<9, kEpiFwd32>(tc, bn, split_buf, w.fwd32, cout, nullptr, a, s);
+  return dispatch_bn<9, kEpiBwd32>(tc, bn, split_buf, w.bwd32, cout, nullptr, a, s);
 }
 
 // Per batch tile b: S_b[p][n] = sum_c F_b[p][c] * D_b[n][c]  (D_b symmetric bf16 [c][c]).  The sum

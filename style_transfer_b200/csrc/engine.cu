@@ -1,6 +1,7 @@
 // libstyle_b200 engine: context, per-tile forward/backward plan and the extern "C" entry points
 // declared in include/style_b200.h.  See DESIGN.md for the data layout and the kernel list.
 #include <algorithm>
+#include <cmath>
 #include <cstring>
 #include <map>
 #include <vector>
@@ -104,6 +105,9 @@ struct st_ctx {
   void* gbuf[2] = {nullptr, nullptr};
   void* sbuf = nullptr;
   size_t gcap = 0;           // elements of gbuf[i] / sbuf
+  void* split_buf = nullptr; // ST_PREC_TC32: fp16 [hi | lo] copy of the convolution input in flight
+  size_t split_cap = 0;      // elements (4 bytes each)
+  float grad_scale = 1.f;    // ST_PREC_TC32: power of two applied to gradients before the fp16 split
   // per batch tile: Gram [C][C], its difference to the target (fp32 and the bf16 copy that is the
   // B operand of the tcgen05 style GEMM)
   float *gram = nullptr, *delta = nullptr, *part = nullptr;
@@ -206,6 +210,10 @@ int reserve_for(st_ctx* ctx, const Dims& d, int last_layer, int nb) {
     if (rc != ST_OK) return rc;
     ctx->gcap = gmax;
   }
+  if (ctx->precision == ST_PREC_TC32) {
+    int rc = ensure(ctx, &ctx->split_buf, &ctx->split_cap, std::max(gmax, ctx->gcap), 4);
+    if (rc != ST_OK) return rc;
+  }
   return ST_OK;
 }
 
@@ -292,6 +300,13 @@ int forward(st_ctx* ctx, const ImageBatch& view, const Dims& d, int last_layer,
           if constexpr (std::is_same<T, __half>::value) {
             set_error("invalid: ST_PREC_FP16 has no SIMT convolution (channels must be multiples of 64)");
             rc = ST_ERR_INVALID;
+          } else if constexpr (std::is_same<T, float>::value) {
+            if (ctx->precision == ST_PREC_TC32 && l.tc.fwd32 != nullptr)
+              rc = conv3x3_tc32(ctx->tc, l.tc, in, out, nb, hb, wb, l.cin, l.cout, true, l.bias,
+                                nullptr, nullptr, 1.f, ctx->split_buf, s);
+            else
+              rc = conv3x3_simt<T>(in, l.w_fwd, l.bias, out, nb, hb, wb, l.cin, l.cout, true, nullptr,
+                                   nullptr, s);
           } else {
             rc = conv3x3_simt<T>(in, l.w_fwd, l.bias, out, nb, hb, wb, l.cin, l.cout, true, nullptr,
                                  nullptr, s);
@@ -496,7 +511,14 @@ int backward(st_ctx* ctx, const Dims& d, int nb, int deepest_blob, const std::ve
         }
       } else {
         ST_REQUIRE(inj_scale == nullptr, "deferred injection scale needs the tensor-core convolution");
-        if constexpr (std::is_same<TA, T>::value) {
+        if constexpr (std::is_same<T, float>::value && std::is_same<TA, float>::value) {
+          if (ctx->precision == ST_PREC_TC32 && l.tc.bwd32 != nullptr)
+            rc = conv3x3_tc32(ctx->tc, l.tc, g, out, nb, hb, wb, l.cout, l.cin, false, nullptr, mask,
+                              inj, ctx->grad_scale, ctx->split_buf, s);
+          else
+            rc = conv3x3_simt<T>(g, l.w_bwd, nullptr, out, nb, hb, wb, l.cout, l.cin, false, mask, inj,
+                                 s);
+        } else if constexpr (std::is_same<TA, T>::value) {
           rc = conv3x3_simt<T>(g, l.w_bwd, nullptr, out, nb, hb, wb, l.cout, l.cin, false, mask, inj,
                                s);
         } else {
@@ -542,6 +564,20 @@ int eval_batch(st_ctx* ctx, const ImageBatch& view, int h, int w, const BatchGeo
     for (int i = 0; i < n_specs; ++i)
       ST_REQUIRE(on_chain[specs[i].blob], "loss blob is not an ancestor of the deepest loss blob");
   }
+  if (ctx->precision == ST_PREC_TC32) {
+    // Every injected term is L1-normalised to mean |.| = its weight (num_utils.normalize), so the
+    // gradient magnitude is known up front: scale it by the power of two that puts the largest
+    // weight at ~2^5 before the fp16 hi/lo split (2^11 of headroom above the mean, lo stays normal)
+    float wmax = 0.f;
+    for (int i = 0; i < n_specs; ++i) {
+      if (specs[i].use_content) wmax = std::max(wmax, std::fabs(specs[i].content_weight) * std::max(ctx->n_contents, 1));
+      if (specs[i].use_style) wmax = std::max(wmax, std::fabs(specs[i].style_weight));
+      if (specs[i].use_dd) wmax = std::max(wmax, std::fabs(specs[i].dd_weight));
+    }
+    int e = 0;
+    if (wmax > 0.f) std::frexp(wmax, &e);
+    ctx->grad_scale = std::ldexp(1.f, std::min(std::max(5 - e, -60), 60));
+  }
   const int last_layer = ctx->blobs[deepest].producer;
   const Dims d = blob_dims(ctx, h, w);
   int rc = reserve_for(ctx, d, last_layer, g.nb);
@@ -558,7 +594,7 @@ int eval_batch_any(st_ctx* ctx, const ImageBatch& view, int h, int w, const Batc
                    int froll_y, int froll_x, int n_specs, const st_loss_spec* specs,
                    double* loss_accum, float* grad, long batch_stride, long plane, long rstride,
                    cudaStream_t s) {
-  if (ctx->precision == ST_PREC_FP32)
+  if (ctx->precision == ST_PREC_FP32 || ctx->precision == ST_PREC_TC32)
     return eval_batch<float, float>(ctx, view, h, w, g, froll_y, froll_x, n_specs, specs, loss_accum,
                                     grad, batch_stride, plane, rstride, s);
   if (ctx->precision == ST_PREC_FP16)
@@ -623,7 +659,8 @@ uint64_t st_launch_count(void) { return g_launches.load(); }
 
 int st_create(int device, int precision, int n_layers, const st_layer_desc* layers, st_ctx** out) {
   ST_REQUIRE(out != nullptr && layers != nullptr && n_layers > 0, "st_create: bad arguments");
-  ST_REQUIRE(precision == ST_PREC_FP32 || precision == ST_PREC_BF16 || precision == ST_PREC_FP16,
+  ST_REQUIRE(precision == ST_PREC_FP32 || precision == ST_PREC_BF16 || precision == ST_PREC_FP16 ||
+                 precision == ST_PREC_TC32,
              "unknown precision");
   int ndev = 0;
   ST_CUDA(cudaGetDeviceCount(&ndev));
@@ -633,7 +670,7 @@ int st_create(int device, int precision, int n_layers, const st_layer_desc* laye
   ST_REQUIRE(prop.major == 10, "libstyle_b200 is built for sm_100a (B200) only");
   st_ctx* ctx = new st_ctx();
   ctx->device = device, ctx->precision = precision, ctx->sm_count = prop.multiProcessorCount;
-  ctx->esize = precision == ST_PREC_FP32 ? 4 : 2;
+  ctx->esize = (precision == ST_PREC_FP32 || precision == ST_PREC_TC32) ? 4 : 2;
   DeviceGuard guard(device);
   ctx->blobs.resize(n_layers + 1);
   ctx->blobs[0].c = 3;
@@ -658,13 +695,15 @@ int st_create(int device, int precision, int n_layers, const st_layer_desc* laye
   }
   int rc = ST_OK;
   if (precision != ST_PREC_FP32) rc = tc_init(ctx->tc, ctx->sm_count);
-  if (rc == ST_OK && precision == ST_PREC_FP16 && !(ctx->tc.enabled && ctx->tc.pair_kernel)) {
-    set_error("invalid: ST_PREC_FP16 needs the tensor-core kernels (unset ST_DISABLE_TC / ST_CONV_V1)");
+  if (rc == ST_OK && (precision == ST_PREC_FP16 || precision == ST_PREC_TC32) &&
+      !(ctx->tc.enabled && ctx->tc.pair_kernel)) {
+    set_error("invalid: ST_PREC_FP16 / ST_PREC_TC32 need the tensor-core kernels (unset ST_DISABLE_TC / ST_CONV_V1)");
     rc = ST_ERR_INVALID;
   }
   // tiles of one shape are evaluated as a batch by the tensor-core kernels; the fp32 SIMT parity
   // path keeps the reference's one-tile-at-a-time order
-  ctx->max_batch = (precision != ST_PREC_FP32 && ctx->tc.enabled && ctx->tc.pair_kernel) ? kMaxBatch : 1;
+  ctx->max_batch = (precision != ST_PREC_FP32 && precision != ST_PREC_TC32 && ctx->tc.enabled &&
+                    ctx->tc.pair_kernel) ? kMaxBatch : 1;
   if (const char* e = getenv("ST_MAX_BATCH")) {
     const int v = atoi(e);
     if (v >= 1 && v < ctx->max_batch) ctx->max_batch = v;
@@ -672,7 +711,7 @@ int st_create(int device, int precision, int n_layers, const st_layer_desc* laye
   const size_t gram_floats = (size_t)ctx->max_batch * 512 * 512;
   if (rc == ST_OK) rc = dev_alloc(ctx, (void**)&ctx->gram, gram_floats * sizeof(float));
   if (rc == ST_OK) rc = dev_alloc(ctx, (void**)&ctx->delta, gram_floats * sizeof(float));
-  if (rc == ST_OK && precision != ST_PREC_FP32) {
+  if (rc == ST_OK && precision != ST_PREC_FP32 && precision != ST_PREC_TC32) {
     rc = dev_alloc(ctx, (void**)&ctx->delta_16, gram_floats * 2);
     if (rc == ST_OK) rc = dev_alloc(ctx, (void**)&ctx->eps_eff, kMaxBatch * sizeof(float));
     if (rc == ST_OK) rc = dev_alloc(ctx, (void**)&ctx->delta_max, kMaxBatch * sizeof(unsigned));
@@ -705,7 +744,7 @@ int st_destroy(st_ctx* ctx) {
     tc_free_weights(l.tc);
   }
   for (BlobRt& b : ctx->blobs) cudaFree(b.act), cudaFree(b.inj), cudaFree(b.inj_scale), cudaFree(b.bits);
-  cudaFree(ctx->gbuf[0]), cudaFree(ctx->gbuf[1]), cudaFree(ctx->sbuf);
+  cudaFree(ctx->gbuf[0]), cudaFree(ctx->gbuf[1]), cudaFree(ctx->sbuf), cudaFree(ctx->split_buf);
   cudaFree(ctx->gram), cudaFree(ctx->delta), cudaFree(ctx->part), cudaFree(ctx->scalars);
   cudaFree(ctx->delta_16), cudaFree(ctx->abs_partials), cudaFree(ctx->eps_eff);
   cudaFree(ctx->delta_max);
@@ -748,7 +787,12 @@ int st_set_conv_params(st_ctx* ctx, int layer, const float* w, const float* b) {
   ST_CUDA(cudaMemcpy(l.w_fwd, fwd.data(), fwd.size() * sizeof(float), cudaMemcpyHostToDevice));
   ST_CUDA(cudaMemcpy(l.w_bwd, bwd.data(), bwd.size() * sizeof(float), cudaMemcpyHostToDevice));
   ST_CUDA(cudaMemcpy(l.bias, b, co_n * sizeof(float), cudaMemcpyHostToDevice));
-  if (ctx->precision != ST_PREC_FP32) {
+  if (ctx->precision == ST_PREC_TC32) {
+    if (!first) {
+      int rc = tc_pack_split(ctx->tc, l.tc, w, ci_n, co_n);
+      if (rc != ST_OK) return rc;
+    }
+  } else if (ctx->precision != ST_PREC_FP32) {
     const bool half = ctx->precision == ST_PREC_FP16;
     int rc = first ? tc_pack_first(ctx->tc, l.tc, w, co_n)
                    : tc_pack_weights(ctx->tc, l.tc, w, ci_n, co_n, half);
@@ -846,7 +890,8 @@ int st_eval_features_tile(st_ctx* ctx, const float* img_dev, int h, int w, int n
   cudaStream_t s = (cudaStream_t)stream;
   std::vector<char> need_full(ctx->blobs.size(), 0);
   for (int i = 0; i < n_blobs; ++i) need_full[blob_ids[i]] = 1;
-  rc = ctx->precision == ST_PREC_FP32
+  const bool f32 = ctx->precision == ST_PREC_FP32 || ctx->precision == ST_PREC_TC32;
+  rc = f32
            ? forward<float>(ctx, view, d, last_layer, need_full, false, s)
            : (ctx->precision == ST_PREC_FP16
                   ? forward<__half>(ctx, view, d, last_layer, need_full, false, s)
@@ -854,7 +899,7 @@ int st_eval_features_tile(st_ctx* ctx, const float* img_dev, int h, int w, int n
   for (int i = 0; i < n_blobs && rc == ST_OK; ++i) {
     const int b = blob_ids[i];
     const int hw = d.h[b] * d.w[b];
-    if (ctx->precision == ST_PREC_FP32)
+    if (f32)
       rc = nhwc_to_nchw_f32<float>((const float*)ctx->blobs[b].act, out_dev[i], hw, ctx->blobs[b].c, s);
     else if (ctx->precision == ST_PREC_FP16)
       rc = nhwc_to_nchw_f32<__half>((const __half*)ctx->blobs[b].act, out_dev[i], hw, ctx->blobs[b].c,

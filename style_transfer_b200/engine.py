@@ -23,7 +23,8 @@ import torch
 from . import _lib, sharding
 from .netdesc import NetDesc
 
-PRECISIONS = {'fp32': _lib.ST_PREC_FP32, 'bf16': _lib.ST_PREC_BF16, 'fp16': _lib.ST_PREC_FP16}
+PRECISIONS = {'fp32': _lib.ST_PREC_FP32, 'bf16': _lib.ST_PREC_BF16, 'fp16': _lib.ST_PREC_FP16,
+              'tc32': _lib.ST_PREC_TC32}
 
 
 def _ptr(t):
