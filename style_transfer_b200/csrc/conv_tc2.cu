@@ -384,9 +384,14 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constan
   uint64_t* a_empty = a_full + Cfg::kSA;
   uint64_t* b_full = a_empty + Cfg::kSA;
   uint64_t* b_empty = b_full + Cfg::kSB;
+  // accumulator buffers in TMEM: two (one tile each); the split-operand mode cycles four, one per
+  // accumulation CHAIN (see the k32 epilogue)
+  constexpr int kNT = k32 ? 4 : 2;
+  constexpr int kTmemCols = k32 ? (4 * BN < 32 ? 32 : 4 * BN) : Cfg::kTmemCols;
+  static_assert(!k32 || (BN <= 128 && !RESB && Cfg::kTB == 3), "split-operand mode: BN <= 128, staged weights");
   uint64_t* t_full = b_empty + Cfg::kSB;
-  uint64_t* t_empty = t_full + 2;
-  uint64_t* e_full = t_empty + 2;          // injected-gradient ring (backward epilogue)
+  uint64_t* t_empty = t_full + kNT;
+  uint64_t* e_full = t_empty + kNT;        // injected-gradient ring (backward epilogue)
   uint64_t* e_empty = e_full + kSE;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(e_empty + kSE);
   uint8_t* inj_base = out_base + 2 * kOutStageBytes;     // kEpiBwd only (no pooling stages there)
@@ -403,11 +408,11 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constan
     prefetch_tmap(&map_in), prefetch_tmap(&map_w), prefetch_tmap(&map_out);
     for (int i = 0; i < Cfg::kSA; ++i) mbar_init(&a_full[i], 1), mbar_init(&a_empty[i], 1);
     for (int i = 0; i < Cfg::kSB; ++i) mbar_init(&b_full[i], 1), mbar_init(&b_empty[i], 1);
-    for (int i = 0; i < 2; ++i) mbar_init(&t_full[i], 1), mbar_init(&t_empty[i], 16);
+    for (int i = 0; i < kNT; ++i) mbar_init(&t_full[i], 1), mbar_init(&t_empty[i], 16);
     for (int i = 0; i < kSE; ++i) mbar_init(&e_full[i], 1), mbar_init(&e_empty[i], 8);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc_pair(tmem_slot, Cfg::kTmemCols);
+  if (warp == 1) tmem_alloc_pair(tmem_slot, kTmemCols);
   if constexpr (kFwd || EPI == kEpiFwd32) {
     for (int i = threadIdx.x; i < a.cout; i += kThreads2) bias_s[i] = a.bias[i];
   }
@@ -483,11 +488,13 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constan
       const uint32_t fmt = a.in_half ? 0u : 1u;
       const uint32_t idesc = Cfg::kIdescBase | (fmt << 7) | (fmt << 10);
       if constexpr (RESB) mbar_wait(&b_full[0], 0);      // the resident weights have landed
-      for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
-        const uint32_t buf = it & 1, use = it >> 1;
-        mbar_wait(&t_empty[buf], (use & 1) ^ 1);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + buf * BN;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs, it += k32 ? 0 : 1) {
+        uint32_t buf = it & 1, use = it >> 1;
+        uint32_t d_tmem = tmem_base + buf * BN;
+        if constexpr (!k32) {
+          mbar_wait(&t_empty[buf], (use & 1) ^ 1);
+          tc_fence_after();
+        }
         for (int cb = 0; cb < kb_per_tap; ++cb) {
           mbar_wait(&a_full[sa], pa);
           tc_fence_after();
@@ -517,6 +524,17 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constan
           } else {
 #pragma unroll
             for (int tg = 0; tg < TAPS; tg += Cfg::kTB) {
+              if constexpr (k32) {
+                // split-operand mode: every weight stage (one kernel row: 12 MMAs) is its own
+                // accumulation CHAIN into a fresh TMEM buffer; the epilogue warps add the chains up
+                // in fp32 registers.  The tensor core truncates when it accumulates (measured: a
+                // relative bias of ~2^-25 per MMA step, i.e. 1e-4 after the 3240 steps to conv4_2),
+                // so the length of a chain, not K, sets the bias.
+                buf = it & 3, use = it >> 2;
+                d_tmem = tmem_base + buf * BN;
+                mbar_wait(&t_empty[buf], (use & 1) ^ 1);
+                tc_fence_after();
+              }
               mbar_wait(&b_full[sb], pb);
               tc_fence_after();
               const uint64_t db0 = make_smem_desc(smem_u32(b_base + sb * Cfg::kBStage));
@@ -530,15 +548,20 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constan
 #pragma unroll
                   for (int k = 0; k < 4; ++k)
                     tc_mma_pair(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc,
-                                (tap | k) != 0 ? 1u : (uint32_t)(cb != 0));
+                                k32 ? (uint32_t)((j | k) != 0)
+                                    : ((tap | k) != 0 ? 1u : (uint32_t)(cb != 0)));
                 }
                 tc_commit_pair(&b_empty[sb]);
+                if constexpr (k32) tc_commit_pair(&t_full[buf]);
                 if (tg + Cfg::kTB >= TAPS) {
                   tc_commit_pair(&a_empty[sa]);
-                  if (last_cb) tc_commit_pair(&t_full[buf]);
+                  if constexpr (!k32) {
+                    if (last_cb) tc_commit_pair(&t_full[buf]);
+                  }
                 }
               }
               __syncwarp();
+              if constexpr (k32) ++it;
               if (++sb == Cfg::kSB) sb = 0, pb ^= 1;
             }
           }
@@ -629,8 +652,10 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constan
         if (a.inj_scale != nullptr) inj_sc = __ldg(a.inj_scale + t.b);
       }
 
-      mbar_wait(&t_full[buf], use & 1);
-      tc_fence_after();
+      if constexpr (!k32) {
+        mbar_wait(&t_full[buf], use & 1);
+        tc_fence_after();
+      }
       const uint32_t taddr = tmem_base + buf * BN + ((uint32_t)(q * 32) << 16);
       if constexpr (EPI == kEpiPix) {
         // backward of the first convolution: accumulator columns 0..2 are d(loss)/d(pixel) of the
@@ -648,51 +673,63 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constan
         continue;
       }
       if constexpr (k32) {
-        // fp32 epilogue of the split-operand mode: no staging, no TMA store -- this thread's 32
-        // channels of its pixel are one 128-byte line of the NHWC fp32 output
+        // fp32 epilogue of the split-operand mode.  The MMA warp delivers one accumulation chain
+        // per weight stage (3 chains per 64-channel K block); they are added here in fp32 with
+        // round-to-nearest.  No staging, no TMA store: this thread's 32 channels of its pixel are one
+        // 128-byte line of the NHWC fp32 output.
+        constexpr int kG = BN / 64;
+        float acc[kG][32];
+#pragma unroll
+        for (int g = 0; g < kG; ++g)
+#pragma unroll
+          for (int i = 0; i < 32; ++i) acc[g][i] = 0.f;
+        const int nchains = kb_per_tap * (TAPS / Cfg::kTB);
 #pragma unroll 1
-        for (int g = 0; g < BN / 64; ++g) {
+        for (int ch = 0; ch < nchains; ++ch, ++it) {
+          const uint32_t cbuf = it & 3, cuse = it >> 2;
+          mbar_wait(&t_full[cbuf], cuse & 1);
+          tc_fence_after();
+          const uint32_t caddr = tmem_base + cbuf * BN + ((uint32_t)(q * 32) << 16);
+#pragma unroll
+          for (int g = 0; g < kG; ++g) {
+            uint32_t r[32];
+            tmem_ld32(caddr + (g * 2 + hsel) * 32, r);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) acc[g][i] += __uint_as_float(r[i]);
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(map_to_cta(smem_u32(&t_empty[cbuf]), 0));
+        }
+        --it;                                  // the tile loop adds one
+#pragma unroll
+        for (int g = 0; g < kG; ++g) {
           const int cc = g * 2 + hsel;
           const size_t eofs = cur.gofs + (size_t)cc * 32;
-          float4 mk[8], ij[8];
-          if constexpr (EPI == kEpiBwd32) {
-            // operands of this chunk first: their DRAM latency overlaps the TMEM read
-            if (valid && a.mask_f32 != nullptr) {
+          float* v = acc[g];
 #pragma unroll
-              for (int i = 0; i < 8; ++i) mk[i] = __ldg(reinterpret_cast<const float4*>(a.mask_f32 + eofs) + i);
-            } else {
-#pragma unroll
-              for (int i = 0; i < 8; ++i) mk[i] = make_float4(1.f, 1.f, 1.f, 1.f);
-            }
-            if (valid && a.inj_f32 != nullptr) {
-#pragma unroll
-              for (int i = 0; i < 8; ++i) ij[i] = __ldg(reinterpret_cast<const float4*>(a.inj_f32 + eofs) + i);
-            } else {
-#pragma unroll
-              for (int i = 0; i < 8; ++i) ij[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-          }
-          uint32_t r[32];
-          tmem_ld32(taddr + cc * 32, r);
-          if (g == BN / 64 - 1) {
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(map_to_cta(smem_u32(&t_empty[buf]), 0));
-          }
-          float v[32];
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * a.out_scale;
+          for (int i = 0; i < 32; ++i) v[i] *= a.out_scale;
           if constexpr (EPI == kEpiFwd32) {
             const float* bs = bias_s + n_tile * BN + cc * 32;
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i] + bs[i], 0.f);
-          } else {
+          } else if (valid) {
+            if (a.mask_f32 != nullptr) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              v[4 * i + 0] = (mk[i].x > 0.f ? v[4 * i + 0] : 0.f) + ij[i].x;
-              v[4 * i + 1] = (mk[i].y > 0.f ? v[4 * i + 1] : 0.f) + ij[i].y;
-              v[4 * i + 2] = (mk[i].z > 0.f ? v[4 * i + 2] : 0.f) + ij[i].z;
-              v[4 * i + 3] = (mk[i].w > 0.f ? v[4 * i + 3] : 0.f) + ij[i].w;
+              for (int i = 0; i < 8; ++i) {
+                const float4 mk = __ldg(reinterpret_cast<const float4*>(a.mask_f32 + eofs) + i);
+                v[4 * i + 0] = mk.x > 0.f ? v[4 * i + 0] : 0.f;
+                v[4 * i + 1] = mk.y > 0.f ? v[4 * i + 1] : 0.f;
+                v[4 * i + 2] = mk.z > 0.f ? v[4 * i + 2] : 0.f;
+                v[4 * i + 3] = mk.w > 0.f ? v[4 * i + 3] : 0.f;
+              }
+            }
+            if (a.inj_f32 != nullptr) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float4 ij = __ldg(reinterpret_cast<const float4*>(a.inj_f32 + eofs) + i);
+                v[4 * i + 0] += ij.x, v[4 * i + 1] += ij.y, v[4 * i + 2] += ij.z, v[4 * i + 3] += ij.w;
+              }
             }
           }
           if (valid) {
@@ -906,7 +943,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constan
 
   tc_fence_before();
   cluster_sync();
-  if (warp == 1) tmem_dealloc_pair(tmem_base, Cfg::kTmemCols);
+  if (warp == 1) tmem_dealloc_pair(tmem_base, kTmemCols);
 }
 
 // ---- host side --------------------------------------------------------------------------------------
@@ -1178,9 +1215,14 @@ int conv3x3_tc32(TcContext& tc, const TcWeights& w, const float* in, float* out,
   a.in_half = 1, a.out_half = 0;
   a.out_scale = 1.f / (w.split_scale * in_scale);
   a.bias = bias, a.mask_f32 = mask_act, a.inj_f32 = inj, a.out_f32 = out;
-  const int bn = choose_bn(tc, nb, h, wd, cout);
-  if (forward) return dispatch_bn<9, kEpiFwd32>(tc, bn, split_buf, w.fwd32, cout, nullptr, a, s);
-  return dispatch_bn<9, kEpiBwd32>(tc, bn, split_buf, w.bwd32, cout, nullptr, a, s);
+  // BN <= 128: the epilogue keeps the running sum of the chains in registers (BN / 2 per thread)
+  const int bn = std::min(choose_bn(tc, nb, h, wd, cout), 128);
+  if (forward) {
+    if (bn == 128) return launch2r<128, 9, kEpiFwd32, false>(tc, split_buf, w.fwd32, cout, nullptr, nullptr, a, s);
+    return launch2r<64, 9, kEpiFwd32, false>(tc, split_buf, w.fwd32, cout, nullptr, nullptr, a, s);
+  }
+  if (bn == 128) return launch2r<128, 9, kEpiBwd32, false>(tc, split_buf, w.bwd32, cout, nullptr, nullptr, a, s);
+  return launch2r<64, 9, kEpiBwd32, false>(tc, split_buf, w.bwd32, cout, nullptr, nullptr, a, s);
 }
 
 // Per batch tile b: S_b[p][n] = sum_c F_b[p][c] * D_b[n][c]  (D_b symmetric bf16 [c][c]).  The sum

@@ -398,9 +398,11 @@ int build_injection(st_ctx* ctx, const st_loss_spec& sp, const Dims& d, const Ba
           set_error("invalid: ST_PREC_FP16 has no SIMT Gram kernel (channels must be 64/128/256/512)");
           return ST_ERR_INVALID;
         } else {
-          ST_REQUIRE(nb == 1, "the SIMT Gram kernel takes one tile at a time");
-          rc = gram_full<TA>(f, hf * wf, c, false, ctx->gram, ctx->part, ctx->part_floats,
-                             ctx->sm_count, s);
+          // the SIMT Gram kernel takes one tile at a time (fp32 mode: nb = 1; tc32 mode: a batch)
+          rc = ST_OK;
+          for (int bi = 0; bi < nb && rc == ST_OK; ++bi)
+            rc = gram_full<TA>(f + (size_t)bi * n, hf * wf, c, false, ctx->gram + (size_t)bi * c * c,
+                               ctx->part, ctx->part_floats, ctx->sm_count, s);
         }
       }
       if (rc == ST_OK && !on_tc)
@@ -433,9 +435,12 @@ int build_injection(st_ctx* ctx, const st_loss_spec& sp, const Dims& d, const Ba
           }
         }
       } else {
-        if constexpr (std::is_same<TA, T>::value)
-          rc = style_grad<T>(f, ctx->delta, static_cast<T*>(ctx->sbuf), hf * wf, c, stats + 2,
-                             ctx->rs, s);
+        if constexpr (std::is_same<TA, T>::value) {
+          for (int bi = 0; bi < nb && rc == ST_OK; ++bi)
+            rc = style_grad<T>(f + (size_t)bi * n, ctx->delta + (size_t)bi * c * c,
+                               static_cast<T*>(ctx->sbuf) + (size_t)bi * n, hf * wf, c,
+                               stats + 2 + (size_t)bi * kStatStride, ctx->rs, s);
+        }
       }
       if (rc == ST_OK)
         rc = inject_scaled<T>(inj, static_cast<const T*>(ctx->sbuf), n, nb, (float)w, stats + 2,
@@ -702,8 +707,7 @@ int st_create(int device, int precision, int n_layers, const st_layer_desc* laye
   }
   // tiles of one shape are evaluated as a batch by the tensor-core kernels; the fp32 SIMT parity
   // path keeps the reference's one-tile-at-a-time order
-  ctx->max_batch = (precision != ST_PREC_FP32 && precision != ST_PREC_TC32 && ctx->tc.enabled &&
-                    ctx->tc.pair_kernel) ? kMaxBatch : 1;
+  ctx->max_batch = (precision != ST_PREC_FP32 && ctx->tc.enabled && ctx->tc.pair_kernel) ? kMaxBatch : 1;
   if (const char* e = getenv("ST_MAX_BATCH")) {
     const int v = atoi(e);
     if (v >= 1 && v < ctx->max_batch) ctx->max_batch = v;

@@ -3,6 +3,9 @@ seeded inputs.  Stated tolerances:
 
   fp32 mode  : max|d| <= 2e-4 * max|ref| for feature maps and gradients, 1e-4 relative for
                losses (float32 round-off + different summation order);
+  tc32 mode  : fp32 storage, convolutions on the tensor cores with split fp16 hi + lo operands and
+               chained fp32 accumulation: losses 1e-4, gradients max|d| <= 1e-3 * max|ref| and
+               relative L2 <= 5e-4 (measured against the fp32 mode: features 3e-6, gradients 1e-4);
   fp16 mode  : tensor cores with fp16 forward activations / weights and bf16 gradients: feature
                maps within 2e-3 relative L2, losses within 5e-3; gradients relative L2 <= 2e-2
                (average-pool nets) / <= 6e-2 (max-pool nets) -- same mechanism as below, 8x finer
@@ -111,7 +114,7 @@ CASES = [
 
 
 @pytest.mark.parametrize('case', CASES, ids=[c[0].split('.')[0] + '-%dx%d' % c[1] for c in CASES])
-@pytest.mark.parametrize('precision', ['fp32', 'bf16', 'fp16'])
+@pytest.mark.parametrize('precision', ['fp32', 'tc32', 'bf16', 'fp16'])
 def test_sc_grad_tile(case, precision):
     model, (h, w), c_layers, s_layers, d_layers, start, roll = case
     eng, ora = engine_for(model, precision)
@@ -132,6 +135,10 @@ def test_sc_grad_tile(case, precision):
     if precision == 'fp32':
         assert abs(loss_g - loss_o) <= 1e-4 * abs(loss_o), (loss_g, loss_o)
         assert maxrel(grad_g, grad_o) < 2e-4
+    elif precision == 'tc32':
+        # split fp16 hi+lo operands on the tensor cores: ~22 bits per operand, chained fp32 accumulation
+        assert abs(loss_g - loss_o) <= 1e-4 * abs(loss_o), (loss_g, loss_o)
+        assert maxrel(grad_g, grad_o) < 1e-3 and l2rel(grad_g, grad_o) < 5e-4
     elif precision == 'fp16':
         assert abs(loss_g - loss_o) <= 5e-3 * abs(loss_o), (loss_g, loss_o)
         assert l2rel(grad_g, grad_o) < (2e-2 if 'avgpool' in model else 6e-2)
@@ -366,7 +373,7 @@ def test_n_iterations_match_oracle(optimizer, iters):
         assert err.max() <= 0.5, float(err.max())
 
 
-@pytest.mark.parametrize('precision', ['fp16', 'bf16'])
+@pytest.mark.parametrize('precision', ['fp16', 'bf16', 'tc32'])
 def test_batching_does_not_change_bits(precision, monkeypatch):
     """Tiles evaluated 16, 3 or 1 at a time give bit-identical gradients: split-K and |S| partial
     sums are grouped by layer shape only, never by batch size (what makes N-rank == 1-rank)."""
