@@ -216,6 +216,22 @@ ST_API int st_resample_coeffs(int in_size, int out_size, int method, int* ksize,
 ST_API int st_lbfgs_inv_hv(const float* grad_dev, size_t n, int m, const float* const* s_dev,
                     const float* const* y_dev, const double* sy_host, float* p_dev,
                     double* scratch_dev, st_stream stream);
+/* LBFGSOptimizer.update / store_curvature_pair (optimizers.py:74-103) with the memory ON THE DEVICE:
+ * no host synchronisation, no host decision.  ring_s_dev / ring_y_dev: f32 [n_corr + 1][n] (n_corr <=
+ * 16); state_dev: 64 doubles, all zero = empty memory ([0] = number of valid pairs, [1] = ring slot of
+ * the next pair, rest: s.y products and scratch); scratch_dev: n floats.
+ * st_lbfgs_step:   s = -H grad by the two-loop recursion over the valid pairs (:105-121), scaled as
+ *                  :81-84 (mean|s| = initial_step while the memory is empty, count / n_corr until it
+ *                  is full), written to the free ring slot, and params += s (:85).
+ * st_lbfgs_commit: after the objective was evaluated at the new params: y = grad_new - grad_old goes
+ *                  to the same slot and the pair is kept iff s.y > 1e-10 (:92-103; the oldest pair
+ *                  falls out once n_corr are held). */
+ST_API int st_lbfgs_step(const float* grad_dev, size_t n, int n_corr, float* ring_s_dev,
+                         const float* ring_y_dev, double* state_dev, float* scratch_dev,
+                         float* params_dev, float initial_step, st_stream stream);
+ST_API int st_lbfgs_commit(const float* grad_new_dev, const float* grad_old_dev, size_t n, int n_corr,
+                           const float* ring_s_dev, float* ring_y_dev, double* state_dev,
+                           st_stream stream);
 /* BLAS-1 helpers used by LBFGSOptimizer.update/store_curvature_pair :74-103. */
 ST_API int st_dot(const float* x, const float* y, size_t n, double* out_dev, st_stream stream);
 ST_API int st_asum(const float* x, size_t n, double* out_dev, st_stream stream);

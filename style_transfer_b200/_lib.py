@@ -62,6 +62,8 @@ PROTOTYPES = {
     'st_adam_step': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _sz, _f, _f, _f, _f, _f, _f, _f, _vp]),
     'st_lbfgs_inv_hv': (_i, [_vp, _sz, _i, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(C.c_double),
                              _vp, _vp, _vp]),
+    'st_lbfgs_step': (_i, [_vp, _sz, _i, _vp, _vp, _vp, _vp, _vp, _f, _vp]),
+    'st_lbfgs_commit': (_i, [_vp, _vp, _sz, _i, _vp, _vp, _vp, _vp]),
     'st_resize_f32': (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     'st_resample_coeffs': (_i, [_i, _i, _i, _ip, _vp, _vp]),
     'st_iter_stats': (_i, [_vp, _vp, _i, _i, _vp, _vp]),

@@ -1224,4 +1224,29 @@ int st_lbfgs_inv_hv(const float* grad_dev, size_t n, int m, const float* const* 
   return rc;
 }
 
+int st_lbfgs_step(const float* grad_dev, size_t n, int n_corr, float* ring_s_dev,
+                  const float* ring_y_dev, double* state_dev, float* scratch_dev, float* params_dev,
+                  float initial_step, st_stream stream) {
+  ST_REQUIRE(grad_dev && ring_s_dev && ring_y_dev && state_dev && scratch_dev && params_dev && n > 0 &&
+                 n_corr >= 1 && n_corr <= 16,
+             "st_lbfgs_step: bad arguments");
+  ReduceScratch rs;
+  int rc = global_scratch(&rs);
+  if (rc != ST_OK) return rc;
+  return lbfgs_direction(grad_dev, n, n_corr, ring_s_dev, ring_y_dev, state_dev, scratch_dev,
+                         params_dev, initial_step, rs, (cudaStream_t)stream);
+}
+
+int st_lbfgs_commit(const float* grad_new_dev, const float* grad_old_dev, size_t n, int n_corr,
+                    const float* ring_s_dev, float* ring_y_dev, double* state_dev, st_stream stream) {
+  ST_REQUIRE(grad_new_dev && grad_old_dev && ring_s_dev && ring_y_dev && state_dev && n > 0 &&
+                 n_corr >= 1 && n_corr <= 16,
+             "st_lbfgs_commit: bad arguments");
+  ReduceScratch rs;
+  int rc = global_scratch(&rs);
+  if (rc != ST_OK) return rc;
+  return lbfgs_commit(grad_new_dev, grad_old_dev, n, n_corr, ring_s_dev, ring_y_dev, state_dev, rs,
+                      (cudaStream_t)stream);
+}
+
 }  // extern "C"

@@ -160,5 +160,12 @@ int axpby(float a, const float* x, float b, float* y, size_t n, cudaStream_t s);
 int axpy_dev(const float* x, float* y, size_t n, const double* num, double den, const double* sub,
              double sign, double* store, cudaStream_t s);
 int scale_dev(float* y, size_t n, double num, const double* den, cudaStream_t s);
+// L-BFGS with device-resident memory (see kernels_image.cu): the step s = -scale * H grad is written
+// to ring_s[head] and added to params; the candidate pair is completed and kept / dropped on the device
+int lbfgs_direction(const float* grad, size_t n, int n_corr, float* ring_s, const float* ring_y,
+                    double* state, float* p_scratch, float* params, float initial_step,
+                    ReduceScratch rs, cudaStream_t s);
+int lbfgs_commit(const float* grad_new, const float* grad_old, size_t n, int n_corr,
+                 const float* ring_s, float* ring_y, double* state, ReduceScratch rs, cudaStream_t s);
 
 }  // namespace st

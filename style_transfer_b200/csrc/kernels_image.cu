@@ -515,4 +515,157 @@ int scale_dev(float* y, size_t n, double num, const double* den, cudaStream_t s)
   return ST_OK;
 }
 
+// -----------------------------------------------------------------------------------------------------
+// L-BFGS with its memory on the device (LBFGSOptimizer, optimizers.py:64-138): no host decisions.
+// state (doubles): [0] count of valid pairs, [1] head = ring slot the NEXT pair is written to,
+// [2] dot scratch, [3] sum|p| scratch, [4 .. 4+17) s.y per slot, [24 .. 24+16) alpha per pair.
+// The ring has n_corr + 1 slots so that the candidate pair can be written before it is known
+// whether it will be kept (optimizers.py:98: kept iff s.y > 1e-10); pair k (0 = newest) lives in
+// slot (head - 1 - k) mod (n_corr + 1).
+// -----------------------------------------------------------------------------------------------------
+namespace {
+constexpr int kLbSy = 4, kLbAlpha = 24;
+__device__ __forceinline__ int lb_slot(const double* st, int k, int n_corr) {
+  int sl = ((int)st[1] - 1 - k) % (n_corr + 1);
+  return sl < 0 ? sl + n_corr + 1 : sl;
+}
+// pair index of iteration j: MODE 0 = first loop (newest -> oldest), 1 = second loop (oldest ->
+// newest), 2 = the newest pair; < 0: nothing to do
+template <int MODE>
+__device__ __forceinline__ int lb_pair(const double* st, int j) {
+  const int count = (int)st[0];
+  if (MODE == 0) return j < count ? j : -1;
+  if (MODE == 1) return count - 1 - j;
+  return count > 0 ? 0 : -1;
+}
+
+// st[2] = dot(ring[slot(pair)], MODE == 2 ? the same vector : p)
+template <int MODE>
+__global__ void lb_dot_kernel(const float* __restrict__ ring, size_t n, int n_corr, double* st, int j,
+                              const float* __restrict__ p, ReduceScratch rs) {
+  const int k = lb_pair<MODE>(st, j);
+  if (k < 0) return;
+  const float* x = ring + (size_t)lb_slot(st, k, n_corr) * n;
+  const float* y = MODE == 2 ? x : p;
+  double v[1] = {0.0};
+  float part = 0.f;
+  int cnt = 0;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
+       i += (size_t)gridDim.x * blockDim.x) {
+    part += x[i] * y[i];
+    if (++cnt == 32) v[0] += part, part = 0.f, cnt = 0;
+  }
+  v[0] += part;
+  if (grid_reduce<1>(v, rs.partials, rs.counter)) st[2] = v[0];
+}
+
+// MODE 0: alpha_k = st[2] / sy_k; p -= alpha_k * y_k        (optimizers.py:110-111)
+// MODE 1: beta = st[2] / sy_k;   p += (alpha_k - beta) * s_k  (:118-119)
+// MODE 2: p *= sy_0 / st[2]                                    (:113-115)
+template <int MODE>
+__global__ void lb_update_kernel(const float* __restrict__ ring, size_t n, int n_corr, double* st,
+                                 int j, float* __restrict__ p) {
+  const int k = lb_pair<MODE>(st, j);
+  if (k < 0) return;
+  const int slot = lb_slot(st, k, n_corr);
+  const double dot = st[2], sy = st[kLbSy + slot];
+  float coef;
+  if (MODE == 0) {
+    const double alpha = dot / sy;
+    coef = (float)(-alpha);
+    if (blockIdx.x == 0 && threadIdx.x == 0) st[kLbAlpha + k] = alpha;
+  } else if (MODE == 1) {
+    coef = (float)(st[kLbAlpha + k] - dot / sy);
+  } else {
+    coef = (float)(sy / dot);
+  }
+  const float* x = ring + (size_t)slot * n;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
+       i += (size_t)gridDim.x * blockDim.x)
+    p[i] = MODE == 2 ? p[i] * coef : p[i] + coef * x[i];
+}
+
+// s = -scale * p into ring_s[head], params += s.  scale (:81-84): initial_step / mean|p| while the
+// memory is empty, count / n_corr until it is full, then 1.  st[3] holds sum|p|.
+__global__ void lb_step_kernel(const float* __restrict__ p, size_t n, int n_corr, const double* st,
+                               float initial_step, float* __restrict__ ring_s,
+                               float* __restrict__ params) {
+  const int count = (int)st[0];
+  double scale = 1.0;
+  if (count == 0)
+    scale = (double)initial_step / (st[3] / (double)n);
+  else if (count < n_corr)
+    scale = (double)count / (double)n_corr;
+  const float coef = (float)(-scale);
+  float* s = ring_s + (size_t)((int)st[1]) * n;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const float v = coef * p[i];
+    s[i] = v;
+    params[i] += v;
+  }
+}
+
+// y = grad_new - grad_old into ring_y[head]; st[2] = s . y
+__global__ void lb_y_kernel(const float* __restrict__ gn, const float* __restrict__ go, size_t n,
+                            const float* __restrict__ ring_s, float* __restrict__ ring_y, double* st,
+                            ReduceScratch rs) {
+  const size_t off = (size_t)((int)st[1]) * n;
+  const float* s = ring_s + off;
+  float* y = ring_y + off;
+  double v[1] = {0.0};
+  float part = 0.f;
+  int cnt = 0;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const float d = gn[i] - go[i];
+    y[i] = d;
+    part += s[i] * d;
+    if (++cnt == 32) v[0] += part, part = 0.f, cnt = 0;
+  }
+  v[0] += part;
+  if (grid_reduce<1>(v, rs.partials, rs.counter)) st[2] = v[0];
+}
+
+// keep the candidate pair iff s.y > 1e-10 (:98-103): advance the head, grow the count up to n_corr
+__global__ void lb_commit_kernel(double* st, int n_corr) {
+  const double sy = st[2];
+  if (sy > 1e-10) {
+    const int head = (int)st[1];
+    st[kLbSy + head] = sy;
+    st[1] = (double)((head + 1) % (n_corr + 1));
+    const int count = (int)st[0];
+    st[0] = (double)(count < n_corr ? count + 1 : n_corr);
+  }
+}
+}  // namespace
+
+int lbfgs_direction(const float* grad, size_t n, int n_corr, float* ring_s, const float* ring_y,
+                    double* st, float* p, float* params, float initial_step, ReduceScratch rs,
+                    cudaStream_t s) {
+  const int grid = ew_grid(n, 256);
+  ST_CUDA(cudaMemcpyAsync(p, grad, n * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  for (int j = 0; j < n_corr; ++j) {                         // optimizers.py:109-111
+    ST_LAUNCH(lb_dot_kernel<0>, grid, 256, 0, s, ring_s, n, n_corr, st, j, p, rs);
+    ST_LAUNCH(lb_update_kernel<0>, grid, 256, 0, s, ring_y, n, n_corr, st, j, p);
+  }
+  ST_LAUNCH(lb_dot_kernel<2>, grid, 256, 0, s, ring_y, n, n_corr, st, 0, p, rs);   // :113-115
+  ST_LAUNCH(lb_update_kernel<2>, grid, 256, 0, s, ring_y, n, n_corr, st, 0, p);
+  for (int j = 0; j < n_corr; ++j) {                         // :117-119
+    ST_LAUNCH(lb_dot_kernel<1>, grid, 256, 0, s, ring_y, n, n_corr, st, j, p, rs);
+    ST_LAUNCH(lb_update_kernel<1>, grid, 256, 0, s, ring_s, n, n_corr, st, j, p);
+  }
+  int rc = asum_to(p, n, st + 3, rs, s);
+  if (rc != ST_OK) return rc;
+  ST_LAUNCH(lb_step_kernel, grid, 256, 0, s, p, n, n_corr, st, initial_step, ring_s, params);
+  return ST_OK;
+}
+
+int lbfgs_commit(const float* grad_new, const float* grad_old, size_t n, int n_corr,
+                 const float* ring_s, float* ring_y, double* st, ReduceScratch rs, cudaStream_t s) {
+  ST_LAUNCH(lb_y_kernel, ew_grid(n, 256), 256, 0, s, grad_new, grad_old, n, ring_s, ring_y, st, rs);
+  ST_LAUNCH(lb_commit_kernel, 1, 1, 0, s, st, n_corr);
+  return ST_OK;
+}
+
 }  // namespace st

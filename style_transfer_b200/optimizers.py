@@ -82,7 +82,10 @@ class AdamOptimizer:
 
 
 class LBFGSOptimizer:
-    """L-BFGS with fixed size steps, no line search (optimizers.py:64-138)."""
+    """L-BFGS with fixed size steps, no line search (optimizers.py:64-138).  The curvature pairs,
+    their s.y products and the pair count live on the device (``st_lbfgs_step`` /
+    ``st_lbfgs_commit``): an update enqueues kernels only -- no ``.item()``, no host decision --
+    so the host runs ahead of the GPU exactly as it does with Adam."""
 
     def __init__(self, params, initial_step=0.1, n_corr=10):
         self.params = params
@@ -90,56 +93,46 @@ class LBFGSOptimizer:
         self.n_corr = n_corr
         self.xy = np.zeros(2, dtype=np.int32)
         self.loss, self.grad = None, None
-        self.sk, self.yk, self.syk = [], [], []
-        self._scratch = torch.zeros(64, dtype=torch.float64, device=params.device)
+        self._alloc()
+
+    def _alloc(self):
+        n, dev = self.params.numel(), self.params.device
+        self._ring_s = torch.empty((self.n_corr + 1, n), dtype=torch.float32, device=dev)
+        self._ring_y = torch.empty((self.n_corr + 1, n), dtype=torch.float32, device=dev)
+        self._state = torch.zeros(64, dtype=torch.float64, device=dev)     # empty memory
+        self._scratch = torch.empty(n, dtype=torch.float32, device=dev)
 
     def update(self, opfunc):
-        if self.loss is None:
+        if self.loss is None:                                                    # (:76-77)
             self.loss, self.grad = opfunc(self.params)
-            self.grad = self.grad.clone()
         n = self.params.numel()
-        s = self.inv_hv(self.grad)                       # s = -H g below
-        if not self.sk:
-            _lib.call('st_asum', _ptr(s), n, _ptr(self._scratch[32:]), _stream())
-            mean_abs = float(self._scratch[32].item()) / n
-            scale = -self.initial_step / mean_abs
-        elif len(self.sk) < self.n_corr:
-            scale = -len(self.sk) / self.n_corr
-        else:
-            scale = -1.0
-        _lib.call('st_axpby', scale, _ptr(s), 0.0, _ptr(s), n, _stream())
-        _lib.call('st_axpby', 1.0, _ptr(s), 1.0, _ptr(self.params), n, _stream())
-        loss, grad = opfunc(self.params)
-        y = grad - self.grad
-        self.store_curvature_pair(s, y)
-        self.loss, self.grad = loss, grad.clone()
+        # s = -H g, scaled (:80-84), params += s (:85)
+        _lib.call('st_lbfgs_step', _ptr(self.grad), n, self.n_corr, _ptr(self._ring_s),
+                  _ptr(self._ring_y), _ptr(self._state), _ptr(self._scratch), _ptr(self.params),
+                  self.initial_step, _stream())
+        loss, grad = opfunc(self.params)                                         # (:88)
+        # y = grad - self.grad; the pair is kept iff s.y > 1e-10 (:89-103)
+        _lib.call('st_lbfgs_commit', _ptr(grad), _ptr(self.grad), n, self.n_corr,
+                  _ptr(self._ring_s), _ptr(self._ring_y), _ptr(self._state), _stream())
+        self.loss, self.grad = loss, grad
         return self.params, loss
 
-    def store_curvature_pair(self, s, y):
-        _lib.call('st_dot', _ptr(s), _ptr(y), s.numel(), _ptr(self._scratch[33:]), _stream())
-        sy = float(self._scratch[33].item())
-        if sy > 1e-10:
-            self.sk.append(s)
-            self.yk.append(y)
-            self.syk.append(sy)
-        if len(self.sk) > self.n_corr:
-            self.sk, self.yk, self.syk = self.sk[1:], self.yk[1:], self.syk[1:]
-
-    def inv_hv(self, p):
-        """Two-loop recursion on the device; returns H p as a new tensor."""
-        m = len(self.sk)
-        out = torch.empty_like(p)
-        s_ptrs = (C.c_void_p * max(m, 1))(*[t.data_ptr() for t in self.sk])
-        y_ptrs = (C.c_void_p * max(m, 1))(*[t.data_ptr() for t in self.yk])
-        sy = (C.c_double * max(m, 1))(*self.syk)
-        _lib.call('st_lbfgs_inv_hv', _ptr(p), p.numel(), m, s_ptrs, y_ptrs, sy, _ptr(out),
-                  _ptr(self._scratch), _stream())
-        return out
+    @property
+    def sk(self):
+        """The stored s vectors, oldest first (host view for tests / inspection: synchronises)."""
+        st = self._state.cpu().numpy()
+        count, head = int(st[0]), int(st[1])
+        slots = [(head - 1 - k) % (self.n_corr + 1) for k in range(count)]
+        return [self._ring_s[i] for i in reversed(slots)]
 
     def roll(self, xy):
         self.xy += np.asarray(xy, dtype=np.int32)
 
     def set_params(self, last_iterate, resize=None):
+        """Cross-scale restart (optimizers.py:134-138): new parameters, memory cleared."""
         self.params = last_iterate
         self.loss, self.grad = None, None
-        self.sk, self.yk, self.syk = [], [], []
+        if self._scratch.numel() != self.params.numel():
+            self._alloc()
+        else:
+            self._state.zero_()
