@@ -59,6 +59,7 @@ def parse_args():
     p.add_argument('--optimizer', default='adam', choices=['adam', 'lbfgs'])
     p.add_argument('--no-cpu-baseline', action='store_true')
     p.add_argument('--no-e2e', action='store_true')
+    p.add_argument('--no-extra', action='store_true', help='skip the tc32 and cfg4 records')
     return p.parse_args()
 
 
@@ -129,6 +130,18 @@ class CpuReference:
         t0 = time.perf_counter()
         self.ora.sc_grad_tile(self.tile, np.array([0, 0]), self.layers, CONTENT_LAYERS,
                               STYLE_LAYERS, [], self.lw, {'conv4_2': 0.05}, self.sw, {})
+        return time.perf_counter() - t0
+
+    def full_iteration(self):
+        """ONE complete iteration: every tile of the image, one after the other, + the tail."""
+        ts = self.tile_px
+        t0 = time.perf_counter()
+        for ty in range(0, self.a.size, ts):
+            for tx in range(0, self.a.size, ts):
+                tile = np.ascontiguousarray(self.full[:, ty:ty + ts, tx:tx + ts])
+                self.ora.sc_grad_tile(tile, np.array([0, 0]), self.layers, CONTENT_LAYERS,
+                                      STYLE_LAYERS, [], self.lw, {'conv4_2': 0.05}, self.sw, {})
+        self.full_image_tail()
         return time.perf_counter() - t0
 
     def full_image_tail(self):
@@ -202,10 +215,16 @@ class OneDnnConvs:
 
 
 def run_reference(a):
+    """The reference arm: the reference's CPU algorithm (oracle port, all host cores) on the engine
+    arm's workload.  A whole 16-tile iteration costs ~50 s here, so every STEP is a bounded sample --
+    one 512x512 tile evaluation (1/16 of an iteration's tiles) -- and ``ms_per_step`` is the measured
+    duration of that sample; ``value`` scales the mean sample to an iteration (tiles are evaluated
+    one after the other and independently by the reference, style_transfer.py:623-643) and adds one
+    measured full-image regulariser + Adam pass.  When it fits (~75 s) ONE complete iteration -- all
+    16 distinct tiles + the tail -- is timed as well and reported beside the scaled figure."""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    # size the per-step sample so that warm-up + K steps stay within ~3 minutes on this host
     ref = CpuReference(a)
     t_probe = ref.tile_eval()
     crop = ref.crop
@@ -220,13 +239,22 @@ def run_reference(a):
     t_tile = float(np.mean(times))
     sec = ref.iteration_seconds(t_tile, t_tail)
     value = 1.0 / sec
+    full = None
+    if ref.crop == ref.tile_px and ref.ntiles * t_tile + t_tail <= 75.0:
+        t_full = ref.full_iteration()
+        full = {'seconds': t_full, 'value': 1.0 / t_full,
+                'what': 'ONE complete iteration measured: all %d distinct tiles of the image one '
+                        'after the other + the regulariser / Adam pass' % ref.ntiles}
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': 'iterations/s',
-        'n_gpus': a.gpus, 'steps': a.steps, 'warmup': a.warmup, 'ms_per_step': sec * 1e3,
+        'n_gpus': a.gpus, 'steps': a.steps, 'warmup': a.warmup, 'ms_per_step': t_tile * 1e3,
+        'ms_per_iteration': sec * 1e3, 'step_is': 'one tile evaluation = 1/%d of an iteration' %
+        round(ref.ntiles * (ref.tile_px / ref.crop) ** 2),
         'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32',
         'data': 'synthetic', 'config': workload_config(a, 1),
         'cpu_baseline': {'value': value, 'unit': 'iterations/s', 'cores': ref.cores, 'kind': 'port',
                          'sample': 'each step = ' + ref.sample_text(1)},
+        'full_iteration': full,
         'e2e': {'value': value, 'unit': 'iterations/s', 'h2d_bytes_per_step': 0,
                 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
@@ -311,13 +339,70 @@ class ClockSampler:
 # =======================================================================================================
 # engine arm
 # =======================================================================================================
+PROFILE_TRAFFIC = os.path.join(ROOT, 'profiles', 'ncu_traffic.json')
+
+
+def measured_traffic(kernel, a, world):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed ncu
+    `--set full` capture of THIS workload (profiles/ncu_traffic.json, written by
+    tools/ncu_traffic.py from the .ncu-rep), or None when no capture matches the configuration."""
+    try:
+        with open(PROFILE_TRAFFIC) as f:
+            table = json.load(f)
+    except (OSError, ValueError):
+        return None, None
+    key = '%s|size=%d|tile=%d|precision=%s|gpus=%d' % (kernel, a.size, a.tile_size, a.precision, world)
+    rec = table.get(key)
+    if not rec:
+        return None, None
+    return rec.get('dram_bytes_per_launch'), rec.get('source')
+
+
+class Workload:
+    """One configured run of the loop body: engine + StyleTransfer, images prepared."""
+
+    def __init__(self, rank, world, local, size, tile, model, optimizer, precision, **flags):
+        import torch
+        from style_transfer_b200 import netdesc, weights
+        from style_transfer_b200.engine import TileEngine
+        from style_transfer_b200.transfer import StyleTransfer, default_args
+        self.torch = torch
+        args = default_args(size=size, min_size=size, tile_size=tile, optimizer=optimizer,
+                            model=model, **flags)
+        net = netdesc.from_model(args.model)
+        self.eng = TileEngine(net, weights.he_normal(net), mean=args.mean, device=local,
+                              precision=precision, rank=rank, world=world)
+        self.eng.init_comm()
+        self.st = StyleTransfer(self.eng, args)
+        content = self.eng.pil_to_image(synthetic_rgb(1, size))
+        style = self.eng.pil_to_image(synthetic_rgb(2, size))
+        np.random.seed(args.seed)
+        self.st.init_first_scale(size, size)
+        self.st.prepare([content], [style])
+        self.old = self.eng.img.clone()
+        self.stats = torch.zeros(2, dtype=torch.float64, device=self.eng.img.device)
+
+    def step(self):
+        """One pass of the loop body (style_transfer.py:777-821): roll, objective, optimizer step,
+        roll back, the update-size / TV statistics and the uint8 picture -- all on the device."""
+        avg, loss = self.st.step()
+        self.st.iter_stats_async(avg, self.old, self.stats)
+        self.picture = self.eng.get_image_u8(avg)
+        self.loss = loss
+        return avg, loss
+
+    def close(self):
+        self.st = self.eng = self.old = self.picture = None
+        import gc
+        gc.collect()
+        self.torch.cuda.empty_cache()
+
+
 def run_engine(a):
     import ctypes as C
     import torch
     import torch.distributed as dist
-    from style_transfer_b200 import _lib, netdesc, weights
-    from style_transfer_b200.engine import TileEngine
-    from style_transfer_b200.transfer import StyleTransfer, default_args
+    from style_transfer_b200 import _lib
 
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -330,18 +415,12 @@ def run_engine(a):
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
         dist.init_process_group('nccl', device_id=dev)
     lib = _lib.load()
-
-    args = default_args(size=a.size, min_size=a.size, tile_size=a.tile_size, optimizer=a.optimizer)
-    net = netdesc.from_model(args.model)
-    eng = TileEngine(net, weights.he_normal(net), mean=args.mean, device=local,
-                     precision=a.precision, rank=rank, world=world)
-    st = StyleTransfer(eng, args)
-    content = eng.pil_to_image(synthetic_rgb(1, a.size))
-    style = eng.pil_to_image(synthetic_rgb(2, a.size))
-    np.random.seed(args.seed)
-    st.init_first_scale(a.size, a.size)
-    st.prepare([content], [style])
-    n = eng.img.numel()
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
+            peaks = json.load(f)
+    except OSError:
+        pass
 
     def barrier():
         if world > 1:
@@ -349,25 +428,86 @@ def run_engine(a):
         torch.cuda.synchronize()
 
     def timed(fn, steps):
+        """(device ms, host enqueue ms) of `steps` calls: CUDA events on the launching stream,
+        barrier + synchronize on both sides, max over ranks."""
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
+        h0 = time.perf_counter()
         for _ in range(steps):
             fn()
+        h1 = time.perf_counter()
         e1.record()
         barrier()
-        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        ms = torch.tensor([e0.elapsed_time(e1), (h1 - h0) * 1e3], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item())
+        return float(ms[0].item()), float(ms[1].item())
 
-    # ---- device-resident throughput --------------------------------------------------------------
+    def measure(w, steps, warmup):
+        for _ in range(warmup):
+            w.step()
+        ms, host_ms = timed(w.step, steps)
+        return steps / (ms * 1e-3), ms / steps, host_ms / steps
+
+    def conv_roofline(w, steps, precision, sm_mhz, sm_max):
+        """Per-launch CUDA events (st_timing_*) around every kernel group of `steps` steps."""
+        lib.st_timing_reset()
+        lib.st_timing_enable(1)
+        ms_timing, _ = timed(w.step, steps)
+        lib.st_timing_enable(0)
+        cats = ['conv_tc', 'conv_edge', 'pool', 'gram', 'style_grad', 'loss', 'image']
+        breakdown = {}
+        for i, name in enumerate(cats):
+            t, wk, k = C.c_double(), C.c_double(), C.c_uint64()
+            _lib.call('st_timing_read', i, C.byref(t), C.byref(wk), C.byref(k))
+            breakdown[name] = {'ms_per_step': t.value / steps, 'work_per_step': wk.value / steps,
+                               'launch_groups_per_step': k.value / steps}
+        lib.st_timing_reset()
+        dom = 'conv_tc' if breakdown['conv_tc']['ms_per_step'] > 0 else 'conv_edge'
+        d = breakdown[dom]
+        if d['ms_per_step'] <= 0:
+            return None, breakdown
+        tensor = precision in ('bf16', 'fp16', 'tc32')
+        if tensor:
+            # burst figure when the SM clock sat at its maximum during the timed region (a short
+            # run on a cool GPU), the sustained one when the power cap had pulled it down
+            at_max = sm_mhz is not None and sm_max and sm_mhz >= 0.97 * sm_max
+            kind = 'burst' if at_max else 'sustained'
+            peak = peaks.get('bf16_tflops' if at_max else 'bf16_tflops_sustained',
+                             1650.0 if at_max else 1400.0)
+            src = ('MEASURED_PEAKS.json bf16_tflops%s' % ('' if at_max else '_sustained')) if peaks \
+                else 'fallback (B200_PROFILING.md)'
+        else:
+            kind, peak = 'nominal', 0.5 * 148 * 128 * 2 * 1.965e-3 * 2
+            src = 'nominal fp32 FFMA peak (no tensor cores in fp32 mode)'
+        ach = d['work_per_step'] / (d['ms_per_step'] * 1e-3) / 1e12
+        kernel = 'conv_tc2_kernel' if dom == 'conv_tc' else 'conv3x3_kernel'
+        traffic, tsrc = measured_traffic(kernel, a, world) if precision == a.precision else (None, None)
+        roof = {'bound': 'tensor', 'kernel': kernel, 'achieved': ach, 'peak': peak, 'unit': 'TFLOP/s',
+                'frac': ach / peak, 'peak_kind': kind, 'peak_source': src,
+                'sm_mhz_during_run': sm_mhz, 'traffic': traffic, 'traffic_source': tsrc,
+                'flops_per_launch': d['work_per_step'] / max(d['launch_groups_per_step'], 1),
+                'avg_launch_ms': d['ms_per_step'] / max(d['launch_groups_per_step'], 1),
+                'share_of_step': d['ms_per_step'] / (ms_timing / steps),
+                'work': 'ALGORITHMIC flops: 2*9*Cin*Cout*H*W per conv launch, forward + backward-data'
+                        + ('; the split-operand mode executes 3 MMAs per product, i.e. 3x these flops'
+                           ' on the tensor pipe' if precision == 'tc32' else '')}
+        for key in ('bf16_tflops', 'bf16_tflops_sustained'):
+            if tensor and peaks.get(key):
+                roof['frac_of_' + key] = ach / peaks[key]
+        return roof, breakdown
+
+    # ---- the headline workload: cfg3 in the fast tensor-core mode -----------------------------------
+    w = Workload(rank, world, local, a.size, a.tile_size, 'vgg19.prototxt', a.optimizer, a.precision)
+    eng, st = w.eng, w.st
+    n = eng.img.numel()
     for _ in range(a.warmup):
-        st.step()
+        w.step()
     sampler = ClockSampler(local) if rank == 0 else None
     launches0 = lib.st_launch_count()
     t0 = time.perf_counter()
-    ms = timed(st.step, a.steps)
+    ms, host_ms = timed(w.step, a.steps)
     t1 = time.perf_counter()
     launches = lib.st_launch_count() - launches0
     clocks = sampler.stop(t0, t1) if sampler else None
@@ -376,101 +516,62 @@ def run_engine(a):
         dist.all_reduce(lt)
     launches = int(lt.item())
     value = a.steps / (ms * 1e-3)
+    sm_mhz = clocks and clocks.get('sm_mhz')
+    sm_max = clocks and clocks.get('sm_max_mhz')
+    if world > 1:                      # every rank needs the same peak choice
+        cl = torch.tensor([sm_mhz or 0.0, sm_max or 0.0], dtype=torch.float64, device=dev)
+        dist.broadcast(cl, src=0)
+        sm_mhz, sm_max = float(cl[0].item()) or None, float(cl[1].item()) or None
 
-    # ---- end to end: host buffers in, host buffers out, every step --------------------------------
+    # ---- end to end: host buffers in, host buffers out, every step ---------------------------------
     e2e = None
     if not a.no_e2e:
-        # Only rank 0 talks to the host (as the reference's master process does); the image reaches
-        # the other ranks over NVLink (one NCCL broadcast), results leave from rank 0.
-        if rank == 0:
-            host_params = torch.empty(eng.img.shape, dtype=torch.float32).pin_memory()
-            host_avg = torch.empty(eng.img.shape, dtype=torch.float32).pin_memory()
-            host_loss = torch.empty(1, dtype=torch.float64).pin_memory()
-            host_params.copy_(eng.img)
-
-        copy_stream = torch.cuda.Stream()
-        ev_step, ev_avg = torch.cuda.Event(), torch.cuda.Event()
-        ev_avg.record()
+        H, W = eng.img.shape[-2:]
+        rows = H // world if H % world == 0 else None
+        host_params = torch.empty(eng.img.shape, dtype=torch.float32).pin_memory()
+        host_params.copy_(eng.img)
+        host_pic = torch.empty((H, W, 3), dtype=torch.uint8).pin_memory()
+        host_scalars = torch.empty(3, dtype=torch.float64).pin_memory()
+        scal = torch.zeros(3, dtype=torch.float64, device=dev)
 
         def e2e_step():
-            main = torch.cuda.current_stream()
+            # H2D: this step's image (every rank its 1/world slab of rows through its own PCIe link,
+            # NVLink all-gather; one GPU: two halves, the second streaming in behind the first tiles)
+            eng.stage_host_image(host_params)
+            w.step()
+            # D2H: the uint8 picture (every rank its slab) + loss and the two statistics (rank 0)
+            if rows is not None:
+                r0 = rank * rows
+                host_pic[r0:r0 + rows].copy_(w.picture[r0:r0 + rows], non_blocking=True)
+            elif rank == 0:
+                host_pic.copy_(w.picture, non_blocking=True)
             if rank == 0:
-                eng.img.copy_(host_params, non_blocking=True)        # H2D: this step's image
-                main.wait_event(ev_avg)      # the previous iterate has left the device buffer
-            if world > 1:
-                dist.broadcast(eng.img, src=0)
-            avg, loss = st.step()
-            if rank == 0:
-                # the averaged iterate goes out on a second stream: its D2H (full duplex with the
-                # next step's H2D) overlaps the start of the next step; everything is inside the
-                # timed region, which ends with a device-wide synchronisation
-                ev_step.record(main)
-                copy_stream.wait_event(ev_step)
-                with torch.cuda.stream(copy_stream):
-                    host_avg.copy_(avg, non_blocking=True)           # D2H: averaged iterate
-                    ev_avg.record(copy_stream)
-                host_params.copy_(eng.img, non_blocking=True)        # D2H: updated parameters
-                host_loss.copy_(loss, non_blocking=True)             # D2H: loss
-            main.synchronize()
-        for _ in range(2):
+                scal[0:1].copy_(w.loss)
+                scal[1:3].copy_(w.stats)
+                host_scalars.copy_(scal, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        for _ in range(3):
             e2e_step()
-        ms_e2e = timed(e2e_step, a.steps)
+        ms_e2e, _ = timed(e2e_step, a.steps)
+        slab = n * 4 // world if rows is not None else n * 4
         e2e = {'value': a.steps / (ms_e2e * 1e-3), 'unit': 'iterations/s',
-               'h2d_bytes_per_step': n * 4, 'd2h_bytes_per_step': 2 * n * 4 + 8,
-               'ms_per_step': ms_e2e / a.steps,
-               'boundary': 'pinned host f32[3,H,W] image in; averaged iterate, updated image and '
-                           'loss out (StyleTransfer.step through the C ABI), every step; with N > 1 '
-                           'rank 0 owns the host side and broadcasts the image over NCCL'}
+               'h2d_bytes_per_step': n * 4, 'd2h_bytes_per_step': H * W * 3 + 24,
+               'h2d_bytes_per_step_per_gpu': slab,
+               'd2h_bytes_per_step_per_gpu': (H * W * 3) // world if rows is not None else H * W * 3,
+               'ms_per_step': ms_e2e / a.steps, 'fraction_of_value': a.steps / (ms_e2e * 1e-3) / value,
+               'boundary': 'pinned host f32[3,H,W] image in (TileEngine.stage_host_image), one pass of '
+                           'the loop body (StyleTransfer.step + statistics + picture), uint8 RGB '
+                           'picture + loss + update-size / TV statistics back to pinned host memory, '
+                           'stream synchronised, every step; N > 1: every rank moves its 1/N slab of '
+                           'rows through its own PCIe link, the image slabs are all-gathered over NCCL'}
 
-    # ---- roofline of the dominant kernel (per-launch CUDA events on the launching stream) ---------
-    roofline, breakdown = None, None
-    peaks = {}
-    try:
-        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
-            peaks = json.load(f)
-    except OSError:
-        pass
-    lib.st_timing_reset()
-    lib.st_timing_enable(1)
-    tsteps = min(a.steps, 3)
-    ms_timing = timed(st.step, tsteps)
-    lib.st_timing_enable(0)
-    cats = ['conv_tc', 'conv_edge', 'pool', 'gram', 'style_grad', 'loss', 'image']
-    breakdown = {}
-    for i, name in enumerate(cats):
-        t, w, k = C.c_double(), C.c_double(), C.c_uint64()
-        _lib.call('st_timing_read', i, C.byref(t), C.byref(w), C.byref(k))
-        breakdown[name] = {'ms_per_step': t.value / tsteps, 'work_per_step': w.value / tsteps,
-                           'launch_groups_per_step': k.value / tsteps}
-    lib.st_timing_reset()
-    dom = 'conv_tc' if breakdown['conv_tc']['ms_per_step'] > 0 else 'conv_edge'
-    d = breakdown[dom]
-    if d['ms_per_step'] > 0:
-        if a.precision in ('bf16', 'fp16', 'tc32'):
-            peak = peaks.get('bf16_tflops_sustained', 1400.0)
-            src = 'MEASURED_PEAKS.json bf16_tflops_sustained' if peaks else 'fallback 1400 (recipe)'
-        else:
-            peak, src = 0.5 * 148 * 128 * 2 * 1.965e-3 * 2, 'nominal fp32 FFMA peak (no tensor cores in fp32 mode)'
-        ach = d['work_per_step'] / (d['ms_per_step'] * 1e-3) / 1e12
-        # dram__bytes_read.sum + dram__bytes_write.sum per launch, averaged over the 24 3x3 conv launches
-        # of one step in the ncu --set full capture summarised in profiles/r01_conv_step_ncu_final.md
-        traffic = 290.4e6 if (dom == 'conv_tc' and a.size == 2048 and a.tile_size == 512 and world == 1
-                              and a.precision == 'fp16') else None
-        burst = peaks.get('bf16_tflops') if a.precision in ('bf16', 'fp16', 'tc32') else None
-        roofline = {'bound': 'tensor', 'kernel': 'conv_tc2_kernel' if dom == 'conv_tc' else 'conv3x3_kernel',
-                    'achieved': ach, 'peak': peak, 'unit': 'TFLOP/s', 'frac': ach / peak,
-                    # the same against the burst figure of MEASURED_PEAKS.json (a kernel timed alone)
-                    'frac_of_burst_peak': (ach / burst) if burst else None,
-                    'traffic': traffic, 'traffic_source': 'profiles/r01_conv_step_ncu_final.md (ncu --set full, per launch)',
-                    'peak_source': src,
-                    'flops_per_launch': d['work_per_step'] / max(d['launch_groups_per_step'], 1),
-                    'avg_launch_ms': d['ms_per_step'] / max(d['launch_groups_per_step'], 1),
-                    'share_of_step': d['ms_per_step'] / (ms_timing / tsteps)}
+    # ---- roofline of the dominant kernel ---------------------------------------------------------------
+    roofline, breakdown = conv_roofline(w, min(a.steps, 3), a.precision, sm_mhz, sm_max)
 
     # Gram kernels against the HBM roofline: algorithmic bytes = every style layer's 16-bit feature
     # map read once (64.9 MB per 512x512 VGG-19 tile) over gram_tc_kernel + finalize time
     roofline_gram = None
-    if breakdown['gram']['ms_per_step'] > 0 and a.tile_size == 512 and a.precision != 'fp32':
+    if breakdown['gram']['ms_per_step'] > 0 and a.tile_size == 512 and a.precision in ('fp16', 'bf16'):
         tiles_here = -(-(((a.size - 1) // a.tile_size + 1) ** 2) // world)
         gbytes = 64.9e6 * tiles_here
         ach = gbytes / (breakdown['gram']['ms_per_step'] * 1e-3) / 1e9
@@ -479,6 +580,40 @@ def run_engine(a):
                          'achieved': ach, 'peak': hbm, 'unit': 'GB/s', 'frac': ach / hbm,
                          'traffic': None, 'algorithmic_bytes_per_step': gbytes,
                          'peak_source': 'MEASURED_PEAKS.json hbm_gbs' if peaks else 'fallback 6650 (recipe)'}
+    w.close()
+
+    # ---- further records: the reference-precision tensor-core mode and BASELINE config 4 -------------
+    records = []
+    if not a.no_extra:
+        k, wu = min(a.steps, 6), 3
+        try:
+            w2 = Workload(rank, world, local, a.size, a.tile_size, 'vgg19.prototxt', a.optimizer, 'tc32')
+            v2, ms2, h2 = measure(w2, k, wu)
+            roof2, bd2 = conv_roofline(w2, 2, 'tc32', sm_mhz, sm_max)
+            w2.close()
+            records.append({
+                'record': 'cfg3 in the tc32 mode (fp32 storage, split fp16 hi+lo tensor-core operands, '
+                          'chained fp32 accumulation): the reference-precision tensor-core path',
+                'value': v2, 'unit': 'iterations/s', 'ms_per_step': ms2, 'steps': k, 'warmup': wu,
+                'dtype': 'f32 storage / split f16 operands / f32 accumulate', 'roofline': roof2,
+                'breakdown_ms': {kk: vv['ms_per_step'] for kk, vv in bd2.items()},
+                'tolerance': 'tests/test_gpu_parity_configs.py: loss 1e-4, gradient relative L2 <= 3e-3 '
+                             'vs the CPU oracle at 256^2 .. 2048^2 (measured 3e-4 .. 1.3e-3, the fp32 '
+                             'SIMT mode measures 1e-4 .. 1.0e-3)'})
+        except Exception as e:                                   # a reporting extra
+            records.append({'record': 'cfg3 tc32', 'unavailable': repr(e)[:300]})
+        try:
+            w4 = Workload(rank, world, local, 4096, 1024, 'vgg19_avgpool.prototxt', 'lbfgs', a.precision,
+                          tv_weight=5.0)
+            v4, ms4, h4 = measure(w4, k, wu)
+            w4.close()
+            records.append({
+                'record': 'cfg4: 4096x4096 image, 16 tiles of 1024px, vgg19_avgpool.prototxt, 5 style + 1 '
+                          'content layer, L-BFGS (device-resident memory), tv-weight 5',
+                'value': v4, 'unit': 'iterations/s', 'ms_per_step': ms4, 'host_enqueue_ms_per_step': h4,
+                'steps': k, 'warmup': wu, 'precision': a.precision})
+        except Exception as e:
+            records.append({'record': 'cfg4', 'unavailable': repr(e)[:300]})
 
     # ---- CPU baseline (rank 0, N = 1) ---------------------------------------------------------------
     cpu = None
@@ -506,16 +641,20 @@ def run_engine(a):
         cfg = workload_config(a, world)
         cfg['l2'] = ('no explicit flush: one step streams the %d MB of image + optimizer state and '
                      '~%d MB of activations per tile, both larger than the 126 MB L2'
-                     % (6 * n * 4 >> 20, 304 if a.precision == 'fp32' else 152))
+                     % (6 * n * 4 >> 20, 304 if a.precision in ('fp32', 'tc32') else 152))
         cfg['precision'] = a.precision
         line = {
             'metric': METRIC, 'value': value, 'unit': 'iterations/s', 'n_gpus': world,
             'steps': a.steps, 'warmup': a.warmup, 'ms_per_step': ms / a.steps,
             'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
             'dtype': {'bf16': 'bf16', 'fp16': 'f16 forward / bf16 backward', 'fp32': 'f32',
-                      'tc32': 'f32 storage, split f16 hi+lo tensor-core operands, f32 accumulate'}[a.precision], 'data': 'synthetic', 'config': cfg,
-            'clocks': clocks, 'e2e': e2e, 'gpu_launches': launches, 'roofline': roofline,
-            'roofline_gram': roofline_gram,
+                      'tc32': 'f32 storage, split f16 hi+lo tensor-core operands, f32 accumulate'}[a.precision],
+            'data': 'synthetic', 'config': cfg,
+            'step_is': 'one pass of the loop body (style_transfer.py:777-821): roll, 16-tile objective, '
+                       'regularisers, optimizer step, update-size / TV statistics, uint8 picture',
+            'clocks': clocks, 'e2e': e2e, 'gpu_launches': launches,
+            'host_enqueue_ms_per_step': host_ms / a.steps, 'roofline': roofline,
+            'roofline_gram': roofline_gram, 'records': records,
             'cpu_baseline': cpu, 'breakdown': breakdown,
             'tile_eval_ms': breakdown and sum(v['ms_per_step'] for k, v in breakdown.items()
                                               if k != 'image') / cfg['tiles_per_gpu'],

@@ -141,13 +141,37 @@ ST_API int st_eval_sc_grad_tiles(st_ctx* ctx, const float* img_dev, int H, int W
                           int tile_size, int rank, int world, int n_specs,
                           const st_loss_spec* specs, double* loss_accum_dev,
                           float* packed_grad_dev, st_stream stream);
+/* The same for the local tiles (slots) [slot_first, slot_first + slot_count) of this rank only
+ * (slot_count < 0: to the end): lets a caller overlap the upload of the image rows the later tiles
+ * read with the evaluation of the earlier ones.  Tiles that share a call share kernel launches. */
+ST_API int st_eval_sc_grad_tile_range(st_ctx* ctx, const float* img_dev, int H, int W, int roll_y,
+                               int roll_x, int tile_size, int rank, int world, int slot_first,
+                               int slot_count, int n_specs, const st_loss_spec* specs,
+                               double* loss_accum_dev, float* packed_grad_dev, st_stream stream);
 /* Geometry of the tile grid used above (style_transfer.py:619-631). */
 ST_API int st_tile_grid(int H, int W, int tile_size, int* ntiles_y, int* ntiles_x, int* tile_h_max,
                  int* tile_w_max);
-/* Pastes the packed gradient tiles of all ranks ([world][tiles_per_rank][3][thmax][twmax], the
- * all-gather result) into grad_dev [3][H][W] in the UN-rolled frame (:642 + the roll-back :805). */
+/* ---- the exchange step (style_transfer.py:635-643: the master's resp_q.get() loop) ---------------
+ * Layout of one rank's chunk of the exchange buffer, st_packed_floats() floats:
+ *   [tiles_per_rank][3][tile_h_max][tile_w_max] gradient tiles (what st_eval_sc_grad_tiles writes),
+ *   padded to a multiple of four floats, then a four-float tail whose first eight bytes hold the
+ *   rank's loss as a double (pass the tail's address as loss_accum_dev to st_eval_sc_grad_tiles).
+ * One all-gather of these chunks moves gradients AND losses: a single collective per evaluation.
+ * st_comm_unique_id (rank 0) / st_comm_init (every rank, same id) create the NCCL communicator of a
+ * context -- libnccl.so.2 is resolved at run time, single-GPU use never needs it; st_allgather_grad
+ * enqueues ncclAllGather on `stream`; packed_all_dev receives world chunks in rank order. */
+#define ST_COMM_ID_BYTES 128
+ST_API size_t st_packed_floats(int H, int W, int tile_size, int world);
+ST_API int st_comm_unique_id(void* id_out /* ST_COMM_ID_BYTES */);
+ST_API int st_comm_init(st_ctx* ctx, const void* id, int rank, int world);
+ST_API int st_comm_destroy(st_ctx* ctx);
+ST_API int st_allgather_grad(st_ctx* ctx, const float* packed_local_dev, float* packed_all_dev,
+                             size_t floats_per_rank, st_stream stream);
+/* Pastes the gradient tiles of all ranks (the all-gather result: world chunks as above; world = 1:
+ * the local chunk itself) into grad_dev [3][H][W] in the UN-rolled frame (:642 + the roll-back :805)
+ * and adds the ranks' losses, in rank order, to *loss_accum_dev (may be NULL). */
 ST_API int st_unpack_grad(const float* packed_all_dev, int H, int W, int roll_y, int roll_x, int tile_size,
-                   int world, float* grad_dev, st_stream stream);
+                   int world, float* grad_dev, double* loss_accum_dev, st_stream stream);
 
 /* ---- Gram of a full feature map (preprocess_images, style_transfer.py:534; num_utils.py:143) -- */
 ST_API int st_gram(st_ctx* ctx, const float* feat_dev, int c, int hw, float* gram_dev, st_stream stream);
@@ -164,7 +188,8 @@ ST_API int st_regularizers(const float* img_dev, int H, int W, const float mean[
                     st_stream stream);
 
 /* st_unpack_grad followed by st_regularizers in ONE pass over the image: grad_dev is written (not
- * accumulated), the gradient tiles are gathered from the all-gather buffer on the fly. */
+ * accumulated), the gradient tiles are gathered from the all-gather buffer on the fly, the ranks'
+ * losses in the chunk tails and the regulariser terms are added to *loss_accum_dev. */
 ST_API int st_unpack_regularize(const float* packed_all_dev, const float* img_dev, int H, int W,
                          int roll_y, int roll_x, int tile_size, int world, const float mean[3],
                          float tv_w, float tv_beta, float p_w, float p_pow, const float* aux_dev,

@@ -12,6 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libstyle_b200.so')
 
 ST_PREC_FP32, ST_PREC_BF16, ST_PREC_FP16, ST_PREC_TC32 = 0, 1, 2, 3
+ST_COMM_ID_BYTES = 128
 ST_CONV3X3, ST_POOL_MAX, ST_POOL_AVE = 0, 1, 2
 
 
@@ -52,8 +53,15 @@ PROTOTYPES = {
                                   _vp, _l, _l, _vp]),
     'st_eval_sc_grad_tiles': (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, C.POINTER(LossSpec),
                                    _vp, _vp, _vp]),
+    'st_eval_sc_grad_tile_range': (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i,
+                                        C.POINTER(LossSpec), _vp, _vp, _vp]),
     'st_tile_grid': (_i, [_i, _i, _i, _ip, _ip, _ip, _ip]),
-    'st_unpack_grad': (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
+    'st_unpack_grad': (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
+    'st_packed_floats': (_sz, [_i, _i, _i, _i]),
+    'st_comm_unique_id': (_i, [_vp]),
+    'st_comm_init': (_i, [_vp, _vp, _i, _i]),
+    'st_comm_destroy': (_i, [_vp]),
+    'st_allgather_grad': (_i, [_vp, _vp, _vp, _sz, _vp]),
     'st_gram': (_i, [_vp, _vp, _i, _i, _vp, _vp]),
     'st_regularizers': (_i, [_vp, _i, _i, C.POINTER(_f), _f, _f, _f, _f, _vp, _f, _i, _i, _vp,
                              _vp, _vp]),

@@ -43,6 +43,22 @@ extern std::atomic<uint64_t> g_launches;
     ST_CUDA(cudaGetLastError());                                       \
   } while (0)
 
+// The same with programmatic dependent launch: the kernel may be scheduled while its predecessor in
+// the stream is still draining (its prologue overlaps the predecessor's tail); the kernel MUST
+// execute griddepcontrol.wait before it touches global memory the predecessor wrote.
+#define ST_LAUNCH_PDL(kernel, grid, block, smem, strm_, pdl, ...)                            \
+  do {                                                                                     \
+    cudaLaunchConfig_t cfg_ = {};                                                          \
+    cfg_.gridDim = dim3(grid), cfg_.blockDim = dim3(block);                                \
+    cfg_.dynamicSmemBytes = (smem), cfg_.stream = (strm_);                                 \
+    cudaLaunchAttribute attr_[1];                                                          \
+    attr_[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                      \
+    attr_[0].val.programmaticStreamSerializationAllowed = (pdl) ? 1 : 0;                   \
+    cfg_.attrs = attr_, cfg_.numAttrs = 1;                                                 \
+    st::g_launches.fetch_add(1, std::memory_order_relaxed);                                \
+    ST_CUDA(cudaLaunchKernelEx(&cfg_, kernel, __VA_ARGS__));                               \
+  } while (0)
+
 inline int cdiv(long a, long b) { return (int)((a + b - 1) / b); }
 
 // ---- opt-in per-kernel timing (st_timing_* in style_b200.h) -------------------------------------

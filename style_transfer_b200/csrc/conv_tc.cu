@@ -506,6 +506,7 @@ int tc_init(TcContext& tc, int sm_count) {
   tc.pool_fusion = getenv("ST_NO_POOL_FUSION") == nullptr;
   tc.pix_rows_kernel = getenv("ST_NO_PIX_ROWS") == nullptr;
   tc.fwd_bits = getenv("ST_NO_FWD_BITS") == nullptr;
+  tc.pdl = getenv("ST_NO_PDL") == nullptr;
   if (const char* f = getenv("ST_TC_BN")) tc.force_bn = atoi(f);
   return ST_OK;
 }

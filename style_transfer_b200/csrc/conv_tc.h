@@ -38,6 +38,7 @@ struct TcContext {
   bool pix_rows_kernel = true;    // ST_NO_PIX_ROWS=1: first-layer backward through conv_tc2.cu instead
   bool fwd_bits = true;           // ST_NO_FWD_BITS=1: ReLU bit masks made from the activations by
                                   // relu_bits_from_act instead of the forward epilogues
+  bool pdl = true;                // ST_NO_PDL=1: no programmatic dependent launch of the conv kernels
   int force_bn = 0;               // ST_TC_BN=64|128|256
   int sm_count = 0;
   void* encode_fn = nullptr;   // cuTensorMapEncodeTiled, fetched through cudaGetDriverEntryPoint

@@ -420,6 +420,12 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constan
   cluster_sync();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // Programmatic dependent launch: everything above (barriers, TMEM, descriptor prefetch, the bias
+  // copy -- weights, never written by a predecessor) may run while the previous kernel of the
+  // stream drains; activations are only touched below.  The next kernel may be scheduled as soon as
+  // SMs free up (it blocks at its own griddepcontrol.wait until this grid has completed).
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 
   if (warp == 0) {
     // ===================================== A producer ============================================
@@ -1035,7 +1041,7 @@ int launch2r(TcContext& tc, const void* in, const void* wk, int wk_rows,
   // (split mode: a.cin counts the three K segments; the algorithmic flops are a third of the executed)
   TimerScope ts(s, EPI == kEpiAbs ? kTimeStyleGrad : (EPI == kEpiPix ? kTimeConvSimt : kTimeConvTc),
                 2.0 * TAPS * (k32 ? a.cin / 3 : a.cin) * (EPI == kEpiPix ? 3 : a.cout) * a.h * a.w * a.nb);
-  ST_LAUNCH(kern, 2 * pairs, kThreads2, smem_bytes, s, map_in, map_w, map_out, map_pool, a);
+  ST_LAUNCH_PDL(kern, 2 * pairs, kThreads2, smem_bytes, s, tc.pdl, map_in, map_w, map_out, map_pool, a);
   return ST_OK;
 }
 

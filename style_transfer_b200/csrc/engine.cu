@@ -1,5 +1,8 @@
 // libstyle_b200 engine: context, per-tile forward/backward plan and the extern "C" entry points
 // declared in include/style_b200.h.  See DESIGN.md for the data layout and the kernel list.
+#include <dlfcn.h>
+#include <nccl.h>
+
 #include <algorithm>
 #include <cmath>
 #include <cstring>
@@ -99,6 +102,8 @@ using namespace st;
 
 struct st_ctx {
   int device = 0, precision = 0, sm_count = 0;
+  void* comm = nullptr;      // ncclComm_t of st_comm_init (multi-GPU exchange), else null
+  int comm_rank = 0, comm_world = 1;
   size_t esize = 4;
   std::vector<LayerRt> layers;
   std::vector<BlobRt> blobs;
@@ -743,6 +748,7 @@ int st_destroy(st_ctx* ctx) {
   if (!ctx) return ST_OK;
   DeviceGuard guard(ctx->device);
   cudaDeviceSynchronize();
+  if (ctx->comm != nullptr) st_comm_destroy(ctx);
   for (LayerRt& l : ctx->layers) {
     cudaFree(l.w_fwd), cudaFree(l.w_bwd), cudaFree(l.bias), cudaFree(l.pool_mask);
     tc_free_weights(l.tc);
@@ -946,8 +952,17 @@ int st_eval_sc_grad_tiles(st_ctx* ctx, const float* img_dev, int H, int W, int r
                           int tile_size, int rank, int world, int n_specs,
                           const st_loss_spec* specs, double* loss_accum_dev,
                           float* packed_grad_dev, st_stream stream) {
+  return st_eval_sc_grad_tile_range(ctx, img_dev, H, W, roll_y, roll_x, tile_size, rank, world, 0, -1,
+                                    n_specs, specs, loss_accum_dev, packed_grad_dev, stream);
+}
+
+int st_eval_sc_grad_tile_range(st_ctx* ctx, const float* img_dev, int H, int W, int roll_y, int roll_x,
+                               int tile_size, int rank, int world, int slot_first, int slot_count,
+                               int n_specs, const st_loss_spec* specs, double* loss_accum_dev,
+                               float* packed_grad_dev, st_stream stream) {
   ST_GUARD(ctx);
   ST_REQUIRE(img_dev && loss_accum_dev && packed_grad_dev, "st_eval_sc_grad_tiles: null pointer");
+  ST_REQUIRE(slot_first >= 0, "st_eval_sc_grad_tile_range: negative first slot");
   ST_REQUIRE(H > 0 && W > 0 && tile_size > 0 && world > 0 && rank >= 0 && rank < world,
              "st_eval_sc_grad_tiles: bad geometry");
   const Grid g = tile_grid(H, W, tile_size);
@@ -964,9 +979,11 @@ int st_eval_sc_grad_tiles(st_ctx* ctx, const float* img_dev, int H, int W, int r
     const int sy = ty * g.th, sx = tx * g.tw;
     tiles.push_back({sy, sx, ty == g.nty - 1 ? H - sy : g.th, tx == g.ntx - 1 ? W - sx : g.tw});
   }
-  for (size_t first = 0; first < tiles.size();) {
+  const size_t slot_end = slot_count < 0 ? tiles.size()
+                                         : std::min(tiles.size(), (size_t)slot_first + (size_t)slot_count);
+  for (size_t first = (size_t)slot_first; first < slot_end;) {
     size_t last = first + 1;
-    while (last < tiles.size() && last - first < (size_t)ctx->max_batch &&
+    while (last < slot_end && last - first < (size_t)ctx->max_batch &&
            tiles[last].h == tiles[first].h && tiles[last].w == tiles[first].w)
       ++last;
     ImageBatch view{};
@@ -987,13 +1004,117 @@ int st_eval_sc_grad_tiles(st_ctx* ctx, const float* img_dev, int H, int W, int r
 }
 
 int st_unpack_grad(const float* packed_all_dev, int H, int W, int roll_y, int roll_x, int tile_size,
-                   int world, float* grad_dev, st_stream stream) {
+                   int world, float* grad_dev, double* loss_accum_dev, st_stream stream) {
   ST_REQUIRE(packed_all_dev && grad_dev && H > 0 && W > 0 && tile_size > 0 && world > 0,
              "st_unpack_grad: bad arguments");
   const Grid g = tile_grid(H, W, tile_size);
   const int tpr = (g.nty * g.ntx + world - 1) / world;
   return unpack_grad(packed_all_dev, H, W, roll_y, roll_x, g.nty, g.ntx, g.th, g.tw, g.thmax,
-                     g.twmax, world, tpr, grad_dev, (cudaStream_t)stream);
+                     g.twmax, world, tpr, grad_dev, loss_accum_dev, (cudaStream_t)stream);
+}
+
+size_t st_packed_floats(int H, int W, int tile_size, int world) {
+  if (H <= 0 || W <= 0 || tile_size <= 0 || world <= 0) return 0;
+  const Grid g = tile_grid(H, W, tile_size);
+  return packed_rank_stride((g.nty * g.ntx + world - 1) / world, g.thmax, g.twmax);
+}
+
+// ---- the exchange step: NCCL all-gather on the caller's stream -------------------------------------
+// libnccl is resolved at run time (the copy the process already holds -- torch's -- or the system
+// one): the library has no link-time dependency on it and single-GPU use never touches it.
+namespace {
+struct NcclApi {
+  void* handle = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+NcclApi g_nccl;
+int nccl_api(NcclApi** out) {
+  if (!g_nccl.handle) {
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) {
+      set_error(std::string("libnccl.so.2 cannot be loaded: ") + dlerror());
+      return ST_ERR_STATE;
+    }
+    g_nccl.GetUniqueId = (decltype(g_nccl.GetUniqueId))dlsym(h, "ncclGetUniqueId");
+    g_nccl.CommInitRank = (decltype(g_nccl.CommInitRank))dlsym(h, "ncclCommInitRank");
+    g_nccl.CommDestroy = (decltype(g_nccl.CommDestroy))dlsym(h, "ncclCommDestroy");
+    g_nccl.AllGather = (decltype(g_nccl.AllGather))dlsym(h, "ncclAllGather");
+    g_nccl.GetErrorString = (decltype(g_nccl.GetErrorString))dlsym(h, "ncclGetErrorString");
+    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.CommDestroy || !g_nccl.AllGather) {
+      set_error("libnccl.so.2 lacks an expected symbol");
+      return ST_ERR_STATE;
+    }
+    g_nccl.handle = h;
+  }
+  *out = &g_nccl;
+  return ST_OK;
+}
+#define ST_NCCL(api, call)                                                                   \
+  do {                                                                                       \
+    ncclResult_t r_ = (call);                                                                \
+    if (r_ != ncclSuccess) {                                                                 \
+      set_error(std::string(#call) + ": " +                                                  \
+                ((api)->GetErrorString ? (api)->GetErrorString(r_) : "NCCL error"));         \
+      return ST_ERR_CUDA;                                                                    \
+    }                                                                                        \
+  } while (0)
+}  // namespace
+
+int st_comm_unique_id(void* id_out) {
+  ST_REQUIRE(id_out != nullptr, "st_comm_unique_id: null pointer");
+  static_assert(sizeof(ncclUniqueId) == ST_COMM_ID_BYTES, "ncclUniqueId size");
+  NcclApi* api;
+  int rc = nccl_api(&api);
+  if (rc != ST_OK) return rc;
+  ST_NCCL(api, api->GetUniqueId(static_cast<ncclUniqueId*>(id_out)));
+  return ST_OK;
+}
+
+int st_comm_init(st_ctx* ctx, const void* id, int rank, int world) {
+  ST_GUARD(ctx);
+  ST_REQUIRE(id != nullptr && world >= 1 && rank >= 0 && rank < world, "st_comm_init: bad arguments");
+  ST_REQUIRE(ctx->comm == nullptr, "st_comm_init: the context already has a communicator");
+  NcclApi* api;
+  int rc = nccl_api(&api);
+  if (rc != ST_OK) return rc;
+  ncclUniqueId uid;
+  std::memcpy(&uid, id, sizeof(uid));
+  ncclComm_t comm = nullptr;
+  ST_NCCL(api, api->CommInitRank(&comm, world, uid, rank));
+  ctx->comm = comm, ctx->comm_rank = rank, ctx->comm_world = world;
+  return ST_OK;
+}
+
+int st_comm_destroy(st_ctx* ctx) {
+  ST_GUARD(ctx);
+  if (ctx->comm != nullptr) {
+    NcclApi* api;
+    int rc = nccl_api(&api);
+    if (rc != ST_OK) return rc;
+    ST_CUDA(cudaDeviceSynchronize());
+    ST_NCCL(api, api->CommDestroy(static_cast<ncclComm_t>(ctx->comm)));
+    ctx->comm = nullptr;
+  }
+  return ST_OK;
+}
+
+int st_allgather_grad(st_ctx* ctx, const float* packed_local_dev, float* packed_all_dev,
+                      size_t floats_per_rank, st_stream stream) {
+  ST_GUARD(ctx);
+  ST_REQUIRE(packed_local_dev && packed_all_dev && floats_per_rank > 0, "st_allgather_grad: bad arguments");
+  ST_REQUIRE(ctx->comm != nullptr, "st_allgather_grad: no communicator (st_comm_init)");
+  NcclApi* api;
+  int rc = nccl_api(&api);
+  if (rc != ST_OK) return rc;
+  ST_NCCL(api, api->AllGather(packed_local_dev, packed_all_dev, floats_per_rank, ncclFloat,
+                              static_cast<ncclComm_t>(ctx->comm), (cudaStream_t)stream));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return ST_OK;
 }
 
 int st_gram(st_ctx* ctx, const float* feat_dev, int c, int hw, float* gram_dev, st_stream stream) {

@@ -126,9 +126,13 @@ int nhwc_to_nchw_f32(const T* in, float* out, int hw, int c, cudaStream_t s);
 int nchw_to_nhwc_f32(const float* in, float* out, int hw, int c, cudaStream_t s);
 
 // ---- whole-image kernels -------------------------------------------------------------------------
+// floats of one rank's chunk of the exchange buffer: the tiles, padded to a multiple of four, plus a
+// four-float tail that carries the rank's loss as a double
+size_t packed_rank_stride(int tiles_per_rank, int thmax, int twmax);
+// loss_accum (optional) += the losses in the tails of the ranks' chunks, in rank order
 int unpack_grad(const float* packed, int H, int W, int roll_y, int roll_x, int nty, int ntx,
                 int th, int tw, int thmax, int twmax, int world, int tiles_per_rank, float* grad,
-                cudaStream_t s);
+                double* loss_accum, cudaStream_t s);
 int regularizers(const float* img, int H, int W, float m0, float m1, float m2, float tv_w,
                  float tv_beta, float p_w, float p_pow, const float* aux, float aux_w, int roll_y,
                  int roll_x, double* loss_accum, float* grad, ReduceScratch rs, cudaStream_t s);

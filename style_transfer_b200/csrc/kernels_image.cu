@@ -15,12 +15,28 @@ static inline int ew_grid(size_t work_items, int block) {
 }
 
 // -----------------------------------------------------------------------------------------------------
+// Exchange buffer of one rank: [tiles_per_rank][3][thmax][twmax] floats, padded to a multiple of four,
+// followed by a four-float tail whose first eight bytes are the rank's loss (a double).  The
+// all-gather result is `world` such chunks; one collective carries gradients and losses.
+// -----------------------------------------------------------------------------------------------------
+size_t packed_rank_stride(int tiles_per_rank, int thmax, int twmax) {
+  const size_t tiles = (size_t)tiles_per_rank * 3 * thmax * twmax;
+  return (tiles + 3) / 4 * 4 + 4;
+}
+__device__ __forceinline__ double packed_loss_sum(const float* packed, int world, size_t rank_stride) {
+  double sum = 0.0;
+  for (int r = 0; r < world; ++r)
+    sum += *reinterpret_cast<const double*>(packed + (size_t)(r + 1) * rank_stride - 4);
+  return sum;
+}
+
+// -----------------------------------------------------------------------------------------------------
 // grad[c][y][x] (un-rolled frame) = packed tile gradient at rolled position ((y+ry) mod H, (x+rx) mod W)
 // -----------------------------------------------------------------------------------------------------
 __global__ void unpack_grad_kernel(const float* __restrict__ packed, int H, int W, int roll_y,
                                    int roll_x, int nty, int ntx, int th, int tw, int thmax,
-                                   int twmax, int world, int tiles_per_rank,
-                                   float* __restrict__ grad) {
+                                   int twmax, int world, size_t rank_stride,
+                                   float* __restrict__ grad, double* loss_accum) {
   // blockIdx.y = image row, blockIdx.z = plane: no per-element div/mod on 64-bit indices
   const int y = blockIdx.y, c = blockIdx.z;
   int yr = y + roll_y;                                     // host passes the roll reduced to [0, H)
@@ -33,18 +49,22 @@ __global__ void unpack_grad_kernel(const float* __restrict__ packed, int H, int 
     const int tx = min(xr / tw, ntx - 1);
     const int t = ty * ntx + tx;
     const int rank = t % world, slot = t / world;
-    const size_t base = ((size_t)(rank * tiles_per_rank + slot) * 3 + c) * thmax * twmax;
+    const size_t base = (size_t)rank * rank_stride + ((size_t)slot * 3 + c) * thmax * twmax;
     out[x] = packed[base + (size_t)(yr - ty * th) * twmax + (xr - tx * tw)];
   }
+  // the ranks' losses ride in the tails of their chunks: added in rank order by one thread
+  if (loss_accum != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0)
+    *loss_accum += packed_loss_sum(packed, world, rank_stride);
 }
 
 int unpack_grad(const float* packed, int H, int W, int roll_y, int roll_x, int nty, int ntx,
                 int th, int tw, int thmax, int twmax, int world, int tiles_per_rank, float* grad,
-                cudaStream_t s) {
+                double* loss_accum, cudaStream_t s) {
   TimerScope ts(s, kTimeImage, 8.0 * 3 * H * W);
   const int ry = ((roll_y % H) + H) % H, rx = ((roll_x % W) + W) % W;
   ST_LAUNCH(unpack_grad_kernel, dim3(cdiv(W, 256), H, 3), 256, 0, s, packed, H, W, ry, rx, nty, ntx,
-            th, tw, thmax, twmax, world, tiles_per_rank, grad);
+            th, tw, thmax, twmax, world, packed_rank_stride(tiles_per_rank, thmax, twmax), grad,
+            loss_accum);
   return ST_OK;
 }
 
@@ -98,6 +118,7 @@ constexpr int kRTW = 32, kRTH = 32, kRThreads = 256, kRRows = kRTH / (kRThreads 
 struct UnpackGeom {
   int roll_y, roll_x;          // reduced to [0, H) x [0, W)
   int nty, ntx, th, tw, thmax, twmax, world, tiles_per_rank;
+  size_t rank_stride;          // floats between the chunks of two ranks (packed_rank_stride)
   FastDiv div_th, div_tw, div_world;
 };
 struct RegTiles {
@@ -184,7 +205,7 @@ regularizers_kernel(const float* __restrict__ img, int H, int W, float m0, float
         const int tyy = min((int)ug.div_th.div(yr), ug.nty - 1);
         const int t = tyy * ug.ntx + txx;
         const int slot = (int)ug.div_world.div(t), rank = t - slot * ug.world;
-        const size_t pb = ((size_t)(rank * ug.tiles_per_rank + slot) * 3 + c) * ug.thmax * ug.twmax;
+        const size_t pb = (size_t)rank * ug.rank_stride + ((size_t)slot * 3 + c) * ug.thmax * ug.twmax;
         base_k[k] = packed[pb + (size_t)(yr - tyy * ug.th) * ug.twmax + (xr - txx * ug.tw)];
       } else {
         base_k[k] = grad[((size_t)c * H + y) * W + x];
@@ -237,7 +258,8 @@ regularizers_kernel(const float* __restrict__ img, int H, int W, float m0, float
     if (++since_flush == 4) v[0] += (double)part, part = 0.f, since_flush = 0;
   }
   v[0] += (double)part;
-  if (grid_reduce<1>(v, rs.partials, rs.counter)) atomicAdd(loss_accum, v[0]);
+  if (grid_reduce<1>(v, rs.partials, rs.counter))
+    atomicAdd(loss_accum, PACKED ? v[0] + packed_loss_sum(packed, ug.world, ug.rank_stride) : v[0]);
 }
 
 static int launch_regularizers(const float* img, int H, int W, float m0, float m1, float m2,
@@ -276,7 +298,8 @@ int unpack_regularizers(const float* packed, int H, int W, int nty, int ntx, int
                         float p_pow, const float* aux, float aux_w, int roll_y, int roll_x,
                         double* loss_accum, float* grad, ReduceScratch rs, cudaStream_t s) {
   UnpackGeom ug{((roll_y % H) + H) % H, ((roll_x % W) + W) % W, nty, ntx, th, tw, thmax, twmax,
-                world, tiles_per_rank, FastDiv(th), FastDiv(tw), FastDiv(world)};
+                world, tiles_per_rank, packed_rank_stride(tiles_per_rank, thmax, twmax),
+                FastDiv(th), FastDiv(tw), FastDiv(world)};
   return launch_regularizers(img, H, W, m0, m1, m2, tv_w, tv_beta, p_w, p_pow, aux, aux_w, roll_y,
                              roll_x, loss_accum, grad, packed, ug, rs, s);
 }

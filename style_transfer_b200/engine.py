@@ -83,6 +83,8 @@ class TileEngine:
         self._loss = torch.zeros(1, dtype=torch.float64, device=self.device)
         self._packed = None
         self._packed_all = None
+        self._comm_ready = False
+        self._host_img, self._copy_stream, self._slabs = None, None, None
 
     def __del__(self):
         ctx, self.ctx = getattr(self, 'ctx', None), None
@@ -316,17 +318,34 @@ class TileEngine:
         layers = self.ordered_layers(content_layers, style_layers, dd_layers)
         specs = self._specs(layers, content_layers, style_layers, dd_layers, layer_weights,
                             content_weight, style_weight, dd_weight)
-        shape = sharding.packed_shape(H, W, tile_size, self.world)
-        if self._packed is None or self._packed.shape != shape:
-            self._packed = torch.zeros(shape, dtype=torch.float32, device=self.device)
+        nfl = sharding.packed_floats(H, W, tile_size, self.world)
+        if self._packed is None or self._packed.numel() != nfl:
+            self._packed = torch.zeros(nfl, dtype=torch.float32, device=self.device)
+            self._packed_all = (torch.empty((self.world, nfl), dtype=torch.float32, device=self.device)
+                                if self.world > 1 else None)
+        # this rank's loss accumulates in the tail of its chunk: gradients and losses travel in ONE
+        # all-gather
+        self._packed[-4:].zero_()
+        tail = C.c_void_p(self._packed.data_ptr() + (nfl - 4) * 4)
+        staged, self._host_img = self._host_img, None
+        if staged is not None and staged.shape == img.shape:
+            self._eval_tiles_from_host(staged, img, ry, rx, tile_size, layers, specs, tail)
+        else:
+            _lib.call('st_eval_sc_grad_tiles', self.ctx, _ptr(img), H, W, ry, rx, tile_size,
+                      self.rank, self.world, len(layers), specs, tail, _ptr(self._packed), _stream())
+        if self.world == 1:
+            packed_all = self._packed
+        elif self._comm_ready:
+            packed_all = self._packed_all
+            _lib.call('st_allgather_grad', self.ctx, _ptr(self._packed), _ptr(packed_all), nfl,
+                      _stream())
+        else:
+            packed_all = sharding.exchange(self._packed, self.world, self.group)
         loss = torch.zeros(1, dtype=torch.float64, device=self.device)
-        _lib.call('st_eval_sc_grad_tiles', self.ctx, _ptr(img), H, W, ry, rx, tile_size, self.rank,
-                  self.world, len(layers), specs, _ptr(loss), _ptr(self._packed), _stream())
-        packed_all, loss = sharding.exchange(self._packed, loss, self.world, self.group)
         grad = torch.empty_like(img)
         if regularizers is None:
             _lib.call('st_unpack_grad', _ptr(packed_all), H, W, ry, rx, tile_size, self.world,
-                      _ptr(grad), _stream())
+                      _ptr(grad), _ptr(loss), _stream())
         else:
             # StyleTransfer.eval_loss_and_grad's full-image terms (:700-736) in the same pass
             mean, tv_w, tv_beta, p_w, p_pow, aux, aux_w = regularizers
@@ -335,6 +354,88 @@ class TileEngine:
                       C.c_void_p(aux.data_ptr()) if aux is not None else None, aux_w, _ptr(loss),
                       _ptr(grad), _stream())
         return loss, grad
+
+    # ---- image arriving from the host ----------------------------------------------------------
+    def stage_host_image(self, host_img):
+        """The next ``eval_sc_grad`` takes its image from ``host_img`` (pinned f32 [3,H,W], the
+        layout of ``self.img``) instead of the resident copy -- the situation of a caller that owns
+        the parameters on the host, as the reference's master process does.  One GPU: the rows the
+        first half of the tiles read are uploaded first and the second half streams in while those
+        tiles are being evaluated.  Several GPUs: every rank uploads only its 1/world slab of rows
+        through its own PCIe link and the slabs are all-gathered over NVLink."""
+        self._host_img = host_img
+
+    def _copy_rows(self, host_img, img, start, count):
+        """img[:, r] = host_img[:, r] for the circular row range [start, start + count) (mod H),
+        plane by plane (contiguous pinned -> device copies on the current stream)."""
+        H = img.shape[-2]
+        for r0, r1 in ((start, min(start + count, H)), (0, max(start + count - H, 0))):
+            if r1 > r0:
+                for c in range(img.shape[0]):
+                    img[c, r0:r1].copy_(host_img[c, r0:r1], non_blocking=True)
+
+    def _eval_tiles_from_host(self, host_img, img, ry, rx, tile_size, layers, specs, tail):
+        H, W = img.shape[-2:]
+        cur = torch.cuda.current_stream()
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+        cs = self._copy_stream
+        cs.wait_stream(cur)                   # earlier readers of the resident image are done
+        if self.world > 1 and H % self.world == 0:
+            import torch.distributed as dist
+            rows = H // self.world
+            if self._slabs is None or self._slabs.shape != (self.world, img.shape[0], rows, W):
+                self._slabs = torch.empty((self.world, img.shape[0], rows, W), dtype=torch.float32,
+                                          device=self.device)
+            with torch.cuda.stream(cs):
+                self._copy_rows(host_img[:, self.rank * rows:(self.rank + 1) * rows],
+                                self._slabs[self.rank], 0, rows)
+            cur.wait_stream(cs)
+            dist.all_gather_into_tensor(self._slabs.view(-1), self._slabs[self.rank].view(-1),
+                                        group=self.group)
+            img.view(img.shape[0], self.world, rows, W).copy_(self._slabs.permute(1, 0, 2, 3))
+            split = [(0, -1, None)]
+        else:
+            nty, ntx, th, _, _, _ = sharding.tile_grid(H, W, tile_size)
+            n_local = len(range(self.rank, nty * ntx, self.world))
+            rows_a = nty // 2 if self.world == 1 else 0
+            with torch.cuda.stream(cs):
+                if rows_a > 0:
+                    # rolled rows [0, rows_a * th) = un-rolled rows starting at (-ry) mod H
+                    self._copy_rows(host_img, img, (-ry) % H, rows_a * th)
+                    ev_a = torch.cuda.Event()
+                    ev_a.record(cs)
+                    self._copy_rows(host_img, img, (rows_a * th - ry) % H, H - rows_a * th)
+                else:
+                    self._copy_rows(host_img, img, 0, H)
+                ev_b = torch.cuda.Event()
+                ev_b.record(cs)
+            split = ([(0, rows_a * ntx, ev_a), (rows_a * ntx, n_local - rows_a * ntx, ev_b)]
+                     if rows_a > 0 else [(0, -1, ev_b)])
+        for first, count, ev in split:
+            if ev is not None:
+                cur.wait_event(ev)
+            _lib.call('st_eval_sc_grad_tile_range', self.ctx, _ptr(img), H, W, ry, rx, tile_size,
+                      self.rank, self.world, first, count, len(layers), specs, tail,
+                      _ptr(self._packed), _stream())
+
+    def init_comm(self):
+        """Creates the context's NCCL communicator (``st_comm_init``) so that the exchange step runs
+        from the C ABI on the caller's stream.  The 128-byte id is made by rank 0 and broadcast
+        through the ``torch.distributed`` group the ranks already share."""
+        if self.world == 1 or self._comm_ready:
+            return
+        import torch.distributed as dist
+        uid = torch.zeros(_lib.ST_COMM_ID_BYTES, dtype=torch.uint8)
+        if self.rank == 0:
+            buf = (C.c_ubyte * _lib.ST_COMM_ID_BYTES)()
+            _lib.call('st_comm_unique_id', buf)
+            uid = torch.frombuffer(bytearray(buf), dtype=torch.uint8).clone()
+        uid = uid.to(self.device)
+        dist.broadcast(uid, src=0, group=self.group)
+        host = bytes(uid.cpu().numpy().tobytes())
+        _lib.call('st_comm_init', self.ctx, host, self.rank, self.world)
+        self._comm_ready = True
 
     # ---- roll -----------------------------------------------------------------------------------
     def roll_features(self, feats, xy, jitter_scale=32):

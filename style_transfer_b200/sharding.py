@@ -3,11 +3,14 @@ dispatcher (style_transfer.py:267-337, 614-645).
 
 Tile ``i`` of the row-major grid goes to rank ``i % world`` -- the round-robin of
 ``TileWorkerPool.request`` (:284-288), restarted at worker 0 for every evaluation (:290-298).  Each
-rank writes the gradients of its tiles into consecutive *slots* of a packed buffer
-``[tiles_per_rank][3][tile_h_max][tile_w_max]``; one all-gather stitches the image gradient and one
-all-reduce sums the loss (the reference's ``resp_q.get()`` loop, :639-643).  The functions here are
+rank writes the gradients of its tiles into consecutive *slots* of its chunk of the exchange buffer,
+``[tiles_per_rank][3][tile_h_max][tile_w_max]`` floats padded to a multiple of four plus a four-float
+tail that carries the rank's loss as a double; ONE all-gather of the chunks stitches the image
+gradient and delivers the losses (the reference's ``resp_q.get()`` loop, :639-643).  On the GPU the
+collective is ``st_allgather_grad`` (ncclAllGather issued from the C ABI); the functions here are
 pure host logic (they run on CPU tensors with the gloo backend too); the CUDA side computes the
-same geometry in ``st_tile_grid`` / ``st_eval_sc_grad_tiles`` / ``st_unpack_grad``.
+same geometry in ``st_tile_grid`` / ``st_packed_floats`` / ``st_eval_sc_grad_tiles`` /
+``st_unpack_grad``.
 """
 
 import numpy as np
@@ -45,26 +48,44 @@ def packed_shape(H, W, tile_size, world):
     return (per_rank, 3, thmax, twmax)
 
 
-def exchange(packed, loss, world, group=None):
-    """All-gather of the packed gradient tiles + all-reduce(sum) of the loss.  Returns
-    (packed_all [world, tiles_per_rank, 3, thmax, twmax], loss).  ``world == 1`` is a no-op."""
+def packed_floats(H, W, tile_size, world):
+    """Floats of one rank's chunk (``st_packed_floats``): tiles, padded to 4, + the 4-float tail."""
+    tiles = int(np.prod(packed_shape(H, W, tile_size, world)))
+    return (tiles + 3) // 4 * 4 + 4
+
+
+def tiles_view(chunk, H, W, tile_size, world):
+    """[tiles_per_rank, 3, thmax, twmax] view of the tile part of one chunk (numpy or torch)."""
+    shape = packed_shape(H, W, tile_size, world)
+    return chunk[:int(np.prod(shape))].reshape(shape)
+
+
+def loss_view(chunk):
+    """The loss (one float64) in the tail of a chunk: numpy array or torch tensor view."""
+    return chunk[-4:-2].view(np.float64) if isinstance(chunk, np.ndarray) else \
+        chunk[-4:-2].view(__import__('torch').float64)
+
+
+def exchange(chunk, world, group=None):
+    """All-gather of the ranks' chunks through ``torch.distributed`` (any backend: the CPU tests run
+    it over gloo).  Returns [world, floats_per_rank]; ``world == 1`` is a no-op."""
     if world == 1:
-        return packed.reshape((1,) + tuple(packed.shape)), loss
+        return chunk.reshape((1,) + tuple(chunk.shape))
     import torch
     import torch.distributed as dist
-    shape = tuple(packed.shape)
-    flat = torch.empty((world * shape[0],) + shape[1:], dtype=packed.dtype, device=packed.device)
-    dist.all_gather_into_tensor(flat, packed.contiguous(), group=group)   # rank-major concatenation
-    dist.all_reduce(loss, group=group)
-    return flat.view((world,) + shape), loss
+    flat = torch.empty(world * chunk.numel(), dtype=chunk.dtype, device=chunk.device)
+    dist.all_gather_into_tensor(flat, chunk.contiguous().view(-1), group=group)   # rank-major
+    return flat.view((world,) + tuple(chunk.shape))
 
 
 def unpack_numpy(packed_all, H, W, tile_size, roll_y=0, roll_x=0):
-    """Host restatement of ``st_unpack_grad``: pastes the slots back (:642) and rolls the result
-    back into the un-rolled frame (:805).  Used by the CPU tests of the sharding logic."""
+    """Host restatement of ``st_unpack_grad``: pastes the slots back (:642), rolls the result back
+    into the un-rolled frame (:805) and sums the ranks' losses.  ``packed_all``: [world, floats]."""
     packed_all = np.asarray(packed_all)
     world = packed_all.shape[0]
     grad = np.zeros((3, H, W), dtype=packed_all.dtype)
+    tiles = [tiles_view(packed_all[r], H, W, tile_size, world) for r in range(world)]
     for t, (sy, sx, ey, ex) in enumerate(tile_boxes(H, W, tile_size)):
-        grad[:, sy:ey, sx:ex] = packed_all[t % world, t // world, :, :ey - sy, :ex - sx]
-    return np.roll(grad, (-roll_y, -roll_x), axis=(1, 2))
+        grad[:, sy:ey, sx:ex] = tiles[t % world][t // world, :, :ey - sy, :ex - sx]
+    loss = sum(float(loss_view(np.ascontiguousarray(packed_all[r]))[0]) for r in range(world))
+    return np.roll(grad, (-roll_y, -roll_x), axis=(1, 2)), loss

@@ -207,11 +207,17 @@ class StyleTransfer:
         return avg_img
 
     @staticmethod
-    def iter_stats(avg_img, old_img, stats):
-        """The update-size and total-variation statistics of :808-815 in one device pass
-        (st_iter_stats), which also performs ``old_img[...] = avg_img``; two doubles come back."""
+    def iter_stats_async(avg_img, old_img, stats):
+        """The update-size and total-variation sums of :808-815 in one device pass (st_iter_stats),
+        which also performs ``old_img[...] = avg_img``: ``stats`` (two device doubles) receives
+        sum |avg - old| and the sum of the squared periodic differences.  Nothing is synchronised."""
         h, w = avg_img.shape[-2:]
         _lib.call('st_iter_stats', _ptr(avg_img), _ptr(old_img), h, w, _ptr(stats), _stream())
-        s = stats.cpu().numpy()
+        return stats
+
+    @staticmethod
+    def iter_stats(avg_img, old_img, stats):
+        """(update_size, tv_loss) of :808-815 as Python floats (copies two doubles to the host)."""
+        s = StyleTransfer.iter_stats_async(avg_img, old_img, stats).cpu().numpy()
         n = float(avg_img.numel())
         return float(s[0] / n), float(np.sqrt(s[1] / n))

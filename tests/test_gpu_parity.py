@@ -199,28 +199,26 @@ def test_tile_sharding_matches_single_rank():
     args = ((8, -16), c_layers, s_layers, [], lw, {'conv3_2': 0.05}, {'conv2_1': 1.0}, {}, tile)
     loss1, grad1 = eng.eval_sc_grad(*args)
     grad1 = grad1.clone()
-    packs, losses = [], []
+    from style_transfer_b200 import sharding
+    nfl = sharding.packed_floats(H, W, tile, 2)
+    allp = torch.zeros((2, nfl), device='cuda')           # = the all-gather result
     for rank in range(2):
         eng.rank, eng.world, eng._packed = rank, 2, None
         layers = eng.ordered_layers(c_layers, s_layers)
         specs = eng._specs(layers, c_layers, s_layers, [], lw, args[5], args[6], {})
-        nty, ntx, thm, twm = C.c_int(), C.c_int(), C.c_int(), C.c_int()
-        _lib.call('st_tile_grid', H, W, tile, C.byref(nty), C.byref(ntx), C.byref(thm), C.byref(twm))
-        per_rank = (nty.value * ntx.value + 1) // 2
-        packed = torch.zeros((per_rank, 3, thm.value, twm.value), device='cuda')
-        loss = torch.zeros(1, dtype=torch.float64, device='cuda')
+        chunk = allp[rank]
         _lib.call('st_eval_sc_grad_tiles', eng.ctx, C.c_void_p(eng.img.data_ptr()), H, W, -16, 8,
-                  tile, rank, 2, len(layers), specs, C.c_void_p(loss.data_ptr()),
-                  C.c_void_p(packed.data_ptr()), None)
-        packs.append(packed)
-        losses.append(loss)
-    allp = torch.stack(packs).contiguous()
+                  tile, rank, 2, len(layers), specs,
+                  C.c_void_p(chunk.data_ptr() + (nfl - 4) * 4),           # the loss rides in the tail
+                  C.c_void_p(chunk.data_ptr()), None)
     grad2 = torch.empty_like(grad1)
+    loss2 = torch.zeros(1, dtype=torch.float64, device='cuda')
     _lib.call('st_unpack_grad', C.c_void_p(allp.data_ptr()), H, W, -16, 8, tile, 2,
-              C.c_void_p(grad2.data_ptr()), None)
+              C.c_void_p(grad2.data_ptr()), C.c_void_p(loss2.data_ptr()), None)
     torch.cuda.synchronize()
     assert torch.equal(grad1, grad2)
-    assert abs(float(losses[0] + losses[1]) - float(loss1)) <= 1e-9 * abs(float(loss1))
+    assert abs(float(loss2) - float(loss1)) <= 1e-9 * abs(float(loss1))
+    eng.rank, eng.world, eng._packed = 0, 1, None
 
 
 @pytest.mark.parametrize('beta,p', [(2.0, 6.0), (1.5, 2.0), (1.0, 1.0), (2.0, 3.5)])
@@ -405,8 +403,10 @@ def test_unpack_regularize_equals_unpack_then_regularize():
     from style_transfer_b200 import _lib, sharding
     rs = np.random.RandomState(8)
     H, W, tile, world = 70, 90, 32, 3
-    shape = sharding.packed_shape(H, W, tile, world)
-    packed = torch.from_numpy(rs.randn(world, *shape).astype(np.float32)).cuda()
+    nfl = sharding.packed_floats(H, W, tile, world)
+    packed = torch.from_numpy(rs.randn(world, nfl).astype(np.float32)).cuda()
+    for r in range(world):                                 # the loss tails: 0.5, 1.5, 2.5
+        sharding.loss_view(packed[r])[0] = r + 0.5
     img = torch.from_numpy(rand_img(rs, H, W)).cuda()
     aux = torch.from_numpy(rand_img(rs, H, W)).cuda()
     mean = (C.c_float * 3)(103.939, 116.779, 123.68)
@@ -415,7 +415,7 @@ def test_unpack_regularize_equals_unpack_then_regularize():
         l1 = torch.zeros(1, dtype=torch.float64, device='cuda')
         l2 = torch.zeros(1, dtype=torch.float64, device='cuda')
         p = lambda t: C.c_void_p(t.data_ptr())
-        _lib.call('st_unpack_grad', p(packed), H, W, roll_y, roll_x, tile, world, p(g1), None)
+        _lib.call('st_unpack_grad', p(packed), H, W, roll_y, roll_x, tile, world, p(g1), p(l1), None)
         _lib.call('st_regularizers', p(img), H, W, mean, 5.0, 2.0, 2.0, 6.0, p(aux), 10.0, roll_y,
                   roll_x, p(l1), p(g1), None)
         _lib.call('st_unpack_regularize', p(packed), p(img), H, W, roll_y, roll_x, tile, world, mean,

@@ -70,6 +70,9 @@ def test_tile_grid_matches_reference_arithmetic(H, W, tile):
             seen += [b for _, b in local]
         assert sorted(seen) == sorted(boxes)
         assert sharding.packed_shape(H, W, tile, world)[0] == -(-len(boxes) // world)
+        nfl = sharding.packed_floats(H, W, tile, world)
+        assert nfl == _lib.load().st_packed_floats(H, W, tile, world)
+        assert nfl % 4 == 0 and nfl >= int(np.prod(sharding.packed_shape(H, W, tile, world))) + 4
 
 
 def test_scale_ladder_and_weights():
@@ -142,17 +145,18 @@ def _dispatcher_worker(rank, world, port, H, W, tile, roll, out_path):
     layers = ora.ordered_layers(c_layers, s_layers)
     rolled = on.roll2_(img.copy(), np.array(roll))
     ora.roll_features_all(ora.w_contents, np.array(roll), 1)
-    packed = torch.zeros(sharding.packed_shape(H, W, tile, world), dtype=torch.float32)
-    loss = torch.zeros(1, dtype=torch.float64)
+    # this rank's chunk of the exchange buffer: tiles + the loss in its tail, ONE all-gather
+    chunk = torch.zeros(sharding.packed_floats(H, W, tile, world), dtype=torch.float32)
+    tiles = sharding.tiles_view(chunk, H, W, tile, world)
     for slot, (sy, sx, ey, ex) in sharding.local_tiles(H, W, tile, rank, world):
         l, g = ora.sc_grad_tile(np.ascontiguousarray(rolled[:, sy:ey, sx:ex]), np.array([sy, sx]),
                                 layers, c_layers, s_layers, [], lw, cw, sw, {})
-        packed[slot, :, :ey - sy, :ex - sx] = torch.from_numpy(g)
-        loss += l
-    packed_all, loss = sharding.exchange(packed, loss, world)
-    grad = sharding.unpack_numpy(packed_all.numpy(), H, W, tile, roll[1], roll[0])
+        tiles[slot, :, :ey - sy, :ex - sx] = torch.from_numpy(g)
+        sharding.loss_view(chunk)[0] += float(l)
+    packed_all = sharding.exchange(chunk, world)
+    grad, loss = sharding.unpack_numpy(packed_all.numpy(), H, W, tile, roll[1], roll[0])
     if rank == 0:
-        np.savez(out_path, grad=grad, loss=loss.numpy())
+        np.savez(out_path, grad=grad, loss=np.float64([loss]))
     dist.destroy_process_group()
 
 

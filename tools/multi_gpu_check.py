@@ -1,6 +1,9 @@
-"""Run under torchrun with N >= 2 GPUs: the N-rank evaluation (tiles dealt round-robin, NCCL
-all-gather of the packed gradient tiles, all-reduce of the loss) must equal the single-rank
-evaluation of the same image bit for bit (tiles are independent and the gather is a permutation)."""
+"""Run under torchrun with N >= 2 GPUs: the N-rank evaluation (tiles dealt round-robin, ONE NCCL
+all-gather of the ranks' chunks -- gradient tiles + loss -- issued from the C ABI by
+st_allgather_grad) must equal the single-rank evaluation of the same image bit for bit (tiles are
+independent and the gather is a permutation).  Also checks the host-image path (every rank uploads its
+slab, NVLink all-gather) against the resident image.  tests/test_gpu_multi.py runs this under
+torch.distributed.run when the machine has two GPUs."""
 import os
 import sys
 
@@ -27,11 +30,19 @@ def main():
     results = []
     for r, w in ((rank, world), (0, 1)):
         eng = TileEngine(net, params, mean=args.mean, device=local, precision='fp16', rank=r, world=w)
+        eng.init_comm()
+        assert w == 1 or eng._comm_ready
         st = StyleTransfer(eng, args)
         np.random.seed(0)
         st.init_first_scale(size, size)
         st.prepare([eng.pil_to_image(content)], [eng.pil_to_image(style)])
-        for _ in range(3):
+        for i in range(3):
+            if i == 2:                    # last step: the image comes from pinned host memory
+                host = torch.empty(eng.img.shape, dtype=torch.float32).pin_memory()
+                host.copy_(eng.img)
+                torch.cuda.synchronize()
+                eng.img.zero_()           # the resident copy must not be what gets evaluated
+                eng.stage_host_image(host)
             avg, loss = st.step()
         torch.cuda.synchronize()
         results.append((avg.clone(), float(loss)))
