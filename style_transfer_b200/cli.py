@@ -216,6 +216,7 @@ def main(argv=None):
             layer_weights = json.load(f)
     eng = TileEngine(net, params, mean=args.mean, device=device, precision=args.precision,
                      rank=rank, world=world)
+    eng.init_comm()              # multi-device: the exchange step runs from the C ABI over NCCL
     st = StyleTransfer(eng, args, layer_weights)
     st.state = state
     if args.display != 'none' and rank == 0:
