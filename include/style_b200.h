@@ -219,6 +219,10 @@ ST_API int st_iter_stats(const float* avg_dev, float* old_dev, int H, int W, dou
                          st_stream stream);
 ST_API int st_get_image_u8(const float* params_dev, int H, int W, const float mean[3], int bgr,
                            uint8_t* out_dev, st_stream stream);
+/* Both of the above in ONE pass over the averaged iterate (every array is read once): the statistics,
+ * old := avg, and -- unless pic_dev is NULL -- the uint8 picture of avg. */
+ST_API int st_output_step(const float* avg_dev, float* old_dev, int H, int W, const float mean[3],
+                          int bgr, double* stats_dev, uint8_t* pic_dev, st_stream stream);
 
 /* ---- scale change (num_utils.resize :90-108, optimizers.py:53-61, style_transfer.py:877-881) ------
  * Per-channel float resampling of in_dev f32 [channels][h][w] to out_dev f32 [channels][out_h][out_w]

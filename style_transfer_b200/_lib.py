@@ -76,6 +76,7 @@ PROTOTYPES = {
     'st_resample_coeffs': (_i, [_i, _i, _i, _ip, _vp, _vp]),
     'st_iter_stats': (_i, [_vp, _vp, _i, _i, _vp, _vp]),
     'st_get_image_u8': (_i, [_vp, _i, _i, C.POINTER(_f), _i, _vp, _vp]),
+    'st_output_step': (_i, [_vp, _vp, _i, _i, C.POINTER(_f), _i, _vp, _vp, _vp]),
     'st_dot': (_i, [_vp, _vp, _sz, _vp, _vp]),
     'st_asum': (_i, [_vp, _sz, _vp, _vp]),
     'st_axpby': (_i, [_f, _vp, _f, _vp, _sz, _vp]),

@@ -1290,6 +1290,16 @@ int st_iter_stats(const float* avg_dev, float* old_dev, int H, int W, double* st
   return rc != ST_OK ? rc : iter_stats(avg_dev, old_dev, H, W, stats_dev, rs, (cudaStream_t)stream);
 }
 
+int st_output_step(const float* avg_dev, float* old_dev, int H, int W, const float mean[3], int bgr,
+                   double* stats_dev, uint8_t* pic_dev, st_stream stream) {
+  ST_REQUIRE(avg_dev && old_dev && mean && stats_dev && H > 0 && W > 0, "st_output_step: bad arguments");
+  ReduceScratch rs;
+  int rc = global_scratch(&rs);
+  return rc != ST_OK ? rc
+                     : output_step(avg_dev, old_dev, H, W, mean[0], mean[1], mean[2], bgr != 0,
+                                   stats_dev, pic_dev, rs, (cudaStream_t)stream);
+}
+
 int st_get_image_u8(const float* params_dev, int H, int W, const float mean[3], int bgr,
                     uint8_t* out_dev, st_stream stream) {
   ST_REQUIRE(params_dev && mean && out_dev && H > 0 && W > 0, "st_get_image_u8: bad arguments");

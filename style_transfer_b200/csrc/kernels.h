@@ -152,6 +152,9 @@ int resample_pass(const float* in, float* out, int channels, int in_h, int in_w,
 // stats[0] = sum |avg - old|, stats[1] = sum of squared periodic forward differences; old := avg
 int iter_stats(const float* avg, float* old, int H, int W, double* stats, ReduceScratch rs,
                cudaStream_t s);
+// iter_stats + get_image_u8 (pic may be null) in one pass over the averaged iterate
+int output_step(const float* avg, float* old, int H, int W, float m0, float m1, float m2, bool bgr,
+                double* stats, uint8_t* pic, ReduceScratch rs, cudaStream_t s);
 // out[y][x][k] = uint8(clip(params[c][y][x] + mean[c], 0, 255)), c = bgr ? 2 - k : k
 int get_image_u8(const float* params, int H, int W, float m0, float m1, float m2, bool bgr,
                  uint8_t* out, cudaStream_t s);

@@ -2,6 +2,8 @@
 // TV / p-norm / aux regularisers (style_transfer.py:700-736, num_utils.py:74-82,150-162), the Adam
 // step with iterate averaging (optimizers.py:26-42) and the BLAS-1 pieces of L-BFGS
 // (optimizers.py:74-121).  All float32, coalesced along the image width, reductions in double.
+#include <cstdlib>
+
 #include "style_b200.h"
 #include "common.cuh"
 #include "kernels.h"
@@ -262,6 +264,94 @@ regularizers_kernel(const float* __restrict__ img, int H, int W, float m0, float
     atomicAdd(loss_accum, PACKED ? v[0] + packed_loss_sum(packed, ug.world, ug.rank_stride) : v[0]);
 }
 
+// The default configuration (tv_power = 2, p_power = 6 or no p-norm, no aux image) fused with the
+// gradient stitch, as a column-strip stencil: a thread owns four consecutive pixels of one plane and
+// walks kRsRows rows downwards with the rows above / below in registers, so the image is read once
+// with 16-byte accesses (+ two scalar neighbours per row that hit L1 / L2), the gradient tiles are
+// gathered with 16-byte loads and the result leaves with 16-byte stores.  Same per-pixel arithmetic
+// as regularizers_kernel<true, true> (which needed ~100 us for the 151 MB of a 2048^2 image: halo
+// staging through shared memory with scalar accesses, 0.24 of the HBM bandwidth).
+// Needs W, tile width and roll_x to be multiples of four.
+constexpr int kRsRows = 16, kRsThreads = 128;
+static const bool g_no_reg_strip = getenv("ST_NO_REG_STRIP") != nullptr;   // debugging switch
+__global__ void __launch_bounds__(kRsThreads)
+regularizers_strip_kernel(const float* __restrict__ img, int H, int W, float m0, float m1, float m2,
+                          float tv_w, float p_w, double* loss_accum, float* __restrict__ grad,
+                          const float* __restrict__ packed, UnpackGeom ug, ReduceScratch rs) {
+  const int x = (blockIdx.x * kRsThreads + threadIdx.x) * 4;
+  const int c = blockIdx.z, y0 = blockIdx.y * kRsRows;
+  const float inv = 1.f / 127.5f;
+  const float mean = c == 0 ? m0 : (c == 1 ? m1 : m2);
+  double total = 0.0;
+  if (x < W) {
+    const float* pl = img + (size_t)c * H * W;
+    const int xl = x == 0 ? W - 1 : x - 1, xr4 = x + 4 == W ? 0 : x + 4;
+    // column part of the gradient-tile lookup (the same for every row of the strip)
+    int xr = x + ug.roll_x;
+    xr = xr >= W ? xr - W : xr;
+    const int txx = min((int)ug.div_tw.div(xr), ug.ntx - 1);
+    const int xin = xr - txx * ug.tw;
+    auto ld4 = [&](int y) { return *reinterpret_cast<const float4*>(pl + (size_t)y * W + x); };
+    const int yu = y0 == 0 ? H - 1 : y0 - 1;
+    float4 up = ld4(yu), cur = ld4(y0);
+    up.x *= inv, up.y *= inv, up.z *= inv, up.w *= inv;
+    float part = 0.f;
+#pragma unroll 2
+    for (int r = 0; r < kRsRows; ++r) {
+      const int y = y0 + r;
+      if (y >= H) break;
+      const int yn = y + 1 == H ? 0 : y + 1;
+      const float4 nxt = ld4(yn);
+      const float left = pl[(size_t)y * W + xl] * inv, right = pl[(size_t)y * W + xr4] * inv;
+      // fused st_unpack_grad: this row of the strip inside its gradient tile
+      int yr = y + ug.roll_y;
+      yr = yr >= H ? yr - H : yr;
+      const int tyy = min((int)ug.div_th.div(yr), ug.nty - 1);
+      const int t = tyy * ug.ntx + txx;
+      const int slot = (int)ug.div_world.div(t), rank = t - slot * ug.world;
+      const size_t pb = (size_t)rank * ug.rank_stride + ((size_t)slot * 3 + c) * ug.thmax * ug.twmax;
+      const float4 base =
+          *reinterpret_cast<const float4*>(packed + pb + (size_t)(yr - tyy * ug.th) * ug.twmax + xin);
+      const float raw[4] = {cur.x, cur.y, cur.z, cur.w};
+      const float xs[6] = {left, cur.x * inv, cur.y * inv, cur.z * inv, cur.w * inv, right};
+      const float dn[4] = {nxt.x * inv, nxt.y * inv, nxt.z * inv, nxt.w * inv};
+      const float upv[4] = {up.x, up.y, up.z, up.w};
+      const float bs[4] = {base.x, base.y, base.z, base.w};
+      float out[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float xc = xs[i + 1];
+        // own term and the terms of the left / upper neighbour (their d/d(dx), d/d(dy) reach here)
+        const TvTerm t0 = tv_term<true>(xc, xs[i + 2], dn[i], 2.f);
+        const TvTerm tl = tv_term<true>(xs[i], xc, 0.f, 2.f);          // only ddx is used
+        const TvTerm tu = tv_term<true>(upv[i], 0.f, xc, 2.f);         // only ddy is used
+        float g = tv_w * (t0.ddx + t0.ddy - tl.ddx - tu.ddy);
+        float l = tv_w * t0.pw;
+        if (p_w != 0.f) {
+          const float a = (raw[i] + mean - 127.5f) * inv;
+          const float mag = fabsf(a), sgn = a > 0.f ? 1.f : (a < 0.f ? -1.f : 0.f);
+          const float a2 = a * a, m5 = a2 * a2 * mag;
+          l += p_w * m5 * mag, g += p_w * 6.f * sgn * m5;
+        }
+        out[i] = bs[i] + g;
+        part += l;
+      }
+      *reinterpret_cast<float4*>(grad + ((size_t)c * H + y) * W + x) =
+          make_float4(out[0], out[1], out[2], out[3]);
+      up = make_float4(xs[1], xs[2], xs[3], xs[4]);
+      cur = nxt;
+      if ((r & 3) == 3) total += (double)part, part = 0.f;
+    }
+    total += (double)part;
+  }
+  double v[1] = {total};
+  // blocks of all three planes reduce together: linear block index over (x, y, z)
+  if (grid_reduce_impl<1>(v, rs.partials, rs.counter,
+                          (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x,
+                          gridDim.x * gridDim.y * gridDim.z))
+    atomicAdd(loss_accum, v[0] + packed_loss_sum(packed, ug.world, ug.rank_stride));
+}
+
 static int launch_regularizers(const float* img, int H, int W, float m0, float m1, float m2,
                                float tv_w, float tv_beta, float p_w, float p_pow, const float* aux,
                                float aux_w, int roll_y, int roll_x, double* loss_accum, float* grad,
@@ -281,6 +371,14 @@ static int launch_regularizers(const float* img, int H, int W, float m0, float m
               aux_w, roll_y, roll_x, loss_accum, grad, packed, ug, rt, rs);
     return ST_OK;
   };
+  if (fast && packed && W % 4 == 0 && ug.tw % 4 == 0 && ug.roll_x % 4 == 0 && W >= 8 && !g_no_reg_strip) {
+    const dim3 sgrid(cdiv(W / 4, kRsThreads), cdiv(H, kRsRows), 3);
+    if ((long)sgrid.x * sgrid.y * sgrid.z <= kMaxReduceBlocks) {
+      ST_LAUNCH(regularizers_strip_kernel, sgrid, kRsThreads, 0, s, img, H, W, m0, m1, m2, tv_w, p_w,
+                loss_accum, grad, packed, ug, rs);
+      return ST_OK;
+    }
+  }
   if (fast) return packed ? launch(regularizers_kernel<true, true>) : launch(regularizers_kernel<true, false>);
   return packed ? launch(regularizers_kernel<false, true>) : launch(regularizers_kernel<false, false>);
 }
@@ -424,6 +522,92 @@ int get_image_u8(const float* params, int H, int W, float m0, float m1, float m2
   TimerScope ts(s, kTimeImage, 15.0 * H * W);
   ST_LAUNCH(get_image_u8_kernel, ew_grid((size_t)H * W, 256), 256, 0, s, params, H, W, m0, m1, m2,
             bgr ? 1 : 0, out);
+  return ST_OK;
+}
+
+// -----------------------------------------------------------------------------------------------------
+// The whole output step in ONE pass (st_output_step): statistics + old := avg + uint8 picture.  Each
+// thread owns four consecutive pixels of all three planes and walks kOsRows image rows downwards, so
+// that the lower neighbour of one row is the centre of the next (every array is read once: 12 B per
+// element + the 3 B/pixel picture; the two separate kernels above move 20 B per element with scalar
+// accesses and ran at 0.2 of the HBM bandwidth).  Needs W % 4 == 0.
+// -----------------------------------------------------------------------------------------------------
+constexpr int kOsRows = 8, kOsThreads = 128;
+__global__ void __launch_bounds__(kOsThreads)
+output_step_kernel(const float* __restrict__ avg, float* __restrict__ old, int H, int W, float m0,
+                   float m1, float m2, int bgr, double* stats, uint8_t* __restrict__ pic,
+                   ReduceScratch rs) {
+  const int x = (blockIdx.x * kOsThreads + threadIdx.x) * 4;
+  const int y0 = blockIdx.y * kOsRows;
+  const size_t plane = (size_t)H * W;
+  float ab = 0.f, sq = 0.f;
+  if (x < W) {
+    const int xr = x + 4 == W ? 0 : x + 4;                      // right neighbour of the last pixel
+    float4 cur[3], nxt[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) cur[c] = *reinterpret_cast<const float4*>(avg + c * plane + (size_t)y0 * W + x);
+    const float mean[3] = {m0, m1, m2};
+#pragma unroll 2
+    for (int r = 0; r < kOsRows; ++r) {
+      const int y = y0 + r;
+      if (y >= H) break;
+      const int yn = y + 1 == H ? 0 : y + 1;
+      float right[3];
+      float4 o[3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        nxt[c] = *reinterpret_cast<const float4*>(avg + c * plane + (size_t)yn * W + x);
+        right[c] = avg[c * plane + (size_t)y * W + xr];
+        o[c] = *reinterpret_cast<const float4*>(old + c * plane + (size_t)y * W + x);
+      }
+      uint32_t bytes[3][4];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float a[5] = {cur[c].x, cur[c].y, cur[c].z, cur[c].w, right[c]};
+        const float dn[4] = {nxt[c].x, nxt[c].y, nxt[c].z, nxt[c].w};
+        const float ov[4] = {o[c].x, o[c].y, o[c].z, o[c].w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float xd = a[i] - a[i + 1], yd = a[i] - dn[i];
+          ab += fabsf(a[i] - ov[i]);
+          sq += xd * xd + yd * yd;
+          bytes[c][i] = (uint32_t)(uint8_t)fminf(fmaxf(__fadd_rn(a[i], mean[c]), 0.f), 255.f);
+        }
+        *reinterpret_cast<float4*>(old + c * plane + (size_t)y * W + x) = cur[c];
+        cur[c] = nxt[c];
+      }
+      if (pic != nullptr) {
+        // picture channel k of a pixel is plane (bgr ? 2 - k : k); 4 pixels = 12 consecutive bytes
+        const int p0 = bgr ? 2 : 0, p2 = bgr ? 0 : 2;
+        uint32_t w3[3];
+        uint8_t b[12];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          b[3 * i] = (uint8_t)bytes[p0][i], b[3 * i + 1] = (uint8_t)bytes[1][i], b[3 * i + 2] = (uint8_t)bytes[p2][i];
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+          w3[j] = b[4 * j] | (b[4 * j + 1] << 8) | (b[4 * j + 2] << 16) | ((uint32_t)b[4 * j + 3] << 24);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(pic + ((size_t)y * W + x) * 3);
+        dst[0] = w3[0], dst[1] = w3[1], dst[2] = w3[2];
+      }
+    }
+  }
+  double v[2] = {(double)ab, (double)sq};
+  if (grid_reduce_2d<2>(v, rs.partials, rs.counter)) stats[0] = v[0], stats[1] = v[1];
+}
+
+int output_step(const float* avg, float* old, int H, int W, float m0, float m1, float m2, bool bgr,
+                double* stats, uint8_t* pic, ReduceScratch rs, cudaStream_t s) {
+  if (W % 4 != 0) {                        // odd widths: the two element-wise kernels
+    int rc = iter_stats(avg, old, H, W, stats, rs, s);
+    if (rc == ST_OK && pic != nullptr) rc = get_image_u8(avg, H, W, m0, m1, m2, bgr, pic, s);
+    return rc;
+  }
+  TimerScope ts(s, kTimeImage, 4.0 * 3 * H * W * 3 + 3.0 * H * W);
+  const dim3 grid(cdiv(W / 4, kOsThreads), cdiv(H, kOsRows));
+  ST_REQUIRE((long)grid.x * grid.y <= kMaxReduceBlocks / 2, "output_step: image too large for the reduction scratch");
+  ST_LAUNCH(output_step_kernel, grid, kOsThreads, 0, s, avg, old, H, W, m0, m1, m2, bgr ? 1 : 0, stats,
+            pic, rs);
   return ST_OK;
 }
 

@@ -215,6 +215,16 @@ class StyleTransfer:
         _lib.call('st_iter_stats', _ptr(avg_img), _ptr(old_img), h, w, _ptr(stats), _stream())
         return stats
 
+    def output_step(self, avg_img, old_img, stats, picture=True):
+        """The loop's output step (:808-821) in ONE device pass (st_output_step): the two statistic
+        sums into ``stats``, ``old_img[...] = avg_img`` and the uint8 RGB picture of ``avg_img``
+        (CaffeModel.get_image :378-386; returned as a CUDA tensor [H,W,3], or None)."""
+        h, w = avg_img.shape[-2:]
+        pic = torch.empty((h, w, 3), dtype=torch.uint8, device=avg_img.device) if picture else None
+        _lib.call('st_output_step', _ptr(avg_img), _ptr(old_img), h, w, self._mean,
+                  1 if self.model.bgr else 0, _ptr(stats), _ptr(pic), _stream())
+        return pic
+
     @staticmethod
     def iter_stats(avg_img, old_img, stats):
         """(update_size, tv_loss) of :808-815 as Python floats (copies two doubles to the host)."""

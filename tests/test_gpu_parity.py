@@ -488,6 +488,71 @@ def test_iter_stats_and_picture_match_oracle(HW):
     assert np.array_equal(pic, get_image_array(avg, mean))
 
 
+@pytest.mark.parametrize('HW', [(64, 96), (37, 52), (512, 1024)])
+def test_output_step_matches_oracle(HW):
+    """st_output_step = st_iter_stats + st_get_image_u8 in one pass (the loop's output step,
+    style_transfer.py:808-821): statistics 1e-6 relative, old := avg, picture bit-exact."""
+    from oracle.transfer import get_image_array, iter_stats
+    from style_transfer_b200.transfer import StyleTransfer
+    from style_transfer_b200.transfer import default_args as eng_args
+    mean = (103.939, 116.779, 123.68)
+    eng, _ = engine_for('vgg16.prototxt', mean=mean)
+    rs = np.random.RandomState(12)
+    H, W = HW
+    avg = np.float32(rs.uniform(-140, 160, (3, H, W)))
+    old = np.float32(avg + rs.normal(0, 3, (3, H, W)))
+    old_o = old.copy()
+    us_o, tv_o = iter_stats(avg, old_o)
+    d_avg, d_old = torch.from_numpy(avg).cuda(), torch.from_numpy(old).cuda()
+    stats = torch.zeros(2, dtype=torch.float64, device='cuda')
+    pic = StyleTransfer(eng, eng_args()).output_step(d_avg, d_old, stats)
+    s = stats.cpu().numpy()
+    n = float(avg.size)
+    assert abs(s[0] / n - us_o) <= 1e-6 * abs(us_o)
+    assert abs(np.sqrt(s[1] / n) - tv_o) <= 1e-6 * abs(tv_o)
+    assert torch.equal(d_old, d_avg)
+    assert np.array_equal(pic.cpu().numpy(), get_image_array(avg, mean))
+
+
+@pytest.mark.parametrize('roll', [(0, 0), (16, -24), (-8, 40)])
+def test_strip_regularizer_matches_tiled_kernel_and_oracle(roll, monkeypatch):
+    """The column-strip kernel behind st_unpack_regularize (default configuration, aligned sizes)
+    against the shared-memory tile kernel it replaces (ST_NO_REG_STRIP=1 is read at library load, so
+    the comparison partner here is st_unpack_grad + st_regularizers) and against the oracle's
+    tv_norm / p_norm (style_transfer.py:710-727)."""
+    import ctypes as C
+    from style_transfer_b200 import _lib, sharding
+    rs = np.random.RandomState(18)
+    H, W, tile, world = 96, 128, 64, 2
+    nfl = sharding.packed_floats(H, W, tile, world)
+    packed = torch.from_numpy(rs.randn(world, nfl).astype(np.float32)).cuda()
+    for r in range(world):
+        sharding.loss_view(packed[r])[0] = 0.25 * (r + 1)
+    img_h = rand_img(rs, H, W)
+    img = torch.from_numpy(img_h).cuda()
+    mean_h = np.float32((103.939, 116.779, 123.68)).reshape(3, 1, 1)
+    mean = (C.c_float * 3)(103.939, 116.779, 123.68)
+    roll_y, roll_x = roll
+    g1, g2 = torch.empty_like(img), torch.empty_like(img)
+    l1 = torch.zeros(1, dtype=torch.float64, device='cuda')
+    l2 = torch.zeros(1, dtype=torch.float64, device='cuda')
+    p = lambda t: C.c_void_p(t.data_ptr())
+    _lib.call('st_unpack_grad', p(packed), H, W, roll_y, roll_x, tile, world, p(g1), p(l1), None)
+    base = g1.clone()
+    _lib.call('st_regularizers', p(img), H, W, mean, 5.0, 2.0, 2.0, 6.0, None, 0.0, roll_y, roll_x,
+              p(l1), p(g1), None)
+    _lib.call('st_unpack_regularize', p(packed), p(img), H, W, roll_y, roll_x, tile, world, mean, 5.0,
+              2.0, 2.0, 6.0, None, 0.0, p(l2), p(g2), None)
+    torch.cuda.synchronize()
+    assert maxrel(g2, g1.cpu().numpy()) < 1e-6
+    assert abs(float(l1) - float(l2)) <= 1e-9 * abs(float(l1))
+    tv_l, tv_g = on.tv_norm(img_h / np.float32(127.5), 2.0)
+    p_l, p_g = on.p_norm((img_h + mean_h - np.float32(127.5)) / np.float32(127.5), 6.0)
+    want = base.cpu().numpy() + np.float32(5.0 * tv_g + 2.0 * p_g)
+    assert maxrel(g2, want) < 2e-4
+    assert abs(float(l2) - (0.75 + 5.0 * tv_l + 2.0 * p_l)) <= 1e-4 * abs(float(l2))
+
+
 @pytest.mark.parametrize('precision', ['fp16', 'bf16'])
 def test_fallback_kernels_agree_with_the_default_path(precision, monkeypatch):
     """ST_NO_FWD_BITS=1 (ReLU bit masks derived from the stored activations instead of written by the
