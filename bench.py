@@ -443,11 +443,22 @@ def run_engine(a):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms[0].item()), float(ms[1].item())
 
+    def host_enqueue_ms(fn, steps=6):
+        """Host time to ENQUEUE one step (no synchronisation inside): measured over a few steps on
+        an empty stream, so that the launch queue never fills up and blocks the host."""
+        torch.cuda.synchronize()
+        h0 = time.perf_counter()
+        for _ in range(steps):
+            fn()
+        h1 = time.perf_counter()
+        torch.cuda.synchronize()
+        return (h1 - h0) * 1e3 / steps
+
     def measure(w, steps, warmup):
         for _ in range(warmup):
             w.step()
-        ms, host_ms = timed(w.step, steps)
-        return steps / (ms * 1e-3), ms / steps, host_ms / steps
+        ms, _ = timed(w.step, steps)
+        return steps / (ms * 1e-3), ms / steps, host_enqueue_ms(w.step)
 
     def conv_roofline(w, steps, precision, sm_mhz, sm_max):
         """Per-launch CUDA events (st_timing_*) around every kernel group of `steps` steps."""
@@ -515,6 +526,7 @@ def run_engine(a):
         dist.all_reduce(lt)
     launches = int(lt.item())
     value = a.steps / (ms * 1e-3)
+    host_ms = host_enqueue_ms(w.step) * a.steps
     sm_mhz = clocks and clocks.get('sm_mhz')
     sm_max = clocks and clocks.get('sm_max_mhz')
     if world > 1:                      # every rank needs the same peak choice

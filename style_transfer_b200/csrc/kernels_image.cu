@@ -2,6 +2,7 @@
 // TV / p-norm / aux regularisers (style_transfer.py:700-736, num_utils.py:74-82,150-162), the Adam
 // step with iterate averaging (optimizers.py:26-42) and the BLAS-1 pieces of L-BFGS
 // (optimizers.py:74-121).  All float32, coalesced along the image width, reductions in double.
+#include <algorithm>
 #include <cstdlib>
 
 #include "style_b200.h"
@@ -847,9 +848,151 @@ __global__ void lb_commit_kernel(double* st, int n_corr) {
 }
 }  // namespace
 
+// ---- the same recursion as ONE cooperative kernel ---------------------------------------------------
+// 2 * n_corr + 2 dot products and as many vector updates are ~45 dependent launches; at 512^2 each
+// moves 3 MB and the launches (host enqueue + gaps) cost more than the work.  Here the blocks of one
+// co-resident grid walk the phases with grid-wide barriers: block partial sums go to `partials`, and
+// after the barrier every block adds them up in index order (the same double in every block).
+namespace {
+__device__ __forceinline__ void lb_grid_sync(unsigned* bar, unsigned& gen) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned target = (++gen) * gridDim.x;
+    atomicAdd(bar, 1u);
+    while (*reinterpret_cast<volatile unsigned*>(bar) < target) {
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+// sum over the grid of this block's `v`; every block returns the same value
+__device__ __forceinline__ double lb_grid_sum(double v, double* partials, unsigned* bar, unsigned& gen) {
+  __shared__ double sh[32];
+  __shared__ double total;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if (lane == 0) sh[warp] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double x = 0.0;
+    for (int w = 0; w < nwarps; ++w) x += sh[w];
+    partials[blockIdx.x] = x;
+  }
+  lb_grid_sync(bar, gen);
+  if (warp == 0) {
+    double x = 0.0;
+    for (unsigned b = lane; b < gridDim.x; b += 32) x += partials[b];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    if (lane == 0) total = x;
+  }
+  __syncthreads();
+  // (every reduction below is followed by a vector update and a grid barrier before the next one
+  // writes `partials`, so no second barrier is needed here)
+  return total;
+}
+__device__ __forceinline__ double lb_dot(const float* x, const float* y, size_t n) {
+  double acc = 0.0;
+  float part = 0.f;
+  int cnt = 0;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
+       i += (size_t)gridDim.x * blockDim.x) {
+    part += x[i] * y[i];
+    if (++cnt == 32) acc += part, part = 0.f, cnt = 0;
+  }
+  return acc + part;
+}
+
+__global__ void __launch_bounds__(256)
+lbfgs_direction_coop_kernel(const float* __restrict__ grad, size_t n, int n_corr, float* ring_s,
+                            const float* ring_y, double* st, float* p, float* params,
+                            float initial_step, double* partials, unsigned* bar) {
+  unsigned gen = 0;
+  const int count = (int)st[0], head = (int)st[1];
+  const size_t tid = blockIdx.x * (size_t)blockDim.x + threadIdx.x, nthr = (size_t)gridDim.x * blockDim.x;
+  auto slot_of = [&](int k) {
+    int sl = (head - 1 - k) % (n_corr + 1);
+    return sl < 0 ? sl + n_corr + 1 : sl;
+  };
+  for (size_t i = tid; i < n; i += nthr) p[i] = grad[i];
+  lb_grid_sync(bar, gen);
+  double alpha[16];
+  for (int k = 0; k < count; ++k) {                                  // optimizers.py:109-111
+    const int sl = slot_of(k);
+    const double dot = lb_grid_sum(lb_dot(ring_s + (size_t)sl * n, p, n), partials, bar, gen);
+    alpha[k] = dot / st[kLbSy + sl];
+    const float coef = (float)(-alpha[k]);
+    const float* y = ring_y + (size_t)sl * n;
+    for (size_t i = tid; i < n; i += nthr) p[i] += coef * y[i];
+    lb_grid_sync(bar, gen);
+  }
+  if (count > 0) {                                                   // :113-115
+    const int sl = slot_of(0);
+    const float* y = ring_y + (size_t)sl * n;
+    const double yy = lb_grid_sum(lb_dot(y, y, n), partials, bar, gen);
+    const float coef = (float)(st[kLbSy + sl] / yy);
+    for (size_t i = tid; i < n; i += nthr) p[i] *= coef;
+    lb_grid_sync(bar, gen);
+  }
+  for (int k = count - 1; k >= 0; --k) {                             // :117-119
+    const int sl = slot_of(k);
+    const double dot = lb_grid_sum(lb_dot(ring_y + (size_t)sl * n, p, n), partials, bar, gen);
+    const float coef = (float)(alpha[k] - dot / st[kLbSy + sl]);
+    const float* sv = ring_s + (size_t)sl * n;
+    for (size_t i = tid; i < n; i += nthr) p[i] += coef * sv[i];
+    lb_grid_sync(bar, gen);
+  }
+  double scale = 1.0;                                                // :81-84
+  if (count == 0) {
+    double a = 0.0;
+    float part = 0.f;
+    int cnt = 0;
+    for (size_t i = tid; i < n; i += nthr) {
+      part += fabsf(p[i]);
+      if (++cnt == 32) a += part, part = 0.f, cnt = 0;
+    }
+    scale = (double)initial_step / (lb_grid_sum(a + part, partials, bar, gen) / (double)n);
+  } else if (count < n_corr) {
+    scale = (double)count / (double)n_corr;
+  }
+  const float coef = (float)(-scale);
+  float* s = ring_s + (size_t)head * n;
+  for (size_t i = tid; i < n; i += nthr) {                           // :85
+    const float v = coef * p[i];
+    s[i] = v;
+    params[i] += v;
+  }
+}
+}  // namespace
+
 int lbfgs_direction(const float* grad, size_t n, int n_corr, float* ring_s, const float* ring_y,
                     double* st, float* p, float* params, float initial_step, ReduceScratch rs,
                     cudaStream_t s) {
+  static const bool no_coop = getenv("ST_LBFGS_NO_COOP") != nullptr;
+  if (!no_coop) {
+    // a co-resident grid: at most the number of blocks the device holds at once
+    static int max_blocks = 0;
+    if (max_blocks == 0) {
+      int dev = 0, sms = 0, per_sm = 0;
+      ST_CUDA(cudaGetDevice(&dev));
+      ST_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+      ST_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lbfgs_direction_coop_kernel, 256, 0));
+      max_blocks = sms * (per_sm < 4 ? per_sm : 4);
+    }
+    int grid = (int)std::min<size_t>((n + 255) / 256, (size_t)max_blocks);
+    double* partials = rs.partials;
+    unsigned* bar = rs.counter;          // zero between kernels (the reduction scratch contract)
+    void* args[] = {(void*)&grad, (void*)&n, (void*)&n_corr, (void*)&ring_s, (void*)&ring_y, (void*)&st,
+                    (void*)&p, (void*)&params, (void*)&initial_step, (void*)&partials, (void*)&bar};
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    ST_CUDA(cudaLaunchCooperativeKernel((const void*)lbfgs_direction_coop_kernel, dim3(grid), dim3(256),
+                                        args, 0, s));
+    // the barrier counter goes back to zero for the next user of the reduction scratch
+    ST_CUDA(cudaMemsetAsync(bar, 0, sizeof(unsigned), s));
+    return ST_OK;
+  }
   const int grid = ew_grid(n, 256);
   ST_CUDA(cudaMemcpyAsync(p, grad, n * sizeof(float), cudaMemcpyDeviceToDevice, s));
   for (int j = 0; j < n_corr; ++j) {                         // optimizers.py:109-111

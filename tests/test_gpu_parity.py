@@ -545,7 +545,7 @@ def test_strip_regularizer_matches_tiled_kernel_and_oracle(roll, monkeypatch):
               2.0, 2.0, 6.0, None, 0.0, p(l2), p(g2), None)
     torch.cuda.synchronize()
     assert maxrel(g2, g1.cpu().numpy()) < 1e-6
-    assert abs(float(l1) - float(l2)) <= 1e-9 * abs(float(l1))
+    assert abs(float(l1) - float(l2)) <= 1e-7 * abs(float(l1))       # float partial sums, other order
     tv_l, tv_g = on.tv_norm(img_h / np.float32(127.5), 2.0)
     p_l, p_g = on.p_norm((img_h + mean_h - np.float32(127.5)) / np.float32(127.5), 6.0)
     want = base.cpu().numpy() + np.float32(5.0 * tv_g + 2.0 * p_g)

@@ -60,7 +60,23 @@ def main():
         # steady-state rate of the LAST scale: skip its first iteration (first-touch allocations)
         last = [m for m in marks if m[0] == marks[-1][0]]
         its = (len(last) - 1) / (last[-1][3] - last[0][3]) if len(last) > 1 else float('nan')
-        out[name] = {'iterations_per_s_last_scale': its, 'last_scale_size': list(last[-1][1]),
+        # the same loop body without a per-iteration callback (nothing synchronises the host)
+        n_free = 30 if args.size <= 1024 else 8
+        for _ in range(3):
+            st.step()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        h0 = time.perf_counter()
+        e0.record()
+        for _ in range(n_free):
+            st.step()
+        e1.record()
+        h1 = time.perf_counter()
+        torch.cuda.synchronize()
+        free = n_free / (e0.elapsed_time(e1) * 1e-3)
+        out[name] = {'iterations_per_s_free_running': free,
+                     'host_enqueue_ms_per_step': (h1 - h0) * 1e3 / n_free,
+                     'iterations_per_s_last_scale': its, 'last_scale_size': list(last[-1][1]),
                      'scales': marks[-1][0], 'total_s': total, 'final_loss': last[-1][4],
                      'finite': bool(np.isfinite(last[-1][4]))}
         print(name, json.dumps(out[name]), flush=True)
