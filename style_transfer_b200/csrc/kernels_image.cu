@@ -970,8 +970,10 @@ lbfgs_direction_coop_kernel(const float* __restrict__ grad, size_t n, int n_corr
 int lbfgs_direction(const float* grad, size_t n, int n_corr, float* ring_s, const float* ring_y,
                     double* st, float* p, float* params, float initial_step, ReduceScratch rs,
                     cudaStream_t s) {
+  // launch-bound regime only: on large images (4096^2: 201 MB per vector) the chain of wide
+  // element-wise kernels below streams at the HBM rate and the barriers buy nothing
   static const bool no_coop = getenv("ST_LBFGS_NO_COOP") != nullptr;
-  if (!no_coop) {
+  if (!no_coop && n <= ((size_t)1 << 22)) {
     // a co-resident grid: at most the number of blocks the device holds at once
     static int max_blocks = 0;
     if (max_blocks == 0) {
