@@ -68,3 +68,24 @@ def test_caffemodel_shape_mismatch(tmp_path):
     path.write_bytes(field(100, 2, layer))
     with pytest.raises((ValueError, KeyError)):
         caffemodel.load_caffemodel(str(path), netdesc.from_model('vgg16.prototxt'))
+
+
+@pytest.mark.parametrize('tag', ['v1', 'v1_unpacked', 'v2'])
+def test_caffemodel_fixtures_from_the_protobuf_library(golden_dir, tag):
+    """Independent bytes: tests/golden/caffemodel_*.bin were serialized by Google's protobuf library
+    from the field numbers of BVLC Caffe's caffe.proto (tests/golden/make_caffemodel_fixture.py), not
+    by any encoder of this repository.  v1: ``layers = 2`` / V1LayerParameter with legacy
+    num/channels/height/width shapes (the format of the published VGG files, download_models.sh:5-6);
+    v1_unpacked: the same with ``data`` stored one key per float; v2: ``layer = 100`` /
+    LayerParameter with BlobShape, one bias stored as double_data.  Every file also carries fields the
+    reader must skip (diff, blobs_lr, convolution_param, bottom / top, ReLU layers without blobs)."""
+    import os
+    from style_transfer_b200 import caffemodel
+    want = np.load(os.path.join(golden_dir, 'caffemodel_expected.npz'))
+    got = caffemodel.load_caffemodel(os.path.join(golden_dir, 'caffemodel_%s.bin' % tag))
+    assert list(got) == ['conv1_1', 'conv1_2', 'conv2_1']
+    for name, (w, b) in got.items():
+        assert w.dtype == np.float32 and np.array_equal(w, want[name + '_w']), name
+        assert b.dtype == np.float32 and np.array_equal(b, want[name + '_b']), name
+    blobs = caffemodel.read_blobs(os.path.join(golden_dir, 'caffemodel_%s.bin' % tag))
+    assert all(not k.startswith('relu') for k in blobs)
