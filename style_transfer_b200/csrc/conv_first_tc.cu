@@ -117,26 +117,33 @@ struct FirstArgs {
   int h, w;                         // tile size
   int tiles_x;                      // ceil(w / 128)
   int num_tiles;                    // nb * h * tiles_x
-  const void* wk;                   // [64][64] K-major, k = tap*3 + ci for the hi half, 27 + that for lo
-  const float* bias;
+  const void* wk;                   // [3 kx][64 n][64 k'] K-major (see tc_pack_first_fwd)
   void* out;                        // [nb][h][w][64], bf16 or fp16 (half)
   uint32_t* bits;                   // ReLU bit mask of the output, [nb][h][w][2] words (may be null)
   int half;                         // operands and output are fp16
 };
 
+// Version 2.  The first version gathered all 27 neighbours per pixel-thread and split each into
+// hi + lo there (27 loads, 54 conversions, 64 bias adds: ~800 SASS instructions per pixel, issue-bound
+// at 2.5x the HBM floor).  Now a thread stages only ITS OWN pixel column: the 3 x 3 (ky, ci) values,
+// hi + lo, as one K-major row  k' = [9 hi | 9 lo | 1, 1 | 0 ...]  of a 130-row array (pixels x0-1 ..
+// x0+128).  The three x taps are three MMA groups whose A descriptor starts one ROW later each --
+// the same rows, shifted by a pixel (start address + kx * 128 bytes inside the swizzle period, the
+// trick of conv_tc2.cu) -- against three weight blocks B_kx.  The bias rides in the two "1" columns
+// (hi + lo of the bias in B_1), so the epilogue is ReLU + pack + mask bits only.
+constexpr int kFirstRows = 136;           // 130 used, padded to a multiple of 8
+
 __global__ void __launch_bounds__(kFirstThreads)
 conv_first_tc_kernel(const FirstArgs a) {
-  __shared__ __align__(1024) uint8_t a_s[128 * 128];     // im2col rows, SWIZZLE_128B
-  __shared__ __align__(1024) uint8_t b_s[64 * 128];      // weights
-  __shared__ float bias_s[kFirstCout];
+  __shared__ __align__(1024) uint8_t a_s[kFirstRows * 128];   // pixel rows, SWIZZLE_128B, K' = 32 used
+  __shared__ __align__(1024) uint8_t b_s[3 * 64 * 128];       // weights per x tap
   __shared__ uint64_t bar;
   __shared__ uint32_t tmem_slot;
   const int tid = threadIdx.x, warp = tid >> 5;
-  if (tid < kFirstCout) bias_s[tid] = a.bias[tid];
 
-  // weights -> swizzled smem: row n, 16-byte chunk j lands at chunk j ^ (n & 7)
-  for (int i = tid; i < 64 * 8; i += kFirstThreads) {
-    const int n = i >> 3, j = i & 7;
+  // weights -> swizzled smem: row n of block kx, 16-byte chunk j lands at chunk j ^ (n & 7)
+  for (int i = tid; i < 3 * 64 * 8; i += kFirstThreads) {
+    const int n = i >> 3, j = i & 7;                      // n = kx * 64 + row
     *reinterpret_cast<uint4*>(b_s + n * 128 + ((j ^ (n & 7)) << 4)) =
         *reinterpret_cast<const uint4*>(static_cast<const uint8_t*>(a.wk) + n * 128 + j * 16);
   }
@@ -156,83 +163,82 @@ conv_first_tc_kernel(const FirstArgs a) {
   const uint32_t idesc = kFirstIdescBase | (fmt << 7) | (fmt << 10);
   const float* base = a.img.base;
   const size_t plane = (size_t)a.img.H * a.img.W;
+  const uint32_t one16 = half ? 0x3C00u : 0x3F80u;        // 1.0 in fp16 / bf16
   uint32_t phase = 0;
 
   for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
     const int tx = tile % a.tiles_x, row_all = tile / a.tiles_x;
     const int y = row_all % a.h, b = row_all / a.h;
-    const int x = tx * 128 + tid;
-    // ---- gather: 27 neighbours of pixel (y, x) of tile b -> one bf16 K-major row --------------------
-    float v[32];                           // k = tap * 3 + ci; k >= 27 is zero padding
+    const int x0 = tx * 128;
+    // ---- stage: row r of a_s = pixel column x0 + r - 1 (rows 0 and 129 are the halo) -----------------
+    // thread t owns row t + 1; threads 0 and 1 also build rows 0 and 129
+    const int oy = a.img.oy[b], ox = a.img.ox[b];
+#pragma unroll 1
+    for (int pass = 0; pass < 2; ++pass) {
+      if (pass == 1 && tid > 1) break;
+      const int r = pass == 0 ? tid + 1 : (tid == 0 ? 0 : 129);
+      const int xx = x0 + r - 1;
+      float v[9];                                         // k = ky * 3 + ci
 #pragma unroll
-    for (int k = 0; k < 32; ++k) v[k] = 0.f;
-    if (x < a.w) {
-      // the tile origin arrives reduced to [0, H) x [0, W) (host) and a tile is no larger than the
-      // image, so the virtual roll wraps with one conditional add / subtract (an integer modulo per
-      // neighbour was a fifth of this kernel's instructions)
-      const int oy = a.img.oy[b], ox = a.img.ox[b];
+      for (int k = 0; k < 9; ++k) v[k] = 0.f;
+      if (xx >= 0 && xx < a.w) {                           // zero padding of the TILE outside
+        // the tile origin arrives reduced to [0, H) x [0, W) (host) and a tile is no larger than the
+        // image, so the virtual roll wraps with one conditional add / subtract
+        int cx = ox + xx;
+        cx = cx >= a.img.W ? cx - a.img.W : cx;
 #pragma unroll
-      for (int ky = 0; ky < 3; ++ky) {
-        const int yy = y + ky - 1;
-        if (yy < 0 || yy >= a.h) continue;                      // zero padding of the TILE
-        int cy = oy + yy;                                       // virtual roll of the image
-        cy = cy < 0 ? cy + a.img.H : (cy >= a.img.H ? cy - a.img.H : cy);
-#pragma unroll
-        for (int kx = 0; kx < 3; ++kx) {
-          const int xx = x + kx - 1;
-          if (xx < 0 || xx >= a.w) continue;
-          int cx = ox + xx;
-          cx = cx < 0 ? cx + a.img.W : (cx >= a.img.W ? cx - a.img.W : cx);
+        for (int ky = 0; ky < 3; ++ky) {
+          const int yy = y + ky - 1;
+          if (yy < 0 || yy >= a.h) continue;
+          int cy = oy + yy;
+          cy = cy < 0 ? cy + a.img.H : (cy >= a.img.H ? cy - a.img.H : cy);
           const float* p = base + (size_t)cy * a.img.W + cx;
 #pragma unroll
-          for (int ci = 0; ci < 3; ++ci) v[(ky * 3 + kx) * 3 + ci] = __ldg(p + ci * plane);
+          for (int ci = 0; ci < 3; ++ci) v[ky * 3 + ci] = __ldg(p + ci * plane);
         }
       }
-    }
-    // Pixels span +-150 grey levels: one bf16 (8 significant bits) would quantise them to 0.5-1
-    // level.  Each value enters as hi + lo (lo = bf16(v - hi)), the weights are repeated for the lo
-    // half: K = 54 of the 64 padded columns, ~16 significant bits, no extra MMA.
-    uint32_t kv[32];                       // 64 x 16 bit: k in [0,27) hi, [27,54) lo, rest zero
-    {
-      float hi[27], lo[27];
-      if (half) {
+      // Pixels span +-150 grey levels: one 16-bit value would quantise them to 0.1-1 level.  Each
+      // enters as hi + lo (lo = r16(v - hi)), the weights are repeated for the lo half.
+      uint32_t h16[9], l16[9];
 #pragma unroll
-        for (int k = 0; k < 27; ++k) hi[k] = __half2float(__float2half_rn(v[k])), lo[k] = v[k] - hi[k];
-      } else {
-#pragma unroll
-        for (int k = 0; k < 27; ++k)
-          hi[k] = __bfloat162float(__float2bfloat16_rn(v[k])), lo[k] = v[k] - hi[k];
-      }
-      float xk[64];
-#pragma unroll
-      for (int k = 0; k < 64; ++k) xk[k] = k < 27 ? hi[k] : (k < 54 ? lo[k - 27] : 0.f);
-      // pixels are a few hundred grey levels at most: no saturation needed (pack16 clamps fp16)
-      if (half) {                            // one uniform branch, not one per packed word
-#pragma unroll
-        for (int k = 0; k < 32; ++k) {
-          const __half2 h2 = __floats2half2_rn(xk[2 * k], xk[2 * k + 1]);
-          kv[k] = *reinterpret_cast<const uint32_t*>(&h2);
+      for (int k = 0; k < 9; ++k) {
+        if (half) {
+          const __half hh = __float2half_rn(v[k]);
+          const __half ll = __float2half_rn(v[k] - __half2float(hh));
+          h16[k] = *reinterpret_cast<const uint16_t*>(&hh), l16[k] = *reinterpret_cast<const uint16_t*>(&ll);
+        } else {
+          const __nv_bfloat16 hh = __float2bfloat16_rn(v[k]);
+          const __nv_bfloat16 ll = __float2bfloat16_rn(v[k] - __bfloat162float(hh));
+          h16[k] = *reinterpret_cast<const uint16_t*>(&hh), l16[k] = *reinterpret_cast<const uint16_t*>(&ll);
         }
-      } else {
-#pragma unroll
-        for (int k = 0; k < 32; ++k) kv[k] = pack16(xk[2 * k], xk[2 * k + 1], false);
       }
-    }
-    uint8_t* row = a_s + tid * 128;
+      // 32 halfs: [h0..h8 | l0..l8 | 1 1 | 0 x 12]
+      uint32_t kv[16];
+      kv[0] = h16[0] | (h16[1] << 16), kv[1] = h16[2] | (h16[3] << 16), kv[2] = h16[4] | (h16[5] << 16);
+      kv[3] = h16[6] | (h16[7] << 16), kv[4] = h16[8] | (l16[0] << 16), kv[5] = l16[1] | (l16[2] << 16);
+      kv[6] = l16[3] | (l16[4] << 16), kv[7] = l16[5] | (l16[6] << 16), kv[8] = l16[7] | (l16[8] << 16);
+      kv[9] = one16 | (one16 << 16);
 #pragma unroll
-    for (int j = 0; j < 8; ++j)            // 16-byte chunk j of the row lands at j ^ (row & 7)
-      *reinterpret_cast<uint4*>(row + ((j ^ (tid & 7)) << 4)) =
-          make_uint4(kv[4 * j], kv[4 * j + 1], kv[4 * j + 2], kv[4 * j + 3]);
+      for (int k = 10; k < 16; ++k) kv[k] = 0u;
+      uint8_t* rowp = a_s + r * 128;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)            // 16-byte chunk j of the row lands at j ^ (row & 7)
+        *reinterpret_cast<uint4*>(rowp + ((j ^ (r & 7)) << 4)) =
+            make_uint4(kv[4 * j], kv[4 * j + 1], kv[4 * j + 2], kv[4 * j + 3]);
+    }
     fence_proxy_async();                  // generic-proxy smem writes -> visible to the tensor core
     tc_fence_before();
     __syncthreads();
-    // ---- MMA: D[128 px][64 ch] = A[128][64] * B[64][64]^T ---------------------------------------------
+    // ---- MMA: D[128 px][64 ch] = sum_kx A[rows kx .. kx+127][32] * B_kx[64][32]^T ----------------------
     if (warp == 0) {
       tc_fence_after();
       if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          tc_mma(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, k != 0);
+        for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+          for (int ks = 0; ks < 2; ++ks)
+            tc_mma(tmem_base, da + (uint64_t)(kx * 8 + ks * 2), db + (uint64_t)(kx * 512 + ks * 2), idesc,
+                   (kx | ks) != 0);
         tc_commit(&bar);
       }
       __syncwarp();
@@ -240,32 +246,30 @@ conv_first_tc_kernel(const FirstArgs a) {
     mbar_wait(&bar, phase);
     phase ^= 1;
     tc_fence_after();
-    // ---- epilogue: bias + ReLU -> bf16 -> a_s (free now: the MMAs have retired) -> coalesced copy --------
+    // ---- epilogue: ReLU -> 16 bit -> a_s (free now: the MMAs have retired) -> coalesced copy ------------
     const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
+    uint8_t* row = a_s + tid * 128;
 #pragma unroll
     for (int cc = 0; cc < 2; ++cc) {
       uint32_t r[32];
       tmem_ld32(taddr + cc * 32, r);
-      float f[32];
-#pragma unroll
-      for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(r[i]) + bias_s[cc * 32 + i];
       // ReLU, saturation and rounding in the pack; the mask bits of the backward pass from the pairs
       uint32_t pw[16], bits = 0u;
       if (half) {
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          pw[i] = pack16_relu(f[2 * i], f[2 * i + 1], true);
+          pw[i] = pack16_relu(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]), true);
           bits |= gt2_mask<true>(pw[i], 0u) & (0x00010001u << i);
         }
       } else {
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          pw[i] = pack16_relu(f[2 * i], f[2 * i + 1], false);
+          pw[i] = pack16_relu(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]), false);
           bits |= gt2_mask<false>(pw[i], 0u) & (0x00010001u << i);
         }
       }
-      if (a.bits != nullptr && tx * 128 + tid < a.w)
-        a.bits[(((size_t)b * a.h + y) * a.w + tx * 128 + tid) * 2 + cc] = bits;
+      if (a.bits != nullptr && x0 + tid < a.w)
+        a.bits[(((size_t)b * a.h + y) * a.w + x0 + tid) * 2 + cc] = bits;
 #pragma unroll
       for (int j = 0; j < 4; ++j)
         *reinterpret_cast<uint4*>(row + (((cc * 4 + j) ^ (tid & 7)) << 4)) =
@@ -276,14 +280,14 @@ conv_first_tc_kernel(const FirstArgs a) {
     // the 128 pixels of the tile are 16 KB of contiguous global memory: 16-byte chunk g of the tile
     // is chunk (g & 7) of row (g >> 3)
     {
-      const int valid_rows = min(128, a.w - tx * 128);
+      const int valid_rows = min(128, a.w - x0);
       uint4* dst = reinterpret_cast<uint4*>(static_cast<uint8_t*>(a.out) +
-                                            (((size_t)b * a.h + y) * a.w + tx * 128) * kFirstCout * 2);
+                                            (((size_t)b * a.h + y) * a.w + x0) * kFirstCout * 2);
 #pragma unroll
       for (int it = 0; it < 8; ++it) {
-        const int g = it * kFirstThreads + tid, r = g >> 3, j = g & 7;
-        if (r < valid_rows)
-          dst[g] = *reinterpret_cast<const uint4*>(a_s + r * 128 + ((j ^ (r & 7)) << 4));
+        const int g = it * kFirstThreads + tid, rr = g >> 3, j = g & 7;
+        if (rr < valid_rows)
+          dst[g] = *reinterpret_cast<const uint4*>(a_s + rr * 128 + ((j ^ (rr & 7)) << 4));
       }
     }
     __syncthreads();                      // a_s and TMEM are free for the next tile
@@ -294,23 +298,40 @@ conv_first_tc_kernel(const FirstArgs a) {
 
 }  // namespace
 
-int tc_pack_first_fwd(TcContext& tc, TcWeights& w, const float* w_host, int cout, bool half) {
+// B_kx[n][k'] (K-major, 64 halfs per row): k' = ky*3 + ci -> w[n][ci][ky][kx] for the hi half (0..8)
+// and again for the lo half (9..17); block kx = 1 also carries the bias as hi + lo in k' = 18, 19
+// (the A rows hold 1.0 there).
+int tc_pack_first_fwd(TcContext& tc, TcWeights& w, const float* w_host, int cout, bool half,
+                      const float* bias_host) {
   if (!tc.enabled || !tc.pair_kernel || cout != kFirstCout) return ST_OK;
-  std::vector<uint16_t> host((size_t)64 * 64, 0);
-  for (int co = 0; co < cout; ++co)
+  auto r16 = [half](float v) {
+    uint16_t bits;
+    if (half) {
+      const __half h = __float2half_rn(v);
+      bits = *reinterpret_cast<const uint16_t*>(&h);
+    } else {
+      const __nv_bfloat16 h = __float2bfloat16_rn(v);
+      bits = *reinterpret_cast<const uint16_t*>(&h);
+    }
+    return bits;
+  };
+  auto f16 = [half](uint16_t bits) {
+    if (half) return __half2float(*reinterpret_cast<const __half*>(&bits));
+    return __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(&bits));
+  };
+  std::vector<uint16_t> host((size_t)3 * 64 * 64, 0);
+  for (int co = 0; co < cout; ++co) {
     for (int ci = 0; ci < 3; ++ci)
-      for (int tap = 0; tap < 9; ++tap) {
-        const float v = w_host[((size_t)co * 3 + ci) * 9 + tap];
-        uint16_t bits;
-        if (half) {
-          const __half h = __float2half_rn(v);
-          bits = *reinterpret_cast<const uint16_t*>(&h);
-        } else {
-          const __nv_bfloat16 h = __float2bfloat16_rn(v);
-          bits = *reinterpret_cast<const uint16_t*>(&h);
+      for (int ky = 0; ky < 3; ++ky)
+        for (int kx = 0; kx < 3; ++kx) {
+          const uint16_t bits = r16(w_host[((size_t)co * 3 + ci) * 9 + ky * 3 + kx]);
+          uint16_t* row = host.data() + ((size_t)kx * 64 + co) * 64;
+          row[ky * 3 + ci] = row[9 + ky * 3 + ci] = bits;
         }
-        host[(size_t)co * 64 + tap * 3 + ci] = host[(size_t)co * 64 + 27 + tap * 3 + ci] = bits;
-      }
+    const uint16_t bh = r16(bias_host[co]);
+    uint16_t* row1 = host.data() + ((size_t)1 * 64 + co) * 64;
+    row1[18] = bh, row1[19] = r16(bias_host[co] - f16(bh));
+  }
   if (!w.fwd) ST_CUDA(cudaMalloc(&w.fwd, host.size() * 2));
   ST_CUDA(cudaMemcpy(w.fwd, host.data(), host.size() * 2, cudaMemcpyHostToDevice));
   w.fwd_half = half;
@@ -329,8 +350,9 @@ int conv_first_fwd_tc(TcContext& tc, const TcWeights& w, const ImageBatch& img, 
     a.img.ox[i] = ((img.ox[i] % img.W) + img.W) % img.W;
   }
   a.num_tiles = img.nb * h * a.tiles_x;
-  a.wk = w.fwd, a.bias = bias, a.out = out;
-  const int grid = a.num_tiles < tc.sm_count * 8 ? a.num_tiles : tc.sm_count * 8;   // 8 x 64 TMEM columns
+  a.wk = w.fwd, a.out = out;
+  (void)bias;                               // packed into the weights (tc_pack_first_fwd)
+  const int grid = a.num_tiles < tc.sm_count * 5 ? a.num_tiles : tc.sm_count * 5;   // 42 KB of smem each
   TimerScope ts(s, kTimeConvSimt, 18.0 * 3 * kFirstCout * h * wd * img.nb);
   ST_LAUNCH(conv_first_tc_kernel, grid, kFirstThreads, 0, s, a);
   return ST_OK;

@@ -114,7 +114,8 @@ int conv_pix_bwd_tc(TcContext& tc, const TcWeights& w, const __nv_bfloat16* dz, 
                     cudaStream_t s);
 // First convolution (3 -> 64 channels) on tensor cores from the planar f32 image (conv_first_tc.cu).
 struct ImageBatch;
-int tc_pack_first_fwd(TcContext& tc, TcWeights& w, const float* w_oihw_host, int cout, bool half);
+int tc_pack_first_fwd(TcContext& tc, TcWeights& w, const float* w_oihw_host, int cout, bool half,
+                      const float* bias_host);
 int conv_first_fwd_tc(TcContext& tc, const TcWeights& w, const ImageBatch& img, int h, int wd,
                       const float* bias, void* out, uint32_t* relu_bits, cudaStream_t s);
 // Per batch tile b: S_b[p][n] = sum_c F_b[p][c] * D_b[n][c] for F [nb][h][w][c] and D [nb][c][c],

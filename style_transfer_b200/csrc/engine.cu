@@ -806,7 +806,7 @@ int st_set_conv_params(st_ctx* ctx, int layer, const float* w, const float* b) {
     const bool half = ctx->precision == ST_PREC_FP16;
     int rc = first ? tc_pack_first(ctx->tc, l.tc, w, co_n)
                    : tc_pack_weights(ctx->tc, l.tc, w, ci_n, co_n, half);
-    if (rc == ST_OK && first) rc = tc_pack_first_fwd(ctx->tc, l.tc, w, co_n, half);
+    if (rc == ST_OK && first) rc = tc_pack_first_fwd(ctx->tc, l.tc, w, co_n, half, b);
     if (rc == ST_OK && first) rc = tc_pack_first_rows(ctx->tc, l.tc, w, co_n);
     if (rc != ST_OK) return rc;
   }
