@@ -381,14 +381,40 @@ class Workload:
         self.st.prepare([content], [style])
         self.old = self.eng.img.clone()
         self.stats = torch.zeros(2, dtype=torch.float64, device=self.eng.img.device)
+        self.rank = rank
+        # the output step runs where the reference runs it -- on the master (rank 0) only -- and on
+        # its own stream: it reads the averaged iterate of step i while step i + 1 is being computed
+        self.out_stream = torch.cuda.Stream(device=self.eng.img.device)
+        self.out_done = []
+        self.picture = self.loss = None
+        self.after_output = None          # e2e: called on the output stream after the output step
 
     def step(self):
         """One pass of the loop body (style_transfer.py:777-821): roll, objective, optimizer step,
-        roll back, the update-size / TV statistics and the uint8 picture -- all on the device."""
+        roll back; then, on rank 0, the update-size / TV statistics and the uint8 picture of the
+        averaged iterate (device-resident, on the output stream)."""
+        torch = self.torch
+        main = torch.cuda.current_stream()
+        if len(self.out_done) >= 2:
+            # the buffer this step's average goes to was read by the output step two steps ago
+            main.wait_event(self.out_done.pop(0))
         avg, loss = self.st.step()
-        self.picture = self.st.output_step(avg, self.old, self.stats)
         self.loss = loss
+        if self.rank == 0:
+            ready = torch.cuda.Event()
+            ready.record(main)
+            self.out_stream.wait_event(ready)
+            with torch.cuda.stream(self.out_stream):
+                self.picture = self.st.output_step(avg, self.old, self.stats)
+                if self.after_output is not None:
+                    self.after_output(loss)
+                done = torch.cuda.Event()
+                done.record(self.out_stream)
+            self.out_done.append(done)
         return avg, loss
+
+    def drain(self):
+        self.out_stream.synchronize()
 
     def close(self):
         self.st = self.eng = self.old = self.picture = None
@@ -426,9 +452,11 @@ def run_engine(a):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps):
+    def timed(fn, steps, join=None):
         """(device ms, host enqueue ms) of `steps` calls: CUDA events on the launching stream,
-        barrier + synchronize on both sides, max over ranks."""
+        barrier + synchronize on both sides, max over ranks.  `join`: a stream whose work (the output
+        step of the last iterations) must be inside the timed region: the launching stream waits for
+        it before the closing event."""
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -436,6 +464,8 @@ def run_engine(a):
         for _ in range(steps):
             fn()
         h1 = time.perf_counter()
+        if join is not None:
+            torch.cuda.current_stream().wait_stream(join)
         e1.record()
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1), (h1 - h0) * 1e3], dtype=torch.float64, device=dev)
@@ -457,14 +487,14 @@ def run_engine(a):
     def measure(w, steps, warmup):
         for _ in range(warmup):
             w.step()
-        ms, _ = timed(w.step, steps)
+        ms, _ = timed(w.step, steps, join=w.out_stream)
         return steps / (ms * 1e-3), ms / steps, host_enqueue_ms(w.step)
 
     def conv_roofline(w, steps, precision, sm_mhz, sm_max):
         """Per-launch CUDA events (st_timing_*) around every kernel group of `steps` steps."""
         lib.st_timing_reset()
         lib.st_timing_enable(1)
-        ms_timing, _ = timed(w.step, steps)
+        ms_timing, _ = timed(w.step, steps, join=w.out_stream)
         lib.st_timing_enable(0)
         cats = ['conv_tc', 'conv_edge', 'pool', 'gram', 'style_grad', 'loss', 'image']
         breakdown = {}
@@ -517,7 +547,7 @@ def run_engine(a):
     sampler = ClockSampler(local) if rank == 0 else None
     launches0 = lib.st_launch_count()
     t0 = time.perf_counter()
-    ms, host_ms = timed(w.step, a.steps)
+    ms, host_ms = timed(w.step, a.steps, join=w.out_stream)
     t1 = time.perf_counter()
     launches = lib.st_launch_count() - launches0
     clocks = sampler.stop(t0, t1) if sampler else None
@@ -544,37 +574,50 @@ def run_engine(a):
         host_pic = torch.empty((H, W, 3), dtype=torch.uint8).pin_memory()
         host_scalars = torch.empty(3, dtype=torch.float64).pin_memory()
         scal = torch.zeros(3, dtype=torch.float64, device=dev)
+        pending = []
+
+        def fetch_results(loss):
+            # (runs on the output stream, after the output step) D2H: picture, loss, statistics
+            host_pic.copy_(w.picture, non_blocking=True)
+            scal[0:1].copy_(loss)
+            scal[1:3].copy_(w.stats)
+            host_scalars.copy_(scal, non_blocking=True)
+        if rank == 0:
+            w.after_output = fetch_results
 
         def e2e_step():
+            # the host consumes the PREVIOUS step's results (they are complete in pinned memory once
+            # that step's output stream is done) before it enqueues this step: one step in flight
+            if pending:
+                pending.pop(0).synchronize()
             # H2D: this step's image (every rank its 1/world slab of rows through its own PCIe link,
             # NVLink all-gather; one GPU: two halves, the second streaming in behind the first tiles)
             eng.stage_host_image(host_params)
             w.step()
-            # D2H: the uint8 picture (every rank its slab) + loss and the two statistics (rank 0)
-            if rows is not None:
-                r0 = rank * rows
-                host_pic[r0:r0 + rows].copy_(w.picture[r0:r0 + rows], non_blocking=True)
-            elif rank == 0:
-                host_pic.copy_(w.picture, non_blocking=True)
             if rank == 0:
-                scal[0:1].copy_(w.loss)
-                scal[1:3].copy_(w.stats)
-                host_scalars.copy_(scal, non_blocking=True)
-            torch.cuda.current_stream().synchronize()
+                pending.append(w.out_done[-1])
+            else:
+                ev = torch.cuda.Event()
+                ev.record()
+                pending.append(ev)
         for _ in range(3):
             e2e_step()
-        ms_e2e, _ = timed(e2e_step, a.steps)
+        ms_e2e, _ = timed(e2e_step, a.steps, join=w.out_stream)
+        w.drain()
+        w.after_output = None
         slab = n * 4 // world if rows is not None else n * 4
         e2e = {'value': a.steps / (ms_e2e * 1e-3), 'unit': 'iterations/s',
                'h2d_bytes_per_step': n * 4, 'd2h_bytes_per_step': H * W * 3 + 24,
                'h2d_bytes_per_step_per_gpu': slab,
-               'd2h_bytes_per_step_per_gpu': (H * W * 3) // world if rows is not None else H * W * 3,
+               'd2h_bytes_per_step_per_gpu': 'rank 0: %d (picture + loss + statistics), others: 0' % (H * W * 3 + 24),
                'ms_per_step': ms_e2e / a.steps, 'fraction_of_value': a.steps / (ms_e2e * 1e-3) / value,
                'boundary': 'pinned host f32[3,H,W] image in (TileEngine.stage_host_image), one pass of '
                            'the loop body (StyleTransfer.step + statistics + picture), uint8 RGB '
                            'picture + loss + update-size / TV statistics back to pinned host memory, '
-                           'stream synchronised, every step; N > 1: every rank moves its 1/N slab of '
-                           'rows through its own PCIe link, the image slabs are all-gathered over NCCL'}
+                           'every step; the host reads step i\'s results while step i + 1 runs (one step '
+                           'in flight; the timed region ends with a device-wide synchronisation); '
+                           'N > 1: every rank uploads its 1/N slab of rows through its own PCIe link, '
+                           'the slabs are all-gathered over NCCL, results leave from rank 0 (the master)'}
 
     if os.environ.get('ST_NCU_RANGE') == '1':
         # for `ncu --profile-from-start off`: exactly one step of the headline workload is profiled

@@ -49,13 +49,19 @@ class AdamOptimizer:
         self.g1 = EWMA(params, b1, correct_bias=not biased_g1)
         self.g2 = EWMA(params, b2)
         self.p1 = EWMA(params, bp1)
-        self.avg = torch.empty_like(params)
+        # the averaged iterate is returned alternately in two buffers, so that a consumer on another
+        # stream (statistics / picture of step i) may still be reading while step i + 1 is enqueued
+        self._avg = [torch.empty_like(params), torch.empty_like(params)]
+        self._avg_i = 0
+        self.avg = self._avg[0]
 
     def update(self, opfunc):
         """Returns (averaged iterate, loss); ``opfunc(params) -> (loss, grad)`` on the device."""
         step_size = self.step_size / self.i ** self.power
         self.i += self.decay
         loss, grad = opfunc(self.params)
+        self._avg_i ^= 1
+        self.avg = self._avg[self._avg_i]
         _lib.call('st_adam_step', _ptr(self.params), _ptr(grad), _ptr(self.g1.value),
                   _ptr(self.g2.value), _ptr(self.p1.value), _ptr(self.avg), self.params.numel(),
                   step_size, self.g1.beta, self.g2.beta, self.p1.beta, self.g1.tick(),
@@ -78,7 +84,8 @@ class AdamOptimizer:
             self.g1.value = resize(self.g1.value, hw, 'lanczos')
             self.g2.value = torch.clamp_min(resize(self.g2.value, hw, 'bilinear'), 0)
             self.p1.value = resize(self.p1.value, hw, 'lanczos')
-        self.avg = torch.empty_like(self.params)
+        self._avg = [torch.empty_like(self.params), torch.empty_like(self.params)]
+        self.avg = self._avg[self._avg_i]
 
 
 class LBFGSOptimizer:

@@ -12,4 +12,4 @@ try:
 except Exception as e:
     print('bench parse failed', e)
 PY
-timeout 600 python tools/config_runs.py 2>&1 | tail -12
+timeout 600 python tools/config_runs.py cfg2 cfg4 2>&1 | tail -3 | cut -c1-600
