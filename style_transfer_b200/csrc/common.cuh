@@ -16,6 +16,7 @@ constexpr float kEps = 1.1920928955078125e-07f;  // float32 machine epsilon (num
 // ---- error plumbing -----------------------------------------------------------------------------
 void set_error(const std::string& msg);
 extern std::atomic<uint64_t> g_launches;
+extern bool g_pdl;          // ST_NO_PDL=1 disables programmatic dependent launch (read once)
 
 #define ST_CUDA(call)                                                                      \
   do {                                                                                     \
@@ -36,27 +37,30 @@ extern std::atomic<uint64_t> g_launches;
   } while (0)
 
 // Every kernel launch of the library goes through this so bench.py can report "gpu_launches".
-#define ST_LAUNCH(kernel, grid, block, smem, stream, ...)              \
-  do {                                                                 \
-    kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);        \
-    st::g_launches.fetch_add(1, std::memory_order_relaxed);            \
-    ST_CUDA(cudaGetLastError());                                       \
-  } while (0)
-
-// The same with programmatic dependent launch: the kernel may be scheduled while its predecessor in
-// the stream is still draining (its prologue overlaps the predecessor's tail); the kernel MUST
-// execute griddepcontrol.wait before it touches global memory the predecessor wrote.
-#define ST_LAUNCH_PDL(kernel, grid, block, smem, strm_, pdl, ...)                            \
+#define ST_LAUNCH(kernel, grid, block, smem, strm_, ...)                                   \
   do {                                                                                     \
     cudaLaunchConfig_t cfg_ = {};                                                          \
     cfg_.gridDim = dim3(grid), cfg_.blockDim = dim3(block);                                \
     cfg_.dynamicSmemBytes = (smem), cfg_.stream = (strm_);                                 \
     cudaLaunchAttribute attr_[1];                                                          \
     attr_[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                      \
-    attr_[0].val.programmaticStreamSerializationAllowed = (pdl) ? 1 : 0;                   \
+    attr_[0].val.programmaticStreamSerializationAllowed = st::g_pdl ? 1 : 0;               \
     cfg_.attrs = attr_, cfg_.numAttrs = 1;                                                 \
     st::g_launches.fetch_add(1, std::memory_order_relaxed);                                \
     ST_CUDA(cudaLaunchKernelEx(&cfg_, kernel, __VA_ARGS__));                               \
+  } while (0)
+
+// Programmatic dependent launch, everywhere: every kernel of the library starts with ST_PDL_ENTRY()
+// and every launch carries the programmatic-stream-serialization attribute.  launch_dependents lets
+// the NEXT kernel of the stream be scheduled as soon as all blocks of this one are resident or done;
+// griddepcontrol.wait blocks until the PREVIOUS kernel has completed and its writes are visible, so
+// the ordering the code relies on is unchanged -- only the launch latency (and, where the wait is
+// placed after a prologue, that prologue) overlaps the predecessor's tail.  A step is ~62 dependent
+// launches; the gaps between them were ~0.3 ms of a 6 ms step (profiles/r02_launches_step_b.md).
+#define ST_PDL_ENTRY()                                                \
+  do {                                                                \
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   \
+    asm volatile("griddepcontrol.wait;" ::: "memory");                \
   } while (0)
 
 inline int cdiv(long a, long b) { return (int)((a + b - 1) / b); }

@@ -135,6 +135,8 @@ constexpr int kFirstRows = 136;           // 130 used, padded to a multiple of 8
 
 __global__ void __launch_bounds__(kFirstThreads)
 conv_first_tc_kernel(const FirstArgs a) {
+  // PDL: the weight staging and the TMEM allocation below overlap the previous kernel's tail
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   __shared__ __align__(1024) uint8_t a_s[kFirstRows * 128];   // pixel rows, SWIZZLE_128B, K' = 32 used
   __shared__ __align__(1024) uint8_t b_s[3 * 64 * 128];       // weights per x tap
   __shared__ uint64_t bar;
@@ -165,6 +167,7 @@ conv_first_tc_kernel(const FirstArgs a) {
   const size_t plane = (size_t)a.img.H * a.img.W;
   const uint32_t one16 = half ? 0x3C00u : 0x3F80u;        // 1.0 in fp16 / bf16
   uint32_t phase = 0;
+  asm volatile("griddepcontrol.wait;" ::: "memory");     // the image is read (and `out` written) below
 
   for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
     const int tx = tile % a.tiles_x, row_all = tile / a.tiles_x;

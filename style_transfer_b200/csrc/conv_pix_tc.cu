@@ -176,6 +176,7 @@ __device__ __forceinline__ PixTile decode(const PixArgs& a, int tile) {
 __global__ void __launch_bounds__(kPThreads, 2)
 conv_pix_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_in,
                        const __grid_constant__ CUtensorMap map_w, const PixArgs a) {
+  ST_PDL_ENTRY();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~(uintptr_t)1023);

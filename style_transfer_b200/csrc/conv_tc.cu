@@ -203,6 +203,7 @@ template <typename T, int BN>
 __global__ void __launch_bounds__(kThreads, 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CUtensorMap map_w,
                   const __grid_constant__ CUtensorMap map_out, const TcArgs a) {
+  ST_PDL_ENTRY();
   using Cfg = TcCfg<T, BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &

@@ -1041,7 +1041,7 @@ int launch2r(TcContext& tc, const void* in, const void* wk, int wk_rows,
   // (split mode: a.cin counts the three K segments; the algorithmic flops are a third of the executed)
   TimerScope ts(s, EPI == kEpiAbs ? kTimeStyleGrad : (EPI == kEpiPix ? kTimeConvSimt : kTimeConvTc),
                 2.0 * TAPS * (k32 ? a.cin / 3 : a.cin) * (EPI == kEpiPix ? 3 : a.cout) * a.h * a.w * a.nb);
-  ST_LAUNCH_PDL(kern, 2 * pairs, kThreads2, smem_bytes, s, tc.pdl, map_in, map_w, map_out, map_pool, a);
+  ST_LAUNCH(kern, 2 * pairs, kThreads2, smem_bytes, s, map_in, map_w, map_out, map_pool, a);
   return ST_OK;
 }
 
@@ -1134,6 +1134,7 @@ namespace {
 __global__ void __launch_bounds__(256) split_f32_kernel(const float* __restrict__ in,
                                                         __half* __restrict__ out, size_t groups,
                                                         int c8, float scale) {
+  ST_PDL_ENTRY();
   // one thread per 8 channels of one pixel
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < groups; i += stride) {

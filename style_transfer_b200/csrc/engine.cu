@@ -18,6 +18,7 @@ namespace st {
 
 static thread_local std::string g_error;
 std::atomic<uint64_t> g_launches{0};
+bool g_pdl = getenv("ST_NO_PDL") == nullptr;
 void set_error(const std::string& msg) { g_error = msg; }
 
 // ---- per-kernel timing ---------------------------------------------------------------------------

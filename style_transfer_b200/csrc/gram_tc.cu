@@ -163,6 +163,8 @@ struct GramArgs {
 template <int C>
 __global__ void __launch_bounds__(kGThreads, C <= 128 ? 2 : 1)
 gram_tc_kernel(const __grid_constant__ CUtensorMap map_f, const GramArgs a) {
+  // PDL: barrier init / TMEM allocation overlap the previous kernel's tail; features are read below
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   using Cfg = GramCfg<C>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -199,6 +201,7 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap map_f, const GramArgs a) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 
   if (warp == 0) {
     // warp-wide loops with warp-uniform state; only the TMA / MMA issue is elected (see conv_tc2.cu)
@@ -296,6 +299,7 @@ template <int R>
 __global__ void __launch_bounds__(1024 / R)
 gram_tc_finish_kernel(const float* __restrict__ part, int nsplit, int c, double scale,
                       const GramFinish fin) {
+  ST_PDL_ENTRY();
   constexpr int kRowsPerPass = 32 / R, kWarps = 32 / R;
   __shared__ float tile[32][33];
   __shared__ double sh[kWarps];

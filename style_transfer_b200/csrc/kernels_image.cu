@@ -40,6 +40,7 @@ __global__ void unpack_grad_kernel(const float* __restrict__ packed, int H, int 
                                    int roll_x, int nty, int ntx, int th, int tw, int thmax,
                                    int twmax, int world, size_t rank_stride,
                                    float* __restrict__ grad, double* loss_accum) {
+  ST_PDL_ENTRY();
   // blockIdx.y = image row, blockIdx.z = plane: no per-element div/mod on 64-bit indices
   const int y = blockIdx.y, c = blockIdx.z;
   int yr = y + roll_y;                                     // host passes the roll reduced to [0, H)
@@ -140,6 +141,7 @@ regularizers_kernel(const float* __restrict__ img, int H, int W, float m0, float
                     const float* __restrict__ aux, float aux_w, int roll_y, int roll_x,
                     double* loss_accum, float* __restrict__ grad,
                     const float* __restrict__ packed, UnpackGeom ug, RegTiles rt, ReduceScratch rs) {
+  ST_PDL_ENTRY();
   __shared__ float xs[kRTH + 2][kRTW + 2];       // scaled pixels, origin (y0-1, x0-1)
   const int tx = threadIdx.x % kRTW, ty0 = threadIdx.x / kRTW;
   const int num_tiles = rt.num_tiles;
@@ -279,6 +281,7 @@ __global__ void __launch_bounds__(kRsThreads)
 regularizers_strip_kernel(const float* __restrict__ img, int H, int W, float m0, float m1, float m2,
                           float tv_w, float p_w, double* loss_accum, float* __restrict__ grad,
                           const float* __restrict__ packed, UnpackGeom ug, ReduceScratch rs) {
+  ST_PDL_ENTRY();
   const int x = (blockIdx.x * kRsThreads + threadIdx.x) * 4;
   const int c = blockIdx.z, y0 = blockIdx.y * kRsRows;
   const float inv = 1.f / 127.5f;
@@ -430,6 +433,7 @@ __global__ void adam_kernel(float* __restrict__ params, const float* __restrict_
                             float* __restrict__ avg, size_t n, float neg_step, float b1, float omb1,
                             float b2, float omb2, float bp1, float ombp1, float g1c, float g2c,
                             float p1c) {
+  ST_PDL_ENTRY();
   const size_t n4 = n >> 2;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4;
        i += (size_t)gridDim.x * blockDim.x) {
@@ -475,6 +479,7 @@ int adam_step(float* params, const float* grad, float* g1, float* g2, float* p1,
 __global__ void __launch_bounds__(256)
 iter_stats_kernel(const float* __restrict__ avg, float* __restrict__ old, int H, int W, double* stats,
                   ReduceScratch rs) {
+  ST_PDL_ENTRY();
   double v[2] = {0.0, 0.0};
   for (int row = blockIdx.x; row < 3 * H; row += gridDim.x) {
     const int c = row / H, y = row - c * H;
@@ -506,6 +511,7 @@ int iter_stats(const float* avg, float* old, int H, int W, double* stats, Reduce
 __global__ void __launch_bounds__(256)
 get_image_u8_kernel(const float* __restrict__ params, int H, int W, float m0, float m1, float m2,
                     int bgr, uint8_t* __restrict__ out) {
+  ST_PDL_ENTRY();
   const size_t n = (size_t)H * W;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
        i += (size_t)gridDim.x * blockDim.x) {
@@ -538,6 +544,7 @@ __global__ void __launch_bounds__(kOsThreads)
 output_step_kernel(const float* __restrict__ avg, float* __restrict__ old, int H, int W, float m0,
                    float m1, float m2, int bgr, double* stats, uint8_t* __restrict__ pic,
                    ReduceScratch rs) {
+  ST_PDL_ENTRY();
   const int x = (blockIdx.x * kOsThreads + threadIdx.x) * 4;
   const int y0 = blockIdx.y * kOsRows;
   const size_t plane = (size_t)H * W;
@@ -622,6 +629,7 @@ template <bool ALONG_Y>
 __global__ void __launch_bounds__(256)
 resample_kernel(const float* __restrict__ in, float* __restrict__ out, int in_h, int in_w, int out_h,
                 int out_w, const int* __restrict__ bounds, const double* __restrict__ kk, int ksize) {
+  ST_PDL_ENTRY();
   const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, c = blockIdx.z;
   if (x >= out_w) return;
   const float* src = in + (size_t)c * in_h * in_w;
@@ -656,6 +664,7 @@ int resample_pass(const float* in, float* out, int channels, int in_h, int in_w,
 template <bool ABS>
 __global__ void dot_kernel(const float* __restrict__ x, const float* __restrict__ y, size_t n,
                            double* out, ReduceScratch rs) {
+  ST_PDL_ENTRY();
   double v[1] = {0.0};
   float part = 0.f;
   int cnt = 0;
@@ -683,6 +692,7 @@ int asum_to(const float* x, size_t n, double* out, ReduceScratch rs, cudaStream_
 
 __global__ void axpby_kernel(float a, const float* __restrict__ x, float b, float* __restrict__ y,
                              size_t n) {
+  ST_PDL_ENTRY();
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
        i += (size_t)gridDim.x * blockDim.x)
     y[i] = b == 0.f ? a * x[i] : a * x[i] + b * y[i];
@@ -696,6 +706,7 @@ int axpby(float a, const float* x, float b, float* y, size_t n, cudaStream_t s) 
 __global__ void axpy_dev_kernel(const float* __restrict__ x, float* __restrict__ y, size_t n,
                                 const double* __restrict__ num, double den,
                                 const double* __restrict__ sub, double sign, double* store) {
+  ST_PDL_ENTRY();
   const double first = num[0] / den;
   const float coef = (float)(sign * (sub ? first - sub[0] : first));
   if (store && blockIdx.x == 0 && threadIdx.x == 0) *store = first;
@@ -712,6 +723,7 @@ int axpy_dev(const float* x, float* y, size_t n, const double* num, double den, 
 
 __global__ void scale_dev_kernel(float* __restrict__ y, size_t n, double num,
                                  const double* __restrict__ den) {
+  ST_PDL_ENTRY();
   const float coef = (float)(num / den[0]);
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
        i += (size_t)gridDim.x * blockDim.x)
@@ -751,6 +763,7 @@ __device__ __forceinline__ int lb_pair(const double* st, int j) {
 template <int MODE>
 __global__ void lb_dot_kernel(const float* __restrict__ ring, size_t n, int n_corr, double* st, int j,
                               const float* __restrict__ p, ReduceScratch rs) {
+  ST_PDL_ENTRY();
   const int k = lb_pair<MODE>(st, j);
   if (k < 0) return;
   const float* x = ring + (size_t)lb_slot(st, k, n_corr) * n;
@@ -773,6 +786,7 @@ __global__ void lb_dot_kernel(const float* __restrict__ ring, size_t n, int n_co
 template <int MODE>
 __global__ void lb_update_kernel(const float* __restrict__ ring, size_t n, int n_corr, double* st,
                                  int j, float* __restrict__ p) {
+  ST_PDL_ENTRY();
   const int k = lb_pair<MODE>(st, j);
   if (k < 0) return;
   const int slot = lb_slot(st, k, n_corr);
@@ -798,6 +812,7 @@ __global__ void lb_update_kernel(const float* __restrict__ ring, size_t n, int n
 __global__ void lb_step_kernel(const float* __restrict__ p, size_t n, int n_corr, const double* st,
                                float initial_step, float* __restrict__ ring_s,
                                float* __restrict__ params) {
+  ST_PDL_ENTRY();
   const int count = (int)st[0];
   double scale = 1.0;
   if (count == 0)
@@ -818,6 +833,7 @@ __global__ void lb_step_kernel(const float* __restrict__ p, size_t n, int n_corr
 __global__ void lb_y_kernel(const float* __restrict__ gn, const float* __restrict__ go, size_t n,
                             const float* __restrict__ ring_s, float* __restrict__ ring_y, double* st,
                             ReduceScratch rs) {
+  ST_PDL_ENTRY();
   const size_t off = (size_t)((int)st[1]) * n;
   const float* s = ring_s + off;
   float* y = ring_y + off;
@@ -837,6 +853,7 @@ __global__ void lb_y_kernel(const float* __restrict__ gn, const float* __restric
 
 // keep the candidate pair iff s.y > 1e-10 (:98-103): advance the head, grow the count up to n_corr
 __global__ void lb_commit_kernel(double* st, int n_corr) {
+  ST_PDL_ENTRY();
   const double sy = st[2];
   if (sy > 1e-10) {
     const int head = (int)st[1];
@@ -909,6 +926,7 @@ __global__ void __launch_bounds__(256)
 lbfgs_direction_coop_kernel(const float* __restrict__ grad, size_t n, int n_corr, float* ring_s,
                             const float* ring_y, double* st, float* p, float* params,
                             float initial_step, double* partials, unsigned* bar) {
+  ST_PDL_ENTRY();
   unsigned gen = 0;
   const int count = (int)st[0], head = (int)st[1];
   const size_t tid = blockIdx.x * (size_t)blockDim.x + threadIdx.x, nthr = (size_t)gridDim.x * blockDim.x;

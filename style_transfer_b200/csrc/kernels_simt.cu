@@ -33,6 +33,7 @@ struct ConvArgs {
 
 template <typename T, int CI, bool PLANAR>
 __global__ void __launch_bounds__(256) conv3x3_kernel(ConvArgs<T> a) {
+  ST_PDL_ENTRY();
   __shared__ __align__(16) float in_s[CI][kTH + 2][kTW + 2];
   __shared__ __align__(16) float w_s[9][CI][kCoT];
 
@@ -185,6 +186,7 @@ __global__ void __launch_bounds__(64) conv_last_bwd_kernel(const T* __restrict__
                                                            float* __restrict__ grad,
                                                            long batch_stride, long plane,
                                                            long rstride) {
+  ST_PDL_ENTRY();
   dz += (size_t)blockIdx.y * h * w * cz;
   grad += (size_t)blockIdx.y * batch_stride;
   __shared__ __align__(16) float in_s[kLH + 2][kLW + 2][kLPad];
@@ -270,6 +272,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 pool_fwd_kernel(const T* __restrict__ in_all, T* __restrict__ out, int nb, int h, int w, int c,
                 int ho, int wo, int is_max) {
+  ST_PDL_ENTRY();
   // 32-bit index arithmetic throughout: 64-bit div/mod made these kernels instruction-bound
   const unsigned c8 = c >> 3, uwo = wo, uho = ho;
   const unsigned total = (unsigned)nb * ho * wo * c8;
@@ -317,6 +320,7 @@ __global__ void __launch_bounds__(256)
 pool_bwd_kernel(const T* __restrict__ d_out, const TA* __restrict__ in_all, T* __restrict__ d_in_all,
                 int nb, int h, int w, int c, int ho, int wo, int is_max, int apply_mask,
                 const T* __restrict__ inj_all, const float* __restrict__ inj_scale) {
+  ST_PDL_ENTRY();
   const unsigned c4 = c >> 2, uwo = wo, uho = ho;
   const unsigned total = (unsigned)nb * ho * wo * c4;
   for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
@@ -385,6 +389,7 @@ __global__ void __launch_bounds__(256)
 pool_bwd_mask_kernel(const T* __restrict__ d_out, const uint8_t* __restrict__ mask,
                      T* __restrict__ d_in_all, int nb, int h, int w, int c, int ho, int wo, int is_max,
                      const T* __restrict__ inj_all, const float* __restrict__ inj_scale) {
+  ST_PDL_ENTRY();
   const unsigned c8 = c >> 3, uwo = wo, uho = ho;
   const unsigned total = (unsigned)nb * ho * wo * c8;
   for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
@@ -483,6 +488,7 @@ template <typename T, bool CM>
 __global__ void __launch_bounds__(256) gram_partial_kernel(const T* __restrict__ f, int hw, int c,
                                                            int px_per_split,
                                                            float* __restrict__ part) {
+  ST_PDL_ENTRY();
   __shared__ __align__(16) float a_s[kGP][kGS];
   __shared__ __align__(16) float b_s[kGP][kGS];
   int bi = 0, rem = blockIdx.x;
@@ -537,6 +543,7 @@ __global__ void __launch_bounds__(256) gram_partial_kernel(const T* __restrict__
 
 __global__ void gram_finalize_kernel(const float* __restrict__ part, int nsplit, int c,
                                      double scale, float* __restrict__ gram) {
+  ST_PDL_ENTRY();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= c * c) return;
   const int i = idx / c, j = idx % c;
@@ -578,6 +585,7 @@ int gram_full(const T* f, int hw, int c, bool channel_major, float* gram, float*
 __global__ void gram_delta_kernel(const float* __restrict__ gram, const float* __restrict__ target,
                                   float* __restrict__ delta, unsigned* max_bits, int c, double w,
                                   double* tile_loss, int loss_stride, ReduceScratch rs) {
+  ST_PDL_ENTRY();
   const size_t off = (size_t)blockIdx.y * c * c;
   double v[1] = {0.0};
   float mx = 0.f;
@@ -606,6 +614,7 @@ __global__ void __launch_bounds__(256)
 delta_pack_kernel(const float* __restrict__ delta, uint16_t* __restrict__ out, unsigned* max_bits,
                   float* eps_eff, int c, int half, const double* __restrict__ loss_part, int n_part,
                   double w, double* tile_loss, int loss_stride) {
+  ST_PDL_ENTRY();
   const size_t off = (size_t)blockIdx.y * c * c;
   if (loss_part != nullptr && blockIdx.x == 0) {
     // the style loss of this tile from the block partials of gram_tc_finish: thread t adds the
@@ -673,6 +682,7 @@ int delta_pack(const float* delta, void* delta_16, bool half, unsigned* max_bits
 __global__ void __launch_bounds__(256)
 sum_partials_kernel(const double* __restrict__ partials, int n, double* out, int out_stride,
                     float* scale, float w, double count, const float* __restrict__ eps_eff) {
+  ST_PDL_ENTRY();
   __shared__ double sh[256];
   const double* p = partials + (size_t)blockIdx.x * n;
   double x = 0.0;
@@ -698,6 +708,7 @@ int sum_partials(const double* partials, int n, int nb, double* out, int out_str
 
 // *loss_accum += tile_loss[0] + tile_loss[stride] + ... (tile order), then clears the slots.
 __global__ void loss_finalize_kernel(double* tile_loss, int stride, int nb, double* loss_accum) {
+  ST_PDL_ENTRY();
   double x = 0.0;
   for (int b = 0; b < nb; ++b) x += tile_loss[(size_t)b * stride], tile_loss[(size_t)b * stride] = 0.0;
   *loss_accum += x;
@@ -709,6 +720,7 @@ int loss_finalize(double* tile_loss, int stride, int nb, double* loss_accum, cud
 
 __global__ void symmetrize_kernel(const float* __restrict__ src, float* __restrict__ dst, int c,
                                   int to_lower) {
+  ST_PDL_ENTRY();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= c * c) return;
   const int i = idx / c, j = idx % c;
@@ -737,6 +749,7 @@ __global__ void __launch_bounds__(256) style_grad_kernel(const T* __restrict__ f
                                                          const float* __restrict__ delta,
                                                          T* __restrict__ s_out, int hw, int c,
                                                          double* sum_abs, ReduceScratch rs) {
+  ST_PDL_ENTRY();
   __shared__ __align__(16) float f_s[kSK][kSS];    // [k][pixel]
   __shared__ __align__(16) float d_s[kSK][kSS];    // [k][out channel]
   const int tid = threadIdx.x, tp = tid >> 4, tq = tid & 15;
@@ -801,6 +814,7 @@ template <typename T>
 __global__ void inject_scaled_kernel(T* __restrict__ inj, const T* __restrict__ src, size_t n4,
                                      float w, const double* __restrict__ sum_abs, int stat_stride,
                                      const float* __restrict__ eps_eff, int accumulate) {
+  ST_PDL_ENTRY();
   // blockIdx.y = tile of the batch; n4 = float4 groups per tile
   const float eps = eps_eff ? eps_eff[blockIdx.y] : kEps;
   const float coef =
@@ -862,6 +876,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 diff_stats_kernel(const T* __restrict__ f, DiffGeom g, const float* __restrict__ tgt,
                   TargetOffsets offs, double* stats, int stat_stride, ReduceScratch rs) {
+  ST_PDL_ENTRY();
   const int b = blockIdx.y;
   const unsigned row8 = (unsigned)g.wf * g.c8;
   f += (size_t)b * g.hf * row8 * 8;
@@ -913,6 +928,7 @@ diff_inject_kernel(const TA* __restrict__ f, DiffGeom g, const float* __restrict
                    TargetOffsets offs, const double* __restrict__ stats, int stat_stride, float w,
                    double loss_w, double* tile_loss, int loss_stride, T* __restrict__ inj,
                    int accumulate) {
+  ST_PDL_ENTRY();
   const int b = blockIdx.y;
   const unsigned row8 = (unsigned)g.wf * g.c8;
   f += (size_t)b * g.hf * row8 * 8, inj += (size_t)b * g.hf * row8 * 8;
@@ -956,6 +972,7 @@ int diff_inject(const TA* f, int nb, int hf, int wf, int c, const float* tgt, in
 // One thread per 32-channel chunk: bit (e >> 1) + 16 * (e & 1) of the word = act[chunk * 32 + e] > 0.
 template <typename T>
 __global__ void relu_bits_kernel(const T* __restrict__ act, uint32_t* __restrict__ bits, size_t words) {
+  ST_PDL_ENTRY();
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < words;
        i += (size_t)gridDim.x * blockDim.x) {
     uint32_t w = 0u;
@@ -987,6 +1004,7 @@ template int relu_bits_from_act<__half>(const __half*, uint32_t*, size_t, int, c
 template <typename TI, typename TO>
 __global__ void transpose_kernel(const TI* __restrict__ in, TO* __restrict__ out, long rows,
                                  long cols, int rows_on_x) {
+  ST_PDL_ENTRY();
   // in [rows][cols] -> out [cols][rows]; the long dimension goes on grid.x (2^31 blocks)
   __shared__ float tile[32][33];
   const long r0 = (long)(rows_on_x ? blockIdx.x : blockIdx.y) * 32;
