@@ -1041,7 +1041,7 @@ int launch2r(TcContext& tc, const void* in, const void* wk, int wk_rows,
   // (split mode: a.cin counts the three K segments; the algorithmic flops are a third of the executed)
   TimerScope ts(s, EPI == kEpiAbs ? kTimeStyleGrad : (EPI == kEpiPix ? kTimeConvSimt : kTimeConvTc),
                 2.0 * TAPS * (k32 ? a.cin / 3 : a.cin) * (EPI == kEpiPix ? 3 : a.cout) * a.h * a.w * a.nb);
-  ST_LAUNCH(kern, 2 * pairs, kThreads2, smem_bytes, s, map_in, map_w, map_out, map_pool, a);
+  ST_LAUNCH_ATTR(kern, 2 * pairs, kThreads2, smem_bytes, s, g_pdl, map_in, map_w, map_out, map_pool, a);
   return ST_OK;
 }
 

@@ -19,6 +19,7 @@ namespace st {
 static thread_local std::string g_error;
 std::atomic<uint64_t> g_launches{0};
 bool g_pdl = getenv("ST_NO_PDL") == nullptr;
+bool g_pdl_all = getenv("ST_PDL_ALL") != nullptr && getenv("ST_NO_PDL") == nullptr;
 void set_error(const std::string& msg) { g_error = msg; }
 
 // ---- per-kernel timing ---------------------------------------------------------------------------
