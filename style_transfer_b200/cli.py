@@ -35,11 +35,12 @@ def resize_to_fit(image, size, div=1, scale_up=False):
 
 def resize_f32(tensor, hw, method='lanczos'):
     """``num_utils.resize`` (:90-108): per-channel float resampling of a CUDA f32 [C][H][W] tensor.
-    Default: through PIL 'F' images on the host, exactly as the reference does (once per scale).
-    ``ST_DEVICE_RESIZE=1`` keeps the data on the device (``st_resize_f32``: the same algorithm,
-    bit-identical to PIL on the B200)."""
+    Default: on the device (``st_resize_f32``: Pillow's float resampling restated, bit-identical to
+    PIL on the B200 -- tests/test_gpu_parity.py::test_device_resize_matches_oracle, and the two-scale
+    run of tests/test_gpu_parity_configs.py).  ``ST_HOST_RESIZE=1`` goes through PIL 'F' images on
+    the host instead, exactly as the reference does (once per scale)."""
     import torch
-    if os.environ.get('ST_DEVICE_RESIZE') == '1' and tensor.is_cuda:
+    if os.environ.get('ST_HOST_RESIZE') != '1' and tensor.is_cuda:
         return resize_f32_device(tensor, hw, method)
     from PIL import Image
     m = {'lanczos': Image.LANCZOS, 'bilinear': Image.BILINEAR}[method]
