@@ -26,6 +26,9 @@ agg = {}
 for r in data:
     name = re.sub(r'\(.*', '', r[col['Kernel Name']]).replace('void ', '').replace('st::', '').replace('<unnamed>::', '')
     base = re.sub(r'<.*', '', name)
+    m = re.match(r'conv_tc2_kernel<\s*\d+,\s*(\d+)', name)
+    if m and m.group(1) == '1':
+        base = 'conv_tc2_kernel_1x1'          # the style GEMM; 'conv_tc2_kernel' = the 3x3 convolutions
     rd = float(r[col['dram__bytes_read.sum']].replace(',', '')) * scale(units[col['dram__bytes_read.sum']])
     wr = float(r[col['dram__bytes_write.sum']].replace(',', '')) * scale(units[col['dram__bytes_write.sum']])
     t = float(r[col['gpu__time_duration.sum']].replace(',', ''))
