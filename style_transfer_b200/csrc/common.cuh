@@ -75,10 +75,15 @@ extern bool g_pdl_all;      // ST_PDL_ALL=1: for every kernel, not only the conv
 // the ordering the code relies on is unchanged -- only the launch latency (and, where the wait is
 // placed after a prologue, that prologue) overlaps the predecessor's tail.  A step is ~62 dependent
 // launches; the gaps between them were ~0.3 ms of a 6 ms step (profiles/r02_launches_step_b.md).
-#define ST_PDL_ENTRY()                                                \
-  do {                                                                \
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   \
-    asm volatile("griddepcontrol.wait;" ::: "memory");                \
+// The early trigger is only issued by grids that are certainly resident as a whole (at most half the
+// thread capacity of the device, kernels without large shared memory): with ST_PDL_ALL=1 an early
+// trigger from a multi-wave grid (16-tile batches: 1000-4000 blocks) hung the device.
+#define ST_PDL_ENTRY()                                                                        \
+  do {                                                                                        \
+    if ((size_t)gridDim.x * gridDim.y * gridDim.z * (blockDim.x * blockDim.y * blockDim.z) <= \
+        (size_t)148 * 1024)                                                                   \
+      asm volatile("griddepcontrol.launch_dependents;" ::: "memory");                         \
+    asm volatile("griddepcontrol.wait;" ::: "memory");                                        \
   } while (0)
 
 inline int cdiv(long a, long b) { return (int)((a + b - 1) / b); }

@@ -164,7 +164,8 @@ template <int C>
 __global__ void __launch_bounds__(kGThreads, C <= 128 ? 2 : 1)
 gram_tc_kernel(const __grid_constant__ CUtensorMap map_f, const GramArgs a) {
   // PDL: barrier init / TMEM allocation overlap the previous kernel's tail; features are read below
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  if (gridDim.x * gridDim.y <= (C <= 128 ? 296u : 148u))       // only when the whole grid is resident
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   using Cfg = GramCfg<C>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
