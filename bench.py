@@ -70,8 +70,17 @@ def workload_config(a, world):
                     'layer, tv+p-norm regularisers, %s' % (a.size, a.size, ntiles, a.tile_size,
                                                            a.optimizer),
         'size': a.size, 'tile_size': a.tile_size, 'tiles': ntiles, 'optimizer': a.optimizer,
-        'tiles_per_gpu': -(-ntiles // world), 'parallelism': 'tiles round-robin over %d GPU(s)' % world,
+        # both arms name the same workload: its working set per step is far larger than any cache
+        'l2': 'no explicit flush: one step streams %d MB of image + optimizer state and >= 152 MB of '
+              'activations per tile, both larger than the 126 MB L2' % (6 * 3 * a.size * a.size * 4 >> 20),
     }
+
+
+def layout_config(a, world):
+    ntiles = ((a.size - 1) // a.tile_size + 1) ** 2
+    return {'tiles_per_gpu': -(-ntiles // world),
+            'parallelism': 'tiles round-robin over %d GPU(s), one NCCL all-gather per evaluation' % world,
+            'precision': a.precision}
 
 
 def synthetic_rgb(seed, size):
@@ -701,17 +710,14 @@ def run_engine(a):
 
     if rank == 0:
         cfg = workload_config(a, world)
-        cfg['l2'] = ('no explicit flush: one step streams the %d MB of image + optimizer state and '
-                     '~%d MB of activations per tile, both larger than the 126 MB L2'
-                     % (6 * n * 4 >> 20, 304 if a.precision in ('fp32', 'tc32') else 152))
-        cfg['precision'] = a.precision
+        layout = layout_config(a, world)
         line = {
             'metric': METRIC, 'value': value, 'unit': 'iterations/s', 'n_gpus': world,
             'steps': a.steps, 'warmup': a.warmup, 'ms_per_step': ms / a.steps,
             'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
             'dtype': {'bf16': 'bf16', 'fp16': 'f16 forward / bf16 backward', 'fp32': 'f32',
                       'tc32': 'f32 storage, split f16 hi+lo tensor-core operands, f32 accumulate'}[a.precision],
-            'data': 'synthetic', 'config': cfg,
+            'data': 'synthetic', 'config': cfg, 'layout': layout,
             'step_is': 'one pass of the loop body (style_transfer.py:777-821): roll, 16-tile objective, '
                        'regularisers, optimizer step, update-size / TV statistics, uint8 picture',
             'clocks': clocks, 'e2e': e2e, 'gpu_launches': launches,
@@ -719,7 +725,7 @@ def run_engine(a):
             'roofline_gram': roofline_gram, 'records': records,
             'cpu_baseline': cpu, 'breakdown': breakdown,
             'tile_eval_ms': breakdown and sum(v['ms_per_step'] for k, v in breakdown.items()
-                                              if k != 'image') / cfg['tiles_per_gpu'],
+                                              if k != 'image') / layout['tiles_per_gpu'],
         }
         print(json.dumps(line), flush=True)
     if world > 1:

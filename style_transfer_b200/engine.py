@@ -272,10 +272,20 @@ class TileEngine:
             self.contents.append(ContentData(feats))
         self.img, self.roll_px = saved_img, saved_roll
 
-    def set_contents_and_styles(self, contents=None, styles=None):
+    def set_contents_and_styles(self, contents=None, styles=None, contents_only=False):
         """``TileWorkerPool.set_contents_and_styles`` (:309-332): hands the targets to the
-        worker -- here, copies them into the library context of this rank's GPU."""
+        worker -- here, copies them into the library context of this rank's GPU.
+        ``contents_only``: the per-iteration update of ``--jitter`` (:788-794) -- the content feature
+        maps are overwritten in place (same shapes: no free / allocate, no device synchronisation),
+        the style Grams stay as they are."""
         contents = self.contents if contents is None else contents
+        if contents_only:
+            for i, content in enumerate(contents):
+                for layer, feat in content.features.items():
+                    feat = self.to_device(feat)
+                    _lib.call('st_set_content_features', self.ctx, i, self.net.blob_index(layer),
+                              _ptr(feat), feat.shape[1], feat.shape[2], _stream())
+            return
         styles = self.styles if styles is None else styles
         _lib.call('st_clear_targets', self.ctx)
         for i, content in enumerate(contents):

@@ -127,6 +127,7 @@ class StyleTransfer:
         if not getattr(a, 'style_multiscale', None):                 # (:754-755)
             model.styles = []
         self.jitter = bool(getattr(a, 'jitter', False))
+        self._jitter_primed = False
         if self.jitter:
             # --jitter (:757-759): only the styles now; the content features are recomputed from the
             # rolled content image(s) in every iteration
@@ -175,7 +176,9 @@ class StyleTransfer:
         model.contents = []
         model.preprocess_images([torch.roll(c, sh, dims=(-2, -1)) for c in self._content_images], [],
                                 self.c_layers, [], a.tile_size, content_passes=1)
-        model.set_contents_and_styles()
+        # only the content features change: overwritten in place, the style Grams stay on the device
+        model.set_contents_and_styles(contents_only=self._jitter_primed)
+        self._jitter_primed = True
         sc_args = (np.zeros(2, dtype=np.int64), self.c_layers, self.s_layers, self.d_layers,
                    self.layer_weights, self.c_weight, self.s_weight, self.d_weight, a.tile_size)
 
