@@ -91,6 +91,11 @@ int split_f32(const float* in, void* out_hi_lo, size_t pixels, int c, float scal
 int conv3x3_tc32(TcContext& tc, const TcWeights& w, const float* in, float* out, int nb, int h,
                  int wd, int cin, int cout, bool forward, const float* bias, const float* mask_act,
                  const float* inj, float in_scale, void* split_buf, cudaStream_t s);
+// Style GEMM of the split-operand mode: S_b = F_b * D_b in fp32 from the [hi | lo] planes of F and the
+// fp32 delta-Gram (split on the fly with a per-tile power-of-two scale), sum |S_b| as partial sums.
+int gemm_abs_tc32(TcContext& tc, const void* f_split, const float* delta, const unsigned* max_bits,
+                  void* d_split, float* inv_sigma, float* s_out, int nb, int h, int w, int c,
+                  double* abs_partials, int* per_tile, cudaStream_t s);
 // Forward convolution + the 2x2/2 pooling layer behind it in one kernel.  pool_out [nb][ho][wo][cout]
 // receives the pooled map, pool_mask (bytes, same shape) what pool_bwd_mask needs:
 //   max: bits 0-1 = window position of the first maximum, bit 2 = maximum > 0
@@ -127,6 +132,12 @@ int gemm_abs_tc_pair(TcContext& tc, const void* f, const void* d, bool half_in, 
                      cudaStream_t s);
 size_t gemm_abs_partials_needed(int nb, int h, int w, int c);
 
+// ST_PREC_TC32: Gram matrices of fp32 features on the tensor cores, from the [hi | lo] fp16 planes of
+// split_f32 (gram_tc.cu).  gram [nb][C][C] full symmetric fp32.
+bool gram_tc32_ok(const TcContext& tc, int c);
+size_t gram_tc32_part_floats(int nb, int hw, int c);
+int gram_tc32(TcContext& tc, const void* f_split, int nb, int hw, int c, float* part, float* gram,
+              cudaStream_t s);
 // G_b = F_b^T F_b / (C*hw) for 16-bit NHWC F [nb][hw][c] on tcgen05 (gram_tc.cu), finished straight
 // into the style term.  part: split-K scratch of gram_tc_part_floats() floats.
 bool gram_tc_ok(const TcContext& tc, int c);

@@ -69,7 +69,7 @@ constexpr int kSmemBudget = 227 * 1024 - 1024 /*alignment slack*/ - kTailBytes;
 // product, ~22 significant bits per operand); the epilogue works in fp32 and stores fp32 straight
 // from registers (each thread owns 32 consecutive channels of one pixel = one 128-byte line).
 enum Epilogue { kEpiFwd = 0, kEpiBwd = 1, kEpiAbs = 2, kEpiPix = 3, kEpiFwdPool = 4, kEpiFwd32 = 5,
-                kEpiBwd32 = 6 };
+                kEpiBwd32 = 6, kEpiAbs32 = 7 };   // kEpiAbs32: the style GEMM of the split-operand mode
 constexpr int kPoolStageBytes = 32 * 128;   // 8 x 4 pooled pixels x 64 channels bf16
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------
@@ -293,6 +293,7 @@ struct Tc2Args {
   int a_wrap;                      // split mode: A channel block of K block cb is cb - a_wrap once
                                    // cb >= a_wrap (the third K segment re-reads the hi planes); else 1 << 30
   float out_scale;                 // split mode: accumulator factor (1 / (weight scale * input scale))
+  const float* out_scale_tile;     // kEpiAbs32: one more factor per batch tile (1 / sigma of its delta-Gram)
   const float* mask_f32;           // kEpiBwd32: fp32 activation whose sign is the ReLU mask, may be null
   const float* inj_f32;            // kEpiBwd32: fp32 injected gradient, may be null
   float* out_f32;                  // kEpiFwd32 / kEpiBwd32: fp32 NHWC output
@@ -370,7 +371,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constan
   // map_aux: the pooled output (kEpiFwdPool) or the injected gradient (kEpiBwd, same geometry as out)
   constexpr bool kPool = EPI == kEpiFwdPool;
   constexpr bool kFwd = EPI == kEpiFwd || EPI == kEpiFwdPool;
-  constexpr bool k32 = EPI == kEpiFwd32 || EPI == kEpiBwd32;
+  constexpr bool k32 = EPI == kEpiFwd32 || EPI == kEpiBwd32 || EPI == kEpiAbs32;
   using Cfg = Cfg2<BN, TAPS, RESB, kPool, EPI == kEpiBwd>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -388,7 +389,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constan
   // accumulation CHAIN (see the k32 epilogue)
   constexpr int kNT = k32 ? 4 : 2;
   constexpr int kTmemCols = k32 ? (4 * BN < 32 ? 32 : 4 * BN) : Cfg::kTmemCols;
-  static_assert(!k32 || (BN <= 128 && !RESB && Cfg::kTB == 3), "split-operand mode: BN <= 128, staged weights");
+  static_assert(!k32 || (BN <= 128 && !RESB), "split-operand mode: BN <= 128, staged weights");
   uint64_t* t_full = b_empty + Cfg::kSB;
   uint64_t* t_empty = t_full + kNT;
   uint64_t* e_full = t_empty + kNT;        // injected-gradient ring (backward epilogue)
@@ -713,9 +714,25 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constan
           const int cc = g * 2 + hsel;
           const size_t eofs = cur.gofs + (size_t)cc * 32;
           float* v = acc[g];
+          float osc = a.out_scale;
+          if constexpr (EPI == kEpiAbs32) osc *= __ldg(a.out_scale_tile + t.b);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] *= a.out_scale;
-          if constexpr (EPI == kEpiFwd32) {
+          for (int i = 0; i < 32; ++i) v[i] *= osc;
+          if constexpr (EPI == kEpiAbs32) {
+            // sum |S| over this warp's 32 rows x 32 channels, one slot per (pixel tile, 64-channel
+            // group, CTA, warp) like kEpiAbs: added up later in slot order (rows outside the tile
+            // hold exact zeros: their A rows were zero-filled)
+            float at = 0.f;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) at += fabsf(v[i]);
+            double x = (double)at;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+            const int m_tile = tile / a.tiles_n;
+            const int g64 = n_tile * (BN / 64) + g;
+            if (lane == 0)
+              a.abs_partials[(((size_t)m_tile * (a.cout >> 6) + g64) * 2 + rank) * 8 + hsel * 4 + q] = x;
+          } else if constexpr (EPI == kEpiFwd32) {
             const float* bs = bias_s + n_tile * BN + cc * 32;
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i] + bs[i], 0.f);
@@ -993,7 +1010,7 @@ int launch2r(TcContext& tc, const void* in, const void* wk, int wk_rows,
     if (rc != ST_OK) return rc;
   }
   if (a.a_wrap == 0) a.a_wrap = 1 << 30;
-  constexpr bool k32 = EPI == kEpiFwd32 || EPI == kEpiBwd32;
+  constexpr bool k32 = EPI == kEpiFwd32 || EPI == kEpiBwd32 || EPI == kEpiAbs32;
   if (EPI != kEpiPix && !k32) {
     const uint64_t dims[4] = {(uint64_t)a.cout, (uint64_t)a.w, (uint64_t)a.h, (uint64_t)a.nb};
     const uint64_t strides[3] = {(uint64_t)a.cout * 2, (uint64_t)a.w * a.cout * 2,
@@ -1039,7 +1056,7 @@ int launch2r(TcContext& tc, const void* in, const void* wk, int wk_rows,
   const int pairs = tiles < max_pairs ? tiles : max_pairs;
   // algorithmic flops: the pixel epilogue computes 3 of its 16 accumulator columns for real
   // (split mode: a.cin counts the three K segments; the algorithmic flops are a third of the executed)
-  TimerScope ts(s, EPI == kEpiAbs ? kTimeStyleGrad : (EPI == kEpiPix ? kTimeConvSimt : kTimeConvTc),
+  TimerScope ts(s, (EPI == kEpiAbs || EPI == kEpiAbs32) ? kTimeStyleGrad : (EPI == kEpiPix ? kTimeConvSimt : kTimeConvTc),
                 2.0 * TAPS * (k32 ? a.cin / 3 : a.cin) * (EPI == kEpiPix ? 3 : a.cout) * a.h * a.w * a.nb);
   ST_LAUNCH_ATTR(kern, 2 * pairs, kThreads2, smem_bytes, s, g_pdl, map_in, map_w, map_out, map_pool, a);
   return ST_OK;
@@ -1230,6 +1247,56 @@ int conv3x3_tc32(TcContext& tc, const TcWeights& w, const float* in, float* out,
   }
   if (bn == 128) return launch2r<128, 9, kEpiBwd32, false>(tc, split_buf, w.bwd32, cout, nullptr, nullptr, a, s);
   return launch2r<64, 9, kEpiBwd32, false>(tc, split_buf, w.bwd32, cout, nullptr, nullptr, a, s);
+}
+
+// ---- style GEMM of the split-operand mode ------------------------------------------------------------
+namespace {
+// delta [nb][c][c] fp32 -> fp16 rows [nb][c][3c] = [Dhi | Dhi | Dlo] of delta * sigma_b, sigma_b the power
+// of two that puts max |delta_b| (max_bits[b], float bits) into [2^12, 2^13); inv_sigma[b] = 1 / sigma_b
+__global__ void __launch_bounds__(256)
+delta_split_kernel(const float* __restrict__ delta, const unsigned* __restrict__ max_bits,
+                   __half* __restrict__ out, float* __restrict__ inv_sigma, int c) {
+  ST_PDL_ENTRY();
+  const int b = blockIdx.y;
+  const float mx = __uint_as_float(max_bits[b]);
+  float sigma = 1.f;
+  if (mx > 0.f && isfinite(mx)) {
+    int e;
+    frexpf(mx, &e);
+    sigma = ldexpf(1.f, 13 - e);
+  }
+  const float* d = delta + (size_t)b * c * c;
+  __half* o = out + (size_t)b * c * 3 * c;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < c * c; idx += gridDim.x * blockDim.x) {
+    const int n = idx / c, k = idx - n * c;
+    const float v = d[idx] * sigma;
+    const __half hi = __float2half_rn(v);
+    const __half lo = __float2half_rn(v - __half2float(hi));
+    __half* row = o + (size_t)n * 3 * c;
+    row[k] = hi, row[c + k] = hi, row[2 * c + k] = lo;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) inv_sigma[b] = 1.f / sigma;
+}
+}  // namespace
+
+// Per batch tile b: S_b[p][n] = sum_c F_b[p][c] * D_b[n][c] in fp32 from the [hi | lo] planes of F
+// (f_split [nb][h][w][2c] fp16, split_f32 with scale 1) and the fp32 delta-Gram D_b (symmetric
+// [c][c]); d_split: scratch of nb * c * 3c fp16, inv_sigma: nb floats; max_bits[b] = max |D_b| as
+// float bits.  sum |S_b| is left as partial sums like gemm_abs_tc_pair.
+int gemm_abs_tc32(TcContext& tc, const void* f_split, const float* delta, const unsigned* max_bits,
+                  void* d_split, float* inv_sigma, float* s_out, int nb, int h, int w, int c,
+                  double* abs_partials, int* per_tile, cudaStream_t s) {
+  ST_LAUNCH(delta_split_kernel, dim3(std::min(cdiv((long)c * c, 256), 64), nb), 256, 0, s, delta, max_bits,
+            static_cast<__half*>(d_split), inv_sigma, c);
+  Tc2Args a{};
+  a.nb = nb, a.h = h, a.w = w, a.cin = 3 * c, a.cout = c, a.w_batched = 1;
+  a.cin_map = 2 * c, a.a_wrap = 2 * (c / 64);
+  a.in_half = 1, a.out_half = 0, a.out_scale = 1.f, a.out_scale_tile = inv_sigma;
+  a.abs_partials = abs_partials, a.out_f32 = s_out;
+  *per_tile = cdiv(w, kBW) * cdiv(h, 2 * kBH) * (c / 64) * 16;
+  const int bn = std::min(choose_bn(tc, nb, h, w, c), 128);
+  if (bn == 128) return launch2r<128, 1, kEpiAbs32, false>(tc, f_split, d_split, c, nullptr, nullptr, a, s);
+  return launch2r<64, 1, kEpiAbs32, false>(tc, f_split, d_split, c, nullptr, nullptr, a, s);
 }
 
 // Per batch tile b: S_b[p][n] = sum_c F_b[p][c] * D_b[n][c]  (D_b symmetric bf16 [c][c]).  The sum

@@ -115,6 +115,7 @@ struct st_ctx {
   void* split_buf = nullptr; // ST_PREC_TC32: fp16 [hi | lo] copy of the convolution input in flight
   size_t split_cap = 0;      // elements (4 bytes each)
   float grad_scale = 1.f;    // ST_PREC_TC32: power of two applied to gradients before the fp16 split
+  bool tc32_simt_gram = false;   // ST_TC32_SIMT_GRAM=1: tc32 Gram matrices on the SIMT kernel
   // per batch tile: Gram [C][C], its difference to the target (fp32 and the bf16 copy that is the
   // B operand of the tcgen05 style GEMM)
   float *gram = nullptr, *delta = nullptr, *part = nullptr;
@@ -405,16 +406,32 @@ int build_injection(st_ctx* ctx, const st_loss_spec& sp, const Dims& d, const Ba
           set_error("invalid: ST_PREC_FP16 has no SIMT Gram kernel (channels must be 64/128/256/512)");
           return ST_ERR_INVALID;
         } else {
-          // the SIMT Gram kernel takes one tile at a time (fp32 mode: nb = 1; tc32 mode: a batch)
           rc = ST_OK;
-          for (int bi = 0; bi < nb && rc == ST_OK; ++bi)
+          bool gram_done = false;
+          if constexpr (std::is_same<TA, float>::value) {
+            if (ctx->precision == ST_PREC_TC32 && gram_tc32_ok(ctx->tc, c) && !ctx->tc32_simt_gram) {
+              // tc32: the Gram contraction on the tensor cores from the [hi | lo] planes of F
+              size_t cap = ctx->part_floats;
+              rc = ensure(ctx, (void**)&ctx->part, &cap, gram_tc32_part_floats(nb, hf * wf, c), 4);
+              ctx->part_floats = cap;
+              if (rc == ST_OK) rc = split_f32(f, ctx->split_buf, (size_t)nb * hf * wf, c, 1.f, s);
+              if (rc == ST_OK)
+                rc = gram_tc32(ctx->tc, ctx->split_buf, nb, hf * wf, c, ctx->part, ctx->gram, s);
+              gram_done = true;
+            }
+          }
+          // the SIMT Gram kernel takes one tile at a time (fp32 mode: nb = 1; tc32 mode: a batch)
+          for (int bi = 0; bi < nb && rc == ST_OK && !gram_done; ++bi)
             rc = gram_full<TA>(f + (size_t)bi * n, hf * wf, c, false, ctx->gram + (size_t)bi * c * c,
                                ctx->part, ctx->part_floats, ctx->sm_count, s);
         }
       }
+      bool style_tc32 = false;
+      if constexpr (std::is_same<TA, float>::value && std::is_same<T, float>::value)
+        style_tc32 = ctx->precision == ST_PREC_TC32 && !ctx->tc32_simt_gram && ctx->delta_16 != nullptr;
       if (rc == ST_OK && !on_tc)
         rc = gram_delta(ctx->gram, it->second, ctx->delta, nullptr, kHalf, ctx->delta_max,
-                        ctx->eps_eff, c, nb, w, tile_loss, kStatStride, ctx->rs, s);
+                        ctx->eps_eff, c, nb, w, tile_loss, kStatStride, ctx->rs, s, style_tc32);
       if (rc != ST_OK) return rc;
       const float* eps_eff = on_tc ? ctx->eps_eff : nullptr;
       // the scale-and-copy pass over S can be skipped when S is this blob's whole injection and a
@@ -442,8 +459,27 @@ int build_injection(st_ctx* ctx, const st_loss_spec& sp, const Dims& d, const Ba
           }
         }
       } else {
+        if constexpr (std::is_same<TA, float>::value && std::is_same<T, float>::value) {
+          if (style_tc32 && rc == ST_OK) {
+            // tc32: S = F sym(dG) on the tensor cores from the [hi | lo] planes (still in split_buf when
+            // the Gram ran there; made here for the 512-channel layers whose Gram is the SIMT one)
+            int per_tile = 0;
+            if (!gram_tc32_ok(ctx->tc, c))
+              rc = split_f32(f, ctx->split_buf, (size_t)nb * hf * wf, c, 1.f, s);
+            if (rc == ST_OK)
+              rc = ensure(ctx, (void**)&ctx->abs_partials, &ctx->abs_cap,
+                          gemm_abs_partials_needed(nb, hf, wf, c), sizeof(double));
+            if (rc == ST_OK)
+              rc = gemm_abs_tc32(ctx->tc, ctx->split_buf, ctx->delta, ctx->delta_max, ctx->delta_16,
+                                 ctx->eps_eff, static_cast<float*>(ctx->sbuf), nb, hf, wf, c,
+                                 ctx->abs_partials, &per_tile, s);
+            if (rc == ST_OK)
+              rc = sum_partials(ctx->abs_partials, per_tile, nb, stats + 2, kStatStride, nullptr,
+                                (float)w, (double)n, nullptr, s);
+          }
+        }
         if constexpr (std::is_same<TA, T>::value) {
-          for (int bi = 0; bi < nb && rc == ST_OK; ++bi)
+          for (int bi = 0; bi < nb && rc == ST_OK && !style_tc32; ++bi)
             rc = style_grad<T>(f + (size_t)bi * n, ctx->delta + (size_t)bi * c * c,
                                static_cast<T*>(ctx->sbuf) + (size_t)bi * n, hf * wf, c,
                                stats + 2 + (size_t)bi * kStatStride, ctx->rs, s);
@@ -683,6 +719,7 @@ int st_create(int device, int precision, int n_layers, const st_layer_desc* laye
   st_ctx* ctx = new st_ctx();
   ctx->device = device, ctx->precision = precision, ctx->sm_count = prop.multiProcessorCount;
   ctx->esize = (precision == ST_PREC_FP32 || precision == ST_PREC_TC32) ? 4 : 2;
+  ctx->tc32_simt_gram = getenv("ST_TC32_SIMT_GRAM") != nullptr;
   DeviceGuard guard(device);
   ctx->blobs.resize(n_layers + 1);
   ctx->blobs[0].c = 3;
@@ -722,8 +759,9 @@ int st_create(int device, int precision, int n_layers, const st_layer_desc* laye
   const size_t gram_floats = (size_t)ctx->max_batch * 512 * 512;
   if (rc == ST_OK) rc = dev_alloc(ctx, (void**)&ctx->gram, gram_floats * sizeof(float));
   if (rc == ST_OK) rc = dev_alloc(ctx, (void**)&ctx->delta, gram_floats * sizeof(float));
-  if (rc == ST_OK && precision != ST_PREC_FP32 && precision != ST_PREC_TC32) {
-    rc = dev_alloc(ctx, (void**)&ctx->delta_16, gram_floats * 2);
+  if (rc == ST_OK && precision != ST_PREC_FP32) {
+    // 16-bit copy of the delta-Gram: [C][C], or [C][3C] = [Dhi | Dhi | Dlo] in the tc32 mode
+    rc = dev_alloc(ctx, (void**)&ctx->delta_16, gram_floats * (precision == ST_PREC_TC32 ? 6 : 2));
     if (rc == ST_OK) rc = dev_alloc(ctx, (void**)&ctx->eps_eff, kMaxBatch * sizeof(float));
     if (rc == ST_OK) rc = dev_alloc(ctx, (void**)&ctx->delta_max, kMaxBatch * sizeof(unsigned));
   }

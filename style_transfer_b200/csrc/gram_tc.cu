@@ -414,7 +414,93 @@ int launch_gram(TcContext& tc, const void* f, bool half, int nb, int hw, float* 
   return ST_OK;
 }
 
+// ---- Gram matrix of an fp32 feature map on the tensor cores (ST_PREC_TC32) -------------------------
+// The features arrive as the fp16 [hi | lo] planes of split_f32 (2C channels per pixel); the Gram
+// kernel above runs on them as a 2C-channel map and delivers per split the four quadrants
+// [[hi^T hi, hi^T lo], [lo^T hi, lo^T lo]], whose sum is F^T F to ~2^-22.  The tensor core truncates
+// when it accumulates (conv_tc2.cu), so a split covers only kChainKb k-blocks (32 MMA steps: a bias of
+// ~1e-6); the many partial blocks are added in double by the fold kernel in split order.
+constexpr int kChainKb = 8;
+
+__global__ void __launch_bounds__(256)
+gram_fold_kernel(const float* __restrict__ part, int nsplit, int c, double scale, float* __restrict__ gram) {
+  ST_PDL_ENTRY();
+  // blockIdx.x = row i of the C x C result, blockIdx.y = tile of the batch.  The 256 threads are
+  // 256 / C groups of C columns; group g adds the splits s = g, g + groups, ... (coalesced rows of
+  // the four quadrants), the groups are then added in index order: deterministic.
+  __shared__ double sh[256];
+  const int c2 = 2 * c, i = blockIdx.x;
+  const int j = threadIdx.x % c, g = threadIdx.x / c, groups = 256 / c;
+  const size_t pstride = (size_t)c2 * c2;
+  const float* p = part + (size_t)blockIdx.y * nsplit * pstride;
+  const size_t o00 = (size_t)i * c2 + j, o01 = o00 + c, o10 = (size_t)(c + i) * c2 + j, o11 = o10 + c;
+  double sum = 0.0;
+#pragma unroll 4
+  for (int s = g; s < nsplit; s += groups) {
+    const float* q = p + (size_t)s * pstride;
+    sum += ((double)q[o00] + (double)q[o01]) + ((double)q[o10] + (double)q[o11]);
+  }
+  sh[threadIdx.x] = sum;
+  __syncthreads();
+  if (g == 0) {
+    for (int k = 1; k < groups; ++k) sum += sh[k * c + j];
+    gram[((size_t)blockIdx.y * c + i) * c + j] = (float)(sum * scale);
+  }
+}
+
+template <int C2>
+int launch_gram_split(TcContext& tc, const void* f_split, int nb, int hw, float* part, float* gram,
+                      cudaStream_t s) {
+  using Cfg = GramCfg<C2>;
+  CUtensorMap map_f;
+  {
+    cuuint64_t gdim[3] = {(cuuint64_t)C2, (cuuint64_t)hw, (cuuint64_t)nb};
+    cuuint64_t gstride[2] = {(cuuint64_t)C2 * 2, (cuuint64_t)hw * C2 * 2};
+    cuuint32_t box[3] = {64, 64, 1}, estride[3] = {1, 1, 1};
+    CUresult r = reinterpret_cast<EncodeTiledFn>(tc.encode_fn)(
+        &map_f, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(f_split), gdim, gstride, box,
+        estride, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      set_error("cuTensorMapEncodeTiled (split gram) failed with CUresult " + std::to_string((int)r));
+      return ST_ERR_CUDA;
+    }
+  }
+  GramArgs a{};
+  a.hw = hw, a.kb_total = cdiv(hw, 64), a.part = part, a.half = 1;
+  a.kb_per_split = kChainKb;
+  a.nsplit = cdiv(a.kb_total, kChainKb);
+  auto kern = gram_tc_kernel<C2>;
+  ST_CUDA(tc_allow_smem(kern, Cfg::kSmemBytes));
+  TimerScope ts(s, kTimeGram, 2.0 * (C2 / 2) * (C2 / 2) * hw * nb);
+  ST_LAUNCH(kern, dim3(a.nsplit * Cfg::kMBlocks, nb), kGThreads, Cfg::kSmemBytes, s, map_f, a);
+  const int c = C2 / 2;
+  ST_LAUNCH(gram_fold_kernel, dim3(c, nb), 256, 0, s, part, a.nsplit, c, 1.0 / ((double)c * hw), gram);
+  return ST_OK;
+}
+
 }  // namespace
+
+bool gram_tc32_ok(const TcContext& tc, int c) {
+  return tc.enabled && tc.pair_kernel && (c == 64 || c == 128 || c == 256);
+}
+
+size_t gram_tc32_part_floats(int nb, int hw, int c) {
+  return (size_t)nb * cdiv(cdiv(hw, 64), kChainKb) * (2 * c) * (2 * c);
+}
+
+// gram[b] (full symmetric [C][C] fp32) = F_b^T F_b / (C * hw) from the [hi | lo] fp16 planes
+// f_split [nb][hw][2C] of the fp32 features; part: gram_tc32_part_floats() floats of scratch.
+int gram_tc32(TcContext& tc, const void* f_split, int nb, int hw, int c, float* part, float* gram,
+              cudaStream_t s) {
+  switch (c) {
+    case 64: return launch_gram_split<128>(tc, f_split, nb, hw, part, gram, s);
+    case 128: return launch_gram_split<256>(tc, f_split, nb, hw, part, gram, s);
+    case 256: return launch_gram_split<512>(tc, f_split, nb, hw, part, gram, s);
+  }
+  set_error("gram_tc32: unsupported channel count");
+  return ST_ERR_INVALID;
+}
 
 bool gram_tc_ok(const TcContext& tc, int c) {
   return tc.enabled && tc.pair_kernel && (c == 64 || c == 128 || c == 256 || c == 512);

@@ -72,9 +72,10 @@ int gram_full(const T* f, int hw, int c, bool channel_major, float* gram, float*
 // tile_loss[b * loss_stride] += w * 0.5 * sum_{j<=i} delta_ij^2.  delta_16 (optional) receives the
 // 16-bit copy for the tensor-core style GEMM: bf16, or fp16 scaled per tile by a power of two
 // (half) -- eps_eff[b] is the EPS that compensates that scaling in normalize().
+// (track_max: max_bits[b] = max |delta_b| even without a 16-bit copy)
 int gram_delta(const float* gram, const float* target, float* delta, void* delta_16, bool half,
                unsigned* max_bits, float* eps_eff, int c, int nb, double w, double* tile_loss,
-               int loss_stride, ReduceScratch rs, cudaStream_t s);
+               int loss_stride, ReduceScratch rs, cudaStream_t s, bool track_max = false);
 // The 16-bit copy of delta alone (second half of gram_delta): bf16, or fp16 scaled per tile by the
 // power of two derived from max_bits[b]; eps_eff[b] as in gram_delta.
 // With loss_part (optional): tile_loss[b * loss_stride] += w * 0.5 * sum_i loss_part[b * n_part + i],

@@ -656,8 +656,8 @@ delta_pack_kernel(const float* __restrict__ delta, uint16_t* __restrict__ out, u
 
 int gram_delta(const float* gram, const float* target, float* delta, void* delta_16, bool half,
                unsigned* max_bits, float* eps_eff, int c, int nb, double w, double* tile_loss,
-               int loss_stride, ReduceScratch rs, cudaStream_t s) {
-  const bool track = delta_16 != nullptr && half;
+               int loss_stride, ReduceScratch rs, cudaStream_t s, bool track_max) {
+  const bool track = (delta_16 != nullptr && half) || (track_max && max_bits != nullptr);
   if (track) ST_CUDA(cudaMemsetAsync(max_bits, 0, nb * sizeof(unsigned), s));
   ST_LAUNCH(gram_delta_kernel, dim3(min(cdiv((long)c * c, 256), 256), nb), 256, 0, s, gram, target,
             delta, track ? max_bits : nullptr, c, w, tile_loss, loss_stride, rs);

@@ -1,20 +1,17 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 600 python tools/tc32_check.py > gpurun_out/tc32_check.log 2>&1; tail -40 gpurun_out/tc32_check.log
-rm -f gpurun_out/parity_report.jsonl
-export ST_PARITY_REPORT=$PWD/gpurun_out/parity_report.jsonl
-timeout 1500 python -m pytest tests/test_gpu_parity_configs.py -m gpu -q --tb=line -k "tc32 and not cfg3 and not cfg4" 2>&1 | tail -30 > gpurun_out/pytest_configs.log
-tail -12 gpurun_out/pytest_configs.log
-cat gpurun_out/parity_report.jsonl
-for p in tc32; do
-timeout 600 python bench.py --precision $p --no-cpu-baseline --no-e2e --steps 3 --warmup 1 > gpurun_out/bench_$p.json 2> gpurun_out/bench_$p.err; tail -2 gpurun_out/bench_$p.err
-python - <<PY
+timeout 300 python tools/tc32_check.py 2>&1 | grep -v "features" | tail -12
+export ST_PARITY_REPORT=$PWD/gpurun_out/parity_tc32.jsonl; rm -f $ST_PARITY_REPORT
+timeout 600 python -m pytest tests/test_gpu_parity_configs.py tests/test_gpu_parity.py -m gpu -q --tb=line -k "tc32 and not cfg3" 2>&1 | tail -6
+python - <<'PY'
 import json
-try:
-    d = json.load(open('gpurun_out/bench_$p.json'))
-    print('$p: it/s %.2f  ms/step %.3f  launches %d' % (d['value'], d['ms_per_step'], d['gpu_launches']))
-    print({k: round(v['ms_per_step'], 3) for k, v in d['breakdown'].items()})
-except Exception as e:
-    print('bench parse failed', e)
+for l in open('gpurun_out/parity_tc32.jsonl'):
+    d = json.loads(l); print(d['case'], {k: (round(v, 7) if isinstance(v, float) else v) for k, v in d.items() if k in ('loss_rel', 'grad_l2rel', 'frac_gt_1e3', 'rms', 'max')})
 PY
+for env in "A=1" "ST_TC32_SIMT_GRAM=1"; do
+env $env timeout 200 python bench.py --precision tc32 --no-cpu-baseline --no-e2e --no-extra --steps 6 --warmup 2 2>/dev/null | python -c "
+import sys, json
+t = sys.stdin.read().strip()
+if not t: print('NO OUTPUT'); sys.exit()
+d = json.loads(t.splitlines()[-1]); print('$env tc32 it/s %.2f ms/step %.3f' % (d['value'], d['ms_per_step']), {k: round(v['ms_per_step'], 3) for k, v in d['breakdown'].items()})"
 done
