@@ -115,7 +115,8 @@ struct st_ctx {
   void* split_buf = nullptr; // ST_PREC_TC32: fp16 [hi | lo] copy of the convolution input in flight
   size_t split_cap = 0;      // elements (4 bytes each)
   float grad_scale = 1.f;    // ST_PREC_TC32: power of two applied to gradients before the fp16 split
-  bool tc32_simt_gram = false;   // ST_TC32_SIMT_GRAM=1: tc32 Gram matrices on the SIMT kernel
+  bool tc32_tc_gram = false;     // ST_TC32_TC_GRAM=1: tc32 Gram matrices on the tensor cores (see build_injection)
+  bool tc32_simt_style = false;  // ST_TC32_SIMT_STYLE=1: tc32 style GEMM on the SIMT kernel
   // per batch tile: Gram [C][C], its difference to the target (fp32 and the bf16 copy that is the
   // B operand of the tcgen05 style GEMM)
   float *gram = nullptr, *delta = nullptr, *part = nullptr;
@@ -409,8 +410,11 @@ int build_injection(st_ctx* ctx, const st_loss_spec& sp, const Dims& d, const Ba
           rc = ST_OK;
           bool gram_done = false;
           if constexpr (std::is_same<TA, float>::value) {
-            if (ctx->precision == ST_PREC_TC32 && gram_tc32_ok(ctx->tc, c) && !ctx->tc32_simt_gram) {
-              // tc32: the Gram contraction on the tensor cores from the [hi | lo] planes of F
+            if (ctx->precision == ST_PREC_TC32 && gram_tc32_ok(ctx->tc, c) && ctx->tc32_tc_gram) {
+              // opt-in (ST_TC32_TC_GRAM=1): the Gram contraction on the tensor cores from the [hi | lo]
+              // planes of F.  Twice as fast as the SIMT kernel, but G - G_style amplifies the ~1e-6 of
+              // accumulation-truncation bias its 32-step chains leave in G (gradient error 1.2e-3 ->
+              // 2.4e-3 at one 512^2 tile), so the exact double-accumulating SIMT kernel stays the default
               size_t cap = ctx->part_floats;
               rc = ensure(ctx, (void**)&ctx->part, &cap, gram_tc32_part_floats(nb, hf * wf, c), 4);
               ctx->part_floats = cap;
@@ -428,7 +432,7 @@ int build_injection(st_ctx* ctx, const st_loss_spec& sp, const Dims& d, const Ba
       }
       bool style_tc32 = false;
       if constexpr (std::is_same<TA, float>::value && std::is_same<T, float>::value)
-        style_tc32 = ctx->precision == ST_PREC_TC32 && !ctx->tc32_simt_gram && ctx->delta_16 != nullptr;
+        style_tc32 = ctx->precision == ST_PREC_TC32 && !ctx->tc32_simt_style && ctx->delta_16 != nullptr;
       if (rc == ST_OK && !on_tc)
         rc = gram_delta(ctx->gram, it->second, ctx->delta, nullptr, kHalf, ctx->delta_max,
                         ctx->eps_eff, c, nb, w, tile_loss, kStatStride, ctx->rs, s, style_tc32);
@@ -464,7 +468,7 @@ int build_injection(st_ctx* ctx, const st_loss_spec& sp, const Dims& d, const Ba
             // tc32: S = F sym(dG) on the tensor cores from the [hi | lo] planes (still in split_buf when
             // the Gram ran there; made here for the 512-channel layers whose Gram is the SIMT one)
             int per_tile = 0;
-            if (!gram_tc32_ok(ctx->tc, c))
+            if (!(gram_tc32_ok(ctx->tc, c) && ctx->tc32_tc_gram))
               rc = split_f32(f, ctx->split_buf, (size_t)nb * hf * wf, c, 1.f, s);
             if (rc == ST_OK)
               rc = ensure(ctx, (void**)&ctx->abs_partials, &ctx->abs_cap,
@@ -719,7 +723,8 @@ int st_create(int device, int precision, int n_layers, const st_layer_desc* laye
   st_ctx* ctx = new st_ctx();
   ctx->device = device, ctx->precision = precision, ctx->sm_count = prop.multiProcessorCount;
   ctx->esize = (precision == ST_PREC_FP32 || precision == ST_PREC_TC32) ? 4 : 2;
-  ctx->tc32_simt_gram = getenv("ST_TC32_SIMT_GRAM") != nullptr;
+  ctx->tc32_tc_gram = getenv("ST_TC32_TC_GRAM") != nullptr;
+  ctx->tc32_simt_style = getenv("ST_TC32_SIMT_STYLE") != nullptr;
   DeviceGuard guard(device);
   ctx->blobs.resize(n_layers + 1);
   ctx->blobs[0].c = 3;
