@@ -444,8 +444,18 @@ class TileEngine:
         uid = uid.to(self.device)
         dist.broadcast(uid, src=0, group=self.group)
         host = bytes(uid.cpu().numpy().tobytes())
-        _lib.call('st_comm_init', self.ctx, host, self.rank, self.world)
-        self._comm_ready = True
+        ok = torch.ones(1, dtype=torch.int32, device=self.device)
+        try:
+            _lib.call('st_comm_init', self.ctx, host, self.rank, self.world)
+        except _lib.StError as e:                 # e.g. no libnccl.so.2 in this process
+            ok.zero_()
+            err = e
+        # all ranks take the same path: the C-ABI collective only if every rank has a communicator
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)
+        self._comm_ready = bool(ok.item())
+        if not self._comm_ready and self.rank == 0:
+            print('note: st_comm_init unavailable on some rank (%s); the exchange step runs through '
+                  'torch.distributed instead' % (err if 'err' in locals() else 'another rank'))
 
     # ---- roll -----------------------------------------------------------------------------------
     def roll_features(self, feats, xy, jitter_scale=32):
