@@ -90,8 +90,7 @@ int tc_pack_split(TcContext& tc, TcWeights& w, const float* w_oihw_host, int cin
 int split_f32(const float* in, void* out_hi_lo, size_t pixels, int c, float scale, cudaStream_t s);
 int conv3x3_tc32(TcContext& tc, const TcWeights& w, const float* in, float* out, int nb, int h,
                  int wd, int cin, int cout, bool forward, const float* bias, const float* mask_act,
-                 const float* inj, float in_scale, const void* presplit, void* split_buf,
-                 void* split_out, float split_out_scale, cudaStream_t s);
+                 const float* inj, float in_scale, void* split_buf, cudaStream_t s);
 // Style GEMM of the split-operand mode: S_b = F_b * D_b in fp32 from the [hi | lo] planes of F and the
 // fp32 delta-Gram (split on the fly with a per-tile power-of-two scale), sum |S_b| as partial sums.
 int gemm_abs_tc32(TcContext& tc, const void* f_split, const float* delta, const unsigned* max_bits,

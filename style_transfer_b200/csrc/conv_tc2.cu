@@ -297,9 +297,6 @@ struct Tc2Args {
   const float* mask_f32;           // kEpiBwd32: fp32 activation whose sign is the ReLU mask, may be null
   const float* inj_f32;            // kEpiBwd32: fp32 injected gradient, may be null
   float* out_f32;                  // kEpiFwd32 / kEpiBwd32: fp32 NHWC output
-  __half* split_out;               // kEpiFwd32 / kEpiBwd32: also the [hi | lo] fp16 planes of the output
-                                   // times split_out_scale ([pixel][2 * cout]), for the next convolution
-  float split_out_scale;
   int resb_bytes;                  // RESB: bytes of the resident weight block (multiple of 1024)
   int tiles_x, tiles_y, tiles_n;   // pair tiles per batch tile: 8 columns x 32 rows x BN channels
   FastDiv div_x, div_y, div_n;     // by tiles_x / tiles_y / tiles_n (decode_tile runs once per tile
@@ -763,35 +760,6 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constan
 #pragma unroll
             for (int i = 0; i < 8; ++i)
               dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-            if constexpr (EPI != kEpiAbs32) {
-              if (a.split_out != nullptr) {
-                // the operand of the convolution that consumes this blob, split here instead of by a
-                // separate pass over the fp32 output (same arithmetic as split_f32_kernel)
-                uint32_t hw[16], lw[16];
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                  const float a0 = v[2 * i] * a.split_out_scale, a1 = v[2 * i + 1] * a.split_out_scale;
-                  const __half2 h = __floats2half2_rn(fminf(fmaxf(a0, -65504.f), 65504.f),
-                                                      fminf(fmaxf(a1, -65504.f), 65504.f));
-                  const float2 hf = __half22float2(h);
-                  const __half2 l = __floats2half2_rn(fminf(fmaxf(a0 - hf.x, -65504.f), 65504.f),
-                                                      fminf(fmaxf(a1 - hf.y, -65504.f), 65504.f));
-                  hw[i] = *reinterpret_cast<const uint32_t*>(&h);
-                  lw[i] = *reinterpret_cast<const uint32_t*>(&l);
-                }
-                // pixel index = eofs / cout (eofs = pixel * cout + channel offset of this chunk)
-                const size_t chan = (size_t)n_tile * BN + (size_t)cc * 32;
-                const size_t pixel = (cur.gofs - (size_t)n_tile * BN) / (size_t)a.cout;
-                __half* sp = a.split_out + pixel * (size_t)(2 * a.cout) + chan;
-                uint4* dh = reinterpret_cast<uint4*>(sp);
-                uint4* dl = reinterpret_cast<uint4*>(sp + a.cout);
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                  dh[i] = make_uint4(hw[4 * i], hw[4 * i + 1], hw[4 * i + 2], hw[4 * i + 3]);
-                  dl[i] = make_uint4(lw[4 * i], lw[4 * i + 1], lw[4 * i + 2], lw[4 * i + 3]);
-                }
-              }
-            }
           }
         }
         continue;
@@ -1259,35 +1227,26 @@ int tc_pack_split(TcContext& tc, TcWeights& w, const float* w_host, int cin, int
 // out = epilogue(conv3x3(in)) on fp32 NHWC tensors through the split-operand tensor-core kernel:
 //   forward : out = max(acc + bias, 0)
 //   backward: out = (mask_act > 0 ? acc : 0) + inj          (mask_act / inj fp32, may be null)
-// The [hi | lo] fp16 copy of `in * in_scale` is taken from `presplit` when the producer of `in` already
-// wrote it (see split_out), else made here into `split_buf` (2 * nb*h*w*cin fp16 elements).
-// split_out (may be null): receives the [hi | lo] copy of `out * split_out_scale` for the next
-// convolution; must not alias the buffer this call reads.
+// `split_buf` (2 * nb*h*w*cin fp16 elements) receives the [hi | lo] copy of `in * in_scale`.
 int conv3x3_tc32(TcContext& tc, const TcWeights& w, const float* in, float* out, int nb, int h,
                  int wd, int cin, int cout, bool forward, const float* bias, const float* mask_act,
-                 const float* inj, float in_scale, const void* presplit, void* split_buf,
-                 void* split_out, float split_out_scale, cudaStream_t s) {
-  const void* a_in = presplit;
-  if (a_in == nullptr) {
-    int rc = split_f32(in, split_buf, (size_t)nb * h * wd, cin, in_scale, s);
-    if (rc != ST_OK) return rc;
-    a_in = split_buf;
-  }
+                 const float* inj, float in_scale, void* split_buf, cudaStream_t s) {
+  int rc = split_f32(in, split_buf, (size_t)nb * h * wd, cin, in_scale, s);
+  if (rc != ST_OK) return rc;
   Tc2Args a{};
   a.nb = nb, a.h = h, a.w = wd, a.cin = 3 * cin, a.cout = cout;
   a.cin_map = 2 * cin, a.a_wrap = 2 * (cin / 64);
   a.in_half = 1, a.out_half = 0;
   a.out_scale = 1.f / (w.split_scale * in_scale);
   a.bias = bias, a.mask_f32 = mask_act, a.inj_f32 = inj, a.out_f32 = out;
-  a.split_out = static_cast<__half*>(split_out), a.split_out_scale = split_out_scale;
   // BN <= 128: the epilogue keeps the running sum of the chains in registers (BN / 2 per thread)
   const int bn = std::min(choose_bn(tc, nb, h, wd, cout), 128);
   if (forward) {
-    if (bn == 128) return launch2r<128, 9, kEpiFwd32, false>(tc, a_in, w.fwd32, cout, nullptr, nullptr, a, s);
-    return launch2r<64, 9, kEpiFwd32, false>(tc, a_in, w.fwd32, cout, nullptr, nullptr, a, s);
+    if (bn == 128) return launch2r<128, 9, kEpiFwd32, false>(tc, split_buf, w.fwd32, cout, nullptr, nullptr, a, s);
+    return launch2r<64, 9, kEpiFwd32, false>(tc, split_buf, w.fwd32, cout, nullptr, nullptr, a, s);
   }
-  if (bn == 128) return launch2r<128, 9, kEpiBwd32, false>(tc, a_in, w.bwd32, cout, nullptr, nullptr, a, s);
-  return launch2r<64, 9, kEpiBwd32, false>(tc, a_in, w.bwd32, cout, nullptr, nullptr, a, s);
+  if (bn == 128) return launch2r<128, 9, kEpiBwd32, false>(tc, split_buf, w.bwd32, cout, nullptr, nullptr, a, s);
+  return launch2r<64, 9, kEpiBwd32, false>(tc, split_buf, w.bwd32, cout, nullptr, nullptr, a, s);
 }
 
 // ---- style GEMM of the split-operand mode ------------------------------------------------------------

@@ -112,12 +112,8 @@ struct st_ctx {
   void* gbuf[2] = {nullptr, nullptr};
   void* sbuf = nullptr;
   size_t gcap = 0;           // elements of gbuf[i] / sbuf
-  // ST_PREC_TC32: fp16 [hi | lo] copies of convolution inputs.  split_buf: made by split_f32 (also the
-  // Gram / style-GEMM operand); split_pp[2]: written by a convolution's epilogue for the convolution
-  // that consumes its output (ping-pong: one is read while the other is written)
-  void* split_buf = nullptr;
-  void* split_pp[2] = {nullptr, nullptr};
-  size_t split_cap = 0, split_pp_cap[2] = {0, 0};      // elements (4 bytes each)
+  void* split_buf = nullptr; // ST_PREC_TC32: fp16 [hi | lo] copy of the convolution input in flight
+  size_t split_cap = 0;      // elements (4 bytes each)
   float grad_scale = 1.f;    // ST_PREC_TC32: power of two applied to gradients before the fp16 split
   bool tc32_tc_gram = false;     // ST_TC32_TC_GRAM=1: tc32 Gram matrices on the tensor cores (see build_injection)
   bool tc32_simt_style = false;  // ST_TC32_SIMT_STYLE=1: tc32 style GEMM on the SIMT kernel
@@ -225,8 +221,6 @@ int reserve_for(st_ctx* ctx, const Dims& d, int last_layer, int nb) {
   }
   if (ctx->precision == ST_PREC_TC32) {
     int rc = ensure(ctx, &ctx->split_buf, &ctx->split_cap, std::max(gmax, ctx->gcap), 4);
-    for (int k = 0; k < 2 && rc == ST_OK; ++k)
-      rc = ensure(ctx, &ctx->split_pp[k], &ctx->split_pp_cap[k], std::max(gmax, ctx->gcap), 4);
     if (rc != ST_OK) return rc;
   }
   return ST_OK;
@@ -253,7 +247,6 @@ template <typename T>
 int forward(st_ctx* ctx, const ImageBatch& view, const Dims& d, int last_layer,
             const std::vector<char>& need_full, bool for_backward, cudaStream_t s) {
   const int nb = view.nb;
-  int split_blob = -1, split_k = 0;      // tc32: blob whose [hi | lo] copy sits in split_pp[split_k]
   for (LayerRt& l : ctx->layers) l.pool_mask_valid = false;
   for (BlobRt& b : ctx->blobs) b.bits_valid = false;
   for (int i = 0; i <= last_layer; ++i) {
@@ -317,17 +310,10 @@ int forward(st_ctx* ctx, const ImageBatch& view, const Dims& d, int last_layer,
             set_error("invalid: ST_PREC_FP16 has no SIMT convolution (channels must be multiples of 64)");
             rc = ST_ERR_INVALID;
           } else if constexpr (std::is_same<T, float>::value) {
-            if (ctx->precision == ST_PREC_TC32 && l.tc.fwd32 != nullptr) {
-              // the split copy of the input comes from the producing convolution's epilogue when
-              // that was the previous layer; this one writes its own for the next convolution
-              const void* presplit = split_blob == l.bottom ? ctx->split_pp[split_k] : nullptr;
-              const bool next_conv = i + 1 <= last_layer && ctx->layers[i + 1].kind == ST_CONV3X3 &&
-                                     ctx->layers[i + 1].bottom == l.top && ctx->layers[i + 1].tc.fwd32;
-              void* split_out = next_conv ? ctx->split_pp[split_k ^ 1] : nullptr;
+            if (ctx->precision == ST_PREC_TC32 && l.tc.fwd32 != nullptr)
               rc = conv3x3_tc32(ctx->tc, l.tc, in, out, nb, hb, wb, l.cin, l.cout, true, l.bias,
-                                nullptr, nullptr, 1.f, presplit, ctx->split_buf, split_out, 1.f, s);
-              split_blob = next_conv ? l.top : -1, split_k ^= 1;
-            } else
+                                nullptr, nullptr, 1.f, ctx->split_buf, s);
+            else
               rc = conv3x3_simt<T>(in, l.w_fwd, l.bias, out, nb, hb, wb, l.cin, l.cout, true, nullptr,
                                    nullptr, s);
           } else {
@@ -529,10 +515,7 @@ int backward(st_ctx* ctx, const Dims& d, int nb, int deepest_blob, const std::ve
              float* grad, long batch_stride, long plane, long rstride, cudaStream_t s) {
   int cur = deepest_blob, pp = 0;
   const T* g = static_cast<const T*>(ctx->blobs[cur].inj);
-  bool g_presplit = false;       // tc32: the [hi | lo] copy of g sits in split_pp[split_k]
-  int split_k = 0;
   while (true) {
-    bool tc32_conv = false;
     const LayerRt& l = ctx->layers[ctx->blobs[cur].producer];
     const int b = l.bottom;
     const int hb = d.h[b], wb = d.w[b];
@@ -581,17 +564,10 @@ int backward(st_ctx* ctx, const Dims& d, int nb, int deepest_blob, const std::ve
       } else {
         ST_REQUIRE(inj_scale == nullptr, "deferred injection scale needs the tensor-core convolution");
         if constexpr (std::is_same<T, float>::value && std::is_same<TA, float>::value) {
-          if (ctx->precision == ST_PREC_TC32 && l.tc.bwd32 != nullptr) {
-            const void* presplit = g_presplit ? ctx->split_pp[split_k] : nullptr;
-            // the consumer of `out` is the backward convolution of the layer that produced blob b
-            const LayerRt& nl = ctx->layers[ctx->blobs[b].producer];
-            const bool next_conv = nl.kind == ST_CONV3X3 && nl.bottom != 0 && nl.tc.bwd32 != nullptr;
+          if (ctx->precision == ST_PREC_TC32 && l.tc.bwd32 != nullptr)
             rc = conv3x3_tc32(ctx->tc, l.tc, g, out, nb, hb, wb, l.cout, l.cin, false, nullptr, mask,
-                              inj, ctx->grad_scale, presplit, ctx->split_buf,
-                              next_conv ? ctx->split_pp[split_k ^ 1] : nullptr, ctx->grad_scale, s);
-            g_presplit = next_conv, split_k ^= 1;
-            tc32_conv = true;
-          } else
+                              inj, ctx->grad_scale, ctx->split_buf, s);
+          else
             rc = conv3x3_simt<T>(g, l.w_bwd, nullptr, out, nb, hb, wb, l.cout, l.cin, false, mask, inj,
                                  s);
         } else if constexpr (std::is_same<TA, T>::value) {
@@ -610,7 +586,6 @@ int backward(st_ctx* ctx, const Dims& d, int nb, int deepest_blob, const std::ve
                            l.kind == ST_POOL_MAX, bb.relu, inj, inj_scale, s);
     }
     if (rc != ST_OK) return rc;
-    if (!tc32_conv) g_presplit = false;
     g = out, pp ^= 1, cur = b;
   }
 }
@@ -824,7 +799,7 @@ int st_destroy(st_ctx* ctx) {
     tc_free_weights(l.tc);
   }
   for (BlobRt& b : ctx->blobs) cudaFree(b.act), cudaFree(b.inj), cudaFree(b.inj_scale), cudaFree(b.bits);
-  cudaFree(ctx->gbuf[0]), cudaFree(ctx->gbuf[1]), cudaFree(ctx->sbuf), cudaFree(ctx->split_buf), cudaFree(ctx->split_pp[0]), cudaFree(ctx->split_pp[1]);
+  cudaFree(ctx->gbuf[0]), cudaFree(ctx->gbuf[1]), cudaFree(ctx->sbuf), cudaFree(ctx->split_buf);
   cudaFree(ctx->gram), cudaFree(ctx->delta), cudaFree(ctx->part), cudaFree(ctx->scalars);
   cudaFree(ctx->delta_16), cudaFree(ctx->abs_partials), cudaFree(ctx->eps_eff);
   cudaFree(ctx->delta_max);
