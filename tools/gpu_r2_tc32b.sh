@@ -8,7 +8,7 @@ import json
 for l in open('gpurun_out/parity_tc32.jsonl'):
     d = json.loads(l); print(d['case'], {k: (round(v, 7) if isinstance(v, float) else v) for k, v in d.items() if k in ('loss_rel', 'grad_l2rel', 'frac_gt_1e3', 'rms', 'max')})
 PY
-for env in "A=1" "ST_TC32_TC_GRAM=1"; do
+for env in "A=1"; do
 env $env timeout 200 python bench.py --precision tc32 --no-cpu-baseline --no-e2e --no-extra --steps 6 --warmup 2 2>/dev/null | python -c "
 import sys, json
 t = sys.stdin.read().strip()
