@@ -370,8 +370,8 @@ class TileEngine:
         """The next ``eval_sc_grad`` takes its image from ``host_img`` (pinned f32 [3,H,W], the
         layout of ``self.img``) instead of the resident copy -- the situation of a caller that owns
         the parameters on the host, as the reference's master process does.  One GPU: the rows the
-        first half of the tiles read are uploaded first and the second half streams in while those
-        tiles are being evaluated.  Several GPUs: every rank uploads only its 1/world slab of rows
+        first tile row reads are uploaded first and the rest streams in while those tiles are being
+        evaluated.  Several GPUs: every rank uploads only its 1/world slab of rows
         through its own PCIe link and the slabs are all-gathered over NVLink."""
         self._host_img = host_img
 
@@ -408,7 +408,9 @@ class TileEngine:
         else:
             nty, ntx, th, _, _, _ = sharding.tile_grid(H, W, tile_size)
             n_local = len(range(self.rank, nty * ntx, self.world))
-            rows_a = nty // 2 if self.world == 1 else 0
+            # the first phase is ONE tile row when there are three or more (its upload is the exposed
+            # part; the rest streams in behind the evaluation of that row), else half of the rows
+            rows_a = (1 if nty >= 3 else nty // 2) if self.world == 1 else 0
             with torch.cuda.stream(cs):
                 if rows_a > 0:
                     # rolled rows [0, rows_a * th) = un-rolled rows starting at (-ry) mod H
