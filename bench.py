@@ -595,9 +595,10 @@ def run_engine(a):
             w.after_output = fetch_results
 
         def e2e_step():
-            # the host consumes the PREVIOUS step's results (they are complete in pinned memory once
-            # that step's output stream is done) before it enqueues this step: one step in flight
-            if pending:
+            # before it enqueues step k the host consumes the results of step k - 2 (complete in
+            # pinned memory once that step's output stream is done): the device always has the next
+            # step queued, every step's results are read, at most two steps are in flight
+            if len(pending) >= 2:
                 pending.pop(0).synchronize()
             # H2D: this step's image (every rank its 1/world slab of rows through its own PCIe link,
             # NVLink all-gather; one GPU: two halves, the second streaming in behind the first tiles)
@@ -623,8 +624,8 @@ def run_engine(a):
                'boundary': 'pinned host f32[3,H,W] image in (TileEngine.stage_host_image), one pass of '
                            'the loop body (StyleTransfer.step + statistics + picture), uint8 RGB '
                            'picture + loss + update-size / TV statistics back to pinned host memory, '
-                           'every step; the host reads step i\'s results while step i + 1 runs (one step '
-                           'in flight; the timed region ends with a device-wide synchronisation); '
+                           'every step; the host reads step k - 2\'s results before it enqueues step k (at most '
+                           'two steps in flight; the timed region ends with a device-wide synchronisation); '
                            'N > 1: every rank uploads its 1/N slab of rows through its own PCIe link, '
                            'the slabs are all-gathered over NCCL, results leave from rank 0 (the master)'}
 
