@@ -58,10 +58,14 @@ enum st_precision {
   ST_PREC_FP16 = 2,                 /* tensor cores with fp16 forward activations / weights (11-bit
                                        significand, range 6e-5 .. 65504) and bf16 gradients: same
                                        speed as ST_PREC_BF16, ~4x smaller gradient error          */
-  ST_PREC_TC32 = 3                  /* fp32 storage, convolutions on the tensor cores with SPLIT fp16
-                                       operands (x = hi + lo, three MMAs per product, fp32
-                                       accumulation): the reference's fp32 arithmetic to ~1e-6 per
-                                       product at a third of the fp16 mode's tensor throughput    */
+  ST_PREC_TC32 = 3                  /* fp32 storage; the 3x3 convolutions and the style GEMM on the
+                                       tensor cores with SPLIT fp16 operands (x = hi + lo, three MMAs
+                                       per product) and CHAINED accumulation (a fresh TMEM buffer per
+                                       12 MMAs, chains summed in fp32 registers: the tensor core
+                                       truncates when it accumulates): the reference's fp32 results
+                                       -- features within 3e-6 of ST_PREC_FP32, gradients within the
+                                       same distance of the CPU oracle -- at a third of the fp16
+                                       mode's tensor throughput                                   */
 };
 
 enum st_layer_kind { ST_CONV3X3 = 0, ST_POOL_MAX = 1, ST_POOL_AVE = 2 };

@@ -420,3 +420,34 @@ def test_jitter_copy_formulation_equals_in_place_rolls():
             return loss, on.roll2_(grad.copy(), -xy)
         avg_b, _ = tr.optimizer.update(opfunc)
     assert np.array_equal(avg_a, avg_b)
+
+
+def test_split_operand_arithmetic_model():
+    """The arithmetic ST_PREC_TC32 relies on, modelled in numpy: x = hi + lo with hi = fp16(x),
+    lo = fp16(x - hi) carries ~22 significant bits, and a*w ~= a_hi*w_hi + a_lo*w_hi + a_hi*w_lo
+    (three fp16 x fp16 products, exact in fp32, summed in fp32) is within 2^-20 of the fp32 product --
+    against 2^-10 for single fp16 operands.  The weights are pre-scaled by a power of two so that their
+    lo parts stay out of the fp16 subnormals (tc_pack_split); the same here."""
+    rs = np.random.RandomState(0)
+    a = np.float32(rs.uniform(0, 300, 20000))                  # post-ReLU activations
+    w = np.float32(rs.randn(20000) * 0.02)                     # He-normal-sized weights
+    scale = np.float32(2.0 ** (13 - np.frexp(np.abs(w).max())[1]))
+    ws = w * scale
+
+    def split(x):
+        hi = np.float16(x)
+        return hi, np.float16(x - np.float32(hi))
+    a_hi, a_lo = split(a)
+    w_hi, w_lo = split(ws)
+    f = np.float32
+    three = (f(a_hi) * f(w_hi) + f(a_lo) * f(w_hi) + f(a_hi) * f(w_lo)) / scale
+    exact = np.float64(a) * np.float64(w)
+    single = np.float64(f(a_hi)) * np.float64(f(np.float16(ws))) / np.float64(scale)
+    err3 = np.abs(three - exact).max() / np.abs(exact).max()
+    err1 = np.abs(single - exact).max() / np.abs(exact).max()
+    assert err3 < 2.0 ** -20, err3
+    assert err1 > 2.0 ** -13 and err3 < err1 / 200
+    # the split is exact to 2^-21 relative for values in fp16's normal range
+    big = np.abs(a) > 1e-2
+    rel = np.abs((f(a_hi) + f(a_lo)) - a)[big] / np.abs(a)[big]
+    assert rel.max() < 2.0 ** -21
