@@ -420,6 +420,10 @@ class Workload:
                 done = torch.cuda.Event()
                 done.record(self.out_stream)
             self.out_done.append(done)
+            if avg.data_ptr() == self.eng.img.data_ptr():
+                # L-BFGS returns the parameters themselves (no averaged copy): the next step updates
+                # them in place, so the output step must have read them first
+                main.wait_event(done)
         return avg, loss
 
     def drain(self):
