@@ -453,3 +453,39 @@ def test_split_operand_arithmetic_model():
     big = np.abs(a) >= 1.0
     assert (err[big] / np.abs(a)[big]).max() < 2.0 ** -21
     assert err[~big].max() <= 2.0 ** -24
+
+
+@pytest.mark.parametrize('H,tile,ry', [(2048, 512, 0), (2048, 512, -424), (2048, 512, 808), (1448, 512, 96),
+                                      (1024, 512, -312), (512, 512, 40)])
+def test_host_image_upload_phases_cover_every_row_once(H, tile, ry):
+    """TileEngine.stage_host_image on one GPU uploads the image in two phases -- first the rows the
+    first tile row reads (a circular range in the un-rolled frame: rolled row y is image row
+    (y - roll) mod H), then the rest.  Index logic only (CPU tensors): the two phases together
+    write every row exactly once, and phase A is exactly what the first batch of tiles reads."""
+    import torch
+    from style_transfer_b200 import sharding
+    from style_transfer_b200.engine import TileEngine
+    eng = object.__new__(TileEngine)                       # no device needed for _copy_rows
+    W = 8
+    host = torch.arange(3 * H * W, dtype=torch.float32).reshape(3, H, W)
+    nty, _, th, _, _, _ = sharding.tile_grid(H, H, tile)
+    rows_a = 1 if nty >= 3 else nty // 2                   # engine._eval_tiles_from_host
+    img = torch.full((3, H, W), -1.0)
+    count = torch.zeros(H, dtype=torch.int64)
+
+    def copy(start, n):
+        before = img.clone()
+        TileEngine._copy_rows(eng, host, img, start, n)
+        changed = (img != before).any(dim=2).any(dim=0)
+        count.add_(changed.to(torch.int64))
+        return changed
+    if rows_a > 0:
+        a = copy((-ry) % H, rows_a * th)
+        # rolled rows [0, rows_a * th) are image rows (y - ry) mod H
+        want = torch.zeros(H, dtype=torch.bool)
+        want[[(y - ry) % H for y in range(rows_a * th)]] = True
+        assert torch.equal(a, want)
+        copy((rows_a * th - ry) % H, H - rows_a * th)
+    else:
+        copy(0, H)
+    assert torch.equal(img, host) and int(count.min()) == 1 and int(count.max()) == 1
