@@ -207,9 +207,6 @@ ST_API int st_unpack_regularize(const float* packed_all_dev, const float* img_de
 ST_API int st_adam_step(float* params, const float* grad, float* g1, float* g2, float* p1, float* avg_out,
                  size_t n, float step_size, float b1, float b2, float bp1, float g1_corr,
                  float g2_corr, float p1_corr, st_stream stream);
-/* LBFGSOptimizer.inv_hv :105-121: two-loop recursion over m (<= 16) curvature pairs.  s_dev/y_dev
- * are HOST arrays of m device pointers (oldest first), sy_host the stored s.y products; p_dev
- * receives H*grad.  scratch_dev: >= 64 doubles. */
 /* ---- per-iteration output step (style_transfer.py:808-821, :378-386) ------------------------------
  * st_iter_stats: the two statistics of StyleTransfer.transfer in one pass over the averaged iterate:
  *   stats_dev[0] = sum |avg - old|                      (update_size = stats[0] / (3*H*W), :809)
@@ -236,8 +233,8 @@ ST_API int st_output_step(const float* avg_dev, float* old_dev, int H, int W, co
  * shrinking) and float64 accumulation without fused multiply-add.  method: 0 = Lanczos, 1 = bilinear.
  * tmp_dev: scratch of channels*h*out_w floats (unused when out_w == w).  Coefficient tables are built
  * on the host per call.  Pinned: oracle.numeric.resize == PIL == the reference's num_utils.resize bit
- * for bit (CPU), and this kernel == the oracle bit for bit (B200).  The command line keeps resizing
- * through PIL unless ST_DEVICE_RESIZE=1. */
+ * for bit (CPU), and this kernel == the oracle bit for bit (B200).  The bundled command line uses it
+ * for the scale change (ST_HOST_RESIZE=1: through PIL on the host, as the reference). */
 ST_API int st_resize_f32(const float* in_dev, int channels, int h, int w, int out_h, int out_w,
                          int method, float* out_dev, float* tmp_dev, st_stream stream);
 /* The coefficient table st_resize_f32 uses for one axis (host only, no device needed): *ksize weights
@@ -246,6 +243,10 @@ ST_API int st_resize_f32(const float* in_dev, int channels, int h, int w, int ou
 ST_API int st_resample_coeffs(int in_size, int out_size, int method, int* ksize, int* bounds_out,
                               double* kk_out);
 
+/* LBFGSOptimizer.inv_hv :105-121 for a binding that keeps the curvature pairs as host-side lists like
+ * the reference: two-loop recursion over m (<= 16) pairs.  s_dev / y_dev are HOST arrays of m device
+ * pointers (oldest first), sy_host the stored s.y products; p_dev receives H*grad.  scratch_dev:
+ * >= 64 doubles. */
 ST_API int st_lbfgs_inv_hv(const float* grad_dev, size_t n, int m, const float* const* s_dev,
                     const float* const* y_dev, const double* sy_host, float* p_dev,
                     double* scratch_dev, st_stream stream);
