@@ -489,3 +489,28 @@ def test_host_image_upload_phases_cover_every_row_once(H, tile, ry):
     else:
         copy(0, H)
     assert torch.equal(img, host) and int(count.min()) == 1 and int(count.max()) == 1
+
+
+@pytest.mark.parametrize('H,W,tile,world', [(75, 52, 40, 3), (2048, 2048, 512, 8), (724, 724, 512, 3),
+                                            (96, 128, 32, 5)])
+def test_exchange_chunks_unpack_for_any_world(H, W, tile, world):
+    """The chunk layout of the exchange step (tiles padded to 4 floats + the loss tail) for world
+    sizes that do not divide the tile count and ragged grids: every rank fills its slots, the
+    rank-major concatenation (= the all-gather result) un-packs to the directly assembled gradient
+    and the losses add up."""
+    from style_transfer_b200 import sharding
+    rs = np.random.RandomState(H + world)
+    full = rs.randn(3, H, W).astype(np.float32)            # the gradient in the rolled frame
+    roll_y, roll_x = 8, -16
+    nfl = sharding.packed_floats(H, W, tile, world)
+    chunks = np.zeros((world, nfl), np.float32)
+    losses = []
+    for rank in range(world):
+        tiles = sharding.tiles_view(chunks[rank], H, W, tile, world)
+        for slot, (sy, sx, ey, ex) in sharding.local_tiles(H, W, tile, rank, world):
+            tiles[slot, :, :ey - sy, :ex - sx] = full[:, sy:ey, sx:ex]
+        losses.append(float(rank) + 0.25)
+        sharding.loss_view(chunks[rank])[0] = losses[-1]
+    grad, loss = sharding.unpack_numpy(chunks, H, W, tile, roll_y, roll_x)
+    assert np.array_equal(grad, np.roll(full, (-roll_y, -roll_x), axis=(1, 2)))
+    assert loss == sum(losses)
